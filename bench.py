@@ -1,0 +1,471 @@
+#!/usr/bin/env python3
+"""bench.py — the gams hot path on B200: GC-wave Gbp/s (headline) and rg overlap counts/s.
+
+One "step" = one pass of the hot path over one batch of synthetic input:
+  wave  : Kernel A (sequence bytes -> per-window GC) + Kernel B (z-score signals) over a human-scale
+          synthetic genome (3.1 Gbp, 24 chromosomes, `gen --piece 500000` ctgs, wave 100/10, lag 100,
+          threshold 3, influence 1) resident in HBM  -> `value` (Gbp/s);
+          the same through the host C-ABI call gams_cuda_wave_batch with pinned HOST buffers, H2D of the
+          sequence and D2H of gc+signal inside the timed region                      -> `e2e`.
+  count : batched `locate --count`: 1e8 query ranges against 1e8 SNP intervals on the same ctg layout,
+          device-resident and end-to-end, reported under "overlap" in the same JSON line.
+
+Multi-GPU: one process per GPU (torchrun), ctg-sharded, no data-path collective; torch.distributed is
+used only for the barrier and the max-over-ranks of the device time.  scaling "weak": every rank
+processes its own 3.1 Gbp genome (a cohort of N genomes); --scaling strong splits one genome by ctg.
+
+`--impl reference` times the reference's CPU algorithm (the oracle port: the reference is Rust and
+cannot be built in this image) on the box's host cores on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+SIZE, STEP, LAG, THRESHOLD, INFLUENCE = 100, 10, 100, 3.0, 1.0
+PIECE = 500_000
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--bases", type=float, default=3.1e9, help="bases per genome (per rank under weak scaling)")
+    ap.add_argument("--queries", type=float, default=1e8, help="overlap queries per genome")
+    ap.add_argument("--intervals", type=float, default=1e8, help="rg intervals per genome")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--influence", type=float, default=INFLUENCE)
+    ap.add_argument("--skip-count", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------ helpers
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)", d
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)", {}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])), mx.append(float(r[2]))
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def layout(n_bases: int):
+    from gams_b200 import synth
+    seq_off, ctgs = synth.ctg_layout(synth.human_like_lengths(n_bases), PIECE)
+    return seq_off, ctgs
+
+
+def pinned(nbytes: int, L):
+    p = L.gams_cuda_host_alloc(max(int(nbytes), 1))
+    if not p:
+        raise MemoryError("gams_cuda_host_alloc failed")
+    return p
+
+
+def as_np(ptr, n, dtype):
+    return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(np.ctypeslib.as_ctypes_type(dtype))), shape=(int(n),))
+
+
+# ------------------------------------------------------------------------------- reference (CPU) arm
+def cpu_wave_rate(seq_host: np.ndarray, seq_off: np.ndarray, threads: int, target_s: float, influence: float):
+    """Oracle (faithful port of wave.rs:138-155) on a bounded sample of ctgs → (Gbp/s, sample description)."""
+    from oracle import oracle as orc
+    n_ctg = seq_off.size - 1
+    cal = min(n_ctg, max(threads, 1))
+    sub_off = (seq_off[:cal + 1] - seq_off[0]).astype(np.uint64)
+    t0 = time.perf_counter()
+    orc.wave_batch(seq_host, sub_off, SIZE, STEP, LAG, THRESHOLD, influence, threads=threads)
+    dt = time.perf_counter() - t0
+    k = int(min(n_ctg, max(cal, cal * target_s / max(dt, 1e-3))))
+    k = max(threads, (k // max(threads, 1)) * max(threads, 1)) if k >= threads else k
+    k = min(k, n_ctg)
+    sub_off = (seq_off[:k + 1] - seq_off[0]).astype(np.uint64)
+    t0 = time.perf_counter()
+    orc.wave_batch(seq_host, sub_off, SIZE, STEP, LAG, THRESHOLD, influence, threads=threads)
+    dt = time.perf_counter() - t0
+    bases = int(sub_off[-1])
+    return bases / dt / 1e9, f"first {k} ctgs ({bases / 1e6:.1f} Mbp) of the workload, wave {SIZE}/{STEP} lag {LAG}, {dt:.1f} s wall"
+
+
+def run_reference(args, rank):
+    """bench.py --impl reference: the reference's CPU path (oracle port) with all host threads."""
+    if rank != 0:
+        return
+    from gams_b200 import synth
+    from oracle import oracle as orc
+    orc.lib()
+    cores = os.cpu_count() or 1
+    seq_off, _ = layout(int(args.bases))
+    # bounded sample: enough ctgs for a few seconds per step, generated on the host
+    n_cal = min(seq_off.size - 1, cores)
+    g = synth.genome(int(seq_off[n_cal]), seed=20240613)
+    rate, _ = cpu_wave_rate(g, seq_off[:n_cal + 1], cores, 1.0, args.influence)
+    per_step_s = min(6.0, 150.0 / max(args.steps + args.warmup, 1))
+    k = int(min(seq_off.size - 1, max(n_cal, rate * 1e9 * per_step_s / PIECE), max(n_cal, 600e6 / PIECE)))  # <= 600 Mbp
+    g = synth.genome(int(seq_off[k]), seed=20240613)
+    sub_off = seq_off[:k + 1].astype(np.uint64)
+    for _ in range(args.warmup):
+        orc.wave_batch(g, sub_off, SIZE, STEP, LAG, THRESHOLD, args.influence, threads=cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc.wave_batch(g, sub_off, SIZE, STEP, LAG, THRESHOLD, args.influence, threads=cores)
+    dt = time.perf_counter() - t0
+    bases = int(sub_off[-1])
+    val = bases * args.steps / dt / 1e9
+    sample = f"{k} ctgs ({bases / 1e6:.1f} Mbp) per step of the {args.bases / 1e9:.2f} Gbp workload"
+    line = {
+        "impl": "reference", "metric": "gc_wave_throughput", "value": val, "unit": "Gbp/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "u8->u32 counts, f32 statistics", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": val, "unit": "Gbp/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference is Rust (no cargo in this image): timed the faithful C port oracle/gams_oracle.c, "
+                "one worker per ctg over all host threads (the reference's --parallel model), inputs in memory",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    return {"workload": f"human-scale synthetic genome ({args.bases / 1e9:.2f} Gbp, 24 chromosomes, gen --piece {PIECE}) "
+                        f"GC-wave --size {SIZE} --step {STEP} --lag {LAG} --threshold {THRESHOLD} --influence {args.influence}",
+            "baseline_config": "configs[3]", "size": SIZE, "step": STEP, "lag": LAG, "threshold": THRESHOLD,
+            "influence": args.influence, "piece": PIECE, "bases_per_genome": int(args.bases),
+            "l2": "inputs larger than L2 (3.1 GB sequence + 1.55 GB outputs per step vs 126 MB L2)",
+            "parallelism": f"ctg-sharded x{args.gpus}, {args.scaling} scaling, no collective"}
+
+
+# ------------------------------------------------------------------------------------------- our arm
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from gams_b200 import _lib, api, synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; gams_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    L = _lib.load()
+    ctx = api.Context([local])
+    hbm_peak, peak_src, peaks_json = peaks()
+
+    # ---- workload: this rank's ctgs ------------------------------------------------------------
+    g_off, _ = layout(int(args.bases))
+    if args.scaling == "strong" and world > 1:
+        part = api.partition(g_off, world)
+        seq_off = (g_off[part[rank]:part[rank + 1] + 1] - g_off[part[rank]]).astype(np.uint64)
+    else:
+        seq_off = g_off
+    n_ctg = seq_off.size - 1
+    plan = api.WavePlan(ctx, seq_off, SIZE, STEP, LAG)
+    n_bases, n_win = plan.total_bases, plan.total_windows
+    d_seq = synth.genome_torch(n_bases, seed=20240613 + rank, device=dev, capacity=plan.seq_capacity)
+    d_gc = torch.empty(n_win, dtype=torch.float32, device=dev)
+    d_sig = torch.empty(n_win, dtype=torch.int8, device=dev)
+    d_filt = torch.empty(n_win, dtype=torch.float32, device=dev) if args.influence != 1.0 else None
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        plan.gc(stream, d_seq, d_gc)
+        plan.signal(stream, d_gc, THRESHOLD, args.influence, d_sig, d_filt)
+
+    for _ in range(args.warmup):
+        step()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    l0 = plan.launches
+    barrier()
+    with ClockSampler(local) as clk:
+        t_start = torch.cuda.Event(enable_timing=True)
+        t_end = torch.cuda.Event(enable_timing=True)
+        t_start.record()
+        for k in range(args.steps):
+            ev[k][0].record()
+            plan.gc(stream, d_seq, d_gc)
+            ev[k][1].record()
+            plan.signal(stream, d_gc, THRESHOLD, args.influence, d_sig, d_filt)
+            ev[k][2].record()
+        t_end.record()
+        barrier()
+    launches = plan.launches - l0
+    ms_total = max_over_ranks(t_start.elapsed_time(t_end))
+    ms_gc = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
+    ms_z = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
+    total_bases = sum_over_ranks(float(n_bases))
+    value = total_bases * args.steps / (ms_total * 1e-3) / 1e9
+    clocks = clk.summary()
+
+    gc_bytes = n_bases * 1 + n_win * 4            # 1 B/base read + 4 B/window (f32 gc) written
+    z_bytes = n_win * 5                           # 4 B gc read + 1 B signal written
+    z_flops = n_win * (4 * LAG + 6)               # non-fusable f32 ops the reference's order forces
+    roof_gc = {"bound": "hbm", "kernel": "gc_window_kernel", "achieved": gc_bytes / (ms_gc * 1e-3) / 1e9, "peak": hbm_peak,
+               "unit": "GB/s", "frac": gc_bytes / (ms_gc * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+               "algorithmic_bytes_per_launch": gc_bytes, "ms_per_launch": ms_gc, "peak_source": peak_src}
+    kern = {
+        "gc_window_kernel": roof_gc,
+        "zscore_kernel": {"bound": "fp32-issue (bit-exact sequential f32 sums; not HBM, no tensor cores)",
+                          "ms_per_launch": ms_z, "achieved_gbs": z_bytes / (ms_z * 1e-3) / 1e9,
+                          "hbm_frac": z_bytes / (ms_z * 1e-3) / 1e9 / hbm_peak,
+                          "achieved_gflops_nonfma": z_flops / (ms_z * 1e-3) / 1e9,
+                          "algorithmic_bytes_per_launch": z_bytes},
+    }
+
+    # ---- sanity: spot-check a few ctgs against the oracle (outside every timed region) ------------
+    parity = None
+    if rank == 0:
+        from oracle import oracle as orc
+        woff = api.win_offsets(seq_off, SIZE, STEP)
+        pick = sorted({0, n_ctg // 2, n_ctg - 1})
+        ok = True
+        for c in pick:
+            s = d_seq[int(seq_off[c]):int(seq_off[c + 1])].cpu().numpy()
+            _, rc, rg, rs = orc.wave_batch(s, np.array([0, s.size], dtype=np.uint64), SIZE, STEP, LAG, THRESHOLD, args.influence, threads=1)
+            a, b = int(woff[c]), int(woff[c + 1])
+            ok &= bool(np.array_equal(d_gc[a:b].cpu().numpy().view(np.uint32), rg.view(np.uint32)))
+            ok &= bool(np.array_equal(d_sig[a:b].cpu().numpy(), rs))
+        parity = {"ctgs_checked": pick, "bit_exact": ok}
+
+    # ---- e2e: host C-ABI call, pinned host buffers, H2D + D2H inside the timed region --------------
+    e2e = None
+    h_seq_ptr = None
+    if not args.skip_e2e:
+        woff = api.win_offsets(seq_off, SIZE, STEP)
+        h_seq_ptr = pinned(n_bases, L)
+        h_gc_ptr, h_sig_ptr = pinned(n_win * 4, L), pinned(n_win, L)
+        h_seq = as_np(h_seq_ptr, n_bases, np.uint8)
+        torch.from_numpy(h_seq).copy_(d_seq[:n_bases])
+        torch.cuda.synchronize()
+
+        def e2e_step():
+            api.check(L.gams_cuda_wave_batch(ctx.handle, n_ctg, h_seq_ptr, seq_off.ctypes.data_as(C.c_void_p), SIZE, STEP,
+                                             LAG, THRESHOLD, args.influence, woff.ctypes.data_as(C.c_void_p), None,
+                                             h_gc_ptr, h_sig_ptr))
+
+        n_e2e = max(1, min(args.steps, 5))
+        for _ in range(min(args.warmup, 2)):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        if rank == 0:
+            hs = as_np(h_sig_ptr, n_win, np.int8)
+            parity["e2e_matches_device_path"] = bool(np.array_equal(hs, d_sig.cpu().numpy()) and np.array_equal(
+                as_np(h_gc_ptr, n_win, np.float32).view(np.uint32), d_gc.cpu().numpy().view(np.uint32)))
+        e2e = {"value": total_bases * n_e2e / dt / 1e9, "unit": "Gbp/s", "h2d_bytes_per_step": int(n_bases),
+               "d2h_bytes_per_step": int(n_win * 5), "steps": n_e2e, "ms_per_step": dt / n_e2e * 1e3,
+               "api": "gams_cuda_wave_batch (host pointers, pinned)", "timer": "host wall clock around the blocking call, max over ranks"}
+        L.gams_cuda_host_free(h_gc_ptr)
+        L.gams_cuda_host_free(h_sig_ptr)
+
+    # ---- CPU baseline (rank 0, N = 1 only) --------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        cores = os.cpu_count() or 1
+        k = min(n_ctg, 4 * cores + 64)
+        h = d_seq[:int(seq_off[k])].cpu().numpy() if h_seq_ptr is None else as_np(h_seq_ptr, int(seq_off[k]), np.uint8)
+        v, sample = cpu_wave_rate(h, seq_off[:k + 1], cores, args.cpu_seconds, args.influence)
+        v1, sample1 = cpu_wave_rate(h, seq_off[:min(k, 9)], 1, 2.0, args.influence)
+        cpu = {"value": v, "unit": "Gbp/s", "cores": cores, "kind": "port", "sample": sample,
+               "single_thread": {"value": v1, "cores": 1, "sample": sample1}}
+    if h_seq_ptr is not None:
+        L.gams_cuda_host_free(h_seq_ptr)
+
+    del d_gc, d_sig, d_filt
+    overlap = None if args.skip_count else bench_count(args, ctx, L, dev, rank, world, g_off, barrier, max_over_ranks,
+                                                     sum_over_ranks, hbm_peak, peak_src)
+
+    if rank == 0:
+        line = {
+            "metric": "gc_wave_throughput", "value": value, "unit": "Gbp/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": args.scaling,
+            "vs_baseline": None, "dtype": "u8->u32 counts, f32 statistics", "data": "synthetic",
+            "config": workload_config(args), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roof_gc, "kernels": kern, "cpu_baseline": cpu, "overlap": overlap, "parity_spot_check": parity,
+            "windows_per_step": int(n_win), "bases_per_rank": int(n_bases),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_count(args, ctx, L, dev, rank, world, g_off, barrier, max_over_ranks, sum_over_ranks, hbm_peak, peak_src):
+    """configs[4]: batched `locate --count` — queries grouped by ctg (the order read_range yields) and in
+    arbitrary order, against SNP intervals; index resident in HBM as it is in the reference's BTreeMap."""
+    import torch
+
+    from gams_b200 import api, synth
+
+    lens = np.diff(g_off.astype(np.int64))
+    n_ctg = lens.size
+    per_ctg = max(1, int(args.intervals) // n_ctg)
+    n_q = int(args.queries)
+    d_st, d_sp, iv_off = synth.rg_index_torch(lens, per_ctg, seed=7 + rank, device=dev)
+    plan = api.CountPlan(ctx, iv_off)
+    stream = torch.cuda.current_stream().cuda_stream
+    out = {}
+    n_iv = int(iv_off[-1])
+    for name, grouped in (("grouped_by_ctg", True), ("arbitrary_order", False)):
+        q_seg, q_s, q_e = synth.queries_torch(lens, n_q, seed=11 + rank, grouped=grouped, device=dev)
+        d_out = torch.empty(n_q, dtype=torch.int32, device=dev)
+        for _ in range(args.warmup):
+            plan.count(stream, d_st, d_sp, q_seg, q_s, q_e, d_out, grouped=grouped)
+        l0 = plan.launches
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(args.steps):
+            plan.count(stream, d_st, d_sp, q_seg, q_s, q_e, d_out, grouped=grouped)
+        t1.record()
+        barrier()
+        ms = max_over_ranks(t0.elapsed_time(t1)) / args.steps
+        tot_q = sum_over_ranks(float(n_q))
+        alg = n_q * 16 + n_iv * 8   # 12 B query + 4 B result per query, 8 B per interval
+        res = {"value": tot_q / (ms * 1e-3), "unit": "counts/s", "ms_per_step": ms, "queries": n_q, "intervals": n_iv,
+               "gpu_launches": int(plan.launches - l0),
+               "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                            "frac": alg / (ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                            "algorithmic_bytes_per_launch": alg, "peak_source": peak_src}}
+        if rank == 0:
+            from oracle import oracle as orc
+            k = 200_000
+            sel = torch.randint(0, n_q, (k,), device=dev)
+            ref = orc.count_batch(d_st.cpu().numpy().view(np.uint32), d_sp.cpu().numpy().view(np.uint32), iv_off,
+                                  q_seg[sel].cpu().numpy(), q_s[sel].cpu().numpy().view(np.uint32),
+                                  q_e[sel].cpu().numpy().view(np.uint32), threads=os.cpu_count() or 1)
+            res["bit_exact_sample"] = bool(np.array_equal(d_out[sel].cpu().numpy().view(np.uint32), ref))
+        out[name] = res
+        if not grouped and not args.skip_e2e:
+            hs = [t.cpu().numpy() for t in (d_st, d_sp, q_seg, q_s, q_e)]
+            h_out = np.empty(n_q, dtype=np.uint32)
+            n_e = max(1, min(args.steps, 3))
+            api.count_overlaps(ctx, hs[0].view(np.uint32), hs[1].view(np.uint32), iv_off, hs[2], hs[3].view(np.uint32), hs[4].view(np.uint32))
+            barrier()
+            t = time.perf_counter()
+            for _ in range(n_e):
+                h_out = api.count_overlaps(ctx, hs[0].view(np.uint32), hs[1].view(np.uint32), iv_off, hs[2],
+                                           hs[3].view(np.uint32), hs[4].view(np.uint32))
+            dt = max_over_ranks(time.perf_counter() - t) / n_e
+            out["e2e"] = {"value": tot_q / dt, "unit": "counts/s", "ms_per_step": dt * 1e3,
+                          "h2d_bytes_per_step": int(n_q * 12 + n_iv * 8), "d2h_bytes_per_step": int(n_q * 4),
+                          "api": "gams_cuda_count_overlaps (host pointers, pageable numpy)",
+                          "matches_device_path": bool(np.array_equal(h_out, d_out.cpu().numpy().view(np.uint32)))}
+            if rank == 0 and world == 1 and not args.skip_cpu:
+                from oracle import oracle as orc
+                cores = os.cpu_count() or 1
+                k = min(n_q, 20_000_000)
+                t = time.perf_counter()
+                orc.count_batch(hs[0].view(np.uint32), hs[1].view(np.uint32), iv_off, hs[2][:k], hs[3][:k].view(np.uint32),
+                                hs[4][:k].view(np.uint32), threads=cores)
+                dtc = time.perf_counter() - t
+                k1 = min(n_q, 2_000_000)
+                t = time.perf_counter()
+                orc.count_batch(hs[0].view(np.uint32), hs[1].view(np.uint32), iv_off, hs[2][:k1], hs[3][:k1].view(np.uint32),
+                                hs[4][:k1].view(np.uint32), threads=1)
+                dt1 = time.perf_counter() - t
+                out["cpu_baseline"] = {"value": k / dtc, "unit": "counts/s", "cores": cores, "kind": "port",
+                                       "sample": f"first {k} arbitrary-order queries against the full index",
+                                       "single_thread": {"value": k1 / dt1, "sample": f"first {k1} queries"}}
+        del q_seg, q_s, q_e, d_out
+    plan.close()
+    return out
+
+
+if __name__ == "__main__":
+    main()

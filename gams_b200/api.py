@@ -1,0 +1,271 @@
+"""Host-side mirror of the reference's `gams::` interface for the hot path, over the C ABI.
+
+Names and argument meaning follow the reference (src/libs/window.rs, stat.rs, utils.rs and the
+proc_ctg bodies of src/cmd_gams/{wave,sw,locate}.rs); arrays are numpy, coordinates 1-based
+inclusive chr positions unless a name ends in 0.  Every function runs on the GPU through
+libgams_cuda.so; nothing here computes on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from ._lib import GamsCudaError, check, load  # noqa: F401
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _arr(a, dt):
+    return np.ascontiguousarray(a, dtype=dt)
+
+
+class Context:
+    """gams_cuda_ctx: the devices this process computes on (one per process under torchrun)."""
+
+    def __init__(self, devices=None):
+        L = load()
+        h = C.c_void_p()
+        if devices is None:
+            check(L.gams_cuda_create(None, 0, C.byref(h)))
+        else:
+            ids = _arr(devices, np.int32)
+            check(L.gams_cuda_create(_p(ids), ids.size, C.byref(h)))
+        self._h = h
+        self._L = L
+
+    @property
+    def handle(self):
+        return self._h
+
+    @property
+    def num_devices(self) -> int:
+        return int(self._L.gams_cuda_ctx_num_devices(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.gams_cuda_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ------------------------------------------------------------------------------ window.rs:78-94
+def sliding_count(length: int, size: int, step: int) -> int:
+    """Number of windows gams::sliding yields on a span of `length` bases."""
+    n = int(load().gams_cuda_wave_nwin(length, size, step))
+    if n < 0:
+        raise ValueError("size and step must be positive")
+    return n
+
+
+def sliding(chr_start: int, chr_end: int, size: int, step: int):
+    """gams::sliding on the single-span parent [chr_start, chr_end] → list of (start, end)."""
+    n = sliding_count(chr_end - chr_start + 1, size, step)
+    return [(chr_start + k * step, chr_start + k * step + size - 1) for k in range(n)]
+
+
+def win_offsets(seq_off, size: int, step: int) -> np.ndarray:
+    seq_off = _arr(seq_off, np.uint64)
+    out = np.zeros(seq_off.size, dtype=np.uint64)
+    check(load().gams_cuda_wave_win_offsets(seq_off.size - 1, _p(seq_off), size, step, _p(out)))
+    return out
+
+
+def partition(item_off, n_part: int) -> np.ndarray:
+    item_off = _arr(item_off, np.uint64)
+    out = np.zeros(n_part + 1, dtype=np.int64)
+    check(load().gams_cuda_partition(item_off.size - 1, _p(item_off), n_part, _p(out)))
+    return out
+
+
+# --------------------------------------------------------------- wave.rs:138-155 (batched)
+def wave_batch(ctx: Context, seq_concat, seq_off, size=100, step=10, lag=100, threshold=3.0, influence=1.0,
+               want_count=True, want_signal=True):
+    """sliding + gc_content + thresholding_algo for a batch of ctgs → (win_off, gc_count, gc, signal)."""
+    seq_concat = _arr(seq_concat, np.uint8)
+    seq_off = _arr(seq_off, np.uint64)
+    woff = win_offsets(seq_off, size, step)
+    n = int(woff[-1])
+    cnt = np.empty(n, dtype=np.uint32) if want_count else None
+    gc = np.empty(n, dtype=np.float32)
+    sig = np.empty(n, dtype=np.int8) if want_signal else None
+    check(load().gams_cuda_wave_batch(ctx.handle, seq_off.size - 1, _p(seq_concat), _p(seq_off), size, step, lag,
+                                      threshold, influence, _p(woff), _p(cnt), _p(gc), _p(sig)))
+    return woff, cnt, gc, sig
+
+
+# ------------------------------------------------------------------------------ stat.rs:16-56
+def thresholding_algo(ctx: Context, data, lag: int, threshold: float, influence: float) -> np.ndarray:
+    """gams::thresholding_algo(data, lag, threshold, influence) → int8 signals (-1/0/1)."""
+    d = _arr(data, np.float32)
+    off = np.array([0, d.size], dtype=np.uint64)
+    return thresholding_batch(ctx, d, off, lag, threshold, influence)
+
+
+def thresholding_batch(ctx: Context, data, off, lag, threshold, influence) -> np.ndarray:
+    d = _arr(data, np.float32)
+    off = _arr(off, np.uint64)
+    sig = np.empty(d.size, dtype=np.int8)
+    check(load().gams_cuda_thresholding_batch(ctx.handle, off.size - 1, _p(d), _p(off), lag, threshold, influence, _p(sig)))
+    return sig
+
+
+# --------------------------------------------------------------- utils.rs:24-36, locate.rs:111-141
+def count_overlaps(ctx: Context, starts, stops, iv_off, q_seg, q_start, q_stop) -> np.ndarray:
+    """Batched gams::count_rg: per query lower_bound(starts, q_stop) - lower_bound(stops, q_start+1)."""
+    starts, stops = _arr(starts, np.uint32), _arr(stops, np.uint32)
+    iv_off = _arr(iv_off, np.uint64)
+    q_seg, q_start, q_stop = _arr(q_seg, np.int32), _arr(q_start, np.uint32), _arr(q_stop, np.uint32)
+    out = np.empty(q_seg.size, dtype=np.uint32)
+    check(load().gams_cuda_count_overlaps(ctx.handle, iv_off.size - 1, _p(starts), _p(stops), _p(iv_off), q_seg.size,
+                                          _p(q_seg), _p(q_start), _p(q_stop), _p(out)))
+    return out
+
+
+def locate_ctg(ctx: Context, ctg_start, ctg_stop, chr_off, q_chr, q_start, q_stop) -> np.ndarray:
+    """Batched gams::find_one_idx → global ctg index or -1."""
+    ctg_start, ctg_stop = _arr(ctg_start, np.uint32), _arr(ctg_stop, np.uint32)
+    chr_off = _arr(chr_off, np.uint64)
+    q_chr, q_start, q_stop = _arr(q_chr, np.int32), _arr(q_start, np.uint32), _arr(q_stop, np.uint32)
+    out = np.empty(q_chr.size, dtype=np.int32)
+    check(load().gams_cuda_locate_ctg(ctx.handle, chr_off.size - 1, _p(ctg_start), _p(ctg_stop), _p(chr_off), q_chr.size,
+                                      _p(q_chr), _p(q_start), _p(q_stop), _p(out)))
+    return out
+
+
+# --------------------------------------------------------------- utils.rs:141-213, sw.rs:141-191
+def gc_ranges(ctx: Context, seq_concat, seq_off, q_ctg, q_from0, q_to0_excl) -> np.ndarray:
+    seq_concat, seq_off = _arr(seq_concat, np.uint8), _arr(seq_off, np.uint64)
+    q_ctg, q_from0, q_to0_excl = _arr(q_ctg, np.uint32), _arr(q_from0, np.uint32), _arr(q_to0_excl, np.uint32)
+    out = np.empty(q_ctg.size, dtype=np.uint32)
+    check(load().gams_cuda_gc_ranges(ctx.handle, seq_off.size - 1, _p(seq_concat), _p(seq_off), q_ctg.size, _p(q_ctg),
+                                     _p(q_from0), _p(q_to0_excl), _p(out)))
+    return out
+
+
+def sw_batch(ctx: Context, seq_concat, seq_off, ctg_chr_start, f_ctg, f_start, f_end, size=100, max_=20, resize=500):
+    """Rows of `gams sw --action gc` for a batch of features → dict of arrays + row_off."""
+    seq_concat, seq_off = _arr(seq_concat, np.uint8), _arr(seq_off, np.uint64)
+    ctg_chr_start = _arr(ctg_chr_start, np.int32)
+    f_ctg, f_start, f_end = _arr(f_ctg, np.uint32), _arr(f_start, np.int32), _arr(f_end, np.int32)
+    nf = f_ctg.size
+    cap = nf * (1 + 2 * max_)
+    row_off = np.zeros(nf + 1, dtype=np.uint64)
+    ws, we, wd = (np.zeros(cap, dtype=np.int32) for _ in range(3))
+    wt = np.zeros(cap, dtype=np.int8)
+    gc, gm, gs, gv = (np.zeros(cap, dtype=np.float32) for _ in range(4))
+    check(load().gams_cuda_sw_batch(ctx.handle, seq_off.size - 1, _p(seq_concat), _p(seq_off), _p(ctg_chr_start), nf,
+                                    _p(f_ctg), _p(f_start), _p(f_end), size, max_, resize, _p(row_off), _p(ws), _p(we),
+                                    _p(wt), _p(wd), _p(gc), _p(gm), _p(gs), _p(gv)))
+    n = int(row_off[-1])
+    return dict(row_off=row_off, start=ws[:n], end=we[:n], type=wt[:n], dist=wd[:n], gc=gc[:n], mean=gm[:n],
+                sd=gs[:n], cv=gv[:n])
+
+
+# --------------------------------------------------------------- host-side format helpers (no GPU)
+def wave_text(chr_id: str, chr_start: int, size: int, step: int, gc, signal, coverage=0.2, is_signal=False) -> str:
+    """The per-ctg stdout block of `gams wave` (wave.rs:157-212), produced by the C++ host layer."""
+    gc, signal = _arr(gc, np.float32), _arr(signal, np.int8)
+    txt, ln = C.c_void_p(), C.c_size_t()
+    L = load()
+    check(L.gams_cuda_wave_text(chr_id.encode(), chr_start, size, step, gc.size, _p(gc), _p(signal), coverage,
+                                int(is_signal), C.byref(txt), C.byref(ln)))
+    try:
+        return C.string_at(txt, ln.value).decode()
+    finally:
+        L.gams_cuda_free(txt)
+
+
+def lapper_blob_view(blob: bytes):
+    """(starts, stops, max_len) sliced zero-copy out of a bincode Lapper<u32,String> blob."""
+    buf = np.frombuffer(blob, dtype=np.uint8)
+    n, st, sp, ml = C.c_uint64(), C.c_void_p(), C.c_void_p(), C.c_uint32()
+    check(load().gams_cuda_lapper_blob_view(_p(buf), buf.size, C.byref(n), C.byref(st), C.byref(sp), C.byref(ml)))
+    base = buf.ctypes.data
+    starts = np.frombuffer(blob, dtype="<u4", count=n.value, offset=(st.value or base) - base)
+    stops = np.frombuffer(blob, dtype="<u4", count=n.value, offset=(sp.value or base) - base)
+    return starts, stops, int(ml.value)
+
+
+# --------------------------------------------------------------- device API (inputs resident in HBM)
+class WavePlan:
+    """gams_cuda_wave_plan on one device; tensors are torch CUDA tensors (used for their data_ptr only)."""
+
+    def __init__(self, ctx: Context, seq_off, size=100, step=10, lag=100, dev_index=0):
+        self._L = load()
+        seq_off = _arr(seq_off, np.uint64)
+        h = C.c_void_p()
+        check(self._L.gams_cuda_wave_plan_create(ctx.handle, dev_index, seq_off.size - 1, _p(seq_off), size, step, lag,
+                                                 C.byref(h)))
+        self._h, self._ctx = h, ctx
+        self.total_windows = int(self._L.gams_cuda_wave_plan_total_windows(h))
+        self.total_bases = int(self._L.gams_cuda_wave_plan_total_bases(h))
+        self.seq_capacity = int(self._L.gams_cuda_wave_plan_seq_capacity(h))
+
+    def gc(self, stream: int, d_seq, d_gc, d_cnt=None):
+        check(self._L.gams_cuda_wave_gc_dev(self._h, stream, d_seq.data_ptr(), d_cnt.data_ptr() if d_cnt is not None else None,
+                                            d_gc.data_ptr()))
+
+    def signal(self, stream: int, d_gc, threshold, influence, d_signal, d_filtered=None):
+        check(self._L.gams_cuda_wave_signal_dev(self._h, stream, d_gc.data_ptr(), threshold, influence,
+                                                d_filtered.data_ptr() if d_filtered is not None else None,
+                                                d_signal.data_ptr()))
+
+    @property
+    def launches(self) -> int:
+        return int(self._L.gams_cuda_wave_plan_launches(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.gams_cuda_wave_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class CountPlan:
+    """gams_cuda_count_plan: the rg index of a set of ctgs resident on one device."""
+
+    def __init__(self, ctx: Context, iv_off, dev_index=0):
+        self._L = load()
+        iv_off = _arr(iv_off, np.uint64)
+        h = C.c_void_p()
+        check(self._L.gams_cuda_count_plan_create(ctx.handle, dev_index, iv_off.size - 1, _p(iv_off), C.byref(h)))
+        self._h, self._ctx = h, ctx
+
+    def count(self, stream: int, d_starts, d_stops, d_q_seg, d_q_start, d_q_stop, d_out, grouped=False):
+        check(self._L.gams_cuda_count_overlaps_dev(self._h, stream, d_starts.data_ptr(), d_stops.data_ptr(),
+                                                   d_q_seg.numel(), d_q_seg.data_ptr(), d_q_start.data_ptr(),
+                                                   d_q_stop.data_ptr(), int(grouped), d_out.data_ptr()))
+
+    @property
+    def launches(self) -> int:
+        return int(self._L.gams_cuda_count_plan_launches(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.gams_cuda_count_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,695 @@
+// api.cu — C ABI of libgams_cuda.so: context, plans, and the host-buffer entry points.
+// See include/gams_cuda.h for the contract of every function and the reference call site it replaces.
+#include <algorithm>
+#include <cstdlib>
+#include <memory>
+#include <string>
+#include <thread>
+
+#include "common.cuh"
+
+namespace gams {
+
+// ---- errors ------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int32_t cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
+    const char *base = strrchr(file, '/');
+    set_error("CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), base ? base + 1 : file, line, what);
+    if (e == cudaErrorMemoryAllocation) {
+        cudaGetLastError();
+        return GAMS_CUDA_ENOMEM;
+    }
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) return GAMS_CUDA_ENODEV;
+    return GAMS_CUDA_ECUDA;
+}
+
+int32_t DevBuf::reserve(size_t bytes) {
+    if (bytes <= cap) return GAMS_CUDA_OK;
+    if (p) {
+        cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    const size_t want = ((bytes + (1u << 20) - 1) >> 20) << 20;
+    CUDA_TRY(cudaMalloc(&p, want));
+    cap = want;
+    return GAMS_CUDA_OK;
+}
+
+void DevBuf::release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+}
+
+int32_t SeriesLayout::build(const uint64_t *h_off, int64_t n, cudaStream_t st) {
+    n_series = n;
+    total = n ? h_off[n] - h_off[0] : 0;
+    min_len = ~0ull;
+    std::vector<TileDesc> zt;
+    std::vector<uint64_t> rel((size_t)n + 1);
+    for (int64_t c = 0; c <= n; ++c) rel[c] = h_off[c] - h_off[0];
+    for (int64_t c = 0; c < n; ++c) {
+        if (h_off[c + 1] < h_off[c]) {
+            set_error("offsets must be non-decreasing (entry %lld)", (long long)c);
+            return GAMS_CUDA_EINVAL;
+        }
+        const uint64_t len = h_off[c + 1] - h_off[c];
+        min_len = std::min(min_len, len);
+        for (uint64_t w = 0; w < len; w += ZS_TILE) zt.push_back({(uint32_t)c, (uint32_t)w});
+    }
+    if (n == 0) min_len = 0;
+    n_ztiles = zt.size();
+    CUDA_TRY(cudaMalloc(&d_off, sizeof(uint64_t) * (size_t)(n + 1)));
+    CUDA_TRY(cudaMemcpyAsync(d_off, rel.data(), sizeof(uint64_t) * (size_t)(n + 1), cudaMemcpyHostToDevice, st));
+    if (n_ztiles) {
+        CUDA_TRY(cudaMalloc(&d_ztiles, sizeof(TileDesc) * n_ztiles));
+        CUDA_TRY(cudaMemcpyAsync(d_ztiles, zt.data(), sizeof(TileDesc) * n_ztiles, cudaMemcpyHostToDevice, st));
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return GAMS_CUDA_OK;
+}
+
+void SeriesLayout::release() {
+    if (d_off) cudaFree(d_off);
+    if (d_ztiles) cudaFree(d_ztiles);
+    d_off = nullptr;
+    d_ztiles = nullptr;
+}
+
+static int64_t nwin(int64_t len, int32_t size, int32_t step) {
+    if (size <= 0 || step <= 0) return -1;
+    return len >= size ? (len - size) / step + 1 : 0;
+}
+
+// Run fn(d) for every device of the ctx, concurrently when there are several.
+template <class F>
+static int32_t for_each_device(gams_cuda_ctx *ctx, int n_used, F fn) {
+    std::vector<int32_t> rc((size_t)n_used, 0);
+    std::vector<std::string> msg((size_t)n_used);
+    if (n_used == 1) return fn(0);
+    std::vector<std::thread> th;
+    for (int d = 0; d < n_used; ++d)
+        th.emplace_back([&, d] {
+            rc[d] = fn(d);
+            if (rc[d]) msg[d] = std::string(g_err);
+        });
+    for (auto &t : th) t.join();
+    for (int d = 0; d < n_used; ++d)
+        if (rc[d]) {
+            set_error("%s", msg[d].c_str());
+            return rc[d];
+        }
+    (void)ctx;
+    return GAMS_CUDA_OK;
+}
+
+}  // namespace gams
+
+using namespace gams;
+
+// ================================================================================ lifecycle =====
+GAMS_API int32_t gams_cuda_version(void) { return 100; /* 0.1.0 */ }
+
+GAMS_API const char *gams_cuda_last_error(void) { return g_err; }
+
+GAMS_API int32_t gams_cuda_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        if (e == cudaErrorNoDevice) return 0;
+        return cuda_fail(e, "cudaGetDeviceCount", __FILE__, __LINE__);
+    }
+    return n;
+}
+
+GAMS_API int32_t gams_cuda_create(const int32_t *device_ids, int32_t n_dev, gams_cuda_ctx **out) {
+    ARG_CHECK(out != nullptr, "gams_cuda_create: out is NULL");
+    *out = nullptr;
+    const int32_t avail = gams_cuda_device_count();
+    if (avail < 0) return avail;
+    if (avail == 0) {
+        set_error("gams_cuda_create: no CUDA device visible; this library has no CPU fallback");
+        return GAMS_CUDA_ENODEV;
+    }
+    std::vector<int> ids;
+    if (!device_ids || n_dev <= 0)
+        for (int d = 0; d < avail; ++d) ids.push_back(d);
+    else
+        for (int i = 0; i < n_dev; ++i) {
+            ARG_CHECK(device_ids[i] >= 0 && device_ids[i] < avail, "gams_cuda_create: device %d not visible (%d devices)",
+                      device_ids[i], avail);
+            ids.push_back(device_ids[i]);
+        }
+    std::unique_ptr<gams_cuda_ctx> ctx(new gams_cuda_ctx);
+    for (int id : ids) {
+        cudaDeviceProp prop;
+        CUDA_TRY(cudaGetDeviceProperties(&prop, id));
+        if (prop.major < 10) {
+            set_error("gams_cuda_create: device %d is sm_%d%d; this library is built for sm_100a only", id, prop.major,
+                      prop.minor);
+            return GAMS_CUDA_ENODEV;
+        }
+        DeviceGuard g(id);
+        PerDevice pd;
+        pd.device = id;
+        CUDA_TRY(cudaStreamCreateWithFlags(&pd.stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&pd.copy_in, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&pd.copy_out, cudaStreamNonBlocking));
+        ctx->devs.push_back(pd);
+    }
+    *out = ctx.release();
+    return GAMS_CUDA_OK;
+}
+
+GAMS_API void gams_cuda_destroy(gams_cuda_ctx *ctx) {
+    if (!ctx) return;
+    for (auto &pd : ctx->devs) {
+        DeviceGuard g(pd.device);
+        cudaStreamSynchronize(pd.stream);
+        for (auto &b : pd.scratch) b.release();
+        cudaStreamDestroy(pd.stream);
+        cudaStreamDestroy(pd.copy_in);
+        cudaStreamDestroy(pd.copy_out);
+    }
+    delete ctx;
+}
+
+GAMS_API int32_t gams_cuda_ctx_num_devices(const gams_cuda_ctx *ctx) { return ctx ? (int32_t)ctx->devs.size() : 0; }
+
+GAMS_API void *gams_cuda_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+        cudaGetLastError();
+        set_error("gams_cuda_host_alloc: cudaMallocHost(%zu) failed", bytes);
+        return nullptr;
+    }
+    return p;
+}
+
+GAMS_API void gams_cuda_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+// ======================================================================== window arithmetic =====
+GAMS_API int64_t gams_cuda_wave_nwin(int64_t ctg_len, int32_t size, int32_t step) { return nwin(ctg_len, size, step); }
+
+GAMS_API int32_t gams_cuda_wave_win_offsets(int64_t n_ctg, const uint64_t *seq_off, int32_t size, int32_t step,
+                                            uint64_t *win_off) {
+    ARG_CHECK(n_ctg >= 0 && seq_off && win_off, "wave_win_offsets: NULL argument");
+    ARG_CHECK(size > 0 && step > 0, "wave_win_offsets: size and step must be positive (got %d, %d)", size, step);
+    win_off[0] = 0;
+    for (int64_t c = 0; c < n_ctg; ++c) {
+        ARG_CHECK(seq_off[c + 1] >= seq_off[c], "wave_win_offsets: seq_off not monotone at %lld", (long long)c);
+        win_off[c + 1] = win_off[c] + (uint64_t)nwin((int64_t)(seq_off[c + 1] - seq_off[c]), size, step);
+    }
+    return GAMS_CUDA_OK;
+}
+
+GAMS_API int32_t gams_cuda_partition(int64_t n_item, const uint64_t *item_off, int32_t n_part, int64_t *part_off) {
+    ARG_CHECK(n_item >= 0 && item_off && part_off && n_part > 0, "partition: bad argument");
+    const uint64_t base = item_off[0], total = item_off[n_item] - base;
+    part_off[0] = 0;
+    int64_t c = 0;
+    for (int32_t p = 1; p < n_part; ++p) {
+        const uint64_t target = base + (uint64_t)((__uint128_t)total * (unsigned)p / (unsigned)n_part);
+        // first item whose end passes the target goes to the shard whose boundary is nearer
+        while (c < n_item && item_off[c + 1] <= target) ++c;
+        if (c < n_item && target - item_off[c] > item_off[c + 1] - target) ++c;
+        part_off[p] = std::max(c, part_off[p - 1]);
+    }
+    part_off[n_part] = n_item;
+    return GAMS_CUDA_OK;
+}
+
+// ================================================================================ wave plan =====
+GAMS_API int32_t gams_cuda_wave_plan_create(gams_cuda_ctx *ctx, int32_t dev_index, int64_t n_ctg,
+                                            const uint64_t *seq_off, int32_t size, int32_t step, uint64_t lag,
+                                            gams_cuda_wave_plan **out) {
+    ARG_CHECK(ctx && out && seq_off, "wave_plan_create: NULL argument");
+    ARG_CHECK(dev_index >= 0 && dev_index < (int32_t)ctx->devs.size(), "wave_plan_create: dev_index %d out of range",
+              dev_index);
+    ARG_CHECK(n_ctg >= 0 && n_ctg < (1ll << 32), "wave_plan_create: n_ctg out of range");
+    ARG_CHECK(size > 0 && step > 0, "wave_plan_create: size and step must be positive (got %d, %d)", size, step);
+    *out = nullptr;
+    std::unique_ptr<gams_cuda_wave_plan, void (*)(gams_cuda_wave_plan *)> p(new gams_cuda_wave_plan,
+                                                                            gams_cuda_wave_plan_destroy);
+    PerDevice &pd = ctx->devs[dev_index];
+    p->ctx = ctx;
+    p->dev_index = dev_index;
+    p->device = pd.device;
+    p->n_ctg = n_ctg;
+    p->size = size;
+    p->step = step;
+    p->lag = lag;
+    p->h_seq_off.resize((size_t)n_ctg + 1);
+    p->h_win_off.resize((size_t)n_ctg + 1);
+    for (int64_t c = 0; c <= n_ctg; ++c) p->h_seq_off[c] = seq_off[c] - seq_off[0];
+    p->total_bases = p->h_seq_off[n_ctg];
+    p->h_win_off[0] = 0;
+    for (int64_t c = 0; c < n_ctg; ++c) {
+        ARG_CHECK(seq_off[c + 1] >= seq_off[c], "wave_plan_create: seq_off not monotone at %lld", (long long)c);
+        const uint64_t len = seq_off[c + 1] - seq_off[c];
+        ARG_CHECK(len < (1ull << 31), "wave_plan_create: ctg %lld longer than 2^31-1 bases", (long long)c);
+        p->h_win_off[c + 1] = p->h_win_off[c] + (uint64_t)nwin((int64_t)len, size, step);
+    }
+    p->geom = plan_gc_geometry(size, step);
+    std::vector<TileDesc> gt;
+    if (p->geom.k) {
+        for (int64_t c = 0; c < n_ctg; ++c) {
+            const uint64_t n_c = p->h_win_off[c + 1] - p->h_win_off[c];
+            for (uint64_t w = 0; w < n_c; w += (uint64_t)p->geom.wt) gt.push_back({(uint32_t)c, (uint32_t)w});
+        }
+        p->geom.n_tiles = gt.size();
+        ARG_CHECK(gt.size() < (1ull << 31), "wave_plan_create: too many tiles");
+    }
+    DeviceGuard g(pd.device);
+    CUDA_TRY(cudaMalloc(&p->d_seq_off, sizeof(uint64_t) * (size_t)(n_ctg + 1)));
+    CUDA_TRY(cudaMemcpyAsync(p->d_seq_off, p->h_seq_off.data(), sizeof(uint64_t) * (size_t)(n_ctg + 1),
+                             cudaMemcpyHostToDevice, pd.stream));
+    if (!gt.empty()) {
+        CUDA_TRY(cudaMalloc(&p->d_gtiles, sizeof(TileDesc) * gt.size()));
+        CUDA_TRY(cudaMemcpyAsync(p->d_gtiles, gt.data(), sizeof(TileDesc) * gt.size(), cudaMemcpyHostToDevice, pd.stream));
+        std::vector<float> tab((size_t)size + 1);
+        const float fs = (float)size;
+        for (int32_t c = 0; c <= size; ++c) tab[c] = (float)c / fs;  // `count as f32 / l as f32`, one IEEE divide
+        CUDA_TRY(cudaMalloc(&p->d_gc_tab, sizeof(float) * tab.size()));
+        CUDA_TRY(cudaMemcpyAsync(p->d_gc_tab, tab.data(), sizeof(float) * tab.size(), cudaMemcpyHostToDevice, pd.stream));
+        CUDA_TRY(cudaStreamSynchronize(pd.stream));
+    }
+    int32_t rc = p->win.build(p->h_win_off.data(), n_ctg, pd.stream);
+    if (rc) return rc;
+    *out = p.release();
+    return GAMS_CUDA_OK;
+}
+
+GAMS_API void gams_cuda_wave_plan_destroy(gams_cuda_wave_plan *p) {
+    if (!p) return;
+    DeviceGuard g(p->device);
+    if (p->d_seq_off) cudaFree(p->d_seq_off);
+    if (p->d_gtiles) cudaFree(p->d_gtiles);
+    if (p->d_gc_tab) cudaFree(p->d_gc_tab);
+    p->win.release();
+    delete p;
+}
+
+GAMS_API uint64_t gams_cuda_wave_plan_total_windows(const gams_cuda_wave_plan *p) { return p ? p->win.total : 0; }
+GAMS_API uint64_t gams_cuda_wave_plan_total_bases(const gams_cuda_wave_plan *p) { return p ? p->total_bases : 0; }
+GAMS_API uint64_t gams_cuda_wave_plan_seq_capacity(const gams_cuda_wave_plan *p) {
+    return p ? ((p->total_bases + 15) & ~15ull) + 16 : 0;
+}
+GAMS_API uint64_t gams_cuda_wave_plan_launches(const gams_cuda_wave_plan *p) { return p ? p->launches : 0; }
+
+GAMS_API int32_t gams_cuda_wave_gc_dev(gams_cuda_wave_plan *p, void *stream, const uint8_t *d_seq,
+                                       uint32_t *d_gc_count, float *d_gc) {
+    ARG_CHECK(p && d_gc && (d_seq || p->total_bases == 0), "wave_gc_dev: NULL argument");
+    DeviceGuard g(p->device);
+    return launch_gc_windows(p, (cudaStream_t)stream, d_seq, d_gc_count, d_gc, &p->launches);
+}
+
+GAMS_API int32_t gams_cuda_wave_signal_dev(gams_cuda_wave_plan *p, void *stream, const float *d_gc, float threshold,
+                                           float influence, float *d_filtered, int8_t *d_signal) {
+    ARG_CHECK(p && d_signal && d_gc, "wave_signal_dev: NULL argument");
+    DeviceGuard g(p->device);
+    return launch_zscore(p->win, (cudaStream_t)stream, d_gc, p->lag, threshold, influence, d_filtered, d_signal,
+                         &p->launches);
+}
+
+// ================================================================================ wave: host ====
+static int32_t wave_on_device(gams_cuda_ctx *ctx, int d, int64_t c0, int64_t c1, const uint8_t *seq_concat,
+                              const uint64_t *seq_off, int32_t size, int32_t step, uint64_t lag, float threshold,
+                              float influence, const uint64_t *win_off, uint32_t *gc_count, float *gc, int8_t *signal) {
+    if (c1 <= c0) return GAMS_CUDA_OK;
+    PerDevice &pd = ctx->devs[d];
+    DeviceGuard g(pd.device);
+    gams_cuda_wave_plan *plan = nullptr;
+    int32_t rc = gams_cuda_wave_plan_create(ctx, d, c1 - c0, seq_off + c0, size, step, lag, &plan);
+    if (rc) return rc;
+    std::unique_ptr<gams_cuda_wave_plan, void (*)(gams_cuda_wave_plan *)> guard(plan, gams_cuda_wave_plan_destroy);
+    const uint64_t nb = plan->total_bases, nwn = plan->win.total;
+    if (nwn != win_off[c1] - win_off[c0]) {
+        set_error("wave_batch: win_off does not match gams_cuda_wave_win_offsets for size=%d step=%d", size, step);
+        return GAMS_CUDA_EINVAL;
+    }
+    if (signal && lag == 0) {
+        set_error("wave_batch: lag must be >= 1");
+        return GAMS_CUDA_EINVAL;
+    }
+    if (signal && plan->win.min_len < lag) {
+        set_error("wave_batch: a ctg has %llu windows but lag is %llu (the reference panics, stat.rs:30)",
+                  (unsigned long long)plan->win.min_len, (unsigned long long)lag);
+        return GAMS_CUDA_ELAG;
+    }
+    if ((rc = pd.scratch[0].reserve(gams_cuda_wave_plan_seq_capacity(plan)))) return rc;
+    if ((rc = pd.scratch[1].reserve(std::max<uint64_t>(nwn, 1) * sizeof(float)))) return rc;
+    if (gc_count && (rc = pd.scratch[2].reserve(std::max<uint64_t>(nwn, 1) * sizeof(uint32_t)))) return rc;
+    if (signal && (rc = pd.scratch[3].reserve(std::max<uint64_t>(nwn, 1)))) return rc;
+    const bool need_filt = signal && !(influence == 1.0f && lag <= 40000);
+    if (need_filt && (rc = pd.scratch[4].reserve(std::max<uint64_t>(nwn, 1) * sizeof(float)))) return rc;
+    uint8_t *d_seq = pd.scratch[0].as<uint8_t>();
+    float *d_gc = pd.scratch[1].as<float>();
+    uint32_t *d_cnt = gc_count ? pd.scratch[2].as<uint32_t>() : nullptr;
+    int8_t *d_sig = signal ? pd.scratch[3].as<int8_t>() : nullptr;
+    float *d_filt = need_filt ? pd.scratch[4].as<float>() : nullptr;
+    cudaStream_t st = pd.stream;
+    CUDA_TRY(cudaMemcpyAsync(d_seq, seq_concat + seq_off[c0], nb, cudaMemcpyHostToDevice, st));
+    if ((rc = gams_cuda_wave_gc_dev(plan, st, d_seq, d_cnt, d_gc))) return rc;
+    if (signal && (rc = gams_cuda_wave_signal_dev(plan, st, d_gc, threshold, influence, d_filt, d_sig))) return rc;
+    const uint64_t wo = win_off[c0];
+    if (nwn) {
+        CUDA_TRY(cudaMemcpyAsync(gc + wo, d_gc, nwn * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (gc_count) CUDA_TRY(cudaMemcpyAsync(gc_count + wo, d_cnt, nwn * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        if (signal) CUDA_TRY(cudaMemcpyAsync(signal + wo, d_sig, nwn, cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return GAMS_CUDA_OK;
+}
+
+GAMS_API int32_t gams_cuda_wave_batch(gams_cuda_ctx *ctx, int64_t n_ctg, const uint8_t *seq_concat,
+                                      const uint64_t *seq_off, int32_t size, int32_t step, uint64_t lag,
+                                      float threshold, float influence, const uint64_t *win_off, uint32_t *gc_count,
+                                      float *gc, int8_t *signal) {
+    ARG_CHECK(ctx, "wave_batch: ctx is NULL");
+    ARG_CHECK(n_ctg >= 0 && seq_off && win_off, "wave_batch: NULL offsets");
+    ARG_CHECK(size > 0 && step > 0, "wave_batch: size and step must be positive (got %d, %d)", size, step);
+    if (n_ctg == 0) return GAMS_CUDA_OK;
+    ARG_CHECK(seq_concat || seq_off[n_ctg] == seq_off[0], "wave_batch: seq_concat is NULL");
+    ARG_CHECK(gc || win_off[n_ctg] == 0, "wave_batch: gc is NULL");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const int n_dev = (int)std::min<int64_t>((int64_t)ctx->devs.size(), n_ctg);
+    std::vector<int64_t> part((size_t)n_dev + 1);
+    int32_t rc = gams_cuda_partition(n_ctg, seq_off, n_dev, part.data());
+    if (rc) return rc;
+    return for_each_device(ctx, n_dev, [&](int d) {
+        return wave_on_device(ctx, d, part[d], part[d + 1], seq_concat, seq_off, size, step, lag, threshold, influence,
+                              win_off, gc_count, gc, signal);
+    });
+}
+
+GAMS_API int32_t gams_cuda_thresholding_batch(gams_cuda_ctx *ctx, int64_t n_series, const float *data,
+                                              const uint64_t *off, uint64_t lag, float threshold, float influence,
+                                              int8_t *signal) {
+    ARG_CHECK(ctx && off, "thresholding_batch: NULL argument");
+    ARG_CHECK(n_series >= 0 && n_series < (1ll << 32), "thresholding_batch: n_series out of range");
+    if (n_series == 0) return GAMS_CUDA_OK;
+    ARG_CHECK(lag >= 1, "thresholding_batch: lag must be >= 1 (the reference underflows lag-1, stat.rs:30)");
+    const uint64_t total = off[n_series] - off[0];
+    ARG_CHECK((data && signal) || total == 0, "thresholding_batch: NULL data/signal");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    PerDevice &pd = ctx->devs[0];
+    DeviceGuard g(pd.device);
+    SeriesLayout L;
+    int32_t rc = L.build(off, n_series, pd.stream);
+    struct Rel { SeriesLayout &l; ~Rel() { l.release(); } } rel{L};
+    if (rc) return rc;
+    if ((rc = pd.scratch[1].reserve(std::max<uint64_t>(total, 1) * sizeof(float)))) return rc;
+    if ((rc = pd.scratch[3].reserve(std::max<uint64_t>(total, 1)))) return rc;
+    if ((rc = pd.scratch[4].reserve(std::max<uint64_t>(total, 1) * sizeof(float)))) return rc;
+    float *d_x = pd.scratch[1].as<float>();
+    int8_t *d_sig = pd.scratch[3].as<int8_t>();
+    cudaStream_t st = pd.stream;
+    CUDA_TRY(cudaMemcpyAsync(d_x, data + off[0], total * sizeof(float), cudaMemcpyHostToDevice, st));
+    if ((rc = launch_zscore(L, st, d_x, lag, threshold, influence, pd.scratch[4].as<float>(), d_sig, nullptr))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(signal + off[0], d_sig, total, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return GAMS_CUDA_OK;
+}
+
+// ============================================================================ overlap counting ==
+GAMS_API int32_t gams_cuda_count_plan_create(gams_cuda_ctx *ctx, int32_t dev_index, int64_t n_seg,
+                                             const uint64_t *iv_off, gams_cuda_count_plan **out) {
+    ARG_CHECK(ctx && out && iv_off, "count_plan_create: NULL argument");
+    ARG_CHECK(dev_index >= 0 && dev_index < (int32_t)ctx->devs.size(), "count_plan_create: dev_index %d out of range",
+              dev_index);
+    ARG_CHECK(n_seg >= 0 && n_seg < (1ll << 31), "count_plan_create: n_seg out of range");
+    *out = nullptr;
+    std::unique_ptr<gams_cuda_count_plan, void (*)(gams_cuda_count_plan *)> p(new gams_cuda_count_plan,
+                                                                              gams_cuda_count_plan_destroy);
+    PerDevice &pd = ctx->devs[dev_index];
+    p->ctx = ctx;
+    p->dev_index = dev_index;
+    p->device = pd.device;
+    p->n_seg = n_seg;
+    p->h_iv_off.resize((size_t)n_seg + 1);
+    for (int64_t s = 0; s <= n_seg; ++s) p->h_iv_off[s] = iv_off[s] - iv_off[0];
+    for (int64_t s = 0; s < n_seg; ++s) {
+        ARG_CHECK(iv_off[s + 1] >= iv_off[s], "count_plan_create: iv_off not monotone at %lld", (long long)s);
+        const uint64_t len = iv_off[s + 1] - iv_off[s];
+        ARG_CHECK(len < (1ull << 32), "count_plan_create: segment %lld has more than 2^32-1 intervals", (long long)s);
+        p->max_seg = std::max(p->max_seg, len);
+    }
+    p->total_iv = p->h_iv_off[n_seg];
+    DeviceGuard g(pd.device);
+    CUDA_TRY(cudaMalloc(&p->d_iv_off, sizeof(uint64_t) * (size_t)(n_seg + 1)));
+    CUDA_TRY(cudaMemcpyAsync(p->d_iv_off, p->h_iv_off.data(), sizeof(uint64_t) * (size_t)(n_seg + 1),
+                             cudaMemcpyHostToDevice, pd.stream));
+    CUDA_TRY(cudaStreamSynchronize(pd.stream));
+    *out = p.release();
+    return GAMS_CUDA_OK;
+}
+
+GAMS_API void gams_cuda_count_plan_destroy(gams_cuda_count_plan *p) {
+    if (!p) return;
+    DeviceGuard g(p->device);
+    if (p->d_iv_off) cudaFree(p->d_iv_off);
+    for (auto &b : p->tmp) b.release();
+    delete p;
+}
+
+GAMS_API uint64_t gams_cuda_count_plan_launches(const gams_cuda_count_plan *p) { return p ? p->launches : 0; }
+
+GAMS_API int32_t gams_cuda_count_overlaps_dev(gams_cuda_count_plan *p, void *stream, const uint32_t *d_starts,
+                                              const uint32_t *d_stops, int64_t n_q, const int32_t *d_q_seg,
+                                              const uint32_t *d_q_start, const uint32_t *d_q_stop, int32_t grouped,
+                                              uint32_t *d_out) {
+    ARG_CHECK(p && n_q >= 0, "count_overlaps_dev: bad argument");
+    if (n_q == 0) return GAMS_CUDA_OK;
+    ARG_CHECK(d_q_seg && d_q_start && d_q_stop && d_out, "count_overlaps_dev: NULL query/output pointer");
+    ARG_CHECK((d_starts && d_stops) || p->total_iv == 0, "count_overlaps_dev: NULL index pointer");
+    DeviceGuard g(p->device);
+    return launch_count_overlaps(p, (cudaStream_t)stream, d_starts, d_stops, n_q, d_q_seg, d_q_start, d_q_stop, grouped,
+                                 d_out);
+}
+
+GAMS_API int32_t gams_cuda_count_overlaps(gams_cuda_ctx *ctx, int64_t n_seg, const uint32_t *starts,
+                                          const uint32_t *stops, const uint64_t *iv_off, int64_t n_q,
+                                          const int32_t *q_seg, const uint32_t *q_start, const uint32_t *q_stop,
+                                          uint32_t *out) {
+    ARG_CHECK(ctx && iv_off && n_seg >= 0 && n_q >= 0, "count_overlaps: bad argument");
+    if (n_q == 0) return GAMS_CUDA_OK;
+    ARG_CHECK(q_seg && q_start && q_stop && out, "count_overlaps: NULL query/output pointer");
+    const uint64_t n_iv = iv_off[n_seg] - iv_off[0];
+    ARG_CHECK((starts && stops) || n_iv == 0, "count_overlaps: NULL index pointer");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    // Queries are split evenly over the devices; every device gets the whole (small) index.
+    const int n_dev = (int)std::min<int64_t>((int64_t)ctx->devs.size(), std::max<int64_t>(1, n_q / 65536));
+    return for_each_device(ctx, n_dev, [&](int d) -> int32_t {
+        const int64_t q0 = n_q * d / n_dev, q1 = n_q * (d + 1) / n_dev, nq = q1 - q0;
+        if (nq == 0) return GAMS_CUDA_OK;
+        PerDevice &pd = ctx->devs[d];
+        DeviceGuard g(pd.device);
+        gams_cuda_count_plan *plan = nullptr;
+        int32_t rc = gams_cuda_count_plan_create(ctx, d, n_seg, iv_off, &plan);
+        if (rc) return rc;
+        std::unique_ptr<gams_cuda_count_plan, void (*)(gams_cuda_count_plan *)> guard(plan, gams_cuda_count_plan_destroy);
+        if ((rc = pd.scratch[0].reserve(std::max<uint64_t>(n_iv, 1) * 4))) return rc;
+        if ((rc = pd.scratch[1].reserve(std::max<uint64_t>(n_iv, 1) * 4))) return rc;
+        if ((rc = pd.scratch[2].reserve((uint64_t)nq * 4))) return rc;
+        if ((rc = pd.scratch[3].reserve((uint64_t)nq * 4))) return rc;
+        if ((rc = pd.scratch[4].reserve((uint64_t)nq * 4))) return rc;
+        if ((rc = pd.scratch[5].reserve((uint64_t)nq * 4))) return rc;
+        cudaStream_t st = pd.stream;
+        uint32_t *d_st = pd.scratch[0].as<uint32_t>(), *d_sp = pd.scratch[1].as<uint32_t>();
+        if (n_iv) {
+            CUDA_TRY(cudaMemcpyAsync(d_st, starts + iv_off[0], n_iv * 4, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(d_sp, stops + iv_off[0], n_iv * 4, cudaMemcpyHostToDevice, st));
+        }
+        CUDA_TRY(cudaMemcpyAsync(pd.scratch[2].p, q_seg + q0, (uint64_t)nq * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(pd.scratch[3].p, q_start + q0, (uint64_t)nq * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(pd.scratch[4].p, q_stop + q0, (uint64_t)nq * 4, cudaMemcpyHostToDevice, st));
+        if ((rc = launch_count_overlaps(plan, st, d_st, d_sp, nq, pd.scratch[2].as<int32_t>(),
+                                        pd.scratch[3].as<uint32_t>(), pd.scratch[4].as<uint32_t>(), 0,
+                                        pd.scratch[5].as<uint32_t>())))
+            return rc;
+        CUDA_TRY(cudaMemcpyAsync(out + q0, pd.scratch[5].p, (uint64_t)nq * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        return GAMS_CUDA_OK;
+    });
+}
+
+GAMS_API int32_t gams_cuda_locate_ctg(gams_cuda_ctx *ctx, int64_t n_chr, const uint32_t *ctg_start,
+                                      const uint32_t *ctg_stop, const uint64_t *chr_off, int64_t n_q,
+                                      const int32_t *q_chr, const uint32_t *q_start, const uint32_t *q_stop,
+                                      int32_t *out) {
+    ARG_CHECK(ctx && chr_off && n_chr >= 0 && n_q >= 0, "locate_ctg: bad argument");
+    if (n_q == 0) return GAMS_CUDA_OK;
+    ARG_CHECK(q_chr && q_start && q_stop && out, "locate_ctg: NULL query/output pointer");
+    ARG_CHECK(chr_off[0] == 0, "locate_ctg: chr_off[0] must be 0");
+    const uint64_t n_ctg = chr_off[n_chr];
+    ARG_CHECK((ctg_start && ctg_stop) || n_ctg == 0, "locate_ctg: NULL index pointer");
+    ARG_CHECK(n_ctg < (1ull << 31), "locate_ctg: too many ctgs");
+    std::vector<uint32_t> maxlen((size_t)std::max<int64_t>(n_chr, 1), 0);  // Lapper::new: max(stop - start)
+    for (int64_t c = 0; c < n_chr; ++c)
+        for (uint64_t k = chr_off[c]; k < chr_off[c + 1]; ++k)
+            if (ctg_stop[k] > ctg_start[k]) maxlen[c] = std::max(maxlen[c], ctg_stop[k] - ctg_start[k]);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    PerDevice &pd = ctx->devs[0];
+    DeviceGuard g(pd.device);
+    int32_t rc;
+    const uint64_t meta = std::max<uint64_t>(n_ctg, 1) * 8 + (uint64_t)(n_chr + 1) * 8 + (uint64_t)std::max<int64_t>(n_chr, 1) * 4;
+    if ((rc = pd.scratch[0].reserve(meta))) return rc;
+    if ((rc = pd.scratch[2].reserve((uint64_t)n_q * 4))) return rc;
+    if ((rc = pd.scratch[3].reserve((uint64_t)n_q * 4))) return rc;
+    if ((rc = pd.scratch[4].reserve((uint64_t)n_q * 4))) return rc;
+    if ((rc = pd.scratch[5].reserve((uint64_t)n_q * 4))) return rc;
+    cudaStream_t st = pd.stream;
+    uint8_t *m = pd.scratch[0].as<uint8_t>();
+    uint64_t *d_chr_off = reinterpret_cast<uint64_t *>(m);
+    uint32_t *d_cs = reinterpret_cast<uint32_t *>(m + (uint64_t)(n_chr + 1) * 8);
+    uint32_t *d_ce = d_cs + std::max<uint64_t>(n_ctg, 1);
+    uint32_t *d_ml = d_ce + std::max<uint64_t>(n_ctg, 1);
+    CUDA_TRY(cudaMemcpyAsync(d_chr_off, chr_off, (uint64_t)(n_chr + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (n_ctg) {
+        CUDA_TRY(cudaMemcpyAsync(d_cs, ctg_start, n_ctg * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d_ce, ctg_stop, n_ctg * 4, cudaMemcpyHostToDevice, st));
+    }
+    CUDA_TRY(cudaMemcpyAsync(d_ml, maxlen.data(), maxlen.size() * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(pd.scratch[2].p, q_chr, (uint64_t)n_q * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(pd.scratch[3].p, q_start, (uint64_t)n_q * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(pd.scratch[4].p, q_stop, (uint64_t)n_q * 4, cudaMemcpyHostToDevice, st));
+    if ((rc = launch_locate_ctg(st, n_chr, d_cs, d_ce, d_chr_off, d_ml, n_q, pd.scratch[2].as<int32_t>(),
+                                pd.scratch[3].as<uint32_t>(), pd.scratch[4].as<uint32_t>(), pd.scratch[5].as<int32_t>())))
+        return rc;
+    CUDA_TRY(cudaMemcpyAsync(out, pd.scratch[5].p, (uint64_t)n_q * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return GAMS_CUDA_OK;
+}
+
+// ============================================================================ GC of ranges / sw ==
+static int32_t upload_seq(PerDevice &pd, int64_t n_ctg, const uint8_t *seq_concat, const uint64_t *seq_off,
+                          uint8_t **d_seq, uint64_t **d_off) {
+    const uint64_t nb = seq_off[n_ctg] - seq_off[0];
+    int32_t rc;
+    if ((rc = pd.scratch[0].reserve(((nb + 15) & ~15ull) + 16))) return rc;
+    if ((rc = pd.scratch[6].reserve((uint64_t)(n_ctg + 1) * 8))) return rc;
+    std::vector<uint64_t> rel((size_t)n_ctg + 1);
+    for (int64_t c = 0; c <= n_ctg; ++c) {
+        if (c && seq_off[c] < seq_off[c - 1]) {
+            set_error("seq_off not monotone at %lld", (long long)c);
+            return GAMS_CUDA_EINVAL;
+        }
+        rel[c] = seq_off[c] - seq_off[0];
+    }
+    *d_seq = pd.scratch[0].as<uint8_t>();
+    *d_off = pd.scratch[6].as<uint64_t>();
+    if (nb) CUDA_TRY(cudaMemcpyAsync(*d_seq, seq_concat + seq_off[0], nb, cudaMemcpyHostToDevice, pd.stream));
+    CUDA_TRY(cudaMemcpyAsync(*d_off, rel.data(), (uint64_t)(n_ctg + 1) * 8, cudaMemcpyHostToDevice, pd.stream));
+    CUDA_TRY(cudaStreamSynchronize(pd.stream));  // rel goes out of scope
+    return GAMS_CUDA_OK;
+}
+
+GAMS_API int32_t gams_cuda_gc_ranges(gams_cuda_ctx *ctx, int64_t n_ctg, const uint8_t *seq_concat,
+                                     const uint64_t *seq_off, int64_t n_q, const uint32_t *q_ctg,
+                                     const uint32_t *q_from0, const uint32_t *q_to0_excl, uint32_t *gc_count) {
+    ARG_CHECK(ctx && seq_off && n_ctg >= 0 && n_q >= 0, "gc_ranges: bad argument");
+    if (n_q == 0) return GAMS_CUDA_OK;
+    ARG_CHECK(q_ctg && q_from0 && q_to0_excl && gc_count, "gc_ranges: NULL query/output pointer");
+    ARG_CHECK(seq_concat || seq_off[n_ctg] == seq_off[0], "gc_ranges: seq_concat is NULL");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    PerDevice &pd = ctx->devs[0];
+    DeviceGuard g(pd.device);
+    uint8_t *d_seq;
+    uint64_t *d_off;
+    int32_t rc = upload_seq(pd, n_ctg, seq_concat, seq_off, &d_seq, &d_off);
+    if (rc) return rc;
+    for (int i = 2; i <= 5; ++i)
+        if ((rc = pd.scratch[i].reserve((uint64_t)n_q * 4))) return rc;
+    cudaStream_t st = pd.stream;
+    CUDA_TRY(cudaMemcpyAsync(pd.scratch[2].p, q_ctg, (uint64_t)n_q * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(pd.scratch[3].p, q_from0, (uint64_t)n_q * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(pd.scratch[4].p, q_to0_excl, (uint64_t)n_q * 4, cudaMemcpyHostToDevice, st));
+    if ((rc = launch_gc_ranges(st, d_seq, d_off, n_ctg, n_q, pd.scratch[2].as<uint32_t>(), pd.scratch[3].as<uint32_t>(),
+                               pd.scratch[4].as<uint32_t>(), pd.scratch[5].as<uint32_t>())))
+        return rc;
+    CUDA_TRY(cudaMemcpyAsync(gc_count, pd.scratch[5].p, (uint64_t)n_q * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return GAMS_CUDA_OK;
+}
+
+GAMS_API int32_t gams_cuda_sw_batch(gams_cuda_ctx *ctx, int64_t n_ctg, const uint8_t *seq_concat,
+                                    const uint64_t *seq_off, const int32_t *ctg_chr_start, int64_t n_feat,
+                                    const uint32_t *f_ctg, const int32_t *f_start, const int32_t *f_end, int32_t size,
+                                    int32_t max, int32_t resize, uint64_t *row_off, int32_t *w_start, int32_t *w_end,
+                                    int8_t *w_type, int32_t *w_dist, float *gc, float *gc_mean, float *gc_stddev,
+                                    float *gc_cv) {
+    ARG_CHECK(ctx && seq_off && ctg_chr_start && row_off && n_ctg >= 0 && n_feat >= 0, "sw_batch: bad argument");
+    ARG_CHECK(size > 0 && max >= 0 && resize > 0, "sw_batch: size/resize must be positive and max >= 0");
+    row_off[0] = 0;
+    if (n_feat == 0) return GAMS_CUDA_OK;
+    ARG_CHECK(f_ctg && f_start && f_end && w_start && w_end && w_type && w_dist && gc && gc_mean && gc_stddev && gc_cv,
+              "sw_batch: NULL feature/output pointer");
+    // Row counts are pure coordinate arithmetic (window.rs:3-56): 1 + #L + #R.
+    for (int64_t f = 0; f < n_feat; ++f) {
+        const uint32_t c = f_ctg[f];
+        ARG_CHECK((int64_t)c < n_ctg, "sw_batch: feature %lld names ctg %u of %lld", (long long)f, c, (long long)n_ctg);
+        const int64_t psize = (int64_t)(seq_off[c + 1] - seq_off[c]);
+        const int64_t s = (int64_t)f_start[f] - ctg_chr_start[c] + 1, e = (int64_t)f_end[f] - ctg_chr_start[c] + 1;
+        ARG_CHECK(s >= 1 && e >= s && e <= psize, "sw_batch: feature %lld (%d-%d) is not inside its ctg", (long long)f,
+                  f_start[f], f_end[f]);
+        const int64_t half = (e - s + 1) / 2;
+        const int64_t ml = half == 0 ? s : s + half - 1, mr = half == 0 ? s : s + half;
+        const int64_t ms = std::max<int64_t>(ml - size / 2 + 1, 1), me = std::min<int64_t>(mr + size / 2 - 1, psize);
+        const int64_t nl = std::min<int64_t>(max, (ms - 1) / size), nr = std::min<int64_t>(max, (psize - me) / size);
+        row_off[f + 1] = row_off[f] + 1 + (uint64_t)nl + (uint64_t)nr;
+    }
+    const uint64_t n_rows = row_off[n_feat];
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    PerDevice &pd = ctx->devs[0];
+    DeviceGuard g(pd.device);
+    uint8_t *d_seq;
+    uint64_t *d_off;
+    int32_t rc = upload_seq(pd, n_ctg, seq_concat, seq_off, &d_seq, &d_off);
+    if (rc) return rc;
+    // inputs: chr_start | f_ctg | f_start | f_end | row_off ; outputs: 4 x i32/f32 x 2 + i8
+    const uint64_t in_bytes = (uint64_t)n_ctg * 4 + (uint64_t)n_feat * 12 + (uint64_t)(n_feat + 1) * 8 + 64;
+    if ((rc = pd.scratch[1].reserve(in_bytes))) return rc;
+    if ((rc = pd.scratch[2].reserve(n_rows * 29 + 64))) return rc;
+    cudaStream_t st = pd.stream;
+    uint8_t *ib = pd.scratch[1].as<uint8_t>();
+    uint64_t *d_row_off = reinterpret_cast<uint64_t *>(ib);
+    int32_t *d_chr_start = reinterpret_cast<int32_t *>(ib + (uint64_t)(n_feat + 1) * 8);
+    uint32_t *d_f_ctg = reinterpret_cast<uint32_t *>(d_chr_start + n_ctg);
+    int32_t *d_f_start = reinterpret_cast<int32_t *>(d_f_ctg + n_feat);
+    int32_t *d_f_end = d_f_start + n_feat;
+    CUDA_TRY(cudaMemcpyAsync(d_row_off, row_off, (uint64_t)(n_feat + 1) * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_chr_start, ctg_chr_start, (uint64_t)n_ctg * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_f_ctg, f_ctg, (uint64_t)n_feat * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_f_start, f_start, (uint64_t)n_feat * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_f_end, f_end, (uint64_t)n_feat * 4, cudaMemcpyHostToDevice, st));
+    uint8_t *ob = pd.scratch[2].as<uint8_t>();
+    int32_t *d_ws = reinterpret_cast<int32_t *>(ob), *d_we = d_ws + n_rows, *d_wd = d_we + n_rows;
+    float *d_g = reinterpret_cast<float *>(d_wd + n_rows), *d_m = d_g + n_rows, *d_s = d_m + n_rows, *d_c = d_s + n_rows;
+    int8_t *d_wt = reinterpret_cast<int8_t *>(d_c + n_rows);
+    if ((rc = launch_sw_rows(st, d_seq, d_off, d_chr_start, n_feat, d_f_ctg, d_f_start, d_f_end, size, max, resize,
+                             d_row_off, n_rows, d_ws, d_we, d_wt, d_wd, d_g, d_m, d_s, d_c)))
+        return rc;
+    CUDA_TRY(cudaMemcpyAsync(w_start, d_ws, n_rows * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(w_end, d_we, n_rows * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(w_dist, d_wd, n_rows * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(gc, d_g, n_rows * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(gc_mean, d_m, n_rows * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(gc_stddev, d_s, n_rows * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(gc_cv, d_c, n_rows * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(w_type, d_wt, n_rows, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return GAMS_CUDA_OK;
+}

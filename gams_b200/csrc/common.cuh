@@ -1,0 +1,153 @@
+// common.cuh — shared declarations of libgams_cuda.so (internal; the public surface is include/gams_cuda.h)
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "../../include/gams_cuda.h"
+
+#define GAMS_API extern "C" __attribute__((visibility("default")))
+
+namespace gams {
+
+// ---- error plumbing -----------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+int32_t cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define CUDA_TRY(expr)                                                       \
+    do {                                                                     \
+        cudaError_t _e = (expr);                                             \
+        if (_e != cudaSuccess) return ::gams::cuda_fail(_e, #expr, __FILE__, __LINE__); \
+    } while (0)
+
+#define ARG_CHECK(cond, ...)            \
+    do {                                \
+        if (!(cond)) {                  \
+            ::gams::set_error(__VA_ARGS__); \
+            return GAMS_CUDA_EINVAL;    \
+        }                               \
+    } while (0)
+
+// ---- small RAII helpers ---------------------------------------------------------------------
+struct DevBuf {  // grow-only device scratch
+    void *p = nullptr;
+    size_t cap = 0;
+    int32_t reserve(size_t bytes);
+    void release();
+    template <class T> T *as() const { return static_cast<T *>(p); }
+};
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// ---- tile descriptors ---------------------------------------------------------------------------
+struct TileDesc {
+    uint32_t item;   // ctg (GC / z-score tiles) index
+    uint32_t first;  // first window of the tile inside the ctg
+};
+
+// Geometry of Kernel A (gc_window.cu)
+constexpr int GC_THREADS = 256;
+struct GcGeom {
+    int k = 0;            // 16-byte chunks per thread (4 or 8); 0 = generic kernel (huge windows)
+    int wt = 0;           // windows per tile
+    uint64_t n_tiles = 0;
+};
+
+// Geometry of Kernel B1 (zscore.cu)
+constexpr int ZS_R = 8;                       // windows per thread
+constexpr int ZS_THREADS = 128;
+constexpr int ZS_TILE = ZS_R * ZS_THREADS;    // windows per tile
+
+// A batch of series (one per ctg) resident on one device: offsets + z-score tiles.
+struct SeriesLayout {
+    int64_t n_series = 0;
+    uint64_t total = 0;
+    uint64_t min_len = 0;
+    uint64_t *d_off = nullptr;       // n_series+1
+    TileDesc *d_ztiles = nullptr;    // z-score tiles
+    uint64_t n_ztiles = 0;
+    int32_t build(const uint64_t *h_off, int64_t n, cudaStream_t st);
+    void release();
+};
+
+struct PerDevice {
+    int device = -1;
+    cudaStream_t stream = nullptr;   // library-owned stream for the host API
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    DevBuf scratch[8];
+};
+
+}  // namespace gams
+
+struct gams_cuda_ctx {
+    std::vector<gams::PerDevice> devs;
+    std::mutex mu;
+};
+
+struct gams_cuda_wave_plan {
+    gams_cuda_ctx *ctx = nullptr;
+    int dev_index = 0;
+    int device = 0;
+    int64_t n_ctg = 0;
+    int32_t size = 0, step = 0;
+    uint64_t lag = 0;
+    uint64_t total_bases = 0;
+    std::vector<uint64_t> h_seq_off, h_win_off;
+    uint64_t *d_seq_off = nullptr;
+    gams::SeriesLayout win;          // window offsets + z-score tiles
+    gams::GcGeom geom;
+    gams::TileDesc *d_gtiles = nullptr;
+    float *d_gc_tab = nullptr;       // (float)c / (float)size for c = 0..size (host-computed IEEE divide)
+    uint64_t launches = 0;
+};
+
+struct gams_cuda_count_plan {
+    gams_cuda_ctx *ctx = nullptr;
+    int dev_index = 0;
+    int device = 0;
+    int64_t n_seg = 0;
+    uint64_t total_iv = 0;
+    uint64_t max_seg = 0;
+    std::vector<uint64_t> h_iv_off;
+    uint64_t *d_iv_off = nullptr;
+    gams::DevBuf tmp[6];
+    uint64_t launches = 0;
+};
+
+namespace gams {
+// kernel launchers (each returns 0 or a GAMS_CUDA_E* code; all asynchronous on `st`)
+int32_t launch_gc_windows(const gams_cuda_wave_plan *p, cudaStream_t st, const uint8_t *d_seq,
+                          uint32_t *d_cnt, float *d_gc, uint64_t *launches);
+int32_t launch_zscore(const SeriesLayout &L, cudaStream_t st, const float *d_x, uint64_t lag, float threshold,
+                      float influence, float *d_filtered, int8_t *d_signal, uint64_t *launches);
+int32_t launch_count_overlaps(gams_cuda_count_plan *p, cudaStream_t st, const uint32_t *d_starts,
+                              const uint32_t *d_stops, int64_t n_q, const int32_t *d_q_seg,
+                              const uint32_t *d_q_start, const uint32_t *d_q_stop, int32_t grouped,
+                              uint32_t *d_out);
+int32_t launch_locate_ctg(cudaStream_t st, int64_t n_chr, const uint32_t *d_ctg_start, const uint32_t *d_ctg_stop,
+                          const uint64_t *d_chr_off, const uint32_t *d_chr_maxlen, int64_t n_q,
+                          const int32_t *d_q_chr, const uint32_t *d_q_start, const uint32_t *d_q_stop, int32_t *d_out);
+int32_t launch_gc_ranges(cudaStream_t st, const uint8_t *d_seq, const uint64_t *d_seq_off, int64_t n_ctg, int64_t n_q,
+                         const uint32_t *d_q_ctg, const uint32_t *d_q_from, const uint32_t *d_q_to, uint32_t *d_cnt);
+int32_t launch_sw_rows(cudaStream_t st, const uint8_t *d_seq, const uint64_t *d_seq_off, const int32_t *d_chr_start,
+                       int64_t n_feat, const uint32_t *d_f_ctg, const int32_t *d_f_start, const int32_t *d_f_end,
+                       int32_t size, int32_t max, int32_t resize, const uint64_t *d_row_off, uint64_t n_rows,
+                       int32_t *d_w_start, int32_t *d_w_end, int8_t *d_w_type, int32_t *d_w_dist, float *d_gc,
+                       float *d_mean, float *d_sd, float *d_cv);
+GcGeom plan_gc_geometry(int32_t size, int32_t step);
+}  // namespace gams

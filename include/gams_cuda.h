@@ -1,0 +1,199 @@
+/*
+ * gams_cuda.h — C ABI of libgams_cuda.so, the B200 (sm_100a) drop-in for the data-parallel
+ * hot path of wang-q/gams.  Plain pointers and sizes only; no C++/torch types.
+ *
+ * Every entry point names the reference interface it replaces (paths relative to the
+ * reference root).  The Rust binding a gams maintainer would add is in INTEGRATION.md and
+ * integration/gams-cuda-sys/.
+ *
+ * Conventions
+ *  - return value: 0 = ok, negative = error (GAMS_CUDA_E*); gams_cuda_last_error() gives text
+ *    (thread-local).  The library never aborts or throws across this boundary.
+ *  - "host API" functions take HOST pointers owned by the caller; outputs are caller-allocated
+ *    and fully overwritten; inputs are never modified.
+ *  - "device API" functions (suffix _dev) take DEVICE pointers that live on the plan's device
+ *    and a cudaStream_t passed as void*; they only enqueue work (no sync).
+ *  - coordinates: a ctg is a byte string; window k of a ctg covers 0-based bytes
+ *    [k*step, k*step+size) == 1-based chr positions chr_start+k*step .. chr_start+k*step+size-1
+ *    (src/libs/window.rs:78-94, src/cmd_gams/wave.rs:146-150).
+ *  - there is NO CPU fallback: every compute entry point fails with GAMS_CUDA_ENODEV/ECUDA
+ *    when no sm_100 device is usable.
+ */
+#ifndef GAMS_CUDA_H
+#define GAMS_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GAMS_CUDA_OK 0
+#define GAMS_CUDA_EINVAL (-1) /* bad argument (null pointer, size/step <= 0, lag == 0, ...)        */
+#define GAMS_CUDA_ECUDA (-2)  /* a CUDA runtime call or kernel failed; see gams_cuda_last_error()   */
+#define GAMS_CUDA_ENOMEM (-3) /* host or device allocation failed                                   */
+#define GAMS_CUDA_ELAG (-4)   /* a ctg has fewer windows than lag: the reference panics here        */
+                              /* (src/libs/stat.rs:30 indexes data[0..lag])                          */
+#define GAMS_CUDA_ENODEV (-5) /* no usable CUDA device                                              */
+#define GAMS_CUDA_EPARSE (-6) /* malformed blob / text passed to a host-side helper                 */
+
+typedef struct gams_cuda_ctx gams_cuda_ctx;
+typedef struct gams_cuda_wave_plan gams_cuda_wave_plan;
+typedef struct gams_cuda_count_plan gams_cuda_count_plan;
+
+/* ---------------------------------------------------------------- lifecycle ---------------- */
+int32_t gams_cuda_version(void); /* 10000*major + 100*minor + patch */
+const char *gams_cuda_last_error(void);
+int32_t gams_cuda_device_count(void); /* >= 0, or negative error */
+
+/* device_ids == NULL or n_dev <= 0: use every visible device.  One ctx may be shared by threads
+ * (calls on the same ctx serialise on an internal mutex), cf. the per-worker Conn of
+ * src/cmd_gams/wave.rs:288-299. */
+int32_t gams_cuda_create(const int32_t *device_ids, int32_t n_dev, gams_cuda_ctx **out);
+void gams_cuda_destroy(gams_cuda_ctx *ctx);
+int32_t gams_cuda_ctx_num_devices(const gams_cuda_ctx *ctx);
+
+/* Page-locked host buffers so the host API's copies run at PCIe speed (the analogue of the
+ * Vec<u8> that Conn::get_seq fills, src/libs/redis.rs:142-146).  Plain malloc'd memory works
+ * too, only slower. */
+void *gams_cuda_host_alloc(size_t bytes);
+void gams_cuda_host_free(void *p);
+
+/* ---------------------------------------------------------------- window arithmetic -------- */
+/* gams::sliding, src/libs/window.rs:78-94: number of windows on a ctg of ctg_len bases.
+ * Returns -1 for size <= 0 or step <= 0. */
+int64_t gams_cuda_wave_nwin(int64_t ctg_len, int32_t size, int32_t step);
+/* win_off[0] = 0, win_off[c+1] = win_off[c] + nwin(len_c).  seq_off has n_ctg+1 entries. */
+int32_t gams_cuda_wave_win_offsets(int64_t n_ctg, const uint64_t *seq_off, int32_t size, int32_t step,
+                                   uint64_t *win_off);
+/* Contiguous, byte-balanced partition of ctgs over n_part shards (work shards by ctg,
+ * no exchange).  part_off has n_part+1 entries: shard p owns ctgs [part_off[p], part_off[p+1]). */
+int32_t gams_cuda_partition(int64_t n_item, const uint64_t *item_off, int32_t n_part, int64_t *part_off);
+
+/* ---------------------------------------------------------------- GC-wave: host API -------- */
+/* Replaces the body of wave::proc_ctg up to the signals, src/cmd_gams/wave.rs:138-155:
+ *   gams::sliding (window.rs:78-94) + bio gc_content per window (wave.rs:143-153)
+ *   + gams::thresholding_algo (stat.rs:16-56), for a whole batch of ctgs at once.
+ *  seq_concat : all ctg sequences back to back (ASCII, mixed case, any byte)
+ *  seq_off    : n_ctg+1 byte offsets into seq_concat
+ *  win_off    : n_ctg+1 window offsets from gams_cuda_wave_win_offsets
+ *  gc_count   : optional (may be NULL) #bytes in {c,g,C,G} per window          [win_off[n_ctg]]
+ *  gc         : count as f32 / size as f32, one IEEE divide                      [win_off[n_ctg]]
+ *  signal     : optional (NULL = GC only) -1/0/+1 per window, 0 for the first lag windows
+ * Sharded over all devices of ctx by ctg; no inter-device exchange.
+ * GAMS_CUDA_ELAG if signal != NULL and some ctg has fewer than lag windows. */
+int32_t gams_cuda_wave_batch(gams_cuda_ctx *ctx, int64_t n_ctg, const uint8_t *seq_concat,
+                             const uint64_t *seq_off, int32_t size, int32_t step, uint64_t lag,
+                             float threshold, float influence, const uint64_t *win_off,
+                             uint32_t *gc_count, float *gc, int8_t *signal);
+
+/* gams::thresholding_algo on caller-supplied series (stat.rs:16-56), batched: series s is
+ * data[off[s] .. off[s+1]).  Same semantics as the signal part of gams_cuda_wave_batch. */
+int32_t gams_cuda_thresholding_batch(gams_cuda_ctx *ctx, int64_t n_series, const float *data,
+                                     const uint64_t *off, uint64_t lag, float threshold, float influence,
+                                     int8_t *signal);
+
+/* ---------------------------------------------------------------- GC-wave: device API ------ */
+/* A plan fixes the ctg layout (seq_off), the window geometry and lag on one device of ctx and
+ * owns the small device-side tables; the bulk arrays stay with the caller. */
+int32_t gams_cuda_wave_plan_create(gams_cuda_ctx *ctx, int32_t dev_index, int64_t n_ctg,
+                                   const uint64_t *seq_off /* host */, int32_t size, int32_t step,
+                                   uint64_t lag, gams_cuda_wave_plan **out);
+void gams_cuda_wave_plan_destroy(gams_cuda_wave_plan *plan);
+uint64_t gams_cuda_wave_plan_total_windows(const gams_cuda_wave_plan *plan);
+uint64_t gams_cuda_wave_plan_total_bases(const gams_cuda_wave_plan *plan);
+/* bytes the caller must make readable behind d_seq (total bases rounded up for 16-byte loads) */
+uint64_t gams_cuda_wave_plan_seq_capacity(const gams_cuda_wave_plan *plan);
+/* Kernel A only: d_seq -> d_gc_count (optional) / d_gc. */
+int32_t gams_cuda_wave_gc_dev(gams_cuda_wave_plan *plan, void *stream, const uint8_t *d_seq,
+                              uint32_t *d_gc_count, float *d_gc);
+/* Kernel B only: d_gc -> d_signal.  d_filtered: scratch of total_windows floats, needed only
+ * when influence != 1 (may be NULL otherwise). */
+int32_t gams_cuda_wave_signal_dev(gams_cuda_wave_plan *plan, void *stream, const float *d_gc,
+                                  float threshold, float influence, float *d_filtered, int8_t *d_signal);
+/* Kernel launches issued by the plan's _dev calls since creation (bench.py's gpu_launches). */
+uint64_t gams_cuda_wave_plan_launches(const gams_cuda_wave_plan *plan);
+
+/* ---------------------------------------------------------------- GC of ranges / sw -------- */
+/* Replaces gams::cache_gc_content without the rounding, src/libs/utils.rs:141-162 (bio
+ * gc_content of an arbitrary sub-range of a ctg): query q covers 0-based bytes
+ * [q_from0[q], q_to0_excl[q]) of ctg q_ctg[q].  gc_count[q] = #bytes in {c,g,C,G}. */
+int32_t gams_cuda_gc_ranges(gams_cuda_ctx *ctx, int64_t n_ctg, const uint8_t *seq_concat,
+                            const uint64_t *seq_off, int64_t n_q, const uint32_t *q_ctg,
+                            const uint32_t *q_from0, const uint32_t *q_to0_excl, uint32_t *gc_count);
+
+/* Replaces the per-feature body of sw::proc_ctg, src/cmd_gams/sw.rs:141-191 (action "gc"):
+ * gams::center_sw (window.rs:3-56) windows around each feature, per window
+ * cache_gc_content (utils.rs:141-162) and cache_gc_stat of the center_resize'd flank
+ * (utils.rs:189-213, window.rs:96-124), all rounded to 4 dp as the reference does.
+ *  ctg_chr_start : n_ctg 1-based chr_start of each ctg (chr_end = chr_start + len - 1)
+ *  f_ctg/f_start/f_end : feature's ctg and 1-based inclusive chr range
+ *  row_off : n_feat+1, out; feature f owns rows [row_off[f], row_off[f+1]) (at most 1+2*max each)
+ *  out arrays sized n_feat*(1+2*max): w_start/w_end (chr coords), w_type (0=M 1=L 2=R), w_dist,
+ *  gc, gc_mean, gc_stddev, gc_cv.  Rows are compacted to the front (row_off indexes them). */
+int32_t gams_cuda_sw_batch(gams_cuda_ctx *ctx, int64_t n_ctg, const uint8_t *seq_concat,
+                           const uint64_t *seq_off, const int32_t *ctg_chr_start, int64_t n_feat,
+                           const uint32_t *f_ctg, const int32_t *f_start, const int32_t *f_end,
+                           int32_t size, int32_t max, int32_t resize, uint64_t *row_off,
+                           int32_t *w_start, int32_t *w_end, int8_t *w_type, int32_t *w_dist,
+                           float *gc, float *gc_mean, float *gc_stddev, float *gc_cv);
+
+/* ---------------------------------------------------------------- overlap counting --------- */
+/* Replaces the count loop of locate::execute, src/cmd_gams/locate.rs:111-141, i.e.
+ * gams::count_rg (src/libs/utils.rs:24-36) -> rust_lapper::Lapper::count(start, stop):
+ *   out[q] = lower_bound(starts_seg, q_stop[q]) - lower_bound(stops_seg, q_start[q] + 1)
+ * where lower_bound(a, key) = #elements < key.  starts/stops are the sorted endpoint arrays that
+ * sit verbatim inside the idx:rg:{ctg} bincode blob (src/libs/redis.rs:276-305); segment s (one
+ * ctg's index) is [iv_off[s], iv_off[s+1]).  gams passes (rg.start, rg.end) — the inclusive end
+ * as Lapper's exclusive stop (utils.rs:35); callers pass the same values here.
+ * q_seg[q] < 0 or >= n_seg -> out[q] = 0 ("not found in idx", utils.rs:29-32).
+ * Queries may come in any order; results are in query order. */
+int32_t gams_cuda_count_overlaps(gams_cuda_ctx *ctx, int64_t n_seg, const uint32_t *starts,
+                                 const uint32_t *stops, const uint64_t *iv_off, int64_t n_q,
+                                 const int32_t *q_seg, const uint32_t *q_start, const uint32_t *q_stop,
+                                 uint32_t *out);
+
+/* Device API: the index stays resident in HBM across query batches (as the lapper BTreeMap stays
+ * resident across the loop of locate.rs:104-141). */
+int32_t gams_cuda_count_plan_create(gams_cuda_ctx *ctx, int32_t dev_index, int64_t n_seg,
+                                    const uint64_t *iv_off /* host */, gams_cuda_count_plan **out);
+void gams_cuda_count_plan_destroy(gams_cuda_count_plan *plan);
+/* d_starts/d_stops: device copies of the concatenated endpoint arrays.  grouped != 0 promises
+ * q_seg is non-decreasing (queries grouped by ctg, the order read_range's BTreeMap yields,
+ * utils.rs:39-79); grouped == 0 accepts any order. */
+int32_t gams_cuda_count_overlaps_dev(gams_cuda_count_plan *plan, void *stream, const uint32_t *d_starts,
+                                     const uint32_t *d_stops, int64_t n_q, const int32_t *d_q_seg,
+                                     const uint32_t *d_q_start, const uint32_t *d_q_stop,
+                                     int32_t grouped, uint32_t *d_out);
+uint64_t gams_cuda_count_plan_launches(const gams_cuda_count_plan *plan);
+
+/* gams::find_one_idx (utils.rs:7-22) -> Lapper::find(start, stop).next() on the idx:ctg:{chr}
+ * index: ctg intervals [chr_start, chr_end+1) sorted by start within each chromosome segment.
+ * out[q] = global index of the first ctg (in start order) with ctg_start < q_stop && ctg_stop >
+ * q_start, or -1 (unknown chr or no hit: the query is skipped, locate.rs:118-122). */
+int32_t gams_cuda_locate_ctg(gams_cuda_ctx *ctx, int64_t n_chr, const uint32_t *ctg_start,
+                             const uint32_t *ctg_stop, const uint64_t *chr_off, int64_t n_q,
+                             const int32_t *q_chr, const uint32_t *q_start, const uint32_t *q_stop,
+                             int32_t *out);
+
+/* ---------------------------------------------------------------- host-side format helpers -- */
+/* Zero-copy view of the sorted endpoint arrays inside a bincode-serialised
+ * rust_lapper::Lapper<u32,String> (src/libs/redis.rs:299-300, 316-317).  starts and stops point
+ * into blob (little-endian u32, possibly unaligned for 4-byte access on exotic hosts). */
+int32_t gams_cuda_lapper_blob_view(const uint8_t *blob, size_t blob_len, uint64_t *n_iv,
+                                   const uint8_t **starts, const uint8_t **stops, uint32_t *max_len);
+
+/* `gams wave` text for one ctg, src/cmd_gams/wave.rs:157-212 incl. merge_ints (wave.rs:217-252):
+ * given gc/signal of the ctg's n windows, append the lines wave prints (no header) to a
+ * malloc'd, NUL-terminated buffer returned in *text (free with gams_cuda_free).  is_signal != 0
+ * selects the --signal form (every window, unmerged). */
+int32_t gams_cuda_wave_text(const char *chr_id, int32_t chr_start, int32_t size, int32_t step, int64_t n,
+                            const float *gc, const int8_t *signal, float coverage, int32_t is_signal,
+                            char **text, size_t *text_len);
+void gams_cuda_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GAMS_CUDA_H */

@@ -1,0 +1,283 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle.  Needs a B200: -m gpu.
+
+Bar: bit-exact for GC counts, GC fractions (identical f32), signals, overlap counts, window
+coordinates.  (north_star's "peak signals identical except |z - threshold| < 1e-9" is met with
+zero exceptions because the kernels replay the reference's f32 evaluation order.)
+"""
+import numpy as np
+import pytest
+
+from conftest import cut_ctgs
+from gams_b200 import api, synth
+from test_oracle_golden import KAT_INPUT, KAT_SIGNALS
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = api.Context([0])
+    yield c
+    c.close()
+
+
+def _eq(name, got, ref):
+    if not np.array_equal(got, ref, equal_nan=True):
+        bad = np.flatnonzero(~((got == ref) | (np.isnan(got.astype(np.float64)) & np.isnan(ref.astype(np.float64)))))
+        raise AssertionError(f"{name}: {bad.size} of {ref.size} differ; first at {bad[:8].tolist()} got {got[bad[:8]].tolist()} ref {ref[bad[:8]].tolist()}")
+
+
+def _check_wave(ctx, orc, seqs, size, step, lag, thr, infl, signal=True):
+    cat, off = orc.pack_ctgs(seqs)
+    woff, cnt, gc, sig = api.wave_batch(ctx, cat, off, size, step, lag, thr, infl, want_signal=signal)
+    rwoff, rcnt, rgc, rsig = orc.wave_batch(cat, off, size, step, lag, thr, infl, threads=8, want_signal=signal)
+    _eq("win_off", woff, rwoff)
+    _eq(f"gc_count[{size}/{step}]", cnt, rcnt)
+    _eq(f"gc[{size}/{step}]", gc.view(np.uint32), rgc.view(np.uint32))
+    if signal:
+        _eq(f"signal[{size}/{step} lag {lag} thr {thr} infl {infl}]", sig, rsig)
+    return woff, cnt, gc, sig
+
+
+# ------------------------------------------------------------------------------------------------ wave
+def test_wave_fixture_is_byte_identical_to_I_peaks_tsv(ctx, orc, s288c):
+    """BASELINE config 1 on the GPU: README.md:155-170 → tests/S288c/I.peaks.tsv."""
+    ctgs = cut_ctgs(orc, s288c, 500000)
+    woff, cnt, gc, sig = _check_wave(ctx, orc, [c[4] for c in ctgs], 100, 10, 100, 3.0, 1.0)
+    i = [k for k, c in enumerate(ctgs) if c[1] == "I"][0]
+    a, b = int(woff[i]), int(woff[i + 1])
+    text = orc.WAVE_HEADER + api.wave_text("I", 1, 100, 10, gc[a:b], sig[a:b], 0.2)
+    assert text.encode() == bytes(s288c["peaks_tsv"])
+
+
+def test_wave_fixture_piece_100000(ctx, orc, s288c):
+    """tests/cli.rs:332-364: 116 stdout lines with the two pinned substrings."""
+    ctgs = [c for c in cut_ctgs(orc, s288c, 100000) if c[1] == "I"]
+    woff, cnt, gc, sig = _check_wave(ctx, orc, [c[4] for c in ctgs], 100, 10, 100, 3.0, 1.0)
+    text = orc.WAVE_HEADER + "".join(
+        api.wave_text(c[1], c[2], 100, 10, gc[int(woff[k]):int(woff[k + 1])], sig[int(woff[k]):int(woff[k + 1])], 0.2)
+        for k, c in enumerate(ctgs))
+    assert len(text.splitlines()) == 116 and "I:7551-7650\t" in text and "I(+):11551-11740\t" in text
+
+
+@pytest.mark.parametrize("size,step,lag", [
+    (100, 10, 100), (100, 20, 50), (100, 5, 200), (97, 13, 31), (1, 1, 100), (16, 16, 8), (15, 17, 7),
+    (500, 500, 10), (33, 64, 3), (1000, 7, 100), (9000, 1000, 5), (20000, 5000, 2), (40000, 10000, 2),
+])
+def test_wave_synthetic_geometries(ctx, orc, size, step, lag):
+    """Ragged ctgs (lengths not multiples of 16, one exactly `size` long... ), lowercase, N runs."""
+    g = synth.genome(1_300_000, seed=size * 131 + step)
+    need = size + (lag + 2) * step
+    cuts = [0, need + 17, 2 * need + 17 + 40_001, 700_003, 700_003 + need + lag * step, 1_300_000]
+    cuts = sorted(set(min(c, 1_300_000) for c in cuts))
+    seqs = [g[a:b] for a, b in zip(cuts[:-1], cuts[1:]) if (b - a - size) // step + 1 >= lag]
+    assert len(seqs) >= 2
+    for infl in (1.0, 0.3):
+        _check_wave(ctx, orc, seqs, size, step, lag, 2.5, infl)
+
+
+def test_wave_degenerate_constant_gc(ctx, orc):
+    """Constant-GC stretches: mean of 100 copies of 0.18f is 0.18000013f and sd is pure rounding noise
+     — the outcome is decided by summation order, so this pins the exact order."""
+    unit = np.frombuffer(b"GC" + b"A" * 48 + b"G" * 7 + b"T" * 43, dtype=np.uint8)  # 9 GC per 100 -> varying per phase
+    flat = np.tile(np.frombuffer(b"ACATTTTTAT" * 5 + b"GCGCGCGCGATATATATATATATATATATATATATATATATATATATATA", dtype=np.uint8), 3000)
+    per = np.tile(unit, 3000)
+    mix = np.concatenate([flat[:120_000], synth.genome(50_000, seed=5), per[:130_000], np.full(30_000, ord("N"), np.uint8),
+                          np.tile(np.frombuffer(b"AC", dtype=np.uint8), 40_000)])
+    for thr in (3.0, 1.0, 0.0):
+        for infl in (1.0, 0.5, 0.0):
+            _check_wave(ctx, orc, [mix, flat[:77_777], per[:50_001]], 100, 10, 100, thr, infl)
+
+
+def test_wave_gc_only_and_empty_ctgs(ctx, orc):
+    """ctgs shorter than one window yield zero windows; with signals requested that is ELAG
+    (the reference panics at stat.rs:30), without them it is fine."""
+    g = synth.genome(50_000, seed=9)
+    seqs = [g[:99], g[99:30_000], g[30_000:30_000], g[30_000:]]
+    _check_wave(ctx, orc, seqs, 100, 10, 100, 3.0, 1.0, signal=False)
+    cat, off = orc.pack_ctgs(seqs)
+    with pytest.raises(api.GamsCudaError) as e:
+        api.wave_batch(ctx, cat, off, 100, 10, 100, 3.0, 1.0)
+    assert e.value.code == -4
+    with pytest.raises(api.GamsCudaError) as e:
+        api.wave_batch(ctx, cat, off, 100, 10, 0, 3.0, 1.0)
+    assert e.value.code == -1
+    woff, cnt, gc, sig = api.wave_batch(ctx, np.zeros(0, np.uint8), np.zeros(1, np.uint64))
+    assert gc.size == 0
+
+
+def test_wave_exactly_lag_windows(ctx, orc):
+    g = synth.genome(5000, seed=10)
+    _check_wave(ctx, orc, [g[:100 + 99 * 10], g[:100 + 100 * 10], g[:100 + 101 * 10]], 100, 10, 100, 3.0, 1.0)
+    _check_wave(ctx, orc, [g[:100 + 99 * 10], g[:100 + 100 * 10], g[:100 + 101 * 10]], 100, 10, 100, 3.0, 0.0)
+
+
+def test_wave_non_ascii_bytes(ctx, orc):
+    """Any byte value is legal input; only c g C G count (bio gc_content)."""
+    rng = np.random.default_rng(12)
+    g = rng.integers(0, 256, 400_000, dtype=np.uint8)
+    _check_wave(ctx, orc, [g[:123_457], g[123_457:]], 100, 10, 100, 3.0, 1.0)
+
+
+# ------------------------------------------------------------------------------------ thresholding
+def test_thresholding_kat(ctx):
+    """src/libs/stat.rs:58-81."""
+    assert api.thresholding_algo(ctx, KAT_INPUT, 30, 5.0, 0.0).tolist() == KAT_SIGNALS
+
+
+@pytest.mark.parametrize("lag", [1, 2, 3, 7, 8, 9, 30, 100, 257])
+@pytest.mark.parametrize("infl", [1.0, 0.0, 0.5])
+def test_thresholding_random_series(ctx, orc, lag, infl):
+    rng = np.random.default_rng(lag * 7 + int(infl * 10))
+    series = [rng.normal(1.0, 0.1, n).astype(np.float32) for n in (lag, lag + 1, lag + 2, 1000, 4097, 2048 + lag)]
+    for s in series:
+        s[rng.integers(0, s.size, max(1, s.size // 50))] += rng.normal(0, 2, max(1, s.size // 50)).astype(np.float32)
+    data = np.concatenate(series)
+    off = np.concatenate(([0], np.cumsum([s.size for s in series]))).astype(np.uint64)
+    for thr in (3.0, 1.5):
+        got = api.thresholding_batch(ctx, data, off, lag, thr, infl)
+        ref = np.concatenate([orc.thresholding_algo(s, lag, thr, infl) for s in series])
+        _eq(f"thresholding lag {lag} infl {infl} thr {thr}", got, ref)
+
+
+def test_thresholding_short_series_is_an_error(ctx):
+    with pytest.raises(api.GamsCudaError) as e:
+        api.thresholding_algo(ctx, [0.1] * 10, 30, 3.0, 1.0)
+    assert e.value.code == -4
+
+
+# ------------------------------------------------------------------------------------ overlap counts
+def _fixture_index(orc, s288c):
+    ctgs = cut_ctgs(orc, s288c, 100000)
+    idx_ctg = orc.build_idx_ctg([c[:4] for c in ctgs])
+    ranges_of = orc.read_range(bytes(s288c["snp_rg"]).decode().splitlines(), idx_ctg)
+    idx_rg = orc.build_idx_rg(ranges_of)
+    ids = [c[0] for c in ctgs]
+    lps = [idx_rg.get(i, orc.lapper_new([])) for i in ids]
+    blobs = [orc.lapper_to_bincode(lp) for lp in lps]
+    views = [api.lapper_blob_view(b) for b in blobs]  # the path a Rust caller takes: slice the idx:rg blob
+    starts = np.concatenate([v[0] for v in views]).astype(np.uint32)
+    stops = np.concatenate([v[1] for v in views]).astype(np.uint32)
+    iv_off = np.concatenate(([0], np.cumsum([v[0].size for v in views]))).astype(np.uint64)
+    return ctgs, ids, idx_ctg, idx_rg, starts, stops, iv_off
+
+
+def test_locate_count_fixture(ctx, orc, s288c):
+    """BASELINE config 2 / tests/cli.rs:426-454: I:1000-2000 → 12, Mito:1000-2000 → 0, II dropped."""
+    ctgs, ids, idx_ctg, idx_rg, starts, stops, iv_off = _fixture_index(orc, s288c)
+    chrs = sorted({c[1] for c in ctgs})
+    by_chr = {ch: sorted((c for c in ctgs if c[1] == ch), key=lambda c: c[2]) for ch in chrs}
+    order = [c for ch in chrs for c in by_chr[ch]]
+    chr_off = np.concatenate(([0], np.cumsum([len(by_chr[ch]) for ch in chrs]))).astype(np.uint64)
+    cs = np.array([c[2] for c in order], dtype=np.uint32)
+    ce = np.array([c[3] + 1 for c in order], dtype=np.uint32)
+    qs = ["I:1000-2000", "II:1001-2000", "Mito:1000-2000", "I:100000-100001", "I:100001", "I:1", "I:230218-230300"]
+    rgs = [orc.range_from_str(q) for q in qs]
+    q_chr = np.array([chrs.index(r[0]) if r[0] in chrs else -1 for r in rgs], dtype=np.int32)
+    q_s = np.array([r[2] for r in rgs], dtype=np.uint32)
+    q_e = np.array([r[3] for r in rgs], dtype=np.uint32)
+    loc = api.locate_ctg(ctx, cs, ce, chr_off, q_chr, q_s, q_e)
+    ref_ids = [orc.find_one_idx(idx_ctg, r) for r in rgs]
+    assert [order[i][0] if i >= 0 else "" for i in loc] == ref_ids
+    seg = np.array([ids.index(order[i][0]) if i >= 0 else -1 for i in loc], dtype=np.int32)
+    cnt = api.count_overlaps(ctx, starts, stops, iv_off, seg, q_s, q_e)
+    out = [f"{q}\t{c}" for q, c, i in zip(qs, cnt, loc) if i >= 0]
+    assert out[:2] == ["I:1000-2000\t12", "Mito:1000-2000\t0"]
+    ref = [orc.count_rg(idx_rg, rid, r) if rid else 0 for rid, r in zip(ref_ids, rgs)]
+    assert cnt.tolist() == ref
+
+
+@pytest.mark.parametrize("grouped", [True, False])
+def test_count_overlaps_random(ctx, orc, grouped):
+    lens = [500_000, 999_999, 5_000, 700_001, 1, 640_000]
+    starts, stops, iv_off = synth.rg_index(lens, [16_000, 40_000, 0, 3, 1, 20_000], seed=3, max_len=1)
+    s2, e2, o2 = synth.rg_index(lens, [1000, 5000, 10, 0, 0, 800], seed=4, max_len=5000)  # real intervals, duplicates
+    st = np.concatenate([np.sort(np.concatenate([starts[iv_off[i]:iv_off[i + 1]], s2[o2[i]:o2[i + 1]]])) for i in range(6)])
+    sp = np.concatenate([np.sort(np.concatenate([stops[iv_off[i]:iv_off[i + 1]], e2[o2[i]:o2[i + 1]]])) for i in range(6)])
+    off = (iv_off + o2).astype(np.uint64)
+    seg, qs, qe = synth.queries(lens, 300_000, seed=5, grouped=grouped)
+    seg[::1000] = -1
+    seg[7::1000] = 6
+    # edge probes: query ending exactly at an interval start, point queries on a SNP
+    k = 5000
+    qs[:k] = st[off[1]:off[1] + k]
+    qe[:k] = qs[:k]
+    seg[:k] = 1
+    qe[k:2 * k] = st[off[1]:off[1] + k]
+    qs[k:2 * k] = np.maximum(qe[k:2 * k].astype(np.int64) - 50, 1).astype(np.uint32)
+    seg[k:2 * k] = 1
+    if grouped:
+        o = np.argsort(seg, kind="stable")
+        seg, qs, qe = seg[o], qs[o], qe[o]
+    got = api.count_overlaps(ctx, st, sp, off, seg, qs, qe)
+    ref = orc.count_batch(st, sp, off, seg, qs, qe, threads=8)
+    _eq("overlap counts", got, ref)
+    assert got.sum() > 0
+
+
+# ------------------------------------------------------------------------------------ gc ranges / sw
+def test_gc_ranges(ctx, orc):
+    g = synth.genome(600_000, seed=21)
+    seqs = [g[:250_003], g[250_003:250_003], g[250_003:]]
+    cat, off = orc.pack_ctgs(seqs)
+    rng = np.random.default_rng(22)
+    n = 20_000
+    qc = rng.choice([0, 2], n).astype(np.uint32)
+    ln = np.diff(off.astype(np.int64))[qc]
+    a = (rng.random(n) * ln).astype(np.int64)
+    b = np.minimum(a + rng.integers(0, 3000, n), ln)
+    a[:10], b[:10] = 0, ln[:10]
+    got = api.gc_ranges(ctx, cat, off, qc, a.astype(np.uint32), b.astype(np.uint32))
+    isgc = np.isin(cat, np.frombuffer(b"cgCG", dtype=np.uint8))
+    cs = np.concatenate(([0], np.cumsum(isgc)))
+    base = off.astype(np.int64)[qc]
+    _eq("gc_ranges", got, (cs[base + b] - cs[base + a]).astype(np.uint32))
+
+
+def test_sw_batch_fixture_features(ctx, orc, s288c):
+    """`gams sw` rows for the spo11 features (tests/cli.rs:306-330) against the oracle, all columns."""
+    ctgs = cut_ctgs(orc, s288c, 100000)
+    idx_ctg = orc.build_idx_ctg([c[:4] for c in ctgs])
+    feats = orc.read_range(bytes(s288c["spo11_rg"]).decode().splitlines(), idx_ctg)
+    cat, off = orc.pack_ctgs([c[4] for c in ctgs])
+    f_ctg, f_s, f_e = [], [], []
+    for k, c in enumerate(ctgs):
+        for rg in feats.get(c[0], []):
+            f_ctg.append(k), f_s.append(rg[2]), f_e.append(rg[3])
+    # plus features at ctg edges and tiny / huge ones
+    for k, c in enumerate(ctgs):
+        for s, e in ((c[2], c[2]), (c[3], c[3]), (c[2], c[2] + 49), (c[3] - 20, c[3]), (c[2] + 1000, c[2] + 1001), (c[2], c[3])):
+            f_ctg.append(k), f_s.append(s), f_e.append(e)
+    r = api.sw_batch(ctx, cat, off, [c[2] for c in ctgs], f_ctg, f_s, f_e)
+    assert int(r["row_off"][-1]) > 2000
+    for f in range(len(f_ctg)):
+        c = ctgs[f_ctg[f]]
+        ref = orc.sw_feature(c[4], c[2], c[3], f_s[f], f_e[f])
+        a, b = int(r["row_off"][f]), int(r["row_off"][f + 1])
+        assert b - a == len(ref["gc"]), (f, b - a, len(ref["gc"]))
+        for key in ("start", "end", "type", "dist"):
+            _eq(f"sw {key} feature {f}", r[key][a:b].astype(np.int64), ref[key].astype(np.int64))
+        for key in ("gc", "mean", "sd", "cv"):
+            _eq(f"sw {key} feature {f}", r[key][a:b].view(np.uint32), ref[key].view(np.uint32))
+
+
+def test_sw_batch_other_geometry(ctx, orc):
+    g = synth.genome(300_000, seed=31)
+    cat, off = orc.pack_ctgs([g[:120_000], g[120_000:]])
+    rng = np.random.default_rng(32)
+    f_ctg = rng.integers(0, 2, 300)
+    starts = [1, 500_001]
+    lens = [120_000, 180_000]
+    f_s = np.array([starts[c] + rng.integers(0, lens[c] - 3000) for c in f_ctg])
+    f_e = f_s + rng.integers(0, 3000, 300)
+    for size, mx, rz in ((100, 20, 500), (50, 3, 1000), (101, 5, 333)):
+        r = api.sw_batch(ctx, cat, off, starts, f_ctg, f_s, f_e, size, mx, rz)
+        for f in range(300):
+            c = int(f_ctg[f])
+            seq = g[:120_000] if c == 0 else g[120_000:]
+            ref = orc.sw_feature(seq, starts[c], starts[c] + lens[c] - 1, int(f_s[f]), int(f_e[f]), size, mx, rz)
+            a, b = int(r["row_off"][f]), int(r["row_off"][f + 1])
+            assert b - a == len(ref["gc"])
+            for key in ("gc", "mean", "sd", "cv"):
+                _eq(f"sw {key} ({size},{mx},{rz}) feature {f}", r[key][a:b].view(np.uint32), ref[key].view(np.uint32))
+            _eq("sw start", r["start"][a:b], ref["start"])
