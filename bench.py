@@ -66,51 +66,77 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons sampled DURING the timed region (NVML every 5 ms; the recipe's
+    nvidia-smi query is the fallback).  Samples carry a timestamp so only those inside [mark_start, mark_end]
+    are summarised."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
-        self.gpu, self.rows, self.proc = gpu_index, [], None
+        self.gpu, self.rows, self.stop, self.th, self.how = gpu_index, [], False, None, None
+        self.t0 = self.t1 = None
+
+    def _nvml_loop(self):
+        import pynvml as nv
+        h = nv.nvmlDeviceGetHandleByIndex(self.gpu)
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+        while not self.stop:
+            try:
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append((time.perf_counter(), float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), float(mx),
+                                  [k for k, b in bits.items() if r & b]))
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def _smi_loop(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
+                                 "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+        for line in proc.stdout:
+            r = [x.strip() for x in line.split(",")]
+            try:
+                self.rows.append((time.perf_counter(), float(r[1]), float(r[2]),
+                                  [n for n, v in zip(names, r[5:9]) if v.lower().startswith("active")]))
+            except Exception:
+                pass
+            if self.stop:
+                break
+        proc.terminate()
 
     def __enter__(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
-            self.th.start()
+            import pynvml as nv
+            nv.nvmlInit()
+            self.how, target = "nvml", self._nvml_loop
         except Exception:
-            self.proc = None
+            self.how, target = "nvidia-smi", self._smi_loop
+        self.th = threading.Thread(target=target, daemon=True)
+        self.th.start()
         return self
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+    def mark_start(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def __exit__(self, *a):
-        if self.proc:
-            time.sleep(0.15)
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=2)
-            except Exception:
-                self.proc.kill()
+        self.stop = True
+        if self.th:
+            self.th.join(timeout=2)
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[1])), mx.append(float(r[2]))
-                for n, v in zip(names, r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
-            except Exception:
-                pass
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        inside = [r for r in self.rows if self.t0 is not None and self.t1 is not None and self.t0 <= r[0] <= self.t1]
+        rows = inside if len(inside) >= 3 else self.rows
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "how": self.how}
+        reasons = sorted({x for r in rows for x in r[3]})
+        return {"sm_mhz": float(np.median([r[1] for r in rows])), "sm_max_mhz": float(max(r[2] for r in rows)),
+                "reasons": reasons, "samples": len(rows), "samples_in_timed_region": len(inside), "how": self.how}
 
 
 def layout(n_bases: int):
@@ -264,12 +290,13 @@ def main():
         plan.gc(stream, d_seq, d_gc)
         plan.signal(stream, d_gc, THRESHOLD, args.influence, d_sig, d_filt)
 
-    for _ in range(args.warmup):
-        step()
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
-    l0 = plan.launches
-    barrier()
     with ClockSampler(local) as clk:
+        for _ in range(args.warmup):
+            step()
+        l0 = plan.launches
+        barrier()
+        clk.mark_start()
         t_start = torch.cuda.Event(enable_timing=True)
         t_end = torch.cuda.Event(enable_timing=True)
         t_start.record()
@@ -281,6 +308,7 @@ def main():
             ev[k][2].record()
         t_end.record()
         barrier()
+        clk.mark_end()
     launches = plan.launches - l0
     ms_total = max_over_ranks(t_start.elapsed_time(t_end))
     ms_gc = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
@@ -358,10 +386,10 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
         cores = os.cpu_count() or 1
-        k = min(n_ctg, 4 * cores + 64)
+        k = n_ctg
         h = d_seq[:int(seq_off[k])].cpu().numpy() if h_seq_ptr is None else as_np(h_seq_ptr, int(seq_off[k]), np.uint8)
         v, sample = cpu_wave_rate(h, seq_off[:k + 1], cores, args.cpu_seconds, args.influence)
-        v1, sample1 = cpu_wave_rate(h, seq_off[:min(k, 9)], 1, 2.0, args.influence)
+        v1, sample1 = cpu_wave_rate(h, seq_off[:k + 1], 1, 3.0, args.influence)
         cpu = {"value": v, "unit": "Gbp/s", "cores": cores, "kind": "port", "sample": sample,
                "single_thread": {"value": v1, "cores": 1, "sample": sample1}}
     if h_seq_ptr is not None:
