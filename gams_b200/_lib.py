@@ -47,6 +47,8 @@ def load() -> C.CDLL:
         "gams_cuda_create": (i32, [vp, i32, C.POINTER(vp)]),
         "gams_cuda_destroy": (None, [vp]),
         "gams_cuda_ctx_num_devices": (i32, [vp]),
+        "gams_cuda_set_zscore_mode": (i32, [vp, i32]),
+        "gams_cuda_zscore_stats": (i32, [vp, vp, i32]),
         "gams_cuda_host_alloc": (vp, [sz]),
         "gams_cuda_host_free": (None, [vp]),
         "gams_cuda_wave_nwin": (i64, [i64, i32, i32]),

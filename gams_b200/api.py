@@ -44,6 +44,16 @@ class Context:
     def num_devices(self) -> int:
         return int(self._L.gams_cuda_ctx_num_devices(self._h))
 
+    def set_zscore_mode(self, mode: int):
+        """0 = certified filter + exact replay (default), 1 = replay every window, 2 = verify."""
+        check(self._L.gams_cuda_set_zscore_mode(self._h, mode))
+
+    def zscore_stats(self, reset=True):
+        """(windows replayed because the certificate was inconclusive, verify mismatches)."""
+        out = np.zeros(2, dtype=np.uint64)
+        check(self._L.gams_cuda_zscore_stats(self._h, _p(out), int(reset)))
+        return int(out[0]), int(out[1])
+
     def close(self):
         if getattr(self, "_h", None):
             self._L.gams_cuda_destroy(self._h)

@@ -165,9 +165,33 @@ GAMS_API int32_t gams_cuda_create(const int32_t *device_ids, int32_t n_dev, gams
         CUDA_TRY(cudaStreamCreateWithFlags(&pd.stream, cudaStreamNonBlocking));
         CUDA_TRY(cudaStreamCreateWithFlags(&pd.copy_in, cudaStreamNonBlocking));
         CUDA_TRY(cudaStreamCreateWithFlags(&pd.copy_out, cudaStreamNonBlocking));
+        CUDA_TRY(cudaMalloc(&pd.d_zstats, 2 * sizeof(unsigned long long)));
+        CUDA_TRY(cudaMemset(pd.d_zstats, 0, 2 * sizeof(unsigned long long)));
         ctx->devs.push_back(pd);
     }
+    if (const char *m = getenv("GAMS_CUDA_ZSCORE_MODE")) ctx->zscore_mode = atoi(m);
     *out = ctx.release();
+    return GAMS_CUDA_OK;
+}
+
+GAMS_API int32_t gams_cuda_set_zscore_mode(gams_cuda_ctx *ctx, int32_t mode) {
+    ARG_CHECK(ctx && mode >= 0 && mode <= 2, "set_zscore_mode: mode must be 0 (filter), 1 (replay) or 2 (verify)");
+    ctx->zscore_mode = mode;
+    return GAMS_CUDA_OK;
+}
+
+GAMS_API int32_t gams_cuda_zscore_stats(gams_cuda_ctx *ctx, uint64_t *out2, int32_t reset) {
+    ARG_CHECK(ctx && out2, "zscore_stats: NULL argument");
+    out2[0] = out2[1] = 0;
+    for (auto &pd : ctx->devs) {
+        DeviceGuard g(pd.device);
+        unsigned long long h[2];
+        CUDA_TRY(cudaDeviceSynchronize());
+        CUDA_TRY(cudaMemcpy(h, pd.d_zstats, sizeof(h), cudaMemcpyDeviceToHost));
+        out2[0] += h[0];
+        out2[1] += h[1];
+        if (reset) CUDA_TRY(cudaMemset(pd.d_zstats, 0, sizeof(h)));
+    }
     return GAMS_CUDA_OK;
 }
 
@@ -177,6 +201,7 @@ GAMS_API void gams_cuda_destroy(gams_cuda_ctx *ctx) {
         DeviceGuard g(pd.device);
         cudaStreamSynchronize(pd.stream);
         for (auto &b : pd.scratch) b.release();
+        if (pd.d_zstats) cudaFree(pd.d_zstats);
         cudaStreamDestroy(pd.stream);
         cudaStreamDestroy(pd.copy_in);
         cudaStreamDestroy(pd.copy_out);
@@ -321,7 +346,7 @@ GAMS_API int32_t gams_cuda_wave_signal_dev(gams_cuda_wave_plan *p, void *stream,
     ARG_CHECK(p && d_signal && d_gc, "wave_signal_dev: NULL argument");
     DeviceGuard g(p->device);
     return launch_zscore(p->win, (cudaStream_t)stream, d_gc, p->lag, threshold, influence, d_filtered, d_signal,
-                         &p->launches);
+                         &p->launches, p->ctx->zscore_mode, p->ctx->devs[p->dev_index].d_zstats);
 }
 
 // ================================================================================ wave: host ====
@@ -353,7 +378,7 @@ static int32_t wave_on_device(gams_cuda_ctx *ctx, int d, int64_t c0, int64_t c1,
     if ((rc = pd.scratch[1].reserve(std::max<uint64_t>(nwn, 1) * sizeof(float)))) return rc;
     if (gc_count && (rc = pd.scratch[2].reserve(std::max<uint64_t>(nwn, 1) * sizeof(uint32_t)))) return rc;
     if (signal && (rc = pd.scratch[3].reserve(std::max<uint64_t>(nwn, 1)))) return rc;
-    const bool need_filt = signal && !(influence == 1.0f && lag <= 40000);
+    const bool need_filt = signal && !(influence == 1.0f && lag <= ZS_MAX_TILED_LAG);
     if (need_filt && (rc = pd.scratch[4].reserve(std::max<uint64_t>(nwn, 1) * sizeof(float)))) return rc;
     uint8_t *d_seq = pd.scratch[0].as<uint8_t>();
     float *d_gc = pd.scratch[1].as<float>();
@@ -418,7 +443,9 @@ GAMS_API int32_t gams_cuda_thresholding_batch(gams_cuda_ctx *ctx, int64_t n_seri
     int8_t *d_sig = pd.scratch[3].as<int8_t>();
     cudaStream_t st = pd.stream;
     CUDA_TRY(cudaMemcpyAsync(d_x, data + off[0], total * sizeof(float), cudaMemcpyHostToDevice, st));
-    if ((rc = launch_zscore(L, st, d_x, lag, threshold, influence, pd.scratch[4].as<float>(), d_sig, nullptr))) return rc;
+    if ((rc = launch_zscore(L, st, d_x, lag, threshold, influence, pd.scratch[4].as<float>(), d_sig, nullptr,
+                            ctx->zscore_mode, pd.d_zstats)))
+        return rc;
     CUDA_TRY(cudaMemcpyAsync(signal + off[0], d_sig, total, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     return GAMS_CUDA_OK;
@@ -448,6 +475,7 @@ GAMS_API int32_t gams_cuda_count_plan_create(gams_cuda_ctx *ctx, int32_t dev_ind
         p->max_seg = std::max(p->max_seg, len);
     }
     p->total_iv = p->h_iv_off[n_seg];
+    if (const char *m = getenv("GAMS_CUDA_COUNT_MODE")) p->mode = atoi(m);
     DeviceGuard g(pd.device);
     CUDA_TRY(cudaMalloc(&p->d_iv_off, sizeof(uint64_t) * (size_t)(n_seg + 1)));
     CUDA_TRY(cudaMemcpyAsync(p->d_iv_off, p->h_iv_off.data(), sizeof(uint64_t) * (size_t)(n_seg + 1),

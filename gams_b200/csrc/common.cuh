@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -60,6 +61,15 @@ struct TileDesc {
     uint32_t first;  // first window of the tile inside the ctg
 };
 
+// Per-segment parameters of the rank tables of Kernel C (overlap.cu); [0] = starts[], [1] = stops[]
+struct alignas(16) SegRank {
+    uint64_t off;   // first interval of the segment in the concatenated arrays
+    uint32_t n;     // intervals in the segment
+    uint32_t pad;
+    uint32_t lo[2], hi[2], shift[2];
+    uint32_t pad2[2];
+};
+
 // Geometry of Kernel A (gc_window.cu)
 constexpr int GC_THREADS = 256;
 struct GcGeom {
@@ -72,6 +82,7 @@ struct GcGeom {
 constexpr int ZS_R = 8;                       // windows per thread
 constexpr int ZS_THREADS = 128;
 constexpr int ZS_TILE = ZS_R * ZS_THREADS;    // windows per tile
+constexpr int ZS_MAX_TILED_LAG = 8000;        // (tile + lag) * 21 B of shared memory must fit 227 KB
 
 // A batch of series (one per ctg) resident on one device: offsets + z-score tiles.
 struct SeriesLayout {
@@ -90,6 +101,7 @@ struct PerDevice {
     cudaStream_t stream = nullptr;   // library-owned stream for the host API
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
     DevBuf scratch[8];
+    unsigned long long *d_zstats = nullptr;  // [0] windows replayed after an inconclusive certificate, [1] verify mismatches
 };
 
 }  // namespace gams
@@ -97,6 +109,7 @@ struct PerDevice {
 struct gams_cuda_ctx {
     std::vector<gams::PerDevice> devs;
     std::mutex mu;
+    int zscore_mode = 0;  // 0 certified filter + exact replay, 1 replay everything, 2 verify
 };
 
 struct gams_cuda_wave_plan {
@@ -125,7 +138,10 @@ struct gams_cuda_count_plan {
     uint64_t max_seg = 0;
     std::vector<uint64_t> h_iv_off;
     uint64_t *d_iv_off = nullptr;
-    gams::DevBuf tmp[6];
+    gams::DevBuf tmp[6];             // [0] SegRank per segment, [1]/[2] rank tables of starts[] / stops[]
+    const uint32_t *idx_starts = nullptr, *idx_stops = nullptr;  // arrays the rank tables were built for
+    bool idx_valid = false;
+    int mode = 0;                    // 0 ranked (default), 1 plain binary search (GAMS_CUDA_COUNT_MODE)
     uint64_t launches = 0;
 };
 
@@ -134,7 +150,8 @@ namespace gams {
 int32_t launch_gc_windows(const gams_cuda_wave_plan *p, cudaStream_t st, const uint8_t *d_seq,
                           uint32_t *d_cnt, float *d_gc, uint64_t *launches);
 int32_t launch_zscore(const SeriesLayout &L, cudaStream_t st, const float *d_x, uint64_t lag, float threshold,
-                      float influence, float *d_filtered, int8_t *d_signal, uint64_t *launches);
+                      float influence, float *d_filtered, int8_t *d_signal, uint64_t *launches, int mode,
+                      unsigned long long *d_stats);
 int32_t launch_count_overlaps(gams_cuda_count_plan *p, cudaStream_t st, const uint32_t *d_starts,
                               const uint32_t *d_stops, int64_t n_q, const int32_t *d_q_seg,
                               const uint32_t *d_q_start, const uint32_t *d_q_stop, int32_t grouped,

@@ -40,13 +40,107 @@ __device__ __forceinline__ int zscore_decide(Ld ld, int64_t a, uint64_t lag, flo
 __host__ __device__ __forceinline__ int zs_swz(int p) { return p + (p >> 5); }  // breaks the stride-ZS_R bank pattern
 
 // ------------------------------------------------------------------------------------------------
-// influence == 1
+// influence == 1: exact replay of ZS_R consecutive windows by one thread (blocked add chains)
 // ------------------------------------------------------------------------------------------------
+// chain r sums smem positions p0+r .. p0+r+lag-1, in order; the window's own value is at p0+r+lag+1
+__device__ __forceinline__ void replay_block(const float *sm, int p0, int lag, float flag, float flagm1,
+                                             float threshold, int (&sig)[ZS_R]) {
+    float s[ZS_R], m[ZS_R], q[ZS_R];
+#pragma unroll
+    for (int r = 0; r < ZS_R; ++r) s[r] = 0.0f;
+#pragma unroll
+    for (int t = 0; t < ZS_R - 1; ++t) {
+        const float v = sm[zs_swz(p0 + t)];
+#pragma unroll
+        for (int r = 0; r < ZS_R; ++r)
+            if (r <= t) s[r] = __fadd_rn(s[r], v);
+    }
+#pragma unroll 4
+    for (int t = ZS_R - 1; t < lag; ++t) {
+        const float v = sm[zs_swz(p0 + t)];
+#pragma unroll
+        for (int r = 0; r < ZS_R; ++r) s[r] = __fadd_rn(s[r], v);
+    }
+#pragma unroll
+    for (int k = 0; k < ZS_R - 1; ++k) {
+        const float v = sm[zs_swz(p0 + lag + k)];
+#pragma unroll
+        for (int r = 0; r < ZS_R; ++r)
+            if (r > k) s[r] = __fadd_rn(s[r], v);
+    }
+#pragma unroll
+    for (int r = 0; r < ZS_R; ++r) {
+        m[r] = __fdiv_rn(s[r], flag);
+        q[r] = 0.0f;
+    }
+#pragma unroll
+    for (int t = 0; t < ZS_R - 1; ++t) {
+        const float v = sm[zs_swz(p0 + t)];
+#pragma unroll
+        for (int r = 0; r < ZS_R; ++r)
+            if (r <= t) {
+                const float d = __fsub_rn(v, m[r]);
+                q[r] = __fadd_rn(q[r], __fmul_rn(d, d));
+            }
+    }
+#pragma unroll 4
+    for (int t = ZS_R - 1; t < lag; ++t) {
+        const float v = sm[zs_swz(p0 + t)];
+#pragma unroll
+        for (int r = 0; r < ZS_R; ++r) {
+            const float d = __fsub_rn(v, m[r]);
+            q[r] = __fadd_rn(q[r], __fmul_rn(d, d));
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < ZS_R - 1; ++k) {
+        const float v = sm[zs_swz(p0 + lag + k)];
+#pragma unroll
+        for (int r = 0; r < ZS_R; ++r)
+            if (r > k) {
+                const float d = __fsub_rn(v, m[r]);
+                q[r] = __fadd_rn(q[r], __fmul_rn(d, d));
+            }
+    }
+#pragma unroll
+    for (int r = 0; r < ZS_R; ++r) {
+        const float sd = __fsqrt_rn(__fdiv_rn(q[r], flagm1));
+        const float xv = sm[zs_swz(p0 + r + lag + 1)];
+        sig[r] = (fabsf(__fsub_rn(xv, m[r])) > __fmul_rn(threshold, sd)) ? ((xv > m[r]) ? 1 : -1) : 0;
+    }
+}
+
+// MODE 0: certified filter, exact replay only where the certificate is inconclusive (default)
+// MODE 1: exact replay of every window (the round-1a kernel)
+// MODE 2: verify — replay every window AND count certified decisions that disagree (must be 0)
+//
+// The filter.  For window i with stats range W (n = lag values) the reference computes, in f32 and in a
+// fixed order, m^ = fl(sum)/n, sd^ = sqrt(fl(sum (x-m^)^2)/(n-1)) and signals iff |x_i - m^| > thr*sd^.
+// Let mu and S = sum (x-mu)^2 be the exact (real) mean and centred sum of squares of the same f32 inputs.
+// Standard forward error bounds for recursive summation (u = 2^-24, M = max|x| over the tile) give
+//     |m^ - mu| <= E_m = 1.01 (n+2) u M,
+//     sd^ in sqrt(Q/(n-1)) [1-R, 1+R],  Q = S + n (mu - m^)^2 in [S, S + n E_m^2],  R = (0.6 n + 8) u,
+//     fl|fl(x_i - m^)| in |x_i - m^| [1-u, 1+u],   fl(thr*sd^) in thr*sd^ [1-u, 1+u]   (u's folded into R).
+// mu and S are evaluated in f64 from per-tile prefix sums of y = x - x_ref and y^2 (errors err_mu, err_S,
+// bounded with N = tile elements and Ymax = max|y|).  If the worst case of the left side still exceeds the
+// worst case of the right side the window certainly signals; if the best case of the left side is below the
+// best case of the right side it certainly does not; otherwise (about 1 window in 10^4 on genomes, and every
+// window inside a constant-GC run, where the reference compares rounding noise with rounding noise) the
+// window is replayed exactly.  Either way the output equals the reference's.
+template <int MODE>
 __global__ void __launch_bounds__(ZS_THREADS)
 zscore_indep_kernel(const float *__restrict__ x, const uint64_t *__restrict__ off,
-                    const TileDesc *__restrict__ tiles, int lag, float threshold, int8_t *__restrict__ signal) {
-    extern __shared__ float sm[];  // zs_swz(ZS_TILE + lag + 1) + 1 floats, then ZS_TILE signal bytes
-    const int tid = threadIdx.x;
+                    const TileDesc *__restrict__ tiles, int lag, float threshold, int8_t *__restrict__ signal,
+                    unsigned long long *__restrict__ stats) {
+    extern __shared__ __align__(16) unsigned char zs_smem[];
+    const int n_el_max = ZS_TILE + lag + 1;
+    double *Y1 = reinterpret_cast<double *>(zs_smem);          // n_el_max + 1 exclusive prefix of y
+    double *Y2 = Y1 + (n_el_max + 1);                          // n_el_max + 1 exclusive prefix of y^2
+    float *sm = reinterpret_cast<float *>(Y2 + (n_el_max + 1));  // zs_swz(n_el_max) + 1 values
+    int8_t *sg = reinterpret_cast<int8_t *>(sm + zs_swz(n_el_max) + 1);
+    __shared__ double red[ZS_THREADS / 32][4];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const TileDesc td = tiles[blockIdx.x];
     const uint64_t base = off[td.item];
     const int64_t n = (int64_t)(off[td.item + 1] - base);
@@ -54,7 +148,6 @@ zscore_indep_kernel(const float *__restrict__ x, const uint64_t *__restrict__ of
     const int nw = (int)min((int64_t)ZS_TILE, n - w0);
     const int64_t lo0 = w0 - 1 - lag;  // series index held at smem position 0 (may be negative)
     const int n_el = nw + lag + 1;
-    int8_t *sg = reinterpret_cast<int8_t *>(sm + zs_swz(ZS_TILE + lag + 1) + 1);
 
     for (int p = tid; p < n_el; p += ZS_THREADS) {
         const int64_t e = lo0 + p;
@@ -64,89 +157,135 @@ zscore_indep_kernel(const float *__restrict__ x, const uint64_t *__restrict__ of
 
     const float flag = __ull2float_rn((unsigned long long)lag);  // `data.len() as f32`
     const float flagm1 = __fsub_rn(flag, 1.0f);                   // `len - 1.`
-    const int p0 = tid * ZS_R;                                    // smem position of chain 0's first element
-    const int64_t i0 = w0 + p0;                                   // first window of this thread
-    int sig[ZS_R];
+    const bool use_filter = (MODE != 1) && lag >= 2 && threshold >= 0.0f && threshold < 3.0e38f;
+
+    double M = 0.0, Ymax = 0.0, xref = 0.0;
+    if (use_filter) {
+        // ---- f64 prefix sums of y and y^2 over the tile's elements (thread-contiguous chunks) ----
+        const int first_valid = (lo0 < 0) ? (int)(-lo0) : 0;
+        xref = (double)sm[zs_swz(first_valid < n_el ? first_valid : 0)];
+        const int per = (n_el + ZS_THREADS - 1) / ZS_THREADS;
+        const int pb = tid * per, pe = min(pb + per, n_el);
+        double a1 = 0.0, a2 = 0.0, mx = 0.0, my = 0.0;
+        for (int p = pb; p < pe; ++p) {
+            const double xv = (double)sm[zs_swz(p)];
+            const double y = (p >= first_valid) ? xv - xref : 0.0;
+            a1 += y;
+            a2 += y * y;
+            mx = fmax(mx, fabs(xv));
+            my = fmax(my, fabs(y));
+        }
+        double s1 = a1, s2 = a2;
 #pragma unroll
-    for (int r = 0; r < ZS_R; ++r) sig[r] = 0;
+        for (int d = 1; d < 32; d <<= 1) {
+            const double t1 = __shfl_up_sync(0xFFFFFFFFu, s1, d), t2 = __shfl_up_sync(0xFFFFFFFFu, s2, d);
+            if (lane >= d) { s1 += t1; s2 += t2; }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            mx = fmax(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, d));
+            my = fmax(my, __shfl_xor_sync(0xFFFFFFFFu, my, d));
+        }
+        if (lane == 31) { red[warp][0] = s1; red[warp][1] = s2; }
+        if (lane == 0) { red[warp][2] = mx; red[warp][3] = my; }
+        __syncthreads();
+        double b1 = s1 - a1, b2 = s2 - a2;  // exclusive within the warp
+#pragma unroll
+        for (int w = 0; w < ZS_THREADS / 32; ++w) {
+            if (w < warp) { b1 += red[w][0]; b2 += red[w][1]; }
+            M = fmax(M, red[w][2]);
+            Ymax = fmax(Ymax, red[w][3]);
+        }
+        for (int p = pb; p < pe; ++p) {
+            Y1[p] = b1;
+            Y2[p] = b2;
+            const double xv = (double)sm[zs_swz(p)];
+            const double y = (p >= first_valid) ? xv - xref : 0.0;
+            b1 += y;
+            b2 += y * y;
+        }
+        if (pe == n_el && pb < pe) { Y1[n_el] = b1; Y2[n_el] = b2; }
+        __syncthreads();
+    }
+
+    const int p0 = tid * ZS_R;     // smem position of chain 0's first element
+    const int64_t i0 = w0 + p0;    // first window of this thread
+    int sig[ZS_R], cert[ZS_R];
+    unsigned todo = 0;             // bit r: window r exists and is past the first `lag` windows
+    unsigned certified = 0;        // bit r: the filter decided window r (decision in cert[r])
+#pragma unroll
+    for (int r = 0; r < ZS_R; ++r) sig[r] = cert[r] = 0;
 
     if (p0 < nw) {
-        const bool fast = (i0 >= (int64_t)lag + 1) && (p0 + ZS_R <= nw) && (lag >= ZS_R);
-        if (fast) {
-            // chain r sums smem positions p0+r .. p0+r+lag-1, in order; the window's own value is at p0+r+lag+1
-            float s[ZS_R], m[ZS_R], q[ZS_R];
 #pragma unroll
-            for (int r = 0; r < ZS_R; ++r) s[r] = 0.0f;
-#pragma unroll
-            for (int t = 0; t < ZS_R - 1; ++t) {
-                const float v = sm[zs_swz(p0 + t)];
-#pragma unroll
-                for (int r = 0; r < ZS_R; ++r)
-                    if (r <= t) s[r] = __fadd_rn(s[r], v);
-            }
-#pragma unroll 4
-            for (int t = ZS_R - 1; t < lag; ++t) {
-                const float v = sm[zs_swz(p0 + t)];
-#pragma unroll
-                for (int r = 0; r < ZS_R; ++r) s[r] = __fadd_rn(s[r], v);
-            }
-#pragma unroll
-            for (int k = 0; k < ZS_R - 1; ++k) {
-                const float v = sm[zs_swz(p0 + lag + k)];
-#pragma unroll
-                for (int r = 0; r < ZS_R; ++r)
-                    if (r > k) s[r] = __fadd_rn(s[r], v);
-            }
+        for (int r = 0; r < ZS_R; ++r) {
+            const int64_t i = i0 + r;
+            if (i < n && i >= (int64_t)lag) todo |= 1u << r;
+        }
+        if (use_filter) {
+            const double u = 5.9604644775390625e-8, u64e = 1.1102230246251565e-16;
+            const double dn = (double)lag, dnm1 = (double)flagm1;
+            const double N2 = (double)n_el * (double)n_el;
+            const double E_m = 1.01 * (dn + 2.0) * u * M + 1e-40;
+            const double err_mu = 4.0 * N2 * u64e * Ymax / dn + 1e-300;
+            const double err_S = 16.0 * N2 * u64e * Ymax * Ymax + 1e-40;
+            const double R = (0.6 * dn + 8.0) * u;
+            const double t2 = (double)threshold * (double)threshold;
+            const double k_hi = t2 * (1.0 + R) * (1.0 + R) / dnm1, k_lo = t2 * (1.0 - R) * (1.0 - R) / dnm1;
+            const double slack = E_m + err_mu;
+            const double extra = err_S + dn * E_m * E_m;
 #pragma unroll
             for (int r = 0; r < ZS_R; ++r) {
-                m[r] = __fdiv_rn(s[r], flag);
-                q[r] = 0.0f;
-            }
-#pragma unroll
-            for (int t = 0; t < ZS_R - 1; ++t) {
-                const float v = sm[zs_swz(p0 + t)];
-#pragma unroll
-                for (int r = 0; r < ZS_R; ++r)
-                    if (r <= t) {
-                        const float d = __fsub_rn(v, m[r]);
-                        q[r] = __fadd_rn(q[r], __fmul_rn(d, d));
-                    }
-            }
-#pragma unroll 4
-            for (int t = ZS_R - 1; t < lag; ++t) {
-                const float v = sm[zs_swz(p0 + t)];
-#pragma unroll
-                for (int r = 0; r < ZS_R; ++r) {
-                    const float d = __fsub_rn(v, m[r]);
-                    q[r] = __fadd_rn(q[r], __fmul_rn(d, d));
+                if (!(todo >> r & 1u)) continue;
+                const int64_t i = i0 + r;
+                const int64_t a = (i - 1 - (int64_t)lag > 0) ? (i - 1 - (int64_t)lag) : 0;
+                const int pa = (int)(a - lo0);
+                const double s1 = Y1[pa + lag] - Y1[pa], s2 = Y2[pa + lag] - Y2[pa];
+                const double mu_y = s1 / dn;
+                const double S = s2 - s1 * mu_y;
+                const double yv = (double)sm[zs_swz((int)(i - lo0))] - xref;
+                const double dev = fabs(yv - mu_y);
+                const double lo = (dev - slack) * (1.0 - 2.0 * u), hi = (dev + slack) * (1.0 + 2.0 * u);
+                if (lo > 0.0 && lo * lo > k_hi * (S + extra)) {
+                    cert[r] = (yv > mu_y) ? 1 : -1;
+                    certified |= 1u << r;
+                } else if (hi * hi < k_lo * fmax(S - err_S, 0.0)) {
+                    cert[r] = 0;
+                    certified |= 1u << r;
                 }
             }
+        }
+        const unsigned need = (MODE == 0) ? (todo & ~certified) : todo;
+        int rs[ZS_R];
 #pragma unroll
-            for (int k = 0; k < ZS_R - 1; ++k) {
-                const float v = sm[zs_swz(p0 + lag + k)];
-#pragma unroll
-                for (int r = 0; r < ZS_R; ++r)
-                    if (r > k) {
-                        const float d = __fsub_rn(v, m[r]);
-                        q[r] = __fadd_rn(q[r], __fmul_rn(d, d));
-                    }
-            }
-#pragma unroll
-            for (int r = 0; r < ZS_R; ++r) {
-                const float sd = __fsqrt_rn(__fdiv_rn(q[r], flagm1));
-                const float xv = sm[zs_swz(p0 + r + lag + 1)];
-                sig[r] = (fabsf(__fsub_rn(xv, m[r])) > __fmul_rn(threshold, sd)) ? ((xv > m[r]) ? 1 : -1) : 0;
-            }
-        } else {
-            // ctg head (i <= lag), tile tail, or tiny lag: one window at a time, same arithmetic
-            auto ld = [&](int64_t e) { return sm[zs_swz((int)(e - lo0))]; };
-            for (int r = 0; r < ZS_R; ++r) {
-                const int64_t i = i0 + r;
-                if (i >= n || i < (int64_t)lag) continue;
-                const int64_t a = (i - 1 - (int64_t)lag > 0) ? (i - 1 - (int64_t)lag) : 0;  // stat.rs:30-31 vs :51-52
-                sig[r] = zscore_decide(ld, a, (uint64_t)lag, flag, flagm1, ld(i), threshold);
+        for (int r = 0; r < ZS_R; ++r) rs[r] = 0;
+        if (need) {
+            const bool block_ok = (i0 >= (int64_t)lag + 1) && (p0 + ZS_R <= nw) && (lag >= ZS_R);
+            if (block_ok && (MODE != 0 || __popc(need) >= 2)) {
+                replay_block(sm, p0, lag, flag, flagm1, threshold, rs);
+            } else {
+                auto ld = [&](int64_t e) { return sm[zs_swz((int)(e - lo0))]; };
+                for (int r = 0; r < ZS_R; ++r) {
+                    if (!(need >> r & 1u)) continue;
+                    const int64_t i = i0 + r;
+                    const int64_t a = (i - 1 - (int64_t)lag > 0) ? (i - 1 - (int64_t)lag) : 0;  // stat.rs:30-31 vs :51-52
+                    rs[r] = zscore_decide(ld, a, (uint64_t)lag, flag, flagm1, ld(i), threshold);
+                }
             }
         }
+        unsigned bad = 0;
+#pragma unroll
+        for (int r = 0; r < ZS_R; ++r) {
+            sig[r] = (need >> r & 1u) ? rs[r] : cert[r];
+            if (MODE == 2 && (certified >> r & 1u) && cert[r] != rs[r]) ++bad;
+        }
+        if (MODE == 2 && bad && stats) atomicAdd(&stats[1], (unsigned long long)bad);
+    }
+    if (stats && MODE != 1) {  // uncertain windows (replayed exactly in MODE 0)
+        unsigned long long unc = (unsigned long long)__popc(todo & ~certified);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) unc += __shfl_xor_sync(0xFFFFFFFFu, unc, d);
+        if (lane == 0 && unc) atomicAdd(&stats[0], unc);
     }
 #pragma unroll
     for (int r = 0; r < ZS_R; ++r)
@@ -217,7 +356,8 @@ zscore_seq_kernel(const float *__restrict__ x_all, const uint64_t *__restrict__ 
 }
 
 int32_t launch_zscore(const SeriesLayout &L, cudaStream_t st, const float *d_x, uint64_t lag, float threshold,
-                      float influence, float *d_filtered, int8_t *d_signal, uint64_t *launches) {
+                      float influence, float *d_filtered, int8_t *d_signal, uint64_t *launches, int mode,
+                      unsigned long long *d_stats) {
     if (lag == 0) {
         set_error("thresholding: lag must be >= 1 (the reference underflows lag-1, stat.rs:30)");
         return GAMS_CUDA_EINVAL;
@@ -228,13 +368,19 @@ int32_t launch_zscore(const SeriesLayout &L, cudaStream_t st, const float *d_x, 
                   (unsigned long long)L.min_len, (unsigned long long)lag);
         return GAMS_CUDA_ELAG;
     }
-    const bool tiled = influence == 1.0f && lag <= 40000;
-    const size_t smem_need = tiled ? (size_t)(zs_swz(ZS_TILE + (int)lag + 1) + 1) * sizeof(float) + ZS_TILE : 0;
+    const bool tiled = influence == 1.0f && lag <= ZS_MAX_TILED_LAG;
     if (tiled) {
-        if (smem_need > 48 * 1024)
-            CUDA_TRY(cudaFuncSetAttribute(zscore_indep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_need));
-        zscore_indep_kernel<<<(unsigned)L.n_ztiles, ZS_THREADS, smem_need, st>>>(d_x, L.d_off, L.d_ztiles, (int)lag,
-                                                                                threshold, d_signal);
+        const int n_el_max = ZS_TILE + (int)lag + 1;
+        const size_t smem_need = (size_t)(n_el_max + 1) * 16 + (size_t)(zs_swz(n_el_max) + 1) * sizeof(float) + ZS_TILE;
+        auto go = [&](auto kern) -> int32_t {
+            if (smem_need > 48 * 1024)
+                CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_need));
+            kern<<<(unsigned)L.n_ztiles, ZS_THREADS, smem_need, st>>>(d_x, L.d_off, L.d_ztiles, (int)lag, threshold,
+                                                                     d_signal, d_stats);
+            return GAMS_CUDA_OK;
+        };
+        int32_t rc = mode == 1 ? go(zscore_indep_kernel<1>) : mode == 2 ? go(zscore_indep_kernel<2>) : go(zscore_indep_kernel<0>);
+        if (rc) return rc;
     } else {
         if (!d_filtered) {
             set_error("thresholding: influence != 1 (or lag too large for the tiled path) needs the d_filtered scratch");

@@ -54,6 +54,15 @@ int32_t gams_cuda_create(const int32_t *device_ids, int32_t n_dev, gams_cuda_ctx
 void gams_cuda_destroy(gams_cuda_ctx *ctx);
 int32_t gams_cuda_ctx_num_devices(const gams_cuda_ctx *ctx);
 
+/* Kernel B strategy for influence == 1 (results are identical in every mode):
+ * 0 = certified filter, exact replay only where the certificate is inconclusive (default),
+ * 1 = exact replay of every window, 2 = verify (replay everything and count certified decisions that
+ * disagree with the replay; must stay 0).  Also settable with env GAMS_CUDA_ZSCORE_MODE at create time. */
+int32_t gams_cuda_set_zscore_mode(gams_cuda_ctx *ctx, int32_t mode);
+/* out2[0] = windows whose certificate was inconclusive (replayed exactly), out2[1] = verify mismatches,
+ * both accumulated since creation / the last reset; synchronises the devices. */
+int32_t gams_cuda_zscore_stats(gams_cuda_ctx *ctx, uint64_t *out2, int32_t reset);
+
 /* Page-locked host buffers so the host API's copies run at PCIe speed (the analogue of the
  * Vec<u8> that Conn::get_seq fills, src/libs/redis.rs:142-146).  Plain malloc'd memory works
  * too, only slower. */

@@ -281,3 +281,102 @@ def test_sw_batch_other_geometry(ctx, orc):
             for key in ("gc", "mean", "sd", "cv"):
                 _eq(f"sw {key} ({size},{mx},{rz}) feature {f}", r[key][a:b].view(np.uint32), ref[key].view(np.uint32))
             _eq("sw start", r["start"][a:b], ref["start"])
+
+
+# ------------------------------------------------------------------- certified z-score filter (Kernel B)
+def _gc_series(orc, seq, size=100, step=10):
+    cat, off = orc.pack_ctgs([seq])
+    _, _, gc, _ = orc.wave_batch(cat, off, size, step, 100, 3.0, 1.0, want_signal=False)
+    return gc
+
+
+def test_zscore_filter_certificates_are_sound(ctx, orc, s288c):
+    """Mode 2 replays every window and counts certified decisions that disagree: must be zero, on the
+    fixture, on synthetic genomes, on degenerate constant-GC data and on non-GC series."""
+    rng = np.random.default_rng(41)
+    flat = np.tile(np.frombuffer(b"ACATTTTTAT" * 5 + b"GCGCGCGCGATATATATATATATATATATATATATATATATATATATATA", dtype=np.uint8), 1500)
+    series = [_gc_series(orc, s288c["seq_I"]), _gc_series(orc, s288c["seq_Mito"]), _gc_series(orc, synth.genome(400_000, seed=42)),
+              _gc_series(orc, flat), _gc_series(orc, np.full(30_000, ord("N"), np.uint8)),
+              rng.normal(1.0, 0.1, 20_000).astype(np.float32), rng.normal(-500.0, 1e-3, 20_000).astype(np.float32),
+              (rng.integers(0, 3, 20_000) * np.float32(1e-30)).astype(np.float32), rng.normal(0, 1e4, 20_000).astype(np.float32)]
+    data = np.concatenate(series)
+    off = np.concatenate(([0], np.cumsum([s.size for s in series]))).astype(np.uint64)
+    try:
+        for lag in (100, 30, 8, 2):
+            for thr in (3.0, 0.0, 1.0, 2.9999, 7.5):
+                ref = np.concatenate([orc.thresholding_algo(s, lag, thr, 1.0) for s in series])
+                ctx.zscore_stats(reset=True)
+                for mode in (2, 1, 0):
+                    ctx.set_zscore_mode(mode)
+                    got = api.thresholding_batch(ctx, data, off, lag, thr, 1.0)
+                    _eq(f"mode {mode} lag {lag} thr {thr}", got, ref)
+                    unc, bad = ctx.zscore_stats(reset=True)
+                    assert bad == 0, f"{bad} certified decisions disagree with the exact replay (lag {lag}, thr {thr})"
+    finally:
+        ctx.set_zscore_mode(0)
+
+
+def test_zscore_filter_borderline_thresholds(ctx, orc, s288c):
+    """Thresholds placed exactly on (and one ulp around) the z value of real windows, so some decision is
+    as close to a tie as f32 allows; the filter must hand those windows to the exact replay."""
+    gc = _gc_series(orc, s288c["seq_I"])
+    lag = 100
+    rng = np.random.default_rng(43)
+    picks = rng.integers(lag + 1, gc.size, 60)
+    thrs = []
+    for i in picks:
+        w = gc[i - 1 - lag:i - 1]
+        m, sd = orc.mean(w), orc.stddev(w)
+        if sd > 0:
+            z = np.float32(abs(np.float32(gc[i] - m)) / sd)
+            thrs += [z, np.nextafter(z, np.float32(0)), np.nextafter(z, np.float32(10))]
+    off = np.array([0, gc.size], dtype=np.uint64)
+    total_unc = 0
+    ctx.zscore_stats(reset=True)
+    for thr in thrs:
+        ref = orc.thresholding_algo(gc, lag, float(thr), 1.0)
+        got = api.thresholding_batch(ctx, gc, off, lag, float(thr), 1.0)
+        _eq(f"borderline thr {thr!r}", got, ref)
+        total_unc += ctx.zscore_stats(reset=True)[0]
+    assert total_unc > 0  # the borderline windows did go through the replay
+    assert total_unc < 0.01 * gc.size * len(thrs)  # ...and only a sliver of all windows did
+
+
+def test_zscore_filter_replay_fraction_on_genome(ctx, orc):
+    gc = _gc_series(orc, synth.genome(2_000_000, seed=44))
+    ctx.zscore_stats(reset=True)
+    got = api.thresholding_batch(ctx, gc, np.array([0, gc.size], dtype=np.uint64), 100, 3.0, 1.0)
+    _eq("genome", got, orc.thresholding_algo(gc, 100, 3.0, 1.0))
+    unc, _ = ctx.zscore_stats(reset=True)
+    assert unc < 0.005 * gc.size, f"{unc} of {gc.size} windows needed the exact replay"
+
+
+def test_count_overlaps_adversarial_distributions(ctx, orc):
+    """Rank tables must stay exact on skewed endpoint distributions: duplicates, far-apart clusters,
+    coordinates near 2^32, single-interval and empty segments."""
+    rng = np.random.default_rng(51)
+    segs = [
+        (np.full(5000, 777, np.uint32), np.full(5000, 778, np.uint32)),                                    # all identical
+        (np.concatenate([rng.integers(1, 50, 3000), rng.integers(4_000_000_000, 4_000_000_100, 3000)]).astype(np.uint32), None),
+        (rng.integers(1, 4_294_967_000, 20000).astype(np.uint32), None),                                   # huge coordinates
+        (np.array([123456], np.uint32), np.array([123999], np.uint32)),                                    # single interval
+        (np.zeros(0, np.uint32), np.zeros(0, np.uint32)),                                                  # empty
+        (np.repeat(rng.integers(1, 10_000, 50), 400).astype(np.uint32), None),                             # heavy duplicates
+        (np.arange(1, 30001, dtype=np.uint32) * 3, None),                                                  # perfectly regular
+    ]
+    st, sp, off = [], [], [0]
+    for s, e in segs:
+        s = np.sort(s)
+        e = np.sort(e if e is not None else (s + rng.integers(1, 200, s.size).astype(np.uint32)))
+        st.append(s), sp.append(e), off.append(off[-1] + s.size)
+    st, sp, off = np.concatenate(st), np.concatenate(sp), np.asarray(off, dtype=np.uint64)
+    n_q = 200_000
+    seg = rng.integers(0, len(segs), n_q).astype(np.int32)
+    pool = np.concatenate([st, sp, np.array([0, 1, 2, 4_294_967_294, 4_294_967_295], np.uint32)])
+    qs = pool[rng.integers(0, pool.size, n_q)].astype(np.int64) + rng.integers(-2, 3, n_q)
+    ln = np.where(rng.random(n_q) < 0.3, 0, rng.integers(0, 5000, n_q))
+    qs = np.clip(qs, 0, 4_294_967_295)
+    qe = np.clip(qs + ln, 0, 4_294_967_295)
+    got = api.count_overlaps(ctx, st, sp, off, seg, qs.astype(np.uint32), qe.astype(np.uint32))
+    ref = orc.count_batch(st, sp, off, seg, qs.astype(np.uint32), qe.astype(np.uint32), threads=8)
+    _eq("adversarial overlap counts", got, ref)
