@@ -8,11 +8,11 @@
 //
 // Design.  A binary search over a 16 K-entry array costs 14 dependent probes per endpoint; on 10^8
 // queries in arbitrary order that is 125 GB of DRAM sectors for 2.4 GB of useful bytes (profiles/r1a).
-// Instead every sorted endpoint array gets a direct-address rank table, built once per index
-// (build_rank_kernel): the segment's coordinate range [lo, hi] is cut into <= n equal power-of-two
-// buckets and cum[b] = #elements < lo + (b << shift).  lower_bound(key) is then cum[b] plus a scan of the
-// one or two elements of bucket b = (key - lo) >> shift: two sectors per endpoint, independent of n,
-// no sorting or bucketing of the queries, results written straight in query order.
+// Instead every sorted endpoint array gets direct-address rank nodes, built once per index
+// (build_rank_kernel): the segment's coordinate range [lo, hi] is cut into equal power-of-two buckets and
+// bucket b = (key - lo) >> shift owns one 32-byte node holding the count of elements before it and the
+// bucket's elements as 16-bit offsets.  lower_bound(key) reads ONE sector per endpoint, independent of n;
+// no sorting or bucketing of the queries is needed and results are written straight in query order.
 #include "common.cuh"
 
 namespace gams {
@@ -29,8 +29,23 @@ __device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t *__restrict__
     return lo;
 }
 
-// ---- rank tables --------------------------------------------------------------------------------
-// Table of segment s starts at entry iv_off[s] + 2 s and has nb + 1 <= n + 1 entries.
+// ---- rank nodes -----------------------------------------------------------------------------------
+// One 32-byte node (one DRAM sector) per bucket: cum = #elements of the segment before the bucket, then up
+// to 14 sorted 16-bit offsets (element - bucket base; 0xFFFF = empty slot).  lower_bound(key) = cum +
+// #offsets < key - base: ONE sector per endpoint.  Buckets are 2^shift wide with shift <= 15 chosen so a
+// segment of n elements has at most n/4 + 1 of them (4..8 elements per bucket on average; the table is
+// 8 B/element at worst).  A bucket with more than 14 elements sets NODE_OVERFLOW and is searched in the raw
+// array between its cum and the next node's; a segment too sparse for 16-bit offsets (shift would exceed
+// 15) sets shift = RANK_PLAIN and is binary-searched directly.
+// Nodes of segment s start at (iv_off[s] >> 2) + 2 s; the node after the last bucket holds cum = n.
+constexpr uint32_t NODE_OVERFLOW = 0x80000000u;
+constexpr uint32_t RANK_PLAIN = 0xFFu;
+
+struct alignas(32) RankNode {
+    uint32_t cum;
+    uint16_t key[14];
+};
+
 __global__ void __launch_bounds__(256)
 rank_params_kernel(const uint32_t *__restrict__ starts, const uint32_t *__restrict__ stops,
                    const uint64_t *__restrict__ iv_off, int64_t n_seg, SegRank *__restrict__ par) {
@@ -42,13 +57,16 @@ rank_params_kernel(const uint32_t *__restrict__ starts, const uint32_t *__restri
     p.off = o;
     p.n = n;
     p.pad = 0;
+    p.pad2[0] = p.pad2[1] = 0;
     for (int which = 0; which < 2; ++which) {
         const uint32_t *a = (which ? stops : starts) + o;
         uint32_t lo = 0, hi = 0, shift = 0;
         if (n) {
             lo = a[0];
             hi = a[n - 1];
-            while ((((uint64_t)(hi - lo)) >> shift) + 1 > (uint64_t)n) ++shift;  // at most n buckets
+            const uint64_t max_buckets = (uint64_t)(n >> 2) + 1;
+            while ((((uint64_t)(hi - lo)) >> shift) + 1 > max_buckets) ++shift;
+            if (shift > 15) shift = RANK_PLAIN;
         }
         p.lo[which] = lo;
         p.hi[which] = hi;
@@ -60,56 +78,76 @@ rank_params_kernel(const uint32_t *__restrict__ starts, const uint32_t *__restri
 __global__ void __launch_bounds__(256)
 build_rank_kernel(const uint32_t *__restrict__ starts, const uint32_t *__restrict__ stops,
                   const uint64_t *__restrict__ iv_off, int64_t n_seg, const SegRank *__restrict__ par,
-                  uint64_t n_entries, uint32_t *__restrict__ cum_starts, uint32_t *__restrict__ cum_stops) {
+                  uint64_t n_nodes, RankNode *__restrict__ node_starts, RankNode *__restrict__ node_stops) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_entries; e += stride) {
-        int64_t lo = 0, hi = n_seg;  // last segment with iv_off[s] + 2 s <= e
+    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_nodes; e += stride) {
+        int64_t lo = 0, hi = n_seg;  // last segment whose node range starts at or before e
         while (hi - lo > 1) {
             const int64_t mid = (lo + hi) >> 1;
-            if (iv_off[mid] + 2 * (uint64_t)mid <= e) lo = mid; else hi = mid;
+            if ((iv_off[mid] >> 2) + 2 * (uint64_t)mid <= e) lo = mid; else hi = mid;
         }
         const SegRank p = par[lo];
-        const uint64_t b = e - (p.off + 2 * (uint64_t)lo);
+        const uint64_t b = e - ((p.off >> 2) + 2 * (uint64_t)lo);
         for (int which = 0; which < 2; ++which) {
-            const uint32_t *a = (which ? stops : starts) + p.off;
-            const uint64_t edge = (uint64_t)p.lo[which] + (b << p.shift[which]);
-            const uint32_t v = (p.n == 0) ? 0u : (edge > (uint64_t)p.hi[which]) ? p.n : lower_bound_u32(a, p.n, (uint32_t)edge);
-            (which ? cum_stops : cum_starts)[e] = v;
+            RankNode nd;
+            nd.cum = p.n;
+#pragma unroll
+            for (int k = 0; k < 14; ++k) nd.key[k] = 0xFFFFu;
+            const uint32_t sh = p.shift[which];
+            if (p.n && sh != RANK_PLAIN) {
+                const uint32_t *a = (which ? stops : starts) + p.off;
+                const uint64_t edge0 = (uint64_t)p.lo[which] + (b << sh), edge1 = edge0 + (1ull << sh);
+                const uint32_t j0 = (edge0 > (uint64_t)p.hi[which]) ? p.n : lower_bound_u32(a, p.n, (uint32_t)edge0);
+                const uint32_t j1 = (edge1 > (uint64_t)p.hi[which]) ? p.n : lower_bound_u32(a, p.n, (uint32_t)edge1);
+                nd.cum = j0;
+                if (j1 - j0 > 14u) nd.cum |= NODE_OVERFLOW;
+                else
+                    for (uint32_t j = j0; j < j1; ++j) nd.key[j - j0] = (uint16_t)(a[j] - (uint32_t)edge0);
+            }
+            (which ? node_stops : node_starts)[e] = nd;
         }
     }
 }
 
-// #elements < key through the rank table
-__device__ __forceinline__ uint32_t ranked_lower_bound(const uint32_t *__restrict__ a, const uint32_t *__restrict__ cum,
+// #elements < key through the rank nodes of one endpoint array of one segment
+__device__ __forceinline__ uint32_t ranked_lower_bound(const uint32_t *__restrict__ a, const RankNode *__restrict__ nodes,
                                                        uint32_t n, uint32_t lo, uint32_t hi, uint32_t shift, uint32_t key) {
     if (n == 0 || key <= lo) return 0;
     if (key > hi) return n;
-    const uint32_t b = (key - lo) >> shift;
-    const uint2 c = make_uint2(__ldg(cum + b), __ldg(cum + b + 1));
-    uint32_t j = c.x;
-    if (c.y - c.x <= 8u) {
-        uint32_t r = c.x;
-        for (; j < c.y; ++j) r += (__ldg(a + j) < key);
-        return r;
+    if (shift == RANK_PLAIN) return lower_bound_u32(a, n, key);
+    const uint32_t d = key - lo, b = d >> shift, koff = d & ((1u << shift) - 1u);
+    const uint4 *np = reinterpret_cast<const uint4 *>(nodes + b);
+    const uint4 w0 = __ldg(np), w1 = __ldg(np + 1);
+    if (w0.x & NODE_OVERFLOW) {
+        const uint32_t j0 = w0.x & ~NODE_OVERFLOW, j1 = __ldg(&nodes[b + 1].cum) & ~NODE_OVERFLOW;
+        return j0 + lower_bound_u32(a + j0, j1 - j0, key);
     }
-    return c.x + lower_bound_u32(a + c.x, c.y - c.x, key);
+    const uint32_t ws[7] = {w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+    uint32_t r = w0.x;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) r += ((ws[k] & 0xFFFFu) < koff) + ((ws[k] >> 16) < koff);
+    return r;
 }
 
 __global__ void __launch_bounds__(256)
 count_overlaps_ranked_kernel(const uint32_t *__restrict__ starts, const uint32_t *__restrict__ stops,
-                             const SegRank *__restrict__ par, const uint32_t *__restrict__ cum_starts,
-                             const uint32_t *__restrict__ cum_stops, int64_t n_seg, int64_t n_q,
+                             const SegRank *__restrict__ par, const RankNode *__restrict__ node_starts,
+                             const RankNode *__restrict__ node_stops, int64_t n_seg, int64_t n_q,
                              const int32_t *__restrict__ q_seg, const uint32_t *__restrict__ q_start,
                              const uint32_t *__restrict__ q_stop, uint32_t *__restrict__ out) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n_q; q += stride) {
         const int32_t s = q_seg[q];
+        const uint32_t qs = q_start[q], qe = q_stop[q];
         uint32_t r = 0;
         if (s >= 0 && s < n_seg) {
-            const SegRank p = par[s];
-            const uint64_t t = p.off + 2 * (uint64_t)s;
-            const uint32_t last = ranked_lower_bound(starts + p.off, cum_starts + t, p.n, p.lo[0], p.hi[0], p.shift[0], q_stop[q]);
-            const uint32_t first = ranked_lower_bound(stops + p.off, cum_stops + t, p.n, p.lo[1], p.hi[1], p.shift[1], q_start[q] + 1u);
+            const uint4 *pp = reinterpret_cast<const uint4 *>(par + s);
+            const uint4 p0 = __ldg(pp), p1 = __ldg(pp + 1), p2 = __ldg(pp + 2);  // off,n,pad | lo0 lo1 hi0 hi1 | sh0 sh1 - -
+            const uint64_t off = (uint64_t)p0.x | ((uint64_t)p0.y << 32);
+            const uint32_t n = p0.z;
+            const uint64_t t = (off >> 2) + 2 * (uint64_t)s;
+            const uint32_t last = ranked_lower_bound(starts + off, node_starts + t, n, p1.x, p1.z, p2.x, qe);
+            const uint32_t first = ranked_lower_bound(stops + off, node_stops + t, n, p1.y, p1.w, p2.y, qs + 1u);
             r = last - first;
         }
         out[q] = r;
@@ -138,18 +176,18 @@ count_overlaps_direct_kernel(const uint32_t *__restrict__ starts, const uint32_t
 }
 
 int32_t build_count_index(gams_cuda_count_plan *p, cudaStream_t st, const uint32_t *d_starts, const uint32_t *d_stops) {
-    const uint64_t n_entries = p->total_iv + 2 * (uint64_t)p->n_seg;
+    const uint64_t n_entries = (p->total_iv >> 2) + 2 * (uint64_t)p->n_seg + 2;
     int32_t rc;
     if ((rc = p->tmp[0].reserve(sizeof(SegRank) * (size_t)std::max<int64_t>(p->n_seg, 1)))) return rc;
-    if ((rc = p->tmp[1].reserve(sizeof(uint32_t) * std::max<uint64_t>(n_entries, 1)))) return rc;
-    if ((rc = p->tmp[2].reserve(sizeof(uint32_t) * std::max<uint64_t>(n_entries, 1)))) return rc;
+    if ((rc = p->tmp[1].reserve(sizeof(RankNode) * n_entries))) return rc;
+    if ((rc = p->tmp[2].reserve(sizeof(RankNode) * n_entries))) return rc;
     if (p->n_seg) {
         rank_params_kernel<<<(unsigned)((p->n_seg + 255) / 256), 256, 0, st>>>(d_starts, d_stops, p->d_iv_off, p->n_seg,
                                                                               p->tmp[0].as<SegRank>());
         uint64_t blocks = (n_entries + 255) / 256;
         if (blocks > 148ull * 32) blocks = 148ull * 32;
         build_rank_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_starts, d_stops, p->d_iv_off, p->n_seg, p->tmp[0].as<SegRank>(),
-                                                            n_entries, p->tmp[1].as<uint32_t>(), p->tmp[2].as<uint32_t>());
+                                                            n_entries, p->tmp[1].as<RankNode>(), p->tmp[2].as<RankNode>());
         p->launches += 2;
         CUDA_TRY(cudaGetLastError());
     }
@@ -176,7 +214,7 @@ int32_t launch_count_overlaps(gams_cuda_count_plan *p, cudaStream_t st, const ui
             if (rc) return rc;
         }
         count_overlaps_ranked_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_starts, d_stops, p->tmp[0].as<SegRank>(),
-                                                                       p->tmp[1].as<uint32_t>(), p->tmp[2].as<uint32_t>(),
+                                                                       p->tmp[1].as<RankNode>(), p->tmp[2].as<RankNode>(),
                                                                        p->n_seg, n_q, d_q_seg, d_q_start, d_q_stop, d_out);
     }
     ++p->launches;

@@ -124,9 +124,15 @@ __device__ __forceinline__ void replay_block(const float *sm, int p0, int lag, f
 // mu and S are evaluated in f64 from per-tile prefix sums of y = x - x_ref and y^2 (errors err_mu, err_S,
 // bounded with N = tile elements and Ymax = max|y|).  If the worst case of the left side still exceeds the
 // worst case of the right side the window certainly signals; if the best case of the left side is below the
-// best case of the right side it certainly does not; otherwise (about 1 window in 10^4 on genomes, and every
-// window inside a constant-GC run, where the reference compares rounding noise with rounding noise) the
-// window is replayed exactly.  Either way the output equals the reference's.
+// best case of the right side it certainly does not; otherwise (a few windows per million on genomes, and
+// every window inside a constant-GC run, where the reference compares rounding noise with rounding noise)
+// the window is replayed exactly.  Either way the output equals the reference's.
+//
+// Mapping: the filter runs one window per thread, strided (lane = consecutive windows: conflict-free f64
+// prefix lookups); inconclusive windows go to a per-tile worklist replayed one per thread; if the list
+// overflows (degenerate tile) the whole tile is replayed with the blocked chains of replay_block.
+constexpr int ZS_LIST_CAP = 256;
+
 template <int MODE>
 __global__ void __launch_bounds__(ZS_THREADS)
 zscore_indep_kernel(const float *__restrict__ x, const uint64_t *__restrict__ off,
@@ -134,11 +140,14 @@ zscore_indep_kernel(const float *__restrict__ x, const uint64_t *__restrict__ of
                     unsigned long long *__restrict__ stats) {
     extern __shared__ __align__(16) unsigned char zs_smem[];
     const int n_el_max = ZS_TILE + lag + 1;
-    double *Y1 = reinterpret_cast<double *>(zs_smem);          // n_el_max + 1 exclusive prefix of y
-    double *Y2 = Y1 + (n_el_max + 1);                          // n_el_max + 1 exclusive prefix of y^2
+    double *Y1 = reinterpret_cast<double *>(zs_smem);            // n_el_max + 1: exclusive prefix of y
+    double *Y2 = Y1 + (n_el_max + 1);                            // n_el_max + 1: exclusive prefix of y^2
     float *sm = reinterpret_cast<float *>(Y2 + (n_el_max + 1));  // zs_swz(n_el_max) + 1 values
-    int8_t *sg = reinterpret_cast<int8_t *>(sm + zs_swz(n_el_max) + 1);
+    int8_t *sg = reinterpret_cast<int8_t *>(sm + zs_swz(n_el_max) + 1);  // ZS_TILE decisions
+    int8_t *cg = sg + ZS_TILE;                                   // ZS_TILE certified decisions (MODE 2), 2 = none
     __shared__ double red[ZS_THREADS / 32][4];
+    __shared__ int list[ZS_LIST_CAP];
+    __shared__ int list_n;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const TileDesc td = tiles[blockIdx.x];
@@ -149,6 +158,7 @@ zscore_indep_kernel(const float *__restrict__ x, const uint64_t *__restrict__ of
     const int64_t lo0 = w0 - 1 - lag;  // series index held at smem position 0 (may be negative)
     const int n_el = nw + lag + 1;
 
+    if (tid == 0) list_n = 0;
     for (int p = tid; p < n_el; p += ZS_THREADS) {
         const int64_t e = lo0 + p;
         sm[zs_swz(p)] = (e >= 0) ? x[base + e] : 0.0f;
@@ -158,14 +168,14 @@ zscore_indep_kernel(const float *__restrict__ x, const uint64_t *__restrict__ of
     const float flag = __ull2float_rn((unsigned long long)lag);  // `data.len() as f32`
     const float flagm1 = __fsub_rn(flag, 1.0f);                   // `len - 1.`
     const bool use_filter = (MODE != 1) && lag >= 2 && threshold >= 0.0f && threshold < 3.0e38f;
+    bool replay_all = !use_filter || MODE == 2;
 
-    double M = 0.0, Ymax = 0.0, xref = 0.0;
     if (use_filter) {
-        // ---- f64 prefix sums of y and y^2 over the tile's elements (thread-contiguous chunks) ----
+        // ---- f64 prefix sums of y = x - xref and y^2 over the tile's elements (thread-contiguous chunks) ----
         const int first_valid = (lo0 < 0) ? (int)(-lo0) : 0;
-        xref = (double)sm[zs_swz(first_valid < n_el ? first_valid : 0)];
-        const int per = (n_el + ZS_THREADS - 1) / ZS_THREADS;
-        const int pb = tid * per, pe = min(pb + per, n_el);
+        const double xref = (double)sm[zs_swz(first_valid < n_el ? first_valid : 0)];
+        const int per = ((n_el + ZS_THREADS - 1) / ZS_THREADS) | 1;  // odd stride: conflict-free chunk starts
+        const int pb = min(tid * per, n_el), pe = min(pb + per, n_el);
         double a1 = 0.0, a2 = 0.0, mx = 0.0, my = 0.0;
         for (int p = pb; p < pe; ++p) {
             const double xv = (double)sm[zs_swz(p)];
@@ -189,7 +199,7 @@ zscore_indep_kernel(const float *__restrict__ x, const uint64_t *__restrict__ of
         if (lane == 31) { red[warp][0] = s1; red[warp][1] = s2; }
         if (lane == 0) { red[warp][2] = mx; red[warp][3] = my; }
         __syncthreads();
-        double b1 = s1 - a1, b2 = s2 - a2;  // exclusive within the warp
+        double b1 = s1 - a1, b2 = s2 - a2, M = 0.0, Ymax = 0.0;  // exclusive within the warp
 #pragma unroll
         for (int w = 0; w < ZS_THREADS / 32; ++w) {
             if (w < warp) { b1 += red[w][0]; b2 += red[w][1]; }
@@ -206,90 +216,94 @@ zscore_indep_kernel(const float *__restrict__ x, const uint64_t *__restrict__ of
         }
         if (pe == n_el && pb < pe) { Y1[n_el] = b1; Y2[n_el] = b2; }
         __syncthreads();
-    }
 
-    const int p0 = tid * ZS_R;     // smem position of chain 0's first element
-    const int64_t i0 = w0 + p0;    // first window of this thread
-    int sig[ZS_R], cert[ZS_R];
-    unsigned todo = 0;             // bit r: window r exists and is past the first `lag` windows
-    unsigned certified = 0;        // bit r: the filter decided window r (decision in cert[r])
-#pragma unroll
-    for (int r = 0; r < ZS_R; ++r) sig[r] = cert[r] = 0;
-
-    if (p0 < nw) {
-#pragma unroll
-        for (int r = 0; r < ZS_R; ++r) {
-            const int64_t i = i0 + r;
-            if (i < n && i >= (int64_t)lag) todo |= 1u << r;
-        }
-        if (use_filter) {
-            const double u = 5.9604644775390625e-8, u64e = 1.1102230246251565e-16;
-            const double dn = (double)lag, dnm1 = (double)flagm1;
-            const double N2 = (double)n_el * (double)n_el;
-            const double E_m = 1.01 * (dn + 2.0) * u * M + 1e-40;
-            const double err_mu = 4.0 * N2 * u64e * Ymax / dn + 1e-300;
-            const double err_S = 16.0 * N2 * u64e * Ymax * Ymax + 1e-40;
-            const double R = (0.6 * dn + 8.0) * u;
-            const double t2 = (double)threshold * (double)threshold;
-            const double k_hi = t2 * (1.0 + R) * (1.0 + R) / dnm1, k_lo = t2 * (1.0 - R) * (1.0 - R) / dnm1;
-            const double slack = E_m + err_mu;
-            const double extra = err_S + dn * E_m * E_m;
-#pragma unroll
-            for (int r = 0; r < ZS_R; ++r) {
-                if (!(todo >> r & 1u)) continue;
-                const int64_t i = i0 + r;
-                const int64_t a = (i - 1 - (int64_t)lag > 0) ? (i - 1 - (int64_t)lag) : 0;
-                const int pa = (int)(a - lo0);
-                const double s1 = Y1[pa + lag] - Y1[pa], s2 = Y2[pa + lag] - Y2[pa];
-                const double mu_y = s1 / dn;
-                const double S = s2 - s1 * mu_y;
-                const double yv = (double)sm[zs_swz((int)(i - lo0))] - xref;
+        // ---- certificate, one window per thread ----
+        const double u = 5.9604644775390625e-8, u64e = 1.1102230246251565e-16;
+        const double dn = (double)lag, dnm1 = (double)flagm1;
+        const double N2 = (double)n_el * (double)n_el;
+        const double E_m = 1.01 * (dn + 2.0) * u * M + 1e-40;
+        const double err_mu = 4.0 * N2 * u64e * Ymax / dn + 1e-300;
+        const double err_S = 16.0 * N2 * u64e * Ymax * Ymax + 1e-40;
+        const double R = (0.6 * dn + 8.0) * u;
+        const double t2 = (double)threshold * (double)threshold;
+        const double k_hi = t2 * (1.0 + R) * (1.0 + R) / dnm1, k_lo = t2 * (1.0 - R) * (1.0 - R) / dnm1;
+        const double slack = E_m + err_mu;
+        const double extra = err_S + dn * E_m * E_m;
+        const double inv_n = 1.0 / dn;  // only to form mu_y; its rounding (<= 2 u64e |s1|/n) is inside err_mu
+        unsigned unc = 0;
+        for (int k = tid; k < nw; k += ZS_THREADS) {
+            const int64_t i = w0 + k;
+            int dec = 0;
+            if (i >= (int64_t)lag) {
+                const int pa = (i - 1 - (int64_t)lag > 0) ? k : (int)(-lo0);  // a - lo0 with a = max(i-1-lag, 0)
+                const double s1w = Y1[pa + lag] - Y1[pa], s2w = Y2[pa + lag] - Y2[pa];
+                const double mu_y = s1w * inv_n;
+                const double S = s2w - s1w * mu_y;
+                const double yv = (double)sm[zs_swz(k + lag + 1)] - xref;
                 const double dev = fabs(yv - mu_y);
                 const double lo = (dev - slack) * (1.0 - 2.0 * u), hi = (dev + slack) * (1.0 + 2.0 * u);
-                if (lo > 0.0 && lo * lo > k_hi * (S + extra)) {
-                    cert[r] = (yv > mu_y) ? 1 : -1;
-                    certified |= 1u << r;
-                } else if (hi * hi < k_lo * fmax(S - err_S, 0.0)) {
-                    cert[r] = 0;
-                    certified |= 1u << r;
+                if (lo > 0.0 && lo * lo > k_hi * (S + extra)) dec = (yv > mu_y) ? 1 : -1;
+                else if (hi * hi < k_lo * fmax(S - err_S, 0.0)) dec = 0;
+                else {
+                    dec = 2;
+                    ++unc;
+                    if (MODE == 0) {
+                        const int slot = atomicAdd(&list_n, 1);
+                        if (slot < ZS_LIST_CAP) list[slot] = k;
+                    }
+                }
+            }
+            if (MODE == 0) sg[k] = (int8_t)dec; else cg[k] = (int8_t)dec;
+        }
+        if (stats) {
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) unc += __shfl_xor_sync(0xFFFFFFFFu, unc, d);
+            if (lane == 0 && unc) atomicAdd(&stats[0], (unsigned long long)unc);
+        }
+        __syncthreads();
+        if (MODE == 0) {
+            const int cnt = list_n;
+            if (cnt > ZS_LIST_CAP) replay_all = true;
+            else {
+                auto ld = [&](int64_t e) { return sm[zs_swz((int)(e - lo0))]; };
+                for (int t = tid; t < cnt; t += ZS_THREADS) {
+                    const int k = list[t];
+                    const int64_t i = w0 + k;
+                    const int64_t a = (i - 1 - (int64_t)lag > 0) ? (i - 1 - (int64_t)lag) : 0;  // stat.rs:30-31 vs :51-52
+                    sg[k] = (int8_t)zscore_decide(ld, a, (uint64_t)lag, flag, flagm1, ld(i), threshold);
                 }
             }
         }
-        const unsigned need = (MODE == 0) ? (todo & ~certified) : todo;
-        int rs[ZS_R];
+    }
+
+    if (replay_all) {  // block-uniform
+        const int p0 = tid * ZS_R;   // smem position of chain 0's first element
+        const int64_t i0 = w0 + p0;  // first window of this thread
+        if (p0 < nw) {
+            int rs[ZS_R];
 #pragma unroll
-        for (int r = 0; r < ZS_R; ++r) rs[r] = 0;
-        if (need) {
-            const bool block_ok = (i0 >= (int64_t)lag + 1) && (p0 + ZS_R <= nw) && (lag >= ZS_R);
-            if (block_ok && (MODE != 0 || __popc(need) >= 2)) {
+            for (int r = 0; r < ZS_R; ++r) rs[r] = 0;
+            if ((i0 >= (int64_t)lag + 1) && (p0 + ZS_R <= nw) && (lag >= ZS_R)) {
                 replay_block(sm, p0, lag, flag, flagm1, threshold, rs);
-            } else {
+            } else {  // ctg head (i <= lag), tile tail, or tiny lag: one window at a time, same arithmetic
                 auto ld = [&](int64_t e) { return sm[zs_swz((int)(e - lo0))]; };
                 for (int r = 0; r < ZS_R; ++r) {
-                    if (!(need >> r & 1u)) continue;
                     const int64_t i = i0 + r;
-                    const int64_t a = (i - 1 - (int64_t)lag > 0) ? (i - 1 - (int64_t)lag) : 0;  // stat.rs:30-31 vs :51-52
+                    if (i >= n || i < (int64_t)lag) continue;
+                    const int64_t a = (i - 1 - (int64_t)lag > 0) ? (i - 1 - (int64_t)lag) : 0;
                     rs[r] = zscore_decide(ld, a, (uint64_t)lag, flag, flagm1, ld(i), threshold);
                 }
             }
+            unsigned bad = 0;
+#pragma unroll
+            for (int r = 0; r < ZS_R; ++r) {
+                if (p0 + r >= nw) continue;
+                if (MODE == 2 && use_filter && cg[p0 + r] != 2 && cg[p0 + r] != (int8_t)rs[r]) ++bad;
+                sg[p0 + r] = (int8_t)rs[r];
+            }
+            if (MODE == 2 && bad && stats) atomicAdd(&stats[1], (unsigned long long)bad);
         }
-        unsigned bad = 0;
-#pragma unroll
-        for (int r = 0; r < ZS_R; ++r) {
-            sig[r] = (need >> r & 1u) ? rs[r] : cert[r];
-            if (MODE == 2 && (certified >> r & 1u) && cert[r] != rs[r]) ++bad;
-        }
-        if (MODE == 2 && bad && stats) atomicAdd(&stats[1], (unsigned long long)bad);
     }
-    if (stats && MODE != 1) {  // uncertain windows (replayed exactly in MODE 0)
-        unsigned long long unc = (unsigned long long)__popc(todo & ~certified);
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) unc += __shfl_xor_sync(0xFFFFFFFFu, unc, d);
-        if (lane == 0 && unc) atomicAdd(&stats[0], unc);
-    }
-#pragma unroll
-    for (int r = 0; r < ZS_R; ++r)
-        if (p0 + r < ZS_TILE) sg[p0 + r] = (int8_t)sig[r];
     __syncthreads();
     for (int p = tid; p < nw; p += ZS_THREADS) signal[base + w0 + p] = sg[p];
 }
@@ -371,7 +385,7 @@ int32_t launch_zscore(const SeriesLayout &L, cudaStream_t st, const float *d_x, 
     const bool tiled = influence == 1.0f && lag <= ZS_MAX_TILED_LAG;
     if (tiled) {
         const int n_el_max = ZS_TILE + (int)lag + 1;
-        const size_t smem_need = (size_t)(n_el_max + 1) * 16 + (size_t)(zs_swz(n_el_max) + 1) * sizeof(float) + ZS_TILE;
+        const size_t smem_need = (size_t)(n_el_max + 1) * 16 + (size_t)(zs_swz(n_el_max) + 1) * sizeof(float) + 2 * ZS_TILE;
         auto go = [&](auto kern) -> int32_t {
             if (smem_need > 48 * 1024)
                 CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_need));
