@@ -330,7 +330,7 @@ GAMS_API void gams_cuda_wave_plan_destroy(gams_cuda_wave_plan *p) {
 GAMS_API uint64_t gams_cuda_wave_plan_total_windows(const gams_cuda_wave_plan *p) { return p ? p->win.total : 0; }
 GAMS_API uint64_t gams_cuda_wave_plan_total_bases(const gams_cuda_wave_plan *p) { return p ? p->total_bases : 0; }
 GAMS_API uint64_t gams_cuda_wave_plan_seq_capacity(const gams_cuda_wave_plan *p) {
-    return p ? ((p->total_bases + 15) & ~15ull) + 16 : 0;
+    return p ? ((p->total_bases + 31) & ~31ull) + 32 : 0;
 }
 GAMS_API uint64_t gams_cuda_wave_plan_launches(const gams_cuda_wave_plan *p) { return p ? p->launches : 0; }
 
@@ -607,7 +607,7 @@ static int32_t upload_seq(PerDevice &pd, int64_t n_ctg, const uint8_t *seq_conca
                           uint8_t **d_seq, uint64_t **d_off) {
     const uint64_t nb = seq_off[n_ctg] - seq_off[0];
     int32_t rc;
-    if ((rc = pd.scratch[0].reserve(((nb + 15) & ~15ull) + 16))) return rc;
+    if ((rc = pd.scratch[0].reserve(((nb + 31) & ~31ull) + 32))) return rc;
     if ((rc = pd.scratch[6].reserve((uint64_t)(n_ctg + 1) * 8))) return rc;
     std::vector<uint64_t> rel((size_t)n_ctg + 1);
     for (int64_t c = 0; c <= n_ctg; ++c) {

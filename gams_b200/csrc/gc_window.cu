@@ -5,7 +5,7 @@
 //
 // Bound: HBM.  Algorithmic traffic 1 B/base read + 4 B/window written (+4 with counts).
 // Design: one CTA per tile of `wt` consecutive windows of one ctg.  The tile's bytes are read
-// exactly once as 16-byte chunks (uint4, coalesced); each chunk is classified with SIMD-in-
+// exactly once, 32 bytes per lane per instruction (LDG.E.256); each 16-byte chunk is classified with SIMD-in-
 // register byte tricks into a 16-bit "is C/G" mask; chunk counts are scanned across the CTA
 // (byte-packed local scan + warp-shuffle scan + one smem hop); a window's count is then
 // prefix(end) - prefix(start) with prefix(x) = chunk_prefix[x>>4] + popc(mask[x>>4] & low(x&15)).
@@ -15,22 +15,40 @@
 
 namespace gams {
 
-// bit (4*i + j) of the result is set iff byte j of word i of the chunk is one of C G c g.
-__device__ __forceinline__ uint32_t gc_nibble(uint32_t w) {
-    uint32_t t = (w & 0xDBDBDBDBu) ^ 0x43434343u;   // byte == 0  <=>  byte | 0x20 in {'c','g'}
-    uint32_t a = (t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;   // bit 7 <=> low seven bits non-zero (no cross-byte carry)
-    uint32_t g = ~(a | t) & 0x80808080u;            // bit 7 <=> byte == 0
-    return (((g >> 7) * 0x00204081u) >> 21) & 0xFu; // gather bits 0,8,16,24 into a nibble
+template <int LUT>
+__device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(d) : "r"(a), "r"(b), "r"(c), "n"(LUT));
+    return d;
 }
 
-__device__ __forceinline__ uint32_t gc_mask16(const uint4 v) {
-    return gc_nibble(v.x) | (gc_nibble(v.y) << 4) | (gc_nibble(v.z) << 8) | (gc_nibble(v.w) << 12);
+// Top nibble of the result: bit (28 + j) is set iff byte j of w is one of C G c g.
+//   t  = (w & 0x5B) ^ 0x43 per byte: zero exactly for {C,G,c,g} and their bit-7 twins  (one LOP3)
+//   a  = t + 0x7F          per byte: bit 7 <=> t != 0, no cross-byte carry (t <= 0x5B)
+//   g7 = ~(a | w) & 0x80   per byte: bit 7 <=> t == 0 and w < 0x80                      (one LOP3)
+//   g7 * 0x204081 moves bits 7,15,23,31 to 28,29,30,31 (all partial products land on distinct bits)
+__device__ __forceinline__ uint32_t gc_gather(uint32_t w) {
+    const uint32_t t = lop3<0x6A>(w, 0x5B5B5B5Bu, 0x43434343u);
+    const uint32_t a = t + 0x7F7F7F7Fu;
+    const uint32_t g7 = lop3<0x02>(a, w, 0x80808080u);
+    return g7 * 0x00204081u;
 }
 
-__device__ __forceinline__ uint4 ld_stream16(const uint4 *p) {
-    uint4 r;  // streamed once: keep it out of L1
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+// bit (4*i + j) is set iff byte j of word i of the 16-byte chunk is one of C G c g
+__device__ __forceinline__ uint32_t gc_mask16(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+    uint32_t m = gc_gather(w0) >> 28;
+    m = lop3<0xEA>(gc_gather(w1) >> 24, 0xF0u, m);     // (a & b) | c
+    m = lop3<0xEA>(gc_gather(w2) >> 20, 0xF00u, m);
+    m = lop3<0xEA>(gc_gather(w3) >> 16, 0xF000u, m);
+    return m;
+}
+
+// 32 bytes per lane in one instruction (Blackwell LDG.E.256), streamed once: read-only path, no L1 allocation
+struct Bytes32 { uint32_t w[8]; };
+__device__ __forceinline__ Bytes32 ld_stream32(const void *p) {
+    Bytes32 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7])
                  : "l"(p));
     return r;
 }
@@ -41,7 +59,11 @@ __device__ __forceinline__ uint32_t prefix_at(const uint32_t *ent, uint32_t x) {
     return (e >> 16) + __popc(e & ((1u << (x & 15u)) - 1u));
 }
 
-template <int K, bool WRITE_CNT>
+constexpr int GC_MAX_BOUNDS = 4096;  // ALIGNED path: window boundaries kept per tile (u16 each)
+
+// ALIGNED: size % step == 0, so windows share boundaries: prefix(boundary) is evaluated once per boundary
+// and a window is the difference of two table entries.
+template <int K, bool WRITE_CNT, bool ALIGNED>
 __global__ void __launch_bounds__(GC_THREADS)
 gc_window_kernel(const uint8_t *__restrict__ seq, const uint64_t *__restrict__ seq_off,
                  const uint64_t *__restrict__ win_off, const TileDesc *__restrict__ tiles,
@@ -51,6 +73,7 @@ gc_window_kernel(const uint8_t *__restrict__ seq, const uint64_t *__restrict__ s
     __shared__ uint32_t ent[NCH + 1];
     __shared__ __align__(16) uint8_t c8[NCH];
     __shared__ uint32_t wsum[GC_THREADS / 32];
+    __shared__ uint16_t bnd[ALIGNED ? GC_MAX_BOUNDS : 1];
 
     const int tid = threadIdx.x;
     const TileDesc td = tiles[blockIdx.x];
@@ -58,26 +81,31 @@ gc_window_kernel(const uint8_t *__restrict__ seq, const uint64_t *__restrict__ s
     const uint32_t n_c = (uint32_t)(win_off[td.item + 1] - wbase);
     const uint32_t nw = min((uint32_t)wt, n_c - td.first);
     const uint64_t byte0 = seq_off[td.item] + (uint64_t)td.first * (uint64_t)step;  // first byte needed
-    const uint64_t chunk0 = byte0 >> 4;
-    const uint32_t lead = (uint32_t)(byte0 & 15u);
+    const uint32_t lead = (uint32_t)(byte0 & 31u);
     const uint32_t span = (nw - 1u) * (uint32_t)step + (uint32_t)size;
     const uint32_t nch = (lead + span + 15u) >> 4;  // <= NCH by construction of wt
 
-    // ---- phase 1: classify (block-strided => each warp instruction reads 512 contiguous bytes)
-    const uint4 *src = reinterpret_cast<const uint4 *>(seq) + chunk0;
-    uint4 v[K];
+    // ---- phase 1: classify.  Lane t of group j reads bytes [32 (j*256 + t), +32): 1 KB contiguous per warp instruction
+    const uint8_t *src = seq + (byte0 - lead);
+    Bytes32 v[K / 2];
 #pragma unroll
-    for (int j = 0; j < K; ++j) {
-        const uint32_t ci = j * GC_THREADS + tid;
-        v[j] = (ci < nch) ? ld_stream16(src + ci) : make_uint4(0, 0, 0, 0);
+    for (int j = 0; j < K / 2; ++j) {
+        const uint32_t pi = j * GC_THREADS + tid;
+        if (2u * pi < nch) v[j] = ld_stream32(src + 32u * pi);
+        else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[j].w[q] = 0u;
+        }
     }
     uint16_t *ent16 = reinterpret_cast<uint16_t *>(ent);
 #pragma unroll
-    for (int j = 0; j < K; ++j) {
-        const uint32_t ci = j * GC_THREADS + tid;
-        const uint32_t m = gc_mask16(v[j]);
-        ent16[2 * ci] = (uint16_t)m;
-        c8[ci] = (uint8_t)__popc(m);
+    for (int j = 0; j < K / 2; ++j) {
+        const uint32_t pi = j * GC_THREADS + tid;
+        const uint32_t m0 = gc_mask16(v[j].w[0], v[j].w[1], v[j].w[2], v[j].w[3]);
+        const uint32_t m1 = gc_mask16(v[j].w[4], v[j].w[5], v[j].w[6], v[j].w[7]);
+        ent16[4 * pi] = (uint16_t)m0;
+        ent16[4 * pi + 2] = (uint16_t)m1;
+        reinterpret_cast<uint16_t *>(c8)[pi] = (uint16_t)(__popc(m0) | (__popc(m1) << 8));
     }
     __syncthreads();
 
@@ -116,11 +144,23 @@ gc_window_kernel(const uint8_t *__restrict__ seq, const uint64_t *__restrict__ s
 
     // ---- phase 2: windows
     const uint64_t obase = wbase + td.first;
-    for (uint32_t w = tid; w < nw; w += GC_THREADS) {
-        const uint32_t x0 = lead + w * (uint32_t)step;
-        const uint32_t cnt = prefix_at(ent, x0 + (uint32_t)size) - prefix_at(ent, x0);
-        gc_out[obase + w] = __ldg(gc_tab + cnt);
-        if (WRITE_CNT) cnt_out[obase + w] = cnt;
+    if (ALIGNED) {
+        const uint32_t r = (uint32_t)size / (uint32_t)step;
+        const uint32_t nb = nw + r;  // boundaries lead + m*step, m = 0 .. nw-1+r
+        for (uint32_t m = tid; m < nb; m += GC_THREADS) bnd[m] = (uint16_t)prefix_at(ent, lead + m * (uint32_t)step);
+        __syncthreads();
+        for (uint32_t w = tid; w < nw; w += GC_THREADS) {
+            const uint32_t cnt = (uint32_t)bnd[w + r] - (uint32_t)bnd[w];
+            gc_out[obase + w] = __ldg(gc_tab + cnt);
+            if (WRITE_CNT) cnt_out[obase + w] = cnt;
+        }
+    } else {
+        for (uint32_t w = tid; w < nw; w += GC_THREADS) {
+            const uint32_t x0 = lead + w * (uint32_t)step;
+            const uint32_t cnt = prefix_at(ent, x0 + (uint32_t)size) - prefix_at(ent, x0);
+            gc_out[obase + w] = __ldg(gc_tab + cnt);
+            if (WRITE_CNT) cnt_out[obase + w] = cnt;
+        }
     }
 }
 
@@ -155,7 +195,7 @@ gc_window_generic_kernel(const uint8_t *__restrict__ seq, const uint64_t *__rest
 GcGeom plan_gc_geometry(int32_t size, int32_t step) {
     GcGeom g;
     for (int k : {4, 8}) {
-        const int64_t span_cap = (int64_t)GC_THREADS * k * 16 - 15;  // worst case lead = 15
+        const int64_t span_cap = (int64_t)GC_THREADS * k * 16 - 31;  // worst case lead = 31
         if (size <= span_cap / 2 || (k == 8 && size <= span_cap)) {
             g.k = k;
             int64_t wt = (span_cap - size) / step + 1;
@@ -169,27 +209,28 @@ GcGeom plan_gc_geometry(int32_t size, int32_t step) {
     return g;
 }
 
-template <int K>
+template <int K, bool ALIGNED>
 static void launch_tiled(const gams_cuda_wave_plan *p, cudaStream_t st, const uint8_t *d_seq, uint32_t *d_cnt,
                          float *d_gc) {
     const unsigned grid = (unsigned)p->geom.n_tiles;
     if (d_cnt)
-        gc_window_kernel<K, true><<<grid, GC_THREADS, 0, st>>>(d_seq, p->d_seq_off, p->win.d_off, p->d_gtiles,
-                                                               p->d_gc_tab, p->size, p->step, p->geom.wt, d_cnt, d_gc);
+        gc_window_kernel<K, true, ALIGNED><<<grid, GC_THREADS, 0, st>>>(d_seq, p->d_seq_off, p->win.d_off, p->d_gtiles,
+                                                                        p->d_gc_tab, p->size, p->step, p->geom.wt, d_cnt, d_gc);
     else
-        gc_window_kernel<K, false><<<grid, GC_THREADS, 0, st>>>(d_seq, p->d_seq_off, p->win.d_off, p->d_gtiles,
-                                                                p->d_gc_tab, p->size, p->step, p->geom.wt, nullptr, d_gc);
+        gc_window_kernel<K, false, ALIGNED><<<grid, GC_THREADS, 0, st>>>(d_seq, p->d_seq_off, p->win.d_off, p->d_gtiles,
+                                                                         p->d_gc_tab, p->size, p->step, p->geom.wt, nullptr, d_gc);
 }
 
 int32_t launch_gc_windows(const gams_cuda_wave_plan *p, cudaStream_t st, const uint8_t *d_seq, uint32_t *d_cnt,
                           float *d_gc, uint64_t *launches) {
     if (p->win.total == 0) return GAMS_CUDA_OK;
-    if ((reinterpret_cast<uintptr_t>(d_seq) & 15u) != 0) {
-        set_error("gc windows: d_seq must be 16-byte aligned");
+    if ((reinterpret_cast<uintptr_t>(d_seq) & 31u) != 0) {
+        set_error("gc windows: d_seq must be 32-byte aligned");
         return GAMS_CUDA_EINVAL;
     }
-    if (p->geom.k == 4) launch_tiled<4>(p, st, d_seq, d_cnt, d_gc);
-    else if (p->geom.k == 8) launch_tiled<8>(p, st, d_seq, d_cnt, d_gc);
+    const bool aligned = p->size % p->step == 0 && (int64_t)p->geom.wt + p->size / p->step <= GC_MAX_BOUNDS;
+    if (p->geom.k == 4) aligned ? launch_tiled<4, true>(p, st, d_seq, d_cnt, d_gc) : launch_tiled<4, false>(p, st, d_seq, d_cnt, d_gc);
+    else if (p->geom.k == 8) aligned ? launch_tiled<8, true>(p, st, d_seq, d_cnt, d_gc) : launch_tiled<8, false>(p, st, d_seq, d_cnt, d_gc);
     else {
         uint64_t blocks = (p->win.total + 7) / 8;
         if (blocks > 148ull * 64) blocks = 148ull * 64;

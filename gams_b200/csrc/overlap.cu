@@ -109,6 +109,17 @@ build_rank_kernel(const uint32_t *__restrict__ starts, const uint32_t *__restric
     }
 }
 
+// One 32-byte node in one instruction: Blackwell's 256-bit global load (LDG.E.256, PTX ld.global.v8.b32,
+// sm_100+), read-only path, not allocated in L1 (each node is used once per query).
+struct Node8 { uint32_t w[8]; };
+__device__ __forceinline__ Node8 ld_node(const void *p) {
+    Node8 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7])
+                 : "l"(p));
+    return r;
+}
+
 // #elements < key through the rank nodes of one endpoint array of one segment
 __device__ __forceinline__ uint32_t ranked_lower_bound(const uint32_t *__restrict__ a, const RankNode *__restrict__ nodes,
                                                        uint32_t n, uint32_t lo, uint32_t hi, uint32_t shift, uint32_t key) {
@@ -116,17 +127,18 @@ __device__ __forceinline__ uint32_t ranked_lower_bound(const uint32_t *__restric
     if (key > hi) return n;
     if (shift == RANK_PLAIN) return lower_bound_u32(a, n, key);
     const uint32_t d = key - lo, b = d >> shift, koff = d & ((1u << shift) - 1u);
-    const uint4 *np = reinterpret_cast<const uint4 *>(nodes + b);
-    const uint4 w0 = __ldg(np), w1 = __ldg(np + 1);
-    if (w0.x & NODE_OVERFLOW) {
-        const uint32_t j0 = w0.x & ~NODE_OVERFLOW, j1 = __ldg(&nodes[b + 1].cum) & ~NODE_OVERFLOW;
+    const Node8 nd = ld_node(nodes + b);
+    if (nd.w[0] & NODE_OVERFLOW) {
+        const uint32_t j0 = nd.w[0] & ~NODE_OVERFLOW, j1 = __ldg(&nodes[b + 1].cum) & ~NODE_OVERFLOW;
         return j0 + lower_bound_u32(a + j0, j1 - j0, key);
     }
-    const uint32_t ws[7] = {w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-    uint32_t r = w0.x;
+    // Two 16-bit offsets per word, koff <= 0x7FFF, valid offsets <= 0x7FFF, empty slots 0xFFFF:
+    // (h | 0x8000) - koff keeps bit 15 exactly when h >= koff and never borrows across the halves.
+    const uint32_t kk = koff * 0x00010001u;
+    uint32_t ge = 0;  // bit (15 - k) / (31 - k): offset of word k is >= koff
 #pragma unroll
-    for (int k = 0; k < 7; ++k) r += ((ws[k] & 0xFFFFu) < koff) + ((ws[k] >> 16) < koff);
-    return r;
+    for (int k = 0; k < 7; ++k) ge |= (((nd.w[k + 1] | 0x80008000u) - kk) & 0x80008000u) >> k;
+    return nd.w[0] + 14u - (uint32_t)__popc(ge);
 }
 
 __global__ void __launch_bounds__(256)

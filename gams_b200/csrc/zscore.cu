@@ -159,9 +159,14 @@ zscore_indep_kernel(const float *__restrict__ x, const uint64_t *__restrict__ of
     const int n_el = nw + lag + 1;
 
     if (tid == 0) list_n = 0;
-    for (int p = tid; p < n_el; p += ZS_THREADS) {
-        const int64_t e = lo0 + p;
-        sm[zs_swz(p)] = (e >= 0) ? x[base + e] : 0.0f;
+    const int first_valid = (lo0 < 0) ? (int)(-lo0) : 0;  // smem position of series index max(lo0, 0)
+    {
+        const float *xt = x + base + (lo0 < 0 ? 0 : lo0);  // element at smem position first_valid
+        const float x0 = xt[0];                             // n_el > first_valid always (nw >= 1)
+        for (int p = tid; p < n_el; p += ZS_THREADS) {
+            const int q = p - first_valid;
+            sm[zs_swz(p)] = (q >= 0) ? xt[q] : x0;  // positions before the series start are never part of a stats window
+        }
     }
     __syncthreads();
 
@@ -172,18 +177,17 @@ zscore_indep_kernel(const float *__restrict__ x, const uint64_t *__restrict__ of
 
     if (use_filter) {
         // ---- f64 prefix sums of y = x - xref and y^2 over the tile's elements (thread-contiguous chunks) ----
-        const int first_valid = (lo0 < 0) ? (int)(-lo0) : 0;
-        const double xref = (double)sm[zs_swz(first_valid < n_el ? first_valid : 0)];
+        const double xref = (double)sm[zs_swz(first_valid)];
         const int per = ((n_el + ZS_THREADS - 1) / ZS_THREADS) | 1;  // odd stride: conflict-free chunk starts
         const int pb = min(tid * per, n_el), pe = min(pb + per, n_el);
-        double a1 = 0.0, a2 = 0.0, mx = 0.0, my = 0.0;
+        double a1 = 0.0, a2 = 0.0;
+        float mxf = 0.0f;
         for (int p = pb; p < pe; ++p) {
-            const double xv = (double)sm[zs_swz(p)];
-            const double y = (p >= first_valid) ? xv - xref : 0.0;
+            const float xf = sm[zs_swz(p)];
+            const double y = (double)xf - xref;
             a1 += y;
-            a2 += y * y;
-            mx = fmax(mx, fabs(xv));
-            my = fmax(my, fabs(y));
+            a2 = fma(y, y, a2);
+            mxf = fmaxf(mxf, fabsf(xf));
         }
         double s1 = a1, s2 = a2;
 #pragma unroll
@@ -192,27 +196,23 @@ zscore_indep_kernel(const float *__restrict__ x, const uint64_t *__restrict__ of
             if (lane >= d) { s1 += t1; s2 += t2; }
         }
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            mx = fmax(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, d));
-            my = fmax(my, __shfl_xor_sync(0xFFFFFFFFu, my, d));
-        }
+        for (int d = 16; d > 0; d >>= 1) mxf = fmaxf(mxf, __shfl_xor_sync(0xFFFFFFFFu, mxf, d));
         if (lane == 31) { red[warp][0] = s1; red[warp][1] = s2; }
-        if (lane == 0) { red[warp][2] = mx; red[warp][3] = my; }
+        if (lane == 0) red[warp][2] = (double)mxf;
         __syncthreads();
-        double b1 = s1 - a1, b2 = s2 - a2, M = 0.0, Ymax = 0.0;  // exclusive within the warp
+        double b1 = s1 - a1, b2 = s2 - a2, M = 0.0;  // exclusive within the warp
 #pragma unroll
         for (int w = 0; w < ZS_THREADS / 32; ++w) {
             if (w < warp) { b1 += red[w][0]; b2 += red[w][1]; }
             M = fmax(M, red[w][2]);
-            Ymax = fmax(Ymax, red[w][3]);
         }
+        const double Ymax = 2.0 * M;  // |y| = |x - xref| <= 2 max|x|
         for (int p = pb; p < pe; ++p) {
             Y1[p] = b1;
             Y2[p] = b2;
-            const double xv = (double)sm[zs_swz(p)];
-            const double y = (p >= first_valid) ? xv - xref : 0.0;
+            const double y = (double)sm[zs_swz(p)] - xref;
             b1 += y;
-            b2 += y * y;
+            b2 = fma(y, y, b2);
         }
         if (pe == n_el && pb < pe) { Y1[n_el] = b1; Y2[n_el] = b2; }
         __syncthreads();
@@ -226,22 +226,24 @@ zscore_indep_kernel(const float *__restrict__ x, const uint64_t *__restrict__ of
         const double err_S = 16.0 * N2 * u64e * Ymax * Ymax + 1e-40;
         const double R = (0.6 * dn + 8.0) * u;
         const double t2 = (double)threshold * (double)threshold;
-        const double k_hi = t2 * (1.0 + R) * (1.0 + R) / dnm1, k_lo = t2 * (1.0 - R) * (1.0 - R) / dnm1;
+        // (1 -+ 2u)^2 of the left side folded into the right-side factors (both inflated a little further)
+        const double k_hi = t2 * (1.0 + R) * (1.0 + R) * (1.0 + 5.0 * u) / dnm1;
+        const double k_lo = t2 * (1.0 - R) * (1.0 - R) * (1.0 - 5.0 * u) / dnm1;
         const double slack = E_m + err_mu;
         const double extra = err_S + dn * E_m * E_m;
         const double inv_n = 1.0 / dn;  // only to form mu_y; its rounding (<= 2 u64e |s1|/n) is inside err_mu
+        const int k_min = (w0 >= (int64_t)lag) ? 0 : (int)((int64_t)lag - w0);  // windows before `lag` never signal
         unsigned unc = 0;
         for (int k = tid; k < nw; k += ZS_THREADS) {
-            const int64_t i = w0 + k;
             int dec = 0;
-            if (i >= (int64_t)lag) {
-                const int pa = (i - 1 - (int64_t)lag > 0) ? k : (int)(-lo0);  // a - lo0 with a = max(i-1-lag, 0)
+            if (k >= k_min) {
+                const int pa = max(k, first_valid);  // a - lo0 with a = max(i-1-lag, 0)  (stat.rs:30-31 vs :51-52)
                 const double s1w = Y1[pa + lag] - Y1[pa], s2w = Y2[pa + lag] - Y2[pa];
                 const double mu_y = s1w * inv_n;
-                const double S = s2w - s1w * mu_y;
+                const double S = fma(-s1w, mu_y, s2w);
                 const double yv = (double)sm[zs_swz(k + lag + 1)] - xref;
                 const double dev = fabs(yv - mu_y);
-                const double lo = (dev - slack) * (1.0 - 2.0 * u), hi = (dev + slack) * (1.0 + 2.0 * u);
+                const double lo = dev - slack, hi = dev + slack;
                 if (lo > 0.0 && lo * lo > k_hi * (S + extra)) dec = (yv > mu_y) ? 1 : -1;
                 else if (hi * hi < k_lo * fmax(S - err_S, 0.0)) dec = 0;
                 else {

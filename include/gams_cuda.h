@@ -112,7 +112,8 @@ int32_t gams_cuda_wave_plan_create(gams_cuda_ctx *ctx, int32_t dev_index, int64_
 void gams_cuda_wave_plan_destroy(gams_cuda_wave_plan *plan);
 uint64_t gams_cuda_wave_plan_total_windows(const gams_cuda_wave_plan *plan);
 uint64_t gams_cuda_wave_plan_total_bases(const gams_cuda_wave_plan *plan);
-/* bytes the caller must make readable behind d_seq (total bases rounded up for 16-byte loads) */
+/* bytes the caller must make readable behind d_seq (total bases rounded up for 32-byte loads);
+ * d_seq itself must be 32-byte aligned */
 uint64_t gams_cuda_wave_plan_seq_capacity(const gams_cuda_wave_plan *plan);
 /* Kernel A only: d_seq -> d_gc_count (optional) / d_gc. */
 int32_t gams_cuda_wave_gc_dev(gams_cuda_wave_plan *plan, void *stream, const uint8_t *d_seq,
