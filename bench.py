@@ -77,20 +77,21 @@ class ClockSampler:
         self.gpu, self.rows, self.stop, self.th, self.how = gpu_index, [], False, None, None
         self.t0 = self.t1 = None
 
-    def _nvml_loop(self):
-        import pynvml as nv
-        h = nv.nvmlDeviceGetHandleByIndex(self.gpu)
-        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+    def _nvml_sample(self):
+        nv, h = self.nv, self.h
+        r = nv.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
         bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+        self.rows.append((time.perf_counter(), float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), float(self.mx),
+                          [k for k, b in bits.items() if r & b]))
+
+    def _nvml_loop(self):
         while not self.stop:
             try:
-                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
-                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                self.rows.append((time.perf_counter(), float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), float(mx),
-                                  [k for k, b in bits.items() if r & b]))
+                self._nvml_sample()
             except Exception:
                 pass
-            time.sleep(0.005)
+            time.sleep(0.004)
 
     def _smi_loop(self):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -111,6 +112,9 @@ class ClockSampler:
         try:
             import pynvml as nv
             nv.nvmlInit()
+            self.nv, self.h = nv, nv.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+            self._nvml_sample()
             self.how, target = "nvml", self._nvml_loop
         except Exception:
             self.how, target = "nvidia-smi", self._smi_loop
@@ -122,6 +126,11 @@ class ClockSampler:
         self.t0 = time.perf_counter()
 
     def mark_end(self):
+        if self.how == "nvml":  # the GPU is still busy here (the caller has not synchronised yet)
+            try:
+                self._nvml_sample()
+            except Exception:
+                pass
         self.t1 = time.perf_counter()
 
     def __exit__(self, *a):
@@ -307,8 +316,8 @@ def main():
             plan.signal(stream, d_gc, THRESHOLD, args.influence, d_sig, d_filt)
             ev[k][2].record()
         t_end.record()
-        barrier()
         clk.mark_end()
+        barrier()
     launches = plan.launches - l0
     z_uncertain, _ = ctx.zscore_stats(reset=True)
     z_uncertain /= max(1, args.steps + args.warmup)
@@ -366,6 +375,13 @@ def main():
                                              LAG, THRESHOLD, args.influence, woff.ctypes.data_as(C.c_void_p), None,
                                              h_gc_ptr, h_sig_ptr))
 
+        # context for the e2e number: what this box's PCIe link gives for one plain pinned copy each way
+        tpc = []
+        for kind in (1, 2):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            api.check(L.gams_cuda_memcpy_probe(ctx.handle, h_seq_ptr, min(n_bases, 1 << 30), kind))
+            tpc.append(min(n_bases, 1 << 30) / (time.perf_counter() - t0) / 1e9)
         n_e2e = max(1, min(args.steps, 5))
         for _ in range(min(args.warmup, 2)):
             e2e_step()
@@ -381,6 +397,7 @@ def main():
                 as_np(h_gc_ptr, n_win, np.float32).view(np.uint32), d_gc.cpu().numpy().view(np.uint32)))
         e2e = {"value": total_bases * n_e2e / dt / 1e9, "unit": "Gbp/s", "h2d_bytes_per_step": int(n_bases),
                "d2h_bytes_per_step": int(n_win * 5), "steps": n_e2e, "ms_per_step": dt / n_e2e * 1e3,
+               "pcie_probe_gbs": {"h2d": tpc[0], "d2h": tpc[1]},
                "api": "gams_cuda_wave_batch (host pointers, pinned)", "timer": "host wall clock around the blocking call, max over ranks"}
         L.gams_cuda_host_free(h_gc_ptr)
         L.gams_cuda_host_free(h_sig_ptr)

@@ -51,6 +51,7 @@ def load() -> C.CDLL:
         "gams_cuda_zscore_stats": (i32, [vp, vp, i32]),
         "gams_cuda_host_alloc": (vp, [sz]),
         "gams_cuda_host_free": (None, [vp]),
+        "gams_cuda_memcpy_probe": (i32, [vp, vp, sz, i32]),
         "gams_cuda_wave_nwin": (i64, [i64, i32, i32]),
         "gams_cuda_wave_win_offsets": (i32, [i64, vp, i32, i32, vp]),
         "gams_cuda_partition": (i32, [i64, vp, i32, vp]),

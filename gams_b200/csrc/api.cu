@@ -55,7 +55,9 @@ int32_t SeriesLayout::build(const uint64_t *h_off, int64_t n, cudaStream_t st) {
     total = n ? h_off[n] - h_off[0] : 0;
     min_len = ~0ull;
     std::vector<TileDesc> zt;
-    std::vector<uint64_t> rel((size_t)n + 1);
+    std::vector<uint64_t> &rel = this->h_off;
+    rel.assign((size_t)n + 1, 0);
+    h_ztile_off.assign((size_t)n + 1, 0);
     for (int64_t c = 0; c <= n; ++c) rel[c] = h_off[c] - h_off[0];
     for (int64_t c = 0; c < n; ++c) {
         if (h_off[c + 1] < h_off[c]) {
@@ -65,6 +67,7 @@ int32_t SeriesLayout::build(const uint64_t *h_off, int64_t n, cudaStream_t st) {
         const uint64_t len = h_off[c + 1] - h_off[c];
         min_len = std::min(min_len, len);
         for (uint64_t w = 0; w < len; w += ZS_TILE) zt.push_back({(uint32_t)c, (uint32_t)w});
+        h_ztile_off[c + 1] = zt.size();
     }
     if (n == 0) min_len = 0;
     n_ztiles = zt.size();
@@ -221,6 +224,19 @@ GAMS_API void *gams_cuda_host_alloc(size_t bytes) {
     return p;
 }
 
+GAMS_API int32_t gams_cuda_memcpy_probe(gams_cuda_ctx *ctx, void *host, size_t bytes, int32_t kind) {
+    ARG_CHECK(ctx && host && (kind == 1 || kind == 2), "memcpy_probe: bad argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    PerDevice &pd = ctx->devs[0];
+    DeviceGuard g(pd.device);
+    int32_t rc;
+    if ((rc = pd.scratch[7].reserve(bytes ? bytes : 1))) return rc;
+    if (kind == 1) CUDA_TRY(cudaMemcpyAsync(pd.scratch[7].p, host, bytes, cudaMemcpyHostToDevice, pd.stream));
+    else CUDA_TRY(cudaMemcpyAsync(host, pd.scratch[7].p, bytes, cudaMemcpyDeviceToHost, pd.stream));
+    CUDA_TRY(cudaStreamSynchronize(pd.stream));
+    return GAMS_CUDA_OK;
+}
+
 GAMS_API void gams_cuda_host_free(void *p) {
     if (p) cudaFreeHost(p);
 }
@@ -289,10 +305,12 @@ GAMS_API int32_t gams_cuda_wave_plan_create(gams_cuda_ctx *ctx, int32_t dev_inde
     }
     p->geom = plan_gc_geometry(size, step);
     std::vector<TileDesc> gt;
+    p->h_gtile_off.assign((size_t)n_ctg + 1, 0);
     if (p->geom.k) {
         for (int64_t c = 0; c < n_ctg; ++c) {
             const uint64_t n_c = p->h_win_off[c + 1] - p->h_win_off[c];
             for (uint64_t w = 0; w < n_c; w += (uint64_t)p->geom.wt) gt.push_back({(uint32_t)c, (uint32_t)w});
+            p->h_gtile_off[c + 1] = gt.size();
         }
         p->geom.n_tiles = gt.size();
         ARG_CHECK(gt.size() < (1ull << 31), "wave_plan_create: too many tiles");
@@ -338,7 +356,7 @@ GAMS_API int32_t gams_cuda_wave_gc_dev(gams_cuda_wave_plan *p, void *stream, con
                                        uint32_t *d_gc_count, float *d_gc) {
     ARG_CHECK(p && d_gc && (d_seq || p->total_bases == 0), "wave_gc_dev: NULL argument");
     DeviceGuard g(p->device);
-    return launch_gc_windows(p, (cudaStream_t)stream, d_seq, d_gc_count, d_gc, &p->launches);
+    return launch_gc_windows(p, (cudaStream_t)stream, d_seq, d_gc_count, d_gc, &p->launches, 0, p->n_ctg);
 }
 
 GAMS_API int32_t gams_cuda_wave_signal_dev(gams_cuda_wave_plan *p, void *stream, const float *d_gc, float threshold,
@@ -346,7 +364,7 @@ GAMS_API int32_t gams_cuda_wave_signal_dev(gams_cuda_wave_plan *p, void *stream,
     ARG_CHECK(p && d_signal && d_gc, "wave_signal_dev: NULL argument");
     DeviceGuard g(p->device);
     return launch_zscore(p->win, (cudaStream_t)stream, d_gc, p->lag, threshold, influence, d_filtered, d_signal,
-                         &p->launches, p->ctx->zscore_mode, p->ctx->devs[p->dev_index].d_zstats);
+                         &p->launches, p->ctx->zscore_mode, p->ctx->devs[p->dev_index].d_zstats, 0, p->n_ctg);
 }
 
 // ================================================================================ wave: host ====
@@ -385,17 +403,52 @@ static int32_t wave_on_device(gams_cuda_ctx *ctx, int d, int64_t c0, int64_t c1,
     uint32_t *d_cnt = gc_count ? pd.scratch[2].as<uint32_t>() : nullptr;
     int8_t *d_sig = signal ? pd.scratch[3].as<int8_t>() : nullptr;
     float *d_filt = need_filt ? pd.scratch[4].as<float>() : nullptr;
-    cudaStream_t st = pd.stream;
-    CUDA_TRY(cudaMemcpyAsync(d_seq, seq_concat + seq_off[c0], nb, cudaMemcpyHostToDevice, st));
-    if ((rc = gams_cuda_wave_gc_dev(plan, st, d_seq, d_cnt, d_gc))) return rc;
-    if (signal && (rc = gams_cuda_wave_signal_dev(plan, st, d_gc, threshold, influence, d_filt, d_sig))) return rc;
-    const uint64_t wo = win_off[c0];
-    if (nwn) {
-        CUDA_TRY(cudaMemcpyAsync(gc + wo, d_gc, nwn * sizeof(float), cudaMemcpyDeviceToHost, st));
-        if (gc_count) CUDA_TRY(cudaMemcpyAsync(gc_count + wo, d_cnt, nwn * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-        if (signal) CUDA_TRY(cudaMemcpyAsync(signal + wo, d_sig, nwn, cudaMemcpyDeviceToHost, st));
+    // Pipeline over slices of ~64 MB of sequence: H2D of slice k+1, kernels of slice k and D2H of slice k-1
+    // run concurrently on three streams (PCIe is full duplex; the kernels are far shorter than either copy).
+    const int64_t n = c1 - c0;
+    const uint64_t slice_bytes = 64ull << 20;
+    std::vector<int64_t> cut{0};
+    for (int64_t c = 0; c < n; ++c)
+        if (plan->h_seq_off[c + 1] - plan->h_seq_off[cut.back()] >= slice_bytes || c + 1 == n) cut.push_back(c + 1);
+    const size_t n_sl = cut.size() - 1;
+    std::vector<cudaEvent_t> ev_in(n_sl), ev_k(n_sl);
+    for (size_t k = 0; k < n_sl; ++k) {
+        CUDA_TRY(cudaEventCreateWithFlags(&ev_in[k], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&ev_k[k], cudaEventDisableTiming));
     }
-    CUDA_TRY(cudaStreamSynchronize(st));
+    struct EvGuard {
+        std::vector<cudaEvent_t> &a, &b;
+        ~EvGuard() {
+            for (auto e : a) cudaEventDestroy(e);
+            for (auto e : b) cudaEventDestroy(e);
+        }
+    } ev_guard{ev_in, ev_k};
+    const uint64_t wo = win_off[c0];
+    const uint8_t *h_seq = seq_concat + seq_off[c0];
+    CUDA_TRY(cudaStreamSynchronize(pd.stream));  // plan tables were uploaded on pd.stream
+    for (size_t k = 0; k < n_sl; ++k) {
+        const int64_t a = cut[k], b = cut[k + 1];
+        const uint64_t b0 = plan->h_seq_off[a], b1 = plan->h_seq_off[b];
+        const uint64_t w0 = plan->h_win_off[a], w1 = plan->h_win_off[b];
+        if (b1 > b0) CUDA_TRY(cudaMemcpyAsync(d_seq + b0, h_seq + b0, b1 - b0, cudaMemcpyHostToDevice, pd.copy_in));
+        CUDA_TRY(cudaEventRecord(ev_in[k], pd.copy_in));
+        CUDA_TRY(cudaStreamWaitEvent(pd.stream, ev_in[k], 0));
+        if ((rc = launch_gc_windows(plan, pd.stream, d_seq, d_cnt, d_gc, &plan->launches, a, b))) return rc;
+        if (signal && (rc = launch_zscore(plan->win, pd.stream, d_gc, lag, threshold, influence, d_filt, d_sig,
+                                          &plan->launches, ctx->zscore_mode, pd.d_zstats, a, b)))
+            return rc;
+        CUDA_TRY(cudaEventRecord(ev_k[k], pd.stream));
+        CUDA_TRY(cudaStreamWaitEvent(pd.copy_out, ev_k[k], 0));
+        if (w1 > w0) {
+            CUDA_TRY(cudaMemcpyAsync(gc + wo + w0, d_gc + w0, (w1 - w0) * sizeof(float), cudaMemcpyDeviceToHost, pd.copy_out));
+            if (gc_count)
+                CUDA_TRY(cudaMemcpyAsync(gc_count + wo + w0, d_cnt + w0, (w1 - w0) * sizeof(uint32_t), cudaMemcpyDeviceToHost, pd.copy_out));
+            if (signal) CUDA_TRY(cudaMemcpyAsync(signal + wo + w0, d_sig + w0, w1 - w0, cudaMemcpyDeviceToHost, pd.copy_out));
+        }
+    }
+    CUDA_TRY(cudaStreamSynchronize(pd.copy_out));
+    CUDA_TRY(cudaStreamSynchronize(pd.stream));
+    (void)nb;
     return GAMS_CUDA_OK;
 }
 
@@ -444,7 +497,7 @@ GAMS_API int32_t gams_cuda_thresholding_batch(gams_cuda_ctx *ctx, int64_t n_seri
     cudaStream_t st = pd.stream;
     CUDA_TRY(cudaMemcpyAsync(d_x, data + off[0], total * sizeof(float), cudaMemcpyHostToDevice, st));
     if ((rc = launch_zscore(L, st, d_x, lag, threshold, influence, pd.scratch[4].as<float>(), d_sig, nullptr,
-                            ctx->zscore_mode, pd.d_zstats)))
+                            ctx->zscore_mode, pd.d_zstats, 0, n_series)))
         return rc;
     CUDA_TRY(cudaMemcpyAsync(signal + off[0], d_sig, total, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));

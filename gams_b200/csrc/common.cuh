@@ -92,6 +92,8 @@ struct SeriesLayout {
     uint64_t *d_off = nullptr;       // n_series+1
     TileDesc *d_ztiles = nullptr;    // z-score tiles
     uint64_t n_ztiles = 0;
+    std::vector<uint64_t> h_off;       // n_series+1 (relative to the first series)
+    std::vector<uint64_t> h_ztile_off; // n_series+1: first z-score tile of each series
     int32_t build(const uint64_t *h_off, int64_t n, cudaStream_t st);
     void release();
 };
@@ -125,6 +127,7 @@ struct gams_cuda_wave_plan {
     gams::SeriesLayout win;          // window offsets + z-score tiles
     gams::GcGeom geom;
     gams::TileDesc *d_gtiles = nullptr;
+    std::vector<uint64_t> h_gtile_off;  // n_ctg+1: first Kernel-A tile of each ctg
     float *d_gc_tab = nullptr;       // (float)c / (float)size for c = 0..size (host-computed IEEE divide)
     uint64_t launches = 0;
 };
@@ -147,11 +150,12 @@ struct gams_cuda_count_plan {
 
 namespace gams {
 // kernel launchers (each returns 0 or a GAMS_CUDA_E* code; all asynchronous on `st`)
+// [c0, c1): ctg / series sub-range to process (the host API pipelines copy and compute over such slices)
 int32_t launch_gc_windows(const gams_cuda_wave_plan *p, cudaStream_t st, const uint8_t *d_seq,
-                          uint32_t *d_cnt, float *d_gc, uint64_t *launches);
+                          uint32_t *d_cnt, float *d_gc, uint64_t *launches, int64_t c0, int64_t c1);
 int32_t launch_zscore(const SeriesLayout &L, cudaStream_t st, const float *d_x, uint64_t lag, float threshold,
                       float influence, float *d_filtered, int8_t *d_signal, uint64_t *launches, int mode,
-                      unsigned long long *d_stats);
+                      unsigned long long *d_stats, int64_t s0, int64_t s1);
 int32_t launch_count_overlaps(gams_cuda_count_plan *p, cudaStream_t st, const uint32_t *d_starts,
                               const uint32_t *d_stops, int64_t n_q, const int32_t *d_q_seg,
                               const uint32_t *d_q_start, const uint32_t *d_q_stop, int32_t grouped,

@@ -59,6 +59,13 @@ __device__ __forceinline__ uint32_t prefix_at(const uint32_t *ent, uint32_t x) {
     return (e >> 16) + __popc(e & ((1u << (x & 15u)) - 1u));
 }
 
+// opaque 32-bit subtract: keeps the table index a plain u32 (no 64-bit range reasoning in the address math)
+__device__ __forceinline__ uint32_t sub_u32(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("sub.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+
 constexpr int GC_MAX_BOUNDS = 4096;  // ALIGNED path: window boundaries kept per tile (u16 each)
 
 // ALIGNED: size % step == 0, so windows share boundaries: prefix(boundary) is evaluated once per boundary
@@ -143,23 +150,28 @@ gc_window_kernel(const uint8_t *__restrict__ seq, const uint64_t *__restrict__ s
     __syncthreads();
 
     // ---- phase 2: windows
-    const uint64_t obase = wbase + td.first;
+    float *__restrict__ out = gc_out + (wbase + td.first);
+    uint32_t *__restrict__ outc = WRITE_CNT ? cnt_out + (wbase + td.first) : nullptr;
     if (ALIGNED) {
         const uint32_t r = (uint32_t)size / (uint32_t)step;
         const uint32_t nb = nw + r;  // boundaries lead + m*step, m = 0 .. nw-1+r
+#pragma unroll 2
         for (uint32_t m = tid; m < nb; m += GC_THREADS) bnd[m] = (uint16_t)prefix_at(ent, lead + m * (uint32_t)step);
         __syncthreads();
-        for (uint32_t w = tid; w < nw; w += GC_THREADS) {
-            const uint32_t cnt = (uint32_t)bnd[w + r] - (uint32_t)bnd[w];
-            gc_out[obase + w] = __ldg(gc_tab + cnt);
-            if (WRITE_CNT) cnt_out[obase + w] = cnt;
+        const uint16_t *b0 = bnd + tid, *b1 = bnd + tid + r;
+#pragma unroll 4
+        for (uint32_t w = tid; w < nw; w += GC_THREADS, b0 += GC_THREADS, b1 += GC_THREADS) {
+            const uint32_t cnt = sub_u32(*b1, *b0);
+            out[w] = __ldg(gc_tab + cnt);
+            if (WRITE_CNT) outc[w] = cnt;
         }
     } else {
+#pragma unroll 2
         for (uint32_t w = tid; w < nw; w += GC_THREADS) {
             const uint32_t x0 = lead + w * (uint32_t)step;
-            const uint32_t cnt = prefix_at(ent, x0 + (uint32_t)size) - prefix_at(ent, x0);
-            gc_out[obase + w] = __ldg(gc_tab + cnt);
-            if (WRITE_CNT) cnt_out[obase + w] = cnt;
+            const uint32_t cnt = sub_u32(prefix_at(ent, x0 + (uint32_t)size), prefix_at(ent, x0));
+            out[w] = __ldg(gc_tab + cnt);
+            if (WRITE_CNT) outc[w] = cnt;
         }
     }
 }
@@ -167,11 +179,11 @@ gc_window_kernel(const uint8_t *__restrict__ seq, const uint64_t *__restrict__ s
 // Any window size (used when one window does not fit a tile): one warp per window, byte scan.
 __global__ void __launch_bounds__(256)
 gc_window_generic_kernel(const uint8_t *__restrict__ seq, const uint64_t *__restrict__ seq_off,
-                         const uint64_t *__restrict__ win_off, int64_t n_ctg, uint64_t total_win, int size,
-                         int step, uint32_t *__restrict__ cnt_out, float *__restrict__ gc_out) {
+                         const uint64_t *__restrict__ win_off, int64_t n_ctg, uint64_t g_begin, uint64_t g_end,
+                         int size, int step, uint32_t *__restrict__ cnt_out, float *__restrict__ gc_out) {
     const int lane = threadIdx.x & 31;
     const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    for (uint64_t g = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < total_win; g += warps) {
+    for (uint64_t g = g_begin + (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); g < g_end; g += warps) {
         int64_t lo = 0, hi = n_ctg;  // last ctg with win_off[c] <= g
         while (hi - lo > 1) {
             const int64_t mid = (lo + hi) >> 1;
@@ -211,31 +223,34 @@ GcGeom plan_gc_geometry(int32_t size, int32_t step) {
 
 template <int K, bool ALIGNED>
 static void launch_tiled(const gams_cuda_wave_plan *p, cudaStream_t st, const uint8_t *d_seq, uint32_t *d_cnt,
-                         float *d_gc) {
-    const unsigned grid = (unsigned)p->geom.n_tiles;
+                         float *d_gc, int64_t c0, int64_t c1) {
+    const uint64_t t0 = p->h_gtile_off[c0], t1 = p->h_gtile_off[c1];
+    if (t1 == t0) return;
+    const unsigned grid = (unsigned)(t1 - t0);
     if (d_cnt)
-        gc_window_kernel<K, true, ALIGNED><<<grid, GC_THREADS, 0, st>>>(d_seq, p->d_seq_off, p->win.d_off, p->d_gtiles,
+        gc_window_kernel<K, true, ALIGNED><<<grid, GC_THREADS, 0, st>>>(d_seq, p->d_seq_off, p->win.d_off, p->d_gtiles + t0,
                                                                         p->d_gc_tab, p->size, p->step, p->geom.wt, d_cnt, d_gc);
     else
-        gc_window_kernel<K, false, ALIGNED><<<grid, GC_THREADS, 0, st>>>(d_seq, p->d_seq_off, p->win.d_off, p->d_gtiles,
+        gc_window_kernel<K, false, ALIGNED><<<grid, GC_THREADS, 0, st>>>(d_seq, p->d_seq_off, p->win.d_off, p->d_gtiles + t0,
                                                                          p->d_gc_tab, p->size, p->step, p->geom.wt, nullptr, d_gc);
 }
 
 int32_t launch_gc_windows(const gams_cuda_wave_plan *p, cudaStream_t st, const uint8_t *d_seq, uint32_t *d_cnt,
-                          float *d_gc, uint64_t *launches) {
-    if (p->win.total == 0) return GAMS_CUDA_OK;
+                          float *d_gc, uint64_t *launches, int64_t c0, int64_t c1) {
+    const uint64_t g0 = p->h_win_off[c0], g1 = p->h_win_off[c1];
+    if (g1 == g0) return GAMS_CUDA_OK;
     if ((reinterpret_cast<uintptr_t>(d_seq) & 31u) != 0) {
         set_error("gc windows: d_seq must be 32-byte aligned");
         return GAMS_CUDA_EINVAL;
     }
     const bool aligned = p->size % p->step == 0 && (int64_t)p->geom.wt + p->size / p->step <= GC_MAX_BOUNDS;
-    if (p->geom.k == 4) aligned ? launch_tiled<4, true>(p, st, d_seq, d_cnt, d_gc) : launch_tiled<4, false>(p, st, d_seq, d_cnt, d_gc);
-    else if (p->geom.k == 8) aligned ? launch_tiled<8, true>(p, st, d_seq, d_cnt, d_gc) : launch_tiled<8, false>(p, st, d_seq, d_cnt, d_gc);
+    if (p->geom.k == 4) aligned ? launch_tiled<4, true>(p, st, d_seq, d_cnt, d_gc, c0, c1) : launch_tiled<4, false>(p, st, d_seq, d_cnt, d_gc, c0, c1);
+    else if (p->geom.k == 8) aligned ? launch_tiled<8, true>(p, st, d_seq, d_cnt, d_gc, c0, c1) : launch_tiled<8, false>(p, st, d_seq, d_cnt, d_gc, c0, c1);
     else {
-        uint64_t blocks = (p->win.total + 7) / 8;
+        uint64_t blocks = (g1 - g0 + 7) / 8;
         if (blocks > 148ull * 64) blocks = 148ull * 64;
-        gc_window_generic_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_seq, p->d_seq_off, p->win.d_off, p->n_ctg,
-                                                                   p->win.total, p->size, p->step, d_cnt, d_gc);
+        gc_window_generic_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_seq, p->d_seq_off, p->win.d_off, p->n_ctg, g0, g1,
+                                                                   p->size, p->step, d_cnt, d_gc);
     }
     if (launches) ++*launches;
     CUDA_TRY(cudaGetLastError());

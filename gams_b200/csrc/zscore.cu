@@ -314,11 +314,11 @@ zscore_indep_kernel(const float *__restrict__ x, const uint64_t *__restrict__ of
 // any influence: one warp per series, speculative 32-window look-ahead, `filt` in global scratch
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
-zscore_seq_kernel(const float *__restrict__ x_all, const uint64_t *__restrict__ off, int64_t n_series, uint64_t lag,
-                  float threshold, float influence, float *filt_all, int8_t *__restrict__ signal) {
+zscore_seq_kernel(const float *__restrict__ x_all, const uint64_t *__restrict__ off, int64_t s_begin, int64_t s_end,
+                  uint64_t lag, float threshold, float influence, float *filt_all, int8_t *__restrict__ signal) {
     const int lane = threadIdx.x & 31;
-    const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (c >= n_series) return;
+    const int64_t c = s_begin + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (c >= s_end) return;
     const uint64_t base = off[c];
     const int64_t n = (int64_t)(off[c + 1] - base);
     const float *x = x_all + base;
@@ -373,12 +373,12 @@ zscore_seq_kernel(const float *__restrict__ x_all, const uint64_t *__restrict__ 
 
 int32_t launch_zscore(const SeriesLayout &L, cudaStream_t st, const float *d_x, uint64_t lag, float threshold,
                       float influence, float *d_filtered, int8_t *d_signal, uint64_t *launches, int mode,
-                      unsigned long long *d_stats) {
+                      unsigned long long *d_stats, int64_t s0, int64_t s1) {
     if (lag == 0) {
         set_error("thresholding: lag must be >= 1 (the reference underflows lag-1, stat.rs:30)");
         return GAMS_CUDA_EINVAL;
     }
-    if (L.n_series == 0) return GAMS_CUDA_OK;
+    if (L.n_series == 0 || s1 <= s0) return GAMS_CUDA_OK;
     if (L.min_len < lag) {
         set_error("thresholding: a series has %llu values but lag is %llu (the reference panics, stat.rs:30)",
                   (unsigned long long)L.min_len, (unsigned long long)lag);
@@ -391,8 +391,10 @@ int32_t launch_zscore(const SeriesLayout &L, cudaStream_t st, const float *d_x, 
         auto go = [&](auto kern) -> int32_t {
             if (smem_need > 48 * 1024)
                 CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_need));
-            kern<<<(unsigned)L.n_ztiles, ZS_THREADS, smem_need, st>>>(d_x, L.d_off, L.d_ztiles, (int)lag, threshold,
-                                                                     d_signal, d_stats);
+            const uint64_t t0 = L.h_ztile_off[s0], t1 = L.h_ztile_off[s1];
+            if (t1 > t0)
+                kern<<<(unsigned)(t1 - t0), ZS_THREADS, smem_need, st>>>(d_x, L.d_off, L.d_ztiles + t0, (int)lag, threshold,
+                                                                        d_signal, d_stats);
             return GAMS_CUDA_OK;
         };
         int32_t rc = mode == 1 ? go(zscore_indep_kernel<1>) : mode == 2 ? go(zscore_indep_kernel<2>) : go(zscore_indep_kernel<0>);
@@ -402,9 +404,8 @@ int32_t launch_zscore(const SeriesLayout &L, cudaStream_t st, const float *d_x, 
             set_error("thresholding: influence != 1 (or lag too large for the tiled path) needs the d_filtered scratch");
             return GAMS_CUDA_EINVAL;
         }
-        const unsigned grid = (unsigned)((L.n_series + 3) / 4);
-        zscore_seq_kernel<<<grid, 128, 0, st>>>(d_x, L.d_off, L.n_series, lag, threshold, influence, d_filtered,
-                                                d_signal);
+        const unsigned grid = (unsigned)((s1 - s0 + 3) / 4);
+        zscore_seq_kernel<<<grid, 128, 0, st>>>(d_x, L.d_off, s0, s1, lag, threshold, influence, d_filtered, d_signal);
     }
     if (launches) ++*launches;
     CUDA_TRY(cudaGetLastError());

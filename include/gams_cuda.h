@@ -68,6 +68,9 @@ int32_t gams_cuda_zscore_stats(gams_cuda_ctx *ctx, uint64_t *out2, int32_t reset
  * too, only slower. */
 void *gams_cuda_host_alloc(size_t bytes);
 void gams_cuda_host_free(void *p);
+/* One plain copy of `bytes` between `host` and a device scratch buffer on device 0 of ctx, synchronous:
+ * kind 1 = host->device, 2 = device->host (overwrites host!).  For measuring what the PCIe link gives. */
+int32_t gams_cuda_memcpy_probe(gams_cuda_ctx *ctx, void *host, size_t bytes, int32_t kind);
 
 /* ---------------------------------------------------------------- window arithmetic -------- */
 /* gams::sliding, src/libs/window.rs:78-94: number of windows on a ctg of ctg_len bases.
