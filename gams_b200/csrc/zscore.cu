@@ -133,16 +133,44 @@ __device__ __forceinline__ void replay_block(const float *sm, int p0, int lag, f
 // overflows (degenerate tile) the whole tile is replayed with the blocked chains of replay_block.
 constexpr int ZS_LIST_CAP = 256;
 
+// Tile-independent factors of the certificate, evaluated once on the host (no f64 divisions on the device).
+struct ZsConst {
+    double k_hi, k_lo;  // thr^2 (1 +- R)^2 (1 +- 5u) / (n - 1)
+    double c_slack;     // slack   = c_slack * M + tiny           (E_m + err_mu)
+    double c_errS;      // err_S   = c_errS * M^2 + tiny
+    double c_extra;     // extra   = c_extra * M^2 + tiny          (err_S + n E_m^2)
+    double inv_n;       // 1 / n (its rounding is inside err_mu)
+};
+
+static ZsConst make_zs_const(uint64_t lag, float threshold) {
+    const double u = 5.9604644775390625e-8, u64e = 1.1102230246251565e-16;
+    const float flag = (float)lag, flagm1 = flag - 1.0f;  // `data.len() as f32`, `len - 1.`
+    const double dn = (double)lag, dnm1 = (double)flagm1;
+    const double n_el = (double)(ZS_TILE + lag + 1), N2 = n_el * n_el;
+    const double cE = 1.01 * (dn + 2.0) * u;                  // E_m    = cE M
+    const double cMu = 4.0 * N2 * u64e * 2.0 / dn;            // err_mu = cMu M        (Ymax <= 2 M)
+    const double cS = 16.0 * N2 * u64e * 4.0;                 // err_S  = cS M^2
+    const double R = (0.6 * dn + 8.0) * u;
+    const double t2 = (double)threshold * (double)threshold;
+    ZsConst c;
+    c.k_hi = t2 * (1.0 + R) * (1.0 + R) * (1.0 + 5.0 * u) / dnm1;
+    c.k_lo = t2 * (1.0 - R) * (1.0 - R) * (1.0 - 5.0 * u) / dnm1;
+    c.c_slack = (cE + cMu) * (1.0 + 1e-9);
+    c.c_errS = cS;
+    c.c_extra = (cS + dn * cE * cE) * (1.0 + 1e-9);
+    c.inv_n = 1.0 / dn;
+    return c;
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(ZS_THREADS)
 zscore_indep_kernel(const float *__restrict__ x, const uint64_t *__restrict__ off,
-                    const TileDesc *__restrict__ tiles, int lag, float threshold, int8_t *__restrict__ signal,
-                    unsigned long long *__restrict__ stats) {
+                    const TileDesc *__restrict__ tiles, int lag, float threshold, const ZsConst zc,
+                    int8_t *__restrict__ signal, unsigned long long *__restrict__ stats) {
     extern __shared__ __align__(16) unsigned char zs_smem[];
     const int n_el_max = ZS_TILE + lag + 1;
-    double *Y1 = reinterpret_cast<double *>(zs_smem);            // n_el_max + 1: exclusive prefix of y
-    double *Y2 = Y1 + (n_el_max + 1);                            // n_el_max + 1: exclusive prefix of y^2
-    float *sm = reinterpret_cast<float *>(Y2 + (n_el_max + 1));  // zs_swz(n_el_max) + 1 values
+    double2 *YY = reinterpret_cast<double2 *>(zs_smem);          // n_el_max + 1: exclusive prefixes of (y, y^2)
+    float *sm = reinterpret_cast<float *>(YY + (n_el_max + 1));  // zs_swz(n_el_max) + 1 values
     int8_t *sg = reinterpret_cast<int8_t *>(sm + zs_swz(n_el_max) + 1);  // ZS_TILE decisions
     int8_t *cg = sg + ZS_TILE;                                   // ZS_TILE certified decisions (MODE 2), 2 = none
     __shared__ double red[ZS_THREADS / 32][4];
@@ -182,6 +210,7 @@ zscore_indep_kernel(const float *__restrict__ x, const uint64_t *__restrict__ of
         const int pb = min(tid * per, n_el), pe = min(pb + per, n_el);
         double a1 = 0.0, a2 = 0.0;
         float mxf = 0.0f;
+#pragma unroll 3
         for (int p = pb; p < pe; ++p) {
             const float xf = sm[zs_swz(p)];
             const double y = (double)xf - xref;
@@ -200,59 +229,48 @@ zscore_indep_kernel(const float *__restrict__ x, const uint64_t *__restrict__ of
         if (lane == 31) { red[warp][0] = s1; red[warp][1] = s2; }
         if (lane == 0) red[warp][2] = (double)mxf;
         __syncthreads();
-        double b1 = s1 - a1, b2 = s2 - a2, M = 0.0;  // exclusive within the warp
+        double b1 = s1 - a1, b2 = s2 - a2, M = 0.0;  // exclusive within the warp; M = max|x| over the tile
 #pragma unroll
         for (int w = 0; w < ZS_THREADS / 32; ++w) {
             if (w < warp) { b1 += red[w][0]; b2 += red[w][1]; }
             M = fmax(M, red[w][2]);
         }
-        const double Ymax = 2.0 * M;  // |y| = |x - xref| <= 2 max|x|
+#pragma unroll 3
         for (int p = pb; p < pe; ++p) {
-            Y1[p] = b1;
-            Y2[p] = b2;
+            YY[p] = make_double2(b1, b2);
             const double y = (double)sm[zs_swz(p)] - xref;
             b1 += y;
             b2 = fma(y, y, b2);
         }
-        if (pe == n_el && pb < pe) { Y1[n_el] = b1; Y2[n_el] = b2; }
+        if (pe == n_el && pb < pe) YY[n_el] = make_double2(b1, b2);
         __syncthreads();
 
-        // ---- certificate, one window per thread ----
-        const double u = 5.9604644775390625e-8, u64e = 1.1102230246251565e-16;
-        const double dn = (double)lag, dnm1 = (double)flagm1;
-        const double N2 = (double)n_el * (double)n_el;
-        const double E_m = 1.01 * (dn + 2.0) * u * M + 1e-40;
-        const double err_mu = 4.0 * N2 * u64e * Ymax / dn + 1e-300;
-        const double err_S = 16.0 * N2 * u64e * Ymax * Ymax + 1e-40;
-        const double R = (0.6 * dn + 8.0) * u;
-        const double t2 = (double)threshold * (double)threshold;
-        // (1 -+ 2u)^2 of the left side folded into the right-side factors (both inflated a little further)
-        const double k_hi = t2 * (1.0 + R) * (1.0 + R) * (1.0 + 5.0 * u) / dnm1;
-        const double k_lo = t2 * (1.0 - R) * (1.0 - R) * (1.0 - 5.0 * u) / dnm1;
-        const double slack = E_m + err_mu;
-        const double extra = err_S + dn * E_m * E_m;
-        const double inv_n = 1.0 / dn;  // only to form mu_y; its rounding (<= 2 u64e |s1|/n) is inside err_mu
+        // ---- certificate, one window per thread, branch-free except for the rare inconclusive case ----
+        const double slack = fma(zc.c_slack, M, 1e-40);
+        const double err_S = fma(zc.c_errS, M * M, 1e-40);
+        const double extra = fma(zc.c_extra, M * M, 2e-40);
         const int k_min = (w0 >= (int64_t)lag) ? 0 : (int)((int64_t)lag - w0);  // windows before `lag` never signal
         unsigned unc = 0;
+#pragma unroll 2
         for (int k = tid; k < nw; k += ZS_THREADS) {
-            int dec = 0;
-            if (k >= k_min) {
-                const int pa = max(k, first_valid);  // a - lo0 with a = max(i-1-lag, 0)  (stat.rs:30-31 vs :51-52)
-                const double s1w = Y1[pa + lag] - Y1[pa], s2w = Y2[pa + lag] - Y2[pa];
-                const double mu_y = s1w * inv_n;
-                const double S = fma(-s1w, mu_y, s2w);
-                const double yv = (double)sm[zs_swz(k + lag + 1)] - xref;
-                const double dev = fabs(yv - mu_y);
-                const double lo = dev - slack, hi = dev + slack;
-                if (lo > 0.0 && lo * lo > k_hi * (S + extra)) dec = (yv > mu_y) ? 1 : -1;
-                else if (hi * hi < k_lo * fmax(S - err_S, 0.0)) dec = 0;
-                else {
-                    dec = 2;
-                    ++unc;
-                    if (MODE == 0) {
-                        const int slot = atomicAdd(&list_n, 1);
-                        if (slot < ZS_LIST_CAP) list[slot] = k;
-                    }
+            // a - lo0 with a = max(i-1-lag, 0) (stat.rs:30-31 vs :51-52); the min() only bites for windows before `lag`
+            const int pa = min(max(k, first_valid), n_el - lag);
+            const double2 A = YY[pa], B = YY[pa + lag];
+            const double s1w = B.x - A.x, s2w = B.y - A.y;
+            const double mu_y = s1w * zc.inv_n;
+            const double S = fma(-s1w, mu_y, s2w);
+            const double d = ((double)sm[zs_swz(k + lag + 1)] - xref) - mu_y;
+            const double dev = fabs(d);
+            const double lo = dev - slack, hi = dev + slack;
+            const bool yes = (lo > 0.0) & (lo * lo > zc.k_hi * (S + extra));
+            const bool no = hi * hi < zc.k_lo * fmax(S - err_S, 0.0);
+            int dec = yes ? (d > 0.0 ? 1 : -1) : (no ? 0 : 2);
+            if (k < k_min) dec = 0;
+            if (dec == 2) {
+                ++unc;
+                if (MODE == 0) {
+                    const int slot = atomicAdd(&list_n, 1);
+                    if (slot < ZS_LIST_CAP) list[slot] = k;
                 }
             }
             if (MODE == 0) sg[k] = (int8_t)dec; else cg[k] = (int8_t)dec;
@@ -388,12 +406,13 @@ int32_t launch_zscore(const SeriesLayout &L, cudaStream_t st, const float *d_x, 
     if (tiled) {
         const int n_el_max = ZS_TILE + (int)lag + 1;
         const size_t smem_need = (size_t)(n_el_max + 1) * 16 + (size_t)(zs_swz(n_el_max) + 1) * sizeof(float) + 2 * ZS_TILE;
+        const ZsConst zc = make_zs_const(lag, threshold);
         auto go = [&](auto kern) -> int32_t {
             if (smem_need > 48 * 1024)
                 CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_need));
             const uint64_t t0 = L.h_ztile_off[s0], t1 = L.h_ztile_off[s1];
             if (t1 > t0)
-                kern<<<(unsigned)(t1 - t0), ZS_THREADS, smem_need, st>>>(d_x, L.d_off, L.d_ztiles + t0, (int)lag, threshold,
+                kern<<<(unsigned)(t1 - t0), ZS_THREADS, smem_need, st>>>(d_x, L.d_off, L.d_ztiles + t0, (int)lag, threshold, zc,
                                                                         d_signal, d_stats);
             return GAMS_CUDA_OK;
         };

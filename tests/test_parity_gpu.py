@@ -380,3 +380,13 @@ def test_count_overlaps_adversarial_distributions(ctx, orc):
     got = api.count_overlaps(ctx, st, sp, off, seg, qs.astype(np.uint32), qe.astype(np.uint32))
     ref = orc.count_batch(st, sp, off, seg, qs.astype(np.uint32), qe.astype(np.uint32), threads=8)
     _eq("adversarial overlap counts", got, ref)
+
+
+def test_thresholding_lag_longer_than_a_tile(ctx, orc):
+    """lag > 1024 (one z-score tile): the first tiles hold only windows before `lag`."""
+    rng = np.random.default_rng(61)
+    s = rng.normal(0.45, 0.05, 9000).astype(np.float32)
+    s[rng.integers(0, s.size, 60)] += 0.5
+    for lag in (1500, 2500):
+        got = api.thresholding_algo(ctx, s, lag, 3.0, 1.0)
+        _eq(f"lag {lag}", got, orc.thresholding_algo(s, lag, 3.0, 1.0))
