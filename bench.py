@@ -282,8 +282,8 @@ def main():
     # ---- workload: this rank's ctgs ------------------------------------------------------------
     g_off, _ = layout(int(args.bases))
     if args.scaling == "strong" and world > 1:
-        part = api.partition(g_off, world)
-        seq_off = (g_off[part[rank]:part[rank + 1] + 1] - g_off[part[rank]]).astype(np.uint64)
+        from gams_b200 import shard
+        _, _, seq_off = shard.shard_for_rank(g_off, rank, world)
     else:
         seq_off = g_off
     n_ctg = seq_off.size - 1

@@ -390,3 +390,23 @@ def test_thresholding_lag_longer_than_a_tile(ctx, orc):
     for lag in (1500, 2500):
         got = api.thresholding_algo(ctx, s, lag, 3.0, 1.0)
         _eq(f"lag {lag}", got, orc.thresholding_algo(s, lag, 3.0, 1.0))
+
+
+# ------------------------------------------------------------------------- several devices in one ctx
+def test_multi_device_context_shards_by_ctg(orc):
+    """gams_cuda_create over every visible device: the host API shards ctgs / queries over them and the
+    gathered result is identical to the oracle (and so to the single-device result)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    g = synth.genome(3_000_000, seed=71)
+    cuts = np.sort(np.random.default_rng(72).choice(np.arange(20_000, 2_980_000), 11, replace=False))
+    seqs = [g[a:b] for a, b in zip(np.concatenate(([0], cuts)), np.concatenate((cuts, [g.size])))]
+    with api.Context() as mctx:
+        assert mctx.num_devices == torch.cuda.device_count()
+        for infl in (1.0, 0.5):
+            _check_wave(mctx, orc, seqs, 100, 10, 100, 3.0, infl)
+        lens = [s.size for s in seqs]
+        st, sp, off = synth.rg_index(lens, [5000] * len(lens), seed=73)
+        seg, qs, qe = synth.queries(lens, 400_000, seed=74, grouped=False)
+        _eq("multi-device counts", api.count_overlaps(mctx, st, sp, off, seg, qs, qe), orc.count_batch(st, sp, off, seg, qs, qe, threads=8))
