@@ -386,9 +386,12 @@ def main():
         for _ in range(min(args.warmup, 2)):
             e2e_step()
         barrier()
+        per_step = []
         t0 = time.perf_counter()
         for _ in range(n_e2e):
+            ts = time.perf_counter()
             e2e_step()
+            per_step.append((time.perf_counter() - ts) * 1e3)
         torch.cuda.synchronize()
         dt = max_over_ranks(time.perf_counter() - t0)
         if rank == 0:
@@ -397,7 +400,7 @@ def main():
                 as_np(h_gc_ptr, n_win, np.float32).view(np.uint32), d_gc.cpu().numpy().view(np.uint32)))
         e2e = {"value": total_bases * n_e2e / dt / 1e9, "unit": "Gbp/s", "h2d_bytes_per_step": int(n_bases),
                "d2h_bytes_per_step": int(n_win * 5), "steps": n_e2e, "ms_per_step": dt / n_e2e * 1e3,
-               "pcie_probe_gbs": {"h2d": tpc[0], "d2h": tpc[1]},
+               "pcie_probe_gbs": {"h2d": tpc[0], "d2h": tpc[1]}, "ms_each_step_rank0": [round(x, 2) for x in per_step],
                "api": "gams_cuda_wave_batch (host pointers, pinned)", "timer": "host wall clock around the blocking call, max over ranks"}
         L.gams_cuda_host_free(h_gc_ptr)
         L.gams_cuda_host_free(h_sig_ptr)
@@ -480,20 +483,36 @@ def bench_count(args, ctx, L, dev, rank, world, g_off, barrier, max_over_ranks, 
             res["bit_exact_sample"] = bool(np.array_equal(d_out[sel].cpu().numpy().view(np.uint32), ref))
         out[name] = res
         if not grouped and not args.skip_e2e:
-            hs = [t.cpu().numpy() for t in (d_st, d_sp, q_seg, q_s, q_e)]
-            h_out = np.empty(n_q, dtype=np.uint32)
+            # end to end through gams_cuda_count_overlaps: index + queries in pinned HOST memory, H2D and D2H inside
+            ptrs, hs = [], []
+            for t in (d_st, d_sp, q_seg, q_s, q_e):
+                pp = pinned(t.numel() * 4, L)
+                h = as_np(pp, t.numel(), np.int32)
+                torch.from_numpy(h).copy_(t)
+                ptrs.append(pp), hs.append(h)
+            p_out = pinned(n_q * 4, L)
+            torch.cuda.synchronize()
+            ivp = iv_off.ctypes.data_as(C.c_void_p)
+
+            def count_e2e():
+                api.check(L.gams_cuda_count_overlaps(ctx.handle, iv_off.size - 1, ptrs[0], ptrs[1], ivp, n_q, ptrs[2], ptrs[3],
+                                                     ptrs[4], p_out))
+
             n_e = max(1, min(args.steps, 3))
-            api.count_overlaps(ctx, hs[0].view(np.uint32), hs[1].view(np.uint32), iv_off, hs[2], hs[3].view(np.uint32), hs[4].view(np.uint32))
+            count_e2e()
             barrier()
             t = time.perf_counter()
             for _ in range(n_e):
-                h_out = api.count_overlaps(ctx, hs[0].view(np.uint32), hs[1].view(np.uint32), iv_off, hs[2],
-                                           hs[3].view(np.uint32), hs[4].view(np.uint32))
+                count_e2e()
             dt = max_over_ranks(time.perf_counter() - t) / n_e
+            h_out = as_np(p_out, n_q, np.uint32)
             out["e2e"] = {"value": tot_q / dt, "unit": "counts/s", "ms_per_step": dt * 1e3,
                           "h2d_bytes_per_step": int(n_q * 12 + n_iv * 8), "d2h_bytes_per_step": int(n_q * 4),
-                          "api": "gams_cuda_count_overlaps (host pointers, pageable numpy)",
+                          "api": "gams_cuda_count_overlaps (host pointers, pinned; index upload and rank-table build inside)",
                           "matches_device_path": bool(np.array_equal(h_out, d_out.cpu().numpy().view(np.uint32)))}
+            hs = [h.copy() if (rank == 0 and world == 1 and not args.skip_cpu) else None for h in hs]
+            for pp in ptrs + [p_out]:
+                L.gams_cuda_host_free(pp)
             if rank == 0 and world == 1 and not args.skip_cpu:
                 from oracle import oracle as orc
                 cores = os.cpu_count() or 1

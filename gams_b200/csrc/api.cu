@@ -594,14 +594,43 @@ GAMS_API int32_t gams_cuda_count_overlaps(gams_cuda_ctx *ctx, int64_t n_seg, con
             CUDA_TRY(cudaMemcpyAsync(d_st, starts + iv_off[0], n_iv * 4, cudaMemcpyHostToDevice, st));
             CUDA_TRY(cudaMemcpyAsync(d_sp, stops + iv_off[0], n_iv * 4, cudaMemcpyHostToDevice, st));
         }
-        CUDA_TRY(cudaMemcpyAsync(pd.scratch[2].p, q_seg + q0, (uint64_t)nq * 4, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(pd.scratch[3].p, q_start + q0, (uint64_t)nq * 4, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(pd.scratch[4].p, q_stop + q0, (uint64_t)nq * 4, cudaMemcpyHostToDevice, st));
-        if ((rc = launch_count_overlaps(plan, st, d_st, d_sp, nq, pd.scratch[2].as<int32_t>(),
-                                        pd.scratch[3].as<uint32_t>(), pd.scratch[4].as<uint32_t>(), 0,
-                                        pd.scratch[5].as<uint32_t>())))
-            return rc;
-        CUDA_TRY(cudaMemcpyAsync(out + q0, pd.scratch[5].p, (uint64_t)nq * 4, cudaMemcpyDeviceToHost, st));
+        if ((rc = build_count_index(plan, st, d_st, d_sp))) return rc;
+        cudaEvent_t ev_idx;
+        CUDA_TRY(cudaEventCreateWithFlags(&ev_idx, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventRecord(ev_idx, st));
+        CUDA_TRY(cudaStreamWaitEvent(pd.copy_in, ev_idx, 0));  // keeps the slices behind the index on the link
+        // Query slices: H2D of slice k+1, kernel of slice k and D2H of slice k-1 overlap (three streams).
+        const int64_t slice = 8 << 20;
+        const size_t n_sl = (size_t)((nq + slice - 1) / slice);
+        std::vector<cudaEvent_t> ev_in(n_sl), ev_k(n_sl);
+        for (size_t k = 0; k < n_sl; ++k) {
+            CUDA_TRY(cudaEventCreateWithFlags(&ev_in[k], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&ev_k[k], cudaEventDisableTiming));
+        }
+        struct EvGuard {
+            std::vector<cudaEvent_t> &a, &b;
+            cudaEvent_t c;
+            ~EvGuard() {
+                for (auto e : a) cudaEventDestroy(e);
+                for (auto e : b) cudaEventDestroy(e);
+                cudaEventDestroy(c);
+            }
+        } ev_guard{ev_in, ev_k, ev_idx};
+        int32_t *d_qseg = pd.scratch[2].as<int32_t>();
+        uint32_t *d_qs = pd.scratch[3].as<uint32_t>(), *d_qe = pd.scratch[4].as<uint32_t>(), *d_o = pd.scratch[5].as<uint32_t>();
+        for (size_t k = 0; k < n_sl; ++k) {
+            const int64_t a = (int64_t)k * slice, m = std::min<int64_t>(slice, nq - a);
+            CUDA_TRY(cudaMemcpyAsync(d_qseg + a, q_seg + q0 + a, (uint64_t)m * 4, cudaMemcpyHostToDevice, pd.copy_in));
+            CUDA_TRY(cudaMemcpyAsync(d_qs + a, q_start + q0 + a, (uint64_t)m * 4, cudaMemcpyHostToDevice, pd.copy_in));
+            CUDA_TRY(cudaMemcpyAsync(d_qe + a, q_stop + q0 + a, (uint64_t)m * 4, cudaMemcpyHostToDevice, pd.copy_in));
+            CUDA_TRY(cudaEventRecord(ev_in[k], pd.copy_in));
+            CUDA_TRY(cudaStreamWaitEvent(st, ev_in[k], 0));
+            if ((rc = launch_count_overlaps(plan, st, d_st, d_sp, m, d_qseg + a, d_qs + a, d_qe + a, 0, d_o + a))) return rc;
+            CUDA_TRY(cudaEventRecord(ev_k[k], st));
+            CUDA_TRY(cudaStreamWaitEvent(pd.copy_out, ev_k[k], 0));
+            CUDA_TRY(cudaMemcpyAsync(out + q0 + a, d_o + a, (uint64_t)m * 4, cudaMemcpyDeviceToHost, pd.copy_out));
+        }
+        CUDA_TRY(cudaStreamSynchronize(pd.copy_out));
         CUDA_TRY(cudaStreamSynchronize(st));
         return GAMS_CUDA_OK;
     });

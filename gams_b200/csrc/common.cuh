@@ -160,6 +160,7 @@ int32_t launch_count_overlaps(gams_cuda_count_plan *p, cudaStream_t st, const ui
                               const uint32_t *d_stops, int64_t n_q, const int32_t *d_q_seg,
                               const uint32_t *d_q_start, const uint32_t *d_q_stop, int32_t grouped,
                               uint32_t *d_out);
+int32_t build_count_index(gams_cuda_count_plan *p, cudaStream_t st, const uint32_t *d_starts, const uint32_t *d_stops);
 int32_t launch_locate_ctg(cudaStream_t st, int64_t n_chr, const uint32_t *d_ctg_start, const uint32_t *d_ctg_stop,
                           const uint64_t *d_chr_off, const uint32_t *d_chr_maxlen, int64_t n_q,
                           const int32_t *d_q_chr, const uint32_t *d_q_start, const uint32_t *d_q_stop, int32_t *d_out);
