@@ -148,6 +148,15 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(rows), "samples_in_timed_region": len(inside), "how": self.how}
 
 
+def ncu_traffic(kernel: str):
+    """DRAM bytes per launch from the committed ncu --set full capture (profiles/traffic.json), or None."""
+    try:
+        d = json.loads((ROOT / "profiles" / "traffic.json").read_text())
+        return float(d[kernel]["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def layout(n_bases: int):
     from gams_b200 import synth
     seq_off, ctgs = synth.ctg_layout(synth.human_like_lengths(n_bases), PIECE)
@@ -332,7 +341,8 @@ def main():
     z_bytes = n_win * 5                           # 4 B gc read + 1 B signal written
     z_flops = n_win * (4 * LAG + 6)               # non-fusable f32 ops the reference's order forces
     roof_gc = {"bound": "hbm", "kernel": "gc_window_kernel", "achieved": gc_bytes / (ms_gc * 1e-3) / 1e9, "peak": hbm_peak,
-               "unit": "GB/s", "frac": gc_bytes / (ms_gc * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+               "unit": "GB/s", "frac": gc_bytes / (ms_gc * 1e-3) / 1e9 / hbm_peak,
+               "traffic": ncu_traffic("gc_window_kernel") if int(args.bases) == 3_100_000_000 else None,
                "algorithmic_bytes_per_launch": gc_bytes, "ms_per_launch": ms_gc, "peak_source": peak_src}
     kern = {
         "gc_window_kernel": roof_gc,
@@ -340,7 +350,8 @@ def main():
                           "ms_per_launch": ms_z, "windows_replayed_exactly_per_launch": z_uncertain,
                           "replay_fraction": z_uncertain / max(1, n_win), "achieved_gbs": z_bytes / (ms_z * 1e-3) / 1e9,
                           "hbm_frac": z_bytes / (ms_z * 1e-3) / 1e9 / hbm_peak,
-                          "achieved_gflops_nonfma": z_flops / (ms_z * 1e-3) / 1e9,
+                          "traffic": ncu_traffic("zscore_kernel") if int(args.bases) == 3_100_000_000 else None,
+                          "reference_equivalent_gflops": z_flops / (ms_z * 1e-3) / 1e9,
                           "algorithmic_bytes_per_launch": z_bytes},
     }
 
@@ -471,7 +482,8 @@ def bench_count(args, ctx, L, dev, rank, world, g_off, barrier, max_over_ranks, 
         res = {"value": tot_q / (ms * 1e-3), "unit": "counts/s", "ms_per_step": ms, "queries": n_q, "intervals": n_iv,
                "gpu_launches": int(plan.launches - l0),
                "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                            "frac": alg / (ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                            "frac": alg / (ms * 1e-3) / 1e9 / hbm_peak,
+                            "traffic": ncu_traffic("count_overlaps_ranked_kernel:grouped_by_ctg") if grouped and n_q == 100_000_000 else None,
                             "algorithmic_bytes_per_launch": alg, "peak_source": peak_src}}
         if rank == 0:
             from oracle import oracle as orc
