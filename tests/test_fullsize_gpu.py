@@ -1,0 +1,186 @@
+"""BASELINE.json configs at FULL size on the GPU, checked through size-independent properties
+(the oracle cannot finish these sizes in seconds) plus oracle spot checks on random ctgs.
+
+  C3  Arabidopsis-scale genome (120 Mbp): GC-wave 100/10 + `sw` around 10^6 features
+  C4  human-scale genome (3.1 Gbp, 24 chromosomes): GC-wave 100/10
+  C5  10^8 query ranges against 10^8 SNP intervals
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from gams_b200 import _lib, api, synth
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+PIECE = 500_000
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = api.Context([0])
+    yield c
+    c.close()
+
+
+def _wave_on_device(ctx, d_seq, seq_off, size, step, lag=100, want_signal=True, want_count=True):
+    plan = api.WavePlan(ctx, seq_off, size, step, lag)
+    assert d_seq.numel() >= plan.seq_capacity
+    n = plan.total_windows
+    d_gc = torch.empty(n, dtype=torch.float32, device=d_seq.device)
+    d_cnt = torch.empty(n, dtype=torch.int32, device=d_seq.device) if want_count else None
+    d_sig = torch.empty(n, dtype=torch.int8, device=d_seq.device) if want_signal else None
+    st = torch.cuda.current_stream().cuda_stream
+    plan.gc(st, d_seq, d_gc, d_cnt)
+    if want_signal:
+        plan.signal(st, d_gc, 3.0, 1.0, d_sig)
+    torch.cuda.synchronize()
+    plan.close()
+    return d_gc, d_cnt, d_sig
+
+
+def _wave_properties(ctx, orc, n_bases, chr_lengths, seed, n_spot):
+    dev = torch.device("cuda", 0)
+    seq_off, ctgs = synth.ctg_layout(chr_lengths, PIECE)
+    n_ctg = seq_off.size - 1
+    cap = ((n_bases + 31) // 32) * 32 + 64
+    d_seq = synth.genome_torch(n_bases, seed=seed, device=dev, capacity=cap)
+    lens = np.diff(seq_off.astype(np.int64))
+
+    gc100, cnt100, sig = _wave_on_device(ctx, d_seq, seq_off, 100, 10)
+    _, cnt10, _ = _wave_on_device(ctx, d_seq, seq_off, 10, 10, want_signal=False)
+    w100 = api.win_offsets(seq_off, 100, 10).astype(np.int64)
+    w10 = api.win_offsets(seq_off, 10, 10).astype(np.int64)
+    assert int(w100[-1]) == cnt100.numel() == int(((lens - 100) // 10 + 1).sum())
+
+    # (P1) checksum of checksums: all 10/10 blocks together hold exactly the GC bases of the covered prefix of every ctg
+    lut = torch.zeros(256, dtype=torch.uint8, device=dev)
+    lut[torch.tensor(list(b"cgCG"), device=dev, dtype=torch.long)] = 1
+    total_gc = 0
+    for s in range(0, n_bases, 1 << 28):
+        total_gc += int(lut[d_seq[s:min(n_bases, s + (1 << 28))].long()].sum(dtype=torch.int64))
+    tail = 0
+    h_off = seq_off.astype(np.int64)
+    for c in range(n_ctg):  # bytes past the last whole 10-block of each ctg (< 10 per ctg)
+        a = h_off[c] + (lens[c] // 10) * 10
+        if a < h_off[c + 1]:
+            tail += int(lut[d_seq[a:h_off[c + 1]].long()].sum())
+    assert int(cnt10.sum(dtype=torch.int64)) == total_gc - tail
+
+    # (P2) linearity: a 100/10 window is the sum of ten consecutive 10/10 blocks, for every window of every ctg
+    cs = torch.zeros(cnt10.numel() + 1, dtype=torch.int64, device=dev)
+    cs[1:] = torch.cumsum(cnt10, 0, dtype=torch.int64)
+    shift = torch.repeat_interleave(torch.as_tensor(w10[:-1] - w100[:-1], device=dev), torch.as_tensor(np.diff(w100), device=dev))
+    idx = torch.arange(cnt100.numel(), device=dev) + shift
+    assert torch.equal(cs[idx + 10] - cs[idx], cnt100.to(torch.int64))
+    del cs, idx, shift
+
+    # (P3) the f32 fraction is exactly count / size
+    # (tensor / tensor: torch turns tensor / python-scalar into a multiply by the reciprocal, which is not IEEE division)
+    assert torch.equal(gc100, cnt100.to(torch.float32) / torch.full_like(gc100, 100.0))
+    assert int(cnt100.max()) <= 100 and int(cnt100.min()) >= 0
+
+    # (P4) signals: zero in the first `lag` windows of every ctg, values in {-1,0,1}, oracle-exact on random ctgs
+    first = torch.as_tensor(w100[:-1], device=dev)
+    for k in (0, 50, 99):
+        assert int(sig[first + k].abs().max()) == 0
+    assert set(torch.unique(sig).tolist()) <= {-1, 0, 1}
+    rng = np.random.default_rng(seed)
+    for c in rng.choice(n_ctg, n_spot, replace=False):
+        s = d_seq[int(seq_off[c]):int(seq_off[c + 1])].cpu().numpy()
+        _, rc, rg, rs = orc.wave_batch(s, np.array([0, s.size], dtype=np.uint64), 100, 10, 100, 3.0, 1.0)
+        a, b = int(w100[c]), int(w100[c + 1])
+        assert np.array_equal(cnt100[a:b].cpu().numpy().view(np.uint32), rc), f"ctg {c} counts"
+        assert np.array_equal(gc100[a:b].cpu().numpy().view(np.uint32), rg.view(np.uint32)), f"ctg {c} gc"
+        assert np.array_equal(sig[a:b].cpu().numpy(), rs), f"ctg {c} signals"
+    frac = float((sig != 0).float().mean())
+    assert 1e-4 < frac < 0.2, frac
+    return d_seq, seq_off, ctgs
+
+
+def test_c4_human_scale_wave(ctx, orc):
+    n = 3_100_000_000
+    _wave_properties(ctx, orc, n, synth.human_like_lengths(n), seed=20240613, n_spot=12)
+    torch.cuda.empty_cache()
+
+
+def test_c3_arabidopsis_scale_wave_and_sw(ctx, orc):
+    chr_lengths = [30_427_671, 19_698_289, 23_459_830, 18_585_056, 26_975_502, 154_478, 366_924]  # Atha: 119 667 750 bp
+    n = int(sum(chr_lengths))
+    d_seq, seq_off, ctgs = _wave_properties(ctx, orc, n, chr_lengths, seed=7, n_spot=6)
+    h_seq = d_seq[:n].cpu().numpy()
+    # 10^6 point features uniform over the genome; chr coordinates per ctg as `gen` assigns them
+    rng = np.random.default_rng(8)
+    lens = np.diff(seq_off.astype(np.int64))
+    chr_start = np.array([c[1] for c in ctgs], dtype=np.int32)
+    n_feat = 1_000_000
+    f_ctg = np.sort(rng.choice(len(ctgs), n_feat, p=lens / lens.sum())).astype(np.uint32)
+    f_s = (chr_start[f_ctg] + (rng.random(n_feat) * lens[f_ctg]).astype(np.int64)).astype(np.int32)
+    f_e = np.minimum(f_s + rng.integers(0, 3, n_feat), chr_start[f_ctg] + lens[f_ctg] - 1).astype(np.int32)
+    r = api.sw_batch(ctx, h_seq, seq_off, chr_start, f_ctg, f_s, f_e)
+    rows = np.diff(r["row_off"].astype(np.int64))
+    assert rows.min() >= 1 and rows.max() <= 41 and int(rows.sum()) == r["gc"].size > 35_000_000
+    assert np.all((r["end"] - r["start"] + 1 <= 100) & (r["end"] >= r["start"]))
+    first = r["row_off"][:-1].astype(np.int64)
+    assert np.all(r["type"][first] == 0) and np.all(r["dist"][first] == 0)
+    assert np.all((r["gc"] >= 0) & (r["gc"] <= 1))
+    ok = ~np.isnan(r["mean"])
+    assert np.all((r["mean"][ok] >= 0) & (r["mean"][ok] <= 1))
+    for f in rng.choice(n_feat, 1500, replace=False):  # oracle-exact rows on a sample of features
+        c = int(f_ctg[f])
+        seq = h_seq[int(seq_off[c]):int(seq_off[c + 1])]
+        ref = orc.sw_feature(seq, int(chr_start[c]), int(chr_start[c] + lens[c] - 1), int(f_s[f]), int(f_e[f]))
+        a, b = int(r["row_off"][f]), int(r["row_off"][f + 1])
+        assert b - a == len(ref["gc"])
+        for key in ("gc", "mean", "sd", "cv"):
+            assert np.array_equal(r[key][a:b].view(np.uint32), ref[key].view(np.uint32)), (f, key)
+        assert np.array_equal(r["start"][a:b], ref["start"]) and np.array_equal(r["type"][a:b].astype(np.int32), ref["type"])
+
+
+def test_c5_overlap_counts_1e8_by_1e8(ctx, orc):
+    dev = torch.device("cuda", 0)
+    n = 3_100_000_000
+    seq_off, _ = synth.ctg_layout(synth.human_like_lengths(n), PIECE)
+    lens = np.diff(seq_off.astype(np.int64))
+    n_ctg = lens.size
+    per = 100_000_000 // n_ctg
+    d_st, d_sp, iv_off = synth.rg_index_torch(lens, per, seed=3, device=dev)
+    plan = api.CountPlan(ctx, iv_off)
+    st = torch.cuda.current_stream().cuda_stream
+    n_q = 100_000_000
+    L = torch.as_tensor(lens, device=dev)
+
+    def count(seg, a, b):
+        out = torch.empty(seg.numel(), dtype=torch.int32, device=dev)
+        plan.count(st, d_st, d_sp, seg, a.to(torch.int32), b.to(torch.int32), out)
+        torch.cuda.synchronize()
+        return out.to(torch.int64)
+
+    g = torch.Generator(device=dev)
+    g.manual_seed(5)
+    seg = torch.randint(0, n_ctg, (n_q,), generator=g, device=dev, dtype=torch.int32)
+    Lq = L[seg.long()]
+    p = torch.sort((torch.rand(3, n_q, generator=g, device=dev, dtype=torch.float64) * Lq.to(torch.float64)[None, :]).to(torch.int64) + 1, dim=0).values
+    a, b, c = p[0], p[1], p[2]
+    # additivity for point intervals under gams' half-open call: count(a,c) = count(a,b) + count(b,c)
+    ac, ab, bc = count(seg, a, c), count(seg, a, b), count(seg, b, c)
+    assert torch.equal(ac, ab + bc)
+    assert int(ac.sum()) > 10 * n_q  # not vacuous: thousands of SNPs per query on average
+    # the whole ctg sees every interval of the ctg
+    segs = torch.arange(n_ctg, device=dev, dtype=torch.int32)
+    assert torch.equal(count(segs, torch.ones(n_ctg, device=dev, dtype=torch.int64), L + 1),
+                       torch.full((n_ctg,), per, device=dev, dtype=torch.int64))
+    # oracle-exact on a sample, arbitrary order incl. unknown segments
+    k = 300_000
+    sel = torch.randint(0, n_q, (k,), generator=g, device=dev)
+    s2 = seg[sel].clone()
+    s2[::97] = -1
+    s2[5::97] = n_ctg
+    got = count(s2, a[sel], c[sel]).cpu().numpy().astype(np.uint32)
+    ref = orc.count_batch(d_st.cpu().numpy().view(np.uint32), d_sp.cpu().numpy().view(np.uint32), iv_off, s2.cpu().numpy(),
+                          a[sel].cpu().numpy().astype(np.uint32), c[sel].cpu().numpy().astype(np.uint32), threads=8)
+    assert np.array_equal(got, ref)
+    plan.close()
+    torch.cuda.empty_cache()
