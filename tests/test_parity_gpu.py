@@ -410,3 +410,25 @@ def test_multi_device_context_shards_by_ctg(orc):
         st, sp, off = synth.rg_index(lens, [5000] * len(lens), seed=73)
         seg, qs, qe = synth.queries(lens, 400_000, seed=74, grouped=False)
         _eq("multi-device counts", api.count_overlaps(mctx, st, sp, off, seg, qs, qe), orc.count_batch(st, sp, off, seg, qs, qe, threads=8))
+
+
+def test_count_overlaps_grouped_device_path(ctx, orc):
+    """The grouped (q_seg non-decreasing) variant of Kernel C: one contiguous share of queries per SM."""
+    import torch
+    lens = [500_000 + 37 * k for k in range(300)]
+    st, sp, off = synth.rg_index(lens, [8000 + (k % 7) * 1000 for k in range(300)], seed=81)
+    seg, qs, qe = synth.queries(lens, 2_500_000, seed=82, grouped=True)
+    dev = torch.device("cuda", 0)
+    t = lambda a, dt: torch.as_tensor(a.view(dt) if a.dtype != dt else a, device=dev)
+    d_st, d_sp = t(st, np.int32), t(sp, np.int32)
+    d_seg, d_qs, d_qe = t(seg, np.int32), t(qs, np.int32), t(qe, np.int32)
+    plan = api.CountPlan(ctx, off)
+    out = torch.empty(seg.size, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    ref = orc.count_batch(st, sp, off, seg, qs, qe, threads=8)
+    for grouped in (True, False):
+        out.zero_()
+        plan.count(stream, d_st, d_sp, d_seg, d_qs, d_qe, out, grouped=grouped)
+        torch.cuda.synchronize()
+        _eq(f"grouped={grouped}", out.cpu().numpy().view(np.uint32), ref)
+    plan.close()
