@@ -234,6 +234,15 @@ class WavePlan:
                                                 d_filtered.data_ptr() if d_filtered is not None else None,
                                                 d_signal.data_ptr()))
 
+    def wave(self, stream: int, d_seq, threshold, influence, d_gc, d_signal, d_cnt=None, d_filtered=None):
+        """GC + signals in one call: the fused kernel when `fused(threshold, influence)`, else gc() + signal()."""
+        check(self._L.gams_cuda_wave_dev(self._h, stream, d_seq.data_ptr(), threshold, influence,
+                                         d_cnt.data_ptr() if d_cnt is not None else None, d_gc.data_ptr(),
+                                         d_filtered.data_ptr() if d_filtered is not None else None, d_signal.data_ptr()))
+
+    def fused(self, threshold, influence) -> bool:
+        return bool(self._L.gams_cuda_wave_plan_fused(self._h, threshold, influence))
+
     @property
     def launches(self) -> int:
         return int(self._L.gams_cuda_wave_plan_launches(self._h))

@@ -315,7 +315,24 @@ GAMS_API int32_t gams_cuda_wave_plan_create(gams_cuda_ctx *ctx, int32_t dev_inde
         p->geom.n_tiles = gt.size();
         ARG_CHECK(gt.size() < (1ull << 31), "wave_plan_create: too many tiles");
     }
+    // Kernel AB tiles (bytes -> GC + signals in one pass); only when the geometry is eligible
+    std::vector<TileDesc> ft;
+    p->h_ftile_off.assign((size_t)n_ctg + 1, 0);
+    p->fused_wt = (p->geom.k && lag >= 1 && !getenv("GAMS_CUDA_NO_FUSED")) ? fused_windows_per_tile(size, step, lag, p->geom.k) : 0;
+    if (p->fused_wt) {
+        for (int64_t c = 0; c < n_ctg; ++c) {
+            const uint64_t n_c = p->h_win_off[c + 1] - p->h_win_off[c];
+            for (uint64_t w = 0; w < n_c; w += (uint64_t)p->fused_wt) ft.push_back({(uint32_t)c, (uint32_t)w});
+            p->h_ftile_off[c + 1] = ft.size();
+        }
+        ARG_CHECK(ft.size() < (1ull << 31), "wave_plan_create: too many tiles");
+    }
     DeviceGuard g(pd.device);
+    if (!ft.empty()) {
+        CUDA_TRY(cudaMalloc(&p->d_ftiles, sizeof(TileDesc) * ft.size()));
+        CUDA_TRY(cudaMemcpyAsync(p->d_ftiles, ft.data(), sizeof(TileDesc) * ft.size(), cudaMemcpyHostToDevice, pd.stream));
+        CUDA_TRY(cudaStreamSynchronize(pd.stream));
+    }
     CUDA_TRY(cudaMalloc(&p->d_seq_off, sizeof(uint64_t) * (size_t)(n_ctg + 1)));
     CUDA_TRY(cudaMemcpyAsync(p->d_seq_off, p->h_seq_off.data(), sizeof(uint64_t) * (size_t)(n_ctg + 1),
                              cudaMemcpyHostToDevice, pd.stream));
@@ -340,6 +357,7 @@ GAMS_API void gams_cuda_wave_plan_destroy(gams_cuda_wave_plan *p) {
     DeviceGuard g(p->device);
     if (p->d_seq_off) cudaFree(p->d_seq_off);
     if (p->d_gtiles) cudaFree(p->d_gtiles);
+    if (p->d_ftiles) cudaFree(p->d_ftiles);
     if (p->d_gc_tab) cudaFree(p->d_gc_tab);
     p->win.release();
     delete p;
@@ -365,6 +383,24 @@ GAMS_API int32_t gams_cuda_wave_signal_dev(gams_cuda_wave_plan *p, void *stream,
     DeviceGuard g(p->device);
     return launch_zscore(p->win, (cudaStream_t)stream, d_gc, p->lag, threshold, influence, d_filtered, d_signal,
                          &p->launches, p->ctx->zscore_mode, p->ctx->devs[p->dev_index].d_zstats, 0, p->n_ctg);
+}
+
+GAMS_API int32_t gams_cuda_wave_dev(gams_cuda_wave_plan *p, void *stream, const uint8_t *d_seq, float threshold,
+                                    float influence, uint32_t *d_gc_count, float *d_gc, float *d_filtered,
+                                    int8_t *d_signal) {
+    ARG_CHECK(p && d_gc && d_signal && (d_seq || p->total_bases == 0), "wave_dev: NULL argument");
+    DeviceGuard g(p->device);
+    if (wave_fused_ok(p, threshold, influence))
+        return launch_gc_wave_fused(p, (cudaStream_t)stream, d_seq, threshold, d_gc_count, d_gc, d_signal,
+                                    p->ctx->devs[p->dev_index].d_zstats, 0, p->n_ctg);
+    int32_t rc = launch_gc_windows(p, (cudaStream_t)stream, d_seq, d_gc_count, d_gc, &p->launches, 0, p->n_ctg);
+    if (rc) return rc;
+    return launch_zscore(p->win, (cudaStream_t)stream, d_gc, p->lag, threshold, influence, d_filtered, d_signal,
+                         &p->launches, p->ctx->zscore_mode, p->ctx->devs[p->dev_index].d_zstats, 0, p->n_ctg);
+}
+
+GAMS_API int32_t gams_cuda_wave_plan_fused(const gams_cuda_wave_plan *p, float threshold, float influence) {
+    return (p && wave_fused_ok(p, threshold, influence)) ? 1 : 0;
 }
 
 // ================================================================================ wave: host ====
@@ -433,10 +469,14 @@ static int32_t wave_on_device(gams_cuda_ctx *ctx, int d, int64_t c0, int64_t c1,
         if (b1 > b0) CUDA_TRY(cudaMemcpyAsync(d_seq + b0, h_seq + b0, b1 - b0, cudaMemcpyHostToDevice, pd.copy_in));
         CUDA_TRY(cudaEventRecord(ev_in[k], pd.copy_in));
         CUDA_TRY(cudaStreamWaitEvent(pd.stream, ev_in[k], 0));
-        if ((rc = launch_gc_windows(plan, pd.stream, d_seq, d_cnt, d_gc, &plan->launches, a, b))) return rc;
-        if (signal && (rc = launch_zscore(plan->win, pd.stream, d_gc, lag, threshold, influence, d_filt, d_sig,
-                                          &plan->launches, ctx->zscore_mode, pd.d_zstats, a, b)))
-            return rc;
+        if (signal && wave_fused_ok(plan, threshold, influence)) {
+            if ((rc = launch_gc_wave_fused(plan, pd.stream, d_seq, threshold, d_cnt, d_gc, d_sig, pd.d_zstats, a, b))) return rc;
+        } else {
+            if ((rc = launch_gc_windows(plan, pd.stream, d_seq, d_cnt, d_gc, &plan->launches, a, b))) return rc;
+            if (signal && (rc = launch_zscore(plan->win, pd.stream, d_gc, lag, threshold, influence, d_filt, d_sig,
+                                              &plan->launches, ctx->zscore_mode, pd.d_zstats, a, b)))
+                return rc;
+        }
         CUDA_TRY(cudaEventRecord(ev_k[k], pd.stream));
         CUDA_TRY(cudaStreamWaitEvent(pd.copy_out, ev_k[k], 0));
         if (w1 > w0) {

@@ -78,6 +78,14 @@ struct GcGeom {
     uint64_t n_tiles = 0;
 };
 
+// Kernel AB (gc_wave_fused.cu): counts / prefixes / decisions kept per tile, and the host-computed bounds of its
+// certificate (see make_fused_const)
+constexpr int FUSED_MAX_EL = 2048;    // tile windows + lag+1 halo windows
+constexpr int FUSED_LIST_CAP = 64;    // inconclusive windows listed per tile before the tile is replayed wholesale
+struct FusedConst {
+    double n, e2, k_hi, k_lo, one_plus_eps, one_minus_eps, b_hi, b_lo;
+};
+
 // Geometry of Kernel B1 (zscore.cu)
 constexpr int ZS_R = 8;                       // windows per thread
 constexpr int ZS_THREADS = 128;
@@ -129,6 +137,9 @@ struct gams_cuda_wave_plan {
     gams::TileDesc *d_gtiles = nullptr;
     std::vector<uint64_t> h_gtile_off;  // n_ctg+1: first Kernel-A tile of each ctg
     float *d_gc_tab = nullptr;       // (float)c / (float)size for c = 0..size (host-computed IEEE divide)
+    int fused_wt = 0;                // windows per Kernel-AB tile; 0 = geometry not eligible for the fused kernel
+    gams::TileDesc *d_ftiles = nullptr;
+    std::vector<uint64_t> h_ftile_off;  // n_ctg+1: first Kernel-AB tile of each ctg
     uint64_t launches = 0;
 };
 
@@ -172,4 +183,10 @@ int32_t launch_sw_rows(cudaStream_t st, const uint8_t *d_seq, const uint64_t *d_
                        int32_t *d_w_start, int32_t *d_w_end, int8_t *d_w_type, int32_t *d_w_dist, float *d_gc,
                        float *d_mean, float *d_sd, float *d_cv);
 GcGeom plan_gc_geometry(int32_t size, int32_t step);
+// Kernel AB: bytes -> GC + signals in one pass (influence == 1, threshold >= 0, eligible geometry only)
+int fused_windows_per_tile(int32_t size, int32_t step, uint64_t lag, int k);
+int32_t launch_gc_wave_fused(gams_cuda_wave_plan *p, cudaStream_t st, const uint8_t *d_seq, float threshold,
+                             uint32_t *d_cnt, float *d_gc, int8_t *d_sig, unsigned long long *d_stats, int64_t c0,
+                             int64_t c1);
+bool wave_fused_ok(const gams_cuda_wave_plan *p, float threshold, float influence);
 }  // namespace gams

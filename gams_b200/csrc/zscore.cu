@@ -16,26 +16,9 @@
 //    ctg in lag order; its 32 lanes evaluate the next 32 windows speculatively ("no signal in
 //    between") and the warp commits up to and including the window after the first signal, which
 //    is exactly what the sequential loop would have produced.
-#include "common.cuh"
+#include "zscore_common.cuh"
 
 namespace gams {
-
-// ---- the reference's arithmetic, one window, elements fetched through `ld(j)` -------------------
-template <class Ld>
-__device__ __forceinline__ int zscore_decide(Ld ld, int64_t a, uint64_t lag, float flag, float flagm1, float x,
-                                             float threshold) {
-    float s = 0.0f;
-    for (uint64_t t = 0; t < lag; ++t) s = __fadd_rn(s, ld(a + (int64_t)t));
-    const float m = __fdiv_rn(s, flag);
-    float q = 0.0f;
-    for (uint64_t t = 0; t < lag; ++t) {
-        const float d = __fsub_rn(ld(a + (int64_t)t), m);
-        q = __fadd_rn(q, __fmul_rn(d, d));
-    }
-    const float sd = __fsqrt_rn(__fdiv_rn(q, flagm1));
-    if (fabsf(__fsub_rn(x, m)) > __fmul_rn(threshold, sd)) return (x > m) ? 1 : -1;
-    return 0;
-}
 
 __host__ __device__ __forceinline__ int zs_swz(int p) { return p + (p >> 5); }  // breaks the stride-ZS_R bank pattern
 

@@ -125,6 +125,16 @@ int32_t gams_cuda_wave_gc_dev(gams_cuda_wave_plan *plan, void *stream, const uin
  * when influence != 1 (may be NULL otherwise). */
 int32_t gams_cuda_wave_signal_dev(gams_cuda_wave_plan *plan, void *stream, const float *d_gc,
                                   float threshold, float influence, float *d_filtered, int8_t *d_signal);
+/* Kernels A+B in one call, src/cmd_gams/wave.rs:138-155: d_seq -> d_gc_count (optional) / d_gc / d_signal.
+ * With the default statistics (influence == 1, threshold >= 0) and size % step == 0 this is ONE fused kernel
+ * (gc_wave_fused.cu) that decides the signals from exact integer window counts while the tile is still in
+ * shared memory; otherwise it enqueues gams_cuda_wave_gc_dev + gams_cuda_wave_signal_dev.  Results are
+ * identical either way.  d_filtered as for gams_cuda_wave_signal_dev.  GAMS_CUDA_ELAG as for wave_batch. */
+int32_t gams_cuda_wave_dev(gams_cuda_wave_plan *plan, void *stream, const uint8_t *d_seq, float threshold,
+                           float influence, uint32_t *d_gc_count, float *d_gc, float *d_filtered,
+                           int8_t *d_signal);
+/* 1 if gams_cuda_wave_dev would take the fused kernel for these statistics, else 0. */
+int32_t gams_cuda_wave_plan_fused(const gams_cuda_wave_plan *plan, float threshold, float influence);
 /* Kernel launches issued by the plan's _dev calls since creation (bench.py's gpu_launches). */
 uint64_t gams_cuda_wave_plan_launches(const gams_cuda_wave_plan *plan);
 

@@ -33,9 +33,27 @@ def _wave_on_device(ctx, d_seq, seq_off, size, step, lag=100, want_signal=True, 
     d_cnt = torch.empty(n, dtype=torch.int32, device=d_seq.device) if want_count else None
     d_sig = torch.empty(n, dtype=torch.int8, device=d_seq.device) if want_signal else None
     st = torch.cuda.current_stream().cuda_stream
-    plan.gc(st, d_seq, d_gc, d_cnt)
     if want_signal:
-        plan.signal(st, d_gc, 3.0, 1.0, d_sig)
+        # the fused kernel (what `wave` runs by default) ...
+        assert plan.fused(3.0, 1.0)
+        plan.wave(st, d_seq, 3.0, 1.0, d_gc, d_sig, d_cnt)
+        torch.cuda.synchronize()
+        # ... against Kernel A + the exact replay of EVERY window (mode 1), over the whole genome
+        d_gc2 = torch.empty_like(d_gc)
+        d_sig2 = torch.empty_like(d_sig)
+        try:
+            ctx.set_zscore_mode(1)
+            plan.gc(st, d_seq, d_gc2, None)
+            plan.signal(st, d_gc2, 3.0, 1.0, d_sig2)
+            torch.cuda.synchronize()
+        finally:
+            ctx.set_zscore_mode(0)
+        assert torch.equal(d_gc.view(torch.int32), d_gc2.view(torch.int32)), "fused GC differs from Kernel A"
+        nbad = int((d_sig != d_sig2).sum())
+        assert nbad == 0, f"{nbad} of {n} fused signals differ from the exact replay"
+        del d_gc2, d_sig2
+    else:
+        plan.gc(st, d_seq, d_gc, d_cnt)
     torch.cuda.synchronize()
     plan.close()
     return d_gc, d_cnt, d_sig

@@ -351,6 +351,78 @@ def test_zscore_filter_replay_fraction_on_genome(ctx, orc):
     assert unc < 0.005 * gc.size, f"{unc} of {gc.size} windows needed the exact replay"
 
 
+# ------------------------------------------------------------------- fused GC-wave kernel (Kernel AB)
+def _wave_all_modes(ctx, orc, seqs, size, step, lag, thr, expect_fused=None):
+    """Fused kernel (mode 0) vs Kernel A + exact replay of every window (mode 1) vs the oracle."""
+    cat, off = orc.pack_ctgs(seqs)
+    plan = api.WavePlan(ctx, off, size, step, lag)
+    if expect_fused is not None:
+        assert plan.fused(thr, 1.0) == expect_fused, (size, step, lag, thr)
+    plan.close()
+    _, rcnt, rgc, rsig = orc.wave_batch(cat, off, size, step, lag, thr, 1.0, threads=8)
+    out = {}
+    try:
+        for mode in (1, 0):
+            ctx.set_zscore_mode(mode)
+            ctx.zscore_stats(reset=True)
+            _, cnt, gc, sig = api.wave_batch(ctx, cat, off, size, step, lag, thr, 1.0)
+            _eq(f"mode {mode} count", cnt, rcnt)
+            _eq(f"mode {mode} gc", gc.view(np.uint32), rgc.view(np.uint32))
+            _eq(f"mode {mode} signal [{size}/{step} lag {lag} thr {thr}]", sig, rsig)
+            out[mode] = ctx.zscore_stats(reset=True)[0]
+    finally:
+        ctx.set_zscore_mode(0)
+    return out[0], rgc, rsig
+
+
+@pytest.mark.parametrize("size,step,lag", [(100, 10, 100), (100, 10, 2), (100, 50, 30), (100, 100, 10), (1, 1, 100),
+                                           (16, 16, 8), (1000, 100, 20), (5000, 1000, 5), (30, 10, 400), (64, 8, 1000)])
+def test_fused_wave_matches_replay_and_oracle(ctx, orc, size, step, lag):
+    g = synth.genome(1_200_000, seed=size * 7 + lag)
+    flat = np.tile(np.frombuffer(b"ACATTTTTAT" * 5 + b"GCGCGCGCGATATATATATATATATATATATATATATATATATATATATA", dtype=np.uint8), 1500)
+    need = size + (lag + 2) * step
+    seqs = [g[:400_003], g[400_003:400_003 + need], g[500_000:], flat, np.full(max(need, 20_000), ord("N"), np.uint8),
+            np.concatenate([g[:need], flat[:need], g[need:3 * need]])]
+    fused = (size, step, lag) not in {(5000, 1000, 5), (30, 10, 400), (64, 8, 1000)}  # halo too large a share of a tile
+    for thr in (3.0, 0.0, 1.0, 7.5):
+        _wave_all_modes(ctx, orc, seqs, size, step, lag, thr, expect_fused=fused)
+
+
+def test_fused_wave_borderline_thresholds(ctx, orc, s288c):
+    """Thresholds one ulp around the z value of real windows: the integer certificate must send those
+    windows to the exact replay (and only a sliver of all windows)."""
+    seq = np.asarray(s288c["seq_I"])
+    gc = _gc_series(orc, seq)
+    lag = 100
+    rng = np.random.default_rng(47)
+    thrs = []
+    for i in rng.integers(lag + 1, gc.size, 40):
+        w = gc[i - 1 - lag:i - 1]
+        m, sd = orc.mean(w), orc.stddev(w)
+        if sd > 0:
+            z = np.float32(abs(np.float32(gc[i] - m)) / sd)
+            thrs += [z, np.nextafter(z, np.float32(0)), np.nextafter(z, np.float32(10))]
+    total = 0
+    for thr in thrs:
+        unc, _, _ = _wave_all_modes(ctx, orc, [seq], 100, 10, lag, float(thr), expect_fused=True)
+        total += unc
+    assert total > 0
+    assert total < 0.01 * gc.size * len(thrs)
+
+
+def test_fused_wave_replay_fraction_and_fallbacks(ctx, orc):
+    g = synth.genome(2_000_000, seed=48)
+    unc, rgc, _ = _wave_all_modes(ctx, orc, [g], 100, 10, 100, 3.0, expect_fused=True)
+    assert unc < 0.005 * rgc.size, f"{unc} of {rgc.size} windows needed the exact replay"
+    # geometries / statistics the fused kernel does not cover take Kernel A + Kernel B
+    _wave_all_modes(ctx, orc, [g[:300_000]], 97, 13, 31, 3.0, expect_fused=False)      # size % step != 0
+    _wave_all_modes(ctx, orc, [g[:300_000]], 100, 10, 100, -1.0, expect_fused=False)    # negative threshold
+    _wave_all_modes(ctx, orc, [g[:300_000]], 20000, 5000, 2, 3.0, expect_fused=False)   # a window per tile
+    plan = api.WavePlan(ctx, np.array([0, 300_000], dtype=np.uint64), 100, 10, 100)
+    assert plan.fused(3.0, 1.0) and not plan.fused(3.0, 0.5) and not plan.fused(float("nan"), 1.0)
+    plan.close()
+
+
 def test_count_overlaps_adversarial_distributions(ctx, orc):
     """Rank tables must stay exact on skewed endpoint distributions: duplicates, far-apart clusters,
     coordinates near 2^32, single-interval and empty segments."""
