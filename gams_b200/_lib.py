@@ -19,7 +19,9 @@ class GamsCudaError(RuntimeError):
 
 
 def lib_path() -> Path:
-    return _PKG / "libgams_cuda.so"
+    """The in-tree library; GAMS_CUDA_LIB selects another build of it (kernel-variant experiments)."""
+    import os
+    return Path(os.environ.get("GAMS_CUDA_LIB") or _PKG / "libgams_cuda.so")
 
 
 def header_symbols() -> list[str]:

@@ -316,21 +316,28 @@ GAMS_API int32_t gams_cuda_wave_plan_create(gams_cuda_ctx *ctx, int32_t dev_inde
         ARG_CHECK(gt.size() < (1ull << 31), "wave_plan_create: too many tiles");
     }
     // Kernel AB tiles (bytes -> GC + signals in one pass); only when the geometry is eligible
-    std::vector<TileDesc> ft;
+    std::vector<FusedTile> ft;
     p->h_ftile_off.assign((size_t)n_ctg + 1, 0);
-    p->fused_wt = (p->geom.k && lag >= 1 && !getenv("GAMS_CUDA_NO_FUSED")) ? fused_windows_per_tile(size, step, lag, p->geom.k) : 0;
+    p->fused_wt = getenv("GAMS_CUDA_NO_FUSED") ? 0 : fused_windows_per_tile(size, step, lag);
     if (p->fused_wt) {
         for (int64_t c = 0; c < n_ctg; ++c) {
             const uint64_t n_c = p->h_win_off[c + 1] - p->h_win_off[c];
-            for (uint64_t w = 0; w < n_c; w += (uint64_t)p->fused_wt) ft.push_back({(uint32_t)c, (uint32_t)w});
+            for (uint64_t w = 0; w < n_c; w += (uint64_t)p->fused_wt) {
+                FusedTile t{};
+                t.hh = w ? (uint32_t)lag + 1u : 0u;   // w is 0 or a multiple of fused_wt >= 4 (lag + 1)
+                t.byte0 = p->h_seq_off[c] + (w - t.hh) * (uint64_t)step;
+                t.out0 = p->h_win_off[c] + w;
+                t.nw = (uint32_t)std::min<uint64_t>((uint64_t)p->fused_wt, n_c - w);
+                ft.push_back(t);
+            }
             p->h_ftile_off[c + 1] = ft.size();
         }
         ARG_CHECK(ft.size() < (1ull << 31), "wave_plan_create: too many tiles");
     }
     DeviceGuard g(pd.device);
     if (!ft.empty()) {
-        CUDA_TRY(cudaMalloc(&p->d_ftiles, sizeof(TileDesc) * ft.size()));
-        CUDA_TRY(cudaMemcpyAsync(p->d_ftiles, ft.data(), sizeof(TileDesc) * ft.size(), cudaMemcpyHostToDevice, pd.stream));
+        CUDA_TRY(cudaMalloc(&p->d_ftiles, sizeof(FusedTile) * ft.size()));
+        CUDA_TRY(cudaMemcpyAsync(p->d_ftiles, ft.data(), sizeof(FusedTile) * ft.size(), cudaMemcpyHostToDevice, pd.stream));
         CUDA_TRY(cudaStreamSynchronize(pd.stream));
     }
     CUDA_TRY(cudaMalloc(&p->d_seq_off, sizeof(uint64_t) * (size_t)(n_ctg + 1)));

@@ -78,12 +78,24 @@ struct GcGeom {
     uint64_t n_tiles = 0;
 };
 
-// Kernel AB (gc_wave_fused.cu): counts / prefixes / decisions kept per tile, and the host-computed bounds of its
-// certificate (see make_fused_const)
-constexpr int FUSED_MAX_EL = 2048;    // tile windows + lag+1 halo windows
-constexpr int FUSED_LIST_CAP = 64;    // inconclusive windows listed per tile before the tile is replayed wholesale
+// Kernel AB (gc_wave_fused.cu): tile geometry and the host-computed bounds of its certificate (make_fused_const)
+constexpr int FW_E = 8;                        // consecutive windows per thread in the statistics phases
+constexpr int FW_MAX_EL = 256 * FW_E;          // windows per tile, lag+1 halo windows included
+constexpr int FW_K = 6;                        // 16-byte chunks per thread: 24 576 bytes of sequence per tile
+constexpr int FW_PAD = 416;                    // front padding of the prefix arrays (>= FW_MAX_LAG, multiple of 8)
+constexpr int FW_MAX_LAG = 400;
+constexpr int FW_MAX_R = 248;                  // size / step
+constexpr int FW_STAB = 256;                   // GC table kept in shared memory when size < FW_STAB
+constexpr int FUSED_LIST_CAP = 64;             // inconclusive windows listed per tile before the tile is replayed wholesale
 struct FusedConst {
-    double n, e2, k_hi, k_lo, one_plus_eps, one_minus_eps, b_hi, b_lo;
+    float k, e2x2, epsk, beta;
+};
+struct alignas(32) FusedTile {
+    uint64_t byte0;   // first sequence byte the tile reads (its first halo window)
+    uint64_t out0;    // global index of the tile's first output window
+    uint32_t nw;      // output windows
+    uint32_t hh;      // halo windows before them: 0 (first tile of a ctg) or lag + 1
+    uint32_t pad[2];
 };
 
 // Geometry of Kernel B1 (zscore.cu)
@@ -138,7 +150,7 @@ struct gams_cuda_wave_plan {
     std::vector<uint64_t> h_gtile_off;  // n_ctg+1: first Kernel-A tile of each ctg
     float *d_gc_tab = nullptr;       // (float)c / (float)size for c = 0..size (host-computed IEEE divide)
     int fused_wt = 0;                // windows per Kernel-AB tile; 0 = geometry not eligible for the fused kernel
-    gams::TileDesc *d_ftiles = nullptr;
+    gams::FusedTile *d_ftiles = nullptr;
     std::vector<uint64_t> h_ftile_off;  // n_ctg+1: first Kernel-AB tile of each ctg
     uint64_t launches = 0;
 };
@@ -184,7 +196,7 @@ int32_t launch_sw_rows(cudaStream_t st, const uint8_t *d_seq, const uint64_t *d_
                        float *d_mean, float *d_sd, float *d_cv);
 GcGeom plan_gc_geometry(int32_t size, int32_t step);
 // Kernel AB: bytes -> GC + signals in one pass (influence == 1, threshold >= 0, eligible geometry only)
-int fused_windows_per_tile(int32_t size, int32_t step, uint64_t lag, int k);
+int fused_windows_per_tile(int32_t size, int32_t step, uint64_t lag);
 int32_t launch_gc_wave_fused(gams_cuda_wave_plan *p, cudaStream_t st, const uint8_t *d_seq, float threshold,
                              uint32_t *d_cnt, float *d_gc, int8_t *d_sig, unsigned long long *d_stats, int64_t c0,
                              int64_t c1);

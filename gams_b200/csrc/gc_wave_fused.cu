@@ -3,217 +3,279 @@
 // Replaces wave::proc_ctg's compute, src/cmd_gams/wave.rs:138-155: gams::sliding (window.rs:78-94), the
 // per-window gc_content loop (wave.rs:143-153) and gams::thresholding_algo (stat.rs:16-56).
 //
-// Why fuse.  With the certified filter (zscore.cu) the z-score step no longer needs the f32 GC values:
-// it needs the exact mean and centred sum of squares of each stats window.  For GC data those follow from
-// INTEGER window counts c_k (x_k = fl(c_k / size)), which Kernel A already holds in shared memory.  So the
-// tile is extended backwards by lag+1 windows, the counts are scanned twice more (sum c, sum c^2: exact, u32),
-// and each window is decided from D = n c_i - sum c and V = n sum c^2 - (sum c)^2:
-//     signal certainly      if (|D| - e2)^2            >  K_hi (V (1+eps) + B_hi)        and |D| > e2
-//     certainly no signal   if (|D| + e2)^2            <  K_lo max(V (1-eps) - B_lo, 0)
-// where e2, K_*, B_*, eps are host-computed bounds on everything the reference's f32 evaluation can do to
-// these exact quantities (derivation in DESIGN.md §3 "Kernel AB"); otherwise the window is replayed exactly
-// (zscore_decide on x_k = gc_tab[c_k], the same f32 values the reference sums).  No separate pass re-reads the
-// 1.24 GB of GC values, and no f64 prefix sums are needed.
+// Why fuse.  With a certified filter the z-score step does not need the f32 GC values: it needs the exact mean
+// and centred sum of squares of each stats window.  For GC data those follow from INTEGER window counts c_k
+// (x_k = fl(c_k / size)), which the GC phase already holds in shared memory.  So the tile is extended backwards
+// by lag+1 windows, the counts are scanned twice more (sum c mod 2^16, sum c^2 mod 2^32: exact differences),
+// and each window is decided from D = n c_i - sum c and V = n sum c^2 - (sum c)^2 (both exact u32):
+//     signal certainly      if (|D| - e2)^2  >  K_hi ((1+eps) V + B_hi)        and |D| > e2
+//     certainly no signal   if (|D| + e2)^2  <  K_lo max((1-eps) V - B_lo, 0)
+// where e2, K_*, B_*, eps are host-computed bounds on everything the reference's f32 evaluation can do to these
+// exact quantities, widened for the f32 arithmetic of the test itself (derivation at make_fused_const and in
+// DESIGN.md §3 "Kernel AB"); otherwise the window is replayed exactly (zscore_decide on x_k = gc_tab[c_k], the same
+// f32 values the reference sums).  No pass re-reads the 1.24 GB of GC values and no f64 is involved.
 //
-// Bound: HBM (1 B/base read + 5 B/window written, + the lag+1-window halo re-read per tile, ~6 % at 100/10/100).
+// The kernel is instruction-issue bound, so the per-window phases are laid out for few instructions: eight
+// consecutive windows per thread, 128-bit shared-memory accesses, everything unrolled.
+//
+// Bound: HBM (1 B/base read + 5 B/window written, + the lag+1-window halo re-read per tile, 5 % at 100/10/100).
 #include "gc_common.cuh"
 #include "zscore_common.cuh"
 
 namespace gams {
 
-template <int K, bool WRITE_CNT>
-__global__ void __launch_bounds__(GC_THREADS)
-gc_wave_fused_kernel(const uint8_t *__restrict__ seq, const uint64_t *__restrict__ seq_off,
-                     const uint64_t *__restrict__ win_off, const TileDesc *__restrict__ tiles,
-                     const float *__restrict__ gc_tab, int size, int step, int wt, int lag, float threshold,
+#ifndef FW_MIN_CTAS
+#define FW_MIN_CTAS 6
+#endif
+constexpr int FW_NCH = GC_THREADS * FW_K;  // 16-byte chunks per tile
+static_assert(FW_MAX_EL == GC_THREADS * FW_E && FW_E == 8 && FW_PAD % 8 == 0 && FW_PAD >= FW_MAX_LAG, "fused tile geometry");
+
+// v + (value of lane - d, if that lane exists): one SHFL and one predicated add
+__device__ __forceinline__ uint32_t scan_step(uint32_t v, int d) {
+    uint32_t out;
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .u32 t;\n\tshfl.sync.up.b32 t|p, %1, %2, 0, 0xffffffff;\n\tmov.u32 %0, %1;\n\t@p add.u32 %0, %1, t;\n\t}"
+                 : "=r"(out) : "r"(v), "r"(d));
+    return out;
+}
+
+// Decision for one window from the exact integers D = n c_i - sum c and V = n sum c^2 - (sum c)^2:
+// z = D^2 - k V against a margin that covers every rounding of the reference and of this test (make_fused_const).
+// Returns 1 / 0xFF (signal up / down), 0 (certainly none) or 2 (inconclusive: replay exactly).
+__device__ __forceinline__ uint32_t fused_certify(int D, uint32_t V, const FusedConst &fc) {
+    const float fd = fabsf(__int2float_rn(D));      // exact: |D| < 2^16
+    const float fv = __uint2float_rn(V);
+    const float t = fd * fd;
+    const float z = fmaf(-fc.k, fv, t);
+    const float m = fmaf(fd, fc.e2x2, fmaf(fv, fc.epsk, fc.beta));
+    const uint32_t sgn = (D > 0) ? 1u : 0xFFu;
+    const uint32_t cert = (z > 0.0f) ? sgn : 0u;
+    return (fabsf(z) > m) ? cert : 2u;
+}
+
+// LAG4: lag % 4 == 0, so the prefix sums lag windows back sit at 16-byte aligned shared-memory addresses.
+// R: size / step when known at compile time (10), 0 = read it from `r_rt`.
+template <bool WRITE_CNT, bool LAG4, int R>
+__global__ void __launch_bounds__(GC_THREADS, FW_MIN_CTAS)
+gc_wave_fused_kernel(const uint8_t *__restrict__ seq, const FusedTile *__restrict__ tiles,
+                     const float *__restrict__ gc_tab, int size, int step, int r_rt, int lag, float threshold,
                      const FusedConst fc, uint32_t *__restrict__ cnt_out, float *__restrict__ gc_out,
                      int8_t *__restrict__ sig_out, unsigned long long *__restrict__ stats) {
-    constexpr int NCH = GC_THREADS * K;
-    __shared__ uint32_t ent[NCH + 1];
-    __shared__ __align__(16) uint8_t c8[NCH];
-    __shared__ uint32_t wsum[GC_THREADS / 32];
-    __shared__ uint2 wsum2[GC_THREADS / 32];
-    __shared__ uint16_t bnd[GC_MAX_BOUNDS];
-    __shared__ uint16_t cw[FUSED_MAX_EL];
-    __shared__ __align__(16) uint2 CC[FUSED_MAX_EL + 1];  // exclusive prefixes (sum c, sum c^2); reused as f32 x[] on replay
-    __shared__ int8_t sg[FUSED_MAX_EL];
-    __shared__ int list[FUSED_LIST_CAP];
+    // R0: WW[FW_NCH + 1], the tile's GC bit per base (WW[i] = bits of bytes [16 i, 16 i + 32)), while the counts are
+    //     built; afterwards P2[FW_PAD + FW_MAX_EL], exclusive prefix of c^2
+    __shared__ __align__(16) uint32_t R0[FW_PAD + FW_MAX_EL];
+    __shared__ __align__(16) uint32_t P1[FW_PAD + FW_MAX_EL];      // exclusive prefix of c
+    // R1: bsum[] (GC bases per step-sized block) while the counts are built; afterwards sg[FW_MAX_EL + 16] and list[]
+    __shared__ __align__(16) uint8_t R1[FW_MAX_EL + FW_MAX_R + 16 + FUSED_LIST_CAP * 4];
+    __shared__ __align__(16) uint16_t cw[FW_MAX_EL + 8];           // window counts c_e
+    __shared__ float stab[FW_STAB];                                 // gc_tab when size < FW_STAB
+    __shared__ uint32_t ws1[GC_THREADS / 32], ws2[GC_THREADS / 32];
     __shared__ int list_n;
+    static_assert(sizeof(R0) >= (FW_NCH + 1) * 4, "R0 holds the bit array");
+    uint32_t *const WW = R0;
+    uint16_t *const WW16 = reinterpret_cast<uint16_t *>(R0);
+    uint32_t *const P2 = R0;
+    uint8_t *const bsum = R1;
+    uint8_t *const sg = R1;                                         // sg[e + 7] = decision of element e
+    int *const list = reinterpret_cast<int *>(R1 + FW_MAX_EL + FW_MAX_R + 16);
 
     const int tid = threadIdx.x;
-    const TileDesc td = tiles[blockIdx.x];
-    const uint64_t wbase = win_off[td.item];
-    const uint32_t n_c = (uint32_t)(win_off[td.item + 1] - wbase);
-    const uint32_t w0 = td.first;
-    const uint32_t nw = min((uint32_t)wt, n_c - w0);
-    const uint32_t h = (uint32_t)lag + 1u;
-    const uint32_t hh = min(h, w0);       // halo windows actually present before the tile
-    const uint32_t n_el = nw + hh;        // windows whose counts this tile holds: [w0 - hh, w0 + nw)
-    const uint64_t byte0 = seq_off[td.item] + (uint64_t)(w0 - hh) * (uint64_t)step;
-    const uint32_t lead = (uint32_t)(byte0 & 31u);
-    const uint32_t span = (n_el - 1u) * (uint32_t)step + (uint32_t)size;
-    const uint32_t nch = (lead + span + 15u) >> 4;  // <= NCH by construction of wt
-    if (tid == 0) list_n = 0;
-
-    // ---- phase 1: classify (see gc_window.cu)
-    const uint8_t *src = seq + (byte0 - lead);
-    Bytes32 v[K / 2];
-#pragma unroll
-    for (int j = 0; j < K / 2; ++j) {
-        const uint32_t pi = j * GC_THREADS + tid;
-        if (2u * pi < nch) v[j] = ld_stream32(src + 32u * pi);
-        else {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) v[j].w[q] = 0u;
-        }
-    }
-    uint16_t *ent16 = reinterpret_cast<uint16_t *>(ent);
-#pragma unroll
-    for (int j = 0; j < K / 2; ++j) {
-        const uint32_t pi = j * GC_THREADS + tid;
-        const uint32_t m0 = gc_mask16(v[j].w[0], v[j].w[1], v[j].w[2], v[j].w[3]);
-        const uint32_t m1 = gc_mask16(v[j].w[4], v[j].w[5], v[j].w[6], v[j].w[7]);
-        ent16[4 * pi] = (uint16_t)m0;
-        ent16[4 * pi + 2] = (uint16_t)m1;
-        reinterpret_cast<uint16_t *>(c8)[pi] = (uint16_t)(__popc(m0) | (__popc(m1) << 8));
-    }
-    __syncthreads();
-
-    // ---- scan of chunk counts
-    uint32_t inc[K / 4];
-    uint32_t total = 0;
-#pragma unroll
-    for (int q = 0; q < K / 4; ++q) {
-        const uint32_t c4 = reinterpret_cast<const uint32_t *>(c8)[tid * (K / 4) + q];
-        inc[q] = c4 * 0x01010101u + total * 0x01010101u;
-        total = inc[q] >> 24;
-    }
-    uint32_t sc = total;
     const int lane = tid & 31, warp = tid >> 5;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, sc, d);
-        if (lane >= d) sc += n;
-    }
-    if (lane == 31) wsum[warp] = sc;
-    __syncthreads();
-    uint32_t excl = sc - total;
-#pragma unroll
-    for (int w = 0; w < GC_THREADS / 32; ++w)
-        if (w < warp) excl += wsum[w];
-#pragma unroll
-    for (int q = 0; q < K / 4; ++q) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const uint32_t before = (i == 0) ? (q == 0 ? 0u : (inc[q - 1] >> 24)) : ((inc[q] >> (8 * (i - 1))) & 0xFFu);
-            ent16[2 * (tid * K + q * 4 + i) + 1] = (uint16_t)(excl + before);
-        }
-    }
-    if (tid == GC_THREADS - 1) ent[NCH] = (excl + total) << 16;
-    __syncthreads();
+    const FusedTile td = tiles[blockIdx.x];
+    const uint32_t nw = td.nw, hh = td.hh;                          // hh: halo windows before the tile (0 or lag + 1)
+    const uint32_t h = (uint32_t)lag + 1u;
+    const uint32_t n_el = nw + hh;                                  // windows whose counts this tile holds
+    const uint32_t lead = (uint32_t)(td.byte0 & 31u);
+    const uint32_t r = R ? (uint32_t)R : (uint32_t)r_rt;
+    const uint32_t span = (n_el - 1u) * (uint32_t)step + (uint32_t)size;
+    const uint32_t nch = (lead + span + 15u) >> 4;                  // <= FW_NCH by construction of the tiles
+    const bool use_stab = size < FW_STAB;
+    if (tid == 0) list_n = 0;
+    if (use_stab && tid <= size) stab[tid] = __ldg(gc_tab + tid);
 
-    // ---- window boundaries, counts, GC output
-    const uint32_t r = (uint32_t)size / (uint32_t)step;
-    const uint32_t nb = n_el + r;
-#pragma unroll 2
-    for (uint32_t m = tid; m < nb; m += GC_THREADS) bnd[m] = (uint16_t)prefix_at(ent, lead + m * (uint32_t)step);
-    __syncthreads();
-    float *__restrict__ out = gc_out + (wbase + w0);
-    uint32_t *__restrict__ outc = WRITE_CNT ? cnt_out + (wbase + w0) : nullptr;
-#pragma unroll 4
-    for (uint32_t e = tid; e < n_el; e += GC_THREADS) {
-        const uint32_t cnt = sub_u32(bnd[e + r], bnd[e]);
-        cw[e] = (uint16_t)cnt;
-        if (e >= hh) {
-            out[e - hh] = __ldg(gc_tab + cnt);
-            if (WRITE_CNT) outc[e - hh] = cnt;
-        }
-    }
-    __syncthreads();
-
-    // ---- exact integer prefix sums of c and c^2 over the tile's windows (thread-contiguous chunks)
+    // ---- phase 1: classify, 32 bytes per lane per load (see gc_common.cuh); one bit per base into WW
     {
-        const uint32_t per = ((n_el + GC_THREADS - 1) / GC_THREADS) | 1u;
-        const uint32_t pb = min((uint32_t)tid * per, n_el), pe = min(pb + per, n_el);
+        const uint8_t *src = seq + (td.byte0 - lead);
+        Bytes32 v[FW_K / 2];
+#pragma unroll
+        for (int j = 0; j < FW_K / 2; ++j) {
+            const uint32_t pi = j * GC_THREADS + tid;
+            if (2u * pi < nch) v[j] = ld_stream32(src + 32u * pi);
+        }
+#pragma unroll
+        for (int j = 0; j < FW_K / 2; ++j) {
+            const uint32_t pi = j * GC_THREADS + tid;
+            if (2u * pi < nch) {
+                const uint32_t m0 = gc_mask16(v[j].w[0], v[j].w[1], v[j].w[2], v[j].w[3]);
+                const uint32_t m1 = gc_mask16(v[j].w[4], v[j].w[5], v[j].w[6], v[j].w[7]);
+                WW[2 * pi] = m0 | (m1 << 16);
+                WW16[4 * pi + 2] = (uint16_t)m1;                    // low half of WW[2 pi + 1]; the next piece adds the high half
+                if (pi) WW16[4 * pi - 1] = (uint16_t)m0;            // high half of WW[2 pi - 1]
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- GC bases of every step-sized block: bsum[m] = popc(bits [lead + m step, + step))
+    {
+        const uint32_t nb = n_el + r;
+        const uint32_t smask = (1u << step) - 1u;                   // step <= 16
+#pragma unroll
+        for (int j = 0; j < (FW_MAX_EL + FW_MAX_R + GC_THREADS - 1) / GC_THREADS; ++j) {
+            const uint32_t m = (uint32_t)(j * GC_THREADS + tid);
+            if (m < nb) {
+                const uint32_t p = lead + m * (uint32_t)step;
+                bsum[m] = (uint8_t)__popc((WW[p >> 4] >> (p & 15u)) & smask);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- window counts by sliding over the block sums (thread t owns windows [8t, 8t+8)), then exact prefix sums of
+    //      c and c^2 over the tile
+    uint32_t c[FW_E + 1], q1[FW_E], q2[FW_E];   // q = exclusive prefix at element 8t + j
+    {
+        const uint8_t *bt = bsum + FW_E * tid;
+        if (R == 10) {
+            const uint2 a = *reinterpret_cast<const uint2 *>(bt), b = *reinterpret_cast<const uint2 *>(bt + 8);
+            const uint32_t d = *reinterpret_cast<const uint32_t *>(bt + 16);
+            const uint32_t s = a.x + a.y + (b.x & 0xFFFFu);        // per-byte sums <= 3 * 16
+            c[0] = (s * 0x01010101u) >> 24;
+            c[1] = c[0] + ((b.x >> 16) & 0xFFu) - (a.x & 0xFFu);
+            c[2] = c[1] + (b.x >> 24) - ((a.x >> 8) & 0xFFu);
+            c[3] = c[2] + (b.y & 0xFFu) - ((a.x >> 16) & 0xFFu);
+            c[4] = c[3] + ((b.y >> 8) & 0xFFu) - (a.x >> 24);
+            c[5] = c[4] + ((b.y >> 16) & 0xFFu) - (a.y & 0xFFu);
+            c[6] = c[5] + (b.y >> 24) - ((a.y >> 8) & 0xFFu);
+            c[7] = c[6] + (d & 0xFFu) - ((a.y >> 16) & 0xFFu);
+        } else {
+            uint32_t s = 0;
+            for (uint32_t m = 0; m < r; ++m) s += bt[m];
+            c[0] = s;
+#pragma unroll
+            for (int j = 1; j < FW_E; ++j) c[j] = c[j - 1] + bt[r + j - 1] - bt[j - 1];
+        }
+        reinterpret_cast<uint4 *>(cw)[tid] = make_uint4(c[0] | (c[1] << 16), c[2] | (c[3] << 16), c[4] | (c[5] << 16), c[6] | (c[7] << 16));
+        if (tid < 4) reinterpret_cast<uint32_t *>(cw + FW_MAX_EL)[tid] = 0u;
         uint32_t a1 = 0, a2 = 0;
-        for (uint32_t p = pb; p < pe; ++p) {
-            const uint32_t c = cw[p];
-            a1 += c;
-            a2 += c * c;
+#pragma unroll
+        for (int j = 0; j < FW_E; ++j) {
+            q1[j] = a1;
+            q2[j] = a2;
+            a1 += c[j];
+            a2 += c[j] * c[j];
         }
         uint32_t s1 = a1, s2 = a2;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t t1 = __shfl_up_sync(0xFFFFFFFFu, s1, d), t2 = __shfl_up_sync(0xFFFFFFFFu, s2, d);
-            if (lane >= d) { s1 += t1; s2 += t2; }
+            s1 = scan_step(s1, d);
+            s2 = scan_step(s2, d);
         }
-        if (lane == 31) wsum2[warp] = make_uint2(s1, s2);
-        __syncthreads();
-        uint32_t b1 = s1 - a1, b2 = s2 - a2;
+        if (lane == 31) { ws1[warp] = s1; ws2[warp] = s2; }
+        __syncthreads();   // also: every thread is done with WW and bsum, so P2 and sg may overwrite them
+        const uint32_t o1 = (lane < warp) ? ws1[lane & 7] : 0u, o2 = (lane < warp) ? ws2[lane & 7] : 0u;
+        const uint32_t b1 = s1 - a1 + __reduce_add_sync(0xFFFFFFFFu, o1), b2 = s2 - a2 + __reduce_add_sync(0xFFFFFFFFu, o2);
 #pragma unroll
-        for (int w = 0; w < GC_THREADS / 32; ++w)
-            if (w < warp) { b1 += wsum2[w].x; b2 += wsum2[w].y; }
-        for (uint32_t p = pb; p < pe; ++p) {
-            CC[p] = make_uint2(b1, b2);
-            const uint32_t c = cw[p];
-            b1 += c;
-            b2 += c * c;
-        }
-        if (pe == n_el && pb < pe) CC[n_el] = make_uint2(b1, b2);
+        for (int j = 0; j < FW_E; ++j) { q1[j] += b1; q2[j] += b2; }
+        reinterpret_cast<uint4 *>(P1 + FW_PAD)[2 * tid] = make_uint4(q1[0], q1[1], q1[2], q1[3]);
+        reinterpret_cast<uint4 *>(P1 + FW_PAD)[2 * tid + 1] = make_uint4(q1[4], q1[5], q1[6], q1[7]);
+        reinterpret_cast<uint4 *>(P2 + FW_PAD)[2 * tid] = make_uint4(q2[0], q2[1], q2[2], q2[3]);
+        reinterpret_cast<uint4 *>(P2 + FW_PAD)[2 * tid + 1] = make_uint4(q2[4], q2[5], q2[6], q2[7]);
+        if (tid == 0) *reinterpret_cast<uint2 *>(sg) = make_uint2(0u, 0u);   // sg[7] = element 0: never a signal
     }
     __syncthreads();
 
-    // ---- certificate per window of the tile
-    const uint32_t k_min = (w0 >= (uint32_t)lag) ? 0u : (uint32_t)lag - w0;  // windows before `lag` never signal
-    const int e_shift = (int)hh - (int)h;                                   // stats window of tile window k starts at max(k + e_shift, 0)
-    unsigned unc = 0;
-#pragma unroll 2
-    for (uint32_t k = tid; k < nw; k += GC_THREADS) {
-        const int ea = max((int)k + e_shift, 0);
-        const uint2 A = CC[ea], B = CC[ea + lag];
-        const double s1 = (double)(B.x - A.x), s2 = (double)(B.y - A.y), ci = (double)cw[k + hh];
-        const double D = fma(fc.n, ci, -s1);
-        const double V = fma(fc.n, s2, -s1 * s1);
-        const double aD = fabs(D);
-        const double lo = aD - fc.e2, hi = aD + fc.e2;
-        const bool yes = (lo > 0.0) & (lo * lo > fc.k_hi * fma(V, fc.one_plus_eps, fc.b_hi));
-        const bool no = hi * hi < fc.k_lo * fmax(fma(V, fc.one_minus_eps, -fc.b_lo), 0.0);
-        int dec = yes ? (D > 0.0 ? 1 : -1) : (no ? 0 : 2);
-        if (k < k_min) dec = 0;
-        if (dec == 2) {
-            ++unc;
-            const int slot = atomicAdd(&list_n, 1);
-            if (slot < FUSED_LIST_CAP) list[slot] = (int)k;
-        }
-        sg[k] = (int8_t)dec;
-    }
-    if (stats) {
+    // ---- GC fractions out (thread-strided: coalesced)
+    {
+        float *__restrict__ out = gc_out + td.out0 - hh;
+        uint32_t *__restrict__ outc = WRITE_CNT ? cnt_out + td.out0 - hh : nullptr;
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) unc += __shfl_xor_sync(0xFFFFFFFFu, unc, d);
-        if (lane == 0 && unc) atomicAdd(&stats[0], (unsigned long long)unc);
+        for (int j = 0; j < FW_E; ++j) {
+            const uint32_t e = (uint32_t)(j * GC_THREADS + tid);
+            if (e >= hh && e < n_el) {
+                const uint32_t cnt = cw[e];
+                out[e] = use_stab ? stab[cnt] : __ldg(gc_tab + cnt);
+                if (WRITE_CNT) outc[e] = cnt;
+            }
+        }
+    }
+
+    // ---- certificate: thread t decides elements e = 8t+1 .. 8t+8; the stats window of e is [e-lag-1, e-1), so its
+    //      sums are P[e-1] - P[e-1-lag] = (own q[j]) - (P lag elements back)
+    const bool first = (hh == 0u);
+    const uint32_t e_lo = h;                    // first element that can signal by the general formula (both tile kinds)
+    {
+        c[FW_E] = cw[FW_E * tid + FW_E];
+        uint32_t p1b[FW_E], p2b[FW_E];
+        const int back = FW_PAD + FW_E * tid - lag;   // >= 0 since FW_PAD >= lag
+        if (LAG4) {
+            const uint4 u0 = *reinterpret_cast<const uint4 *>(P1 + back), u1 = *reinterpret_cast<const uint4 *>(P1 + back + 4);
+            p1b[0] = u0.x; p1b[1] = u0.y; p1b[2] = u0.z; p1b[3] = u0.w;
+            p1b[4] = u1.x; p1b[5] = u1.y; p1b[6] = u1.z; p1b[7] = u1.w;
+            const uint4 v0 = *reinterpret_cast<const uint4 *>(P2 + back), v1 = *reinterpret_cast<const uint4 *>(P2 + back + 4);
+            p2b[0] = v0.x; p2b[1] = v0.y; p2b[2] = v0.z; p2b[3] = v0.w;
+            p2b[4] = v1.x; p2b[5] = v1.y; p2b[6] = v1.z; p2b[7] = v1.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < FW_E; ++j) { p1b[j] = P1[back + j]; p2b[j] = P2[back + j]; }
+        }
+        uint32_t pk0 = 0u, pk1 = 0u;
+#pragma unroll
+        for (int j = 0; j < FW_E; ++j) {
+            const uint32_t s1 = q1[j] - p1b[j], s2 = q2[j] - p2b[j];
+            const int D = (int)(c[j + 1] * (uint32_t)lag) - (int)s1;
+            const uint32_t V = s2 * (uint32_t)lag - s1 * s1;
+            const uint32_t dec = fused_certify(D, V, fc);
+            if (j < 4) pk0 = dec * (1u << (8 * (j & 3))) + pk0;
+            else pk1 = dec * (1u << (8 * (j & 3))) + pk1;
+        }
+        const uint32_t e0 = FW_E * tid + 1;
+        if (e0 < e_lo || e0 + FW_E > n_el) {   // edge threads: elements that cannot signal (before `lag`) or do not exist
+#pragma unroll
+            for (int j = 0; j < FW_E; ++j)
+                if (e0 + j < e_lo || e0 + j >= n_el) {
+                    if (j < 4) pk0 &= ~(0xFFu << (8 * (j & 3)));
+                    else pk1 &= ~(0xFFu << (8 * (j & 3)));
+                }
+        }
+        // bytes equal to 2 (bit 1 set, bit 0 clear; 0xFF has both): rare, some window is inconclusive
+        if (((pk0 & ~(pk0 << 1)) | (pk1 & ~(pk1 << 1))) & 0x02020202u) {
+#pragma unroll
+            for (int j = 0; j < FW_E; ++j)
+                if (((((j < 4) ? pk0 : pk1) >> (8 * (j & 3))) & 3u) == 2u) {
+                    const int slot = atomicAdd(&list_n, 1);
+                    if (slot < FUSED_LIST_CAP) list[slot] = (int)(e0 + j);
+                }
+        }
+        *reinterpret_cast<uint2 *>(sg + 8 + FW_E * tid) = make_uint2(pk0, pk1);
     }
     __syncthreads();
 
     // ---- exact replay of inconclusive windows (rare): x_k = gc_tab[c_k] are the f32 values the reference sums
     const int n_list = list_n;  // block-uniform
-    if (n_list > 0) {
-        float *xs = reinterpret_cast<float *>(CC);  // the prefix sums are no longer needed
-        for (uint32_t e = tid; e < n_el; e += GC_THREADS) xs[e] = __ldg(gc_tab + cw[e]);
-        __syncthreads();
+    if (n_list > 0 || first) {
         const float flag = __ull2float_rn((unsigned long long)lag);
         const float flagm1 = __fsub_rn(flag, 1.0f);
-        auto ld = [&](int64_t e) { return xs[e]; };
-        const int n_todo = (n_list <= FUSED_LIST_CAP) ? n_list : (int)nw;  // overflow: replay the whole tile
-        for (int t = tid; t < n_todo; t += GC_THREADS) {
-            const uint32_t k = (n_list <= FUSED_LIST_CAP) ? (uint32_t)list[t] : (uint32_t)t;
-            if (k < k_min) continue;
-            const int ea = max((int)k + e_shift, 0);
-            sg[k] = (int8_t)zscore_decide(ld, (int64_t)ea, (uint64_t)lag, flag, flagm1, xs[k + hh], threshold);
+        auto ld = [&](int64_t e) { return __ldg(gc_tab + cw[e]); };
+        if (first && tid == 0 && n_el > (uint32_t)lag) {
+            // window `lag` of the ctg takes its statistics from windows [0, lag) (stat.rs:30-31), not [lag-1-lag, lag-1)
+            sg[lag + 7] = (uint8_t)zscore_decide(ld, 0, (uint64_t)lag, flag, flagm1, ld(lag), threshold);
         }
+        const int n_todo = (n_list <= FUSED_LIST_CAP) ? n_list : (int)n_el;  // overflow: replay the whole tile
+        for (int t = tid; t < n_todo; t += GC_THREADS) {
+            const uint32_t e = (n_list <= FUSED_LIST_CAP) ? (uint32_t)list[t] : (uint32_t)t;
+            if (e < e_lo || e >= n_el) continue;
+            sg[e + 7] = (uint8_t)zscore_decide(ld, (int64_t)e - (int64_t)h, (uint64_t)lag, flag, flagm1, ld(e), threshold);
+        }
+        if (stats && tid == 0 && n_list) atomicAdd(&stats[0], (unsigned long long)n_list);
         __syncthreads();
     }
-    int8_t *__restrict__ so = sig_out + (wbase + w0);
-    for (uint32_t k = tid; k < nw; k += GC_THREADS) so[k] = sg[k];
+    {
+        int8_t *__restrict__ so = sig_out + td.out0 + tid;
+        const uint8_t *sgo = sg + 7 + hh + tid;
+#pragma unroll
+        for (int j = 0; j < FW_E; ++j)
+            if ((uint32_t)(j * GC_THREADS + tid) < nw) so[j * GC_THREADS] = (int8_t)sgo[j * GC_THREADS];
+    }
 }
 
 // Host-side bounds of the certificate (derivation: DESIGN.md §3 "Kernel AB").  With u = 2^-24, n = lag,
@@ -223,6 +285,15 @@ gc_wave_fused_kernel(const uint8_t *__restrict__ seq, const uint64_t *__restrict
 //   fl(thr * sd^) = thr sqrt(Q*/(n-1)) (1 +- R),  R = (0.6 n + 8) u,  Q* = sum (x_j - m^)^2 in [S_x, S_x + n E_m^2]
 //   sqrt(S_x) = sqrt(S_c) +- sqrt(n) u  =>  S_x in [(1-eps) S_c - (1/eps - 1) n u^2, (1+eps) S_c + (1 + 1/eps) n u^2]
 // and everything is scaled by n*size (D = n*size*(x^c_i - mu_c)) resp. n*size^2 (V = n*size^2*S_c).
+// The device evaluates the two tests in f32 (|D| exact, V rounded once, one rounding per operation): the
+// constants are widened by 8u and rounded away from the uncertain band so that a computed "certain" implies the
+// exact-arithmetic one.
+static float f_up(double x) {
+    float f = (float)x;
+    if ((double)f < x) f = nextafterf(f, INFINITY);
+    return f;
+}
+
 FusedConst make_fused_const(int32_t size, uint64_t lag, float threshold) {
     const double u = 5.9604644775390625e-8;
     const float flag = (float)lag, flagm1 = flag - 1.0f;  // `data.len() as f32`, `len - 1.`
@@ -232,38 +303,45 @@ FusedConst make_fused_const(int32_t size, uint64_t lag, float threshold) {
     const double R = (0.6 * n + 8.0) * u;
     const double eps = 2e-6;
     const double b2 = 4.0 * n * u * u;            // 4x the n u^2 needed
-    const double t2 = (double)threshold * (double)threshold;
+    const double k = (double)threshold * (double)threshold * n / nm1;
+    const double rho_hi = (1.0 + R) * (1.0 + R) * (1.0 + 3.0 * u) - 1.0, rho_lo = 1.0 - (1.0 - R) * (1.0 - R) * (1.0 - 3.0 * u);
+    const double e2 = E2 * n * sz;                                                   // on |D|
+    const double B_hi = n * sz * sz * (b2 * (1.0 + 1.0 / eps) + n * E_m * E_m);      // on V
+    const double B_lo = n * sz * sz * (b2 * (1.0 / eps - 1.0));
+    // exact tests:  signal        <=  (|D| - e2)^2 > k (1 + rho_hi) ((1 + eps) V + B_hi)   and |D| > e2
+    //               no signal     <=  (|D| + e2)^2 < k (1 - rho_lo) max((1 - eps) V - B_lo, 0)
+    // both follow from |D^2 - k V| > 2 e2 |D| + k eps' V + beta with the sign of D^2 - k V choosing between them:
+    const double eps1 = (1.0 + rho_hi) * (1.0 + eps) - 1.0, eps2 = 1.0 - (1.0 - rho_lo) * (1.0 - eps);
+    const double beta = std::max(k * (1.0 + rho_hi) * B_hi, k * (1.0 - rho_lo) * B_lo + e2 * e2);
+    // f32 evaluation on the device: z = fma(-k_f, fl(V), fl(D^2)) is within 3u D^2 + 4u k V of D^2 - k V, and the margin
+    // itself carries three roundings: 3u |D| n size >= 3u D^2 goes into the |D| term, 6u into eps', (1 + 8u) on top.
+    const double infl = 1.0 + 8.0 * u;
     FusedConst c;
-    c.n = n;
-    c.e2 = E2 * n * sz * (1.0 + 1e-9);
-    c.k_hi = t2 * (1.0 + R) * (1.0 + R) * (1.0 + 3.0 * u) * n / nm1 * (1.0 + 1e-9);
-    c.k_lo = t2 * (1.0 - R) * (1.0 - R) * (1.0 - 3.0 * u) * n / nm1 * (1.0 - 1e-9);
-    c.one_plus_eps = 1.0 + eps;
-    c.one_minus_eps = 1.0 - eps;
-    c.b_hi = n * sz * sz * (b2 * (1.0 + 1.0 / eps) + n * E_m * E_m) * (1.0 + 1e-9);
-    c.b_lo = n * sz * sz * (b2 * (1.0 / eps - 1.0)) * (1.0 + 1e-9);
+    c.k = (float)k;
+    c.e2x2 = f_up((2.0 * e2 + 3.0 * u * n * sz) * infl);
+    c.epsk = f_up(k * (std::max(eps1, eps2) + 6.0 * u) * infl);
+    c.beta = f_up(beta * infl);
     return c;
 }
 
 // The fused kernel covers the default statistics only: influence exactly 1 (filtered == data, stat.rs:42,47),
 // a finite non-negative threshold (the certificate squares it) and an eligible geometry.
 bool wave_fused_ok(const gams_cuda_wave_plan *p, float threshold, float influence) {
-    return p->fused_wt > 0 && influence == 1.0f && threshold >= 0.0f && threshold < 1.0e18f && p->ctx->zscore_mode == 0 &&
+    return p->fused_wt > 0 && influence == 1.0f && threshold >= 0.0f && threshold < 1.0e9f && p->ctx->zscore_mode == 0 &&
            p->win.min_len >= p->lag;
 }
 
 // Windows per fused tile, or 0 when the fused path does not apply to this geometry.
-int fused_windows_per_tile(int32_t size, int32_t step, uint64_t lag, int k) {
-    if (k != 4 && k != 8) return 0;
-    if (size % step != 0 || lag < 2 || lag > 4000) return 0;
-    const int64_t span_cap = (int64_t)GC_THREADS * k * 16 - 31;
-    const int64_t h = (int64_t)lag + 1, r = size / step;
-    int64_t wt = (span_cap - size) / step + 1 - h;           // tile windows + halo windows must fit the byte span
-    wt = std::min<int64_t>(wt, FUSED_MAX_EL - h);            // counts / prefixes / decisions per tile
-    wt = std::min<int64_t>(wt, GC_MAX_BOUNDS - h - r);       // boundary table
+int fused_windows_per_tile(int32_t size, int32_t step, uint64_t lag) {
+    if (step > 16 || size % step != 0 || size / step > FW_MAX_R) return 0;   // a block's bits come from one 32-bit word
+    if (lag < 2 || lag > FW_MAX_LAG) return 0;
+    if ((uint64_t)lag * (uint64_t)size >= 65536) return 0;   // D and V = n sum c^2 - (sum c)^2 exact in 32 bits
+    const int64_t span_cap = (int64_t)FW_NCH * 16 - 31;      // worst case lead = 31
+    if (size > span_cap) return 0;
+    const int64_t h = (int64_t)lag + 1;
+    const int64_t n_el = std::min<int64_t>((span_cap - size) / step + 1, FW_MAX_EL);
+    const int64_t wt = n_el - h;
     if (wt < 4 * h || wt < 64) return 0;                     // halo re-read would exceed 25 %
-    if ((uint64_t)size * (uint64_t)size * (uint64_t)(wt + h) >= (1ull << 32)) return 0;  // sum c^2 must fit u32
-    if ((double)lag * (double)size * (double)lag * (double)size >= 4e15) return 0;        // n s2, s1^2 exact in f64
     return (int)wt;
 }
 
@@ -278,13 +356,18 @@ int32_t launch_gc_wave_fused(gams_cuda_wave_plan *p, cudaStream_t st, const uint
     if (t1 == t0) return GAMS_CUDA_OK;
     const FusedConst fc = make_fused_const(p->size, p->lag, threshold);
     const unsigned grid = (unsigned)(t1 - t0);
-    const TileDesc *tiles = p->d_ftiles + t0;
-#define GAMS_FUSED_LAUNCH(KK, WC)                                                                                       \
-    gc_wave_fused_kernel<KK, WC><<<grid, GC_THREADS, 0, st>>>(d_seq, p->d_seq_off, p->win.d_off, tiles, p->d_gc_tab,   \
-                                                              p->size, p->step, p->fused_wt, (int)p->lag, threshold,   \
-                                                              fc, d_cnt, d_gc, d_sig, d_stats)
-    if (p->geom.k == 4) { if (d_cnt) GAMS_FUSED_LAUNCH(4, true); else GAMS_FUSED_LAUNCH(4, false); }
-    else { if (d_cnt) GAMS_FUSED_LAUNCH(8, true); else GAMS_FUSED_LAUNCH(8, false); }
+    const FusedTile *tiles = p->d_ftiles + t0;
+    const int r = p->size / p->step;
+#define GAMS_FUSED_LAUNCH(WC, L4, RR)                                                                                   \
+    gc_wave_fused_kernel<WC, L4, RR><<<grid, GC_THREADS, 0, st>>>(d_seq, tiles, p->d_gc_tab, p->size, p->step, r,      \
+                                                                  (int)p->lag, threshold, fc, d_cnt, d_gc, d_sig, d_stats)
+#define GAMS_FUSED_LAUNCH_R(WC, L4)                                                                                     \
+    do {                                                                                                               \
+        if (r == 10) GAMS_FUSED_LAUNCH(WC, L4, 10); else GAMS_FUSED_LAUNCH(WC, L4, 0);                                 \
+    } while (0)
+    if (p->lag % 4 == 0) { if (d_cnt) GAMS_FUSED_LAUNCH_R(true, true); else GAMS_FUSED_LAUNCH_R(false, true); }
+    else { if (d_cnt) GAMS_FUSED_LAUNCH_R(true, false); else GAMS_FUSED_LAUNCH_R(false, false); }
+#undef GAMS_FUSED_LAUNCH_R
 #undef GAMS_FUSED_LAUNCH
     ++p->launches;
     CUDA_TRY(cudaGetLastError());

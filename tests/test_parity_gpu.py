@@ -376,14 +376,21 @@ def _wave_all_modes(ctx, orc, seqs, size, step, lag, thr, expect_fused=None):
 
 
 @pytest.mark.parametrize("size,step,lag", [(100, 10, 100), (100, 10, 2), (100, 50, 30), (100, 100, 10), (1, 1, 100),
-                                           (16, 16, 8), (1000, 100, 20), (5000, 1000, 5), (30, 10, 400), (64, 8, 1000)])
+                                           (16, 16, 8), (1000, 100, 20), (5000, 1000, 5), (30, 10, 400), (64, 8, 1000),
+                                           (64, 8, 100), (100, 5, 200), (160, 16, 101), (120, 12, 30), (12, 12, 33)])
 def test_fused_wave_matches_replay_and_oracle(ctx, orc, size, step, lag):
     g = synth.genome(1_200_000, seed=size * 7 + lag)
     flat = np.tile(np.frombuffer(b"ACATTTTTAT" * 5 + b"GCGCGCGCGATATATATATATATATATATATATATATATATATATATATA", dtype=np.uint8), 1500)
     need = size + (lag + 2) * step
     seqs = [g[:400_003], g[400_003:400_003 + need], g[500_000:], flat, np.full(max(need, 20_000), ord("N"), np.uint8),
             np.concatenate([g[:need], flat[:need], g[need:3 * need]])]
-    fused = (size, step, lag) not in {(5000, 1000, 5), (30, 10, 400), (64, 8, 1000)}  # halo too large a share of a tile
+    # eligibility of the fused kernel (fused_windows_per_tile, gc_wave_fused.cu): a block's bits come from one 32-bit
+    # word, D and V exact in 32 bits, the lag+1-window halo at most a quarter of a tile
+    n_el = min((256 * 6 * 16 - 31 - size) // step + 1, 2048)
+    fused = (step <= 16 and size % step == 0 and size // step <= 248 and 2 <= lag <= 400 and lag * size < 65536
+             and n_el - (lag + 1) >= max(4 * (lag + 1), 64))
+    assert fused == ((size, step, lag) in {(100, 10, 100), (100, 10, 2), (1, 1, 100), (16, 16, 8), (30, 10, 400), (64, 8, 100),
+                                           (100, 5, 200), (160, 16, 101), (120, 12, 30), (12, 12, 33)})
     for thr in (3.0, 0.0, 1.0, 7.5):
         _wave_all_modes(ctx, orc, seqs, size, step, lag, thr, expect_fused=fused)
 
@@ -417,7 +424,8 @@ def test_fused_wave_replay_fraction_and_fallbacks(ctx, orc):
     # geometries / statistics the fused kernel does not cover take Kernel A + Kernel B
     _wave_all_modes(ctx, orc, [g[:300_000]], 97, 13, 31, 3.0, expect_fused=False)      # size % step != 0
     _wave_all_modes(ctx, orc, [g[:300_000]], 100, 10, 100, -1.0, expect_fused=False)    # negative threshold
-    _wave_all_modes(ctx, orc, [g[:300_000]], 20000, 5000, 2, 3.0, expect_fused=False)   # a window per tile
+    _wave_all_modes(ctx, orc, [g[:300_000]], 20000, 5000, 2, 3.0, expect_fused=False)   # step > 16
+    _wave_all_modes(ctx, orc, [g[:300_000]], 700, 10, 100, 3.0, expect_fused=False)     # lag * size >= 2^16
     plan = api.WavePlan(ctx, np.array([0, 300_000], dtype=np.uint64), 100, 10, 100)
     assert plan.fused(3.0, 1.0) and not plan.fused(3.0, 0.5) and not plan.fused(float("nan"), 1.0)
     plan.close()
