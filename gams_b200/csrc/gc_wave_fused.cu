@@ -28,6 +28,8 @@ namespace gams {
 #define FW_MIN_CTAS 6
 #endif
 constexpr int FW_NCH = GC_THREADS * FW_K;  // 16-byte chunks per tile
+constexpr int FW_NBLK = ((FW_MAX_EL + FW_MAX_R + GC_THREADS - 1) / GC_THREADS) * GC_THREADS;  // block sums per tile
+static_assert((31 + (FW_NBLK - 1) * 16) / 16 < FW_PAD + FW_MAX_EL, "stale block reads stay inside R0");
 static_assert(FW_MAX_EL == GC_THREADS * FW_E && FW_E == 8 && FW_PAD % 8 == 0 && FW_PAD >= FW_MAX_LAG, "fused tile geometry");
 
 // v + (value of lane - d, if that lane exists): one SHFL and one predicated add
@@ -65,7 +67,7 @@ gc_wave_fused_kernel(const uint8_t *__restrict__ seq, const FusedTile *__restric
     __shared__ __align__(16) uint32_t R0[FW_PAD + FW_MAX_EL];
     __shared__ __align__(16) uint32_t P1[FW_PAD + FW_MAX_EL];      // exclusive prefix of c
     // R1: bsum[] (GC bases per step-sized block) while the counts are built; afterwards sg[FW_MAX_EL + 16] and list[]
-    __shared__ __align__(16) uint8_t R1[FW_MAX_EL + FW_MAX_R + 16 + FUSED_LIST_CAP * 4];
+    __shared__ __align__(16) uint8_t R1[FW_NBLK + 8 + FW_MAX_LAG + FUSED_LIST_CAP * 4];
     __shared__ __align__(16) uint16_t cw[FW_MAX_EL + 8];           // window counts c_e
     __shared__ float stab[FW_STAB];                                 // gc_tab when size < FW_STAB
     __shared__ uint32_t ws1[GC_THREADS / 32], ws2[GC_THREADS / 32];
@@ -76,7 +78,7 @@ gc_wave_fused_kernel(const uint8_t *__restrict__ seq, const FusedTile *__restric
     uint32_t *const P2 = R0;
     uint8_t *const bsum = R1;
     uint8_t *const sg = R1;                                         // sg[e + 7] = decision of element e
-    int *const list = reinterpret_cast<int *>(R1 + FW_MAX_EL + FW_MAX_R + 16);
+    int *const list = reinterpret_cast<int *>(R1 + FW_NBLK + 8 + FW_MAX_LAG);
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -115,18 +117,15 @@ gc_wave_fused_kernel(const uint8_t *__restrict__ seq, const FusedTile *__restric
     }
     __syncthreads();
 
-    // ---- GC bases of every step-sized block: bsum[m] = popc(bits [lead + m step, + step))
+    // ---- GC bases of every step-sized block: bsum[m] = popc(bits [lead + m step, + step)).  Branch-free: blocks past
+    //      the tile's last boundary read stale (in-bounds) words and are never used.
     {
-        const uint32_t nb = n_el + r;
         const uint32_t smask = (1u << step) - 1u;                   // step <= 16
+        uint32_t p = lead + (uint32_t)tid * (uint32_t)step;
+        const uint32_t dp = (uint32_t)GC_THREADS * (uint32_t)step;
 #pragma unroll
-        for (int j = 0; j < (FW_MAX_EL + FW_MAX_R + GC_THREADS - 1) / GC_THREADS; ++j) {
-            const uint32_t m = (uint32_t)(j * GC_THREADS + tid);
-            if (m < nb) {
-                const uint32_t p = lead + m * (uint32_t)step;
-                bsum[m] = (uint8_t)__popc((WW[p >> 4] >> (p & 15u)) & smask);
-            }
-        }
+        for (int j = 0; j < FW_NBLK / GC_THREADS; ++j, p += dp)
+            bsum[j * GC_THREADS + tid] = (uint8_t)__popc((WW[p >> 4] >> (p & 15u)) & smask);
     }
     __syncthreads();
 
@@ -184,17 +183,29 @@ gc_wave_fused_kernel(const uint8_t *__restrict__ seq, const FusedTile *__restric
     }
     __syncthreads();
 
-    // ---- GC fractions out (thread-strided: coalesced)
+    // ---- GC fractions out (thread-strided: coalesced); loads are unconditional, only the stores are predicated
     {
-        float *__restrict__ out = gc_out + td.out0 - hh;
-        uint32_t *__restrict__ outc = WRITE_CNT ? cnt_out + td.out0 - hh : nullptr;
+        float *__restrict__ out = gc_out + (td.out0 - hh) + tid;
+        uint32_t *__restrict__ outc = WRITE_CNT ? cnt_out + (td.out0 - hh) + tid : nullptr;
+        const uint16_t *cwt = cw + tid;
+        if (use_stab) {
 #pragma unroll
-        for (int j = 0; j < FW_E; ++j) {
-            const uint32_t e = (uint32_t)(j * GC_THREADS + tid);
-            if (e >= hh && e < n_el) {
-                const uint32_t cnt = cw[e];
-                out[e] = use_stab ? stab[cnt] : __ldg(gc_tab + cnt);
-                if (WRITE_CNT) outc[e] = cnt;
+            for (int j = 0; j < FW_E; ++j) {
+                const uint32_t cnt = cwt[j * GC_THREADS];
+                const float g = stab[cnt & (FW_STAB - 1)];
+                if ((uint32_t)(j * GC_THREADS + tid) - hh < nw) {
+                    out[j * GC_THREADS] = g;
+                    if (WRITE_CNT) outc[j * GC_THREADS] = cnt;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < FW_E; ++j) {
+                const uint32_t cnt = cwt[j * GC_THREADS];
+                if ((uint32_t)(j * GC_THREADS + tid) - hh < nw) {
+                    out[j * GC_THREADS] = __ldg(gc_tab + cnt);
+                    if (WRITE_CNT) outc[j * GC_THREADS] = cnt;
+                }
             }
         }
     }
@@ -273,8 +284,10 @@ gc_wave_fused_kernel(const uint8_t *__restrict__ seq, const FusedTile *__restric
         int8_t *__restrict__ so = sig_out + td.out0 + tid;
         const uint8_t *sgo = sg + 7 + hh + tid;
 #pragma unroll
-        for (int j = 0; j < FW_E; ++j)
-            if ((uint32_t)(j * GC_THREADS + tid) < nw) so[j * GC_THREADS] = (int8_t)sgo[j * GC_THREADS];
+        for (int j = 0; j < FW_E; ++j) {
+            const int8_t v = (int8_t)sgo[j * GC_THREADS];
+            if ((uint32_t)(j * GC_THREADS + tid) < nw) so[j * GC_THREADS] = v;
+        }
     }
 }
 
