@@ -322,14 +322,7 @@ GAMS_API int32_t gams_cuda_wave_plan_create(gams_cuda_ctx *ctx, int32_t dev_inde
     if (p->fused_wt) {
         for (int64_t c = 0; c < n_ctg; ++c) {
             const uint64_t n_c = p->h_win_off[c + 1] - p->h_win_off[c];
-            for (uint64_t w = 0; w < n_c; w += (uint64_t)p->fused_wt) {
-                FusedTile t{};
-                t.hh = w ? (uint32_t)lag + 1u : 0u;   // w is 0 or a multiple of fused_wt >= 4 (lag + 1)
-                t.byte0 = p->h_seq_off[c] + (w - t.hh) * (uint64_t)step;
-                t.out0 = p->h_win_off[c] + w;
-                t.nw = (uint32_t)std::min<uint64_t>((uint64_t)p->fused_wt, n_c - w);
-                ft.push_back(t);
-            }
+            fused_tiles_for_ctg(ft, p->h_seq_off[c], p->h_win_off[c], n_c, step, lag, p->fused_wt);
             p->h_ftile_off[c + 1] = ft.size();
         }
         ARG_CHECK(ft.size() < (1ull << 31), "wave_plan_create: too many tiles");
@@ -397,7 +390,10 @@ GAMS_API int32_t gams_cuda_wave_dev(gams_cuda_wave_plan *p, void *stream, const 
                                     int8_t *d_signal) {
     ARG_CHECK(p && d_gc && d_signal && (d_seq || p->total_bases == 0), "wave_dev: NULL argument");
     DeviceGuard g(p->device);
-    if (wave_fused_ok(p, threshold, influence))
+    // the fused kernel writes 32 / 8 aligned bytes per thread
+    const bool aligned = (reinterpret_cast<uintptr_t>(d_gc) & 15u) == 0 && (reinterpret_cast<uintptr_t>(d_signal) & 7u) == 0 &&
+                         (reinterpret_cast<uintptr_t>(d_gc_count) & 15u) == 0;
+    if (aligned && wave_fused_ok(p, threshold, influence))
         return launch_gc_wave_fused(p, (cudaStream_t)stream, d_seq, threshold, d_gc_count, d_gc, d_signal,
                                     p->ctx->devs[p->dev_index].d_zstats, 0, p->n_ctg);
     int32_t rc = launch_gc_windows(p, (cudaStream_t)stream, d_seq, d_gc_count, d_gc, &p->launches, 0, p->n_ctg);

@@ -91,11 +91,12 @@ struct FusedConst {
     float k, e2x2, epsk, beta;
 };
 struct alignas(32) FusedTile {
-    uint64_t byte0;   // first sequence byte the tile reads (its first halo window)
-    uint64_t out0;    // global index of the tile's first output window
-    uint32_t nw;      // output windows
-    uint32_t hh;      // halo windows before them: 0 (first tile of a ctg) or lag + 1
-    uint32_t pad[2];
+    int64_t byte0;     // sequence byte where element 0 starts (negative only for the first tile of the buffer)
+    int64_t g0;        // global window index of element 0; g0 = 7 (mod 8)
+    uint32_t e_out0;   // outputs are elements [e_out0, e_out1)
+    uint32_t e_out1;
+    int32_t e_ctg0;    // element of the ctg's window 0 (first tile of a ctg), else far negative
+    uint32_t pi_min;   // 32-byte pieces of the tile that lie before the start of the sequence buffer (not loaded)
 };
 
 // Geometry of Kernel B1 (zscore.cu)
@@ -200,5 +201,7 @@ int fused_windows_per_tile(int32_t size, int32_t step, uint64_t lag);
 int32_t launch_gc_wave_fused(gams_cuda_wave_plan *p, cudaStream_t st, const uint8_t *d_seq, float threshold,
                              uint32_t *d_cnt, float *d_gc, int8_t *d_sig, unsigned long long *d_stats, int64_t c0,
                              int64_t c1);
+void fused_tiles_for_ctg(std::vector<FusedTile> &out, uint64_t seq_off, uint64_t win_off, uint64_t n_c, int32_t step,
+                         uint64_t lag, int wt);
 bool wave_fused_ok(const gams_cuda_wave_plan *p, float threshold, float influence);
 }  // namespace gams

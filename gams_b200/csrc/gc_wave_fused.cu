@@ -29,7 +29,7 @@ namespace gams {
 #endif
 constexpr int FW_NCH = GC_THREADS * FW_K;  // 16-byte chunks per tile
 constexpr int FW_NBLK = ((FW_MAX_EL + FW_MAX_R + GC_THREADS - 1) / GC_THREADS) * GC_THREADS;  // block sums per tile
-static_assert((31 + (FW_NBLK - 1) * 16) / 16 < FW_PAD + FW_MAX_EL, "stale block reads stay inside R0");
+static_assert((31 + (FW_NBLK - 1) * 16) / 16 < FW_NBLK + 4, "stale block reads stay inside WW");
 static_assert(FW_MAX_EL == GC_THREADS * FW_E && FW_E == 8 && FW_PAD % 8 == 0 && FW_PAD >= FW_MAX_LAG, "fused tile geometry");
 
 // v + (value of lane - d, if that lane exists): one SHFL and one predicated add
@@ -54,7 +54,22 @@ __device__ __forceinline__ uint32_t fused_certify(int D, uint32_t V, const Fused
     return (fabsf(z) > m) ? cert : 2u;
 }
 
-// LAG4: lag % 4 == 0, so the prefix sums lag windows back sit at 16-byte aligned shared-memory addresses.
+// GC bit of each of the 32 bytes in v (bit i <=> byte i is one of C G c g): the four flags of a word are gathered
+// into the top nibble by one multiply (gc_gather) and shifted into the mask by one funnel shift.
+__device__ __forceinline__ uint32_t gc_mask32(const Bytes32 &v) {
+    uint32_t m = gc_gather(v.w[7]) >> 28;
+#pragma unroll
+    for (int q = 6; q >= 0; --q) m = __funnelshift_l(gc_gather(v.w[q]), m, 4);
+    return m;
+}
+
+// Tile layout.  A tile holds FW_MAX_EL consecutive windows ("elements") of one ctg; element e is global window
+// g0 + e with g0 = 7 (mod 8), so that the eight elements 8t+1 .. 8t+8 a thread decides start at a multiple of 8 in the
+// output arrays: 32 bytes of GC fractions go out as two 128-bit stores and the eight signals as one 64-bit store.
+// Elements [e_out0, e_out1) are the tile's outputs; those before are the lag+1-window halo (or, in a ctg's first tile,
+// the 1-8 alignment elements before the ctg's window 0, which read the neighbouring bytes and are never used).
+//
+// LAG4: lag % 4 == 0, so the counts lag windows back sit at 8-byte aligned shared-memory addresses.
 // R: size / step when known at compile time (10), 0 = read it from `r_rt`.
 template <bool WRITE_CNT, bool LAG4, int R>
 __global__ void __launch_bounds__(GC_THREADS, FW_MIN_CTAS)
@@ -62,56 +77,60 @@ gc_wave_fused_kernel(const uint8_t *__restrict__ seq, const FusedTile *__restric
                      const float *__restrict__ gc_tab, int size, int step, int r_rt, int lag, float threshold,
                      const FusedConst fc, uint32_t *__restrict__ cnt_out, float *__restrict__ gc_out,
                      int8_t *__restrict__ sig_out, unsigned long long *__restrict__ stats) {
-    // R0: WW[FW_NCH + 1], the tile's GC bit per base (WW[i] = bits of bytes [16 i, 16 i + 32)), while the counts are
-    //     built; afterwards P2[FW_PAD + FW_MAX_EL], exclusive prefix of c^2
-    __shared__ __align__(16) uint32_t R0[FW_PAD + FW_MAX_EL];
-    __shared__ __align__(16) uint32_t P1[FW_PAD + FW_MAX_EL];      // exclusive prefix of c
-    // R1: bsum[] (GC bases per step-sized block) while the counts are built; afterwards sg[FW_MAX_EL + 16] and list[]
-    __shared__ __align__(16) uint8_t R1[FW_NBLK + 8 + FW_MAX_LAG + FUSED_LIST_CAP * 4];
-    __shared__ __align__(16) uint16_t cw[FW_MAX_EL + 8];           // window counts c_e
+    // WW[i] = GC bits of bytes [16 i, 16 i + 32) of the tile's span (consecutive words overlap by 16 bits so that a
+    // block of <= 16 bases always comes out of one word)
+    __shared__ __align__(16) uint32_t WW[FW_NBLK + 4];
+    // R1: bsum[] (GC bases per step-sized block) while the counts are built; afterwards sg[] and list[]
+    __shared__ __align__(16) uint8_t R1[FW_NBLK + 8 + FUSED_LIST_CAP * 4];
+    __shared__ __align__(16) uint16_t cwp[FW_PAD + FW_MAX_EL + 8];  // window counts c_e at cwp[FW_PAD + e]
+    __shared__ __align__(16) uint2 Pq[(FW_PAD + FW_MAX_EL) / 4];    // (sum c, sum c^2) over elements < 4 m, at Pq[FW_PAD/4 + m]
     __shared__ float stab[FW_STAB];                                 // gc_tab when size < FW_STAB
     __shared__ uint32_t ws1[GC_THREADS / 32], ws2[GC_THREADS / 32];
     __shared__ int list_n;
-    static_assert(sizeof(R0) >= (FW_NCH + 1) * 4, "R0 holds the bit array");
-    uint32_t *const WW = R0;
-    uint16_t *const WW16 = reinterpret_cast<uint16_t *>(R0);
-    uint32_t *const P2 = R0;
+    static_assert(FW_NBLK + 4 >= FW_NCH + 1, "WW holds the bit array");
+    uint16_t *const WW16 = reinterpret_cast<uint16_t *>(WW);
+    uint16_t *const cw = cwp + FW_PAD;
     uint8_t *const bsum = R1;
-    uint8_t *const sg = R1;                                         // sg[e + 7] = decision of element e
-    int *const list = reinterpret_cast<int *>(R1 + FW_NBLK + 8 + FW_MAX_LAG);
+    uint8_t *const sg = R1;                                         // sg[e - 1] = decision of element e
+    int *const list = reinterpret_cast<int *>(R1 + FW_NBLK + 8);
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const FusedTile td = tiles[blockIdx.x];
-    const uint32_t nw = td.nw, hh = td.hh;                          // hh: halo windows before the tile (0 or lag + 1)
-    const uint32_t h = (uint32_t)lag + 1u;
-    const uint32_t n_el = nw + hh;                                  // windows whose counts this tile holds
-    const uint32_t lead = (uint32_t)(td.byte0 & 31u);
+    const uint32_t e_out0 = td.e_out0, e_out1 = td.e_out1;          // e_out1 is also the number of elements the tile holds
+    const uint32_t lead = (uint32_t)(td.byte0 & 31);
     const uint32_t r = R ? (uint32_t)R : (uint32_t)r_rt;
-    const uint32_t span = (n_el - 1u) * (uint32_t)step + (uint32_t)size;
+    const uint32_t span = (e_out1 - 1u) * (uint32_t)step + (uint32_t)size;
     const uint32_t nch = (lead + span + 15u) >> 4;                  // <= FW_NCH by construction of the tiles
     const bool use_stab = size < FW_STAB;
     if (tid == 0) list_n = 0;
     if (use_stab && tid <= size) stab[tid] = __ldg(gc_tab + tid);
+    // Elements before the tile count as zeros: a thread whose first stats window starts before element 0 then slides
+    // into correct sums by the time its window lies inside the tile.
+    if (tid < FW_PAD / 8) reinterpret_cast<uint4 *>(cwp)[tid] = make_uint4(0u, 0u, 0u, 0u);
+    else if (tid < FW_PAD / 4) reinterpret_cast<uint4 *>(Pq)[tid - FW_PAD / 8] = make_uint4(0u, 0u, 0u, 0u);
 
     // ---- phase 1: classify, 32 bytes per lane per load (see gc_common.cuh); one bit per base into WW
     {
-        const uint8_t *src = seq + (td.byte0 - lead);
+        const uint8_t *src = seq + (td.byte0 - (int64_t)lead);
         Bytes32 v[FW_K / 2];
 #pragma unroll
         for (int j = 0; j < FW_K / 2; ++j) {
             const uint32_t pi = j * GC_THREADS + tid;
-            if (2u * pi < nch) v[j] = ld_stream32(src + 32u * pi);
+            if (2u * pi < nch && pi >= td.pi_min) v[j] = ld_stream32(src + 32u * pi);
         }
 #pragma unroll
         for (int j = 0; j < FW_K / 2; ++j) {
             const uint32_t pi = j * GC_THREADS + tid;
-            if (2u * pi < nch) {
-                const uint32_t m0 = gc_mask16(v[j].w[0], v[j].w[1], v[j].w[2], v[j].w[3]);
-                const uint32_t m1 = gc_mask16(v[j].w[4], v[j].w[5], v[j].w[6], v[j].w[7]);
-                WW[2 * pi] = m0 | (m1 << 16);
-                WW16[4 * pi + 2] = (uint16_t)m1;                    // low half of WW[2 pi + 1]; the next piece adds the high half
-                if (pi) WW16[4 * pi - 1] = (uint16_t)m0;            // high half of WW[2 pi - 1]
+            if (2u * (pi - lane) < nch) {                           // warp-uniform
+                const uint32_t m = gc_mask32(v[j]);
+                const uint32_t nx = __shfl_down_sync(0xFFFFFFFFu, m, 1);
+                if (lane != 31) *reinterpret_cast<uint2 *>(WW + 2 * pi) = make_uint2(m, __funnelshift_r(m, nx, 16));
+                else {
+                    WW[2 * pi] = m;
+                    WW16[4 * pi + 2] = (uint16_t)(m >> 16);         // low half of WW[2 pi + 1] ...
+                }
+                if (lane == 0 && pi) WW16[4 * pi - 1] = (uint16_t)m;  // ... whose high half comes from the next warp's lane 0
             }
         }
     }
@@ -130,8 +149,9 @@ gc_wave_fused_kernel(const uint8_t *__restrict__ seq, const FusedTile *__restric
     __syncthreads();
 
     // ---- window counts by sliding over the block sums (thread t owns windows [8t, 8t+8)), then exact prefix sums of
-    //      c and c^2 over the tile
-    uint32_t c[FW_E + 1], q1[FW_E], q2[FW_E];   // q = exclusive prefix at element 8t + j
+    //      c and c^2 over the tile, kept for every fourth element
+    uint32_t c[FW_E + 1];
+    uint32_t q1, q2;                            // sums over the elements before 8t
     {
         const uint8_t *bt = bsum + FW_E * tid;
         if (R == 10) {
@@ -155,14 +175,8 @@ gc_wave_fused_kernel(const uint8_t *__restrict__ seq, const FusedTile *__restric
         }
         reinterpret_cast<uint4 *>(cw)[tid] = make_uint4(c[0] | (c[1] << 16), c[2] | (c[3] << 16), c[4] | (c[5] << 16), c[6] | (c[7] << 16));
         if (tid < 4) reinterpret_cast<uint32_t *>(cw + FW_MAX_EL)[tid] = 0u;
-        uint32_t a1 = 0, a2 = 0;
-#pragma unroll
-        for (int j = 0; j < FW_E; ++j) {
-            q1[j] = a1;
-            q2[j] = a2;
-            a1 += c[j];
-            a2 += c[j] * c[j];
-        }
+        const uint32_t h1 = c[0] + c[1] + c[2] + c[3], h2 = c[0] * c[0] + c[1] * c[1] + c[2] * c[2] + c[3] * c[3];
+        const uint32_t a1 = h1 + c[4] + c[5] + c[6] + c[7], a2 = h2 + c[4] * c[4] + c[5] * c[5] + c[6] * c[6] + c[7] * c[7];
         uint32_t s1 = a1, s2 = a2;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -170,80 +184,89 @@ gc_wave_fused_kernel(const uint8_t *__restrict__ seq, const FusedTile *__restric
             s2 = scan_step(s2, d);
         }
         if (lane == 31) { ws1[warp] = s1; ws2[warp] = s2; }
-        __syncthreads();   // also: every thread is done with WW and bsum, so P2 and sg may overwrite them
+        __syncthreads();   // also: every thread is done with bsum, so sg may overwrite it
         const uint32_t o1 = (lane < warp) ? ws1[lane & 7] : 0u, o2 = (lane < warp) ? ws2[lane & 7] : 0u;
-        const uint32_t b1 = s1 - a1 + __reduce_add_sync(0xFFFFFFFFu, o1), b2 = s2 - a2 + __reduce_add_sync(0xFFFFFFFFu, o2);
-#pragma unroll
-        for (int j = 0; j < FW_E; ++j) { q1[j] += b1; q2[j] += b2; }
-        reinterpret_cast<uint4 *>(P1 + FW_PAD)[2 * tid] = make_uint4(q1[0], q1[1], q1[2], q1[3]);
-        reinterpret_cast<uint4 *>(P1 + FW_PAD)[2 * tid + 1] = make_uint4(q1[4], q1[5], q1[6], q1[7]);
-        reinterpret_cast<uint4 *>(P2 + FW_PAD)[2 * tid] = make_uint4(q2[0], q2[1], q2[2], q2[3]);
-        reinterpret_cast<uint4 *>(P2 + FW_PAD)[2 * tid + 1] = make_uint4(q2[4], q2[5], q2[6], q2[7]);
-        if (tid == 0) *reinterpret_cast<uint2 *>(sg) = make_uint2(0u, 0u);   // sg[7] = element 0: never a signal
+        q1 = s1 - a1 + __reduce_add_sync(0xFFFFFFFFu, o1);
+        q2 = s2 - a2 + __reduce_add_sync(0xFFFFFFFFu, o2);
+        reinterpret_cast<uint4 *>(Pq + FW_PAD / 4)[tid] = make_uint4(q1, q2, q1 + h1, q2 + h2);
     }
     __syncthreads();
 
-    // ---- GC fractions out (thread-strided: coalesced); loads are unconditional, only the stores are predicated
+    // ---- GC fractions of elements 8t+1 .. 8t+8: 32 aligned bytes per thread
+    const uint32_t e0 = FW_E * tid + 1;
+    const bool whole = e0 >= e_out0 && e0 + FW_E <= e_out1;         // all eight elements are outputs of this tile
+    c[FW_E] = cw[FW_E * tid + FW_E];
     {
-        float *__restrict__ out = gc_out + (td.out0 - hh) + tid;
-        uint32_t *__restrict__ outc = WRITE_CNT ? cnt_out + (td.out0 - hh) + tid : nullptr;
-        const uint16_t *cwt = cw + tid;
+        float g[FW_E];
         if (use_stab) {
 #pragma unroll
-            for (int j = 0; j < FW_E; ++j) {
-                const uint32_t cnt = cwt[j * GC_THREADS];
-                const float g = stab[cnt & (FW_STAB - 1)];
-                if ((uint32_t)(j * GC_THREADS + tid) - hh < nw) {
-                    out[j * GC_THREADS] = g;
-                    if (WRITE_CNT) outc[j * GC_THREADS] = cnt;
-                }
+            for (int j = 0; j < FW_E; ++j) g[j] = stab[c[j + 1] & (FW_STAB - 1)];
+        } else {
+#pragma unroll
+            for (int j = 0; j < FW_E; ++j) g[j] = __ldg(gc_tab + min(c[j + 1], (uint32_t)size));
+        }
+        float *__restrict__ out = gc_out + (td.g0 + (int64_t)e0);
+        uint32_t *__restrict__ outc = WRITE_CNT ? cnt_out + (td.g0 + (int64_t)e0) : nullptr;
+        if (whole) {
+            reinterpret_cast<float4 *>(out)[0] = make_float4(g[0], g[1], g[2], g[3]);
+            reinterpret_cast<float4 *>(out)[1] = make_float4(g[4], g[5], g[6], g[7]);
+            if (WRITE_CNT) {
+                reinterpret_cast<uint4 *>(outc)[0] = make_uint4(c[1], c[2], c[3], c[4]);
+                reinterpret_cast<uint4 *>(outc)[1] = make_uint4(c[5], c[6], c[7], c[8]);
             }
         } else {
 #pragma unroll
-            for (int j = 0; j < FW_E; ++j) {
-                const uint32_t cnt = cwt[j * GC_THREADS];
-                if ((uint32_t)(j * GC_THREADS + tid) - hh < nw) {
-                    out[j * GC_THREADS] = __ldg(gc_tab + cnt);
-                    if (WRITE_CNT) outc[j * GC_THREADS] = cnt;
+            for (int j = 0; j < FW_E; ++j)
+                if (e0 + j >= e_out0 && e0 + j < e_out1) {
+                    out[j] = g[j];
+                    if (WRITE_CNT) outc[j] = c[j + 1];
                 }
-            }
         }
     }
 
-    // ---- certificate: thread t decides elements e = 8t+1 .. 8t+8; the stats window of e is [e-lag-1, e-1), so its
-    //      sums are P[e-1] - P[e-1-lag] = (own q[j]) - (P lag elements back)
-    const bool first = (hh == 0u);
-    const uint32_t e_lo = h;                    // first element that can signal by the general formula (both tile kinds)
+    // ---- certificate: thread t decides elements e = 8t+1 .. 8t+8.  The stats window of e is [e-lag-1, e-1): for
+    //      e = 8t+1 its sums are (sums before 8t) - (sums before 8t-lag), and they slide by one count in, one out.
+    const int e_sp = td.e_ctg0 + lag;           // the ctg's window `lag` (only in a ctg's first tile; else far negative)
+    const uint32_t e_lo = (uint32_t)max((int)e_out0, e_sp + 1);   // first element that can signal by the general formula
     {
-        c[FW_E] = cw[FW_E * tid + FW_E];
-        uint32_t p1b[FW_E], p2b[FW_E];
-        const int back = FW_PAD + FW_E * tid - lag;   // >= 0 since FW_PAD >= lag
+        const int i0 = FW_E * tid - lag;        // first element of the first stats window; >= -FW_PAD
+        uint32_t cb[FW_E];                      // counts leaving the stats window: c[i0 + j]
+        uint32_t s1, s2;
         if (LAG4) {
-            const uint4 u0 = *reinterpret_cast<const uint4 *>(P1 + back), u1 = *reinterpret_cast<const uint4 *>(P1 + back + 4);
-            p1b[0] = u0.x; p1b[1] = u0.y; p1b[2] = u0.z; p1b[3] = u0.w;
-            p1b[4] = u1.x; p1b[5] = u1.y; p1b[6] = u1.z; p1b[7] = u1.w;
-            const uint4 v0 = *reinterpret_cast<const uint4 *>(P2 + back), v1 = *reinterpret_cast<const uint4 *>(P2 + back + 4);
-            p2b[0] = v0.x; p2b[1] = v0.y; p2b[2] = v0.z; p2b[3] = v0.w;
-            p2b[4] = v1.x; p2b[5] = v1.y; p2b[6] = v1.z; p2b[7] = v1.w;
+            const uint2 u0 = *reinterpret_cast<const uint2 *>(cw + i0), u1 = *reinterpret_cast<const uint2 *>(cw + i0 + 4);
+            cb[0] = u0.x & 0xFFFFu; cb[1] = u0.x >> 16; cb[2] = u0.y & 0xFFFFu; cb[3] = u0.y >> 16;
+            cb[4] = u1.x & 0xFFFFu; cb[5] = u1.x >> 16; cb[6] = u1.y & 0xFFFFu; cb[7] = u1.y >> 16;
+            const uint2 pb = Pq[(FW_PAD + i0) >> 2];
+            s1 = q1 - pb.x;
+            s2 = q2 - pb.y;
         } else {
 #pragma unroll
-            for (int j = 0; j < FW_E; ++j) { p1b[j] = P1[back + j]; p2b[j] = P2[back + j]; }
+            for (int j = 0; j < FW_E; ++j) cb[j] = cw[i0 + j];
+            const int m4 = (FW_PAD + i0) >> 2, rho = (FW_PAD + i0) & 3;   // rho is the same for every thread
+            uint2 pb = Pq[m4];
+            for (int k = 0; k < rho; ++k) {
+                const uint32_t x = cw[4 * m4 - FW_PAD + k];
+                pb.x += x;
+                pb.y += x * x;
+            }
+            s1 = q1 - pb.x;
+            s2 = q2 - pb.y;
         }
         uint32_t pk0 = 0u, pk1 = 0u;
 #pragma unroll
         for (int j = 0; j < FW_E; ++j) {
-            const uint32_t s1 = q1[j] - p1b[j], s2 = q2[j] - p2b[j];
             const int D = (int)(c[j + 1] * (uint32_t)lag) - (int)s1;
             const uint32_t V = s2 * (uint32_t)lag - s1 * s1;
             const uint32_t dec = fused_certify(D, V, fc);
             if (j < 4) pk0 = dec * (1u << (8 * (j & 3))) + pk0;
             else pk1 = dec * (1u << (8 * (j & 3))) + pk1;
+            s1 += c[j] - cb[j];
+            s2 += c[j] * c[j] - cb[j] * cb[j];
         }
-        const uint32_t e0 = FW_E * tid + 1;
-        if (e0 < e_lo || e0 + FW_E > n_el) {   // edge threads: elements that cannot signal (before `lag`) or do not exist
+        if (e0 < e_lo || e0 + FW_E > e_out1) {   // edge threads: elements that cannot signal (before `lag`) or do not exist
 #pragma unroll
             for (int j = 0; j < FW_E; ++j)
-                if (e0 + j < e_lo || e0 + j >= n_el) {
+                if (e0 + j < e_lo || e0 + j >= e_out1) {
                     if (j < 4) pk0 &= ~(0xFFu << (8 * (j & 3)));
                     else pk1 &= ~(0xFFu << (8 * (j & 3)));
                 }
@@ -257,36 +280,38 @@ gc_wave_fused_kernel(const uint8_t *__restrict__ seq, const FusedTile *__restric
                     if (slot < FUSED_LIST_CAP) list[slot] = (int)(e0 + j);
                 }
         }
-        *reinterpret_cast<uint2 *>(sg + 8 + FW_E * tid) = make_uint2(pk0, pk1);
+        *reinterpret_cast<uint2 *>(sg + FW_E * tid) = make_uint2(pk0, pk1);
     }
     __syncthreads();
 
     // ---- exact replay of inconclusive windows (rare): x_k = gc_tab[c_k] are the f32 values the reference sums
     const int n_list = list_n;  // block-uniform
-    if (n_list > 0 || first) {
+    if (n_list > 0 || e_sp >= 0) {
         const float flag = __ull2float_rn((unsigned long long)lag);
         const float flagm1 = __fsub_rn(flag, 1.0f);
         auto ld = [&](int64_t e) { return __ldg(gc_tab + cw[e]); };
-        if (first && tid == 0 && n_el > (uint32_t)lag) {
+        if (e_sp >= 0 && tid == 0 && (uint32_t)e_sp < e_out1) {
             // window `lag` of the ctg takes its statistics from windows [0, lag) (stat.rs:30-31), not [lag-1-lag, lag-1)
-            sg[lag + 7] = (uint8_t)zscore_decide(ld, 0, (uint64_t)lag, flag, flagm1, ld(lag), threshold);
+            sg[e_sp - 1] = (uint8_t)zscore_decide(ld, (int64_t)td.e_ctg0, (uint64_t)lag, flag, flagm1, ld(e_sp), threshold);
         }
-        const int n_todo = (n_list <= FUSED_LIST_CAP) ? n_list : (int)n_el;  // overflow: replay the whole tile
+        const int n_todo = (n_list <= FUSED_LIST_CAP) ? n_list : (int)e_out1;  // overflow: replay the whole tile
         for (int t = tid; t < n_todo; t += GC_THREADS) {
             const uint32_t e = (n_list <= FUSED_LIST_CAP) ? (uint32_t)list[t] : (uint32_t)t;
-            if (e < e_lo || e >= n_el) continue;
-            sg[e + 7] = (uint8_t)zscore_decide(ld, (int64_t)e - (int64_t)h, (uint64_t)lag, flag, flagm1, ld(e), threshold);
+            if (e < e_lo || e >= e_out1) continue;
+            sg[e - 1] = (uint8_t)zscore_decide(ld, (int64_t)e - 1 - (int64_t)lag, (uint64_t)lag, flag, flagm1, ld(e), threshold);
         }
         if (stats && tid == 0 && n_list) atomicAdd(&stats[0], (unsigned long long)n_list);
         __syncthreads();
     }
+    // ---- signals of elements 8t+1 .. 8t+8: one aligned 64-bit store per thread
     {
-        int8_t *__restrict__ so = sig_out + td.out0 + tid;
-        const uint8_t *sgo = sg + 7 + hh + tid;
+        int8_t *__restrict__ so = sig_out + (td.g0 + (int64_t)e0);
+        const uint2 pk = *reinterpret_cast<const uint2 *>(sg + FW_E * tid);
+        if (whole) *reinterpret_cast<uint2 *>(so) = pk;
+        else {
 #pragma unroll
-        for (int j = 0; j < FW_E; ++j) {
-            const int8_t v = (int8_t)sgo[j * GC_THREADS];
-            if ((uint32_t)(j * GC_THREADS + tid) < nw) so[j * GC_THREADS] = v;
+            for (int j = 0; j < FW_E; ++j)
+                if (e0 + j >= e_out0 && e0 + j < e_out1) so[j] = (int8_t)(((j < 4) ? pk.x : pk.y) >> (8 * (j & 3)));
         }
     }
 }
@@ -344,7 +369,7 @@ bool wave_fused_ok(const gams_cuda_wave_plan *p, float threshold, float influenc
            p->win.min_len >= p->lag;
 }
 
-// Windows per fused tile, or 0 when the fused path does not apply to this geometry.
+// Output windows per fused tile, or 0 when the fused path does not apply to this geometry.
 int fused_windows_per_tile(int32_t size, int32_t step, uint64_t lag) {
     if (step > 16 || size % step != 0 || size / step > FW_MAX_R) return 0;   // a block's bits come from one 32-bit word
     if (lag < 2 || lag > FW_MAX_LAG) return 0;
@@ -353,9 +378,31 @@ int fused_windows_per_tile(int32_t size, int32_t step, uint64_t lag) {
     if (size > span_cap) return 0;
     const int64_t h = (int64_t)lag + 1;
     const int64_t n_el = std::min<int64_t>((span_cap - size) / step + 1, FW_MAX_EL);
-    const int64_t wt = n_el - h;
+    const int64_t wt = ((n_el - h - 7) / 8) * 8;             // up to 7 alignment elements before the halo
     if (wt < 4 * h || wt < 64) return 0;                     // halo re-read would exceed 25 %
     return (int)wt;
+}
+
+// Tiles of one ctg (see the layout comment at the kernel).  seq_off / win_off: the ctg's first byte / window in the
+// device arrays; n_c windows.
+void fused_tiles_for_ctg(std::vector<FusedTile> &out, uint64_t seq_off, uint64_t win_off, uint64_t n_c, int32_t step,
+                         uint64_t lag, int wt) {
+    const int64_t h = (int64_t)lag + 1;
+    for (uint64_t w = 0; w < n_c; w += (uint64_t)wt) {
+        FusedTile t{};
+        const int64_t g_first = (int64_t)(win_off + w);            // first output window, global index
+        const int64_t need = w ? h : 1;                            // elements wanted before it
+        int64_t g0 = g_first - need;
+        g0 -= ((g0 % 8) + 8 + 1) % 8;                              // largest g0' <= g0 with g0' = 7 (mod 8)
+        t.g0 = g0;
+        t.e_out0 = (uint32_t)(g_first - g0);
+        t.e_out1 = t.e_out0 + (uint32_t)std::min<uint64_t>((uint64_t)wt, n_c - w);
+        t.e_ctg0 = w ? -(1 << 30) : (int32_t)t.e_out0;
+        t.byte0 = (int64_t)seq_off + ((int64_t)w - (int64_t)t.e_out0) * (int64_t)step;
+        const int64_t base = t.byte0 - (t.byte0 & 31);             // 32-byte aligned (also for negative byte0)
+        t.pi_min = base < 0 ? (uint32_t)((-base + 31) / 32) : 0u;  // pieces before the start of the sequence buffer
+        out.push_back(t);
+    }
 }
 
 int32_t launch_gc_wave_fused(gams_cuda_wave_plan *p, cudaStream_t st, const uint8_t *d_seq, float threshold,

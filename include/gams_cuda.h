@@ -129,7 +129,8 @@ int32_t gams_cuda_wave_signal_dev(gams_cuda_wave_plan *plan, void *stream, const
  * With the default statistics (influence == 1, threshold >= 0) and size % step == 0 this is ONE fused kernel
  * (gc_wave_fused.cu) that decides the signals from exact integer window counts while the tile is still in
  * shared memory; otherwise it enqueues gams_cuda_wave_gc_dev + gams_cuda_wave_signal_dev.  Results are
- * identical either way.  d_filtered as for gams_cuda_wave_signal_dev.  GAMS_CUDA_ELAG as for wave_batch. */
+ * identical either way.  d_filtered as for gams_cuda_wave_signal_dev.  GAMS_CUDA_ELAG as for wave_batch.
+ * (The fused kernel needs d_gc / d_gc_count 16-byte and d_signal 8-byte aligned; other pointers take the two kernels.) */
 int32_t gams_cuda_wave_dev(gams_cuda_wave_plan *plan, void *stream, const uint8_t *d_seq, float threshold,
                            float influence, uint32_t *d_gc_count, float *d_gc, float *d_filtered,
                            int8_t *d_signal);
