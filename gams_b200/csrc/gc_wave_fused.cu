@@ -56,10 +56,18 @@ __device__ __forceinline__ uint32_t fused_certify(int D, uint32_t V, const Fused
 
 // GC bit of each of the 32 bytes in v (bit i <=> byte i is one of C G c g): the four flags of a word are gathered
 // into the top nibble by one multiply (gc_gather) and shifted into the mask by one funnel shift.
-__device__ __forceinline__ uint32_t gc_mask32(const Bytes32 &v) {
-    uint32_t m = gc_gather(v.w[7]) >> 28;
+// `one` is the constant 1 passed as a kernel argument: t * one + 0x7F.. keeps that add on the FMA pipe (IMAD), which
+// idles here, instead of the ALU pipe, which is the busiest unit of this kernel.
+__device__ __forceinline__ uint32_t gc_gather_fma(uint32_t w, uint32_t one) {
+    const uint32_t t = lop3<0x6A>(w, 0x5B5B5B5Bu, 0x43434343u);
+    const uint32_t a = t * one + 0x7F7F7F7Fu;
+    const uint32_t g7 = lop3<0x02>(a, w, 0x80808080u);
+    return g7 * 0x00204081u;
+}
+__device__ __forceinline__ uint32_t gc_mask32(const Bytes32 &v, uint32_t one) {
+    uint32_t m = gc_gather_fma(v.w[7], one) >> 28;
 #pragma unroll
-    for (int q = 6; q >= 0; --q) m = __funnelshift_l(gc_gather(v.w[q]), m, 4);
+    for (int q = 6; q >= 0; --q) m = __funnelshift_l(gc_gather_fma(v.w[q], one), m, 4);
     return m;
 }
 
@@ -75,7 +83,7 @@ template <bool WRITE_CNT, bool LAG4, int R>
 __global__ void __launch_bounds__(GC_THREADS, FW_MIN_CTAS)
 gc_wave_fused_kernel(const uint8_t *__restrict__ seq, const FusedTile *__restrict__ tiles,
                      const float *__restrict__ gc_tab, int size, int step, int r_rt, int lag, float threshold,
-                     const FusedConst fc, uint32_t *__restrict__ cnt_out, float *__restrict__ gc_out,
+                     uint32_t one, const FusedConst fc, uint32_t *__restrict__ cnt_out, float *__restrict__ gc_out,
                      int8_t *__restrict__ sig_out, unsigned long long *__restrict__ stats) {
     // WW[i] = GC bits of bytes [16 i, 16 i + 32) of the tile's span (consecutive words overlap by 16 bits so that a
     // block of <= 16 bases always comes out of one word)
@@ -123,7 +131,7 @@ gc_wave_fused_kernel(const uint8_t *__restrict__ seq, const FusedTile *__restric
         for (int j = 0; j < FW_K / 2; ++j) {
             const uint32_t pi = j * GC_THREADS + tid;
             if (2u * (pi - lane) < nch) {                           // warp-uniform
-                const uint32_t m = gc_mask32(v[j]);
+                const uint32_t m = gc_mask32(v[j], one);
                 const uint32_t nx = __shfl_down_sync(0xFFFFFFFFu, m, 1);
                 if (lane != 31) *reinterpret_cast<uint2 *>(WW + 2 * pi) = make_uint2(m, __funnelshift_r(m, nx, 16));
                 else {
@@ -140,11 +148,13 @@ gc_wave_fused_kernel(const uint8_t *__restrict__ seq, const FusedTile *__restric
     //      the tile's last boundary read stale (in-bounds) words and are never used.
     {
         const uint32_t smask = (1u << step) - 1u;                   // step <= 16
-        uint32_t p = lead + (uint32_t)tid * (uint32_t)step;
-        const uint32_t dp = (uint32_t)GC_THREADS * (uint32_t)step;
+        const uint32_t p0 = lead + (uint32_t)tid * (uint32_t)step;
+        const uint32_t sh = p0 & 15u;                               // 256 * step is a multiple of 16: the same for every j
+        const uint32_t *wp = WW + (p0 >> 4);
+        const uint32_t dw = 16u * (uint32_t)step;                   // words between blocks m and m + 256
 #pragma unroll
-        for (int j = 0; j < FW_NBLK / GC_THREADS; ++j, p += dp)
-            bsum[j * GC_THREADS + tid] = (uint8_t)__popc((WW[p >> 4] >> (p & 15u)) & smask);
+        for (int j = 0; j < FW_NBLK / GC_THREADS; ++j, wp += dw)
+            bsum[j * GC_THREADS + tid] = (uint8_t)__popc((*wp >> sh) & smask);
     }
     __syncthreads();
 
@@ -231,14 +241,14 @@ gc_wave_fused_kernel(const uint8_t *__restrict__ seq, const FusedTile *__restric
     {
         const int i0 = FW_E * tid - lag;        // first element of the first stats window; >= -FW_PAD
         uint32_t cb[FW_E];                      // counts leaving the stats window: c[i0 + j]
-        uint32_t s1, s2;
+        uint32_t s1 = q1, s2 = q2;
         if (LAG4) {
             const uint2 u0 = *reinterpret_cast<const uint2 *>(cw + i0), u1 = *reinterpret_cast<const uint2 *>(cw + i0 + 4);
             cb[0] = u0.x & 0xFFFFu; cb[1] = u0.x >> 16; cb[2] = u0.y & 0xFFFFu; cb[3] = u0.y >> 16;
             cb[4] = u1.x & 0xFFFFu; cb[5] = u1.x >> 16; cb[6] = u1.y & 0xFFFFu; cb[7] = u1.y >> 16;
             const uint2 pb = Pq[(FW_PAD + i0) >> 2];
-            s1 = q1 - pb.x;
-            s2 = q2 - pb.y;
+            s1 -= pb.x;
+            s2 -= pb.y;
         } else {
 #pragma unroll
             for (int j = 0; j < FW_E; ++j) cb[j] = cw[i0 + j];
@@ -249,8 +259,8 @@ gc_wave_fused_kernel(const uint8_t *__restrict__ seq, const FusedTile *__restric
                 pb.x += x;
                 pb.y += x * x;
             }
-            s1 = q1 - pb.x;
-            s2 = q2 - pb.y;
+            s1 -= pb.x;
+            s2 -= pb.y;
         }
         uint32_t pk0 = 0u, pk1 = 0u;
 #pragma unroll
@@ -420,7 +430,7 @@ int32_t launch_gc_wave_fused(gams_cuda_wave_plan *p, cudaStream_t st, const uint
     const int r = p->size / p->step;
 #define GAMS_FUSED_LAUNCH(WC, L4, RR)                                                                                   \
     gc_wave_fused_kernel<WC, L4, RR><<<grid, GC_THREADS, 0, st>>>(d_seq, tiles, p->d_gc_tab, p->size, p->step, r,      \
-                                                                  (int)p->lag, threshold, fc, d_cnt, d_gc, d_sig, d_stats)
+                                                                  (int)p->lag, threshold, 1u, fc, d_cnt, d_gc, d_sig, d_stats)
 #define GAMS_FUSED_LAUNCH_R(WC, L4)                                                                                     \
     do {                                                                                                               \
         if (r == 10) GAMS_FUSED_LAUNCH(WC, L4, 10); else GAMS_FUSED_LAUNCH(WC, L4, 0);                                 \
