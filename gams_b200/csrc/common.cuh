@@ -168,6 +168,10 @@ struct gams_cuda_count_plan {
     gams::DevBuf tmp[6];             // [0] SegRank per segment, [1]/[2] rank tables of starts[] / stops[]
     const uint32_t *idx_starts = nullptr, *idx_stops = nullptr;  // arrays the rank tables were built for
     bool idx_valid = false;
+    // compact per-segment index of the staged kernel (queries grouped by segment): tmp[4] = offsets + parameters, tmp[5] = data
+    const uint32_t *cidx_starts = nullptr, *cidx_stops = nullptr;
+    bool cidx_valid = false;
+    size_t cpar_off = 0;
     int mode = 0;                    // 0 ranked (default), 1 plain binary search (GAMS_CUDA_COUNT_MODE)
     uint64_t launches = 0;
 };
@@ -185,6 +189,7 @@ int32_t launch_count_overlaps(gams_cuda_count_plan *p, cudaStream_t st, const ui
                               const uint32_t *d_q_start, const uint32_t *d_q_stop, int32_t grouped,
                               uint32_t *d_out);
 int32_t build_count_index(gams_cuda_count_plan *p, cudaStream_t st, const uint32_t *d_starts, const uint32_t *d_stops);
+int32_t build_compact_index(gams_cuda_count_plan *p, cudaStream_t st, const uint32_t *d_starts, const uint32_t *d_stops);
 int32_t launch_locate_ctg(cudaStream_t st, int64_t n_chr, const uint32_t *d_ctg_start, const uint32_t *d_ctg_stop,
                           const uint64_t *d_chr_off, const uint32_t *d_chr_maxlen, int64_t n_q,
                           const int32_t *d_q_chr, const uint32_t *d_q_start, const uint32_t *d_q_stop, int32_t *d_out);

@@ -166,6 +166,216 @@ count_overlaps_ranked_kernel(const uint32_t *__restrict__ starts, const uint32_t
     }
 }
 
+// ---- staged kernel: queries grouped by segment ------------------------------------------------------
+// When the caller promises q_seg is non-decreasing (grouped != 0: the order the reference processes ranges in,
+// per ctg out of read_range's BTreeMap, locate.rs:104-141) every probe becomes a shared-memory access.  Each
+// sorted endpoint array of each segment has a COMPACT form, built once per index (build_compact_kernel):
+//   cum2[b] (u32) = cum[b] | cum[b+1] << 16,  cum[b] = #elements < lo + (b << l),   b = 0 .. nb-1 (width 2^l, l <= 7)
+//   low[i]  (u8)  = (a[i] - lo) & (2^l - 1),                                         i = 0 .. n-1
+//   lower_bound(key) = cum[b] + #{ i in [cum[b], cum[b+1]) : low[i] < rem },  b = (key - lo) >> l, rem = (key - lo) & (2^l - 1)
+// about 4 B per bucket + 1 B per element (~3 B per interval endpoint instead of 4 B raw): a 16 K-interval ctg is
+// 94 KB for both arrays, so two CTAs per SM each hold one segment.  A work item is (segment, chunk of <= ST_CHUNK of
+// its queries): the CTA copies the segment's compact form into shared memory (coalesced 16-byte loads) and answers
+// its queries with one cum2 word and an 8-byte window of low[] per endpoint, compared SIMD-in-register.
+// DRAM traffic: the query stream once + ~6 B per interval (neighbouring chunks of a segment hit L2).
+// Arrays that do not fit the form (l > 7, n > ST_MAX_N) are binary-searched in global memory by the same CTA.
+constexpr int ST_THREADS = 512;
+constexpr int ST_NB = 8192;          // buckets per endpoint array
+constexpr int ST_MAX_N = 24576;      // elements per endpoint array
+constexpr int ST_CHUNK = 16384;      // queries per work item
+constexpr uint32_t ST_PLAIN = 0xFFu;
+constexpr size_t ST_ARR_BYTES = 4 * (ST_NB + 4) + ST_MAX_N + 32;
+constexpr size_t ST_SMEM = 2 * ST_ARR_BYTES;
+
+struct alignas(16) SegCompact {      // one per (segment, endpoint array)
+    uint32_t lo, hi, n, l;           // l == ST_PLAIN: no compact form
+    uint32_t nb;                     // buckets
+    uint32_t low_off;                // byte offset of low[] behind cum2[] (multiple of 16)
+    uint32_t bytes;                  // bytes of the compact form (multiple of 16)
+    uint32_t pad;
+};
+
+// bucket budget of an array of n elements (host and device agree on it: the host sizes the buffer with it)
+__host__ __device__ __forceinline__ uint32_t st_nb_cap(uint32_t n) {
+    return n < 64u ? 64u : (n > (uint32_t)ST_NB ? (uint32_t)ST_NB : n);
+}
+__host__ __device__ __forceinline__ uint64_t st_arr_cap_bytes(uint32_t n) {   // upper bound of SegCompact::bytes
+    if (n == 0 || n > (uint32_t)ST_MAX_N) return 0;
+    return ((4ull * (st_nb_cap(n) + 1) + 15) & ~15ull) + (((uint64_t)n + 16 + 15) & ~15ull);
+}
+
+// one CTA per segment: parameters and compact form of both endpoint arrays
+__global__ void __launch_bounds__(256)
+build_compact_kernel(const uint32_t *__restrict__ starts, const uint32_t *__restrict__ stops,
+                     const uint64_t *__restrict__ iv_off, int64_t n_seg, const uint64_t *__restrict__ cofs,
+                     SegCompact *__restrict__ par, uint8_t *__restrict__ buf) {
+    for (int64_t s = blockIdx.x; s < n_seg; s += gridDim.x) {
+        const uint64_t off = iv_off[s];
+        const uint32_t n = (uint32_t)min((uint64_t)0xFFFFFFFFu, iv_off[s + 1] - off);
+        for (int which = 0; which < 2; ++which) {
+            const uint32_t *a = (which ? stops : starts) + off;
+            SegCompact p;
+            p.n = n;
+            p.lo = n ? a[0] : 0u;
+            p.hi = n ? a[n - 1] : 0u;
+            p.pad = 0;
+            const uint32_t range = p.hi - p.lo, cap = st_nb_cap(n);
+            uint32_t l = 0;
+            while (l < 32u && (range >> l) + 1u > cap) ++l;
+            const bool ok = n > 0 && n <= (uint32_t)ST_MAX_N && l <= 7;
+            p.l = ok ? l : ST_PLAIN;
+            p.nb = ok ? (range >> l) + 1u : 0u;
+            p.low_off = ok ? ((4u * (p.nb + 1u) + 15u) & ~15u) : 0u;
+            p.bytes = ok ? p.low_off + ((n + 16u + 15u) & ~15u) : 0u;
+            if (threadIdx.x == 0) par[2 * s + which] = p;
+            if (!ok) continue;
+            uint8_t *base = buf + cofs[s] + (which ? st_arr_cap_bytes(n) : 0);
+            uint16_t *cum16 = reinterpret_cast<uint16_t *>(base);     // cum[b] lives in halves 2b and 2b-1
+            uint8_t *low = base + p.low_off;
+            const uint32_t mask = (1u << l) - 1u;
+            for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+                const uint32_t d = a[i] - p.lo, b = d >> l;
+                low[i] = (uint8_t)(d & mask);
+                const uint32_t pb = i ? ((a[i - 1] - p.lo) >> l) + 1u : 0u;   // buckets (b_prev, b] start at element i
+                for (uint32_t bb = pb; bb <= b; ++bb) {
+                    cum16[2 * bb] = (uint16_t)i;
+                    if (bb) cum16[2 * bb - 1] = (uint16_t)i;
+                }
+                if (i == n - 1) {                                             // b == nb - 1: cum[nb] = n
+                    cum16[2 * p.nb - 1] = (uint16_t)n;
+                    cum16[2 * p.nb] = (uint16_t)n;
+                    cum16[2 * p.nb + 1] = (uint16_t)n;
+                }
+            }
+            for (uint32_t i = n + threadIdx.x; i < ((n + 16u + 15u) & ~15u); i += blockDim.x) low[i] = 0xFFu;  // never < rem
+        }
+    }
+}
+
+// first query of every segment in the grouped stream: qoff[s] = #queries with q_seg < s, s = 0 .. n_seg
+__global__ void __launch_bounds__(256)
+seg_query_bounds_kernel(const int32_t *__restrict__ q_seg, int64_t n_q, int64_t n_seg, int64_t *__restrict__ qoff) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q <= n_q; q += stride) {
+        const int64_t prev = q ? min((int64_t)max(q_seg[q - 1], -1), n_seg) : -1;
+        const int64_t cur = q < n_q ? min((int64_t)max(q_seg[q], -1), n_seg) : n_seg;
+        for (int64_t s = prev + 1; s <= cur; ++s) qoff[s] = q;
+    }
+}
+
+// work items: segment s is cut into ceil(nq_s / ST_CHUNK) items; ioff[s] = first item of segment s (one CTA scans)
+__global__ void __launch_bounds__(1024)
+seg_items_kernel(const int64_t *__restrict__ qoff, int64_t n_seg, int64_t *__restrict__ ioff) {
+    __shared__ int64_t wsum[32];
+    __shared__ int64_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < n_seg; base += 1024) {
+        const int64_t s = base + threadIdx.x;
+        int64_t v = s < n_seg ? (qoff[s + 1] - qoff[s] + ST_CHUNK - 1) / ST_CHUNK : 0, inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int64_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+            if ((threadIdx.x & 31) >= d) inc += t;
+        }
+        if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = inc;
+        __syncthreads();
+        int64_t before = carry;
+        for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) before += wsum[w];
+        if (s < n_seg) ioff[s] = before + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = before + inc;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) ioff[n_seg] = carry;
+}
+
+// #elements < key of one endpoint array: compact form in shared memory (sm), or the raw array `a` in global memory
+__device__ __forceinline__ uint32_t staged_lower_bound(const SegCompact &P, const uint32_t *__restrict__ a, const uint8_t *sm,
+                                                       uint32_t key) {
+    if (P.n == 0 || key <= P.lo) return 0;
+    if (key > P.hi) return P.n;
+    if (P.l == ST_PLAIN) return lower_bound_u32(a, P.n, key);
+    const uint32_t d = key - P.lo, b = d >> P.l, rem = d & ((1u << P.l) - 1u);
+    const uint32_t w = reinterpret_cast<const uint32_t *>(sm)[b];
+    const uint32_t c0 = w & 0xFFFFu, m = (w >> 16) - c0;                 // the bucket's elements are low[c0 .. c0 + m)
+    const uint8_t *low = sm + P.low_off;
+    if (m > 8u) {                                                         // rare: a crowded bucket
+        uint32_t cnt = c0;
+        for (uint32_t i = 0; i < m; ++i) cnt += (low[c0 + i] < rem) ? 1u : 0u;
+        return cnt;
+    }
+    // 8-byte window of low[] at c0 out of three aligned words; byte < rem <=> bit 7 of (byte | 0x80) - rem is clear
+    const uint32_t *lw = reinterpret_cast<const uint32_t *>(low) + (c0 >> 2);
+    const uint32_t x0 = lw[0], x1 = lw[1], x2 = lw[2], sh = (c0 & 3u) * 8u;
+    const uint32_t y0 = __funnelshift_r(x0, x1, sh), y1 = __funnelshift_r(x1, x2, sh);
+    const uint32_t rr = rem * 0x01010101u;
+    const uint32_t lt0 = ~((y0 | 0x80808080u) - rr) & 0x80808080u, lt1 = ~((y1 | 0x80808080u) - rr) & 0x80808080u;
+    // keep the first m bytes of the window
+    const uint32_t k0 = m >= 4u ? 0xFFFFFFFFu : ((1u << (8u * m)) - 1u);
+    const uint32_t k1 = m <= 4u ? 0u : (m >= 8u ? 0xFFFFFFFFu : ((1u << (8u * (m - 4u))) - 1u));
+    return c0 + (uint32_t)__popc(lt0 & k0) + (uint32_t)__popc(lt1 & k1);
+}
+
+__global__ void __launch_bounds__(ST_THREADS, 2)
+count_overlaps_staged_kernel(const uint32_t *__restrict__ starts, const uint32_t *__restrict__ stops,
+                             const uint64_t *__restrict__ iv_off, int64_t n_seg, int64_t n_q,
+                             const int64_t *__restrict__ qoff, const int64_t *__restrict__ ioff,
+                             const SegCompact *__restrict__ par, const uint64_t *__restrict__ cofs,
+                             const uint8_t *__restrict__ cbuf, const uint32_t *__restrict__ q_start,
+                             const uint32_t *__restrict__ q_stop, uint32_t *__restrict__ out) {
+    extern __shared__ __align__(16) uint8_t st_smem[];
+    const int64_t n_items = ioff[n_seg];
+    const int64_t item = blockIdx.x;
+    if (item >= n_items) {
+        // the CTAs past the last item zero the results of queries outside every segment (utils.rs:29-32: count 0)
+        const int64_t v_lo = qoff[0], v_hi = qoff[n_seg], n_bad = v_lo + (n_q - v_hi);
+        const int64_t stride = (int64_t)(gridDim.x - n_items) * ST_THREADS;
+        for (int64_t k = (item - n_items) * ST_THREADS + threadIdx.x; k < n_bad; k += stride) out[k < v_lo ? k : v_hi + (k - v_lo)] = 0u;
+        return;
+    }
+    int64_t lo = 0, hi = n_seg;   // last segment with ioff[s] <= item
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (ioff[mid] <= item) lo = mid; else hi = mid;
+    }
+    const int64_t s = lo;
+    const int64_t q0 = qoff[s] + (item - ioff[s]) * ST_CHUNK, q1 = min(q0 + (int64_t)ST_CHUNK, qoff[s + 1]);
+    const uint64_t off = iv_off[s];
+    SegCompact A = par[2 * s], B = par[2 * s + 1];
+    // staging copies A.bytes + B.bytes; a handful of queries is cheaper by plain binary search (2 * 14 probes each)
+    if ((uint64_t)(q1 - q0) * 64u < (uint64_t)A.bytes + B.bytes) A.l = B.l = ST_PLAIN;
+    uint8_t *smA = st_smem, *smB = st_smem + (A.l == ST_PLAIN ? 0u : A.bytes);
+    {
+        const uint8_t *gA = cbuf + cofs[s], *gB = gA + st_arr_cap_bytes(A.n);
+        if (A.l != ST_PLAIN)
+            for (uint32_t i = threadIdx.x * 16u; i < A.bytes; i += ST_THREADS * 16u)
+                *reinterpret_cast<uint4 *>(smA + i) = __ldg(reinterpret_cast<const uint4 *>(gA + i));
+        if (B.l != ST_PLAIN)
+            for (uint32_t i = threadIdx.x * 16u; i < B.bytes; i += ST_THREADS * 16u)
+                *reinterpret_cast<uint4 *>(smB + i) = __ldg(reinterpret_cast<const uint4 *>(gB + i));
+    }
+    __syncthreads();
+    constexpr int U = 4;
+    for (int64_t qb = q0 + threadIdx.x; qb < q1; qb += (int64_t)U * ST_THREADS) {
+        uint32_t qs[U], qe[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t q = qb + (int64_t)u * ST_THREADS;
+            if (q < q1) { qs[u] = q_start[q]; qe[u] = q_stop[q]; }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t q = qb + (int64_t)u * ST_THREADS;
+            if (q < q1) {
+                const uint32_t last = staged_lower_bound(A, starts + off, smA, qe[u]);
+                const uint32_t first = staged_lower_bound(B, stops + off, smB, qs[u] + 1u);
+                out[q] = last - first;
+            }
+        }
+    }
+}
+
 // v1 (kept for A/B measurements, GAMS_CUDA_COUNT_MODE=1): one thread per query, two binary searches.
 __global__ void __launch_bounds__(256)
 count_overlaps_direct_kernel(const uint32_t *__restrict__ starts, const uint32_t *__restrict__ stops,
@@ -209,12 +419,70 @@ int32_t build_count_index(gams_cuda_count_plan *p, cudaStream_t st, const uint32
     return GAMS_CUDA_OK;
 }
 
+// Compact per-segment index of the staged kernel: offsets are sized on the host from the interval counts alone.
+int32_t build_compact_index(gams_cuda_count_plan *p, cudaStream_t st, const uint32_t *d_starts, const uint32_t *d_stops) {
+    std::vector<uint64_t> cofs((size_t)p->n_seg + 1, 0);
+    for (int64_t s = 0; s < p->n_seg; ++s) {
+        const uint64_t n = p->h_iv_off[s + 1] - p->h_iv_off[s];
+        cofs[s + 1] = cofs[s] + 2 * st_arr_cap_bytes((uint32_t)std::min<uint64_t>(n, 0xFFFFFFFFull));
+    }
+    p->cpar_off = (sizeof(uint64_t) * cofs.size() + 15) & ~(size_t)15;
+    int32_t rc;
+    if ((rc = p->tmp[4].reserve(p->cpar_off + sizeof(SegCompact) * 2 * (size_t)std::max<int64_t>(p->n_seg, 1)))) return rc;
+    if ((rc = p->tmp[5].reserve(std::max<uint64_t>(cofs.back(), 16)))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(p->tmp[4].p, cofs.data(), sizeof(uint64_t) * cofs.size(), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));   // cofs is a local
+    if (p->n_seg) {
+        const int64_t blocks = std::min<int64_t>(p->n_seg, 148 * 16);
+        build_compact_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_starts, d_stops, p->d_iv_off, p->n_seg, p->tmp[4].as<uint64_t>(),
+                                                               reinterpret_cast<SegCompact *>(p->tmp[4].as<uint8_t>() + p->cpar_off),
+                                                               p->tmp[5].as<uint8_t>());
+        ++p->launches;
+        CUDA_TRY(cudaGetLastError());
+    }
+    p->cidx_starts = d_starts;
+    p->cidx_stops = d_stops;
+    p->cidx_valid = true;
+    return GAMS_CUDA_OK;
+}
+
 int32_t launch_count_overlaps(gams_cuda_count_plan *p, cudaStream_t st, const uint32_t *d_starts,
                               const uint32_t *d_stops, int64_t n_q, const int32_t *d_q_seg,
                               const uint32_t *d_q_start, const uint32_t *d_q_stop, int32_t grouped,
                               uint32_t *d_out) {
-    (void)grouped;  // the ranked kernel needs no ordering; kept in the ABI as a promise callers may give
     if (n_q == 0) return GAMS_CUDA_OK;
+    if (grouped && p->mode == 0) {
+        // staged path: q_seg is non-decreasing; each segment's compact index is staged in shared memory
+        static bool attr_set = false;
+        if (!attr_set) {
+            CUDA_TRY(cudaFuncSetAttribute(count_overlaps_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM));
+            attr_set = true;
+        }
+        int32_t rc;
+        if (!p->cidx_valid || p->cidx_starts != d_starts || p->cidx_stops != d_stops) {
+            if ((rc = build_compact_index(p, st, d_starts, d_stops))) return rc;
+        }
+        if ((rc = p->tmp[3].reserve(sizeof(int64_t) * 2 * (size_t)(p->n_seg + 1)))) return rc;
+        int64_t *qoff = p->tmp[3].as<int64_t>(), *ioff = qoff + (p->n_seg + 1);
+        int64_t b0 = (n_q + 1 + 255) / 256;
+        if (b0 > 148 * 32) b0 = 148 * 32;
+        seg_query_bounds_kernel<<<(unsigned)b0, 256, 0, st>>>(d_q_seg, n_q, p->n_seg, qoff);
+        seg_items_kernel<<<1, 1024, 0, st>>>(qoff, p->n_seg, ioff);
+        // items <= n_q / ST_CHUNK + n_seg; the CTAs beyond the actual count zero the out-of-index queries
+        const int64_t grid = n_q / ST_CHUNK + p->n_seg + 8;
+        if (grid >= (1ll << 31)) {
+            set_error("count_overlaps: too many segments for one launch");
+            return GAMS_CUDA_EINVAL;
+        }
+        const uint64_t *d_cofs = p->tmp[4].as<uint64_t>();
+        const SegCompact *d_par = reinterpret_cast<const SegCompact *>(p->tmp[4].as<uint8_t>() + p->cpar_off);
+        count_overlaps_staged_kernel<<<(unsigned)grid, ST_THREADS, ST_SMEM, st>>>(d_starts, d_stops, p->d_iv_off, p->n_seg, n_q, qoff,
+                                                                                 ioff, d_par, d_cofs, p->tmp[5].as<uint8_t>(),
+                                                                                 d_q_start, d_q_stop, d_out);
+        p->launches += 3;
+        CUDA_TRY(cudaGetLastError());
+        return GAMS_CUDA_OK;
+    }
     int64_t blocks = (n_q + 255) / 256;
     if (blocks > 148 * 32) blocks = 148 * 32;
     if (p->mode == 1) {
