@@ -252,15 +252,40 @@ build_compact_kernel(const uint32_t *__restrict__ starts, const uint32_t *__rest
     }
 }
 
-// first query of every segment in the grouped stream: qoff[s] = #queries with q_seg < s, s = 0 .. n_seg
+// first query of every segment in the grouped stream: qoff[s] = #queries with q_seg < s, s = 0 .. n_seg.
+// Four consecutive queries per thread (one 16-byte load when q_seg is 16-byte aligned); a boundary is where the
+// clamped segment id changes.
+__device__ __forceinline__ void seg_bound_step(int64_t q, int32_t prev, int32_t cur, int64_t n_seg, int64_t *__restrict__ qoff) {
+    if (prev != cur) {
+        const int64_t a = min((int64_t)max(prev, -1), n_seg), b = min((int64_t)max(cur, -1), n_seg);
+        for (int64_t s = a + 1; s <= b; ++s) qoff[s] = q;
+    }
+}
 __global__ void __launch_bounds__(256)
 seg_query_bounds_kernel(const int32_t *__restrict__ q_seg, int64_t n_q, int64_t n_seg, int64_t *__restrict__ qoff) {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q <= n_q; q += stride) {
-        const int64_t prev = q ? min((int64_t)max(q_seg[q - 1], -1), n_seg) : -1;
-        const int64_t cur = q < n_q ? min((int64_t)max(q_seg[q], -1), n_seg) : n_seg;
-        for (int64_t s = prev + 1; s <= cur; ++s) qoff[s] = q;
+    const bool vec = (reinterpret_cast<uintptr_t>(q_seg) & 15u) == 0;
+    const int64_t n4 = (n_q + 3) >> 2, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n4; g += stride) {
+        const int64_t q = g << 2;
+        int32_t v[4];
+        if (vec && q + 4 <= n_q) {
+            const int4 t = __ldg(reinterpret_cast<const int4 *>(q_seg + q));
+            v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = q + k < n_q ? q_seg[q + k] : 0x7FFFFFFF;   // past the end: "segment" n_seg
+        }
+        const int32_t prev = q ? __ldg(q_seg + q - 1) : -1;
+        seg_bound_step(q, prev, v[0], n_seg, qoff);
+#pragma unroll
+        for (int k = 1; k < 4; ++k) seg_bound_step(q + k, v[k - 1], v[k], n_seg, qoff);
+        if (q + 4 >= n_q && q + 4 > 0) {   // the thread holding the last query closes the table
+            const int32_t last = v[(n_q - 1) & 3];
+            if (((n_q - 1) >> 2) == g) seg_bound_step(n_q, last, 0x7FFFFFFF, n_seg, qoff);
+        }
     }
+    if (n_q == 0 && blockIdx.x == 0 && threadIdx.x == 0)
+        for (int64_t s = 0; s <= n_seg; ++s) qoff[s] = 0;
 }
 
 // work items: segment s is cut into ceil(nq_s / ST_CHUNK) items; ioff[s] = first item of segment s (one CTA scans)
@@ -293,28 +318,28 @@ seg_items_kernel(const int64_t *__restrict__ qoff, int64_t n_seg, int64_t *__res
 // #elements < key of one endpoint array: compact form in shared memory (sm), or the raw array `a` in global memory
 __device__ __forceinline__ uint32_t staged_lower_bound(const SegCompact &P, const uint32_t *__restrict__ a, const uint8_t *sm,
                                                        uint32_t key) {
-    if (P.n == 0 || key <= P.lo) return 0;
-    if (key > P.hi) return P.n;
     if (P.l == ST_PLAIN) return lower_bound_u32(a, P.n, key);
-    const uint32_t d = key - P.lo, b = d >> P.l, rem = d & ((1u << P.l) - 1u);
+    // clamp instead of branching: key <= lo gives d = 0 (bucket 0, rem 0: nothing below), key > hi is patched at the end
+    const uint32_t d = max(key, P.lo) - P.lo, b = min(d >> P.l, P.nb - 1u), rem = d & ((1u << P.l) - 1u);
     const uint32_t w = reinterpret_cast<const uint32_t *>(sm)[b];
     const uint32_t c0 = w & 0xFFFFu, m = (w >> 16) - c0;                 // the bucket's elements are low[c0 .. c0 + m)
     const uint8_t *low = sm + P.low_off;
+    uint32_t cnt;
     if (m > 8u) {                                                         // rare: a crowded bucket
-        uint32_t cnt = c0;
+        cnt = c0;
         for (uint32_t i = 0; i < m; ++i) cnt += (low[c0 + i] < rem) ? 1u : 0u;
-        return cnt;
+    } else {
+        // 8-byte window of low[] at c0 out of three aligned words; byte < rem <=> bit 7 of (byte | 0x80) - rem is clear
+        const uint32_t *lw = reinterpret_cast<const uint32_t *>(low) + (c0 >> 2);
+        const uint32_t x0 = lw[0], x1 = lw[1], x2 = lw[2], sh = (c0 & 3u) * 8u;
+        const uint32_t y0 = __funnelshift_r(x0, x1, sh), y1 = __funnelshift_r(x1, x2, sh);
+        const uint32_t rr = rem * 0x01010101u;
+        const uint32_t lt0 = ~((y0 | 0x80808080u) - rr) & 0x80808080u, lt1 = ~((y1 | 0x80808080u) - rr) & 0x80808080u;
+        // keep the first m bytes of the window: a 64-bit mask of 8 m ones
+        const uint64_t keep = m >= 8u ? ~0ull : ((1ull << (8u * m)) - 1ull);
+        cnt = c0 + (uint32_t)__popc(lt0 & (uint32_t)keep) + (uint32_t)__popc(lt1 & (uint32_t)(keep >> 32));
     }
-    // 8-byte window of low[] at c0 out of three aligned words; byte < rem <=> bit 7 of (byte | 0x80) - rem is clear
-    const uint32_t *lw = reinterpret_cast<const uint32_t *>(low) + (c0 >> 2);
-    const uint32_t x0 = lw[0], x1 = lw[1], x2 = lw[2], sh = (c0 & 3u) * 8u;
-    const uint32_t y0 = __funnelshift_r(x0, x1, sh), y1 = __funnelshift_r(x1, x2, sh);
-    const uint32_t rr = rem * 0x01010101u;
-    const uint32_t lt0 = ~((y0 | 0x80808080u) - rr) & 0x80808080u, lt1 = ~((y1 | 0x80808080u) - rr) & 0x80808080u;
-    // keep the first m bytes of the window
-    const uint32_t k0 = m >= 4u ? 0xFFFFFFFFu : ((1u << (8u * m)) - 1u);
-    const uint32_t k1 = m <= 4u ? 0u : (m >= 8u ? 0xFFFFFFFFu : ((1u << (8u * (m - 4u))) - 1u));
-    return c0 + (uint32_t)__popc(lt0 & k0) + (uint32_t)__popc(lt1 & k1);
+    return key > P.hi ? P.n : cnt;
 }
 
 __global__ void __launch_bounds__(ST_THREADS, 2)
@@ -356,22 +381,28 @@ count_overlaps_staged_kernel(const uint32_t *__restrict__ starts, const uint32_t
                 *reinterpret_cast<uint4 *>(smB + i) = __ldg(reinterpret_cast<const uint4 *>(gB + i));
     }
     __syncthreads();
+    if (A.n == 0) {   // an empty index counts nothing (and has no lo / hi to clamp to)
+        for (int64_t q = q0 + threadIdx.x; q < q1; q += ST_THREADS) out[q] = 0u;
+        return;
+    }
     constexpr int U = 4;
-    for (int64_t qb = q0 + threadIdx.x; qb < q1; qb += (int64_t)U * ST_THREADS) {
+    const uint32_t nq = (uint32_t)(q1 - q0);
+    const uint32_t *__restrict__ qsp = q_start + q0, *__restrict__ qep = q_stop + q0;
+    uint32_t *__restrict__ op = out + q0;
+    for (uint32_t qb = threadIdx.x; qb < nq; qb += U * ST_THREADS) {
         uint32_t qs[U], qe[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int64_t q = qb + (int64_t)u * ST_THREADS;
-            if (q < q1) { qs[u] = q_start[q]; qe[u] = q_stop[q]; }
+            const uint32_t q = min(qb + u * ST_THREADS, nq - 1u);   // clamped: the tail repeats the last query
+            qs[u] = qsp[q];
+            qe[u] = qep[q];
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int64_t q = qb + (int64_t)u * ST_THREADS;
-            if (q < q1) {
-                const uint32_t last = staged_lower_bound(A, starts + off, smA, qe[u]);
-                const uint32_t first = staged_lower_bound(B, stops + off, smB, qs[u] + 1u);
-                out[q] = last - first;
-            }
+            const uint32_t last = staged_lower_bound(A, starts + off, smA, qe[u]);
+            const uint32_t first = staged_lower_bound(B, stops + off, smB, qs[u] + 1u);
+            const uint32_t q = qb + u * ST_THREADS;
+            if (q < nq) op[q] = last - first;
         }
     }
 }

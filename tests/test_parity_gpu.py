@@ -512,3 +512,67 @@ def test_count_overlaps_grouped_device_path(ctx, orc):
         torch.cuda.synchronize()
         _eq(f"grouped={grouped}", out.cpu().numpy().view(np.uint32), ref)
     plan.close()
+
+
+def test_count_overlaps_staged_adversarial(ctx, orc):
+    """The staged (grouped) kernel on every shape its compact index has to special-case: identical endpoints, clusters
+    2^32 apart (no compact form), more elements than a staged array holds, empty and single-interval segments, a
+    crowded bucket, segments with no or very few queries, query segment ids outside the index, a q_seg pointer that is
+    not 16-byte aligned, and query chunks that end inside a segment."""
+    import torch
+    rng = np.random.default_rng(91)
+    segs = [
+        (np.full(5000, 777, np.uint32), np.full(5000, 778, np.uint32)),                                    # all identical
+        (np.concatenate([rng.integers(1, 50, 3000), rng.integers(4_000_000_000, 4_000_000_100, 3000)]).astype(np.uint32), None),
+        (rng.integers(1, 4_294_967_000, 20000).astype(np.uint32), None),                                   # huge coordinates
+        (np.array([123456], np.uint32), np.array([123999], np.uint32)),                                    # single interval
+        (np.zeros(0, np.uint32), np.zeros(0, np.uint32)),                                                  # empty
+        (np.repeat(rng.integers(1, 10_000, 50), 400).astype(np.uint32), None),                             # crowded buckets
+        (np.arange(1, 30001, dtype=np.uint32) * 3, None),                                                  # n > ST_MAX_N
+        (rng.integers(1, 500_000, 16000).astype(np.uint32), None),                                         # the C5 shape
+        (rng.integers(1, 900_000, 24000).astype(np.uint32), None),                                         # l = 7
+        (rng.integers(1, 2_000_000, 24000).astype(np.uint32), None),                                       # l = 8: plain
+        (rng.integers(1, 500_000, 16000).astype(np.uint32), None),                                         # gets no queries
+        (rng.integers(1, 500_000, 16000).astype(np.uint32), None),                                         # gets 3 queries
+    ]
+    st, sp, off = [], [], [0]
+    for a, e in segs:
+        a = np.sort(a)
+        e = np.sort(e if e is not None else (a + rng.integers(1, 200, a.size).astype(np.uint32)))
+        st.append(a), sp.append(e), off.append(off[-1] + a.size)
+    st, sp, off = np.concatenate(st), np.concatenate(sp), np.asarray(off, dtype=np.uint64)
+    n_q = 400_000
+    w = np.array([3, 3, 3, 1, 1, 3, 3, 40, 10, 10, 0, 0], dtype=np.float64)
+    seg = rng.choice(len(segs), size=n_q, p=w / w.sum()).astype(np.int32)
+    seg[:7] = [-3, -1, -1, 11, 11, 11, 12]            # outside the index below and above; 3 queries for segment 11
+    seg[7:40] = 57
+    seg.sort()
+    pool = np.concatenate([st, sp, np.array([0, 1, 2, 4_294_967_294, 4_294_967_295], np.uint32)])
+    qs = pool[rng.integers(0, pool.size, n_q)].astype(np.int64) + rng.integers(-2, 3, n_q)
+    ln = np.where(rng.random(n_q) < 0.3, 0, rng.integers(0, 5000, n_q))
+    qs = np.clip(qs, 0, 4_294_967_295)
+    qe = np.clip(qs + ln, 0, 4_294_967_295)
+    qs, qe = qs.astype(np.uint32), qe.astype(np.uint32)
+    ref = orc.count_batch(st, sp, off, seg, qs, qe, threads=8)
+    dev = torch.device("cuda", 0)
+    t = lambda a: torch.as_tensor(a.view(np.int32) if a.dtype != np.int32 else a, device=dev)
+    d_st, d_sp, d_qs, d_qe = t(st), t(sp), t(qs), t(qe)
+    plan = api.CountPlan(ctx, off)
+    stream = torch.cuda.current_stream().cuda_stream
+    for shift in (0, 1, 3):                           # shift > 0: q_seg (and the rest) start off a 16-byte boundary
+        d_seg = torch.empty(n_q + 4, dtype=torch.int32, device=dev)[shift:shift + n_q - shift]
+        d_seg.copy_(t(seg[shift:]))
+        out = torch.full((n_q - shift,), -1, dtype=torch.int32, device=dev)
+        plan.count(stream, d_st, d_sp, d_seg, d_qs[shift:], d_qe[shift:], out, grouped=True)
+        torch.cuda.synchronize()
+        _eq(f"staged adversarial (shift {shift})", out.cpu().numpy().view(np.uint32), ref[shift:])
+    # every query outside the index; a single query
+    d_seg = torch.full((1000,), 99, dtype=torch.int32, device=dev)
+    out = torch.full((1000,), -1, dtype=torch.int32, device=dev)
+    plan.count(stream, d_st, d_sp, d_seg, d_qs[:1000], d_qe[:1000], out, grouped=True)
+    torch.cuda.synchronize()
+    assert int(out.abs().sum()) == 0
+    plan.count(stream, d_st, d_sp, t(seg[100_000:100_001]), d_qs[100_000:100_001], d_qe[100_000:100_001], out[:1], grouped=True)
+    torch.cuda.synchronize()
+    assert int(out[0]) == int(ref[100_000])
+    plan.close()
