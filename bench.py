@@ -515,7 +515,8 @@ def bench_count(args, ctx, L, dev, rank, world, g_off, barrier, max_over_ranks, 
                "gpu_launches": int(plan.launches - l0),
                "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                             "frac": alg / (ms * 1e-3) / 1e9 / hbm_peak,
-                            "traffic": ncu_traffic("count_overlaps_ranked_kernel:grouped_by_ctg") if grouped and n_q == 100_000_000 else None,
+                            "kernel": "seg_query_bounds_kernel + seg_items_kernel + count_overlaps_staged_kernel" if grouped else "count_overlaps_ranked_kernel",
+                            "traffic": ncu_traffic("count_overlaps:grouped_by_ctg" if grouped else "count_overlaps:arbitrary_order") if n_q == 100_000_000 else None,
                             "algorithmic_bytes_per_launch": alg, "peak_source": peak_src}}
         if rank == 0:
             from oracle import oracle as orc

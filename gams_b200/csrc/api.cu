@@ -31,21 +31,70 @@ int32_t cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
     return GAMS_CUDA_ECUDA;
 }
 
+size_t BlockCache::round_up(size_t bytes) {
+    if (bytes <= 256) return 256;
+    if (bytes >= (1u << 20)) return ((bytes + (1u << 20) - 1) >> 20) << 20;
+    size_t r = 256;
+    while (r < bytes) r <<= 1;
+    return r;
+}
+
+int32_t BlockCache::get(void **p, size_t bytes) {
+    const size_t want = round_up(bytes);
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = free_blocks.lower_bound(want);
+        if (it != free_blocks.end() && it->first <= want + want / 4) {   // at most 25 % larger than asked
+            *p = it->second;
+            free_blocks.erase(it);
+            return GAMS_CUDA_OK;
+        }
+    }
+    cudaError_t e = cudaMalloc(p, want);
+    if (e == cudaErrorMemoryAllocation) {   // give the cached blocks back and try once more
+        cudaGetLastError();
+        clear();
+        e = cudaMalloc(p, want);
+    }
+    CUDA_TRY(e);
+    return GAMS_CUDA_OK;
+}
+
+void BlockCache::put(void *p, size_t bytes) {
+    std::lock_guard<std::mutex> lk(mu);
+    free_blocks.emplace(round_up(bytes), p);
+}
+
+void BlockCache::clear() {
+    std::lock_guard<std::mutex> lk(mu);
+    for (auto &kv : free_blocks) cudaFree(kv.second);
+    free_blocks.clear();
+}
+
+int32_t dev_alloc(BlockCache *cache, void **p, size_t bytes) {
+    if (cache) return cache->get(p, bytes);
+    CUDA_TRY(cudaMalloc(p, bytes ? bytes : 1));
+    return GAMS_CUDA_OK;
+}
+
+void dev_free(BlockCache *cache, void *p, size_t bytes) {
+    if (!p) return;
+    if (cache) cache->put(p, bytes);
+    else cudaFree(p);
+}
+
 int32_t DevBuf::reserve(size_t bytes) {
     if (bytes <= cap) return GAMS_CUDA_OK;
-    if (p) {
-        cudaFree(p);
-        p = nullptr;
-        cap = 0;
-    }
-    const size_t want = ((bytes + (1u << 20) - 1) >> 20) << 20;
-    CUDA_TRY(cudaMalloc(&p, want));
+    release();
+    const size_t want = BlockCache::round_up(bytes);
+    int32_t rc = dev_alloc(cache, &p, want);
+    if (rc) return rc;
     cap = want;
     return GAMS_CUDA_OK;
 }
 
 void DevBuf::release() {
-    if (p) cudaFree(p);
+    dev_free(cache, p, cap);
     p = nullptr;
     cap = 0;
 }
@@ -71,10 +120,11 @@ int32_t SeriesLayout::build(const uint64_t *h_off, int64_t n, cudaStream_t st) {
     }
     if (n == 0) min_len = 0;
     n_ztiles = zt.size();
-    CUDA_TRY(cudaMalloc(&d_off, sizeof(uint64_t) * (size_t)(n + 1)));
+    int32_t rc;
+    if ((rc = dev_alloc(cache, reinterpret_cast<void **>(&d_off), sizeof(uint64_t) * (size_t)(n + 1)))) return rc;
     CUDA_TRY(cudaMemcpyAsync(d_off, rel.data(), sizeof(uint64_t) * (size_t)(n + 1), cudaMemcpyHostToDevice, st));
     if (n_ztiles) {
-        CUDA_TRY(cudaMalloc(&d_ztiles, sizeof(TileDesc) * n_ztiles));
+        if ((rc = dev_alloc(cache, reinterpret_cast<void **>(&d_ztiles), sizeof(TileDesc) * n_ztiles))) return rc;
         CUDA_TRY(cudaMemcpyAsync(d_ztiles, zt.data(), sizeof(TileDesc) * n_ztiles, cudaMemcpyHostToDevice, st));
     }
     CUDA_TRY(cudaStreamSynchronize(st));
@@ -82,8 +132,8 @@ int32_t SeriesLayout::build(const uint64_t *h_off, int64_t n, cudaStream_t st) {
 }
 
 void SeriesLayout::release() {
-    if (d_off) cudaFree(d_off);
-    if (d_ztiles) cudaFree(d_ztiles);
+    dev_free(cache, d_off, sizeof(uint64_t) * (size_t)(n_series + 1));
+    dev_free(cache, d_ztiles, sizeof(TileDesc) * n_ztiles);
     d_off = nullptr;
     d_ztiles = nullptr;
 }
@@ -118,6 +168,21 @@ static int32_t for_each_device(gams_cuda_ctx *ctx, int n_used, F fn) {
 }  // namespace gams
 
 using namespace gams;
+
+// GAMS_CUDA_TRACE=1: host-clock stage timings of the host API on stderr (synchronises; for debugging only)
+#include <chrono>
+static bool trace_on() {
+    static const bool on = getenv("GAMS_CUDA_TRACE") != nullptr;
+    return on;
+}
+static void trace_stage(const char *what, cudaStream_t st = nullptr, bool sync = false) {
+    if (!trace_on()) return;
+    static thread_local auto last = std::chrono::steady_clock::now();
+    if (sync) cudaStreamSynchronize(st);
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[gams_cuda] %-28s +%8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - last).count());
+    last = now;
+}
 
 // ================================================================================ lifecycle =====
 GAMS_API int32_t gams_cuda_version(void) { return 100; /* 0.1.0 */ }
@@ -170,6 +235,8 @@ GAMS_API int32_t gams_cuda_create(const int32_t *device_ids, int32_t n_dev, gams
         CUDA_TRY(cudaStreamCreateWithFlags(&pd.copy_out, cudaStreamNonBlocking));
         CUDA_TRY(cudaMalloc(&pd.d_zstats, 2 * sizeof(unsigned long long)));
         CUDA_TRY(cudaMemset(pd.d_zstats, 0, 2 * sizeof(unsigned long long)));
+        pd.cache = new BlockCache;
+        for (auto &b : pd.scratch) b.cache = pd.cache;
         ctx->devs.push_back(pd);
     }
     if (const char *m = getenv("GAMS_CUDA_ZSCORE_MODE")) ctx->zscore_mode = atoi(m);
@@ -204,6 +271,10 @@ GAMS_API void gams_cuda_destroy(gams_cuda_ctx *ctx) {
         DeviceGuard g(pd.device);
         cudaStreamSynchronize(pd.stream);
         for (auto &b : pd.scratch) b.release();
+        if (pd.cache) {
+            pd.cache->clear();
+            delete pd.cache;
+        }
         if (pd.d_zstats) cudaFree(pd.d_zstats);
         cudaStreamDestroy(pd.stream);
         cudaStreamDestroy(pd.copy_in);
@@ -328,21 +399,25 @@ GAMS_API int32_t gams_cuda_wave_plan_create(gams_cuda_ctx *ctx, int32_t dev_inde
         ARG_CHECK(ft.size() < (1ull << 31), "wave_plan_create: too many tiles");
     }
     DeviceGuard g(pd.device);
+    BlockCache *cache = pd.cache;
+    p->win.cache = cache;
+    p->n_ftiles = ft.size();
+    int32_t arc;
     if (!ft.empty()) {
-        CUDA_TRY(cudaMalloc(&p->d_ftiles, sizeof(FusedTile) * ft.size()));
+        if ((arc = dev_alloc(cache, reinterpret_cast<void **>(&p->d_ftiles), sizeof(FusedTile) * ft.size()))) return arc;
         CUDA_TRY(cudaMemcpyAsync(p->d_ftiles, ft.data(), sizeof(FusedTile) * ft.size(), cudaMemcpyHostToDevice, pd.stream));
         CUDA_TRY(cudaStreamSynchronize(pd.stream));
     }
-    CUDA_TRY(cudaMalloc(&p->d_seq_off, sizeof(uint64_t) * (size_t)(n_ctg + 1)));
+    if ((arc = dev_alloc(cache, reinterpret_cast<void **>(&p->d_seq_off), sizeof(uint64_t) * (size_t)(n_ctg + 1)))) return arc;
     CUDA_TRY(cudaMemcpyAsync(p->d_seq_off, p->h_seq_off.data(), sizeof(uint64_t) * (size_t)(n_ctg + 1),
                              cudaMemcpyHostToDevice, pd.stream));
     if (!gt.empty()) {
-        CUDA_TRY(cudaMalloc(&p->d_gtiles, sizeof(TileDesc) * gt.size()));
+        if ((arc = dev_alloc(cache, reinterpret_cast<void **>(&p->d_gtiles), sizeof(TileDesc) * gt.size()))) return arc;
         CUDA_TRY(cudaMemcpyAsync(p->d_gtiles, gt.data(), sizeof(TileDesc) * gt.size(), cudaMemcpyHostToDevice, pd.stream));
         std::vector<float> tab((size_t)size + 1);
         const float fs = (float)size;
         for (int32_t c = 0; c <= size; ++c) tab[c] = (float)c / fs;  // `count as f32 / l as f32`, one IEEE divide
-        CUDA_TRY(cudaMalloc(&p->d_gc_tab, sizeof(float) * tab.size()));
+        if ((arc = dev_alloc(cache, reinterpret_cast<void **>(&p->d_gc_tab), sizeof(float) * tab.size()))) return arc;
         CUDA_TRY(cudaMemcpyAsync(p->d_gc_tab, tab.data(), sizeof(float) * tab.size(), cudaMemcpyHostToDevice, pd.stream));
         CUDA_TRY(cudaStreamSynchronize(pd.stream));
     }
@@ -355,10 +430,12 @@ GAMS_API int32_t gams_cuda_wave_plan_create(gams_cuda_ctx *ctx, int32_t dev_inde
 GAMS_API void gams_cuda_wave_plan_destroy(gams_cuda_wave_plan *p) {
     if (!p) return;
     DeviceGuard g(p->device);
-    if (p->d_seq_off) cudaFree(p->d_seq_off);
-    if (p->d_gtiles) cudaFree(p->d_gtiles);
-    if (p->d_ftiles) cudaFree(p->d_ftiles);
-    if (p->d_gc_tab) cudaFree(p->d_gc_tab);
+    cudaDeviceSynchronize();   // as cudaFree would: nothing in flight may still read the tables that go back to the cache
+    BlockCache *cache = p->ctx ? p->ctx->devs[p->dev_index].cache : nullptr;
+    dev_free(cache, p->d_seq_off, sizeof(uint64_t) * (size_t)(p->n_ctg + 1));
+    dev_free(cache, p->d_gtiles, sizeof(TileDesc) * (size_t)p->geom.n_tiles);
+    dev_free(cache, p->d_ftiles, sizeof(FusedTile) * p->n_ftiles);
+    dev_free(cache, p->d_gc_tab, sizeof(float) * ((size_t)p->size + 1));
     p->win.release();
     delete p;
 }
@@ -529,6 +606,7 @@ GAMS_API int32_t gams_cuda_thresholding_batch(gams_cuda_ctx *ctx, int64_t n_seri
     PerDevice &pd = ctx->devs[0];
     DeviceGuard g(pd.device);
     SeriesLayout L;
+    L.cache = pd.cache;
     int32_t rc = L.build(off, n_series, pd.stream);
     struct Rel { SeriesLayout &l; ~Rel() { l.release(); } } rel{L};
     if (rc) return rc;
@@ -573,7 +651,9 @@ GAMS_API int32_t gams_cuda_count_plan_create(gams_cuda_ctx *ctx, int32_t dev_ind
     p->total_iv = p->h_iv_off[n_seg];
     if (const char *m = getenv("GAMS_CUDA_COUNT_MODE")) p->mode = atoi(m);
     DeviceGuard g(pd.device);
-    CUDA_TRY(cudaMalloc(&p->d_iv_off, sizeof(uint64_t) * (size_t)(n_seg + 1)));
+    for (auto &b : p->tmp) b.cache = pd.cache;
+    int32_t arc = dev_alloc(pd.cache, reinterpret_cast<void **>(&p->d_iv_off), sizeof(uint64_t) * (size_t)(n_seg + 1));
+    if (arc) return arc;
     CUDA_TRY(cudaMemcpyAsync(p->d_iv_off, p->h_iv_off.data(), sizeof(uint64_t) * (size_t)(n_seg + 1),
                              cudaMemcpyHostToDevice, pd.stream));
     CUDA_TRY(cudaStreamSynchronize(pd.stream));
@@ -584,7 +664,8 @@ GAMS_API int32_t gams_cuda_count_plan_create(gams_cuda_ctx *ctx, int32_t dev_ind
 GAMS_API void gams_cuda_count_plan_destroy(gams_cuda_count_plan *p) {
     if (!p) return;
     DeviceGuard g(p->device);
-    if (p->d_iv_off) cudaFree(p->d_iv_off);
+    cudaDeviceSynchronize();   // as cudaFree would
+    dev_free(p->ctx ? p->ctx->devs[p->dev_index].cache : nullptr, p->d_iv_off, sizeof(uint64_t) * (size_t)(p->n_seg + 1));
     for (auto &b : p->tmp) b.release();
     delete p;
 }
@@ -622,8 +703,10 @@ GAMS_API int32_t gams_cuda_count_overlaps(gams_cuda_ctx *ctx, int64_t n_seg, con
         PerDevice &pd = ctx->devs[d];
         DeviceGuard g(pd.device);
         gams_cuda_count_plan *plan = nullptr;
+        trace_stage("count: enter");
         int32_t rc = gams_cuda_count_plan_create(ctx, d, n_seg, iv_off, &plan);
         if (rc) return rc;
+        trace_stage("count: plan_create");
         std::unique_ptr<gams_cuda_count_plan, void (*)(gams_cuda_count_plan *)> guard(plan, gams_cuda_count_plan_destroy);
         if ((rc = pd.scratch[0].reserve(std::max<uint64_t>(n_iv, 1) * 4))) return rc;
         if ((rc = pd.scratch[1].reserve(std::max<uint64_t>(n_iv, 1) * 4))) return rc;
@@ -637,7 +720,9 @@ GAMS_API int32_t gams_cuda_count_overlaps(gams_cuda_ctx *ctx, int64_t n_seg, con
             CUDA_TRY(cudaMemcpyAsync(d_st, starts + iv_off[0], n_iv * 4, cudaMemcpyHostToDevice, st));
             CUDA_TRY(cudaMemcpyAsync(d_sp, stops + iv_off[0], n_iv * 4, cudaMemcpyHostToDevice, st));
         }
+        trace_stage("count: reserve + index H2D", st, true);
         if ((rc = build_count_index(plan, st, d_st, d_sp))) return rc;
+        trace_stage("count: build_count_index", st, true);
         cudaEvent_t ev_idx;
         CUDA_TRY(cudaEventCreateWithFlags(&ev_idx, cudaEventDisableTiming));
         CUDA_TRY(cudaEventRecord(ev_idx, st));
@@ -675,6 +760,9 @@ GAMS_API int32_t gams_cuda_count_overlaps(gams_cuda_ctx *ctx, int64_t n_seg, con
         }
         CUDA_TRY(cudaStreamSynchronize(pd.copy_out));
         CUDA_TRY(cudaStreamSynchronize(st));
+        trace_stage("count: slices");
+        guard.reset();
+        trace_stage("count: plan_destroy");
         return GAMS_CUDA_OK;
     });
 }

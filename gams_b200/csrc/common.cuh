@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <algorithm>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <vector>
 
@@ -34,10 +35,25 @@ int32_t cuda_fail(cudaError_t e, const char *what, const char *file, int line);
         }                               \
     } while (0)
 
-// ---- small RAII helpers ---------------------------------------------------------------------
+// ---- device memory ----------------------------------------------------------------------------
+// Freed blocks of one device, kept for reuse: the host API creates and destroys a plan per call, and cudaMalloc /
+// cudaFree of its tables (up to GBs of rank nodes) cost from milliseconds to a second each.  Blocks return to the
+// driver when the context is destroyed.
+struct BlockCache {
+    std::mutex mu;
+    std::multimap<size_t, void *> free_blocks;
+    static size_t round_up(size_t bytes);
+    int32_t get(void **p, size_t bytes);      // *p has round_up(bytes) bytes
+    void put(void *p, size_t bytes);
+    void clear();
+};
+int32_t dev_alloc(BlockCache *cache, void **p, size_t bytes);   // cache == nullptr: plain cudaMalloc
+void dev_free(BlockCache *cache, void *p, size_t bytes);
+
 struct DevBuf {  // grow-only device scratch
     void *p = nullptr;
     size_t cap = 0;
+    BlockCache *cache = nullptr;
     int32_t reserve(size_t bytes);
     void release();
     template <class T> T *as() const { return static_cast<T *>(p); }
@@ -115,6 +131,7 @@ struct SeriesLayout {
     uint64_t n_ztiles = 0;
     std::vector<uint64_t> h_off;       // n_series+1 (relative to the first series)
     std::vector<uint64_t> h_ztile_off; // n_series+1: first z-score tile of each series
+    BlockCache *cache = nullptr;
     int32_t build(const uint64_t *h_off, int64_t n, cudaStream_t st);
     void release();
 };
@@ -125,6 +142,7 @@ struct PerDevice {
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
     DevBuf scratch[8];
     unsigned long long *d_zstats = nullptr;  // [0] windows replayed after an inconclusive certificate, [1] verify mismatches
+    BlockCache *cache = nullptr;             // owned by the context
 };
 
 }  // namespace gams
@@ -152,6 +170,7 @@ struct gams_cuda_wave_plan {
     float *d_gc_tab = nullptr;       // (float)c / (float)size for c = 0..size (host-computed IEEE divide)
     int fused_wt = 0;                // windows per Kernel-AB tile; 0 = geometry not eligible for the fused kernel
     gams::FusedTile *d_ftiles = nullptr;
+    size_t n_ftiles = 0;
     std::vector<uint64_t> h_ftile_off;  // n_ctg+1: first Kernel-AB tile of each ctg
     uint64_t launches = 0;
 };
