@@ -9,7 +9,7 @@ _PKG = Path(__file__).resolve().parent
 _ROOT = _PKG.parent
 _LIB = None
 
-ERR = {0: "OK", -1: "EINVAL", -2: "ECUDA", -3: "ENOMEM", -4: "ELAG", -5: "ENODEV", -6: "EPARSE"}
+ERR = {0: "OK", -1: "EINVAL", -2: "ECUDA", -3: "ENOMEM", -4: "ELAG", -5: "ENODEV", -6: "EPARSE", -7: "ECAP"}
 
 
 class GamsCudaError(RuntimeError):
@@ -59,6 +59,10 @@ def load() -> C.CDLL:
         "gams_cuda_partition": (i32, [i64, vp, i32, vp]),
         "gams_cuda_wave_batch": (i32, [vp, i64, vp, vp, i32, i32, u64, f32, f32, vp, vp, vp, vp]),
         "gams_cuda_thresholding_batch": (i32, [vp, i64, vp, vp, u64, f32, f32, vp]),
+        "gams_cuda_wave_peaks_batch": (i32, [vp, i64, vp, vp, i32, i32, u64, f32, f32, f32, vp, u64, vp, vp, vp, vp, vp, vp]),
+        "gams_cuda_wave_peaks_dev": (i32, [vp, vp, vp, vp, f32, u64, vp, vp, vp, vp, vp, vp]),
+        "gams_cuda_peak_link_batch": (i32, [vp, i64, vp, vp, vp, i64] + [vp] * 11),
+        "gams_cuda_wave_peaks_text": (i32, [C.c_char_p, i32, i32, i32, i64, vp, vp, vp, vp, C.POINTER(vp), C.POINTER(sz)]),
         "gams_cuda_wave_plan_create": (i32, [vp, i32, i64, vp, i32, i32, u64, C.POINTER(vp)]),
         "gams_cuda_wave_plan_destroy": (None, [vp]),
         "gams_cuda_wave_plan_total_windows": (u64, [vp]),

@@ -117,6 +117,60 @@ def wave_batch(ctx: Context, seq_concat, seq_off, size=100, step=10, lag=100, th
     return woff, cnt, gc, sig
 
 
+# --------------------------------------------------------------- wave.rs:138-252 (peaks only)
+def wave_peaks_batch(ctx: Context, seq_concat, seq_off, size=100, step=10, lag=100, threshold=3.0, influence=1.0,
+                     coverage=0.2, cap=None):
+    """`gams wave` (merged peaks) for a batch of ctgs → dict(ctg, first, last, gc, signal): one record per printed line."""
+    seq_concat = _arr(seq_concat, np.uint8)
+    seq_off = _arr(seq_off, np.uint64)
+    woff = win_offsets(seq_off, size, step)
+    L = load()
+    cap = int(cap if cap is not None else max(4096, int(woff[-1]) // 32))
+    while True:
+        ctg, first, last = (np.empty(cap, dtype=np.uint32) for _ in range(3))
+        gc, sig, n = np.empty(cap, dtype=np.float32), np.empty(cap, dtype=np.int8), C.c_uint64()
+        rc = L.gams_cuda_wave_peaks_batch(ctx.handle, seq_off.size - 1, _p(seq_concat), _p(seq_off), size, step, lag, threshold,
+                                          influence, coverage, _p(woff), cap, _p(ctg), _p(first), _p(last), _p(gc), _p(sig),
+                                          C.byref(n))
+        if rc == -7 and n.value > cap:  # ECAP: the call reports how many records there are
+            cap = int(n.value)
+            continue
+        check(rc)
+        k = int(n.value)
+        return dict(ctg=ctg[:k], first=first[:k], last=last[:k], gc=gc[:k], signal=sig[:k])
+
+
+def wave_peaks_text(chr_id: str, chr_start: int, size: int, step: int, first, last, gc, signal) -> str:
+    """The per-ctg stdout block of `gams wave` from the peak records of that ctg."""
+    first, last = _arr(first, np.uint32), _arr(last, np.uint32)
+    gc, signal = _arr(gc, np.float32), _arr(signal, np.int8)
+    txt, ln = C.c_void_p(), C.c_size_t()
+    L = load()
+    check(L.gams_cuda_wave_peaks_text(chr_id.encode(), chr_start, size, step, first.size, _p(first), _p(last), _p(gc), _p(signal),
+                                      C.byref(txt), C.byref(ln)))
+    try:
+        return C.string_at(txt, ln.value).decode()
+    finally:
+        L.gams_cuda_free(txt)
+
+
+# --------------------------------------------------------------- peak.rs:66-160
+def peak_link_batch(ctx: Context, seq_concat, seq_off, ctg_chr_start, p_ctg, p_start, p_end, p_signal):
+    """`gams peak`: GC of each peak range and its links to the neighbouring peaks of the ctg → dict of arrays."""
+    seq_concat, seq_off = _arr(seq_concat, np.uint8), _arr(seq_off, np.uint64)
+    ctg_chr_start = _arr(ctg_chr_start, np.int32)
+    p_ctg, p_start, p_end, p_signal = _arr(p_ctg, np.uint32), _arr(p_start, np.int32), _arr(p_end, np.int32), _arr(p_signal, np.int8)
+    n = p_ctg.size
+    gc, la, ra = (np.empty(n, dtype=np.float32) for _ in range(3))
+    ll, rl = (np.empty(n, dtype=np.int32) for _ in range(2))
+    ls, rs = (np.empty(n, dtype=np.int8) for _ in range(2))
+    check(load().gams_cuda_peak_link_batch(ctx.handle, seq_off.size - 1, _p(seq_concat), _p(seq_off), _p(ctg_chr_start), n,
+                                           _p(p_ctg), _p(p_start), _p(p_end), _p(p_signal), _p(gc), _p(ls), _p(ll), _p(la),
+                                           _p(rs), _p(rl), _p(ra)))
+    return dict(gc=gc, left_signal=ls, left_wave_length=ll, left_amplitude=la, right_signal=rs, right_wave_length=rl,
+                right_amplitude=ra)
+
+
 # ------------------------------------------------------------------------------ stat.rs:16-56
 def thresholding_algo(ctx: Context, data, lag: int, threshold: float, influence: float) -> np.ndarray:
     """gams::thresholding_algo(data, lag, threshold, influence) → int8 signals (-1/0/1)."""

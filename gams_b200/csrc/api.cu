@@ -401,6 +401,7 @@ GAMS_API int32_t gams_cuda_wave_plan_create(gams_cuda_ctx *ctx, int32_t dev_inde
     DeviceGuard g(pd.device);
     BlockCache *cache = pd.cache;
     p->win.cache = cache;
+    p->peak_tmp.cache = cache;
     p->n_ftiles = ft.size();
     int32_t arc;
     if (!ft.empty()) {
@@ -436,6 +437,7 @@ GAMS_API void gams_cuda_wave_plan_destroy(gams_cuda_wave_plan *p) {
     dev_free(cache, p->d_gtiles, sizeof(TileDesc) * (size_t)p->geom.n_tiles);
     dev_free(cache, p->d_ftiles, sizeof(FusedTile) * p->n_ftiles);
     dev_free(cache, p->d_gc_tab, sizeof(float) * ((size_t)p->size + 1));
+    p->peak_tmp.release();
     p->win.release();
     delete p;
 }
@@ -483,10 +485,35 @@ GAMS_API int32_t gams_cuda_wave_plan_fused(const gams_cuda_wave_plan *p, float t
     return (p && wave_fused_ok(p, threshold, influence)) ? 1 : 0;
 }
 
+GAMS_API int32_t gams_cuda_wave_peaks_dev(gams_cuda_wave_plan *p, void *stream, const float *d_gc, const int8_t *d_signal,
+                                          float coverage, uint64_t cap, uint32_t *d_pk_ctg, uint32_t *d_pk_first,
+                                          uint32_t *d_pk_last, float *d_pk_gc, int8_t *d_pk_signal, uint64_t *d_n_peaks) {
+    ARG_CHECK(p && d_n_peaks && (p->win.total == 0 || (d_gc && d_signal)), "wave_peaks_dev: NULL argument");
+    ARG_CHECK(cap == 0 || (d_pk_ctg && d_pk_first && d_pk_last && d_pk_gc && d_pk_signal), "wave_peaks_dev: NULL output");
+    ARG_CHECK(peak_merge_is_runs(p->size, p->step, coverage),
+              "wave_peaks_dev: with coverage %g some intersecting windows are not merged (wave.rs:229-231): components are "
+              "not runs; use gams_cuda_wave_text on the per-window arrays", (double)coverage);
+    DeviceGuard g(p->device);
+    const uint64_t tiles = (p->win.total + 2047) / 2048;
+    int32_t rc = p->peak_tmp.reserve(sizeof(uint64_t) * 2 * (tiles + 2));
+    if (rc) return rc;
+    p->launches += 3;
+    return launch_peak_runs((cudaStream_t)stream, d_signal, d_gc, p->win.d_off, p->n_ctg, 0, p->win.total, p->size, p->step,
+                            p->peak_tmp.as<uint64_t>(), cap, d_pk_ctg, d_pk_first, d_pk_last, d_pk_gc, d_pk_signal, d_n_peaks);
+}
+
 // ================================================================================ wave: host ====
+struct PeakSink {   // per-device results of gams_cuda_wave_peaks_batch
+    float coverage = 0.0f;
+    std::vector<uint32_t> ctg, first, last;
+    std::vector<float> gc;
+    std::vector<int8_t> sig;
+};
+
 static int32_t wave_on_device(gams_cuda_ctx *ctx, int d, int64_t c0, int64_t c1, const uint8_t *seq_concat,
                               const uint64_t *seq_off, int32_t size, int32_t step, uint64_t lag, float threshold,
-                              float influence, const uint64_t *win_off, uint32_t *gc_count, float *gc, int8_t *signal) {
+                              float influence, const uint64_t *win_off, uint32_t *gc_count, float *gc, int8_t *signal,
+                              PeakSink *sink = nullptr) {
     if (c1 <= c0) return GAMS_CUDA_OK;
     PerDevice &pd = ctx->devs[d];
     DeviceGuard g(pd.device);
@@ -499,25 +526,26 @@ static int32_t wave_on_device(gams_cuda_ctx *ctx, int d, int64_t c0, int64_t c1,
         set_error("wave_batch: win_off does not match gams_cuda_wave_win_offsets for size=%d step=%d", size, step);
         return GAMS_CUDA_EINVAL;
     }
-    if (signal && lag == 0) {
+    if ((signal || sink) && lag == 0) {
         set_error("wave_batch: lag must be >= 1");
         return GAMS_CUDA_EINVAL;
     }
-    if (signal && plan->win.min_len < lag) {
+    if ((signal || sink) && plan->win.min_len < lag) {
         set_error("wave_batch: a ctg has %llu windows but lag is %llu (the reference panics, stat.rs:30)",
                   (unsigned long long)plan->win.min_len, (unsigned long long)lag);
         return GAMS_CUDA_ELAG;
     }
     if ((rc = pd.scratch[0].reserve(gams_cuda_wave_plan_seq_capacity(plan)))) return rc;
+    const bool want_sig = signal || sink;   // sink: the per-window arrays stay on the device, only peak records come back
     if ((rc = pd.scratch[1].reserve(std::max<uint64_t>(nwn, 1) * sizeof(float)))) return rc;
     if (gc_count && (rc = pd.scratch[2].reserve(std::max<uint64_t>(nwn, 1) * sizeof(uint32_t)))) return rc;
-    if (signal && (rc = pd.scratch[3].reserve(std::max<uint64_t>(nwn, 1)))) return rc;
-    const bool need_filt = signal && !(influence == 1.0f && lag <= ZS_MAX_TILED_LAG);
+    if (want_sig && (rc = pd.scratch[3].reserve(std::max<uint64_t>(nwn, 1)))) return rc;
+    const bool need_filt = want_sig && !(influence == 1.0f && lag <= ZS_MAX_TILED_LAG);
     if (need_filt && (rc = pd.scratch[4].reserve(std::max<uint64_t>(nwn, 1) * sizeof(float)))) return rc;
     uint8_t *d_seq = pd.scratch[0].as<uint8_t>();
     float *d_gc = pd.scratch[1].as<float>();
     uint32_t *d_cnt = gc_count ? pd.scratch[2].as<uint32_t>() : nullptr;
-    int8_t *d_sig = signal ? pd.scratch[3].as<int8_t>() : nullptr;
+    int8_t *d_sig = want_sig ? pd.scratch[3].as<int8_t>() : nullptr;
     float *d_filt = need_filt ? pd.scratch[4].as<float>() : nullptr;
     // Pipeline over slices of ~64 MB of sequence: H2D of slice k+1, kernels of slice k and D2H of slice k-1
     // run concurrently on three streams (PCIe is full duplex; the kernels are far shorter than either copy).
@@ -549,21 +577,51 @@ static int32_t wave_on_device(gams_cuda_ctx *ctx, int d, int64_t c0, int64_t c1,
         if (b1 > b0) CUDA_TRY(cudaMemcpyAsync(d_seq + b0, h_seq + b0, b1 - b0, cudaMemcpyHostToDevice, pd.copy_in));
         CUDA_TRY(cudaEventRecord(ev_in[k], pd.copy_in));
         CUDA_TRY(cudaStreamWaitEvent(pd.stream, ev_in[k], 0));
-        if (signal && wave_fused_ok(plan, threshold, influence)) {
+        if (want_sig && wave_fused_ok(plan, threshold, influence)) {
             if ((rc = launch_gc_wave_fused(plan, pd.stream, d_seq, threshold, d_cnt, d_gc, d_sig, pd.d_zstats, a, b))) return rc;
         } else {
             if ((rc = launch_gc_windows(plan, pd.stream, d_seq, d_cnt, d_gc, &plan->launches, a, b))) return rc;
-            if (signal && (rc = launch_zscore(plan->win, pd.stream, d_gc, lag, threshold, influence, d_filt, d_sig,
-                                              &plan->launches, ctx->zscore_mode, pd.d_zstats, a, b)))
+            if (want_sig && (rc = launch_zscore(plan->win, pd.stream, d_gc, lag, threshold, influence, d_filt, d_sig,
+                                                &plan->launches, ctx->zscore_mode, pd.d_zstats, a, b)))
                 return rc;
         }
         CUDA_TRY(cudaEventRecord(ev_k[k], pd.stream));
         CUDA_TRY(cudaStreamWaitEvent(pd.copy_out, ev_k[k], 0));
-        if (w1 > w0) {
+        if (w1 > w0 && gc) {
             CUDA_TRY(cudaMemcpyAsync(gc + wo + w0, d_gc + w0, (w1 - w0) * sizeof(float), cudaMemcpyDeviceToHost, pd.copy_out));
             if (gc_count)
                 CUDA_TRY(cudaMemcpyAsync(gc_count + wo + w0, d_cnt + w0, (w1 - w0) * sizeof(uint32_t), cudaMemcpyDeviceToHost, pd.copy_out));
             if (signal) CUDA_TRY(cudaMemcpyAsync(signal + wo + w0, d_sig + w0, w1 - w0, cudaMemcpyDeviceToHost, pd.copy_out));
+        }
+    }
+    if (sink) {
+        // peak merge on the device; two attempts at most: the first sizes the record arrays
+        uint64_t cap = std::max<uint64_t>(nwn / 64, 4096), n_pk = 0;
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            const uint64_t rec = cap * 17 + 64;
+            if ((rc = pd.scratch[5].reserve(rec + 16))) return rc;
+            uint8_t *base = pd.scratch[5].as<uint8_t>();
+            uint64_t *d_n = reinterpret_cast<uint64_t *>(base);
+            uint32_t *k_ctg = reinterpret_cast<uint32_t *>(base + 16), *k_first = k_ctg + cap, *k_last = k_first + cap;
+            float *k_gc = reinterpret_cast<float *>(k_last + cap);
+            int8_t *k_sig = reinterpret_cast<int8_t *>(k_gc + cap);
+            if ((rc = gams_cuda_wave_peaks_dev(plan, pd.stream, d_gc, d_sig, sink->coverage, cap, k_ctg, k_first, k_last, k_gc,
+                                               k_sig, d_n)))
+                return rc;
+            CUDA_TRY(cudaMemcpyAsync(&n_pk, d_n, sizeof(uint64_t), cudaMemcpyDeviceToHost, pd.stream));
+            CUDA_TRY(cudaStreamSynchronize(pd.stream));
+            if (n_pk <= cap) {
+                sink->ctg.resize(n_pk), sink->first.resize(n_pk), sink->last.resize(n_pk), sink->gc.resize(n_pk), sink->sig.resize(n_pk);
+                if (n_pk) {
+                    CUDA_TRY(cudaMemcpyAsync(sink->ctg.data(), k_ctg, n_pk * 4, cudaMemcpyDeviceToHost, pd.stream));
+                    CUDA_TRY(cudaMemcpyAsync(sink->first.data(), k_first, n_pk * 4, cudaMemcpyDeviceToHost, pd.stream));
+                    CUDA_TRY(cudaMemcpyAsync(sink->last.data(), k_last, n_pk * 4, cudaMemcpyDeviceToHost, pd.stream));
+                    CUDA_TRY(cudaMemcpyAsync(sink->gc.data(), k_gc, n_pk * 4, cudaMemcpyDeviceToHost, pd.stream));
+                    CUDA_TRY(cudaMemcpyAsync(sink->sig.data(), k_sig, n_pk, cudaMemcpyDeviceToHost, pd.stream));
+                }
+                break;
+            }
+            cap = n_pk;
         }
     }
     CUDA_TRY(cudaStreamSynchronize(pd.copy_out));
@@ -591,6 +649,52 @@ GAMS_API int32_t gams_cuda_wave_batch(gams_cuda_ctx *ctx, int64_t n_ctg, const u
         return wave_on_device(ctx, d, part[d], part[d + 1], seq_concat, seq_off, size, step, lag, threshold, influence,
                               win_off, gc_count, gc, signal);
     });
+}
+
+GAMS_API int32_t gams_cuda_wave_peaks_batch(gams_cuda_ctx *ctx, int64_t n_ctg, const uint8_t *seq_concat,
+                                            const uint64_t *seq_off, int32_t size, int32_t step, uint64_t lag,
+                                            float threshold, float influence, float coverage, const uint64_t *win_off,
+                                            uint64_t cap, uint32_t *pk_ctg, uint32_t *pk_first, uint32_t *pk_last,
+                                            float *pk_gc, int8_t *pk_signal, uint64_t *n_peaks) {
+    ARG_CHECK(ctx && n_peaks, "wave_peaks_batch: NULL argument");
+    ARG_CHECK(n_ctg >= 0 && seq_off && win_off, "wave_peaks_batch: NULL offsets");
+    ARG_CHECK(size > 0 && step > 0, "wave_peaks_batch: size and step must be positive (got %d, %d)", size, step);
+    ARG_CHECK(cap == 0 || (pk_ctg && pk_first && pk_last && pk_gc && pk_signal), "wave_peaks_batch: NULL output");
+    *n_peaks = 0;
+    if (n_ctg == 0) return GAMS_CUDA_OK;
+    ARG_CHECK(seq_concat || seq_off[n_ctg] == seq_off[0], "wave_peaks_batch: seq_concat is NULL");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const int n_dev = (int)std::min<int64_t>((int64_t)ctx->devs.size(), n_ctg);
+    std::vector<int64_t> part((size_t)n_dev + 1);
+    int32_t rc = gams_cuda_partition(n_ctg, seq_off, n_dev, part.data());
+    if (rc) return rc;
+    std::vector<PeakSink> sinks((size_t)n_dev);
+    for (auto &sk : sinks) sk.coverage = coverage;
+    rc = for_each_device(ctx, n_dev, [&](int d) {
+        return wave_on_device(ctx, d, part[d], part[d + 1], seq_concat, seq_off, size, step, lag, threshold, influence, win_off,
+                              nullptr, nullptr, nullptr, &sinks[d]);
+    });
+    if (rc) return rc;
+    uint64_t total = 0;
+    for (auto &sk : sinks) total += sk.ctg.size();
+    *n_peaks = total;
+    if (total > cap) {
+        set_error("wave_peaks_batch: %llu peak records, room for %llu (n_peaks is set: call again with larger arrays)",
+                  (unsigned long long)total, (unsigned long long)cap);
+        return GAMS_CUDA_ECAP;
+    }
+    uint64_t o = 0;
+    for (int d = 0; d < n_dev; ++d) {
+        const PeakSink &sk = sinks[d];
+        for (size_t i = 0; i < sk.ctg.size(); ++i, ++o) {
+            pk_ctg[o] = sk.ctg[i] + (uint32_t)part[d];   // shards are contiguous ctg ranges: ctg order is kept
+            pk_first[o] = sk.first[i];
+            pk_last[o] = sk.last[i];
+            pk_gc[o] = sk.gc[i];
+            pk_signal[o] = sk.sig[i];
+        }
+    }
+    return GAMS_CUDA_OK;
 }
 
 GAMS_API int32_t gams_cuda_thresholding_batch(gams_cuda_ctx *ctx, int64_t n_series, const float *data,
@@ -862,6 +966,74 @@ GAMS_API int32_t gams_cuda_gc_ranges(gams_cuda_ctx *ctx, int64_t n_ctg, const ui
                                pd.scratch[4].as<uint32_t>(), pd.scratch[5].as<uint32_t>())))
         return rc;
     CUDA_TRY(cudaMemcpyAsync(gc_count, pd.scratch[5].p, (uint64_t)n_q * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return GAMS_CUDA_OK;
+}
+
+GAMS_API int32_t gams_cuda_peak_link_batch(gams_cuda_ctx *ctx, int64_t n_ctg, const uint8_t *seq_concat,
+                                           const uint64_t *seq_off, const int32_t *ctg_chr_start, int64_t n_pk,
+                                           const uint32_t *p_ctg, const int32_t *p_start, const int32_t *p_end,
+                                           const int8_t *p_signal, float *gc, int8_t *left_signal,
+                                           int32_t *left_wave_length, float *left_amplitude, int8_t *right_signal,
+                                           int32_t *right_wave_length, float *right_amplitude) {
+    ARG_CHECK(ctx && seq_off && ctg_chr_start && n_ctg >= 0 && n_pk >= 0, "peak_link_batch: bad argument");
+    if (n_pk == 0) return GAMS_CUDA_OK;
+    ARG_CHECK(p_ctg && p_start && p_end && p_signal && gc && left_signal && left_wave_length && left_amplitude && right_signal &&
+                  right_wave_length && right_amplitude,
+              "peak_link_batch: NULL peak/output pointer");
+    std::vector<uint32_t> from((size_t)n_pk), to((size_t)n_pk);
+    std::vector<int32_t> chr_end((size_t)std::max<int64_t>(n_ctg, 1));
+    for (int64_t c = 0; c < n_ctg; ++c) chr_end[c] = ctg_chr_start[c] + (int32_t)(seq_off[c + 1] - seq_off[c]) - 1;
+    for (int64_t i = 0; i < n_pk; ++i) {
+        const uint32_t c = p_ctg[i];
+        ARG_CHECK((int64_t)c < n_ctg, "peak_link_batch: peak %lld names ctg %u of %lld", (long long)i, c, (long long)n_ctg);
+        ARG_CHECK(i == 0 || p_ctg[i - 1] < c || (p_ctg[i - 1] == c && p_start[i - 1] <= p_start[i]),
+                  "peak_link_batch: peaks must be sorted by (ctg, start) (peak %lld)", (long long)i);
+        ARG_CHECK(p_start[i] >= ctg_chr_start[c] && p_end[i] >= p_start[i] && p_end[i] <= chr_end[c],
+                  "peak_link_batch: peak %lld (%d-%d) is not inside its ctg", (long long)i, p_start[i], p_end[i]);
+        from[i] = (uint32_t)(p_start[i] - ctg_chr_start[c]);      // parent.index(start) - 1 (utils.rs:151-155)
+        to[i] = (uint32_t)(p_end[i] - ctg_chr_start[c] + 1);
+    }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    PerDevice &pd = ctx->devs[0];
+    DeviceGuard g(pd.device);
+    uint8_t *d_seq;
+    uint64_t *d_off;
+    int32_t rc = upload_seq(pd, n_ctg, seq_concat, seq_off, &d_seq, &d_off);
+    if (rc) return rc;
+    const uint64_t np = (uint64_t)n_pk, in_bytes = np * 21 + (uint64_t)n_ctg * 8 + 64, out_bytes = np * 26 + 64;
+    if ((rc = pd.scratch[1].reserve(in_bytes))) return rc;
+    if ((rc = pd.scratch[2].reserve(out_bytes))) return rc;
+    cudaStream_t st = pd.stream;
+    uint8_t *ib = pd.scratch[1].as<uint8_t>();
+    uint32_t *d_ctg = reinterpret_cast<uint32_t *>(ib), *d_from = d_ctg + np, *d_to = d_from + np, *d_cnt = d_to + np;
+    int32_t *d_ps = reinterpret_cast<int32_t *>(d_cnt + np), *d_cs = d_ps + np, *d_ce = d_cs + n_ctg;
+    // p_end and the signals go behind the ctg tables
+    CUDA_TRY(cudaMemcpyAsync(d_ctg, p_ctg, np * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_from, from.data(), np * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_to, to.data(), np * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_ps, p_start, np * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_cs, ctg_chr_start, (uint64_t)n_ctg * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_ce, chr_end.data(), (uint64_t)n_ctg * 4, cudaMemcpyHostToDevice, st));
+    if ((rc = pd.scratch[3].reserve(np * 5 + 16))) return rc;
+    int32_t *d_pe = pd.scratch[3].as<int32_t>();
+    int8_t *d_psig = reinterpret_cast<int8_t *>(d_pe + np);
+    CUDA_TRY(cudaMemcpyAsync(d_pe, p_end, np * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_psig, p_signal, np, cudaMemcpyHostToDevice, st));
+    if ((rc = launch_gc_ranges(st, d_seq, d_off, n_ctg, n_pk, d_ctg, d_from, d_to, d_cnt))) return rc;
+    uint8_t *ob = pd.scratch[2].as<uint8_t>();
+    float *o_gc = reinterpret_cast<float *>(ob), *o_la = o_gc + np, *o_ra = o_la + np;
+    int32_t *o_ll = reinterpret_cast<int32_t *>(o_ra + np), *o_rl = o_ll + np;
+    int8_t *o_ls = reinterpret_cast<int8_t *>(o_rl + np), *o_rs = o_ls + np;
+    if ((rc = launch_peak_link(st, n_pk, d_ctg, d_ps, d_pe, d_psig, d_cnt, d_cs, d_ce, o_gc, o_ls, o_ll, o_la, o_rs, o_rl, o_ra)))
+        return rc;
+    CUDA_TRY(cudaMemcpyAsync(gc, o_gc, np * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(left_amplitude, o_la, np * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(right_amplitude, o_ra, np * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(left_wave_length, o_ll, np * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(right_wave_length, o_rl, np * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(left_signal, o_ls, np, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(right_signal, o_rs, np, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     return GAMS_CUDA_OK;
 }

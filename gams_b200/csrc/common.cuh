@@ -172,6 +172,7 @@ struct gams_cuda_wave_plan {
     gams::FusedTile *d_ftiles = nullptr;
     size_t n_ftiles = 0;
     std::vector<uint64_t> h_ftile_off;  // n_ctg+1: first Kernel-AB tile of each ctg
+    gams::DevBuf peak_tmp;           // tile counts / bases of the peak-merge kernels
     uint64_t launches = 0;
 };
 
@@ -220,6 +221,15 @@ int32_t launch_sw_rows(cudaStream_t st, const uint8_t *d_seq, const uint64_t *d_
                        int32_t *d_w_start, int32_t *d_w_end, int8_t *d_w_type, int32_t *d_w_dist, float *d_gc,
                        float *d_mean, float *d_sd, float *d_cv);
 GcGeom plan_gc_geometry(int32_t size, int32_t step);
+// peaks.cu
+bool peak_merge_is_runs(int32_t size, int32_t step, float coverage);
+int32_t launch_peak_runs(cudaStream_t st, const int8_t *d_sig, const float *d_gc, const uint64_t *d_win_off, int64_t n_ctg,
+                         uint64_t g0, uint64_t g1, int32_t size, int32_t step, uint64_t *d_tmp, uint64_t cap,
+                         uint32_t *pk_ctg, uint32_t *pk_first, uint32_t *pk_last, float *pk_gc, int8_t *pk_sig,
+                         uint64_t *d_n_peaks);
+int32_t launch_peak_link(cudaStream_t st, int64_t n_pk, const uint32_t *p_ctg, const int32_t *p_start, const int32_t *p_end,
+                         const int8_t *p_sig, const uint32_t *cnt, const int32_t *chr_start, const int32_t *chr_end, float *gc,
+                         int8_t *l_sig, int32_t *l_len, float *l_amp, int8_t *r_sig, int32_t *r_len, float *r_amp);
 // Kernel AB: bytes -> GC + signals in one pass (influence == 1, threshold >= 0, eligible geometry only)
 int fused_windows_per_tile(int32_t size, int32_t step, uint64_t lag);
 int32_t launch_gc_wave_fused(gams_cuda_wave_plan *p, cudaStream_t st, const uint8_t *d_seq, float threshold,

@@ -156,6 +156,37 @@ GAMS_API int32_t gams_cuda_wave_text(const char *chr_id, int32_t chr_start, int3
     return GAMS_CUDA_OK;
 }
 
+GAMS_API int32_t gams_cuda_wave_peaks_text(const char *chr_id, int32_t chr_start, int32_t size, int32_t step, int64_t n_pk,
+                                           const uint32_t *pk_first, const uint32_t *pk_last, const float *pk_gc,
+                                           const int8_t *pk_signal, char **text, size_t *text_len) {
+    if (!chr_id || !text || n_pk < 0 || size <= 0 || step <= 0 || (n_pk > 0 && (!pk_first || !pk_last || !pk_gc || !pk_signal))) {
+        set_error("wave_peaks_text: bad argument");
+        return GAMS_CUDA_EINVAL;
+    }
+    std::string out;
+    for (int64_t i = 0; i < n_pk; ++i) {
+        out += chr_id;
+        if (pk_last[i] != pk_first[i]) out += "(+)";   // a merged peak (wave.rs:196-203)
+        out += ':';
+        fmt_runlist(out, (int64_t)chr_start + (int64_t)pk_first[i] * step, (int64_t)chr_start + (int64_t)pk_last[i] * step + size - 1);
+        out += '\t';
+        fmt_f32(out, pk_gc[i]);
+        out += '\t';
+        out += std::to_string((int)pk_signal[i]);
+        out += '\n';
+    }
+    char *buf = (char *)malloc(out.size() + 1);
+    if (!buf) {
+        set_error("wave_peaks_text: out of memory");
+        return GAMS_CUDA_ENOMEM;
+    }
+    memcpy(buf, out.data(), out.size());
+    buf[out.size()] = 0;
+    *text = buf;
+    if (text_len) *text_len = out.size();
+    return GAMS_CUDA_OK;
+}
+
 GAMS_API void gams_cuda_free(void *p) { free(p); }
 
 // bincode 1.3 default config: little-endian, fixed-width ints, u64 length prefixes.

@@ -33,6 +33,7 @@ extern "C" {
 #define GAMS_CUDA_EINVAL (-1) /* bad argument (null pointer, size/step <= 0, lag == 0, ...)        */
 #define GAMS_CUDA_ECUDA (-2)  /* a CUDA runtime call or kernel failed; see gams_cuda_last_error()   */
 #define GAMS_CUDA_ENOMEM (-3) /* host or device allocation failed                                   */
+#define GAMS_CUDA_ECAP (-7)   /* caller-provided output arrays are too small; the needed count is reported        */
 #define GAMS_CUDA_ELAG (-4)   /* a ctg has fewer windows than lag: the reference panics here        */
                               /* (src/libs/stat.rs:30 indexes data[0..lag])                          */
 #define GAMS_CUDA_ENODEV (-5) /* no usable CUDA device                                              */
@@ -100,6 +101,34 @@ int32_t gams_cuda_wave_batch(gams_cuda_ctx *ctx, int64_t n_ctg, const uint8_t *s
                              float threshold, float influence, const uint64_t *win_off,
                              uint32_t *gc_count, float *gc, int8_t *signal);
 
+/* `gams wave` without --signal, src/cmd_gams/wave.rs:138-212: the same computation as gams_cuda_wave_batch followed by
+ * merge_ints (wave.rs:217-252) ON THE DEVICE, so that only the peaks cross PCIe (a few MB instead of 5 B per window).
+ * One record per line wave prints, ctgs in input order, lines of a ctg in the reference's order:
+ *   pk_ctg   : ctg index          pk_first / pk_last : first and last member window of the merged peak (pk_last == pk_first
+ *   for an unmerged window; the printed range is chr_start + pk_first*step .. chr_start + pk_last*step + size - 1)
+ *   pk_gc / pk_signal : GC fraction and signal of the FIRST member (what the reference prints, wave.rs:196-203)
+ * coverage: wave's --coverage.  The device merge needs every intersecting pair of windows to pass the coverage test
+ * (true for coverage <= 1, where size/intersect >= 1 always holds); otherwise GAMS_CUDA_EINVAL.
+ * cap: room in the pk_* arrays; *n_peaks receives the number of records; GAMS_CUDA_ECAP if it exceeds cap. */
+int32_t gams_cuda_wave_peaks_batch(gams_cuda_ctx *ctx, int64_t n_ctg, const uint8_t *seq_concat,
+                                   const uint64_t *seq_off, int32_t size, int32_t step, uint64_t lag,
+                                   float threshold, float influence, float coverage, const uint64_t *win_off,
+                                   uint64_t cap, uint32_t *pk_ctg, uint32_t *pk_first, uint32_t *pk_last,
+                                   float *pk_gc, int8_t *pk_signal, uint64_t *n_peaks);
+
+/* `gams peak`, src/cmd_gams/peak.rs:66-160, for peaks sorted by (ctg, start): GC content of each peak range
+ * (cache_gc_content, utils.rs:141-162: rounded to 4 decimals) and its links to the previous / next peak of the ctg:
+ *   left_wave_length  = start - prev_end + 1   (prev_end = the ctg's chr_start for the first peak)
+ *   left_amplitude    = |gc - prev_gc|         (0 for the first peak), left_signal = prev signal (own for the first)
+ *   right_*           : the same towards the next peak, with chr_end for the last one.
+ * p_start / p_end are 1-based inclusive chr positions inside the ctg. */
+int32_t gams_cuda_peak_link_batch(gams_cuda_ctx *ctx, int64_t n_ctg, const uint8_t *seq_concat,
+                                  const uint64_t *seq_off, const int32_t *ctg_chr_start, int64_t n_pk,
+                                  const uint32_t *p_ctg, const int32_t *p_start, const int32_t *p_end,
+                                  const int8_t *p_signal, float *gc, int8_t *left_signal, int32_t *left_wave_length,
+                                  float *left_amplitude, int8_t *right_signal, int32_t *right_wave_length,
+                                  float *right_amplitude);
+
 /* gams::thresholding_algo on caller-supplied series (stat.rs:16-56), batched: series s is
  * data[off[s] .. off[s+1]).  Same semantics as the signal part of gams_cuda_wave_batch. */
 int32_t gams_cuda_thresholding_batch(gams_cuda_ctx *ctx, int64_t n_series, const float *data,
@@ -134,6 +163,11 @@ int32_t gams_cuda_wave_signal_dev(gams_cuda_wave_plan *plan, void *stream, const
 int32_t gams_cuda_wave_dev(gams_cuda_wave_plan *plan, void *stream, const uint8_t *d_seq, float threshold,
                            float influence, uint32_t *d_gc_count, float *d_gc, float *d_filtered,
                            int8_t *d_signal);
+/* Peak merge (see gams_cuda_wave_peaks_batch) on device arrays: d_gc / d_signal as produced by gams_cuda_wave_dev;
+ * d_pk_* have room for cap records; *d_n_peaks (device) receives the record count (records past cap are not written). */
+int32_t gams_cuda_wave_peaks_dev(gams_cuda_wave_plan *plan, void *stream, const float *d_gc, const int8_t *d_signal,
+                                 float coverage, uint64_t cap, uint32_t *d_pk_ctg, uint32_t *d_pk_first,
+                                 uint32_t *d_pk_last, float *d_pk_gc, int8_t *d_pk_signal, uint64_t *d_n_peaks);
 /* 1 if gams_cuda_wave_dev would take the fused kernel for these statistics, else 0. */
 int32_t gams_cuda_wave_plan_fused(const gams_cuda_wave_plan *plan, float threshold, float influence);
 /* Kernel launches issued by the plan's _dev calls since creation (bench.py's gpu_launches). */
@@ -215,6 +249,10 @@ int32_t gams_cuda_lapper_blob_view(const uint8_t *blob, size_t blob_len, uint64_
 int32_t gams_cuda_wave_text(const char *chr_id, int32_t chr_start, int32_t size, int32_t step, int64_t n,
                             const float *gc, const int8_t *signal, float coverage, int32_t is_signal,
                             char **text, size_t *text_len);
+/* The same text from the records of gams_cuda_wave_peaks_batch (the records of ONE ctg, in order). */
+int32_t gams_cuda_wave_peaks_text(const char *chr_id, int32_t chr_start, int32_t size, int32_t step, int64_t n_pk,
+                                  const uint32_t *pk_first, const uint32_t *pk_last, const float *pk_gc,
+                                  const int8_t *pk_signal, char **text, size_t *text_len);
 void gams_cuda_free(void *p);
 
 #ifdef __cplusplus

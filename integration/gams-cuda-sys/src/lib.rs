@@ -65,6 +65,11 @@ extern "C" {
         plan: *mut gams_cuda_wave_plan, stream: *mut c_void, d_gc: *const f32, threshold: f32, influence: f32,
         d_filtered: *mut f32, d_signal: *mut i8,
     ) -> i32;
+    pub fn gams_cuda_wave_dev(
+        plan: *mut gams_cuda_wave_plan, stream: *mut c_void, d_seq: *const u8, threshold: f32, influence: f32,
+        d_gc_count: *mut u32, d_gc: *mut f32, d_filtered: *mut f32, d_signal: *mut i8,
+    ) -> i32;
+    pub fn gams_cuda_wave_plan_fused(plan: *const gams_cuda_wave_plan, threshold: f32, influence: f32) -> i32;
     pub fn gams_cuda_wave_plan_launches(plan: *const gams_cuda_wave_plan) -> u64;
 
     pub fn gams_cuda_gc_ranges(

@@ -295,6 +295,58 @@ def wave_text(chr_id: str, chr_start: int, size: int, step: int, gc, signal, cov
     return "".join(out)
 
 
+def wave_peak_records(size: int, step: int, gc, signal, coverage=0.2):
+    """The lines wave.rs:170-211 prints for one ctg, as records (first_window, last_window, gc, signal): a merged peak is
+    listed once, at its first member, with that member's gc/signal (wave.rs:196-203); an unmerged window has last == first.
+    Only defined when every merged component is one contiguous run (always for coverage <= 1)."""
+    n = len(gc)
+    wins = [(1 + k * step, k * step + size) for k in range(n)]
+    recs, seen = [], set()
+    merge_of = {}
+    merge_of.update(merge_ints([wins[k] for k in range(n) if signal[k] == 1], coverage))
+    merge_of.update(merge_ints([wins[k] for k in range(n) if signal[k] == -1], coverage))
+    for k in range(n):
+        if signal[k] == 0:
+            continue
+        rl = runlist(*wins[k])
+        if rl in merge_of:
+            m = merge_of[rl]
+            if m in seen:
+                continue
+            seen.add(m)
+            assert "," not in m, "component is not a single run"
+            a, b = (int(x) for x in m.split("-"))
+            recs.append(((a - 1) // step, (b - size) // step, np.float32(gc[k]), int(signal[k])))
+        else:
+            recs.append((k, k, np.float32(gc[k]), int(signal[k])))
+    return recs
+
+
+def peak_link(seq, chr_start: int, peaks):
+    """peak.rs:66-160 for one ctg.  peaks: [(start, end, signal)] sorted by start (1-based inclusive chr positions);
+    seq: the ctg's bytes.  -> list of dict(gc, left_signal, left_wave_length, left_amplitude, right_*)."""
+    chr_end = chr_start + len(seq) - 1
+    out = []
+    for s, e, sg in peaks:
+        sub = bytes(seq[s - chr_start:e - chr_start + 1])  # utils.rs:151-155
+        cnt = sum(sub.count(b) for b in (b"c", b"g", b"C", b"G"))
+        g = round_(np.float32(cnt) / np.float32(len(sub)), 4)  # bio gc_content, then utils.rs:161
+        out.append(dict(gc=g, signal=sg, start=s, end=e))
+    if not out:
+        return out
+    prev_sig, prev_gc, prev_end = out[0]["signal"], out[0]["gc"], chr_start  # peak.rs:112-114
+    for p in out:
+        p["left_signal"], p["left_wave_length"] = prev_sig, p["start"] - prev_end + 1
+        p["left_amplitude"] = np.float32(abs(np.float32(p["gc"] - prev_gc)))
+        prev_sig, prev_end, prev_gc = p["signal"], p["end"], p["gc"]
+    next_sig, next_gc, next_start = out[-1]["signal"], out[-1]["gc"], chr_end  # peak.rs:137-139
+    for p in reversed(out):
+        p["right_signal"], p["right_wave_length"] = next_sig, next_start - p["end"] + 1
+        p["right_amplitude"] = np.float32(abs(np.float32(p["gc"] - next_gc)))
+        next_sig, next_start, next_gc = p["signal"], p["start"], p["gc"]
+    return out
+
+
 WAVE_HEADER = "#range\tgc_content\tsignal\n"  # wave.rs:263-266
 
 

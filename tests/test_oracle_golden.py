@@ -185,3 +185,29 @@ def test_lapper_bincode_layout(orc):
 
 def test_fmt_f32(orc):
     assert [orc.fmt_f32(x) for x in (0.18, 0.5, 1.0, 0.0, 0.4321, float("nan"))] == ["0.18", "0.5", "1", "0", "0.4321", "NaN"]
+
+
+def test_wave_peak_records_reproduce_I_peaks_tsv(orc, s288c):
+    """The record form of wave's output (what the device merge returns) formats back to tests/S288c/I.peaks.tsv."""
+    seq = np.asarray(s288c["seq_I"])
+    cat, off = orc.pack_ctgs([seq])
+    _, _, gc, sig = orc.wave_batch(cat, off, 100, 10, 100, 3.0, 1.0)
+    recs = orc.wave_peak_records(100, 10, gc, sig, 0.2)
+    lines = []
+    for first, last, g, s in recs:
+        a, b = 1 + first * 10, 1 + last * 10 + 99
+        lines.append(f"I{'(+)' if last != first else ''}:{orc.runlist(a, b)}\t{orc.fmt_f32(g)}\t{s}\n")
+    assert (orc.WAVE_HEADER + "".join(lines)).encode() == bytes(s288c["peaks_tsv"])
+    assert len(recs) == 116
+
+
+def test_peak_link_oracle_small_case(orc):
+    """peak.rs:108-157 on a hand-checked case: first / last peak link to the ctg's ends with amplitude 0."""
+    seq = np.frombuffer(b"GGGGGGGGGGAAAAAAAAAAGCGCGCGCGCATATATATATCCCCCAAAAA", dtype=np.uint8)  # chr 101..150
+    out = orc.peak_link(seq, 101, [(101, 110, 1), (121, 130, -1), (141, 150, 1)])
+    assert [float(p["gc"]) for p in out] == [1.0, 1.0, 0.5]
+    assert [p["left_wave_length"] for p in out] == [1, 12, 12]
+    assert [p["right_wave_length"] for p in out] == [12, 12, 1]
+    assert [float(p["left_amplitude"]) for p in out] == [0.0, 0.0, 0.5]
+    assert [float(p["right_amplitude"]) for p in out] == [0.0, 0.5, 0.0]
+    assert [p["left_signal"] for p in out] == [1, 1, -1] and [p["right_signal"] for p in out] == [-1, 1, 1]

@@ -576,3 +576,85 @@ def test_count_overlaps_staged_adversarial(ctx, orc):
     torch.cuda.synchronize()
     assert int(out[0]) == int(ref[100_000])
     plan.close()
+
+
+# ------------------------------------------------------------------- peaks: device merge + linking
+def _records_of(pk, c):
+    m = pk["ctg"] == c
+    return list(zip(pk["first"][m].tolist(), pk["last"][m].tolist(), pk["gc"][m].view(np.uint32).tolist(), pk["signal"][m].tolist()))
+
+
+def test_wave_peaks_fixture_is_byte_identical_to_I_peaks_tsv(ctx, orc, s288c):
+    """wave.rs:170-252 on the device: the merged peak records of chr I format to tests/S288c/I.peaks.tsv byte for byte."""
+    ctgs = cut_ctgs(orc, s288c, 500000)
+    cat, off = orc.pack_ctgs([c[4] for c in ctgs])
+    pk = api.wave_peaks_batch(ctx, cat, off, 100, 10, 100, 3.0, 1.0, 0.2)
+    i = [k for k, c in enumerate(ctgs) if c[1] == "I"][0]
+    m = pk["ctg"] == i
+    text = orc.WAVE_HEADER + api.wave_peaks_text("I", 1, 100, 10, pk["first"][m], pk["last"][m], pk["gc"][m], pk["signal"][m])
+    assert text.encode() == bytes(s288c["peaks_tsv"])
+    # and the same text as the host-side merge of the per-window arrays, for every ctg
+    woff, _, gc, sig = api.wave_batch(ctx, cat, off, 100, 10, 100, 3.0, 1.0)
+    for k, c in enumerate(ctgs):
+        a, b = int(woff[k]), int(woff[k + 1])
+        mk = pk["ctg"] == k
+        assert api.wave_peaks_text(c[1], c[2], 100, 10, pk["first"][mk], pk["last"][mk], pk["gc"][mk], pk["signal"][mk]) == \
+            api.wave_text(c[1], c[2], 100, 10, gc[a:b], sig[a:b], 0.2)
+
+
+@pytest.mark.parametrize("size,step,lag,thr", [(100, 10, 100, 3.0), (100, 10, 100, 1.5), (100, 50, 30, 2.0), (100, 100, 10, 2.0),
+                                               (16, 1, 50, 2.5), (97, 13, 31, 2.0), (1000, 7, 100, 2.5)])
+def test_wave_peaks_match_oracle_merge(ctx, orc, size, step, lag, thr):
+    """Device run detection against merge_ints (union-find over intersecting same-sign windows) of the oracle, on ragged
+    ctgs with constant-GC stretches (long runs), for the fused and the two-kernel paths, several caps."""
+    g = synth.genome(900_000, seed=size + step)
+    flat = np.tile(np.frombuffer(b"ACATTTTTAT" * 5 + b"GCGCGCGCGATATATATATATATATATATATATATATATATATATATATA", dtype=np.uint8), 1200)
+    need = size + (lag + 2) * step
+    seqs = [g[:300_003], np.concatenate([flat[:60_000], g[300_003:360_000], flat[:30_000]]), g[400_000:400_000 + need], g[500_000:]]
+    cat, off = orc.pack_ctgs(seqs)
+    _, _, rgc, rsig = orc.wave_batch(cat, off, size, step, lag, thr, 1.0, threads=8)
+    rwoff = orc.win_offsets(off, size, step)
+    for cap in (None, 1):
+        pk = api.wave_peaks_batch(ctx, cat, off, size, step, lag, thr, 1.0, 0.2, cap=cap)
+        assert np.all(np.diff(pk["ctg"].astype(np.int64)) >= 0)
+        total = 0
+        for c in range(len(seqs)):
+            a, b = int(rwoff[c]), int(rwoff[c + 1])
+            ref = [(f, l, int(np.float32(x).view(np.uint32)), s) for f, l, x, s in orc.wave_peak_records(size, step, rgc[a:b], rsig[a:b], 0.2)]
+            got = _records_of(pk, c)
+            assert got == ref, f"ctg {c}: {len(got)} records vs {len(ref)}; first difference at {next((i for i, (x, y) in enumerate(zip(got, ref)) if x != y), None)}"
+            total += len(ref)
+        assert total == pk["ctg"].size and total > 0
+    # a coverage that rejects some intersecting pairs is not a run merge: the device path refuses it
+    if (size - 1) // step >= 1:
+        with pytest.raises(api.GamsCudaError) as e:
+            api.wave_peaks_batch(ctx, cat, off, size, step, lag, thr, 1.0, coverage=float(size))
+        assert e.value.code == -1
+
+
+def test_peak_link_matches_oracle(ctx, orc, s288c):
+    """`gams peak` (peak.rs:66-160): the peaks of I.peaks.tsv on the piece-100000 ctgs, plus synthetic corner cases."""
+    ctgs = [c for c in cut_ctgs(orc, s288c, 100000) if c[1] == "I"]
+    cat, off = orc.pack_ctgs([c[4] for c in ctgs])
+    chr_start = np.array([c[2] for c in ctgs], dtype=np.int32)
+    peaks = []
+    for line in bytes(s288c["peaks_tsv"]).decode().splitlines()[1:]:
+        rg, _, sg = line.split("\t")
+        _, _, a, b = orc.range_from_str(rg)
+        k = [i for i, c in enumerate(ctgs) if c[2] <= a <= c[3]][0]
+        if b <= ctgs[k][3]:
+            peaks.append((k, a, b, int(sg)))
+    peaks += [(0, 1, 1, 1), (0, 5, 5, -1), (1, ctgs[1][3], ctgs[1][3], 1)]   # single-base peaks at the very ends
+    peaks.sort()
+    p_ctg, p_s, p_e, p_sig = (np.array(x) for x in zip(*peaks))
+    got = api.peak_link_batch(ctx, cat, off, chr_start, p_ctg, p_s, p_e, p_sig)
+    for k, c in enumerate(ctgs):
+        m = np.flatnonzero(p_ctg == k)
+        ref = orc.peak_link(c[4], c[2], [(int(p_s[i]), int(p_e[i]), int(p_sig[i])) for i in m])
+        for j, i in enumerate(m):
+            for key in ("gc", "left_amplitude", "right_amplitude"):
+                assert np.float32(got[key][i]).view(np.uint32) == np.float32(ref[j][key]).view(np.uint32), (k, j, key, got[key][i], ref[j][key])
+            for key in ("left_signal", "right_signal", "left_wave_length", "right_wave_length"):
+                assert int(got[key][i]) == int(ref[j][key]), (k, j, key)
+    with pytest.raises(api.GamsCudaError):
+        api.peak_link_batch(ctx, cat, off, chr_start, p_ctg[::-1], p_s[::-1], p_e[::-1], p_sig[::-1])   # not sorted
