@@ -448,6 +448,26 @@ def main():
         L.gams_cuda_host_free(h_gc_ptr)
         L.gams_cuda_host_free(h_sig_ptr)
 
+        # the same through gams_cuda_wave_peaks_batch: what `gams wave` prints (merged peaks), so only the peak records come back
+        cap = max(4096, n_win // 16)
+        pk = [np.empty(cap, dtype=dt) for dt in (np.uint32, np.uint32, np.uint32, np.float32, np.int8)]
+        n_pk = C.c_uint64()
+
+        def peaks_step():
+            api.check(L.gams_cuda_wave_peaks_batch(ctx.handle, n_ctg, h_seq_ptr, seq_off.ctypes.data_as(C.c_void_p), SIZE, STEP, LAG,
+                                                   THRESHOLD, args.influence, 0.2, woff.ctypes.data_as(C.c_void_p), cap,
+                                                   *[a.ctypes.data_as(C.c_void_p) for a in pk], C.byref(n_pk)))
+
+        peaks_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            peaks_step()
+        dtp = max_over_ranks(time.perf_counter() - t0)
+        e2e["peaks_only"] = {"value": total_bases * n_e2e / dtp / 1e9, "unit": "Gbp/s", "ms_per_step": dtp / n_e2e * 1e3,
+                             "h2d_bytes_per_step": int(n_bases), "d2h_bytes_per_step": int(n_pk.value * 17 + 8),
+                             "peak_records": int(n_pk.value), "api": "gams_cuda_wave_peaks_batch (host pointers, pinned; merge_ints on the device)"}
+
     # ---- CPU baseline (rank 0, N = 1 only) --------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:

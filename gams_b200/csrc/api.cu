@@ -505,6 +505,11 @@ GAMS_API int32_t gams_cuda_wave_peaks_dev(gams_cuda_wave_plan *p, void *stream, 
 // ================================================================================ wave: host ====
 struct PeakSink {   // per-device results of gams_cuda_wave_peaks_batch
     float coverage = 0.0f;
+    // single device: records go straight into the caller's arrays (room for `cap`); otherwise into the vectors below
+    uint64_t cap = 0, n = 0;
+    uint32_t *o_ctg = nullptr, *o_first = nullptr, *o_last = nullptr;
+    float *o_gc = nullptr;
+    int8_t *o_sig = nullptr;
     std::vector<uint32_t> ctg, first, last;
     std::vector<float> gc;
     std::vector<int8_t> sig;
@@ -610,14 +615,22 @@ static int32_t wave_on_device(gams_cuda_ctx *ctx, int d, int64_t c0, int64_t c1,
                 return rc;
             CUDA_TRY(cudaMemcpyAsync(&n_pk, d_n, sizeof(uint64_t), cudaMemcpyDeviceToHost, pd.stream));
             CUDA_TRY(cudaStreamSynchronize(pd.stream));
+            sink->n = n_pk;
+            if (sink->o_ctg && n_pk > sink->cap) break;   // the caller's arrays are too small: report the count only
             if (n_pk <= cap) {
-                sink->ctg.resize(n_pk), sink->first.resize(n_pk), sink->last.resize(n_pk), sink->gc.resize(n_pk), sink->sig.resize(n_pk);
+                uint32_t *h_ctg = sink->o_ctg, *h_first = sink->o_first, *h_last = sink->o_last;
+                float *h_gc = sink->o_gc;
+                int8_t *h_sig = sink->o_sig;
+                if (!h_ctg) {
+                    sink->ctg.resize(n_pk), sink->first.resize(n_pk), sink->last.resize(n_pk), sink->gc.resize(n_pk), sink->sig.resize(n_pk);
+                    h_ctg = sink->ctg.data(), h_first = sink->first.data(), h_last = sink->last.data(), h_gc = sink->gc.data(), h_sig = sink->sig.data();
+                }
                 if (n_pk) {
-                    CUDA_TRY(cudaMemcpyAsync(sink->ctg.data(), k_ctg, n_pk * 4, cudaMemcpyDeviceToHost, pd.stream));
-                    CUDA_TRY(cudaMemcpyAsync(sink->first.data(), k_first, n_pk * 4, cudaMemcpyDeviceToHost, pd.stream));
-                    CUDA_TRY(cudaMemcpyAsync(sink->last.data(), k_last, n_pk * 4, cudaMemcpyDeviceToHost, pd.stream));
-                    CUDA_TRY(cudaMemcpyAsync(sink->gc.data(), k_gc, n_pk * 4, cudaMemcpyDeviceToHost, pd.stream));
-                    CUDA_TRY(cudaMemcpyAsync(sink->sig.data(), k_sig, n_pk, cudaMemcpyDeviceToHost, pd.stream));
+                    CUDA_TRY(cudaMemcpyAsync(h_ctg, k_ctg, n_pk * 4, cudaMemcpyDeviceToHost, pd.stream));
+                    CUDA_TRY(cudaMemcpyAsync(h_first, k_first, n_pk * 4, cudaMemcpyDeviceToHost, pd.stream));
+                    CUDA_TRY(cudaMemcpyAsync(h_last, k_last, n_pk * 4, cudaMemcpyDeviceToHost, pd.stream));
+                    CUDA_TRY(cudaMemcpyAsync(h_gc, k_gc, n_pk * 4, cudaMemcpyDeviceToHost, pd.stream));
+                    CUDA_TRY(cudaMemcpyAsync(h_sig, k_sig, n_pk, cudaMemcpyDeviceToHost, pd.stream));
                 }
                 break;
             }
@@ -670,19 +683,25 @@ GAMS_API int32_t gams_cuda_wave_peaks_batch(gams_cuda_ctx *ctx, int64_t n_ctg, c
     if (rc) return rc;
     std::vector<PeakSink> sinks((size_t)n_dev);
     for (auto &sk : sinks) sk.coverage = coverage;
+    if (n_dev == 1) {
+        PeakSink &sk = sinks[0];
+        sk.cap = cap, sk.o_ctg = pk_ctg, sk.o_first = pk_first, sk.o_last = pk_last, sk.o_gc = pk_gc, sk.o_sig = pk_signal;
+        if (!sk.o_ctg) sk.o_ctg = reinterpret_cast<uint32_t *>(&sk.n), sk.cap = 0;   // cap == 0: count only
+    }
     rc = for_each_device(ctx, n_dev, [&](int d) {
         return wave_on_device(ctx, d, part[d], part[d + 1], seq_concat, seq_off, size, step, lag, threshold, influence, win_off,
                               nullptr, nullptr, nullptr, &sinks[d]);
     });
     if (rc) return rc;
     uint64_t total = 0;
-    for (auto &sk : sinks) total += sk.ctg.size();
+    for (auto &sk : sinks) total += sk.n;
     *n_peaks = total;
     if (total > cap) {
         set_error("wave_peaks_batch: %llu peak records, room for %llu (n_peaks is set: call again with larger arrays)",
                   (unsigned long long)total, (unsigned long long)cap);
         return GAMS_CUDA_ECAP;
     }
+    if (n_dev == 1) return GAMS_CUDA_OK;   // already in the caller's arrays (ctg offset of the only shard is 0)
     uint64_t o = 0;
     for (int d = 0; d < n_dev; ++d) {
         const PeakSink &sk = sinks[d];
