@@ -117,6 +117,24 @@ def wave_batch(ctx: Context, seq_concat, seq_off, size=100, step=10, lag=100, th
     return woff, cnt, gc, sig
 
 
+# --------------------------------------------------------------- gen.rs:80-127
+def gen_ctgs(ctx: Context, seq_concat, chr_off, piece=500000, fill=50, min_=5000):
+    """`gams gen`'s region finding for a batch of chromosomes → (ctg_chr, ctg_start, ctg_end), 1-based inclusive."""
+    seq_concat, chr_off = _arr(seq_concat, np.uint8), _arr(chr_off, np.uint64)
+    L = load()
+    cap = 4096
+    while True:
+        c, s, e, n = np.empty(cap, dtype=np.uint32), np.empty(cap, dtype=np.int32), np.empty(cap, dtype=np.int32), C.c_uint64()
+        rc = L.gams_cuda_gen_ctgs(ctx.handle, chr_off.size - 1, _p(seq_concat), _p(chr_off), fill, min_, piece, cap, _p(c), _p(s),
+                                  _p(e), C.byref(n))
+        if rc == -7 and n.value > cap:
+            cap = int(n.value)
+            continue
+        check(rc)
+        k = int(n.value)
+        return c[:k], s[:k], e[:k]
+
+
 # --------------------------------------------------------------- wave.rs:138-252 (peaks only)
 def wave_peaks_batch(ctx: Context, seq_concat, seq_off, size=100, step=10, lag=100, threshold=3.0, influence=1.0,
                      coverage=0.2, cap=None):

@@ -961,6 +961,95 @@ static int32_t upload_seq(PerDevice &pd, int64_t n_ctg, const uint8_t *seq_conca
     return GAMS_CUDA_OK;
 }
 
+// ================================================================================ gen ===========
+GAMS_API int32_t gams_cuda_gen_ctgs(gams_cuda_ctx *ctx, int64_t n_chr, const uint8_t *seq_concat, const uint64_t *chr_off,
+                                    int32_t fill, int32_t min_len, int32_t piece, uint64_t cap, uint32_t *ctg_chr,
+                                    int32_t *ctg_start, int32_t *ctg_end, uint64_t *n_ctg) {
+    ARG_CHECK(ctx && chr_off && n_ctg && n_chr >= 0, "gen_ctgs: bad argument");
+    ARG_CHECK(fill >= 1 && min_len >= 0 && piece >= 1, "gen_ctgs: fill and piece must be >= 1, min >= 0");
+    ARG_CHECK(cap == 0 || (ctg_chr && ctg_start && ctg_end), "gen_ctgs: NULL output");
+    *n_ctg = 0;
+    if (n_chr == 0) return GAMS_CUDA_OK;
+    const uint64_t total = chr_off[n_chr] - chr_off[0];
+    ARG_CHECK(seq_concat || total == 0, "gen_ctgs: seq_concat is NULL");
+    for (int64_t c = 0; c < n_chr; ++c)
+        ARG_CHECK(chr_off[c + 1] >= chr_off[c] && chr_off[c + 1] - chr_off[c] < (1ull << 31), "gen_ctgs: chromosome %lld: bad length",
+                  (long long)c);
+    std::vector<uint64_t> rs, re;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        PerDevice &pd = ctx->devs[0];
+        DeviceGuard g(pd.device);
+        uint8_t *d_seq;
+        uint64_t *d_off;
+        int32_t rc = upload_seq(pd, n_chr, seq_concat, chr_off, &d_seq, &d_off);
+        if (rc) return rc;
+        const uint64_t tiles = (total + 8191) / 8192;
+        if ((rc = pd.scratch[1].reserve(sizeof(uint64_t) * (4 * (tiles + 1) + 2)))) return rc;
+        uint64_t *d_tmp = pd.scratch[1].as<uint64_t>(), *d_n = d_tmp + 4 * (tiles + 1);
+        uint64_t rcap = std::max<uint64_t>(total / 4096, 4096), n_runs = 0;
+        for (int attempt = 0; attempt < 2; ++attempt) {   // the first attempt sizes the run arrays
+            if ((rc = pd.scratch[2].reserve(rcap * 16))) return rc;
+            uint64_t *d_rs = pd.scratch[2].as<uint64_t>(), *d_re = d_rs + rcap;
+            if ((rc = launch_valid_runs(pd.stream, d_seq, total, d_off, n_chr, d_tmp, rcap, d_rs, d_re, d_n))) return rc;
+            CUDA_TRY(cudaMemcpyAsync(&n_runs, d_n, sizeof(uint64_t), cudaMemcpyDeviceToHost, pd.stream));
+            CUDA_TRY(cudaStreamSynchronize(pd.stream));
+            if (n_runs <= rcap) {
+                rs.resize(n_runs), re.resize(n_runs);
+                if (n_runs) {
+                    CUDA_TRY(cudaMemcpyAsync(rs.data(), d_rs, n_runs * 8, cudaMemcpyDeviceToHost, pd.stream));
+                    CUDA_TRY(cudaMemcpyAsync(re.data(), d_re, n_runs * 8, cudaMemcpyDeviceToHost, pd.stream));
+                    CUDA_TRY(cudaStreamSynchronize(pd.stream));
+                }
+                break;
+            }
+            rcap = n_runs;
+        }
+    }
+    // gen.rs:102-126 on the run list: fill(fill - 1), excise(min), pieces with the tail merged into the last one
+    uint64_t n_out = 0;
+    auto emit = [&](uint32_t c, int64_t s, int64_t e) {
+        if (n_out < cap) {
+            ctg_chr[n_out] = c;
+            ctg_start[n_out] = (int32_t)s;
+            ctg_end[n_out] = (int32_t)e;
+        }
+        ++n_out;
+    };
+    auto flush_span = [&](uint32_t c, int64_t s, int64_t e) {
+        if (e - s + 1 < min_len) return;                      // excise(min), gen.rs:104
+        int64_t pos = s;
+        bool any = false;
+        while (e - pos + 1 > piece) {                         // gen.rs:111-115
+            emit(c, pos, pos + piece - 1);
+            pos += piece;
+            any = true;
+        }
+        if (!any) emit(c, pos, e);                            // gen.rs:117-119
+        else if (n_out - 1 < cap) ctg_end[n_out - 1] = (int32_t)e;   // gen.rs:120-122: the remainder joins the last piece
+    };
+    int64_t c = 0, cur_s = 0, cur_e = -1;
+    bool open = false;
+    uint32_t cur_c = 0;
+    for (size_t k = 0; k < rs.size(); ++k) {
+        while (chr_off[c + 1] - chr_off[0] <= rs[k]) ++c;
+        const int64_t s = (int64_t)(rs[k] - (chr_off[c] - chr_off[0])) + 1, e = (int64_t)(re[k] - (chr_off[c] - chr_off[0])) + 1;
+        if (open && cur_c == (uint32_t)c && s - cur_e - 1 <= fill - 1) cur_e = e;   // fill
+        else {
+            if (open) flush_span(cur_c, cur_s, cur_e);
+            open = true, cur_c = (uint32_t)c, cur_s = s, cur_e = e;
+        }
+    }
+    if (open) flush_span(cur_c, cur_s, cur_e);
+    *n_ctg = n_out;
+    if (n_out > cap) {
+        set_error("gen_ctgs: %llu ctgs, room for %llu (n_ctg is set: call again with larger arrays)", (unsigned long long)n_out,
+                  (unsigned long long)cap);
+        return GAMS_CUDA_ECAP;
+    }
+    return GAMS_CUDA_OK;
+}
+
 GAMS_API int32_t gams_cuda_gc_ranges(gams_cuda_ctx *ctx, int64_t n_ctg, const uint8_t *seq_concat,
                                      const uint64_t *seq_off, int64_t n_q, const uint32_t *q_ctg,
                                      const uint32_t *q_from0, const uint32_t *q_to0_excl, uint32_t *gc_count) {

@@ -221,6 +221,9 @@ int32_t launch_sw_rows(cudaStream_t st, const uint8_t *d_seq, const uint64_t *d_
                        int32_t *d_w_start, int32_t *d_w_end, int8_t *d_w_type, int32_t *d_w_dist, float *d_gc,
                        float *d_mean, float *d_sd, float *d_cv);
 GcGeom plan_gc_geometry(int32_t size, int32_t step);
+// gen.cu
+int32_t launch_valid_runs(cudaStream_t st, const uint8_t *d_seq, uint64_t total, const uint64_t *d_chr_off, int64_t n_chr,
+                          uint64_t *d_tmp, uint64_t cap, uint64_t *d_run_start, uint64_t *d_run_end, uint64_t *d_n_runs);
 // peaks.cu
 bool peak_merge_is_runs(int32_t size, int32_t step, float coverage);
 int32_t launch_peak_runs(cudaStream_t st, const int8_t *d_sig, const float *d_gc, const uint64_t *d_win_off, int64_t n_ctg,

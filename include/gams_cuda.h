@@ -173,6 +173,19 @@ int32_t gams_cuda_wave_plan_fused(const gams_cuda_wave_plan *plan, float thresho
 /* Kernel launches issued by the plan's _dev calls since creation (bench.py's gpu_launches). */
 uint64_t gams_cuda_wave_plan_launches(const gams_cuda_wave_plan *plan);
 
+/* ---------------------------------------------------------------- gen ---------------------- */
+/* The region finding of `gams gen`, src/cmd_gams/gen.rs:80-127: bases other than A C G T a c g t are ambiguous
+ * (gen.rs:86-93); the valid regions are the complement with holes of less than `fill` bases filled (IntSpan::fill(fill-1),
+ * gen.rs:103) and regions shorter than `min_len` dropped (excise, gen.rs:104); each region is cut into pieces of `piece`
+ * bases with the remainder joined to the last piece (gen.rs:107-126).  The per-base scan runs on the device; the run list
+ * it returns (one entry per valid run) is processed on the host.
+ *  seq_concat / chr_off : the chromosomes back to back, n_chr+1 byte offsets
+ *  ctg_chr / ctg_start / ctg_end : per ctg its chromosome index and 1-based inclusive chr positions, in gen's order
+ *  cap : room in the output arrays; *n_ctg receives the number of ctgs; GAMS_CUDA_ECAP if it exceeds cap. */
+int32_t gams_cuda_gen_ctgs(gams_cuda_ctx *ctx, int64_t n_chr, const uint8_t *seq_concat, const uint64_t *chr_off,
+                           int32_t fill, int32_t min_len, int32_t piece, uint64_t cap, uint32_t *ctg_chr,
+                           int32_t *ctg_start, int32_t *ctg_end, uint64_t *n_ctg);
+
 /* ---------------------------------------------------------------- GC of ranges / sw -------- */
 /* Replaces gams::cache_gc_content without the rounding, src/libs/utils.rs:141-162 (bio
  * gc_content of an arbitrary sub-range of a ctg): query q covers 0-based bytes

@@ -658,3 +658,36 @@ def test_peak_link_matches_oracle(ctx, orc, s288c):
                 assert int(got[key][i]) == int(ref[j][key]), (k, j, key)
     with pytest.raises(api.GamsCudaError):
         api.peak_link_batch(ctx, cat, off, chr_start, p_ctg[::-1], p_s[::-1], p_e[::-1], p_sig[::-1])   # not sorted
+
+
+# ------------------------------------------------------------------- gen: ambiguity scan
+def test_gen_ctgs_fixture_matches_ctg_tsv(ctx, orc, s288c):
+    """tests/S288c/ctg.tsv: `gams gen --piece 100000` on the fixture → I:1-100000, I:100001-230218, Mito:1-85779."""
+    names = s288c["chr_names"].tolist()
+    cat, off = orc.pack_ctgs([s288c["seq_" + n] for n in names])
+    for piece in (100000, 500000, 30000):
+        c, s, e = api.gen_ctgs(ctx, cat, off, piece=piece)
+        ref = [(k, a, b) for k, n in enumerate(names) for a, b in orc.gen_ctgs(s288c["seq_" + n], piece=piece)]
+        assert list(zip(c.tolist(), s.tolist(), e.tolist())) == ref
+    c, s, e = api.gen_ctgs(ctx, cat, off, piece=100000)
+    assert [(names[k], a, b) for k, a, b in zip(c.tolist(), s.tolist(), e.tolist())] == [("I", 1, 100000), ("I", 100001, 230218), ("Mito", 1, 85779)]
+
+
+def test_gen_ctgs_synthetic_gaps(ctx, orc):
+    """N runs of every length around --fill, non-ACGT bytes of every value, runs touching chromosome ends and 32-byte
+    piece boundaries, chromosomes shorter than one load, an all-N and an empty chromosome."""
+    rng = np.random.default_rng(71)
+    g = synth.genome(700_000, seed=72).copy()
+    pos = np.sort(rng.choice(np.arange(1000, 690_000), 400, replace=False))
+    for k, p0 in enumerate(pos):
+        ln = [1, 2, 31, 32, 33, 48, 49, 50, 51, 64, 100, 4999, 5000][k % 13]
+        g[p0:p0 + ln] = ord("N") if k % 3 else rng.integers(0, 256, ln).astype(np.uint8)
+    g[:7] = ord("n")
+    g[-40:] = ord("-")
+    chrs = [g[:250_000], g[250_000:250_031], g[250_031:250_033], np.zeros(0, np.uint8), np.full(9000, ord("N"), np.uint8),
+            g[250_033:600_001], g[600_001:], synth.genome(6000, seed=73)]
+    cat, off = orc.pack_ctgs(chrs)
+    for piece, fill, mn in ((50_000, 50, 5000), (7_777, 1, 1), (500_000, 64, 0), (10_000, 33, 31)):
+        c, s, e = api.gen_ctgs(ctx, cat, off, piece=piece, fill=fill, min_=mn)
+        ref = [(k, a, b) for k, q in enumerate(chrs) for a, b in orc.gen_ctgs(q, piece=piece, fill=fill, min_=mn)]
+        assert list(zip(c.tolist(), s.tolist(), e.tolist())) == ref, (piece, fill, mn)
