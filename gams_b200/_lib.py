@@ -73,6 +73,7 @@ def load() -> C.CDLL:
         "gams_cuda_wave_dev": (i32, [vp, vp, vp, f32, f32, vp, vp, vp, vp]),
         "gams_cuda_wave_plan_fused": (i32, [vp, f32, f32]),
         "gams_cuda_wave_plan_launches": (u64, [vp]),
+        "gams_cuda_anno_coverage": (i32, [vp, i64, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp]),
         "gams_cuda_gen_ctgs": (i32, [vp, i64, vp, vp, i32, i32, i32, u64, vp, vp, vp, vp]),
         "gams_cuda_gc_ranges": (i32, [vp, i64, vp, vp, i64, vp, vp, vp, vp]),
         "gams_cuda_sw_batch": (i32, [vp, i64, vp, vp, vp, i64, vp, vp, vp, i32, i32, i32] + [vp] * 9),

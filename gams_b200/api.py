@@ -117,6 +117,17 @@ def wave_batch(ctx: Context, seq_concat, seq_off, size=100, step=10, lag=100, th
     return woff, cnt, gc, sig
 
 
+# --------------------------------------------------------------- anno.rs:128-139
+def anno_coverage(ctx: Context, run_start, run_end, run_off, q_chr, q_ctg_start, q_ctg_end, q_start, q_end) -> np.ndarray:
+    """`gams anno`: proportion of each range covered by the runlist of its chromosome inside its ctg (f32)."""
+    run_start, run_end, run_off = _arr(run_start, np.int32), _arr(run_end, np.int32), _arr(run_off, np.uint64)
+    q = [_arr(a, np.int32) for a in (q_chr, q_ctg_start, q_ctg_end, q_start, q_end)]
+    prop = np.empty(q[0].size, dtype=np.float32)
+    check(load().gams_cuda_anno_coverage(ctx.handle, run_off.size - 1, _p(run_start), _p(run_end), _p(run_off), q[0].size,
+                                         *[_p(a) for a in q], _p(prop)))
+    return prop
+
+
 # --------------------------------------------------------------- gen.rs:80-127
 def gen_ctgs(ctx: Context, seq_concat, chr_off, piece=500000, fill=50, min_=5000):
     """`gams gen`'s region finding for a batch of chromosomes → (ctg_chr, ctg_start, ctg_end), 1-based inclusive."""

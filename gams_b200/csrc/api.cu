@@ -961,6 +961,56 @@ static int32_t upload_seq(PerDevice &pd, int64_t n_ctg, const uint8_t *seq_conca
     return GAMS_CUDA_OK;
 }
 
+// ================================================================================ anno ==========
+GAMS_API int32_t gams_cuda_anno_coverage(gams_cuda_ctx *ctx, int64_t n_chr, const int32_t *run_start, const int32_t *run_end,
+                                         const uint64_t *run_off, int64_t n_q, const int32_t *q_chr, const int32_t *q_ctg_start,
+                                         const int32_t *q_ctg_end, const int32_t *q_start, const int32_t *q_end, float *prop) {
+    ARG_CHECK(ctx && run_off && n_chr >= 0 && n_q >= 0, "anno_coverage: bad argument");
+    if (n_q == 0) return GAMS_CUDA_OK;
+    ARG_CHECK(q_chr && q_ctg_start && q_ctg_end && q_start && q_end && prop, "anno_coverage: NULL query/output pointer");
+    ARG_CHECK(run_off[0] == 0, "anno_coverage: run_off[0] must be 0");
+    const uint64_t n_run = run_off[n_chr];
+    ARG_CHECK((run_start && run_end) || n_run == 0, "anno_coverage: NULL run arrays");
+    std::vector<int64_t> cum((size_t)std::max<uint64_t>(n_run, 1), 0);   // covered positions before each run of its chromosome
+    for (int64_t c = 0; c < n_chr; ++c) {
+        ARG_CHECK(run_off[c + 1] >= run_off[c] && run_off[c + 1] - run_off[c] < (1ull << 32), "anno_coverage: bad run_off at %lld", (long long)c);
+        int64_t acc = 0;
+        for (uint64_t k = run_off[c]; k < run_off[c + 1]; ++k) {
+            ARG_CHECK(run_end[k] >= run_start[k] && (k == run_off[c] || run_start[k] > run_end[k - 1]),
+                      "anno_coverage: runs of chromosome %lld must be sorted and disjoint (run %llu)", (long long)c, (unsigned long long)k);
+            cum[k] = acc;
+            acc += (int64_t)run_end[k] - run_start[k] + 1;
+        }
+    }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    PerDevice &pd = ctx->devs[0];
+    DeviceGuard g(pd.device);
+    int32_t rc;
+    const uint64_t nr = std::max<uint64_t>(n_run, 1), nq = (uint64_t)n_q;
+    if ((rc = pd.scratch[1].reserve(nr * 16 + (uint64_t)(n_chr + 1) * 8 + 64))) return rc;
+    if ((rc = pd.scratch[2].reserve(nq * 24 + 64))) return rc;
+    cudaStream_t st = pd.stream;
+    uint8_t *ib = pd.scratch[1].as<uint8_t>();
+    int64_t *d_cum = reinterpret_cast<int64_t *>(ib);
+    uint64_t *d_roff = reinterpret_cast<uint64_t *>(d_cum + nr);
+    int32_t *d_rs = reinterpret_cast<int32_t *>(d_roff + (n_chr + 1)), *d_re = d_rs + nr;
+    CUDA_TRY(cudaMemcpyAsync(d_cum, cum.data(), nr * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_roff, run_off, (uint64_t)(n_chr + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (n_run) {
+        CUDA_TRY(cudaMemcpyAsync(d_rs, run_start, n_run * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d_re, run_end, n_run * 4, cudaMemcpyHostToDevice, st));
+    }
+    int32_t *d_q = pd.scratch[2].as<int32_t>();
+    const int32_t *src[5] = {q_chr, q_ctg_start, q_ctg_end, q_start, q_end};
+    for (int k = 0; k < 5; ++k) CUDA_TRY(cudaMemcpyAsync(d_q + (uint64_t)k * nq, src[k], nq * 4, cudaMemcpyHostToDevice, st));
+    float *d_p = reinterpret_cast<float *>(d_q + 5 * nq);
+    if ((rc = launch_anno_coverage(st, d_rs, d_re, d_cum, d_roff, n_chr, n_q, d_q, d_q + nq, d_q + 2 * nq, d_q + 3 * nq, d_q + 4 * nq, d_p)))
+        return rc;
+    CUDA_TRY(cudaMemcpyAsync(prop, d_p, nq * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));   // cum is a local
+    return GAMS_CUDA_OK;
+}
+
 // ================================================================================ gen ===========
 GAMS_API int32_t gams_cuda_gen_ctgs(gams_cuda_ctx *ctx, int64_t n_chr, const uint8_t *seq_concat, const uint64_t *chr_off,
                                     int32_t fill, int32_t min_len, int32_t piece, uint64_t cap, uint32_t *ctg_chr,

@@ -221,6 +221,9 @@ int32_t launch_sw_rows(cudaStream_t st, const uint8_t *d_seq, const uint64_t *d_
                        int32_t *d_w_start, int32_t *d_w_end, int8_t *d_w_type, int32_t *d_w_dist, float *d_gc,
                        float *d_mean, float *d_sd, float *d_cv);
 GcGeom plan_gc_geometry(int32_t size, int32_t step);
+int32_t launch_anno_coverage(cudaStream_t st, const int32_t *run_start, const int32_t *run_end, const int64_t *run_cum,
+                             const uint64_t *run_off, int64_t n_chr, int64_t n_q, const int32_t *q_chr, const int32_t *q_ctg_start,
+                             const int32_t *q_ctg_end, const int32_t *q_start, const int32_t *q_end, float *prop);
 // gen.cu
 int32_t launch_valid_runs(cudaStream_t st, const uint8_t *d_seq, uint64_t total, const uint64_t *d_chr_off, int64_t n_chr,
                           uint64_t *d_tmp, uint64_t cap, uint64_t *d_run_start, uint64_t *d_run_end, uint64_t *d_n_runs);

@@ -220,3 +220,64 @@ int32_t launch_peak_link(cudaStream_t st, int64_t n_pk, const uint32_t *p_ctg, c
 }
 
 }  // namespace gams
+
+// ---- anno coverage (src/cmd_gams/anno.rs:128-139) -------------------------------------------------------
+// prop = |set(chr) ∩ ctg ∩ range| / |range| as f32: the set of a chromosome is a sorted list of disjoint inclusive runs;
+// with cum[k] = positions covered by the runs before k, the covered positions <= x are one binary search away.
+namespace gams {
+
+// positions <= x covered by runs [rs[k], re[k]], k = 0 .. n-1 (sorted, disjoint); cum[k] = sum of the lengths before k
+__device__ __forceinline__ int64_t covered_upto(const int32_t *__restrict__ rs, const int32_t *__restrict__ re,
+                                                const int64_t *__restrict__ cum, uint32_t n, int64_t x) {
+    uint32_t lo = 0, len = n;   // first run with start > x
+    while (len > 0) {
+        const uint32_t half = len >> 1;
+        const bool right = (int64_t)__ldg(rs + lo + half) <= x;
+        lo = right ? lo + half + 1 : lo;
+        len = right ? len - half - 1 : half;
+    }
+    if (lo == 0) return 0;
+    const uint32_t k = lo - 1;  // last run starting at or before x
+    const int64_t e = min((int64_t)__ldg(re + k), x);
+    return __ldg(cum + k) + (e - (int64_t)__ldg(rs + k) + 1);
+}
+
+__global__ void __launch_bounds__(256)
+anno_coverage_kernel(const int32_t *__restrict__ run_start, const int32_t *__restrict__ run_end,
+                     const int64_t *__restrict__ run_cum, const uint64_t *__restrict__ run_off, int64_t n_chr, int64_t n_q,
+                     const int32_t *__restrict__ q_chr, const int32_t *__restrict__ q_ctg_start,
+                     const int32_t *__restrict__ q_ctg_end, const int32_t *__restrict__ q_start,
+                     const int32_t *__restrict__ q_end, float *__restrict__ prop) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n_q; q += stride) {
+        const int32_t c = q_chr[q];
+        const int64_t s = q_start[q], e = q_end[q];
+        float p = 0.0f;
+        if (c >= 0 && c < n_chr && e >= s) {
+            const int64_t a = max(s, (int64_t)q_ctg_start[q]), b = min(e, (int64_t)q_ctg_end[q]);
+            int64_t cov = 0;
+            if (b >= a) {
+                const uint64_t o = run_off[c];
+                const uint32_t n = (uint32_t)(run_off[c + 1] - o);
+                cov = covered_upto(run_start + o, run_end + o, run_cum + o, n, b) -
+                      covered_upto(run_start + o, run_end + o, run_cum + o, n, a - 1);
+            }
+            p = __fdiv_rn(__ll2float_rn(cov), __ll2float_rn(e - s + 1));   // `cardinality() as f32 / cardinality() as f32`
+        }
+        prop[q] = p;
+    }
+}
+
+int32_t launch_anno_coverage(cudaStream_t st, const int32_t *run_start, const int32_t *run_end, const int64_t *run_cum,
+                             const uint64_t *run_off, int64_t n_chr, int64_t n_q, const int32_t *q_chr, const int32_t *q_ctg_start,
+                             const int32_t *q_ctg_end, const int32_t *q_start, const int32_t *q_end, float *prop) {
+    if (n_q == 0) return GAMS_CUDA_OK;
+    int64_t blocks = (n_q + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    anno_coverage_kernel<<<(unsigned)blocks, 256, 0, st>>>(run_start, run_end, run_cum, run_off, n_chr, n_q, q_chr, q_ctg_start,
+                                                           q_ctg_end, q_start, q_end, prop);
+    CUDA_TRY(cudaGetLastError());
+    return GAMS_CUDA_OK;
+}
+
+}  // namespace gams

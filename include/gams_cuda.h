@@ -173,6 +173,15 @@ int32_t gams_cuda_wave_plan_fused(const gams_cuda_wave_plan *plan, float thresho
 /* Kernel launches issued by the plan's _dev calls since creation (bench.py's gpu_launches). */
 uint64_t gams_cuda_wave_plan_launches(const gams_cuda_wave_plan *plan);
 
+/* ---------------------------------------------------------------- anno --------------------- */
+/* The proportion `gams anno` appends to each line, src/cmd_gams/anno.rs:128-139:
+ *   prop = |set(chr) ∩ [ctg_start, ctg_end] ∩ [start, end]| as f32 / |[start, end]| as f32
+ * set(chr): the runlist of the chromosome as sorted, disjoint, inclusive runs run_start/run_end[run_off[c] .. run_off[c+1]).
+ * q_chr < 0 or >= n_chr (the chromosome is not in the runlist file) gives 0 (anno.rs:127). */
+int32_t gams_cuda_anno_coverage(gams_cuda_ctx *ctx, int64_t n_chr, const int32_t *run_start, const int32_t *run_end,
+                                const uint64_t *run_off, int64_t n_q, const int32_t *q_chr, const int32_t *q_ctg_start,
+                                const int32_t *q_ctg_end, const int32_t *q_start, const int32_t *q_end, float *prop);
+
 /* ---------------------------------------------------------------- gen ---------------------- */
 /* The region finding of `gams gen`, src/cmd_gams/gen.rs:80-127: bases other than A C G T a c g t are ambiguous
  * (gen.rs:86-93); the valid regions are the complement with holes of less than `fill` bases filled (IntSpan::fill(fill-1),

@@ -347,6 +347,34 @@ def peak_link(seq, chr_start: int, peaks):
     return out
 
 
+def runlist_to_runs(text: str):
+    """IntSpan runlist "a-b,c,d-e" -> sorted disjoint inclusive runs [(a, b), (c, c), (d, e)] (as json2set yields them)."""
+    runs = []
+    for part in text.split(","):
+        if not part or part == "-":
+            continue
+        a, _, b = part.partition("-")
+        runs.append((int(a), int(b) if b else int(a)))
+    runs.sort()
+    merged = []
+    for a, b in runs:  # IntSpan coalesces overlapping and adjacent runs
+        if merged and a <= merged[-1][1] + 1:
+            merged[-1][1] = max(merged[-1][1], b)
+        else:
+            merged.append([a, b])
+    return [(a, b) for a, b in merged]
+
+
+def anno_prop(runs, ctg_start: int, ctg_end: int, start: int, end: int) -> np.float32:
+    """anno.rs:128-139: |set ∩ ctg ∩ range| as f32 / |range| as f32; runs = the chromosome's set, or None when the
+    chromosome is not in the runlist file (prop stays 0.0)."""
+    if runs is None:
+        return np.float32(0.0)
+    a, b = max(start, ctg_start), min(end, ctg_end)
+    cov = sum(max(0, min(b, re) - max(a, rs) + 1) for rs, re in runs) if b >= a else 0
+    return np.float32(cov) / np.float32(end - start + 1)
+
+
 WAVE_HEADER = "#range\tgc_content\tsignal\n"  # wave.rs:263-266
 
 

@@ -211,3 +211,11 @@ def test_peak_link_oracle_small_case(orc):
     assert [float(p["left_amplitude"]) for p in out] == [0.0, 0.0, 0.5]
     assert [float(p["right_amplitude"]) for p in out] == [0.0, 0.5, 0.0]
     assert [p["left_signal"] for p in out] == [1, 1, -1] and [p["right_signal"] for p in out] == [-1, 1, 1]
+
+
+def test_anno_prop_golden(orc, s288c):
+    """tests/cli.rs:457-481: `gams anno intergenic.json ctg.range.tsv -H` prints "85779\t0.0000" and "130218\t0.1072"."""
+    import json
+    sets = {k: orc.runlist_to_runs(v) for k, v in json.loads(bytes(s288c["intergenic_json"]).decode()).items()}
+    assert f"{orc.anno_prop(sets.get('Mito'), 1, 85779, 1, 85779):.4f}" == "0.0000"
+    assert f"{orc.anno_prop(sets.get('I'), 100001, 230218, 100001, 230218):.4f}" == "0.1072"

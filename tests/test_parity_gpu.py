@@ -691,3 +691,35 @@ def test_gen_ctgs_synthetic_gaps(ctx, orc):
         c, s, e = api.gen_ctgs(ctx, cat, off, piece=piece, fill=fill, min_=mn)
         ref = [(k, a, b) for k, q in enumerate(chrs) for a, b in orc.gen_ctgs(q, piece=piece, fill=fill, min_=mn)]
         assert list(zip(c.tolist(), s.tolist(), e.tolist())) == ref, (piece, fill, mn)
+
+
+# ------------------------------------------------------------------- anno coverage
+def test_anno_coverage(ctx, orc, s288c):
+    """anno.rs:128-139 against the oracle: the fixture's goldens (tests/cli.rs:477-478), then random ranges that start
+    before / end after their ctg, touch run ends exactly, lie in chromosomes without a set, and single positions."""
+    import json
+    js = json.loads(bytes(s288c["intergenic_json"]).decode())
+    names = sorted(js)
+    sets = [orc.runlist_to_runs(js[n]) for n in names]
+    rs = np.array([a for s in sets for a, _ in s], dtype=np.int32)
+    re_ = np.array([b for s in sets for _, b in s], dtype=np.int32)
+    roff = np.concatenate(([0], np.cumsum([len(s) for s in sets]))).astype(np.uint64)
+    ci = names.index("I")
+    mito = names.index("Mito") if "Mito" in names else -1
+    got = api.anno_coverage(ctx, rs, re_, roff, [mito, ci, ci], [1, 1, 100001], [85779, 100000, 230218], [1, 1, 100001], [85779, 100000, 230218])
+    assert f"{got[0]:.4f}" == "0.0000" and f"{got[2]:.4f}" == "0.1072"
+    rng = np.random.default_rng(61)
+    n_q = 200_000
+    q_chr = rng.integers(-1, len(names) + 1, n_q).astype(np.int32)
+    ctg_s = rng.integers(1, 400_000, n_q).astype(np.int32)
+    ctg_e = (ctg_s + rng.integers(0, 300_000, n_q)).astype(np.int32)
+    ends = np.concatenate([rs, re_])
+    q_s = np.where(rng.random(n_q) < 0.5, ends[rng.integers(0, ends.size, n_q)] + rng.integers(-2, 3, n_q), rng.integers(1, 700_000, n_q))
+    q_s = np.maximum(q_s, 1).astype(np.int32)
+    q_e = (q_s + np.where(rng.random(n_q) < 0.2, 0, rng.integers(0, 20_000, n_q))).astype(np.int32)
+    got = api.anno_coverage(ctx, rs, re_, roff, q_chr, ctg_s, ctg_e, q_s, q_e)
+    for i in rng.integers(0, n_q, 4000):
+        c = int(q_chr[i])
+        ref = orc.anno_prop(sets[c] if 0 <= c < len(sets) else None, int(ctg_s[i]), int(ctg_e[i]), int(q_s[i]), int(q_e[i]))
+        assert np.float32(got[i]).view(np.uint32) == np.float32(ref).view(np.uint32), (i, got[i], ref)
+    assert float(got.max()) <= 1.0 and float(got.min()) >= 0.0
