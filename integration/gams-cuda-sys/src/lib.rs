@@ -72,6 +72,32 @@ extern "C" {
     pub fn gams_cuda_wave_plan_fused(plan: *const gams_cuda_wave_plan, threshold: f32, influence: f32) -> i32;
     pub fn gams_cuda_wave_plan_launches(plan: *const gams_cuda_wave_plan) -> u64;
 
+    pub fn gams_cuda_wave_peaks_batch(
+        ctx: *mut gams_cuda_ctx, n_ctg: i64, seq_concat: *const u8, seq_off: *const u64, size: i32, step: i32, lag: u64,
+        threshold: f32, influence: f32, coverage: f32, win_off: *const u64, cap: u64, pk_ctg: *mut u32, pk_first: *mut u32,
+        pk_last: *mut u32, pk_gc: *mut f32, pk_signal: *mut i8, n_peaks: *mut u64,
+    ) -> i32;
+    pub fn gams_cuda_wave_peaks_dev(
+        plan: *mut gams_cuda_wave_plan, stream: *mut c_void, d_gc: *const f32, d_signal: *const i8, coverage: f32, cap: u64,
+        d_pk_ctg: *mut u32, d_pk_first: *mut u32, d_pk_last: *mut u32, d_pk_gc: *mut f32, d_pk_signal: *mut i8,
+        d_n_peaks: *mut u64,
+    ) -> i32;
+    pub fn gams_cuda_peak_link_batch(
+        ctx: *mut gams_cuda_ctx, n_ctg: i64, seq_concat: *const u8, seq_off: *const u64, ctg_chr_start: *const i32, n_pk: i64,
+        p_ctg: *const u32, p_start: *const i32, p_end: *const i32, p_signal: *const i8, gc: *mut f32, left_signal: *mut i8,
+        left_wave_length: *mut i32, left_amplitude: *mut f32, right_signal: *mut i8, right_wave_length: *mut i32,
+        right_amplitude: *mut f32,
+    ) -> i32;
+    pub fn gams_cuda_anno_coverage(
+        ctx: *mut gams_cuda_ctx, n_chr: i64, run_start: *const i32, run_end: *const i32, run_off: *const u64, n_q: i64,
+        q_chr: *const i32, q_ctg_start: *const i32, q_ctg_end: *const i32, q_start: *const i32, q_end: *const i32,
+        prop: *mut f32,
+    ) -> i32;
+    pub fn gams_cuda_gen_ctgs(
+        ctx: *mut gams_cuda_ctx, n_chr: i64, seq_concat: *const u8, chr_off: *const u64, fill: i32, min_len: i32, piece: i32,
+        cap: u64, ctg_chr: *mut u32, ctg_start: *mut i32, ctg_end: *mut i32, n_ctg: *mut u64,
+    ) -> i32;
+
     pub fn gams_cuda_gc_ranges(
         ctx: *mut gams_cuda_ctx, n_ctg: i64, seq_concat: *const u8, seq_off: *const u64, n_q: i64, q_ctg: *const u32,
         q_from0: *const u32, q_to0_excl: *const u32, gc_count: *mut u32,
@@ -108,6 +134,10 @@ extern "C" {
     pub fn gams_cuda_wave_text(
         chr_id: *const c_char, chr_start: i32, size: i32, step: i32, n: i64, gc: *const f32, signal: *const i8,
         coverage: f32, is_signal: i32, text: *mut *mut c_char, text_len: *mut usize,
+    ) -> i32;
+    pub fn gams_cuda_wave_peaks_text(
+        chr_id: *const c_char, chr_start: i32, size: i32, step: i32, n_pk: i64, pk_first: *const u32, pk_last: *const u32,
+        pk_gc: *const f32, pk_signal: *const i8, text: *mut *mut c_char, text_len: *mut usize,
     ) -> i32;
     pub fn gams_cuda_free(p: *mut c_void);
 }
