@@ -522,11 +522,57 @@ static int32_t wave_on_device(gams_cuda_ctx *ctx, int d, int64_t c0, int64_t c1,
     if (c1 <= c0) return GAMS_CUDA_OK;
     PerDevice &pd = ctx->devs[d];
     DeviceGuard g(pd.device);
+    trace_stage("wave: enter");
+    int32_t rc;
+    // 1. start the upload: slices of ~64 MB of sequence go out on copy_in before anything else is done, so that the
+    //    plan (host loops over every tile + table uploads, ~7 ms for a human-size genome) is built while the link is busy
+    const int64_t n = c1 - c0;
+    const uint64_t base0 = seq_off[c0], nb = seq_off[c1] - base0;
+    if ((rc = pd.scratch[0].reserve(((nb + 31) & ~31ull) + 32))) return rc;
+    uint8_t *d_seq = pd.scratch[0].as<uint8_t>();
+    const uint64_t slice_bytes = 64ull << 20;
+    std::vector<int64_t> cut{0};
+    for (int64_t c = 0; c < n; ++c) {
+        if (seq_off[c0 + c + 1] < seq_off[c0 + c]) {
+            set_error("wave_batch: seq_off not monotone at %lld", (long long)(c0 + c));
+            return GAMS_CUDA_EINVAL;
+        }
+        if (seq_off[c0 + c + 1] - seq_off[c0 + cut.back()] >= slice_bytes || c + 1 == n) cut.push_back(c + 1);
+    }
+    const size_t n_sl = cut.size() - 1;
+    std::vector<cudaEvent_t> ev_in(n_sl), ev_k(n_sl);
+    for (size_t k = 0; k < n_sl; ++k) {
+        CUDA_TRY(cudaEventCreateWithFlags(&ev_in[k], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&ev_k[k], cudaEventDisableTiming));
+    }
+    struct EvGuard {
+        std::vector<cudaEvent_t> &a, &b;
+        cudaStream_t in;
+        ~EvGuard() {
+            cudaStreamSynchronize(in);   // an early error return must not leave copies from the caller's buffer in flight
+            for (auto e : a) cudaEventDestroy(e);
+            for (auto e : b) cudaEventDestroy(e);
+        }
+    } ev_guard{ev_in, ev_k, pd.copy_in};
+    const uint8_t *h_seq = seq_concat + base0;
+    auto enqueue_h2d = [&](size_t k) -> int32_t {
+        const uint64_t b0 = seq_off[c0 + cut[k]] - base0, b1 = seq_off[c0 + cut[k + 1]] - base0;
+        if (b1 > b0) CUDA_TRY(cudaMemcpyAsync(d_seq + b0, h_seq + b0, b1 - b0, cudaMemcpyHostToDevice, pd.copy_in));
+        CUDA_TRY(cudaEventRecord(ev_in[k], pd.copy_in));
+        return GAMS_CUDA_OK;
+    };
+    // ~10 ms of link time up front (the plan's own table uploads must not queue behind the whole genome)
+    const size_t n_pre = std::min<size_t>(n_sl, 8);
+    for (size_t k = 0; k < n_pre; ++k)
+        if ((rc = enqueue_h2d(k))) return rc;
+    trace_stage("wave: H2D enqueued");
+    // 2. the plan
     gams_cuda_wave_plan *plan = nullptr;
-    int32_t rc = gams_cuda_wave_plan_create(ctx, d, c1 - c0, seq_off + c0, size, step, lag, &plan);
+    rc = gams_cuda_wave_plan_create(ctx, d, c1 - c0, seq_off + c0, size, step, lag, &plan);
     if (rc) return rc;
+    trace_stage("wave: plan_create");
     std::unique_ptr<gams_cuda_wave_plan, void (*)(gams_cuda_wave_plan *)> guard(plan, gams_cuda_wave_plan_destroy);
-    const uint64_t nb = plan->total_bases, nwn = plan->win.total;
+    const uint64_t nwn = plan->win.total;
     if (nwn != win_off[c1] - win_off[c0]) {
         set_error("wave_batch: win_off does not match gams_cuda_wave_win_offsets for size=%d step=%d", size, step);
         return GAMS_CUDA_EINVAL;
@@ -540,47 +586,26 @@ static int32_t wave_on_device(gams_cuda_ctx *ctx, int d, int64_t c0, int64_t c1,
                   (unsigned long long)plan->win.min_len, (unsigned long long)lag);
         return GAMS_CUDA_ELAG;
     }
-    if ((rc = pd.scratch[0].reserve(gams_cuda_wave_plan_seq_capacity(plan)))) return rc;
     const bool want_sig = signal || sink;   // sink: the per-window arrays stay on the device, only peak records come back
     if ((rc = pd.scratch[1].reserve(std::max<uint64_t>(nwn, 1) * sizeof(float)))) return rc;
     if (gc_count && (rc = pd.scratch[2].reserve(std::max<uint64_t>(nwn, 1) * sizeof(uint32_t)))) return rc;
     if (want_sig && (rc = pd.scratch[3].reserve(std::max<uint64_t>(nwn, 1)))) return rc;
     const bool need_filt = want_sig && !(influence == 1.0f && lag <= ZS_MAX_TILED_LAG);
     if (need_filt && (rc = pd.scratch[4].reserve(std::max<uint64_t>(nwn, 1) * sizeof(float)))) return rc;
-    uint8_t *d_seq = pd.scratch[0].as<uint8_t>();
     float *d_gc = pd.scratch[1].as<float>();
     uint32_t *d_cnt = gc_count ? pd.scratch[2].as<uint32_t>() : nullptr;
     int8_t *d_sig = want_sig ? pd.scratch[3].as<int8_t>() : nullptr;
     float *d_filt = need_filt ? pd.scratch[4].as<float>() : nullptr;
-    // Pipeline over slices of ~64 MB of sequence: H2D of slice k+1, kernels of slice k and D2H of slice k-1
-    // run concurrently on three streams (PCIe is full duplex; the kernels are far shorter than either copy).
-    const int64_t n = c1 - c0;
-    const uint64_t slice_bytes = 64ull << 20;
-    std::vector<int64_t> cut{0};
-    for (int64_t c = 0; c < n; ++c)
-        if (plan->h_seq_off[c + 1] - plan->h_seq_off[cut.back()] >= slice_bytes || c + 1 == n) cut.push_back(c + 1);
-    const size_t n_sl = cut.size() - 1;
-    std::vector<cudaEvent_t> ev_in(n_sl), ev_k(n_sl);
-    for (size_t k = 0; k < n_sl; ++k) {
-        CUDA_TRY(cudaEventCreateWithFlags(&ev_in[k], cudaEventDisableTiming));
-        CUDA_TRY(cudaEventCreateWithFlags(&ev_k[k], cudaEventDisableTiming));
-    }
-    struct EvGuard {
-        std::vector<cudaEvent_t> &a, &b;
-        ~EvGuard() {
-            for (auto e : a) cudaEventDestroy(e);
-            for (auto e : b) cudaEventDestroy(e);
-        }
-    } ev_guard{ev_in, ev_k};
+    // 3. kernels of slice k as soon as it has arrived, D2H of its results behind them: three streams, PCIe both ways
+    //    (the kernels are far shorter than either copy)
     const uint64_t wo = win_off[c0];
-    const uint8_t *h_seq = seq_concat + seq_off[c0];
     CUDA_TRY(cudaStreamSynchronize(pd.stream));  // plan tables were uploaded on pd.stream
+    for (size_t k = n_pre; k < n_sl; ++k)
+        if ((rc = enqueue_h2d(k))) return rc;
+    trace_stage("wave: reserve");
     for (size_t k = 0; k < n_sl; ++k) {
         const int64_t a = cut[k], b = cut[k + 1];
-        const uint64_t b0 = plan->h_seq_off[a], b1 = plan->h_seq_off[b];
         const uint64_t w0 = plan->h_win_off[a], w1 = plan->h_win_off[b];
-        if (b1 > b0) CUDA_TRY(cudaMemcpyAsync(d_seq + b0, h_seq + b0, b1 - b0, cudaMemcpyHostToDevice, pd.copy_in));
-        CUDA_TRY(cudaEventRecord(ev_in[k], pd.copy_in));
         CUDA_TRY(cudaStreamWaitEvent(pd.stream, ev_in[k], 0));
         if (want_sig && wave_fused_ok(plan, threshold, influence)) {
             if ((rc = launch_gc_wave_fused(plan, pd.stream, d_seq, threshold, d_cnt, d_gc, d_sig, pd.d_zstats, a, b))) return rc;
@@ -598,6 +623,15 @@ static int32_t wave_on_device(gams_cuda_ctx *ctx, int d, int64_t c0, int64_t c1,
                 CUDA_TRY(cudaMemcpyAsync(gc_count + wo + w0, d_cnt + w0, (w1 - w0) * sizeof(uint32_t), cudaMemcpyDeviceToHost, pd.copy_out));
             if (signal) CUDA_TRY(cudaMemcpyAsync(signal + wo + w0, d_sig + w0, w1 - w0, cudaMemcpyDeviceToHost, pd.copy_out));
         }
+    }
+    trace_stage("wave: enqueue slices");
+    if (trace_on()) {
+        cudaStreamSynchronize(pd.copy_in);
+        trace_stage("wave: H2D done");
+        cudaStreamSynchronize(pd.stream);
+        trace_stage("wave: kernels done");
+        cudaStreamSynchronize(pd.copy_out);
+        trace_stage("wave: D2H done");
     }
     if (sink) {
         // peak merge on the device; two attempts at most: the first sizes the record arrays
@@ -638,8 +672,11 @@ static int32_t wave_on_device(gams_cuda_ctx *ctx, int d, int64_t c0, int64_t c1,
         }
     }
     CUDA_TRY(cudaStreamSynchronize(pd.copy_out));
+    trace_stage("wave: sync copy_out");
     CUDA_TRY(cudaStreamSynchronize(pd.stream));
-    (void)nb;
+    trace_stage("wave: all streams idle");
+    guard.reset();
+    trace_stage("wave: plan_destroy");
     return GAMS_CUDA_OK;
 }
 
