@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--influence", type=float, default=INFLUENCE)
     ap.add_argument("--skip-count", action="store_true")
+    ap.add_argument("--skip-sw", action="store_true")
+    ap.add_argument("--sw-features", type=float, default=1e6, help="features of the sw section (configs[2])")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
@@ -485,18 +487,92 @@ def main():
     overlap = None if args.skip_count else bench_count(args, ctx, L, dev, rank, world, g_off, barrier, max_over_ranks,
                                                      sum_over_ranks, hbm_peak, peak_src)
 
+    sw = None
+    if rank == 0 and not args.skip_sw and not args.skip_e2e:
+        sw = bench_sw(args, ctx, L, dev)
+
     if rank == 0:
         line = {
             "metric": "gc_wave_throughput", "value": value, "unit": "Gbp/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "u8->u32 counts, f32 statistics", "data": "synthetic",
             "config": workload_config(args), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roof_main, "kernels": kern, "path": "fused (gc_wave_fused_kernel)" if fused else "gc_window_kernel + zscore kernel", "cpu_baseline": cpu, "overlap": overlap, "parity_spot_check": parity,
+            "roofline": roof_main, "kernels": kern, "path": "fused (gc_wave_fused_kernel)" if fused else "gc_window_kernel + zscore kernel", "cpu_baseline": cpu, "overlap": overlap, "sw": sw, "parity_spot_check": parity,
             "windows_per_step": int(n_win), "bases_per_rank": int(n_bases),
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_sw(args, ctx, L, dev):
+    """configs[2]: `gams sw` around 10^6 point features on an Arabidopsis-scale genome (120 Mbp), end to end through
+    gams_cuda_sw_batch (host arrays in, the rows of sw.rs:141-191 out), with the oracle timed on a sample beside it."""
+    import torch
+
+    from gams_b200 import api, synth
+    from oracle import oracle as orc
+
+    chr_lengths = [30_427_671, 19_698_289, 23_459_830, 18_585_056, 26_975_502, 154_478, 366_924]   # Atha, 119.7 Mbp
+    n = int(sum(chr_lengths))
+    seq_off, ctgs = synth.ctg_layout(chr_lengths, PIECE)
+    h_seq = synth.genome_torch(n, seed=7, device=dev, capacity=n + 64)[:n].cpu().numpy()
+    rng = np.random.default_rng(8)
+    lens = np.diff(seq_off.astype(np.int64))
+    chr_start = np.array([c[1] for c in ctgs], dtype=np.int32)
+    n_feat = int(args.sw_features)
+    f_ctg = np.sort(rng.choice(len(ctgs), n_feat, p=lens / lens.sum())).astype(np.uint32)
+    f_s = (chr_start[f_ctg] + (rng.random(n_feat) * lens[f_ctg]).astype(np.int64)).astype(np.int32)
+    f_e = np.minimum(f_s + rng.integers(0, 3, n_feat), chr_start[f_ctg] + lens[f_ctg] - 1).astype(np.int32)
+    # pinned host buffers, as for the wave path: the rows are 1.2 GB
+    cap = n_feat * 41
+    p_seq = pinned(n, L)
+    as_np(p_seq, n, np.uint8)[:] = h_seq
+    specs = [("start", np.int32), ("end", np.int32), ("type", np.int8), ("dist", np.int32), ("gc", np.float32), ("mean", np.float32),
+             ("sd", np.float32), ("cv", np.float32)]
+    ptrs = {k: pinned(cap * np.dtype(dt).itemsize, L) for k, dt in specs}
+    row_off = np.zeros(n_feat + 1, dtype=np.uint64)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+
+    def sw_step():
+        api.check(L.gams_cuda_sw_batch(ctx.handle, len(ctgs), p_seq, vp(seq_off), vp(chr_start), n_feat, vp(f_ctg), vp(f_s), vp(f_e),
+                                       100, 20, 500, vp(row_off), ptrs["start"], ptrs["end"], ptrs["type"], ptrs["dist"], ptrs["gc"],
+                                       ptrs["mean"], ptrs["sd"], ptrs["cv"]))
+
+    sw_step()   # warm-up (allocations)
+    reps = 3
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        sw_step()
+    dt = (time.perf_counter() - t0) / reps
+    r = {k: as_np(ptrs[k], int(row_off[-1]), dt_) for k, dt_ in specs}
+    r["row_off"] = row_off
+    n_rows = int(r["gc"].size)
+    # oracle on a sample of the features (single thread: sw::proc_ctg's per-feature loop, cache lookups replaced by recomputation)
+    k = min(n_feat, 20_000)
+    pick = rng.choice(n_feat, k, replace=False)
+    t0 = time.perf_counter()
+    rows_cpu, ok = 0, True
+    for f in pick:
+        c = int(f_ctg[f])
+        ref = orc.sw_feature(h_seq[int(seq_off[c]):int(seq_off[c + 1])], int(chr_start[c]), int(chr_start[c] + lens[c] - 1),
+                             int(f_s[f]), int(f_e[f]))
+        rows_cpu += len(ref["gc"])
+        if f in pick[:300]:
+            a, b = int(r["row_off"][f]), int(r["row_off"][f + 1])
+            ok &= bool(b - a == len(ref["gc"]) and all(np.array_equal(r[key][a:b].view(np.uint32), ref[key].view(np.uint32))
+                                                      for key in ("gc", "mean", "sd", "cv")))
+    dt_cpu = time.perf_counter() - t0
+    for pp in list(ptrs.values()) + [p_seq]:
+        L.gams_cuda_host_free(pp)
+    return {"workload": "Arabidopsis-scale synthetic genome (119.7 Mbp) + sw --size 100 --max 20 --resize 500 around "
+                        f"{n_feat} point features (configs[2])",
+            "value": n_rows / dt, "unit": "sw rows/s", "features_per_s": n_feat / dt, "rows": n_rows, "ms_per_step": dt * 1e3,
+            "h2d_bytes_per_step": int(n + n_feat * 12), "d2h_bytes_per_step": int(n_rows * 29 + (n_feat + 1) * 8),
+            "api": "gams_cuda_sw_batch (host pointers, pinned; copies and row layout inside)",
+            "bit_exact_sample": ok,
+            "cpu_baseline": {"value": rows_cpu / dt_cpu, "unit": "sw rows/s", "cores": 1, "kind": "port",
+                             "sample": f"{k} of the features through the oracle (ctypes call per feature)"}}
 
 
 def bench_count(args, ctx, L, dev, rank, world, g_off, barrier, max_over_ranks, sum_over_ranks, hbm_peak, peak_src):

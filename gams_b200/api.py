@@ -257,9 +257,9 @@ def sw_batch(ctx: Context, seq_concat, seq_off, ctg_chr_start, f_ctg, f_start, f
     nf = f_ctg.size
     cap = nf * (1 + 2 * max_)
     row_off = np.zeros(nf + 1, dtype=np.uint64)
-    ws, we, wd = (np.zeros(cap, dtype=np.int32) for _ in range(3))
-    wt = np.zeros(cap, dtype=np.int8)
-    gc, gm, gs, gv = (np.zeros(cap, dtype=np.float32) for _ in range(4))
+    ws, we, wd = (np.empty(cap, dtype=np.int32) for _ in range(3))
+    wt = np.empty(cap, dtype=np.int8)
+    gc, gm, gs, gv = (np.empty(cap, dtype=np.float32) for _ in range(4))
     check(load().gams_cuda_sw_batch(ctx.handle, seq_off.size - 1, _p(seq_concat), _p(seq_off), _p(ctg_chr_start), nf,
                                     _p(f_ctg), _p(f_start), _p(f_end), size, max_, resize, _p(row_off), _p(ws), _p(we),
                                     _p(wt), _p(wd), _p(gc), _p(gm), _p(gs), _p(gv)))

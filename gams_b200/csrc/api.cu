@@ -1241,6 +1241,7 @@ GAMS_API int32_t gams_cuda_sw_batch(gams_cuda_ctx *ctx, int64_t n_ctg, const uin
                                     float *gc_cv) {
     ARG_CHECK(ctx && seq_off && ctg_chr_start && row_off && n_ctg >= 0 && n_feat >= 0, "sw_batch: bad argument");
     ARG_CHECK(size > 0 && max >= 0 && resize > 0, "sw_batch: size/resize must be positive and max >= 0");
+    trace_stage("sw: enter");
     row_off[0] = 0;
     if (n_feat == 0) return GAMS_CUDA_OK;
     ARG_CHECK(f_ctg && f_start && f_end && w_start && w_end && w_type && w_dist && gc && gc_mean && gc_stddev && gc_cv,
@@ -1260,6 +1261,7 @@ GAMS_API int32_t gams_cuda_sw_batch(gams_cuda_ctx *ctx, int64_t n_ctg, const uin
         row_off[f + 1] = row_off[f] + 1 + (uint64_t)nl + (uint64_t)nr;
     }
     const uint64_t n_rows = row_off[n_feat];
+    trace_stage("sw: row counts (host)");
     std::lock_guard<std::mutex> lk(ctx->mu);
     PerDevice &pd = ctx->devs[0];
     DeviceGuard g(pd.device);
@@ -1267,6 +1269,7 @@ GAMS_API int32_t gams_cuda_sw_batch(gams_cuda_ctx *ctx, int64_t n_ctg, const uin
     uint64_t *d_off;
     int32_t rc = upload_seq(pd, n_ctg, seq_concat, seq_off, &d_seq, &d_off);
     if (rc) return rc;
+    trace_stage("sw: upload_seq");
     // inputs: chr_start | f_ctg | f_start | f_end | row_off ; outputs: 4 x i32/f32 x 2 + i8
     const uint64_t in_bytes = (uint64_t)n_ctg * 4 + (uint64_t)n_feat * 12 + (uint64_t)(n_feat + 1) * 8 + 64;
     if ((rc = pd.scratch[1].reserve(in_bytes))) return rc;
@@ -1290,6 +1293,7 @@ GAMS_API int32_t gams_cuda_sw_batch(gams_cuda_ctx *ctx, int64_t n_ctg, const uin
     if ((rc = launch_sw_rows(st, d_seq, d_off, d_chr_start, n_feat, d_f_ctg, d_f_start, d_f_end, size, max, resize,
                              d_row_off, n_rows, d_ws, d_we, d_wt, d_wd, d_g, d_m, d_s, d_c)))
         return rc;
+    trace_stage("sw: kernel", st, true);
     CUDA_TRY(cudaMemcpyAsync(w_start, d_ws, n_rows * 4, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(w_end, d_we, n_rows * 4, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(w_dist, d_wd, n_rows * 4, cudaMemcpyDeviceToHost, st));
@@ -1299,5 +1303,6 @@ GAMS_API int32_t gams_cuda_sw_batch(gams_cuda_ctx *ctx, int64_t n_ctg, const uin
     CUDA_TRY(cudaMemcpyAsync(gc_cv, d_c, n_rows * 4, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(w_type, d_wt, n_rows, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    trace_stage("sw: D2H");
     return GAMS_CUDA_OK;
 }

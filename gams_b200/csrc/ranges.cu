@@ -86,79 +86,122 @@ __device__ __forceinline__ void center_resize_idx(int32_t psize, int32_t s, int3
     oe = r;
 }
 
-__global__ void __launch_bounds__(256)
+// #GC bytes in absolute byte range [b0, b1) of seq, by ONE thread (windows are ~100 bytes: 26 aligned words)
+__device__ __forceinline__ uint32_t thread_gc_count(const uint8_t *__restrict__ seq, uint64_t b0, uint64_t b1) {
+    if (b1 <= b0) return 0;
+    const uint64_t w_first = b0 >> 2, w_last = (b1 - 1) >> 2;
+    const uint32_t *words = reinterpret_cast<const uint32_t *>(seq);
+    const uint32_t m_first = 0xFFFFFFFFu << (8u * (uint32_t)(b0 & 3u));
+    const uint32_t m_last = 0xFFFFFFFFu >> (8u * (3u - (uint32_t)((b1 - 1) & 3u)));
+    if (w_first == w_last) return __popc(gc_flags(__ldg(words + w_first)) & m_first & m_last);
+    uint32_t c = __popc(gc_flags(__ldg(words + w_first)) & m_first) + __popc(gc_flags(__ldg(words + w_last)) & m_last);
+#pragma unroll 4
+    for (uint64_t w = w_first + 1; w < w_last; ++w) c += __popc(gc_flags(__ldg(words + w)));
+    return c;
+}
+
+// One thread per row; a CTA owns 256 consecutive rows and finds their features through a shared-memory copy of the
+// row offsets of the (at most 257) features that can own them.  (A warp per row with a 20-step binary search in global
+// memory per row, the first version of this kernel, spent 96 ms on the 4.1e7 rows of C3 waiting on that search.)
+constexpr int SW_THREADS = 256;
+constexpr int SW_MAXSUB = 8;   // flank sub-windows kept in registers (resize / size + 1; more are recomputed)
+
+__global__ void __launch_bounds__(SW_THREADS)
 sw_rows_kernel(const uint8_t *__restrict__ seq, const uint64_t *__restrict__ seq_off,
                const int32_t *__restrict__ chr_start, int64_t n_feat, const uint32_t *__restrict__ f_ctg,
                const int32_t *__restrict__ f_start, const int32_t *__restrict__ f_end, int32_t size, int32_t maxd,
                int32_t resize, const uint64_t *__restrict__ row_off, uint64_t n_rows, int32_t *__restrict__ w_start,
                int32_t *__restrict__ w_end, int8_t *__restrict__ w_type, int32_t *__restrict__ w_dist,
                float *__restrict__ gc, float *__restrict__ gmean, float *__restrict__ gsd, float *__restrict__ gcv) {
-    const int lane = threadIdx.x & 31;
-    const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    for (uint64_t row = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n_rows; row += warps) {
-        int64_t lo = 0, hi = n_feat;  // last feature with row_off[f] <= row
+    __shared__ uint64_t roff[SW_THREADS + 2];
+    __shared__ int64_t f0_s;
+    const uint64_t r0 = (uint64_t)blockIdx.x * SW_THREADS;
+    if (threadIdx.x == 0) {
+        int64_t lo = 0, hi = n_feat;  // last feature with row_off[f] <= r0
         while (hi - lo > 1) {
             const int64_t mid = (lo + hi) >> 1;
-            if (row_off[mid] <= row) lo = mid; else hi = mid;
+            if (row_off[mid] <= r0) lo = mid; else hi = mid;
         }
-        const int64_t f = lo;
-        const int32_t k = (int32_t)(row - row_off[f]);
-        const uint32_t c = f_ctg[f];
-        const uint64_t so = seq_off[c];
-        const int32_t psize = (int32_t)(seq_off[c + 1] - so);
-        const int32_t p_start = chr_start[c];
-        // index space of the parent: idx = chr - p_start + 1
-        int32_t ms, me;
-        center_resize_idx(psize, f_start[f] - p_start + 1, f_end[f] - p_start + 1, size, ms, me);
-        int32_t nl = (ms - 1) / size;  // L windows need sw_start = ms - d*size >= 1
-        if (nl > maxd) nl = maxd;
-        if (nl < 0) nl = 0;
-        int32_t ws, we, type, dist;
-        if (k == 0) { ws = ms; we = me; type = 0; dist = 0; }
-        else if (k <= nl) { dist = k; type = 1; we = ms - 1 - (k - 1) * size; ws = we - size + 1; }
-        else { dist = k - nl; type = 2; ws = me + 1 + (dist - 1) * size; we = ws + size - 1; }
+        f0_s = lo;
+    }
+    __syncthreads();
+    const int64_t f0 = f0_s;
+    // every feature has at least one row, so rows r0 .. r0+255 belong to features f0 .. f0+255
+    for (int i = threadIdx.x; i < SW_THREADS + 2; i += SW_THREADS) roff[i] = row_off[min(f0 + i, n_feat)];
+    __syncthreads();
+    const uint64_t row = r0 + threadIdx.x;
+    if (row >= n_rows) return;
+    int lo = 0, hi = SW_THREADS + 1;   // last i with roff[i] <= row
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (roff[mid] <= row) lo = mid; else hi = mid;
+    }
+    const int64_t f = f0 + lo;
+    const int32_t k = (int32_t)(row - roff[lo]);
+    const uint32_t c = f_ctg[f];
+    const uint64_t so = seq_off[c];
+    const int32_t psize = (int32_t)(seq_off[c + 1] - so);
+    const int32_t p_start = chr_start[c];
+    // index space of the parent: idx = chr - p_start + 1
+    int32_t ms, me;
+    center_resize_idx(psize, f_start[f] - p_start + 1, f_end[f] - p_start + 1, size, ms, me);
+    int32_t nl = (ms - 1) / size;  // L windows need sw_start = ms - d*size >= 1
+    if (nl > maxd) nl = maxd;
+    if (nl < 0) nl = 0;
+    int32_t ws, we, type, dist;
+    if (k == 0) { ws = ms; we = me; type = 0; dist = 0; }
+    else if (k <= nl) { dist = k; type = 1; we = ms - 1 - (k - 1) * size; ws = we - size + 1; }
+    else { dist = k - nl; type = 2; ws = me + 1 + (dist - 1) * size; we = ws + size - 1; }
+    const uint32_t cnt = thread_gc_count(seq, so + (uint64_t)(ws - 1), so + (uint64_t)we);
+    const float g = round4(__fdiv_rn(__uint2float_rn(cnt), __uint2float_rn((uint32_t)(we - ws + 1))));
 
-        const uint32_t cnt = warp_gc_count(seq, so + (uint64_t)(ws - 1), so + (uint64_t)we, lane);
-        const float g = round4(__fdiv_rn(__uint2float_rn(cnt), __uint2float_rn((uint32_t)(we - ws + 1))));
-
-        // flank statistics: utils.rs:189-213
-        int32_t rs, re;
-        center_resize_idx(psize, ws, we, resize, rs, re);
-        const int32_t span = re - rs + 1;
-        const int32_t nsub = (span >= size) ? (span - size) / size + 1 : 0;
-        const float fsz = __uint2float_rn((uint32_t)size);
-        float s = 0.0f;
+    // flank statistics: utils.rs:189-213
+    int32_t rs, re;
+    center_resize_idx(psize, ws, we, resize, rs, re);
+    const int32_t span = re - rs + 1;
+    const int32_t nsub = (span >= size) ? (span - size) / size + 1 : 0;
+    const float fsz = __uint2float_rn((uint32_t)size);
+    float gsub[SW_MAXSUB];
+    float s = 0.0f;
+    for (int32_t j = 0; j < nsub; ++j) {
+        const uint64_t b0 = so + (uint64_t)(rs - 1) + (uint64_t)j * size;
+        const float gj = round4(__fdiv_rn(__uint2float_rn(thread_gc_count(seq, b0, b0 + size)), fsz));
+#pragma unroll
+        for (int q = 0; q < SW_MAXSUB; ++q)
+            if (q == j) gsub[q] = gj;
+        s = __fadd_rn(s, gj);
+    }
+    const float flen = __uint2float_rn((uint32_t)nsub);
+    const float m = __fdiv_rn(s, flen);
+    float qq = 0.0f;
+    if (nsub <= SW_MAXSUB) {
+#pragma unroll
+        for (int q = 0; q < SW_MAXSUB; ++q)
+            if (q < nsub) {
+                const float d = __fsub_rn(gsub[q], m);
+                qq = __fadd_rn(qq, __fmul_rn(d, d));
+            }
+    } else {
         for (int32_t j = 0; j < nsub; ++j) {
             const uint64_t b0 = so + (uint64_t)(rs - 1) + (uint64_t)j * size;
-            const uint32_t cj = warp_gc_count(seq, b0, b0 + size, lane);
-            s = __fadd_rn(s, round4(__fdiv_rn(__uint2float_rn(cj), fsz)));
-        }
-        const float flen = __uint2float_rn((uint32_t)nsub);
-        const float m = __fdiv_rn(s, flen);
-        float qq = 0.0f;
-        for (int32_t j = 0; j < nsub; ++j) {
-            const uint64_t b0 = so + (uint64_t)(rs - 1) + (uint64_t)j * size;
-            const uint32_t cj = warp_gc_count(seq, b0, b0 + size, lane);
-            const float d = __fsub_rn(round4(__fdiv_rn(__uint2float_rn(cj), fsz)), m);
+            const float d = __fsub_rn(round4(__fdiv_rn(__uint2float_rn(thread_gc_count(seq, b0, b0 + size)), fsz)), m);
             qq = __fadd_rn(qq, __fmul_rn(d, d));
         }
-        const float sd = __fsqrt_rn(__fdiv_rn(qq, __fsub_rn(flen, 1.0f)));
-        float cv;
-        if (m == 0.0f || m == 1.0f) cv = 0.0f;
-        else if (m <= 0.5f) cv = __fdiv_rn(sd, m);
-        else cv = __fdiv_rn(sd, __fsub_rn(1.0f, m));
-
-        if (lane == 0) {
-            w_start[row] = p_start + ws - 1;
-            w_end[row] = p_start + we - 1;
-            w_type[row] = (int8_t)type;
-            w_dist[row] = dist;
-            gc[row] = g;
-            gmean[row] = round4(m);
-            gsd[row] = round4(sd);
-            gcv[row] = round4(cv);
-        }
     }
+    const float sd = __fsqrt_rn(__fdiv_rn(qq, __fsub_rn(flen, 1.0f)));
+    float cv;
+    if (m == 0.0f || m == 1.0f) cv = 0.0f;
+    else if (m <= 0.5f) cv = __fdiv_rn(sd, m);
+    else cv = __fdiv_rn(sd, __fsub_rn(1.0f, m));
+
+    w_start[row] = p_start + ws - 1;
+    w_end[row] = p_start + we - 1;
+    w_type[row] = (int8_t)type;
+    w_dist[row] = dist;
+    gc[row] = g;
+    gmean[row] = round4(m);
+    gsd[row] = round4(sd);
+    gcv[row] = round4(cv);
 }
 
 int32_t launch_sw_rows(cudaStream_t st, const uint8_t *d_seq, const uint64_t *d_seq_off, const int32_t *d_chr_start,
@@ -167,9 +210,12 @@ int32_t launch_sw_rows(cudaStream_t st, const uint8_t *d_seq, const uint64_t *d_
                        int32_t *d_w_start, int32_t *d_w_end, int8_t *d_w_type, int32_t *d_w_dist, float *d_gc,
                        float *d_mean, float *d_sd, float *d_cv) {
     if (n_rows == 0) return GAMS_CUDA_OK;
-    uint64_t blocks = (n_rows + 7) / 8;
-    if (blocks > 148ull * 64) blocks = 148ull * 64;
-    sw_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_seq, d_seq_off, d_chr_start, n_feat, d_f_ctg, d_f_start, d_f_end,
+    const uint64_t blocks = (n_rows + SW_THREADS - 1) / SW_THREADS;
+    if (blocks >= (1ull << 31)) {
+        set_error("sw_batch: too many rows for one launch");
+        return GAMS_CUDA_EINVAL;
+    }
+    sw_rows_kernel<<<(unsigned)blocks, SW_THREADS, 0, st>>>(d_seq, d_seq_off, d_chr_start, n_feat, d_f_ctg, d_f_start, d_f_end,
                                                      size, max, resize, d_row_off, n_rows, d_w_start, d_w_end, d_w_type,
                                                      d_w_dist, d_gc, d_mean, d_sd, d_cv);
     CUDA_TRY(cudaGetLastError());
