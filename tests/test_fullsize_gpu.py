@@ -118,9 +118,64 @@ def _wave_properties(ctx, orc, n_bases, chr_lengths, seed, n_spot):
     return d_seq, seq_off, ctgs
 
 
+def _peaks_properties(ctx, orc, d_seq, seq_off, n_bases):
+    """Full-size checks of the device peak merge against a torch restatement of the run rule and the host-side merge."""
+    dev = d_seq.device
+    st = torch.cuda.current_stream().cuda_stream
+    L = _lib.load()
+    plan = api.WavePlan(ctx, seq_off, 100, 10, 100)
+    n = plan.total_windows
+    d_gc = torch.empty(n, dtype=torch.float32, device=dev)
+    d_sig = torch.empty(n, dtype=torch.int8, device=dev)
+    plan.wave(st, d_seq, 3.0, 1.0, d_gc, d_sig)
+    cap = n // 16
+    pk = [torch.empty(cap, dtype=dt, device=dev) for dt in (torch.int32, torch.int32, torch.int32, torch.float32, torch.int8)]
+    d_n = torch.zeros(1, dtype=torch.int64, device=dev)
+    _lib.check(L.gams_cuda_wave_peaks_dev(plan._h, st, d_gc.data_ptr(), d_sig.data_ptr(), 0.2, cap, *[t.data_ptr() for t in pk],
+                                          d_n.data_ptr()))
+    torch.cuda.synchronize()
+    n_pk = int(d_n.item())
+    assert 0 < n_pk <= cap
+    ctg, first, last, gcf, sgn = (t[:n_pk] for t in pk)
+    woff = torch.as_tensor(api.win_offsets(seq_off, 100, 10).astype(np.int64), device=dev)
+    # (P5) records are the run starts: a signal window with no same-sign signal among the 9 windows before it in its ctg
+    idx = torch.arange(n, device=dev)
+    cid = torch.searchsorted(woff, idx, right=True) - 1
+    is_start = d_sig != 0
+    for d in range(1, 10):
+        same = torch.zeros(n, dtype=torch.bool, device=dev)
+        same[d:] = (d_sig[d:] == d_sig[:-d]) & (cid[d:] == cid[:-d])
+        is_start &= ~same
+    starts = torch.nonzero(is_start).flatten()
+    assert starts.numel() == n_pk
+    g_first = woff[ctg.long()] + first.long()
+    assert torch.equal(g_first, starts), "records are not the run starts in window order"
+    assert torch.equal(sgn, d_sig[starts]) and torch.equal(gcf.view(torch.int32), d_gc[starts].view(torch.int32))
+    # (P6) every run ends on a window of its sign, stays inside its ctg, and is followed by 9 windows without that sign
+    g_last = woff[ctg.long()] + last.long()
+    assert bool((last >= first).all()) and torch.equal(d_sig[g_last], sgn) and bool((g_last < woff[ctg.long() + 1]).all())
+    for d in range(1, 10):
+        nxt = torch.clamp(g_last + d, max=n - 1)
+        inside = (g_last + d) < woff[ctg.long() + 1]
+        assert not bool(((d_sig[nxt] == sgn) & inside).any())
+    # ... and the text of a few ctgs equals the host-side merge_ints of the per-window arrays
+    rng = np.random.default_rng(3)
+    h_ctg = ctg.cpu().numpy()
+    for c in rng.choice(seq_off.size - 1, 6, replace=False):
+        a, b = int(woff[c]), int(woff[c + 1])
+        m = h_ctg == c
+        got = api.wave_peaks_text("X", 1, 100, 10, first.cpu().numpy()[m], last.cpu().numpy()[m], gcf.cpu().numpy()[m], sgn.cpu().numpy()[m])
+        assert got == api.wave_text("X", 1, 100, 10, d_gc[a:b].cpu().numpy(), d_sig[a:b].cpu().numpy(), 0.2)
+    plan.close()
+    del d_gc, d_sig, pk, idx, cid, is_start
+    torch.cuda.empty_cache()
+
+
 def test_c4_human_scale_wave(ctx, orc):
     n = 3_100_000_000
-    _wave_properties(ctx, orc, n, synth.human_like_lengths(n), seed=20240613, n_spot=12)
+    d_seq, seq_off, _ = _wave_properties(ctx, orc, n, synth.human_like_lengths(n), seed=20240613, n_spot=12)
+    torch.cuda.empty_cache()
+    _peaks_properties(ctx, orc, d_seq, seq_off, n)
     torch.cuda.empty_cache()
 
 
@@ -129,6 +184,15 @@ def test_c3_arabidopsis_scale_wave_and_sw(ctx, orc):
     n = int(sum(chr_lengths))
     d_seq, seq_off, ctgs = _wave_properties(ctx, orc, n, chr_lengths, seed=7, n_spot=6)
     h_seq = d_seq[:n].cpu().numpy()
+    # `gams gen` on the whole genome (7 chromosomes, N gaps of 1-49 bases every 250 kbp, --fill 50): the device scan + host
+    # fill / excise / piece cut against the oracle's numpy restatement, chromosome by chromosome
+    chr_off = np.concatenate(([0], np.cumsum(chr_lengths))).astype(np.uint64)
+    for piece, fill in ((PIECE, 50), (PIECE, 10)):
+        gc_, gs_, ge_ = api.gen_ctgs(ctx, h_seq, chr_off, piece=piece, fill=fill, min_=5000)
+        ref = [(k, a, b) for k in range(len(chr_lengths))
+               for a, b in orc.gen_ctgs(h_seq[int(chr_off[k]):int(chr_off[k + 1])], piece=piece, fill=fill, min_=5000)]
+        assert list(zip(gc_.tolist(), gs_.tolist(), ge_.tolist())) == ref
+    assert len(ref) > len(ctgs)   # --fill 10 leaves the longer N gaps open: more, shorter regions
     # 10^6 point features uniform over the genome; chr coordinates per ctg as `gen` assigns them
     rng = np.random.default_rng(8)
     lens = np.diff(seq_off.astype(np.int64))
