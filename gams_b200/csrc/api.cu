@@ -881,8 +881,7 @@ GAMS_API int32_t gams_cuda_count_overlaps(gams_cuda_ctx *ctx, int64_t n_seg, con
             CUDA_TRY(cudaMemcpyAsync(d_sp, stops + iv_off[0], n_iv * 4, cudaMemcpyHostToDevice, st));
         }
         trace_stage("count: reserve + index H2D", st, true);
-        if ((rc = build_count_index(plan, st, d_st, d_sp))) return rc;
-        trace_stage("count: build_count_index", st, true);
+        // (the index tables - compact form or rank nodes - are built by the first launch that needs them)
         cudaEvent_t ev_idx;
         CUDA_TRY(cudaEventCreateWithFlags(&ev_idx, cudaEventDisableTiming));
         CUDA_TRY(cudaEventRecord(ev_idx, st));
