@@ -192,6 +192,7 @@ struct gams_cuda_count_plan {
     const uint32_t *cidx_starts = nullptr, *cidx_stops = nullptr;
     bool cidx_valid = false;
     size_t cpar_off = 0;
+    size_t st_smem = 0;              // dynamic shared memory of the staged kernel: the largest staged segment
     int mode = 0;                    // 0 ranked (default), 1 plain binary search (GAMS_CUDA_COUNT_MODE)
     uint64_t launches = 0;
 };

@@ -184,6 +184,7 @@ constexpr int ST_NB = 8192;          // buckets per endpoint array
 constexpr int ST_MAX_N = 24576;      // elements per endpoint array
 constexpr int ST_CHUNK = 16384;      // queries per work item
 constexpr uint32_t ST_PLAIN = 0xFFu;
+constexpr uint32_t ST_ALIAS = 0xFEu;   // stops[i] == starts[i] + 1 for every i (point intervals): lower_bound(stops, k) = lower_bound(starts, k - 1)
 constexpr size_t ST_ARR_BYTES = 4 * (ST_NB + 4) + ST_MAX_N + 32;
 constexpr size_t ST_SMEM = 2 * ST_ARR_BYTES;
 
@@ -208,10 +209,16 @@ __host__ __device__ __forceinline__ uint64_t st_arr_cap_bytes(uint32_t n) {   //
 __global__ void __launch_bounds__(256)
 build_compact_kernel(const uint32_t *__restrict__ starts, const uint32_t *__restrict__ stops,
                      const uint64_t *__restrict__ iv_off, int64_t n_seg, const uint64_t *__restrict__ cofs,
-                     SegCompact *__restrict__ par, uint8_t *__restrict__ buf) {
+                     SegCompact *__restrict__ par, uint8_t *__restrict__ buf, uint32_t *__restrict__ max_bytes) {
     for (int64_t s = blockIdx.x; s < n_seg; s += gridDim.x) {
         const uint64_t off = iv_off[s];
         const uint32_t n = (uint32_t)min((uint64_t)0xFFFFFFFFu, iv_off[s + 1] - off);
+        // point intervals (rg `chr:p` -> [p, p+1), redis.rs:291-295): the stops are the starts shifted by one, one table serves both
+        int same = 1;
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) same &= (stops[off + i] == starts[off + i] + 1u) ? 1 : 0;
+        const bool alias = __syncthreads_and(same) != 0 && n > 0;
+        uint32_t seg_bytes = 0;
+        bool par_ok_a = false;
         for (int which = 0; which < 2; ++which) {
             const uint32_t *a = (which ? stops : starts) + off;
             SegCompact p;
@@ -227,6 +234,14 @@ build_compact_kernel(const uint32_t *__restrict__ starts, const uint32_t *__rest
             p.nb = ok ? (range >> l) + 1u : 0u;
             p.low_off = ok ? ((4u * (p.nb + 1u) + 15u) & ~15u) : 0u;
             p.bytes = ok ? p.low_off + ((n + 16u + 15u) & ~15u) : 0u;
+            if (which == 1 && alias && par_ok_a) {   // the stops go through the starts' table
+                p.l = ST_ALIAS;
+                p.nb = 0, p.low_off = 0, p.bytes = 0;
+                if (threadIdx.x == 0) par[2 * s + 1] = p;
+                continue;
+            }
+            if (which == 0) par_ok_a = ok;
+            seg_bytes += p.bytes;
             if (threadIdx.x == 0) par[2 * s + which] = p;
             if (!ok) continue;
             uint8_t *base = buf + cofs[s] + (which ? st_arr_cap_bytes(n) : 0);
@@ -249,6 +264,8 @@ build_compact_kernel(const uint32_t *__restrict__ starts, const uint32_t *__rest
             }
             for (uint32_t i = n + threadIdx.x; i < ((n + 16u + 15u) & ~15u); i += blockDim.x) low[i] = 0xFFu;  // never < rem
         }
+        if (threadIdx.x == 0) atomicMax(max_bytes, seg_bytes);
+        __syncthreads();
     }
 }
 
@@ -370,13 +387,15 @@ count_overlaps_staged_kernel(const uint32_t *__restrict__ starts, const uint32_t
     SegCompact A = par[2 * s], B = par[2 * s + 1];
     // staging copies A.bytes + B.bytes; a handful of queries is cheaper by plain binary search (2 * 14 probes each)
     if ((uint64_t)(q1 - q0) * 64u < (uint64_t)A.bytes + B.bytes) A.l = B.l = ST_PLAIN;
-    uint8_t *smA = st_smem, *smB = st_smem + (A.l == ST_PLAIN ? 0u : A.bytes);
+    const bool alias = B.l == ST_ALIAS;   // lower_bound(stops, k) = lower_bound(starts, k - 1)
+    if (alias) B = A;
+    uint8_t *smA = st_smem, *smB = st_smem + ((A.l == ST_PLAIN || alias) ? 0u : A.bytes);
     {
         const uint8_t *gA = cbuf + cofs[s], *gB = gA + st_arr_cap_bytes(A.n);
         if (A.l != ST_PLAIN)
             for (uint32_t i = threadIdx.x * 16u; i < A.bytes; i += ST_THREADS * 16u)
                 *reinterpret_cast<uint4 *>(smA + i) = __ldg(reinterpret_cast<const uint4 *>(gA + i));
-        if (B.l != ST_PLAIN)
+        if (B.l != ST_PLAIN && !alias)
             for (uint32_t i = threadIdx.x * 16u; i < B.bytes; i += ST_THREADS * 16u)
                 *reinterpret_cast<uint4 *>(smB + i) = __ldg(reinterpret_cast<const uint4 *>(gB + i));
     }
@@ -400,7 +419,9 @@ count_overlaps_staged_kernel(const uint32_t *__restrict__ starts, const uint32_t
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const uint32_t last = staged_lower_bound(A, starts + off, smA, qe[u]);
-            const uint32_t first = staged_lower_bound(B, stops + off, smB, qs[u] + 1u);
+            const uint32_t kb = qs[u] + 1u;
+            const uint32_t first = alias ? (kb ? staged_lower_bound(B, starts + off, smB, kb - 1u) : 0u)
+                                         : staged_lower_bound(B, stops + off, smB, kb);
             const uint32_t q = qb + u * ST_THREADS;
             if (q < nq) op[q] = last - first;
         }
@@ -460,16 +481,23 @@ int32_t build_compact_index(gams_cuda_count_plan *p, cudaStream_t st, const uint
     p->cpar_off = (sizeof(uint64_t) * cofs.size() + 15) & ~(size_t)15;
     int32_t rc;
     if ((rc = p->tmp[4].reserve(p->cpar_off + sizeof(SegCompact) * 2 * (size_t)std::max<int64_t>(p->n_seg, 1)))) return rc;
-    if ((rc = p->tmp[5].reserve(std::max<uint64_t>(cofs.back(), 16)))) return rc;
+    if ((rc = p->tmp[5].reserve(cofs.back() + 64))) return rc;
     CUDA_TRY(cudaMemcpyAsync(p->tmp[4].p, cofs.data(), sizeof(uint64_t) * cofs.size(), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaStreamSynchronize(st));   // cofs is a local
     if (p->n_seg) {
         const int64_t blocks = std::min<int64_t>(p->n_seg, 148 * 16);
+        uint32_t *d_max = reinterpret_cast<uint32_t *>(p->tmp[5].as<uint8_t>() + ((cofs.back() + 15) & ~15ull));
+        CUDA_TRY(cudaMemsetAsync(d_max, 0, sizeof(uint32_t), st));
         build_compact_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_starts, d_stops, p->d_iv_off, p->n_seg, p->tmp[4].as<uint64_t>(),
                                                                reinterpret_cast<SegCompact *>(p->tmp[4].as<uint8_t>() + p->cpar_off),
-                                                               p->tmp[5].as<uint8_t>());
+                                                               p->tmp[5].as<uint8_t>(), d_max);
         ++p->launches;
         CUDA_TRY(cudaGetLastError());
+        // the largest staged segment decides the shared memory of the count launches (and so how many CTAs share an SM)
+        uint32_t h_max = 0;
+        CUDA_TRY(cudaMemcpyAsync(&h_max, d_max, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        p->st_smem = std::min<size_t>(ST_SMEM, std::max<size_t>(h_max, 1024));
     }
     p->cidx_starts = d_starts;
     p->cidx_stops = d_stops;
@@ -507,7 +535,7 @@ int32_t launch_count_overlaps(gams_cuda_count_plan *p, cudaStream_t st, const ui
         }
         const uint64_t *d_cofs = p->tmp[4].as<uint64_t>();
         const SegCompact *d_par = reinterpret_cast<const SegCompact *>(p->tmp[4].as<uint8_t>() + p->cpar_off);
-        count_overlaps_staged_kernel<<<(unsigned)grid, ST_THREADS, ST_SMEM, st>>>(d_starts, d_stops, p->d_iv_off, p->n_seg, n_q, qoff,
+        count_overlaps_staged_kernel<<<(unsigned)grid, ST_THREADS, p->st_smem, st>>>(d_starts, d_stops, p->d_iv_off, p->n_seg, n_q, qoff,
                                                                                  ioff, d_par, d_cofs, p->tmp[5].as<uint8_t>(),
                                                                                  d_q_start, d_q_stop, d_out);
         p->launches += 3;
