@@ -350,16 +350,19 @@ __device__ __forceinline__ uint32_t staged_lower_bound(const SegCompact &P, cons
         const uint32_t *lw = reinterpret_cast<const uint32_t *>(low) + (c0 >> 2);
         const uint32_t x0 = lw[0], x1 = lw[1], x2 = lw[2], sh = (c0 & 3u) * 8u;
         const uint32_t y0 = __funnelshift_r(x0, x1, sh), y1 = __funnelshift_r(x1, x2, sh);
-        const uint32_t rr = rem * 0x01010101u;
-        const uint32_t lt0 = ~((y0 | 0x80808080u) - rr) & 0x80808080u, lt1 = ~((y1 | 0x80808080u) - rr) & 0x80808080u;
-        // keep the first m bytes of the window: a 64-bit mask of 8 m ones
-        const uint64_t keep = m >= 8u ? ~0ull : ((1ull << (8u * m)) - 1ull);
-        cnt = c0 + (uint32_t)__popc(lt0 & (uint32_t)keep) + (uint32_t)__popc(lt1 & (uint32_t)(keep >> 32));
+        // byte < rem <=> bit 7 of (byte | 0x80) - rem is clear; byte index < m <=> bit 7 of (0x80 + index) - m is clear
+        const uint32_t rr = rem * 0x01010101u, mm = m * 0x01010101u;
+        const uint32_t a0 = (y0 | 0x80808080u) - rr, a1 = (y1 | 0x80808080u) - rr;
+        const uint32_t i0 = 0x83828180u - mm, i1 = 0x87868584u - mm;
+        cnt = c0 + (uint32_t)__popc(~a0 & ~i0 & 0x80808080u) + (uint32_t)__popc(~a1 & ~i1 & 0x80808080u);
     }
     return key > P.hi ? P.n : cnt;
 }
 
-__global__ void __launch_bounds__(ST_THREADS, 2)
+#ifndef ST_MIN_CTAS
+#define ST_MIN_CTAS 4
+#endif
+__global__ void __launch_bounds__(ST_THREADS, ST_MIN_CTAS)
 count_overlaps_staged_kernel(const uint32_t *__restrict__ starts, const uint32_t *__restrict__ stops,
                              const uint64_t *__restrict__ iv_off, int64_t n_seg, int64_t n_q,
                              const int64_t *__restrict__ qoff, const int64_t *__restrict__ ioff,
