@@ -193,7 +193,7 @@ struct alignas(16) SegCompact {      // one per (segment, endpoint array)
     uint32_t nb;                     // buckets
     uint32_t low_off;                // byte offset of low[] behind cum2[] (multiple of 16)
     uint32_t bytes;                  // bytes of the compact form (multiple of 16)
-    uint32_t pad;
+    uint32_t fmt;                    // 0: cum2[] + low[] (two arrays);  1: one 8-byte entry per bucket (E8, point intervals)
 };
 
 // bucket budget of an array of n elements (host and device agree on it: the host sizes the buffer with it)
@@ -219,13 +219,55 @@ build_compact_kernel(const uint32_t *__restrict__ starts, const uint32_t *__rest
         const bool alias = __syncthreads_and(same) != 0 && n > 0;
         uint32_t seg_bytes = 0;
         bool par_ok_a = false;
+        if (alias) {
+            // E8: one 8-byte entry per bucket = cum (15 bits) | overflow flag (bit 15) | up to six low values (0xFF = empty);
+            // both endpoints of a query are answered by ONE 64-bit shared-memory load each
+            const uint32_t *a = starts + off;
+            SegCompact p;
+            p.n = n, p.lo = a[0], p.hi = a[n - 1], p.fmt = 1, p.low_off = 0;
+            const uint32_t range = p.hi - p.lo, cap = st_nb_cap(n);
+            uint32_t l = 0;
+            while (l < 32u && (range >> l) + 1u > cap) ++l;
+            if (n <= (uint32_t)ST_MAX_N && l <= 7) {
+                p.l = l;
+                p.nb = (range >> l) + 1u;
+                p.bytes = (8u * (p.nb + 1u) + 15u) & ~15u;
+                uint2 *ent = reinterpret_cast<uint2 *>(buf + cofs[s]);
+                uint16_t *ent16 = reinterpret_cast<uint16_t *>(ent);
+                uint8_t *ent8 = reinterpret_cast<uint8_t *>(ent);
+                for (uint32_t b = threadIdx.x; b < p.bytes / 8u; b += blockDim.x) ent[b] = make_uint2(0xFFFF0000u | n, 0xFFFFFFFFu);
+                __syncthreads();
+                const uint32_t mask = (1u << l) - 1u;
+                for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {          // cum of every bucket
+                    const uint32_t b = (a[i] - p.lo) >> l;
+                    const uint32_t pb = i ? ((a[i - 1] - p.lo) >> l) + 1u : 0u;
+                    for (uint32_t bb = pb; bb <= b; ++bb) ent16[4 * bb] = (uint16_t)i;
+                }
+                __syncthreads();                                                  // (entries past the last bucket keep cum = n)
+                for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {          // low values into the bucket's slots
+                    const uint32_t d = a[i] - p.lo, b = d >> l, slot = i - (ent16[4 * b] & 0x7FFFu);
+                    if (slot < 6u) ent8[8 * b + 2 + slot] = (uint8_t)(d & mask);
+                }
+                __syncthreads();
+                for (uint32_t b = threadIdx.x; b < p.nb; b += blockDim.x)         // more than six elements: flag the bucket
+                    if ((uint32_t)(ent16[4 * b + 4] & 0x7FFFu) - (uint32_t)(ent16[4 * b] & 0x7FFFu) > 6u) ent16[4 * b] |= 0x8000u;
+                if (threadIdx.x == 0) {
+                    par[2 * s] = p;
+                    p.l = ST_ALIAS;
+                    par[2 * s + 1] = p;
+                    atomicMax(max_bytes, p.bytes);
+                }
+                __syncthreads();
+                continue;
+            }
+        }
         for (int which = 0; which < 2; ++which) {
             const uint32_t *a = (which ? stops : starts) + off;
             SegCompact p;
             p.n = n;
             p.lo = n ? a[0] : 0u;
             p.hi = n ? a[n - 1] : 0u;
-            p.pad = 0;
+            p.fmt = 0;
             const uint32_t range = p.hi - p.lo, cap = st_nb_cap(n);
             uint32_t l = 0;
             while (l < 32u && (range >> l) + 1u > cap) ++l;
@@ -362,6 +404,20 @@ __device__ __forceinline__ uint32_t staged_lower_bound(const SegCompact &P, cons
 #ifndef ST_MIN_CTAS
 #define ST_MIN_CTAS 4
 #endif
+// E8 format: #elements < key with one 64-bit load.  Entry b: cum | overflow << 15 | six low bytes (0xFF = empty slot).
+__device__ __forceinline__ uint32_t e8_lower_bound(const SegCompact &P, const uint32_t *__restrict__ a, const uint2 *ent, uint32_t key) {
+    const uint32_t d = max(key, P.lo) - P.lo, b = min(d >> P.l, P.nb - 1u), rem = d & ((1u << P.l) - 1u);
+    const uint2 e = ent[b];
+    const uint32_t cum = e.x & 0x7FFFu, rr = rem * 0x01010101u;
+    // byte < rem <=> bit 7 of (byte | 0x80) - rem is clear; the two cum bytes are forced to 0xFF, empty slots are 0xFF
+    uint32_t cnt = cum + (uint32_t)__popc(~((e.x | 0x8080FFFFu) - rr) & 0x80808080u) + (uint32_t)__popc(~((e.y | 0x80808080u) - rr) & 0x80808080u);
+    if (e.x & 0x8000u) {   // rare: more than six elements in the bucket
+        const uint32_t nxt = ent[b + 1].x & 0x7FFFu;
+        cnt = cum + lower_bound_u32(a + cum, nxt - cum, key);
+    }
+    return key > P.hi ? P.n : cnt;
+}
+
 __global__ void __launch_bounds__(ST_THREADS, ST_MIN_CTAS)
 count_overlaps_staged_kernel(const uint32_t *__restrict__ starts, const uint32_t *__restrict__ stops,
                              const uint64_t *__restrict__ iv_off, int64_t n_seg, int64_t n_q,
@@ -409,6 +465,29 @@ count_overlaps_staged_kernel(const uint32_t *__restrict__ starts, const uint32_t
     }
     constexpr int U = 4;
     const uint32_t nq = (uint32_t)(q1 - q0);
+    if (alias && A.fmt == 1u) {
+        const uint2 *ent = reinterpret_cast<const uint2 *>(smA);
+        const uint32_t *__restrict__ qsp = q_start + q0, *__restrict__ qep = q_stop + q0;
+        uint32_t *__restrict__ op = out + q0;
+        for (uint32_t qb = threadIdx.x; qb < nq; qb += U * ST_THREADS) {
+            uint32_t qs[U], qe[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint32_t q = min(qb + u * ST_THREADS, nq - 1u);
+                qs[u] = qsp[q];
+                qe[u] = qep[q];
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                // lower_bound(stops, qs + 1) = lower_bound(starts, qs); qs + 1 wrapping to 0 counts nothing, as in the general path
+                const uint32_t last = e8_lower_bound(A, starts + off, ent, qe[u]);
+                const uint32_t first = (qs[u] + 1u) ? e8_lower_bound(A, starts + off, ent, qs[u]) : 0u;
+                const uint32_t q = qb + u * ST_THREADS;
+                if (q < nq) op[q] = last - first;
+            }
+        }
+        return;
+    }
     const uint32_t *__restrict__ qsp = q_start + q0, *__restrict__ qep = q_stop + q0;
     uint32_t *__restrict__ op = out + q0;
     for (uint32_t qb = threadIdx.x; qb < nq; qb += U * ST_THREADS) {
