@@ -64,12 +64,38 @@ __device__ __forceinline__ uint32_t gc_gather_fma(uint32_t w, uint32_t one) {
     const uint32_t g7 = lop3<0x02>(a, w, 0x80808080u);
     return g7 * 0x00204081u;
 }
+// u8 x s8 dot product with accumulator (IDP.4A, FMA pipe)
+__device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c) {
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+#ifdef FW_DP4A_GATHER
+// flags in bit 7 of every byte (0x80 / 0x00), not yet gathered
+__device__ __forceinline__ uint32_t gc_flags_fma(uint32_t w, uint32_t one) {
+    const uint32_t t = lop3<0x6A>(w, 0x5B5B5B5Bu, 0x43434343u);
+    const uint32_t a = t * one + 0x7F7F7F7Fu;
+    return lop3<0x02>(a, w, 0x80808080u);
+}
+// Two words per dot-product chain: weights 1 2 4 8 / 16 32 64 128 put the eight flags (each worth 128) of a word pair
+// into bits 7..14; the four pairs are merged by two multiply-adds and one shift: 17 ALU + 19 FMA-pipe instructions
+// per 32 bytes instead of 24 + 16.
+__device__ __forceinline__ uint32_t gc_mask32(const Bytes32 &v, uint32_t one) {
+    uint32_t P[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        P[q] = __dp4a(gc_flags_fma(v.w[2 * q], one), 0x08040201u, __dp4a(gc_flags_fma(v.w[2 * q + 1], one), 0x80402010u, 0u));
+    const uint32_t lo = P[1] * 256u + P[0], hi = P[3] * 256u + P[2];   // 128 x (16 flags)
+    return hi * 512u + (lo >> 7);
+}
+#else
 __device__ __forceinline__ uint32_t gc_mask32(const Bytes32 &v, uint32_t one) {
     uint32_t m = gc_gather_fma(v.w[7], one) >> 28;
 #pragma unroll
     for (int q = 6; q >= 0; --q) m = __funnelshift_l(gc_gather_fma(v.w[q], one), m, 4);
     return m;
 }
+#endif
 
 // Tile layout.  A tile holds FW_MAX_EL consecutive windows ("elements") of one ctg; element e is global window
 // g0 + e with g0 = 7 (mod 8), so that the eight elements 8t+1 .. 8t+8 a thread decides start at a multiple of 8 in the
@@ -167,6 +193,20 @@ gc_wave_fused_kernel(const uint8_t *__restrict__ seq, const FusedTile *__restric
         if (R == 10) {
             const uint2 a = *reinterpret_cast<const uint2 *>(bt), b = *reinterpret_cast<const uint2 *>(bt + 8);
             const uint32_t d = *reinterpret_cast<const uint32_t *>(bt + 16);
+#ifdef FW_DP4A_COUNTS
+            // byte sums and byte differences as dot products (IDP.4A, FMA pipe) instead of extract + add on the ALU pipe
+            c[0] = (uint32_t)dp4a_us(a.x, 0x01010101, dp4a_us(a.y, 0x01010101, dp4a_us(b.x, 0x00000101, 0)));
+            c[1] = (uint32_t)dp4a_us(b.x, 0x00010000, dp4a_us(a.x, (int)0x000000FF, (int)c[0]));
+            c[2] = (uint32_t)dp4a_us(b.x, 0x01000000, dp4a_us(a.x, (int)0x0000FF00, (int)c[1]));
+            c[3] = (uint32_t)dp4a_us(b.y, 0x00000001, dp4a_us(a.x, (int)0x00FF0000, (int)c[2]));
+            c[4] = (uint32_t)dp4a_us(b.y, 0x00000100, dp4a_us(a.x, (int)0xFF000000, (int)c[3]));
+            c[5] = (uint32_t)dp4a_us(b.y, 0x00010000, dp4a_us(a.y, (int)0x000000FF, (int)c[4]));
+            c[6] = (uint32_t)dp4a_us(b.y, 0x01000000, dp4a_us(a.y, (int)0x0000FF00, (int)c[5]));
+            c[7] = (uint32_t)dp4a_us(d, 0x00000001, dp4a_us(a.y, (int)0x00FF0000, (int)c[6]));
+        } else if (false) {
+            const uint2 a = make_uint2(0u, 0u), b = a;
+            const uint32_t d = 0u;
+#endif
             const uint32_t s = a.x + a.y + (b.x & 0xFFFFu);        // per-byte sums <= 3 * 16
             c[0] = (s * 0x01010101u) >> 24;
             c[1] = c[0] + ((b.x >> 16) & 0xFFu) - (a.x & 0xFFu);

@@ -347,16 +347,28 @@ seg_query_bounds_kernel(const int32_t *__restrict__ q_seg, int64_t n_q, int64_t 
         for (int64_t s = 0; s <= n_seg; ++s) qoff[s] = 0;
 }
 
-// work items: segment s is cut into ceil(nq_s / ST_CHUNK) items; ioff[s] = first item of segment s (one CTA scans)
-__global__ void __launch_bounds__(1024)
-seg_items_kernel(const int64_t *__restrict__ qoff, int64_t n_seg, int64_t *__restrict__ ioff) {
+// work items: segment s is cut into ceil(nq_s / ST_CHUNK) items; ioff[s] = first item of segment s, item_seg[i] = segment
+// of item i.  One CTA: every thread takes a contiguous run of segments (all its loads are in flight at once), one block scan.
+constexpr int SI_THREADS = 1024;
+constexpr int SI_PER = 8;            // segments per thread and round
+__global__ void __launch_bounds__(SI_THREADS)
+seg_items_kernel(const int64_t *__restrict__ qoff, int64_t n_seg, int64_t *__restrict__ ioff, int32_t *__restrict__ item_seg) {
     __shared__ int64_t wsum[32];
     __shared__ int64_t carry;
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
-    for (int64_t base = 0; base < n_seg; base += 1024) {
-        const int64_t s = base + threadIdx.x;
-        int64_t v = s < n_seg ? (qoff[s + 1] - qoff[s] + ST_CHUNK - 1) / ST_CHUNK : 0, inc = v;
+    for (int64_t base = 0; base < n_seg; base += (int64_t)SI_THREADS * SI_PER) {
+        const int64_t s0 = base + (int64_t)threadIdx.x * SI_PER;
+        int64_t b[SI_PER + 1];
+#pragma unroll
+        for (int k = 0; k <= SI_PER; ++k) b[k] = qoff[min(s0 + k, n_seg)];
+        int64_t v[SI_PER], tot = 0;
+#pragma unroll
+        for (int k = 0; k < SI_PER; ++k) {
+            v[k] = (b[k + 1] - b[k] + ST_CHUNK - 1) / ST_CHUNK;   // 0 past the last segment
+            tot += v[k];
+        }
+        int64_t inc = tot;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const int64_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
@@ -366,9 +378,17 @@ seg_items_kernel(const int64_t *__restrict__ qoff, int64_t n_seg, int64_t *__res
         __syncthreads();
         int64_t before = carry;
         for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) before += wsum[w];
-        if (s < n_seg) ioff[s] = before + inc - v;
+        int64_t at = before + inc - tot;
+#pragma unroll
+        for (int k = 0; k < SI_PER; ++k) {
+            if (s0 + k < n_seg) {
+                ioff[s0 + k] = at;
+                for (int64_t i = 0; i < v[k]; ++i) item_seg[at + i] = (int32_t)(s0 + k);
+            }
+            at += v[k];
+        }
         __syncthreads();
-        if (threadIdx.x == 1023) carry = before + inc;
+        if (threadIdx.x == SI_THREADS - 1) carry = before + inc;
         __syncthreads();
     }
     if (threadIdx.x == 0) ioff[n_seg] = carry;
@@ -405,24 +425,27 @@ __device__ __forceinline__ uint32_t staged_lower_bound(const SegCompact &P, cons
 #define ST_MIN_CTAS 4
 #endif
 // E8 format: #elements < key with one 64-bit load.  Entry b: cum | overflow << 15 | six low bytes (0xFF = empty slot).
+// Entry nb is a sentinel (cum = n, no elements): every key past the last bucket lands there, so key > hi needs no
+// special case (inside the last bucket the byte compare already counts every element).
 __device__ __forceinline__ uint32_t e8_lower_bound(const SegCompact &P, const uint32_t *__restrict__ a, const uint2 *ent, uint32_t key) {
-    const uint32_t d = max(key, P.lo) - P.lo, b = min(d >> P.l, P.nb - 1u), rem = d & ((1u << P.l) - 1u);
+    const uint32_t d = max(key, P.lo) - P.lo, b = min(d >> P.l, P.nb), rem = d & ((1u << P.l) - 1u);
     const uint2 e = ent[b];
     const uint32_t cum = e.x & 0x7FFFu, rr = rem * 0x01010101u;
     // byte < rem <=> bit 7 of (byte | 0x80) - rem is clear; the two cum bytes are forced to 0xFF, empty slots are 0xFF
     uint32_t cnt = cum + (uint32_t)__popc(~((e.x | 0x8080FFFFu) - rr) & 0x80808080u) + (uint32_t)__popc(~((e.y | 0x80808080u) - rr) & 0x80808080u);
-    if (e.x & 0x8000u) {   // rare: more than six elements in the bucket
+    if (e.x & 0x8000u) {   // rare: more than six elements in the bucket; the seventh and later ones are compared in the raw array
         const uint32_t nxt = ent[b + 1].x & 0x7FFFu;
-        cnt = cum + lower_bound_u32(a + cum, nxt - cum, key);
+#pragma unroll 1
+        for (uint32_t i = cum + 6u; i < nxt; ++i) cnt += (__ldg(a + i) < key) ? 1u : 0u;
     }
-    return key > P.hi ? P.n : cnt;
+    return cnt;
 }
 
 __global__ void __launch_bounds__(ST_THREADS, ST_MIN_CTAS)
 count_overlaps_staged_kernel(const uint32_t *__restrict__ starts, const uint32_t *__restrict__ stops,
                              const uint64_t *__restrict__ iv_off, int64_t n_seg, int64_t n_q,
                              const int64_t *__restrict__ qoff, const int64_t *__restrict__ ioff,
-                             const SegCompact *__restrict__ par, const uint64_t *__restrict__ cofs,
+                             const int32_t *__restrict__ item_seg, const SegCompact *__restrict__ par, const uint64_t *__restrict__ cofs,
                              const uint8_t *__restrict__ cbuf, const uint32_t *__restrict__ q_start,
                              const uint32_t *__restrict__ q_stop, uint32_t *__restrict__ out) {
     extern __shared__ __align__(16) uint8_t st_smem[];
@@ -435,12 +458,7 @@ count_overlaps_staged_kernel(const uint32_t *__restrict__ starts, const uint32_t
         for (int64_t k = (item - n_items) * ST_THREADS + threadIdx.x; k < n_bad; k += stride) out[k < v_lo ? k : v_hi + (k - v_lo)] = 0u;
         return;
     }
-    int64_t lo = 0, hi = n_seg;   // last segment with ioff[s] <= item
-    while (hi - lo > 1) {
-        const int64_t mid = (lo + hi) >> 1;
-        if (ioff[mid] <= item) lo = mid; else hi = mid;
-    }
-    const int64_t s = lo;
+    const int64_t s = item_seg[item];
     const int64_t q0 = qoff[s] + (item - ioff[s]) * ST_CHUNK, q1 = min(q0 + (int64_t)ST_CHUNK, qoff[s + 1]);
     const uint64_t off = iv_off[s];
     SegCompact A = par[2 * s], B = par[2 * s + 1];
@@ -467,24 +485,31 @@ count_overlaps_staged_kernel(const uint32_t *__restrict__ starts, const uint32_t
     const uint32_t nq = (uint32_t)(q1 - q0);
     if (alias && A.fmt == 1u) {
         const uint2 *ent = reinterpret_cast<const uint2 *>(smA);
-        const uint32_t *__restrict__ qsp = q_start + q0, *__restrict__ qep = q_stop + q0;
-        uint32_t *__restrict__ op = out + q0;
-        for (uint32_t qb = threadIdx.x; qb < nq; qb += U * ST_THREADS) {
+        const uint32_t *__restrict__ a = starts + off;
+        // whole groups of U * ST_THREADS queries: fixed offsets from three running pointers, no bounds checks
+        const uint32_t *__restrict__ ps = q_start + q0 + threadIdx.x, *__restrict__ pe = q_stop + q0 + threadIdx.x;
+        uint32_t *__restrict__ po = out + q0 + threadIdx.x;
+        uint32_t left = nq;
+        for (; left >= (uint32_t)(U * ST_THREADS); left -= U * ST_THREADS, ps += U * ST_THREADS, pe += U * ST_THREADS, po += U * ST_THREADS) {
             uint32_t qs[U], qe[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const uint32_t q = min(qb + u * ST_THREADS, nq - 1u);
-                qs[u] = qsp[q];
-                qe[u] = qep[q];
+                qs[u] = __ldg(ps + u * ST_THREADS);
+                qe[u] = __ldg(pe + u * ST_THREADS);
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 // lower_bound(stops, qs + 1) = lower_bound(starts, qs); qs + 1 wrapping to 0 counts nothing, as in the general path
-                const uint32_t last = e8_lower_bound(A, starts + off, ent, qe[u]);
-                const uint32_t first = (qs[u] + 1u) ? e8_lower_bound(A, starts + off, ent, qs[u]) : 0u;
-                const uint32_t q = qb + u * ST_THREADS;
-                if (q < nq) op[q] = last - first;
+                const uint32_t last = e8_lower_bound(A, a, ent, qe[u]);
+                const uint32_t first = (qs[u] + 1u) ? e8_lower_bound(A, a, ent, qs[u]) : 0u;
+                po[u * ST_THREADS] = last - first;
             }
+        }
+        for (uint32_t q = threadIdx.x; q < left; q += ST_THREADS) {
+            const uint32_t qs = __ldg(ps + (q - threadIdx.x)), qe = __ldg(pe + (q - threadIdx.x));
+            const uint32_t last = e8_lower_bound(A, a, ent, qe);
+            const uint32_t first = (qs + 1u) ? e8_lower_bound(A, a, ent, qs) : 0u;
+            po[q - threadIdx.x] = last - first;
         }
         return;
     }
@@ -603,14 +628,15 @@ int32_t launch_count_overlaps(gams_cuda_count_plan *p, cudaStream_t st, const ui
         if (!p->cidx_valid || p->cidx_starts != d_starts || p->cidx_stops != d_stops) {
             if ((rc = build_compact_index(p, st, d_starts, d_stops))) return rc;
         }
-        if ((rc = p->tmp[3].reserve(sizeof(int64_t) * 2 * (size_t)(p->n_seg + 1)))) return rc;
+        // items <= n_q / ST_CHUNK + n_seg; the CTAs beyond the actual count zero the out-of-index queries
+        const int64_t grid = n_q / ST_CHUNK + p->n_seg + 8;
+        if ((rc = p->tmp[3].reserve(sizeof(int64_t) * 2 * (size_t)(p->n_seg + 1) + sizeof(int32_t) * (size_t)grid))) return rc;
         int64_t *qoff = p->tmp[3].as<int64_t>(), *ioff = qoff + (p->n_seg + 1);
+        int32_t *item_seg = reinterpret_cast<int32_t *>(ioff + (p->n_seg + 1));
         int64_t b0 = (n_q + 1 + 255) / 256;
         if (b0 > 148 * 32) b0 = 148 * 32;
         seg_query_bounds_kernel<<<(unsigned)b0, 256, 0, st>>>(d_q_seg, n_q, p->n_seg, qoff);
-        seg_items_kernel<<<1, 1024, 0, st>>>(qoff, p->n_seg, ioff);
-        // items <= n_q / ST_CHUNK + n_seg; the CTAs beyond the actual count zero the out-of-index queries
-        const int64_t grid = n_q / ST_CHUNK + p->n_seg + 8;
+        seg_items_kernel<<<1, SI_THREADS, 0, st>>>(qoff, p->n_seg, ioff, item_seg);
         if (grid >= (1ll << 31)) {
             set_error("count_overlaps: too many segments for one launch");
             return GAMS_CUDA_EINVAL;
@@ -618,7 +644,7 @@ int32_t launch_count_overlaps(gams_cuda_count_plan *p, cudaStream_t st, const ui
         const uint64_t *d_cofs = p->tmp[4].as<uint64_t>();
         const SegCompact *d_par = reinterpret_cast<const SegCompact *>(p->tmp[4].as<uint8_t>() + p->cpar_off);
         count_overlaps_staged_kernel<<<(unsigned)grid, ST_THREADS, p->st_smem, st>>>(d_starts, d_stops, p->d_iv_off, p->n_seg, n_q, qoff,
-                                                                                 ioff, d_par, d_cofs, p->tmp[5].as<uint8_t>(),
+                                                                                 ioff, item_seg, d_par, d_cofs, p->tmp[5].as<uint8_t>(),
                                                                                  d_q_start, d_q_stop, d_out);
         p->launches += 3;
         CUDA_TRY(cudaGetLastError());
