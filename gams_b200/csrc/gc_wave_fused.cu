@@ -70,7 +70,6 @@ __device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c) {
     asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
 }
-#ifdef FW_DP4A_GATHER
 // flags in bit 7 of every byte (0x80 / 0x00), not yet gathered
 __device__ __forceinline__ uint32_t gc_flags_fma(uint32_t w, uint32_t one) {
     const uint32_t t = lop3<0x6A>(w, 0x5B5B5B5Bu, 0x43434343u);
@@ -88,14 +87,23 @@ __device__ __forceinline__ uint32_t gc_mask32(const Bytes32 &v, uint32_t one) {
     const uint32_t lo = P[1] * 256u + P[0], hi = P[3] * 256u + P[2];   // 128 x (16 flags)
     return hi * 512u + (lo >> 7);
 }
-#else
-__device__ __forceinline__ uint32_t gc_mask32(const Bytes32 &v, uint32_t one) {
-    uint32_t m = gc_gather_fma(v.w[7], one) >> 28;
-#pragma unroll
-    for (int q = 6; q >= 0; --q) m = __funnelshift_l(gc_gather_fma(v.w[q], one), m, 4);
-    return m;
+
+// bits [P, P + 10) of the bit string x[0] | x[1] << 32 | ..., UNMASKED above the field (P is a compile-time constant)
+template <int P>
+__device__ __forceinline__ uint32_t bits_from(const uint32_t (&x)[6]) {
+    constexpr int w = P >> 5, o = P & 31;
+    if (o == 0) return x[w];
+    if (o <= 22) return x[w] >> o;
+    return __funnelshift_r(x[w], x[w + 1], o);
 }
-#endif
+// popc(in field) - popc(out field) + 10 for two 10-bit fields, with ONE population count:
+// the inverted out-field is placed above the in-field
+template <int PIN, int POUT>
+__device__ __forceinline__ uint32_t popc_in_minus_out_plus10(const uint32_t (&x)[6]) {
+    const uint32_t a = bits_from<PIN>(x) & 0x3FFu;
+    const uint32_t b = ~bits_from<POUT>(x) & 0x3FFu;
+    return (uint32_t)__popc(b * 1024u + a);
+}
 
 // Tile layout.  A tile holds FW_MAX_EL consecutive windows ("elements") of one ctg; element e is global window
 // g0 + e with g0 = 7 (mod 8), so that the eight elements 8t+1 .. 8t+8 a thread decides start at a multiple of 8 in the
@@ -105,7 +113,9 @@ __device__ __forceinline__ uint32_t gc_mask32(const Bytes32 &v, uint32_t one) {
 //
 // LAG4: lag % 4 == 0, so the counts lag windows back sit at 8-byte aligned shared-memory addresses.
 // R: size / step when known at compile time (10), 0 = read it from `r_rt`.
-template <bool WRITE_CNT, bool LAG4, int R>
+// S10: size == 100 and step == 10 (the reference's documented geometry, README `gams wave --size 100 --step 10`): the
+// window counts come straight out of the bit array, without the per-block sums and their barrier.
+template <bool WRITE_CNT, bool LAG4, int R, bool S10>
 __global__ void __launch_bounds__(GC_THREADS, FW_MIN_CTAS)
 gc_wave_fused_kernel(const uint8_t *__restrict__ seq, const FusedTile *__restrict__ tiles,
                      const float *__restrict__ gc_tab, int size, int step, int r_rt, int lag, float threshold,
@@ -113,20 +123,16 @@ gc_wave_fused_kernel(const uint8_t *__restrict__ seq, const FusedTile *__restric
                      int8_t *__restrict__ sig_out, unsigned long long *__restrict__ stats) {
     // WW[i] = GC bits of bytes [16 i, 16 i + 32) of the tile's span (consecutive words overlap by 16 bits so that a
     // block of <= 16 bases always comes out of one word)
-    __shared__ __align__(16) uint32_t WW[FW_NBLK + 4];
-    // R1: bsum[] (GC bases per step-sized block) while the counts are built; afterwards sg[] and list[]
-    __shared__ __align__(16) uint8_t R1[FW_NBLK + 8 + FUSED_LIST_CAP * 4];
+    __shared__ __align__(16) uint32_t WW[S10 ? FW_NCH / 2 + 8 : FW_NBLK + 4];   // S10: plain bit array, word i = bits [32 i, 32 i + 32)
+    __shared__ __align__(16) uint8_t R1[S10 ? 16 : FW_NBLK + 8];   // bsum[]: GC bases per step-sized block
     __shared__ __align__(16) uint16_t cwp[FW_PAD + FW_MAX_EL + 8];  // window counts c_e at cwp[FW_PAD + e]
     __shared__ __align__(16) uint2 Pq[(FW_PAD + FW_MAX_EL) / 4];    // (sum c, sum c^2) over elements < 4 m, at Pq[FW_PAD/4 + m]
     __shared__ float stab[FW_STAB];                                 // gc_tab when size < FW_STAB
     __shared__ uint32_t ws1[GC_THREADS / 32], ws2[GC_THREADS / 32];
-    __shared__ int list_n;
     static_assert(FW_NBLK + 4 >= FW_NCH + 1, "WW holds the bit array");
     uint16_t *const WW16 = reinterpret_cast<uint16_t *>(WW);
     uint16_t *const cw = cwp + FW_PAD;
     uint8_t *const bsum = R1;
-    uint8_t *const sg = R1;                                         // sg[e - 1] = decision of element e
-    int *const list = reinterpret_cast<int *>(R1 + FW_NBLK + 8);
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -137,7 +143,6 @@ gc_wave_fused_kernel(const uint8_t *__restrict__ seq, const FusedTile *__restric
     const uint32_t span = (e_out1 - 1u) * (uint32_t)step + (uint32_t)size;
     const uint32_t nch = (lead + span + 15u) >> 4;                  // <= FW_NCH by construction of the tiles
     const bool use_stab = size < FW_STAB;
-    if (tid == 0) list_n = 0;
     if (use_stab && tid <= size) stab[tid] = __ldg(gc_tab + tid);
     // Elements before the tile count as zeros: a thread whose first stats window starts before element 0 then slides
     // into correct sums by the time its window lies inside the tile.
@@ -158,6 +163,10 @@ gc_wave_fused_kernel(const uint8_t *__restrict__ seq, const FusedTile *__restric
             const uint32_t pi = j * GC_THREADS + tid;
             if (2u * (pi - lane) < nch) {                           // warp-uniform
                 const uint32_t m = gc_mask32(v[j], one);
+                if (S10) {                                          // plain bit array: word pi = bits [32 pi, 32 pi + 32)
+                    WW[pi] = m;
+                    continue;
+                }
                 const uint32_t nx = __shfl_down_sync(0xFFFFFFFFu, m, 1);
                 if (lane != 31) *reinterpret_cast<uint2 *>(WW + 2 * pi) = make_uint2(m, __funnelshift_r(m, nx, 16));
                 else {
@@ -172,7 +181,7 @@ gc_wave_fused_kernel(const uint8_t *__restrict__ seq, const FusedTile *__restric
 
     // ---- GC bases of every step-sized block: bsum[m] = popc(bits [lead + m step, + step)).  Branch-free: blocks past
     //      the tile's last boundary read stale (in-bounds) words and are never used.
-    {
+    if (!S10) {
         const uint32_t smask = (1u << step) - 1u;                   // step <= 16
         const uint32_t p0 = lead + (uint32_t)tid * (uint32_t)step;
         const uint32_t sh = p0 & 15u;                               // 256 * step is a multiple of 16: the same for every j
@@ -181,8 +190,8 @@ gc_wave_fused_kernel(const uint8_t *__restrict__ seq, const FusedTile *__restric
 #pragma unroll
         for (int j = 0; j < FW_NBLK / GC_THREADS; ++j, wp += dw)
             bsum[j * GC_THREADS + tid] = (uint8_t)__popc((*wp >> sh) & smask);
+        __syncthreads();
     }
-    __syncthreads();
 
     // ---- window counts by sliding over the block sums (thread t owns windows [8t, 8t+8)), then exact prefix sums of
     //      c and c^2 over the tile, kept for every fourth element
@@ -190,10 +199,30 @@ gc_wave_fused_kernel(const uint8_t *__restrict__ seq, const FusedTile *__restric
     uint32_t q1, q2;                            // sums over the elements before 8t
     {
         const uint8_t *bt = bsum + FW_E * tid;
-        if (R == 10) {
+        if (S10) {
+            // the thread's eight windows are bits [p0, p0 + 170) of the tile's bit array: seven words, shifted so that
+            // block k sits at bits [10 k, 10 k + 10); window 0 is one 100-bit population count and window j + 1 differs
+            // from window j by the block that enters and the block that leaves.  Words past the tile's last chunk are
+            // stale (in bounds) and only reach elements the tile does not have.
+            const uint32_t p0 = lead + 80u * (uint32_t)tid;
+            const uint32_t *wp = WW + (p0 >> 5);
+            const uint32_t sh = p0 & 31u;
+            uint32_t w[7], x[6];
+#pragma unroll
+            for (int k = 0; k < 7; ++k) w[k] = wp[k];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) x[k] = __funnelshift_r(w[k], w[k + 1], sh);
+            c[0] = (uint32_t)(__popc(x[0]) + __popc(x[1])) + (uint32_t)(__popc(x[2]) + __popc(x[3] & 0xFu));
+            c[1] = c[0] + popc_in_minus_out_plus10<100, 0>(x) - 10u;
+            c[2] = c[1] + popc_in_minus_out_plus10<110, 10>(x) - 10u;
+            c[3] = c[2] + popc_in_minus_out_plus10<120, 20>(x) - 10u;
+            c[4] = c[3] + popc_in_minus_out_plus10<130, 30>(x) - 10u;
+            c[5] = c[4] + popc_in_minus_out_plus10<140, 40>(x) - 10u;
+            c[6] = c[5] + popc_in_minus_out_plus10<150, 50>(x) - 10u;
+            c[7] = c[6] + popc_in_minus_out_plus10<160, 60>(x) - 10u;
+        } else if (R == 10) {
             const uint2 a = *reinterpret_cast<const uint2 *>(bt), b = *reinterpret_cast<const uint2 *>(bt + 8);
             const uint32_t d = *reinterpret_cast<const uint32_t *>(bt + 16);
-#ifdef FW_DP4A_COUNTS
             // byte sums and byte differences as dot products (IDP.4A, FMA pipe) instead of extract + add on the ALU pipe
             c[0] = (uint32_t)dp4a_us(a.x, 0x01010101, dp4a_us(a.y, 0x01010101, dp4a_us(b.x, 0x00000101, 0)));
             c[1] = (uint32_t)dp4a_us(b.x, 0x00010000, dp4a_us(a.x, (int)0x000000FF, (int)c[0]));
@@ -203,19 +232,6 @@ gc_wave_fused_kernel(const uint8_t *__restrict__ seq, const FusedTile *__restric
             c[5] = (uint32_t)dp4a_us(b.y, 0x00010000, dp4a_us(a.y, (int)0x000000FF, (int)c[4]));
             c[6] = (uint32_t)dp4a_us(b.y, 0x01000000, dp4a_us(a.y, (int)0x0000FF00, (int)c[5]));
             c[7] = (uint32_t)dp4a_us(d, 0x00000001, dp4a_us(a.y, (int)0x00FF0000, (int)c[6]));
-        } else if (false) {
-            const uint2 a = make_uint2(0u, 0u), b = a;
-            const uint32_t d = 0u;
-#endif
-            const uint32_t s = a.x + a.y + (b.x & 0xFFFFu);        // per-byte sums <= 3 * 16
-            c[0] = (s * 0x01010101u) >> 24;
-            c[1] = c[0] + ((b.x >> 16) & 0xFFu) - (a.x & 0xFFu);
-            c[2] = c[1] + (b.x >> 24) - ((a.x >> 8) & 0xFFu);
-            c[3] = c[2] + (b.y & 0xFFu) - ((a.x >> 16) & 0xFFu);
-            c[4] = c[3] + ((b.y >> 8) & 0xFFu) - (a.x >> 24);
-            c[5] = c[4] + ((b.y >> 16) & 0xFFu) - (a.y & 0xFFu);
-            c[6] = c[5] + (b.y >> 24) - ((a.y >> 8) & 0xFFu);
-            c[7] = c[6] + (d & 0xFFu) - ((a.y >> 16) & 0xFFu);
         } else {
             uint32_t s = 0;
             for (uint32_t m = 0; m < r; ++m) s += bt[m];
@@ -234,7 +250,7 @@ gc_wave_fused_kernel(const uint8_t *__restrict__ seq, const FusedTile *__restric
             s2 = scan_step(s2, d);
         }
         if (lane == 31) { ws1[warp] = s1; ws2[warp] = s2; }
-        __syncthreads();   // also: every thread is done with bsum, so sg may overwrite it
+        __syncthreads();
         const uint32_t o1 = (lane < warp) ? ws1[lane & 7] : 0u, o2 = (lane < warp) ? ws2[lane & 7] : 0u;
         q1 = s1 - a1 + __reduce_add_sync(0xFFFFFFFFu, o1);
         q2 = s2 - a2 + __reduce_add_sync(0xFFFFFFFFu, o2);
@@ -321,47 +337,39 @@ gc_wave_fused_kernel(const uint8_t *__restrict__ seq, const FusedTile *__restric
                     else pk1 &= ~(0xFFu << (8 * (j & 3)));
                 }
         }
-        // bytes equal to 2 (bit 1 set, bit 0 clear; 0xFF has both): rare, some window is inconclusive
-        if (((pk0 & ~(pk0 << 1)) | (pk1 & ~(pk1 << 1))) & 0x02020202u) {
-#pragma unroll
-            for (int j = 0; j < FW_E; ++j)
-                if (((((j < 4) ? pk0 : pk1) >> (8 * (j & 3))) & 3u) == 2u) {
-                    const int slot = atomicAdd(&list_n, 1);
-                    if (slot < FUSED_LIST_CAP) list[slot] = (int)(e0 + j);
-                }
+        // ---- exact replay of inconclusive windows by the lane that owns them (rare: 7.6e-6 of windows): x_k = gc_tab[c_k]
+        //      are the f32 values the reference sums.  Decisions never leave the thread, so no barrier and no list.
+        // bytes equal to 2 (bit 1 set, bit 0 clear; 0xFF has both): some window is inconclusive
+        const bool own_sp = e_sp >= (int)e0 && e_sp < (int)(e0 + FW_E) && (uint32_t)e_sp < e_out1;
+        if ((((pk0 & ~(pk0 << 1)) | (pk1 & ~(pk1 << 1))) & 0x02020202u) || own_sp) {
+            const float flag = __ull2float_rn((unsigned long long)lag);
+            const float flagm1 = __fsub_rn(flag, 1.0f);
+            auto ld = [&](int64_t e) { return __ldg(gc_tab + cw[e]); };
+            unsigned long long n_rep = 0;
+#pragma unroll 1
+            for (int j = 0; j < FW_E; ++j) {
+                const uint32_t e = e0 + (uint32_t)j;
+                uint32_t cur = (((j < 4) ? pk0 : pk1) >> (8 * (j & 3))) & 0xFFu;
+                if (own_sp && (int)e == e_sp) {
+                    // window `lag` of the ctg takes its statistics from windows [0, lag) (stat.rs:30-31), not [lag-1-lag, lag-1)
+                    cur = (uint32_t)zscore_decide(ld, (int64_t)td.e_ctg0, (uint64_t)lag, flag, flagm1, ld(e), threshold) & 0xFFu;
+                } else if (cur == 2u) {
+                    cur = (uint32_t)zscore_decide(ld, (int64_t)e - 1 - (int64_t)lag, (uint64_t)lag, flag, flagm1, ld(e), threshold) & 0xFFu;
+                    ++n_rep;
+                } else continue;
+                const uint32_t sh = 8u * (uint32_t)(j & 3), keep = ~(0xFFu << sh);
+                if (j < 4) pk0 = (pk0 & keep) | (cur << sh);
+                else pk1 = (pk1 & keep) | (cur << sh);
+            }
+            if (stats && n_rep) atomicAdd(&stats[0], n_rep);
         }
-        *reinterpret_cast<uint2 *>(sg + FW_E * tid) = make_uint2(pk0, pk1);
-    }
-    __syncthreads();
-
-    // ---- exact replay of inconclusive windows (rare): x_k = gc_tab[c_k] are the f32 values the reference sums
-    const int n_list = list_n;  // block-uniform
-    if (n_list > 0 || e_sp >= 0) {
-        const float flag = __ull2float_rn((unsigned long long)lag);
-        const float flagm1 = __fsub_rn(flag, 1.0f);
-        auto ld = [&](int64_t e) { return __ldg(gc_tab + cw[e]); };
-        if (e_sp >= 0 && tid == 0 && (uint32_t)e_sp < e_out1) {
-            // window `lag` of the ctg takes its statistics from windows [0, lag) (stat.rs:30-31), not [lag-1-lag, lag-1)
-            sg[e_sp - 1] = (uint8_t)zscore_decide(ld, (int64_t)td.e_ctg0, (uint64_t)lag, flag, flagm1, ld(e_sp), threshold);
-        }
-        const int n_todo = (n_list <= FUSED_LIST_CAP) ? n_list : (int)e_out1;  // overflow: replay the whole tile
-        for (int t = tid; t < n_todo; t += GC_THREADS) {
-            const uint32_t e = (n_list <= FUSED_LIST_CAP) ? (uint32_t)list[t] : (uint32_t)t;
-            if (e < e_lo || e >= e_out1) continue;
-            sg[e - 1] = (uint8_t)zscore_decide(ld, (int64_t)e - 1 - (int64_t)lag, (uint64_t)lag, flag, flagm1, ld(e), threshold);
-        }
-        if (stats && tid == 0 && n_list) atomicAdd(&stats[0], (unsigned long long)n_list);
-        __syncthreads();
-    }
-    // ---- signals of elements 8t+1 .. 8t+8: one aligned 64-bit store per thread
-    {
+        // ---- signals of elements 8t+1 .. 8t+8: one aligned 64-bit store per thread
         int8_t *__restrict__ so = sig_out + (td.g0 + (int64_t)e0);
-        const uint2 pk = *reinterpret_cast<const uint2 *>(sg + FW_E * tid);
-        if (whole) *reinterpret_cast<uint2 *>(so) = pk;
+        if (whole) *reinterpret_cast<uint2 *>(so) = make_uint2(pk0, pk1);
         else {
 #pragma unroll
             for (int j = 0; j < FW_E; ++j)
-                if (e0 + j >= e_out0 && e0 + j < e_out1) so[j] = (int8_t)(((j < 4) ? pk.x : pk.y) >> (8 * (j & 3)));
+                if (e0 + j >= e_out0 && e0 + j < e_out1) so[j] = (int8_t)(((j < 4) ? pk0 : pk1) >> (8 * (j & 3)));
         }
     }
 }
@@ -468,12 +476,14 @@ int32_t launch_gc_wave_fused(gams_cuda_wave_plan *p, cudaStream_t st, const uint
     const unsigned grid = (unsigned)(t1 - t0);
     const FusedTile *tiles = p->d_ftiles + t0;
     const int r = p->size / p->step;
-#define GAMS_FUSED_LAUNCH(WC, L4, RR)                                                                                   \
-    gc_wave_fused_kernel<WC, L4, RR><<<grid, GC_THREADS, 0, st>>>(d_seq, tiles, p->d_gc_tab, p->size, p->step, r,      \
+#define GAMS_FUSED_LAUNCH(WC, L4, RR, S)                                                                                \
+    gc_wave_fused_kernel<WC, L4, RR, S><<<grid, GC_THREADS, 0, st>>>(d_seq, tiles, p->d_gc_tab, p->size, p->step, r,      \
                                                                   (int)p->lag, threshold, 1u, fc, d_cnt, d_gc, d_sig, d_stats)
 #define GAMS_FUSED_LAUNCH_R(WC, L4)                                                                                     \
     do {                                                                                                               \
-        if (r == 10) GAMS_FUSED_LAUNCH(WC, L4, 10); else GAMS_FUSED_LAUNCH(WC, L4, 0);                                 \
+        if (r == 10 && p->step == 10) GAMS_FUSED_LAUNCH(WC, L4, 10, true);                                             \
+        else if (r == 10) GAMS_FUSED_LAUNCH(WC, L4, 10, false);                                                        \
+        else GAMS_FUSED_LAUNCH(WC, L4, 0, false);                                                                      \
     } while (0)
     if (p->lag % 4 == 0) { if (d_cnt) GAMS_FUSED_LAUNCH_R(true, true); else GAMS_FUSED_LAUNCH_R(false, true); }
     else { if (d_cnt) GAMS_FUSED_LAUNCH_R(true, false); else GAMS_FUSED_LAUNCH_R(false, false); }
