@@ -228,6 +228,21 @@ def count_overlaps(ctx: Context, starts, stops, iv_off, q_seg, q_start, q_stop) 
     return out
 
 
+def build_idx_rg(ctx: Context, start, stop, iv_off, want_blob=True):
+    """gams::build_idx_rg (redis.rs:276-305): Lapper::new + bincode per ctg segment, on the device.
+    start/stop: the intervals [s, e+1) of every segment back to back, any order inside a segment.
+    Returns dict(iv_start, iv_stop, starts, stops, max_len, blob, blob_off): blob_off[s] = 24*iv_off[s] + 30*s."""
+    start, stop, iv_off = _arr(start, np.uint32), _arr(stop, np.uint32), _arr(iv_off, np.uint64)
+    n_seg, n = iv_off.size - 1, int(iv_off[-1])
+    out = {k: np.empty(n, dtype=np.uint32) for k in ("iv_start", "iv_stop", "starts", "stops")}
+    out["max_len"] = np.empty(n_seg, dtype=np.uint32)
+    out["blob_off"] = 24 * iv_off + 30 * np.arange(n_seg + 1, dtype=np.uint64)
+    out["blob"] = np.empty(int(out["blob_off"][-1]), dtype=np.uint8) if want_blob else None
+    check(load().gams_cuda_build_idx_rg(ctx.handle, n_seg, _p(start), _p(stop), _p(iv_off), _p(out["iv_start"]), _p(out["iv_stop"]),
+                                        _p(out["starts"]), _p(out["stops"]), _p(out["max_len"]), _p(out["blob"])))
+    return out
+
+
 def locate_ctg(ctx: Context, ctg_start, ctg_stop, chr_off, q_chr, q_start, q_stop) -> np.ndarray:
     """Batched gams::find_one_idx → global ctg index or -1."""
     ctg_start, ctg_stop = _arr(ctg_start, np.uint32), _arr(ctg_stop, np.uint32)

@@ -1,0 +1,179 @@
+// idx_build.cu — the rg index of a ctg set, built on the device.
+//
+// Replaces the tail of `gams rg`: gams::build_idx_rg (src/libs/redis.rs:276-305) = per ctg
+//   rust_lapper::Lapper::new(intervals)  — sort the intervals by (start, stop); starts[] and stops[] sorted on their own;
+//                                          max_len = max(stop - start), 0 for stop < start (rust-lapper 1.1.0 lib.rs `new`)
+//   bincode::serialize(&lapper)          — the blob stored under idx:rg:{ctg} (layout: SURVEY.md §8 a14, restated in
+//                                          oracle/oracle.py lapper_to_bincode; "parity unpinned": no reference test reads bytes)
+// What leaves the device is exactly what gams_cuda_count_overlaps consumes (starts[] / stops[] per segment), so the
+// index never has to round-trip through the host when queries follow.
+//
+// Sorting is cub::DeviceSegmentedSort (CUDA toolkit, library code: segments of any size in one call) on 64-bit keys
+// start << 32 | stop; everything around it (key packing, unpacking, per-segment max_len, the blob bytes) is written here.
+// Bound: HBM; ~56 B moved per interval by our kernels + the sort's passes.  Not on BASELINE's timed path.
+#include "common.cuh"
+#include <cub/device/device_segmented_sort.cuh>
+
+namespace gams {
+
+__global__ void __launch_bounds__(256)
+idx_pack_kernel(const uint32_t *__restrict__ start, const uint32_t *__restrict__ stop, uint64_t n, uint64_t *__restrict__ key) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        key[i] = ((uint64_t)start[i] << 32) | (uint64_t)stop[i];
+}
+
+// sorted keys -> the interval columns; starts[] is the start column itself (sorted by start first)
+__global__ void __launch_bounds__(256)
+idx_unpack_kernel(const uint64_t *__restrict__ key, uint64_t n, uint32_t *__restrict__ iv_start, uint32_t *__restrict__ iv_stop,
+                  uint32_t *__restrict__ starts) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint64_t k = key[i];
+        const uint32_t s = (uint32_t)(k >> 32), e = (uint32_t)k;
+        iv_start[i] = s;
+        iv_stop[i] = e;
+        starts[i] = s;
+    }
+}
+
+// one CTA per segment (grid-stride over segments): max_len, then the segment's bincode blob in 16-bit units
+// (blob offset 24 iv_off[s] + 30 s is even, not always a multiple of 4)
+__global__ void __launch_bounds__(256)
+idx_blob_kernel(const uint32_t *__restrict__ iv_start, const uint32_t *__restrict__ iv_stop, const uint32_t *__restrict__ starts,
+                const uint32_t *__restrict__ stops, const uint64_t *__restrict__ iv_off, int64_t n_seg,
+                uint32_t *__restrict__ max_len, uint8_t *__restrict__ blob) {
+    __shared__ uint32_t red[8];
+    __shared__ uint32_t ml_sh;
+    for (int64_t s = blockIdx.x; s < n_seg; s += gridDim.x) {
+        const uint64_t o = iv_off[s], n = iv_off[s + 1] - o;
+        uint32_t ml = 0;
+        for (uint64_t i = threadIdx.x; i < n; i += blockDim.x) {
+            const uint32_t a = iv_start[o + i], b = iv_stop[o + i];
+            ml = max(ml, b >= a ? b - a : 0u);   // checked_sub(..).unwrap_or(0)
+        }
+        ml = __reduce_max_sync(0xFFFFFFFFu, ml);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ml;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t m = 0;
+            for (int w = 0; w < 8; ++w) m = max(m, red[w]);
+            ml_sh = m;
+            max_len[s] = m;
+        }
+        __syncthreads();
+        if (blob) {
+            const uint32_t mlen = ml_sh;
+            uint16_t *out = reinterpret_cast<uint16_t *>(blob + 24 * o + 30 * (uint64_t)s);
+            const uint64_t units = 12 * n + 15;
+            // byte offsets: [0,8) n | [8, 8+16n) {start, stop, u64 len("") = 0} | +8 n | +4n starts | +8 n | +4n stops | max_len | 0 | 0
+            const uint64_t b_iv = 8, b_n2 = 8 + 16 * n, b_st = b_n2 + 8, b_n3 = b_st + 4 * n, b_sp = b_n3 + 8, b_ml = b_sp + 4 * n;
+            for (uint64_t u = threadIdx.x; u < units; u += blockDim.x) {
+                const uint64_t b = 2 * u;
+                uint64_t word = 0;      // the 8-byte (or 4-byte) field the unit lies in, and the unit's byte offset inside it
+                uint32_t in = 0;
+                if (b < b_iv) { word = n; in = (uint32_t)b; }
+                else if (b < b_n2) {
+                    const uint64_t r = b - b_iv, i = r >> 4;
+                    const uint32_t f = (uint32_t)(r & 15);
+                    if (f < 4) { word = iv_start[o + i]; in = f; }
+                    else if (f < 8) { word = iv_stop[o + i]; in = f - 4; }
+                    else { word = 0; in = 0; }
+                }
+                else if (b < b_st) { word = n; in = (uint32_t)(b - b_n2); }
+                else if (b < b_n3) { const uint64_t r = b - b_st; word = starts[o + (r >> 2)]; in = (uint32_t)(r & 3); }
+                else if (b < b_sp) { word = n; in = (uint32_t)(b - b_n3); }
+                else if (b < b_ml) { const uint64_t r = b - b_sp; word = stops[o + (r >> 2)]; in = (uint32_t)(r & 3); }
+                else if (b < b_ml + 4) { word = mlen; in = (uint32_t)(b - b_ml); }
+                else { word = 0; in = 0; }   // cov: None (tag 0), overlaps_merged: false
+                out[u] = (uint16_t)(word >> (8 * in));
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// All pointers device memory.  d_key_a / d_key_b: n u64 each; d_tmp_stop: n u32; d_cub: cub_bytes of sort workspace.
+size_t idx_sort_workspace(uint64_t n, int64_t n_seg) {
+    size_t a = 0, b = 0;
+    cub::DeviceSegmentedSort::SortKeys(nullptr, a, (const uint64_t *)nullptr, (uint64_t *)nullptr, (int)n, (int)n_seg,
+                                       (const uint64_t *)nullptr, (const uint64_t *)nullptr);
+    cub::DeviceSegmentedSort::SortKeys(nullptr, b, (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)n, (int)n_seg,
+                                       (const uint64_t *)nullptr, (const uint64_t *)nullptr);
+    return std::max(a, b) + 256;
+}
+
+int32_t launch_build_idx(cudaStream_t st, int64_t n_seg, uint64_t n, const uint32_t *d_start, const uint32_t *d_stop,
+                         const uint64_t *d_iv_off, uint64_t *d_key_a, uint64_t *d_key_b, void *d_cub, size_t cub_bytes,
+                         uint32_t *d_iv_start, uint32_t *d_iv_stop, uint32_t *d_starts, uint32_t *d_stops, uint32_t *d_max_len,
+                         uint8_t *d_blob) {
+    if (n_seg == 0) return GAMS_CUDA_OK;
+    if (n) {
+        const unsigned blocks = (unsigned)std::min<uint64_t>((n + 255) / 256, 148ull * 32);
+        idx_pack_kernel<<<blocks, 256, 0, st>>>(d_start, d_stop, n, d_key_a);
+        size_t wb = cub_bytes;
+        CUDA_TRY(cub::DeviceSegmentedSort::SortKeys(d_cub, wb, d_key_a, d_key_b, (int)n, (int)n_seg, d_iv_off, d_iv_off + 1, st));
+        idx_unpack_kernel<<<blocks, 256, 0, st>>>(d_key_b, n, d_iv_start, d_iv_stop, d_starts);
+        wb = cub_bytes;
+        CUDA_TRY(cub::DeviceSegmentedSort::SortKeys(d_cub, wb, d_stop, d_stops, (int)n, (int)n_seg, d_iv_off, d_iv_off + 1, st));
+    }
+    const unsigned sb = (unsigned)std::min<int64_t>(n_seg, 148 * 8);
+    idx_blob_kernel<<<sb, 256, 0, st>>>(d_iv_start, d_iv_stop, d_starts, d_stops, d_iv_off, n_seg, d_max_len, d_blob);
+    CUDA_TRY(cudaGetLastError());
+    return GAMS_CUDA_OK;
+}
+
+}  // namespace gams
+
+using namespace gams;
+
+// Host entry point (declared in include/gams_cuda.h).
+GAMS_API int32_t gams_cuda_build_idx_rg(gams_cuda_ctx *ctx, int64_t n_seg, const uint32_t *start, const uint32_t *stop,
+                                        const uint64_t *iv_off, uint32_t *iv_start, uint32_t *iv_stop, uint32_t *starts,
+                                        uint32_t *stops, uint32_t *max_len, uint8_t *blob) {
+    ARG_CHECK(ctx && iv_off && n_seg >= 0, "build_idx_rg: bad argument");
+    if (n_seg == 0) return GAMS_CUDA_OK;
+    ARG_CHECK(iv_off[0] == 0, "build_idx_rg: iv_off[0] must be 0");
+    for (int64_t s = 0; s < n_seg; ++s) ARG_CHECK(iv_off[s + 1] >= iv_off[s], "build_idx_rg: iv_off decreases at %lld", (long long)s);
+    const uint64_t n = iv_off[n_seg];
+    ARG_CHECK(n < (1ull << 31) && n_seg < (1ll << 31), "build_idx_rg: more than 2^31 intervals or segments in one call");
+    ARG_CHECK(max_len != nullptr, "build_idx_rg: max_len is NULL");
+    ARG_CHECK(n == 0 || (start && stop && iv_start && iv_stop && starts && stops), "build_idx_rg: NULL interval array");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    PerDevice &pd = ctx->devs[0];
+    DeviceGuard g(pd.device);
+    cudaStream_t st = pd.stream;
+    const uint64_t np = std::max<uint64_t>(n, 1);
+    const size_t cub_bytes = idx_sort_workspace(n, n_seg);
+    const uint64_t blob_bytes = blob ? 24 * n + 30 * (uint64_t)n_seg : 0;
+    int32_t rc;
+    // [1] inputs + offsets, [2] keys (two u64 buffers), [3] outputs (4 u32 columns + max_len), [4] sort workspace, [5] blob
+    if ((rc = pd.scratch[1].reserve(np * 8 + (uint64_t)(n_seg + 1) * 8 + 64))) return rc;
+    if ((rc = pd.scratch[2].reserve(np * 16 + 64))) return rc;
+    if ((rc = pd.scratch[3].reserve(np * 16 + (uint64_t)n_seg * 4 + 64))) return rc;
+    if ((rc = pd.scratch[4].reserve(cub_bytes))) return rc;
+    if ((rc = pd.scratch[5].reserve(blob_bytes + 64))) return rc;
+    uint64_t *d_off = pd.scratch[1].as<uint64_t>();
+    uint32_t *d_start = reinterpret_cast<uint32_t *>(d_off + (n_seg + 1)), *d_stop = d_start + np;
+    uint64_t *d_ka = pd.scratch[2].as<uint64_t>(), *d_kb = d_ka + np;
+    uint32_t *d_ivs = pd.scratch[3].as<uint32_t>(), *d_ive = d_ivs + np, *d_sts = d_ive + np, *d_sps = d_sts + np, *d_ml = d_sps + np;
+    uint8_t *d_blob = blob ? pd.scratch[5].as<uint8_t>() : nullptr;
+    CUDA_TRY(cudaMemcpyAsync(d_off, iv_off, (uint64_t)(n_seg + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (n) {
+        CUDA_TRY(cudaMemcpyAsync(d_start, start, n * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d_stop, stop, n * 4, cudaMemcpyHostToDevice, st));
+    }
+    if ((rc = launch_build_idx(st, n_seg, n, d_start, d_stop, d_off, d_ka, d_kb, pd.scratch[4].p, cub_bytes, d_ivs, d_ive, d_sts,
+                               d_sps, d_ml, d_blob)))
+        return rc;
+    if (n) {
+        CUDA_TRY(cudaMemcpyAsync(iv_start, d_ivs, n * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(iv_stop, d_ive, n * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(starts, d_sts, n * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(stops, d_sps, n * 4, cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_TRY(cudaMemcpyAsync(max_len, d_ml, (uint64_t)n_seg * 4, cudaMemcpyDeviceToHost, st));
+    if (blob) CUDA_TRY(cudaMemcpyAsync(blob, d_blob, blob_bytes, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return GAMS_CUDA_OK;
+}

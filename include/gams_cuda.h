@@ -248,6 +248,20 @@ int32_t gams_cuda_count_overlaps_dev(gams_cuda_count_plan *plan, void *stream, c
                                      int32_t grouped, uint32_t *d_out);
 uint64_t gams_cuda_count_plan_launches(const gams_cuda_count_plan *plan);
 
+/* gams::build_idx_rg (src/libs/redis.rs:276-305): rust_lapper::Lapper::new + bincode::serialize per ctg, on the
+ * device.  Input: the intervals of segment s (one ctg) are start[i], stop[i] for i in [iv_off[s], iv_off[s+1]),
+ * in any order, stop = rg.end + 1 as redis.rs:291-295 builds them.  Output, segment by segment at the same offsets:
+ *   iv_start/iv_stop  the intervals sorted by (start, stop)            (Lapper.intervals; val is "" for rg)
+ *   starts, stops     each endpoint array sorted on its own            (Lapper.starts / Lapper.stops: what
+ *                                                                        gams_cuda_count_overlaps consumes)
+ *   max_len[s]        max(stop - start), 0 where stop < start          (Lapper.max_len)
+ *   blob (optional)   the bincode 1.3 bytes of every Lapper back to back, segment s at byte 24*iv_off[s] + 30*s,
+ *                     24*n_s + 30 bytes each (layout: SURVEY.md section 8 a14) -- what `SET idx:rg:{ctg}` stores.
+ * At most 2^31 - 1 intervals per call. */
+int32_t gams_cuda_build_idx_rg(gams_cuda_ctx *ctx, int64_t n_seg, const uint32_t *start, const uint32_t *stop,
+                               const uint64_t *iv_off, uint32_t *iv_start, uint32_t *iv_stop, uint32_t *starts,
+                               uint32_t *stops, uint32_t *max_len, uint8_t *blob /* NULL: no blobs */);
+
 /* gams::find_one_idx (utils.rs:7-22) -> Lapper::find(start, stop).next() on the idx:ctg:{chr}
  * index: ctg intervals [chr_start, chr_end+1) sorted by start within each chromosome segment.
  * out[q] = global index of the first ctg (in start order) with ctg_start < q_stop && ctg_stop >

@@ -122,6 +122,10 @@ extern "C" {
         d_q_seg: *const i32, d_q_start: *const u32, d_q_stop: *const u32, grouped: i32, d_out: *mut u32,
     ) -> i32;
     pub fn gams_cuda_count_plan_launches(plan: *const gams_cuda_count_plan) -> u64;
+    pub fn gams_cuda_build_idx_rg(
+        ctx: *mut gams_cuda_ctx, n_seg: i64, start: *const u32, stop: *const u32, iv_off: *const u64,
+        iv_start: *mut u32, iv_stop: *mut u32, starts: *mut u32, stops: *mut u32, max_len: *mut u32, blob: *mut u8,
+    ) -> i32;
     pub fn gams_cuda_locate_ctg(
         ctx: *mut gams_cuda_ctx, n_chr: i64, ctg_start: *const u32, ctg_stop: *const u32, chr_off: *const u64,
         n_q: i64, q_chr: *const i32, q_start: *const u32, q_stop: *const u32, out: *mut i32,

@@ -723,3 +723,68 @@ def test_anno_coverage(ctx, orc, s288c):
         ref = orc.anno_prop(sets[c] if 0 <= c < len(sets) else None, int(ctg_s[i]), int(ctg_e[i]), int(q_s[i]), int(q_e[i]))
         assert np.float32(got[i]).view(np.uint32) == np.float32(ref).view(np.uint32), (i, got[i], ref)
     assert float(got.max()) <= 1.0 and float(got.min()) >= 0.0
+
+
+# ------------------------------------------------------------------------------------------------ index build
+def _check_idx(ctx, orc, per_seg):
+    """per_seg: list of lists of (start, stop) in input order → device index == Lapper::new + bincode of the oracle."""
+    iv_off = np.concatenate(([0], np.cumsum([len(v) for v in per_seg]))).astype(np.uint64)
+    flat = [iv for v in per_seg for iv in v]
+    start = np.array([a for a, _ in flat], dtype=np.uint32)
+    stop = np.array([b for _, b in flat], dtype=np.uint32)
+    got = api.build_idx_rg(ctx, start, stop, iv_off)
+    for s, v in enumerate(per_seg):
+        lp = orc.lapper_new([(a, b, "") for a, b in v])
+        a, b = int(iv_off[s]), int(iv_off[s + 1])
+        _eq(f"seg {s} iv_start", got["iv_start"][a:b], lp["start"])
+        _eq(f"seg {s} iv_stop", got["iv_stop"][a:b], lp["stop"])
+        _eq(f"seg {s} starts", got["starts"][a:b], lp["starts"])
+        _eq(f"seg {s} stops", got["stops"][a:b], lp["stops"])
+        assert int(got["max_len"][s]) == lp["max_len"], (s, int(got["max_len"][s]), lp["max_len"])
+        blob = got["blob"][int(got["blob_off"][s]):int(got["blob_off"][s + 1])].tobytes()
+        assert blob == orc.lapper_to_bincode(lp), f"seg {s}: bincode blob differs"
+        st, sp, ml = api.lapper_blob_view(blob)   # and the blob parses back through the library's own reader
+        assert np.array_equal(st, lp["starts"]) and np.array_equal(sp, lp["stops"]) and ml == lp["max_len"]
+    return got, iv_off
+
+
+def test_build_idx_rg_fixture(ctx, orc, s288c):
+    """`gams rg tests/S288c/SK1.snp.rg` tail: the idx:rg:* blobs (redis.rs:276-305), then cli.rs:449's `I:1000-2000 -> 12`
+    counted on the device-built index."""
+    ctgs, ids, idx_ctg, idx_rg, starts, stops, iv_off = _fixture_index(orc, s288c)
+    rng = np.random.default_rng(3)
+    per_seg = []
+    for cid in ids:
+        lp = idx_rg.get(cid, orc.lapper_new([]))
+        order = rng.permutation(lp["start"].size)           # the loader sees them in file order, not sorted
+        per_seg.append([(int(lp["start"][i]), int(lp["stop"][i])) for i in order])
+    got, off = _check_idx(ctx, orc, per_seg)
+    _eq("starts vs fixture index", got["starts"], starts)
+    _eq("stops vs fixture index", got["stops"], stops)
+    seg = np.array([ids.index("ctg:I:1")], dtype=np.int32)
+    assert api.count_overlaps(ctx, got["starts"], got["stops"], off, seg, np.array([1000], np.uint32), np.array([2000], np.uint32)).tolist() == [12]
+
+
+def test_build_idx_rg_synthetic(ctx, orc):
+    """Ties on start (order decided by stop), duplicates, stop < start (max_len clamps to 0), empty and single-interval
+    segments, a segment larger than any shared-memory sort would hold, coordinates above 2^31."""
+    rng = np.random.default_rng(17)
+    def rand_seg(n, lo, hi, max_len):
+        s = rng.integers(lo, hi, n)
+        return [(int(a), int(a) + int(l)) for a, l in zip(s, rng.integers(1, max_len + 1, n))]
+    per_seg = [
+        rand_seg(5000, 1, 2000, 3),                      # many equal starts, few distinct stops
+        [],
+        [(7, 8)],
+        [(10, 5), (10, 12), (3, 3), (10, 11), (3, 2)],   # stop < start, ties
+        rand_seg(70_000, 1, 1_000_000, 500),
+        rand_seg(1000, 2**31 - 100, 2**32 - 600, 500),
+        [(5, 6)] * 300,
+        [],
+    ]
+    _check_idx(ctx, orc, per_seg)
+    # no blob wanted, and an entirely empty index
+    got = api.build_idx_rg(ctx, np.array([4, 2], np.uint32), np.array([9, 3], np.uint32), np.array([0, 2], np.uint64), want_blob=False)
+    assert got["blob"] is None and got["iv_start"].tolist() == [2, 4] and got["stops"].tolist() == [3, 9] and got["max_len"].tolist() == [5]
+    got = api.build_idx_rg(ctx, np.zeros(0, np.uint32), np.zeros(0, np.uint32), np.array([0, 0, 0], np.uint64))
+    assert got["blob"].tobytes() == orc.lapper_to_bincode(orc.lapper_new([])) * 2
