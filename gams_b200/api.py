@@ -386,3 +386,44 @@ class CountPlan:
             self.close()
         except Exception:
             pass
+
+
+# --------------------------------------------------------------- window.rs:78-94 x utils.rs:24-36
+def count_windows(ctx: Context, chr_start, win_off, size, step, starts, stops, iv_off) -> np.ndarray:
+    """count_rg of every sliding window of every ctg (window k of ctg c = [chr_start[c] + k*step, + size - 1])."""
+    chr_start, win_off = _arr(chr_start, np.int32), _arr(win_off, np.uint64)
+    starts, stops, iv_off = _arr(starts, np.uint32), _arr(stops, np.uint32), _arr(iv_off, np.uint64)
+    out = np.empty(int(win_off[-1]), dtype=np.uint32)
+    check(load().gams_cuda_count_windows(ctx.handle, chr_start.size, _p(chr_start), _p(win_off), size, step, _p(starts), _p(stops),
+                                         _p(iv_off), _p(out)))
+    return out
+
+
+class CountWindowsPlan:
+    """gams_cuda_cwin_plan: window geometry + index offsets of a ctg set bound to one device; index and counts stay in HBM."""
+
+    def __init__(self, ctx: Context, chr_start, win_off, size, step, iv_off, dev_index=0):
+        self._L = load()
+        chr_start, win_off, iv_off = _arr(chr_start, np.int32), _arr(win_off, np.uint64), _arr(iv_off, np.uint64)
+        h = C.c_void_p()
+        check(self._L.gams_cuda_cwin_plan_create(ctx.handle, dev_index, chr_start.size, _p(chr_start), _p(win_off), size, step,
+                                                 _p(iv_off), C.byref(h)))
+        self._h, self._ctx = h, ctx
+
+    @property
+    def total_windows(self) -> int:
+        return int(self._L.gams_cuda_cwin_plan_total_windows(self._h))
+
+    def count(self, stream: int, d_starts, d_stops, d_out):
+        check(self._L.gams_cuda_count_windows_dev(self._h, stream, d_starts.data_ptr(), d_stops.data_ptr(), d_out.data_ptr()))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.gams_cuda_cwin_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -42,6 +42,7 @@ extern "C" {
 typedef struct gams_cuda_ctx gams_cuda_ctx;
 typedef struct gams_cuda_wave_plan gams_cuda_wave_plan;
 typedef struct gams_cuda_count_plan gams_cuda_count_plan;
+typedef struct gams_cuda_cwin_plan gams_cuda_cwin_plan;
 
 /* ---------------------------------------------------------------- lifecycle ---------------- */
 int32_t gams_cuda_version(void); /* 10000*major + 100*minor + patch */
@@ -247,6 +248,26 @@ int32_t gams_cuda_count_overlaps_dev(gams_cuda_count_plan *plan, void *stream, c
                                      const uint32_t *d_q_start, const uint32_t *d_q_stop,
                                      int32_t grouped, uint32_t *d_out);
 uint64_t gams_cuda_count_plan_launches(const gams_cuda_count_plan *plan);
+
+/* rg counts along sliding windows: what the reference computes when gams::sliding (src/libs/window.rs:78-94) is
+ * walked and gams::count_rg (src/libs/utils.rs:24-36) is asked for every window -- the "sliding" / "fsw ... rg counting"
+ * workload of BASELINE configs[1].  Window k of ctg c is [ws, we] = [chr_start[c] + k*step, ws + size - 1];
+ *   out[win_off[c] + k] = lower_bound(starts_c, we) - lower_bound(stops_c, ws + 1)
+ * exactly as gams_cuda_count_overlaps answers the query (seg c, ws, we), but with no query arrays at all: the keys are
+ * an arithmetic progression, so each tile of windows is one histogram + prefix sum over its slice of the index.
+ * win_off: as gams_cuda_wave_win_offsets returns it (n_ctg + 1); the index of ctg c is segment c of starts/stops/iv_off
+ * (an empty segment counts 0 everywhere). */
+int32_t gams_cuda_count_windows(gams_cuda_ctx *ctx, int64_t n_ctg, const int32_t *chr_start, const uint64_t *win_off,
+                                int32_t size, int32_t step, const uint32_t *starts, const uint32_t *stops,
+                                const uint64_t *iv_off, uint32_t *out);
+/* Device API: geometry and offsets are bound in a plan (host arrays, copied); the index and the counts stay in HBM. */
+int32_t gams_cuda_cwin_plan_create(gams_cuda_ctx *ctx, int32_t dev_index, int64_t n_ctg, const int32_t *chr_start,
+                                   const uint64_t *win_off, int32_t size, int32_t step, const uint64_t *iv_off,
+                                   gams_cuda_cwin_plan **out);
+void gams_cuda_cwin_plan_destroy(gams_cuda_cwin_plan *plan);
+uint64_t gams_cuda_cwin_plan_total_windows(const gams_cuda_cwin_plan *plan);
+int32_t gams_cuda_count_windows_dev(gams_cuda_cwin_plan *plan, void *stream, const uint32_t *d_starts,
+                                    const uint32_t *d_stops, uint32_t *d_out);
 
 /* gams::build_idx_rg (src/libs/redis.rs:276-305): rust_lapper::Lapper::new + bincode::serialize per ctg, on the
  * device.  Input: the intervals of segment s (one ctg) are start[i], stop[i] for i in [iv_off[s], iv_off[s+1]),

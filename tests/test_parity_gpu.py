@@ -788,3 +788,48 @@ def test_build_idx_rg_synthetic(ctx, orc):
     assert got["blob"] is None and got["iv_start"].tolist() == [2, 4] and got["stops"].tolist() == [3, 9] and got["max_len"].tolist() == [5]
     got = api.build_idx_rg(ctx, np.zeros(0, np.uint32), np.zeros(0, np.uint32), np.array([0, 0, 0], np.uint64))
     assert got["blob"].tobytes() == orc.lapper_to_bincode(orc.lapper_new([])) * 2
+
+
+# ------------------------------------------------------------------------------------------------ counts along windows
+def _ref_count_windows(orc, chr_start, lens, size, step, st, sp, off):
+    seg, ws, we, woff = [], [], [], [0]
+    for c, (cs, ln) in enumerate(zip(chr_start, lens)):
+        n = orc.nwin(ln, size, step)
+        k = np.arange(n, dtype=np.int64)
+        seg.append(np.full(n, c, np.int32)); ws.append(cs + k * step); we.append(cs + k * step + size - 1)
+        woff.append(woff[-1] + n)
+    seg, ws, we = np.concatenate(seg), np.concatenate(ws).astype(np.uint32), np.concatenate(we).astype(np.uint32)
+    return np.asarray(woff, np.uint64), orc.count_batch(st, sp, off, seg, ws, we, threads=8)
+
+
+@pytest.mark.parametrize("size,step,max_len", [(100, 10, 1), (100, 10, 300), (100, 100, 1), (50, 7, 40), (1, 1, 1), (1000, 3, 5)])
+def test_count_windows_matches_count_rg(ctx, orc, size, step, max_len):
+    """Sliding windows x rg index == count_rg per window (utils.rs:24-36 on window.rs:78-94), incl. ctgs shorter than a
+    window, ctgs without intervals, intervals before / after the ctg's windows, many tiles per ctg."""
+    lens = [230_218, 85_779, 60, 5_000, 1_000_003, 99, 100]
+    chr_start = [1, 100_001, 7, 2_000_000, 1, 1, 1]
+    npc = [9000, 0, 5, 700, 60_000, 3, 1]
+    rng = np.random.default_rng(size * 31 + step)
+    starts, stops, off = [], [], [0]
+    for cs, ln, k in zip(chr_start, lens, npc):
+        s = rng.integers(max(1, cs - 500), cs + ln + 500, k)       # some intervals outside the ctg's range
+        e = s + rng.integers(1, max_len + 1, k)
+        starts.append(np.sort(s).astype(np.uint32)); stops.append(np.sort(e).astype(np.uint32)); off.append(off[-1] + k)
+    st, sp, off = np.concatenate(starts), np.concatenate(stops), np.asarray(off, np.uint64)
+    woff, ref = _ref_count_windows(orc, chr_start, lens, size, step, st, sp, off)
+    got = api.count_windows(ctx, chr_start, woff, size, step, st, sp, off)
+    _eq(f"count_windows[{size}/{step}]", got, ref)
+
+
+def test_count_windows_fixture(ctx, orc, s288c):
+    """BASELINE configs[1]: S288c sliding 100/10 with SK1.snp.rg counting; the window starting at I:1000 of size 1001
+    reproduces cli.rs:449's `I:1000-2000 -> 12`."""
+    ctgs, ids, idx_ctg, idx_rg, starts, stops, iv_off = _fixture_index(orc, s288c)
+    chr_start = [c[2] for c in ctgs]
+    lens = [c[3] - c[2] + 1 for c in ctgs]
+    woff, ref = _ref_count_windows(orc, chr_start, lens, 100, 10, starts, stops, iv_off)
+    _eq("fixture 100/10", api.count_windows(ctx, chr_start, woff, 100, 10, starts, stops, iv_off), ref)
+    woff, ref = _ref_count_windows(orc, chr_start, lens, 1001, 1, starts, stops, iv_off)
+    got = api.count_windows(ctx, chr_start, woff, 1001, 1, starts, stops, iv_off)
+    _eq("fixture 1001/1", got, ref)
+    assert ids[0] == "ctg:I:1" and int(got[999]) == 12      # window 999 of ctg:I:1 is I:1000-2000
