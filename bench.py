@@ -672,6 +672,41 @@ def bench_count(args, ctx, L, dev, rank, world, g_off, barrier, max_over_ranks, 
                                        "single_thread": {"value": k1 / dt1, "sample": f"first {k1} queries"}}
         del q_seg, q_s, q_e, d_out
     plan.close()
+    # rg counts along every sliding window of the genome (gams::sliding x count_rg): no query arrays, 4 B per window out
+    chr_start = np.ones(n_ctg, dtype=np.int32)
+    woff = np.zeros(n_ctg + 1, dtype=np.uint64)
+    woff[1:] = np.cumsum([max(0, (int(x) - SIZE) // STEP + 1) if x >= SIZE else 0 for x in lens])
+    wplan = api.CountWindowsPlan(ctx, chr_start, woff, SIZE, STEP, iv_off)
+    n_w = int(woff[-1])
+    d_cnt = torch.empty(n_w, dtype=torch.int32, device=dev)
+    for _ in range(args.warmup):
+        wplan.count(stream, d_st, d_sp, d_cnt)
+    lw0 = wplan.launches
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        wplan.count(stream, d_st, d_sp, d_cnt)
+    t1.record()
+    barrier()
+    ms = max_over_ranks(t0.elapsed_time(t1)) / args.steps
+    alg = n_w * 4 + n_iv * 8
+    res = {"value": sum_over_ranks(float(n_w)) / (ms * 1e-3), "unit": "window counts/s", "ms_per_step": ms, "windows": n_w,
+           "intervals": n_iv, "gpu_launches": int(wplan.launches - lw0),
+           "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": alg / (ms * 1e-3) / 1e9 / hbm_peak, "kernel": "cw_tile_kernel (per-tile descriptors built once per index by cw_desc_kernel)",
+                        "traffic": ncu_traffic("count_windows"), "algorithmic_bytes_per_launch": alg, "peak_source": peak_src}}
+    if rank == 0:
+        from oracle import oracle as orc
+        k = 200_000
+        sel = np.sort(np.random.default_rng(5).integers(0, n_w, k))
+        c = np.searchsorted(woff, sel, side="right") - 1
+        ws = (1 + (sel - woff[c].astype(np.int64)) * STEP).astype(np.uint32)
+        ref = orc.count_batch(d_st.cpu().numpy().view(np.uint32), d_sp.cpu().numpy().view(np.uint32), iv_off, c.astype(np.int32), ws,
+                              (ws + np.uint32(SIZE - 1)), threads=os.cpu_count() or 1)
+        res["bit_exact_sample"] = bool(np.array_equal(d_cnt[torch.as_tensor(sel, device=dev)].cpu().numpy().view(np.uint32), ref))
+    out["sliding_windows"] = res
+    wplan.close()
     return out
 
 

@@ -86,6 +86,8 @@ def load() -> C.CDLL:
         "gams_cuda_cwin_plan_create": (i32, [vp, i32, i64, vp, vp, i32, i32, vp, C.POINTER(vp)]),
         "gams_cuda_cwin_plan_destroy": (None, [vp]),
         "gams_cuda_cwin_plan_total_windows": (u64, [vp]),
+        "gams_cuda_cwin_plan_launches": (u64, [vp]),
+        "gams_cuda_cwin_plan_invalidate": (None, [vp]),
         "gams_cuda_count_windows_dev": (i32, [vp, vp, vp, vp, vp]),
         "gams_cuda_build_idx_rg": (i32, [vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "gams_cuda_locate_ctg": (i32, [vp, i64, vp, vp, vp, i64, vp, vp, vp, vp]),

@@ -417,6 +417,13 @@ class CountWindowsPlan:
     def count(self, stream: int, d_starts, d_stops, d_out):
         check(self._L.gams_cuda_count_windows_dev(self._h, stream, d_starts.data_ptr(), d_stops.data_ptr(), d_out.data_ptr()))
 
+    @property
+    def launches(self) -> int:
+        return int(self._L.gams_cuda_cwin_plan_launches(self._h))
+
+    def invalidate(self):
+        self._L.gams_cuda_cwin_plan_invalidate(self._h)
+
     def close(self):
         if getattr(self, "_h", None):
             self._L.gams_cuda_cwin_plan_destroy(self._h)

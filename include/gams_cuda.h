@@ -266,6 +266,10 @@ int32_t gams_cuda_cwin_plan_create(gams_cuda_ctx *ctx, int32_t dev_index, int64_
                                    gams_cuda_cwin_plan **out);
 void gams_cuda_cwin_plan_destroy(gams_cuda_cwin_plan *plan);
 uint64_t gams_cuda_cwin_plan_total_windows(const gams_cuda_cwin_plan *plan);
+uint64_t gams_cuda_cwin_plan_launches(const gams_cuda_cwin_plan *plan);
+/* The per-tile slices of the index are found once per (d_starts, d_stops) pair and kept in the plan; call this after
+ * rewriting the index in place under the same pointers. */
+void gams_cuda_cwin_plan_invalidate(gams_cuda_cwin_plan *plan);
 int32_t gams_cuda_count_windows_dev(gams_cuda_cwin_plan *plan, void *stream, const uint32_t *d_starts,
                                     const uint32_t *d_stops, uint32_t *d_out);
 

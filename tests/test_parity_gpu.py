@@ -802,7 +802,8 @@ def _ref_count_windows(orc, chr_start, lens, size, step, st, sp, off):
     return np.asarray(woff, np.uint64), orc.count_batch(st, sp, off, seg, ws, we, threads=8)
 
 
-@pytest.mark.parametrize("size,step,max_len", [(100, 10, 1), (100, 10, 300), (100, 100, 1), (50, 7, 40), (1, 1, 1), (1000, 3, 5)])
+@pytest.mark.parametrize("size,step,max_len", [(100, 10, 1), (100, 10, 300), (100, 100, 1), (50, 7, 40), (1, 1, 1), (1000, 3, 5),
+                                                (3000, 1500, 50), (200, 1023, 2), (5, 2, 9)])
 def test_count_windows_matches_count_rg(ctx, orc, size, step, max_len):
     """Sliding windows x rg index == count_rg per window (utils.rs:24-36 on window.rs:78-94), incl. ctgs shorter than a
     window, ctgs without intervals, intervals before / after the ctg's windows, many tiles per ctg."""
