@@ -619,13 +619,11 @@ int32_t launch_count_overlaps(gams_cuda_count_plan *p, cudaStream_t st, const ui
     if (n_q == 0) return GAMS_CUDA_OK;
     if (grouped && p->mode == 0) {
         // staged path: q_seg is non-decreasing; each segment's compact index is staged in shared memory
-        static bool attr_set = false;
-        if (!attr_set) {
-            CUDA_TRY(cudaFuncSetAttribute(count_overlaps_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM));
-            attr_set = true;
-        }
         int32_t rc;
         if (!p->cidx_valid || p->cidx_starts != d_starts || p->cidx_stops != d_stops) {
+            // function attributes belong to the current device: set with every index build (a process-wide flag would
+            // leave the second device of a multi-device context at the 48 KB default)
+            CUDA_TRY(cudaFuncSetAttribute(count_overlaps_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM));
             if ((rc = build_compact_index(p, st, d_starts, d_stops))) return rc;
         }
         // items <= n_q / ST_CHUNK + n_seg; the CTAs beyond the actual count zero the out-of-index queries
