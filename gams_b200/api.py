@@ -434,3 +434,33 @@ class CountWindowsPlan:
             self.close()
         except Exception:
             pass
+
+
+# --------------------------------------------------------------- redis.rs:142-161 (get_seq -> decode_gz)
+def pack_blobs(blobs):
+    """bytes objects back to back → (uint8 array, uint64 offsets)."""
+    off = np.zeros(len(blobs) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([len(b) for b in blobs])
+    cat = np.frombuffer(b"".join(blobs), dtype=np.uint8) if blobs else np.zeros(0, np.uint8)
+    return cat, off
+
+
+def gz_sizes(gz_concat, gz_off) -> np.ndarray:
+    gz_concat, gz_off = _arr(gz_concat, np.uint8), _arr(gz_off, np.uint64)
+    out = np.empty(gz_off.size - 1, dtype=np.uint64)
+    check(load().gams_cuda_gz_sizes(gz_off.size - 1, _p(gz_concat), _p(gz_off), _p(out)))
+    return out
+
+
+def gunzip_batch(ctx: Context, gz_concat, gz_off, out_off=None, raise_on_error=True):
+    """decode_gz of a batch of seq:{ctg} blobs → (out_concat, out_off, status)."""
+    gz_concat, gz_off = _arr(gz_concat, np.uint8), _arr(gz_off, np.uint64)
+    if out_off is None:
+        out_off = np.concatenate(([0], np.cumsum(gz_sizes(gz_concat, gz_off)))).astype(np.uint64)
+    out_off = _arr(out_off, np.uint64)
+    out = np.empty(int(out_off[-1]), dtype=np.uint8)
+    status = np.zeros(gz_off.size - 1, dtype=np.int32)
+    rc = load().gams_cuda_gunzip_batch(ctx.handle, gz_off.size - 1, _p(gz_concat), _p(gz_off), _p(out_off), _p(out), _p(status))
+    if rc != 0 and (raise_on_error or not status.any()):
+        check(rc)
+    return out, out_off, status

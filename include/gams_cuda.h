@@ -249,6 +249,20 @@ int32_t gams_cuda_count_overlaps_dev(gams_cuda_count_plan *plan, void *stream, c
                                      int32_t grouped, uint32_t *d_out);
 uint64_t gams_cuda_count_plan_launches(const gams_cuda_count_plan *plan);
 
+/* Conn::get_seq's decode_gz (src/libs/redis.rs:142-161: flate2 GzDecoder over the `seq:{ctg}` value), batched, on the
+ * device: one gzip member (RFC 1952, deflate RFC 1951: stored / fixed / dynamic blocks) per blob, blobs back to back in
+ * gz_concat at gz_off[n_blob + 1].  Blob i inflates to out_concat[out_off[i] .. out_off[i+1]); the caller knows the sizes
+ * (ctg lengths) or reads them from the trailers with gams_cuda_gz_sizes.  Like GzDecoder only the first member of a blob is
+ * read.  ISIZE and the expected size are checked; the CRC-32 of the trailer is NOT verified (GzDecoder does verify it).
+ * status[i]: 0 ok, 1 bad gzip header, 2 invalid code / block, 3 output larger than expected, 4 distance before the start,
+ * 5 size mismatch, 6 truncated input.  Returns GAMS_CUDA_EINVAL if any blob failed (the good ones are still written). */
+int32_t gams_cuda_gz_sizes(int64_t n_blob, const uint8_t *gz_concat, const uint64_t *gz_off, uint64_t *out_len);
+int32_t gams_cuda_gunzip_batch(gams_cuda_ctx *ctx, int64_t n_blob, const uint8_t *gz_concat, const uint64_t *gz_off,
+                               const uint64_t *out_off, uint8_t *out_concat, int32_t *status);
+/* Device API: all pointers device memory (offsets relative to d_gz / d_out), asynchronous on `stream`. */
+int32_t gams_cuda_gunzip_dev(gams_cuda_ctx *ctx, int32_t dev_index, void *stream, int64_t n_blob, const uint8_t *d_gz,
+                             const uint64_t *d_gz_off, uint8_t *d_out, const uint64_t *d_out_off, int32_t *d_status);
+
 /* rg counts along sliding windows: what the reference computes when gams::sliding (src/libs/window.rs:78-94) is
  * walked and gams::count_rg (src/libs/utils.rs:24-36) is asked for every window -- the "sliding" / "fsw ... rg counting"
  * workload of BASELINE configs[1].  Window k of ctg c is [ws, we] = [chr_start[c] + k*step, ws + size - 1];

@@ -516,3 +516,24 @@ def count_rg(idx_rg, ctg_id, rg) -> int:
     if lp is None:
         return 0
     return lapper_count(lp["starts"], lp["stops"], rg[2], rg[3])
+
+
+# ----------------------------------------------------------------------------------------
+# Conn::get_seq -> decode_gz (redis.rs:142-161): flate2 1.0.30 GzDecoder::read_to_end.  The algorithm is RFC 1951/1952,
+# implemented by flate2's miniz_oxide backend (not vendored in the reference); the checker here is zlib, an independent
+# implementation of the same RFCs.  GzDecoder reads ONE member (MultiGzDecoder would read them all), so does this.
+# encode_gz (redis.rs:149-154) is GzEncoder with Compression::fast() = level 1.
+# ----------------------------------------------------------------------------------------
+def decode_gz(blob: bytes) -> bytes:
+    import zlib
+    d = zlib.decompressobj(wbits=31)
+    out = d.decompress(blob)
+    if not d.eof:
+        raise ValueError("truncated gzip member")
+    return out
+
+
+def encode_gz(seq: bytes, level: int = 1) -> bytes:
+    import zlib
+    c = zlib.compressobj(level, zlib.DEFLATED, 31)
+    return c.compress(seq) + c.flush()

@@ -43,4 +43,20 @@ with api.Context([0]) as ctx:
     assert lk["gc"].size == 3
     pr = api.anno_coverage(ctx, [5, 100], [50, 200], [0, 2], [0, 0, 1], [1, 1, 1], [1000, 1000, 10], [1, 40, 1], [300, 60, 5])
     assert pr.size == 3
+    # rg counts along sliding windows and the index build (non-point intervals, an empty segment)
+    st2, sp2, ioff2 = synth.rg_index(lens, [4000, 0, 30000], seed=9, max_len=50)
+    for size, step in ((100, 10), (50, 7), (3000, 1500)):
+        woff = np.concatenate(([0], np.cumsum([orc.nwin(n, size, step) for n in lens]))).astype(np.uint64)
+        seg = np.concatenate([np.full(int(woff[c + 1] - woff[c]), c, np.int32) for c in range(3)])
+        k = np.concatenate([np.arange(int(woff[c + 1] - woff[c])) for c in range(3)])
+        ws = (1 + k * step).astype(np.uint32)
+        got = api.count_windows(ctx, cs, woff, size, step, st2, sp2, ioff2)
+        assert np.array_equal(got, orc.count_batch(st2, sp2, ioff2, seg, ws, ws + np.uint32(size - 1)))
+    rng = np.random.default_rng(1)
+    a = rng.integers(1, 100_000, 50_000).astype(np.uint32)
+    b = a + rng.integers(1, 30, 50_000).astype(np.uint32)
+    ix = api.build_idx_rg(ctx, a, b, np.array([0, 20_000, 20_000, 50_000], np.uint64))
+    lp = orc.lapper_new([(int(x), int(y), "") for x, y in zip(a[:20_000], b[:20_000])])
+    assert np.array_equal(ix["iv_start"][:20_000], lp["start"]) and np.array_equal(ix["stops"][:20_000], lp["stops"])
+    assert ix["blob"][:int(ix["blob_off"][1])].tobytes() == orc.lapper_to_bincode(lp)
 print("sanitize_small ok")

@@ -14,6 +14,7 @@ Contents
   spo11_rg           bytes of tests/S288c/spo11_hot.rg       (golden #6)
   ctg_tsv            bytes of tests/S288c/ctg.tsv            (golden #7)
   intergenic_json    bytes of tests/S288c/intergenic.json    (anno fixture, §8f-4)
+  genome_fa_gz       bytes of tests/S288c/genome.fa.gz       (a gzip member as the reference's loaders read it; gunzip golden)
 """
 import gzip
 import hashlib
@@ -56,6 +57,7 @@ def main():
         "spo11_rg": np.frombuffer((REF / "spo11_hot.rg").read_bytes(), dtype=np.uint8),
         "ctg_tsv": np.frombuffer((REF / "ctg.tsv").read_bytes(), dtype=np.uint8),
         "intergenic_json": np.frombuffer((REF / "intergenic.json").read_bytes(), dtype=np.uint8),
+        "genome_fa_gz": np.frombuffer((REF / "genome.fa.gz").read_bytes(), dtype=np.uint8),
     }
     for n, s in zip(names, seqs):
         arrs["seq_" + n] = np.frombuffer(s, dtype=np.uint8)

@@ -834,3 +834,92 @@ def test_count_windows_fixture(ctx, orc, s288c):
     got = api.count_windows(ctx, chr_start, woff, 1001, 1, starts, stops, iv_off)
     _eq("fixture 1001/1", got, ref)
     assert ids[0] == "ctg:I:1" and int(got[999]) == 12      # window 999 of ctg:I:1 is I:1000-2000
+
+
+# ------------------------------------------------------------------------------------------------ gunzip of seq:* blobs
+def _gz(data: bytes, level=1, strategy=0, mem=8):
+    import zlib
+    c = zlib.compressobj(level, zlib.DEFLATED, 31, mem, strategy)
+    return c.compress(data) + c.flush()
+
+
+def test_gunzip_reference_fixture(ctx, orc, s288c):
+    """tests/S288c/genome.fa.gz (the reference's own gzip fixture) and the seq:{ctg} blobs `gams gen` would store."""
+    blob = bytes(s288c["genome_fa_gz"])
+    out, off, st = api.gunzip_batch(ctx, *api.pack_blobs([blob]))
+    ref = orc.decode_gz(blob)
+    assert st.tolist() == [0] and out.tobytes() == ref
+    assert bytes(s288c["seq_I"][:60]) in ref.replace(b"\n", b"")[:100]
+    ctgs = cut_ctgs(orc, s288c, 100000)
+    blobs = [orc.encode_gz(c[4].tobytes()) for c in ctgs]                    # encode_gz: Compression::fast()
+    cat, goff = api.pack_blobs(blobs)
+    assert api.gz_sizes(cat, goff).tolist() == [len(c[4]) for c in ctgs]
+    out, off, st = api.gunzip_batch(ctx, cat, goff)
+    assert not st.any()
+    for i, c in enumerate(ctgs):
+        assert out[int(off[i]):int(off[i + 1])].tobytes() == c[4].tobytes() == orc.decode_gz(blobs[i])
+    # the decoded ctgs feed the wave path unchanged: byte-identical input, so identical output (spot check through gc counts)
+    woff, cnt, gc, sig = api.wave_batch(ctx, out, off, 100, 10, 100, 3.0, 1.0)
+    rw, rc, rg, rs = orc.wave_batch(out, off, 100, 10, 100, 3.0, 1.0, threads=4)
+    _eq("gc after gunzip", cnt, rc); _eq("signal after gunzip", sig, rs)
+
+
+def test_gunzip_block_types_and_edges(ctx, orc):
+    """Every deflate feature: stored blocks (level 0, incompressible data), fixed Huffman (Z_FIXED, tiny inputs), dynamic
+    blocks at levels 1/6/9, literals only (Z_HUFFMAN_ONLY), run-length matches (Z_RLE, N-runs: distance 1 and short periods),
+    distances up to 32 KB, 258-byte matches, empty input, gzip headers with FNAME / FEXTRA / FCOMMENT / FHCRC, many blobs."""
+    import gzip, io, zlib
+    rng = np.random.default_rng(11)
+    dna = synth.genome(400_000, seed=3)
+    dna[5_000:9_000] = ord("N")
+    dna[20_000:20_700] = np.frombuffer(b"ACGTTGA" * 100, dtype=np.uint8)
+    dna = dna.tobytes()
+    rnd = rng.integers(0, 256, 150_000, dtype=np.uint8).tobytes()
+    rep = (rnd[:30_000] + b"x" * 5 + rnd[:30_000] + dna[:40_000] + rnd[1000:31_000])       # matches ~30 000 back
+    blobs, plain = [], []
+    def add(data, **kw):
+        blobs.append(_gz(data, **kw)); plain.append(data)
+    for lvl in (0, 1, 6, 9):
+        add(dna, level=lvl)
+    add(rnd, level=6); add(rep, level=9); add(dna[:70_000], level=6, strategy=zlib.Z_FIXED)
+    add(dna[:90_000], level=6, strategy=zlib.Z_HUFFMAN_ONLY); add(dna[:90_000], level=6, strategy=zlib.Z_RLE)
+    add(b"", level=1); add(b"A", level=1); add(b"ACGT" * 3, level=1); add(b"N" * 100_000, level=1); add(bytes(range(256)) * 40, level=1, mem=1)
+    for k in range(40):
+        a = int(rng.integers(0, 300_000)); add(dna[a:a + int(rng.integers(1, 60_000))], level=1)
+    bio = io.BytesIO()
+    with gzip.GzipFile(filename="seq.fa", mode="wb", fileobj=bio, compresslevel=1, mtime=0) as fh:
+        fh.write(dna[:12_345])
+    blobs.append(bio.getvalue()); plain.append(dna[:12_345])
+    body = _gz(dna[:5_000])[10:]                                                             # hand-made header: all optional fields
+    hdr = bytes([0x1F, 0x8B, 8, 2 | 4 | 8 | 16, 0, 0, 0, 0, 0, 255]) + bytes([3, 0]) + b"xyz" + b"name\0" + b"comment\0"
+    hdr += (zlib.crc32(hdr) & 0xFFFF).to_bytes(2, "little")                                  # FHCRC
+    blobs.append(hdr + body); plain.append(dna[:5_000])
+    blobs.append(_gz(dna[:3_000]) + _gz(b"second member is ignored")); plain.append(dna[:3_000])
+    assert all(orc.decode_gz(b) == p for b, p in zip(blobs, plain))
+    cat, goff = api.pack_blobs(blobs)
+    ooff = np.concatenate(([0], np.cumsum([len(p) for p in plain]))).astype(np.uint64)
+    out, off, st = api.gunzip_batch(ctx, cat, goff, ooff)
+    assert not st.any(), st.tolist()
+    for i, p in enumerate(plain):
+        got = out[int(off[i]):int(off[i + 1])].tobytes()
+        assert got == p, f"blob {i}: first difference at {next((k for k in range(min(len(got), len(p))) if got[k] != p[k]), None)}"
+
+
+def test_gunzip_corrupt_input_is_reported(ctx, orc):
+    """Truncated blobs, flipped bits, a wrong expected size and non-gzip bytes end in a status code, not in a crash, and do
+    not disturb the good blobs of the same batch (GzDecoder returns an error for all of these too, CRC aside)."""
+    dna = synth.genome(50_000, seed=8).tobytes()
+    good = _gz(dna)
+    bad_trunc = good[:len(good) // 2]
+    flipped = bytearray(good); flipped[len(good) // 3] ^= 0x55
+    not_gz = b"PK\x03\x04" + good[4:]
+    blobs = [good, bad_trunc, bytes(flipped), not_gz, good]
+    cat, goff = api.pack_blobs(blobs)
+    ooff = (np.arange(6) * len(dna)).astype(np.uint64)
+    out, off, st = api.gunzip_batch(ctx, cat, goff, ooff, raise_on_error=False)
+    assert st[0] == 0 and st[4] == 0 and st[1] != 0 and st[3] == 1
+    assert out[:len(dna)].tobytes() == dna and out[4 * len(dna):].tobytes() == dna
+    with pytest.raises(api.GamsCudaError):
+        api.gunzip_batch(ctx, cat, goff, ooff)
+    _, _, st = api.gunzip_batch(ctx, *api.pack_blobs([good]), np.array([0, len(dna) - 1], np.uint64), raise_on_error=False)
+    assert st.tolist() == [3] or st.tolist() == [5]
