@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--skip-sw", action="store_true")
     ap.add_argument("--sw-features", type=float, default=1e6, help="features of the sw section (configs[2])")
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-gz", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     return ap.parse_args()
@@ -470,6 +471,11 @@ def main():
                              "h2d_bytes_per_step": int(n_bases), "d2h_bytes_per_step": int(n_pk.value * 17 + 8),
                              "peak_records": int(n_pk.value), "api": "gams_cuda_wave_peaks_batch (host pointers, pinned; merge_ints on the device)"}
 
+    # ---- feed step (a18): the seq:{ctg} blobs as Redis holds them (gzip, level 1) inflated on the device ------------
+    feed = None
+    if rank == 0 and world == 1 and h_seq_ptr is not None and not args.skip_gz:
+        feed = bench_gunzip(args, ctx, L, dev, as_np(h_seq_ptr, n_bases, np.uint8), seq_off, d_seq, n_bases)
+
     # ---- CPU baseline (rank 0, N = 1 only) --------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
@@ -497,12 +503,71 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "u8->u32 counts, f32 statistics", "data": "synthetic",
             "config": workload_config(args), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roof_main, "kernels": kern, "path": "fused (gc_wave_fused_kernel)" if fused else "gc_window_kernel + zscore kernel", "cpu_baseline": cpu, "overlap": overlap, "sw": sw, "parity_spot_check": parity,
+            "roofline": roof_main, "kernels": kern, "path": "fused (gc_wave_fused_kernel)" if fused else "gc_window_kernel + zscore kernel", "cpu_baseline": cpu, "overlap": overlap, "sw": sw, "feed": feed, "parity_spot_check": parity,
             "windows_per_step": int(n_win), "bases_per_rank": int(n_bases),
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_gunzip(args, ctx, L, dev, h_seq, seq_off, d_seq, n_bases):
+    """SURVEY a18 (Conn::get_seq -> decode_gz): every ctg compressed as encode_gz does (gzip level 1), inflated by
+    gunzip_kernel with blobs and output resident in HBM; checked byte for byte against the genome it was made from."""
+    import zlib
+    from concurrent.futures import ThreadPoolExecutor
+
+    import torch
+
+    from gams_b200 import api
+
+    n_ctg = seq_off.size - 1
+    cores = os.cpu_count() or 1
+
+    def comp(c):
+        o = zlib.compressobj(1, zlib.DEFLATED, 31)
+        return o.compress(h_seq[int(seq_off[c]):int(seq_off[c + 1])].tobytes()) + o.flush()
+
+    t = time.perf_counter()
+    with ThreadPoolExecutor(cores) as ex:
+        blobs = list(ex.map(comp, range(n_ctg)))
+    t_comp = time.perf_counter() - t
+    cat, goff = api.pack_blobs(blobs)
+    k = min(n_ctg, 400)
+    t = time.perf_counter()
+    for b in blobs[:k]:
+        zlib.decompress(b, 31)
+    cpu_rate = float(seq_off[k]) / (time.perf_counter() - t) / 1e9
+    del blobs
+    d_gz = torch.from_numpy(cat).to(dev)
+    d_goff = torch.from_numpy(goff.astype(np.int64)).to(dev)
+    d_ooff = torch.from_numpy(seq_off.astype(np.int64)).to(dev)
+    d_out = torch.zeros(n_bases + 64, dtype=torch.uint8, device=dev)
+    d_st = torch.zeros(n_ctg, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def run():
+        api.check(L.gams_cuda_gunzip_dev(ctx.handle, 0, stream, n_ctg, d_gz.data_ptr(), d_goff.data_ptr(), d_out.data_ptr(),
+                                         d_ooff.data_ptr(), d_st.data_ptr()))
+
+    run()
+    torch.cuda.synchronize()
+    ok = bool(int(d_st.abs().sum()) == 0 and torch.equal(d_out[:n_bases], d_seq[:n_bases]))
+    n = max(1, min(args.steps, 3))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    return {"what": "gunzip of the seq:{ctg} blobs on the device (gams_cuda_gunzip_dev), blobs and output in HBM",
+            "value": n_bases / (ms * 1e-3) / 1e9, "unit": "Gbp/s", "ms_per_step": ms, "blobs": int(n_ctg),
+            "compressed_bytes": int(cat.size), "ratio": n_bases / cat.size, "bit_exact": ok, "gpu_launches": n,
+            "bound": "instruction issue: one dependent chain per deflate symbol, one warp per blob; the longest blob sets the time",
+            "cpu_baseline": {"value": cpu_rate, "unit": "Gbp/s", "cores": 1, "kind": "zlib",
+                             "sample": f"zlib.decompress of the first {k} blobs, one thread"},
+            "host_compress_s": t_comp}
 
 
 def bench_sw(args, ctx, L, dev):

@@ -8,23 +8,33 @@
 // read; the ISIZE trailer is checked, the CRC-32 is not (documented in include/gams_cuda.h).
 //
 // One WARP per blob (a deflate stream is bit-serial; the batch is the parallelism: one human genome is 6 200 streams).
-// Lane 0 owns the bit reader and decodes one symbol per iteration — a 9-bit primary lookup table per alphabet in shared
-// memory, canonical bit-by-bit decoding for the rare longer codes; the symbol is broadcast and the warp acts on it
-// together: the 32 lanes copy a match (level-1 DNA is almost all matches of ~4 bases), stored blocks and table builds are
-// cooperative as well.  History is read back from the output buffer itself (L1/L2), no window is staged.
-// Bound: instruction issue / latency (~40 warp instructions per symbol), not HBM.
+// Every lane keeps the same bit reader and decodes the same symbol (broadcast loads, no divergence, no shuffles): one
+// primary-table lookup per alphabet in shared memory (9 / 7 index bits; an entry carries code length, extra-bit count and
+// base, so a length or distance is one load, one shift and one add), canonical bit-by-bit decoding for the rare longer
+// codes.  The lanes differ only in the copies: the 32 lanes copy a match together (level-1 DNA is almost all matches of
+// ~4 bases); stored blocks and table builds are cooperative as well.  History is read back from the output buffer itself
+// (L1/L2), no window is staged.
+// Bound: instruction issue (one symbol = one dependent chain), not HBM.
 #include "common.cuh"
 
 namespace gams {
 
-constexpr int INF_WARPS = 8;        // per CTA
-constexpr int INF_PBITS = 9;        // primary table index bits
+constexpr int INF_WARPS = 4;        // per CTA: small CTAs free their slots soon (streams of a batch end at different times)
+constexpr int INF_LBITS = 9;        // primary table index bits, literal/length alphabet
+constexpr int INF_DBITS = 7;        // primary table index bits, distance alphabet
 
-struct InfTables {                  // per warp, shared memory (3 KB)
+// Table entry (both alphabets): bits 0-3 code length (0: the code is longer than the primary index -> canonical decoding),
+// bits 4-7 number of extra bits, bits 8-9 kind (0 literal, 1 length, 2 end of block, 3 invalid), bits 16-31 literal / base.
+constexpr uint32_t INF_KLIT = 0u << 8, INF_KLEN = 1u << 8, INF_KEOB = 2u << 8, INF_KBAD = 3u << 8;
+
+struct InfTables {                  // per warp, shared memory (3.4 KB: 48 warps per SM)
+    uint32_t ltab[1 << INF_LBITS];
+    uint32_t dtab[1 << INF_DBITS];
     uint16_t lcnt[16], dcnt[16];    // codes per length
     uint16_t lsym[288], dsym[32];   // symbols in canonical order
-    uint16_t ltab[1 << INF_PBITS], dtab[1 << INF_PBITS];   // (symbol << 4) | length, 0 = longer than INF_PBITS
     uint8_t lens[320];              // code lengths of the block being set up
+    uint16_t ccnt[8];               // the code-length alphabet of a dynamic header
+    uint8_t csym[20], clen[20];
 };
 
 __constant__ uint16_t INF_LBASE[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
@@ -33,55 +43,73 @@ __constant__ uint16_t INF_DBASE[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 
 __constant__ uint8_t INF_DEXT[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
 __constant__ uint8_t INF_CLORDER[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
-struct BitReader {                  // lives in lane 0's registers
-    const uint8_t *in;
-    uint64_t pos, end;              // next byte to load, end of the blob
-    uint64_t buf;
-    int cnt;
-    __device__ __forceinline__ void refill() {   // at least 56 bits afterwards (zeros past the end)
-        while (cnt <= 56) {
-            const uint64_t b = pos < end ? (uint64_t)__ldg(in + pos) : 0ull;
-            ++pos;
-            buf |= b << cnt;
-            cnt += 8;
+__device__ __forceinline__ uint32_t inf_lit_entry(int s) {     // without the code length
+    if (s < 256) return INF_KLIT | ((uint32_t)s << 16);
+    if (s == 256) return INF_KEOB;
+    if (s > 285) return INF_KBAD;
+    return INF_KLEN | ((uint32_t)INF_LEXT[s - 257] << 4) | ((uint32_t)INF_LBASE[s - 257] << 16);
+}
+__device__ __forceinline__ uint32_t inf_dist_entry(int s) {
+    if (s > 29) return INF_KBAD;
+    return ((uint32_t)INF_DEXT[s] << 4) | ((uint32_t)INF_DBASE[s] << 16);
+}
+
+// The bit reader: two consecutive aligned 32-bit words of the blob and a bit offset into the first.  EVERY lane of the
+// warp keeps an identical copy and decodes the same symbols (same addresses: broadcast loads), so the decode loop has no
+// divergence, no shuffles and no predication; only the copies use the lanes differently.
+struct BitReader {
+    const uint32_t *w;              // the blob's first byte lies `mis` bytes into w[0]
+    uint32_t n_words;               // words that hold blob bytes; zeros are read beyond
+    uint32_t mis;
+    uint32_t w0, w1, o, wi;         // w0 = w[wi - 2], w1 = w[wi - 1], o < 32 bits of w0 are consumed
+    __device__ __forceinline__ uint32_t ld(uint32_t i) const { return i < n_words ? __ldg(w + i) : 0u; }
+    __device__ __forceinline__ void seek(uint32_t byte) {
+        const uint32_t a = mis + byte;
+        wi = (a >> 2) + 2;
+        o = (a & 3u) * 8u;
+        w0 = ld(wi - 2);
+        w1 = ld(wi - 1);
+    }
+    __device__ __forceinline__ uint32_t peek() const { return __funnelshift_r(w0, w1, o); }   // the next 32 bits
+    __device__ __forceinline__ void drop(uint32_t n) {                                        // n <= 32
+        o += n;
+        if (o >= 32u) {
+            w0 = w1;
+            w1 = ld(wi);
+            ++wi;
+            o -= 32u;
         }
     }
-    __device__ __forceinline__ uint32_t peek(int n) const { return (uint32_t)buf & ((1u << n) - 1u); }
-    __device__ __forceinline__ void drop(int n) { buf >>= n; cnt -= n; }
-    __device__ __forceinline__ uint32_t bits(int n) { const uint32_t v = peek(n); drop(n); return v; }   // n <= 16, caller refilled
-    __device__ __forceinline__ bool overrun() const { return pos - (uint64_t)(cnt >> 3) > end; }          // consumed bytes past the end
+    __device__ __forceinline__ uint32_t bits(uint32_t n) { const uint32_t v = peek() & ((1u << n) - 1u); drop(n); return v; }   // n < 32
+    __device__ __forceinline__ uint64_t consumed_bits() const { return 32ull * (wi - 2) + o - 8ull * mis; }
 };
 
-// canonical decoding, one bit at a time (codes longer than the primary table; the code-length alphabet)
-__device__ __forceinline__ int inf_decode_slow(BitReader &br, const uint16_t *cnt, const uint16_t *sym, int max_sym) {
+// canonical decoding of a code longer than the primary index (or of the code-length alphabet), one bit at a time from the
+// peeked 32 bits; returns the symbol (or -1) and the code length
+__device__ __forceinline__ int inf_decode_slow(uint32_t pk, const uint16_t *cnt, const uint16_t *sym, int max_sym, uint32_t *code_len) {
     int code = 0, first = 0, index = 0;
     for (int len = 1; len <= 15; ++len) {
-        code |= (int)br.bits(1);
+        code |= (int)((pk >> (len - 1)) & 1u);
         const int c = cnt[len];
         if (code - c < first) {
             const int k = index + (code - first);
-            return k < max_sym ? sym[k] : -1;
+            *code_len = (uint32_t)len;
+            return k < max_sym ? (int)sym[k] : -1;
         }
         index += c;
         first += c;
         first <<= 1;
         code <<= 1;
     }
+    *code_len = 15;
     return -1;
-}
-__device__ __forceinline__ int inf_decode(BitReader &br, const uint16_t *tab, const uint16_t *cnt, const uint16_t *sym, int max_sym) {
-    const uint32_t e = tab[br.peek(INF_PBITS)];
-    if (e & 15u) {
-        br.drop((int)(e & 15u));
-        return (int)(e >> 4);
-    }
-    return inf_decode_slow(br, cnt, sym, max_sym);
 }
 
 // Warp-cooperative table build from code lengths lens[0 .. n): lane L (1..15) owns the codes of length L.
 // Returns false for an over-subscribed set of lengths.
-__device__ bool inf_build(const uint8_t *lens, int n, uint16_t *cnt, uint16_t *sym, uint16_t *tab, int lane) {
-    for (int i = lane; i < (1 << INF_PBITS); i += 32) tab[i] = 0;
+template <int PBITS, bool DIST>
+__device__ bool inf_build(const uint8_t *lens, int n, uint16_t *cnt, uint16_t *sym, uint32_t *tab, int lane) {
+    for (int i = lane; i < (1 << PBITS); i += 32) tab[i] = 0;
     int mine = 0;
     if (lane >= 1 && lane <= 15)
         for (int s = 0; s < n; ++s) mine += (lens[s] == lane) ? 1 : 0;
@@ -104,9 +132,10 @@ __device__ bool inf_build(const uint8_t *lens, int n, uint16_t *cnt, uint16_t *s
         for (int s = 0; s < n && ok; ++s) {
             if (lens[s] != lane) continue;
             sym[offs + k] = (uint16_t)s;
-            if (lane <= INF_PBITS) {
+            if (lane <= PBITS) {
                 const uint32_t rev = __brev((uint32_t)(code + k)) >> (32 - lane);
-                for (uint32_t j = rev; j < (1u << INF_PBITS); j += (1u << lane)) tab[j] = (uint16_t)((s << 4) | lane);
+                const uint32_t e = (DIST ? inf_dist_entry(s) : inf_lit_entry(s)) | (uint32_t)lane;
+                for (uint32_t j = rev; j < (1u << PBITS); j += (1u << lane)) tab[j] = e;
             }
             ++k;
         }
@@ -118,7 +147,7 @@ __device__ bool inf_build(const uint8_t *lens, int n, uint16_t *cnt, uint16_t *s
 
 enum { INF_OK = 0, INF_EHEADER = 1, INF_ECODE = 2, INF_EOVERFLOW = 3, INF_EDIST = 4, INF_ESIZE = 5, INF_ETRUNC = 6 };
 
-__global__ void __launch_bounds__(INF_WARPS * 32)
+__global__ void __launch_bounds__(INF_WARPS * 32, 12)
 gunzip_kernel(const uint8_t *__restrict__ gz, const uint64_t *__restrict__ gz_off, int64_t n_blob, uint8_t *out_base,
               const uint64_t *__restrict__ out_off, int32_t *__restrict__ status) {
     __shared__ InfTables tabs[INF_WARPS];
@@ -127,61 +156,48 @@ gunzip_kernel(const uint8_t *__restrict__ gz, const uint64_t *__restrict__ gz_of
     if (blob >= n_blob) return;
     InfTables &T = tabs[wib];
     uint8_t *out = out_base + out_off[blob];
-    const uint64_t cap = out_off[blob + 1] - out_off[blob];
-    BitReader br;
-    br.in = gz + gz_off[blob];
-    br.pos = 0, br.end = gz_off[blob + 1] - gz_off[blob], br.buf = 0, br.cnt = 0;
+    const uint64_t cap64 = out_off[blob + 1] - out_off[blob], len64 = gz_off[blob + 1] - gz_off[blob];
+    const uint8_t *in = gz + gz_off[blob];
     int err = INF_OK;
-    // ---- gzip header (RFC 1952): every lane parses it (same bytes), only lane 0's reader is used afterwards
-    {
-        const uint8_t *h = br.in;
-        const uint64_t n = br.end;
-        if (n < 18 || h[0] != 0x1F || h[1] != 0x8B || h[2] != 8) err = INF_EHEADER;
+    if (cap64 > 0xFFFFFF00ull || len64 > 0xFFFFFF00ull) err = INF_ESIZE;     // positions are 32-bit
+    const uint32_t cap = (uint32_t)cap64, in_len = (uint32_t)len64;
+    BitReader br;
+    br.mis = (uint32_t)(reinterpret_cast<uintptr_t>(in) & 3u);
+    br.w = reinterpret_cast<const uint32_t *>(in - br.mis);
+    br.n_words = (br.mis + in_len + 3u) >> 2;
+    // ---- gzip header (RFC 1952)
+    uint32_t p = 10;
+    if (!err) {
+        if (in_len < 18 || in[0] != 0x1F || in[1] != 0x8B || in[2] != 8) err = INF_EHEADER;
         else {
-            const uint32_t flg = h[3];
-            uint64_t p = 10;
-            if (flg & 4u) p += 2 + (p + 2 <= n ? (uint64_t)h[p] | ((uint64_t)h[p + 1] << 8) : 0);   // FEXTRA
-            if (flg & 8u) { while (p < n && h[p]) ++p; ++p; }                                        // FNAME
-            if (flg & 16u) { while (p < n && h[p]) ++p; ++p; }                                       // FCOMMENT
-            if (flg & 2u) p += 2;                                                                    // FHCRC
-            if (p + 8 > n) err = INF_EHEADER;
-            br.pos = p;
+            const uint32_t flg = in[3];
+            if (flg & 4u) p += 2 + (p + 2 <= in_len ? (uint32_t)in[p] | ((uint32_t)in[p + 1] << 8) : 0u);   // FEXTRA
+            if (flg & 8u) { while (p < in_len && in[p]) ++p; ++p; }                                           // FNAME
+            if (flg & 16u) { while (p < in_len && in[p]) ++p; ++p; }                                          // FCOMMENT
+            if (flg & 2u) p += 2;                                                                             // FHCRC
+            if (p + 8 > in_len) err = INF_EHEADER;
         }
     }
-    uint64_t pos = 0;               // bytes written; uniform over the warp
+    br.seek(err ? 0u : p);
+    uint32_t pos = 0;               // bytes written; the same in every lane
     bool last = false;
     while (!err && !last) {
-        // ---- block header: lane 0 reads, everything the warp needs is broadcast
-        uint32_t hdr = 0;
-        if (lane == 0) {
-            br.refill();
-            hdr = br.bits(3);
-        }
-        hdr = __shfl_sync(0xFFFFFFFFu, hdr, 0);
+        const uint32_t hdr = br.bits(3);
         last = hdr & 1u;
         const uint32_t type = hdr >> 1;
         if (type == 0) {
             // stored: skip to the byte boundary, LEN / NLEN, copy
-            uint64_t src = 0;
-            uint32_t len = 0, bad = 0;
-            if (lane == 0) {
-                br.drop(br.cnt & 7);
-                br.refill();
-                len = br.bits(16);
-                const uint32_t nlen = br.bits(16);
-                bad = (len ^ 0xFFFFu) != nlen;
-                src = br.pos - (uint64_t)(br.cnt >> 3);     // first byte not yet consumed
-                br.pos = src + len;
-                br.buf = 0, br.cnt = 0;
-                if (br.pos > br.end) bad = 1;
-            }
-            len = __shfl_sync(0xFFFFFFFFu, len, 0);
-            bad = __shfl_sync(0xFFFFFFFFu, bad, 0);
-            src = __shfl_sync(0xFFFFFFFFu, src, 0);
-            if (bad) { err = INF_ETRUNC; break; }
-            if (pos + len > cap) { err = INF_EOVERFLOW; break; }
-            for (uint32_t i = lane; i < len; i += 32) out[pos + i] = __ldg(br.in + src + i);
+            br.drop((8u - (br.o & 7u)) & 7u);
+            const uint32_t ln = br.peek();
+            br.drop(32);
+            const uint32_t len = ln & 0xFFFFu;
+            if ((len ^ 0xFFFFu) != (ln >> 16)) { err = INF_ETRUNC; break; }
+            const uint32_t src = (uint32_t)(br.consumed_bits() >> 3);
+            if ((uint64_t)src + len > in_len) { err = INF_ETRUNC; break; }
+            if ((uint64_t)pos + len > cap) { err = INF_EOVERFLOW; break; }
+            for (uint32_t i = lane; i < len; i += 32) out[pos + i] = __ldg(in + src + i);
             pos += len;
+            br.seek(src + len);
             continue;
         }
         if (type == 3) { err = INF_ECODE; break; }
@@ -190,98 +206,117 @@ gunzip_kernel(const uint8_t *__restrict__ gz, const uint64_t *__restrict__ gz_of
             for (int s = lane; s < 288; s += 32) T.lens[s] = s < 144 ? 8 : s < 256 ? 9 : s < 280 ? 7 : 8;
             if (lane < 30) T.lens[288 + lane] = 5;
         } else {
-            // dynamic: code-length code, then HLIT + HDIST lengths (lane 0, sequential: ~300 short symbols per block)
-            uint32_t info = 0;
-            if (lane == 0) {
-                br.refill();
-                const int hlit = (int)br.bits(5) + 257, hdist = (int)br.bits(5) + 1, hclen = (int)br.bits(4) + 4;
-                bool bad = hlit > 286 || hdist > 30;
-                uint8_t cl[19];
-                for (int i = 0; i < 19; ++i) cl[i] = 0;
-                for (int i = 0; i < hclen; ++i) {
-                    br.refill();
-                    cl[INF_CLORDER[i]] = (uint8_t)br.bits(3);
-                }
-                // code-length alphabet: canonical tables in the (still unused) distance arrays
-                uint16_t *ccnt = T.dcnt, *csym = T.dsym;
-                for (int l = 0; l < 16; ++l) ccnt[l] = 0;
-                for (int i = 0; i < 19; ++i) ccnt[cl[i]]++;
-                ccnt[0] = 0;
-                int offs[16];
-                offs[1] = 0;
-                for (int l = 1; l < 15; ++l) offs[l + 1] = offs[l] + ccnt[l];
-                for (int i = 0; i < 19; ++i)
-                    if (cl[i]) csym[offs[cl[i]]++] = (uint16_t)i;
-                int idx = 0;
-                const int total = hlit + hdist;
-                while (idx < total && !bad) {
-                    br.refill();
-                    const int s = inf_decode_slow(br, ccnt, csym, 19);
-                    if (s < 0) { bad = true; break; }
-                    if (s < 16) T.lens[idx++] = (uint8_t)s;
-                    else {
-                        int rep, v = 0;
-                        if (s == 16) {
-                            if (idx == 0) { bad = true; break; }
-                            v = T.lens[idx - 1];
-                            rep = 3 + (int)br.bits(2);
-                        } else if (s == 17) rep = 3 + (int)br.bits(3);
-                        else rep = 11 + (int)br.bits(7);
-                        if (idx + rep > total) { bad = true; break; }
-                        while (rep--) T.lens[idx++] = (uint8_t)v;
-                    }
-                }
-                if (!bad && T.lens[256] == 0) bad = true;      // no end-of-block code
-                info = bad ? 0xFFFFFFFFu : ((uint32_t)hlit | ((uint32_t)hdist << 16));
+            // dynamic: code-length code, then HLIT + HDIST lengths.  Sequential (~300 short symbols per block); every lane
+            // runs it and writes the same values.
+            const int hlit = (int)br.bits(5) + 257, hdist = (int)br.bits(5) + 1, hclen = (int)br.bits(4) + 4;
+            bool bad = hlit > 286 || hdist > 30;
+            if (lane < 19) T.clen[lane] = 0;
+            if (lane < 8) T.ccnt[lane] = 0;
+            __syncwarp();
+            for (int i = 0; i < hclen; ++i) {
+                const uint32_t v = br.bits(3);
+                if (lane == 0) T.clen[INF_CLORDER[i]] = (uint8_t)v;
             }
-            info = __shfl_sync(0xFFFFFFFFu, info, 0);
-            if (info == 0xFFFFFFFFu) { err = INF_ECODE; break; }
-            nlen = (int)(info & 0xFFFFu);
-            ndist = (int)(info >> 16);
+            __syncwarp();
+            if (lane == 0) {
+                uint32_t cc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                for (int i = 0; i < 19; ++i) cc[T.clen[i]]++;
+                cc[0] = 0;
+                uint32_t offs[8];
+                offs[1] = 0;
+                for (int l = 1; l < 7; ++l) offs[l + 1] = offs[l] + cc[l];
+                for (int l = 0; l < 8; ++l) T.ccnt[l] = (uint16_t)cc[l];
+                for (int i = 0; i < 19; ++i)
+                    if (T.clen[i]) T.csym[offs[T.clen[i]]++] = (uint8_t)i;
+            }
+            __syncwarp();
+            int idx = 0;
+            const int total = hlit + hdist;
+            int prev = 0;
+            while (idx < total && !bad) {
+                // canonical decoding over the (at most 7-bit) code-length codes
+                const uint32_t pk = br.peek();
+                int code = 0, first = 0, index = 0, s = -1;
+                uint32_t cl = 7;
+                for (int len = 1; len <= 7; ++len) {
+                    code |= (int)((pk >> (len - 1)) & 1u);
+                    const int c = T.ccnt[len];
+                    if (code - c < first) { s = T.csym[index + (code - first)]; cl = (uint32_t)len; break; }
+                    index += c; first += c; first <<= 1; code <<= 1;
+                }
+                if (s < 0) { bad = true; break; }
+                br.drop(cl);
+                if (s < 16) {
+                    if (lane == 0) T.lens[idx] = (uint8_t)s;
+                    prev = s;
+                    ++idx;
+                } else {
+                    int rep, v = 0;
+                    if (s == 16) {
+                        if (idx == 0) { bad = true; break; }
+                        v = prev;
+                        rep = 3 + (int)br.bits(2);
+                    } else if (s == 17) rep = 3 + (int)br.bits(3);
+                    else rep = 11 + (int)br.bits(7);
+                    if (idx + rep > total) { bad = true; break; }
+                    if (lane == 0)
+                        for (int k = 0; k < rep; ++k) T.lens[idx + k] = (uint8_t)v;
+                    idx += rep;
+                    prev = v;
+                }
+            }
+            __syncwarp();
+            if (!bad && T.lens[256] == 0) bad = true;      // no end-of-block code
+            if (bad) { err = INF_ECODE; break; }
+            nlen = hlit;
+            ndist = hdist;
         }
         __syncwarp();
-        const bool ok1 = inf_build(T.lens, nlen, T.lcnt, T.lsym, T.ltab, lane);
-        const bool ok2 = inf_build(T.lens + (type == 1 ? 288 : nlen), ndist, T.dcnt, T.dsym, T.dtab, lane);
+        const bool ok1 = inf_build<INF_LBITS, false>(T.lens, nlen, T.lcnt, T.lsym, T.ltab, lane);
+        const bool ok2 = inf_build<INF_DBITS, true>(T.lens + (type == 1 ? 288 : nlen), ndist, T.dcnt, T.dsym, T.dtab, lane);
         if (!ok1 || !ok2) { err = INF_ECODE; break; }
-        // ---- symbols: lane 0 decodes one, the warp executes it
+        // ---- symbols
         for (;;) {
-            uint32_t a = 0, b = 0;      // a: symbol (0..255 literal, 256 end, 257 match, 0xFFFF error); b: length | distance << 16
-            if (lane == 0) {
-                br.refill();
-                int s = inf_decode(br, T.ltab, T.lcnt, T.lsym, nlen);
-                if (s < 0 || s > 285) a = 0xFFFFu;
-                else if (s <= 256) a = (uint32_t)s;
-                else {
-                    s -= 257;
-                    const uint32_t len = INF_LBASE[s] + br.bits(INF_LEXT[s]);
-                    const int d = inf_decode(br, T.dtab, T.dcnt, T.dsym, ndist);
-                    if (d < 0 || d > 29) a = 0xFFFFu;
-                    else {
-                        const uint32_t dist = INF_DBASE[d] + br.bits(INF_DEXT[d]);
-                        a = 257u;
-                        b = len | (dist << 16);
-                    }
-                }
-                if (br.overrun()) a = 0xFFFFu;
+            uint32_t pk = br.peek();
+            uint32_t e = T.ltab[pk & ((1u << INF_LBITS) - 1u)];
+            if ((e & 15u) == 0u) {
+                uint32_t cl;
+                const int s = inf_decode_slow(pk, T.lcnt, T.lsym, nlen, &cl);
+                e = (s < 0 ? INF_KBAD : inf_lit_entry(s)) | cl;
             }
-            a = __shfl_sync(0xFFFFFFFFu, a, 0);
-            if (a < 256u) {
+            const uint32_t cl = e & 15u, ex = (e >> 4) & 15u, kind = e & (3u << 8);
+            const uint32_t val = (e >> 16) + ((pk >> cl) & ((1u << ex) - 1u));
+            br.drop(cl + ex);
+            if (kind == INF_KLIT) {
                 if (pos >= cap) { err = INF_EOVERFLOW; break; }
-                if (lane == 0) out[pos] = (uint8_t)a;
+                if (lane == 0) out[pos] = (uint8_t)val;
                 ++pos;
                 continue;
             }
-            if (a == 256u) break;
-            if (a != 257u) { err = INF_ECODE; break; }
-            b = __shfl_sync(0xFFFFFFFFu, b, 0);
-            const uint32_t len = b & 0xFFFFu, dist = b >> 16;
+            if (kind != INF_KLEN) {
+                if (kind != INF_KEOB) err = INF_ECODE;
+                break;
+            }
+            pk = br.peek();
+            uint32_t d = T.dtab[pk & ((1u << INF_DBITS) - 1u)];
+            if ((d & 15u) == 0u) {
+                uint32_t dl;
+                const int s = inf_decode_slow(pk, T.dcnt, T.dsym, ndist, &dl);
+                d = (s < 0 ? INF_KBAD : inf_dist_entry(s)) | dl;
+            }
+            if ((d & (3u << 8)) != 0u) { err = INF_ECODE; break; }
+            const uint32_t dl = d & 15u, dx = (d >> 4) & 15u;
+            const uint32_t dist = (d >> 16) + ((pk >> dl) & ((1u << dx) - 1u));
+            br.drop(dl + dx);
+            const uint32_t len = val;
             if (dist > pos) { err = INF_EDIST; break; }
-            if (pos + len > cap) { err = INF_EOVERFLOW; break; }
+            if (len > cap - pos) { err = INF_EOVERFLOW; break; }
             __syncwarp();               // the bytes written so far (lane 0's literals, every lane's copies) are visible
-            const uint8_t *src = out + pos - dist;
+            const uint8_t *src = out + (pos - dist);
             uint8_t *dst = out + pos;
             if (dist >= len) {
-                for (uint32_t i = lane; i < len; i += 32) dst[i] = src[i];
+                if (lane < len) dst[lane] = src[lane];
+                for (uint32_t i = lane + 32; i < len; i += 32) dst[i] = src[i];
             } else if (dist == 1) {
                 const uint8_t v = src[0];
                 for (uint32_t i = lane; i < len; i += 32) dst[i] = v;
@@ -294,12 +329,12 @@ gunzip_kernel(const uint8_t *__restrict__ gz, const uint64_t *__restrict__ gz_of
     // ---- trailer: ISIZE (RFC 1952: size of the original input modulo 2^32) and the size the caller expects
     if (lane == 0) {
         if (!err) {
-            const uint64_t t = br.pos - (uint64_t)(br.cnt >> 3);   // first unread byte = CRC32
-            if (t + 8 > br.end) err = INF_ETRUNC;
+            const uint64_t t = (br.consumed_bits() + 7) >> 3;      // first byte after the deflate stream = CRC32
+            if (t + 8 > in_len) err = INF_ETRUNC;
             else {
-                const uint8_t *q = br.in + t + 4;
+                const uint8_t *q = in + t + 4;
                 const uint32_t isize = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24);
-                if (isize != (uint32_t)pos || pos != cap) err = INF_ESIZE;
+                if (isize != pos || pos != cap) err = INF_ESIZE;
             }
         }
         status[blob] = err;
