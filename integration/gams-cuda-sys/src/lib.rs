@@ -122,6 +122,19 @@ extern "C" {
         d_q_seg: *const i32, d_q_start: *const u32, d_q_stop: *const u32, grouped: i32, d_out: *mut u32,
     ) -> i32;
     pub fn gams_cuda_count_plan_launches(plan: *const gams_cuda_count_plan) -> u64;
+    pub fn gams_cuda_gz_sizes(n_blob: i64, gz_concat: *const u8, gz_off: *const u64, out_len: *mut u64) -> i32;
+    pub fn gams_cuda_gunzip_batch(
+        ctx: *mut gams_cuda_ctx, n_blob: i64, gz_concat: *const u8, gz_off: *const u64, out_off: *const u64,
+        out_concat: *mut u8, status: *mut i32,
+    ) -> i32;
+    pub fn gams_cuda_gunzip_dev(
+        ctx: *mut gams_cuda_ctx, dev_index: i32, stream: *mut c_void, n_blob: i64, d_gz: *const u8, d_gz_off: *const u64,
+        d_out: *mut u8, d_out_off: *const u64, d_status: *mut i32,
+    ) -> i32;
+    pub fn gams_cuda_count_windows(
+        ctx: *mut gams_cuda_ctx, n_ctg: i64, chr_start: *const i32, win_off: *const u64, size: i32, step: i32,
+        starts: *const u32, stops: *const u32, iv_off: *const u64, out: *mut u32,
+    ) -> i32;
     pub fn gams_cuda_build_idx_rg(
         ctx: *mut gams_cuda_ctx, n_seg: i64, start: *const u32, stop: *const u32, iv_off: *const u64,
         iv_start: *mut u32, iv_stop: *mut u32, starts: *mut u32, stops: *mut u32, max_len: *mut u32, blob: *mut u8,
