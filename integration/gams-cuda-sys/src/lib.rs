@@ -17,6 +17,10 @@ pub struct gams_cuda_wave_plan {
 pub struct gams_cuda_count_plan {
     _private: [u8; 0],
 }
+#[repr(C)]
+pub struct gams_cuda_cwin_plan {
+    _private: [u8; 0],
+}
 
 pub const GAMS_CUDA_OK: i32 = 0;
 pub const GAMS_CUDA_EINVAL: i32 = -1;
@@ -134,6 +138,17 @@ extern "C" {
     pub fn gams_cuda_count_windows(
         ctx: *mut gams_cuda_ctx, n_ctg: i64, chr_start: *const i32, win_off: *const u64, size: i32, step: i32,
         starts: *const u32, stops: *const u32, iv_off: *const u64, out: *mut u32,
+    ) -> i32;
+    pub fn gams_cuda_cwin_plan_create(
+        ctx: *mut gams_cuda_ctx, dev_index: i32, n_ctg: i64, chr_start: *const i32, win_off: *const u64, size: i32,
+        step: i32, iv_off: *const u64, out: *mut *mut gams_cuda_cwin_plan,
+    ) -> i32;
+    pub fn gams_cuda_cwin_plan_destroy(plan: *mut gams_cuda_cwin_plan);
+    pub fn gams_cuda_cwin_plan_total_windows(plan: *const gams_cuda_cwin_plan) -> u64;
+    pub fn gams_cuda_cwin_plan_launches(plan: *const gams_cuda_cwin_plan) -> u64;
+    pub fn gams_cuda_cwin_plan_invalidate(plan: *mut gams_cuda_cwin_plan);
+    pub fn gams_cuda_count_windows_dev(
+        plan: *mut gams_cuda_cwin_plan, stream: *mut c_void, d_starts: *const u32, d_stops: *const u32, d_out: *mut u32,
     ) -> i32;
     pub fn gams_cuda_build_idx_rg(
         ctx: *mut gams_cuda_ctx, n_seg: i64, start: *const u32, stop: *const u32, iv_off: *const u64,
