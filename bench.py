@@ -539,7 +539,7 @@ def bench_gunzip(args, ctx, L, dev, h_seq, seq_off, d_seq, n_bases):
         zlib.decompress(b, 31)
     cpu_rate = float(seq_off[k]) / (time.perf_counter() - t) / 1e9
     del blobs
-    d_gz = torch.from_numpy(cat).to(dev)
+    d_gz = torch.from_numpy(cat.copy()).to(dev)
     d_goff = torch.from_numpy(goff.astype(np.int64)).to(dev)
     d_ooff = torch.from_numpy(seq_off.astype(np.int64)).to(dev)
     d_out = torch.zeros(n_bases + 64, dtype=torch.uint8, device=dev)
