@@ -99,3 +99,47 @@ def test_no_cpu_fallback_without_a_device():
     out = np.zeros(1, dtype=np.float32)
     rc = L.gams_cuda_wave_batch(None, 0, None, None, 100, 10, 100, 3.0, 1.0, None, None, out.ctypes.data_as(C.c_void_p), None)
     assert rc == -1  # NULL ctx is rejected, not silently computed on the host
+
+
+def test_gz_sizes_and_decode_gz_oracle(orc, s288c):
+    """gams_cuda_gz_sizes is host arithmetic (the ISIZE trailer); the gunzip oracle (zlib) against the reference's own
+    gzip fixture: tests/S288c/genome.fa.gz inflates to the FASTA whose sequences the other goldens are built from."""
+    blob = bytes(s288c["genome_fa_gz"])
+    fa = orc.decode_gz(blob)
+    names, seqs, cur = [], [], []
+    for line in fa.splitlines():
+        if line.startswith(b">"):
+            if names:
+                seqs.append(b"".join(cur))
+            names.append(line[1:].split()[0].decode()); cur = []
+        else:
+            cur.append(line)
+    seqs.append(b"".join(cur))
+    assert names == s288c["chr_names"].tolist()
+    assert seqs[0] == s288c["seq_I"].tobytes() and seqs[1] == s288c["seq_Mito"].tobytes()
+    parts = [orc.encode_gz(s288c["seq_I"].tobytes()), orc.encode_gz(b""), blob]
+    cat, off = api.pack_blobs(parts)
+    assert api.gz_sizes(cat, off).tolist() == [230218, 0, len(fa)]
+    assert orc.decode_gz(parts[0]) == s288c["seq_I"].tobytes()
+    with pytest.raises(api.GamsCudaError) as e:
+        api.gz_sizes(np.frombuffer(b"not a gzip member at all", dtype=np.uint8), np.array([0, 24], np.uint64))
+    assert e.value.code == -1
+
+
+def test_new_entry_points_reject_bad_arguments_without_a_device():
+    """NULL context / NULL arrays are EINVAL on every entry point added for the index build, window counts and gunzip:
+    nothing is computed on the host."""
+    L = _lib.load()
+    z = np.zeros(4, dtype=np.uint64)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    assert L.gams_cuda_build_idx_rg(None, 1, None, None, p(z), None, None, None, None, None, None) == -1
+    assert L.gams_cuda_count_windows(None, 1, None, p(z), 100, 10, None, None, p(z), None) == -1
+    assert L.gams_cuda_gunzip_batch(None, 1, None, p(z), p(z), None, None) == -1
+    assert L.gams_cuda_gunzip_dev(None, 0, None, 1, None, None, None, None, None) == -1
+    h = C.c_void_p()
+    assert L.gams_cuda_cwin_plan_create(None, 0, 1, None, p(z), 100, 10, p(z), C.byref(h)) == -1 and not h.value
+    assert L.gams_cuda_count_windows_dev(None, None, None, None, None) == -1
+    assert L.gams_cuda_cwin_plan_total_windows(None) == 0 and L.gams_cuda_cwin_plan_launches(None) == 0
+    L.gams_cuda_cwin_plan_destroy(None)
+    L.gams_cuda_cwin_plan_invalidate(None)
+    assert b"NULL" in L.gams_cuda_last_error() or b"bad" in L.gams_cuda_last_error()
