@@ -9,6 +9,8 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/gams_cuda.h"
@@ -34,6 +36,28 @@ int32_t cuda_fail(cudaError_t e, const char *what, const char *file, int line);
             return GAMS_CUDA_EINVAL;    \
         }                               \
     } while (0)
+
+// Run fn(d) for d = 0 .. n_used-1, one host thread per device when there are several; the first failure wins and its
+// message becomes the caller's gams_cuda_last_error().
+template <class F>
+inline int32_t run_on_devices(int n_used, F fn) {
+    if (n_used <= 1) return fn(0);
+    std::vector<int32_t> rc((size_t)n_used, 0);
+    std::vector<std::string> msg((size_t)n_used);
+    std::vector<std::thread> th;
+    for (int d = 0; d < n_used; ++d)
+        th.emplace_back([&, d] {
+            rc[d] = fn(d);
+            if (rc[d]) msg[d] = std::string(gams_cuda_last_error());
+        });
+    for (auto &t : th) t.join();
+    for (int d = 0; d < n_used; ++d)
+        if (rc[d]) {
+            set_error("%s", msg[d].c_str());
+            return rc[d];
+        }
+    return GAMS_CUDA_OK;
+}
 
 // ---- device memory ----------------------------------------------------------------------------
 // Freed blocks of one device, kept for reuse: the host API creates and destroys a plan per call, and cudaMalloc /

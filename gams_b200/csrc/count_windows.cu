@@ -294,20 +294,17 @@ GAMS_API int32_t gams_cuda_count_windows_dev(gams_cuda_cwin_plan *p, void *strea
     return GAMS_CUDA_OK;
 }
 
-// Host entry point: index up, counts down (4 bytes per window); everything on device 0 of the context.
-GAMS_API int32_t gams_cuda_count_windows(gams_cuda_ctx *ctx, int64_t n_ctg, const int32_t *chr_start, const uint64_t *win_off,
-                                         int32_t size, int32_t step, const uint32_t *starts, const uint32_t *stops,
-                                         const uint64_t *iv_off, uint32_t *out) {
-    ARG_CHECK(ctx && win_off && iv_off && n_ctg >= 0, "count_windows: bad argument");
-    if (n_ctg == 0) return GAMS_CUDA_OK;
+// One device's share of the host call: ctgs [0, n_ctg) of the (shifted) offset arrays; starts / stops / out are the caller's
+// whole arrays, addressed through the absolute offsets.
+static int32_t count_windows_one(gams_cuda_ctx *ctx, int d, int64_t n_ctg, const int32_t *chr_start, const uint64_t *win_off,
+                                 int32_t size, int32_t step, const uint32_t *starts, const uint32_t *stops, const uint64_t *iv_off,
+                                 uint32_t *out) {
     const uint64_t n_win = win_off[n_ctg] - win_off[0], n_iv = iv_off[n_ctg] - iv_off[0];
-    if (n_win == 0) return GAMS_CUDA_OK;
-    ARG_CHECK(out && ((starts && stops) || n_iv == 0), "count_windows: NULL array");
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    PerDevice &pd = ctx->devs[0];
+    if (n_ctg == 0 || n_win == 0) return GAMS_CUDA_OK;
+    PerDevice &pd = ctx->devs[d];
     DeviceGuard g(pd.device);
     gams_cuda_cwin_plan *plan = nullptr;
-    int32_t rc = gams_cuda_cwin_plan_create(ctx, 0, n_ctg, chr_start, win_off, size, step, iv_off, &plan);
+    int32_t rc = gams_cuda_cwin_plan_create(ctx, d, n_ctg, chr_start, win_off, size, step, iv_off, &plan);
     if (rc) return rc;
     std::unique_ptr<gams_cuda_cwin_plan, void (*)(gams_cuda_cwin_plan *)> guard(plan, gams_cuda_cwin_plan_destroy);
     if ((rc = pd.scratch[0].reserve(std::max<uint64_t>(n_iv, 1) * 8))) return rc;
@@ -322,4 +319,24 @@ GAMS_API int32_t gams_cuda_count_windows(gams_cuda_ctx *ctx, int64_t n_ctg, cons
     CUDA_TRY(cudaMemcpyAsync(out + win_off[0], d_o, n_win * 4, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     return GAMS_CUDA_OK;
+}
+
+// Host entry point: index up, counts down (4 bytes per window); ctgs are split over the context's devices by windows.
+GAMS_API int32_t gams_cuda_count_windows(gams_cuda_ctx *ctx, int64_t n_ctg, const int32_t *chr_start, const uint64_t *win_off,
+                                         int32_t size, int32_t step, const uint32_t *starts, const uint32_t *stops,
+                                         const uint64_t *iv_off, uint32_t *out) {
+    ARG_CHECK(ctx && win_off && iv_off && n_ctg >= 0, "count_windows: bad argument");
+    if (n_ctg == 0) return GAMS_CUDA_OK;
+    const uint64_t n_win = win_off[n_ctg] - win_off[0], n_iv = iv_off[n_ctg] - iv_off[0];
+    if (n_win == 0) return GAMS_CUDA_OK;
+    ARG_CHECK(out && ((starts && stops) || n_iv == 0), "count_windows: NULL array");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const int n_dev = (int)std::min<int64_t>((int64_t)ctx->devs.size(), std::max<int64_t>(1, (int64_t)(n_win >> 20)));
+    std::vector<int64_t> part((size_t)n_dev + 1);
+    int32_t rc = gams_cuda_partition(n_ctg, win_off, n_dev, part.data());
+    if (rc) return rc;
+    return run_on_devices(n_dev, [&](int d) {
+        const int64_t c0 = part[d], c1 = part[d + 1];
+        return count_windows_one(ctx, d, c1 - c0, chr_start + c0, win_off + c0, size, step, starts, stops, iv_off + c0, out);
+    });
 }

@@ -127,20 +127,15 @@ int32_t launch_build_idx(cudaStream_t st, int64_t n_seg, uint64_t n, const uint3
 
 using namespace gams;
 
-// Host entry point (declared in include/gams_cuda.h).
-GAMS_API int32_t gams_cuda_build_idx_rg(gams_cuda_ctx *ctx, int64_t n_seg, const uint32_t *start, const uint32_t *stop,
-                                        const uint64_t *iv_off, uint32_t *iv_start, uint32_t *iv_stop, uint32_t *starts,
-                                        uint32_t *stops, uint32_t *max_len, uint8_t *blob) {
-    ARG_CHECK(ctx && iv_off && n_seg >= 0, "build_idx_rg: bad argument");
+// One device's share: segments [0, n_seg) of the (shifted) iv_off; the interval arrays are the caller's whole arrays.
+static int32_t build_idx_one(gams_cuda_ctx *ctx, int dv, int64_t n_seg, uint64_t seg0, const uint32_t *start, const uint32_t *stop,
+                             const uint64_t *iv_off, uint32_t *iv_start, uint32_t *iv_stop, uint32_t *starts, uint32_t *stops,
+                             uint32_t *max_len, uint8_t *blob) {
     if (n_seg == 0) return GAMS_CUDA_OK;
-    ARG_CHECK(iv_off[0] == 0, "build_idx_rg: iv_off[0] must be 0");
-    for (int64_t s = 0; s < n_seg; ++s) ARG_CHECK(iv_off[s + 1] >= iv_off[s], "build_idx_rg: iv_off decreases at %lld", (long long)s);
-    const uint64_t n = iv_off[n_seg];
-    ARG_CHECK(n < (1ull << 31) && n_seg < (1ll << 31), "build_idx_rg: more than 2^31 intervals or segments in one call");
-    ARG_CHECK(max_len != nullptr, "build_idx_rg: max_len is NULL");
-    ARG_CHECK(n == 0 || (start && stop && iv_start && iv_stop && starts && stops), "build_idx_rg: NULL interval array");
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    PerDevice &pd = ctx->devs[0];
+    const uint64_t base = iv_off[0], n = iv_off[n_seg] - base;
+    std::vector<uint64_t> rel((size_t)n_seg + 1);
+    for (int64_t s = 0; s <= n_seg; ++s) rel[s] = iv_off[s] - base;
+    PerDevice &pd = ctx->devs[dv];
     DeviceGuard g(pd.device);
     cudaStream_t st = pd.stream;
     const uint64_t np = std::max<uint64_t>(n, 1);
@@ -158,22 +153,47 @@ GAMS_API int32_t gams_cuda_build_idx_rg(gams_cuda_ctx *ctx, int64_t n_seg, const
     uint64_t *d_ka = pd.scratch[2].as<uint64_t>(), *d_kb = d_ka + np;
     uint32_t *d_ivs = pd.scratch[3].as<uint32_t>(), *d_ive = d_ivs + np, *d_sts = d_ive + np, *d_sps = d_sts + np, *d_ml = d_sps + np;
     uint8_t *d_blob = blob ? pd.scratch[5].as<uint8_t>() : nullptr;
-    CUDA_TRY(cudaMemcpyAsync(d_off, iv_off, (uint64_t)(n_seg + 1) * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_off, rel.data(), (uint64_t)(n_seg + 1) * 8, cudaMemcpyHostToDevice, st));
     if (n) {
-        CUDA_TRY(cudaMemcpyAsync(d_start, start, n * 4, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(d_stop, stop, n * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d_start, start + base, n * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d_stop, stop + base, n * 4, cudaMemcpyHostToDevice, st));
     }
     if ((rc = launch_build_idx(st, n_seg, n, d_start, d_stop, d_off, d_ka, d_kb, pd.scratch[4].p, cub_bytes, d_ivs, d_ive, d_sts,
                                d_sps, d_ml, d_blob)))
         return rc;
     if (n) {
-        CUDA_TRY(cudaMemcpyAsync(iv_start, d_ivs, n * 4, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaMemcpyAsync(iv_stop, d_ive, n * 4, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaMemcpyAsync(starts, d_sts, n * 4, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaMemcpyAsync(stops, d_sps, n * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(iv_start + base, d_ivs, n * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(iv_stop + base, d_ive, n * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(starts + base, d_sts, n * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(stops + base, d_sps, n * 4, cudaMemcpyDeviceToHost, st));
     }
     CUDA_TRY(cudaMemcpyAsync(max_len, d_ml, (uint64_t)n_seg * 4, cudaMemcpyDeviceToHost, st));
-    if (blob) CUDA_TRY(cudaMemcpyAsync(blob, d_blob, blob_bytes, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
+    // the share's blobs are contiguous in the caller's buffer: segment seg0 + s sits at 24 iv_off[s] + 30 (seg0 + s)
+    if (blob) CUDA_TRY(cudaMemcpyAsync(blob + 24 * base + 30 * seg0, d_blob, blob_bytes, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));   // rel is a local
     return GAMS_CUDA_OK;
+}
+
+// Host entry point (declared in include/gams_cuda.h): segments are split over the context's devices by interval count.
+GAMS_API int32_t gams_cuda_build_idx_rg(gams_cuda_ctx *ctx, int64_t n_seg, const uint32_t *start, const uint32_t *stop,
+                                        const uint64_t *iv_off, uint32_t *iv_start, uint32_t *iv_stop, uint32_t *starts,
+                                        uint32_t *stops, uint32_t *max_len, uint8_t *blob) {
+    ARG_CHECK(ctx && iv_off && n_seg >= 0, "build_idx_rg: bad argument");
+    if (n_seg == 0) return GAMS_CUDA_OK;
+    ARG_CHECK(iv_off[0] == 0, "build_idx_rg: iv_off[0] must be 0");
+    for (int64_t s = 0; s < n_seg; ++s) ARG_CHECK(iv_off[s + 1] >= iv_off[s], "build_idx_rg: iv_off decreases at %lld", (long long)s);
+    const uint64_t n = iv_off[n_seg];
+    ARG_CHECK(n < (1ull << 31) && n_seg < (1ll << 31), "build_idx_rg: more than 2^31 intervals or segments in one call");
+    ARG_CHECK(max_len != nullptr, "build_idx_rg: max_len is NULL");
+    ARG_CHECK(n == 0 || (start && stop && iv_start && iv_stop && starts && stops), "build_idx_rg: NULL interval array");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const int n_dev = (int)std::min<int64_t>((int64_t)ctx->devs.size(), std::max<int64_t>(1, (int64_t)(n >> 20)));
+    std::vector<int64_t> part((size_t)n_dev + 1);
+    int32_t rc = gams_cuda_partition(n_seg, iv_off, n_dev, part.data());
+    if (rc) return rc;
+    return run_on_devices(n_dev, [&](int d) {
+        const int64_t s0 = part[d], s1 = part[d + 1];
+        return build_idx_one(ctx, d, s1 - s0, (uint64_t)s0, start, stop, iv_off + s0, iv_start, iv_stop, starts, stops, max_len + s0,
+                             blob);
+    });
 }

@@ -378,21 +378,16 @@ GAMS_API int32_t gams_cuda_gunzip_dev(gams_cuda_ctx *ctx, int32_t dev_index, voi
     return launch_gunzip(static_cast<cudaStream_t>(stream), d_gz, d_gz_off, n_blob, d_out, d_out_off, d_status);
 }
 
-GAMS_API int32_t gams_cuda_gunzip_batch(gams_cuda_ctx *ctx, int64_t n_blob, const uint8_t *gz_concat, const uint64_t *gz_off,
-                                        const uint64_t *out_off, uint8_t *out_concat, int32_t *status) {
-    ARG_CHECK(ctx && n_blob >= 0 && gz_off && out_off, "gunzip_batch: bad argument");
+static int32_t gunzip_one(gams_cuda_ctx *ctx, int d, int64_t n_blob, const uint8_t *gz_concat, const uint64_t *gz_off,
+                          const uint64_t *out_off, uint8_t *out_concat, int32_t *status) {
     if (n_blob == 0) return GAMS_CUDA_OK;
-    ARG_CHECK(gz_concat && status, "gunzip_batch: NULL argument");
     const uint64_t n_in = gz_off[n_blob] - gz_off[0], n_out = out_off[n_blob] - out_off[0];
-    ARG_CHECK(out_concat || n_out == 0, "gunzip_batch: out_concat is NULL");
     std::vector<uint64_t> go((size_t)n_blob + 1), oo((size_t)n_blob + 1);
     for (int64_t i = 0; i <= n_blob; ++i) {
         go[i] = gz_off[i] - gz_off[0];
         oo[i] = out_off[i] - out_off[0];
-        ARG_CHECK(i == 0 || (gz_off[i] >= gz_off[i - 1] && out_off[i] >= out_off[i - 1]), "gunzip_batch: offsets decrease at %lld", (long long)i);
     }
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    PerDevice &pd = ctx->devs[0];
+    PerDevice &pd = ctx->devs[d];
     DeviceGuard g(pd.device);
     cudaStream_t st = pd.stream;
     int32_t rc;
@@ -408,7 +403,29 @@ GAMS_API int32_t gams_cuda_gunzip_batch(gams_cuda_ctx *ctx, int64_t n_blob, cons
     if ((rc = launch_gunzip(st, d_gz, d_go, n_blob, d_out, d_oo, d_status))) return rc;
     if (n_out) CUDA_TRY(cudaMemcpyAsync(out_concat + out_off[0], d_out, n_out, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(status, d_status, (size_t)n_blob * 4, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaStreamSynchronize(st));   // go / oo are locals
+    return GAMS_CUDA_OK;
+}
+
+// Host entry point: blobs are split over the context's devices by compressed bytes.
+GAMS_API int32_t gams_cuda_gunzip_batch(gams_cuda_ctx *ctx, int64_t n_blob, const uint8_t *gz_concat, const uint64_t *gz_off,
+                                        const uint64_t *out_off, uint8_t *out_concat, int32_t *status) {
+    ARG_CHECK(ctx && n_blob >= 0 && gz_off && out_off, "gunzip_batch: bad argument");
+    if (n_blob == 0) return GAMS_CUDA_OK;
+    ARG_CHECK(gz_concat && status, "gunzip_batch: NULL argument");
+    ARG_CHECK(out_concat || out_off[n_blob] == out_off[0], "gunzip_batch: out_concat is NULL");
+    for (int64_t i = 1; i <= n_blob; ++i)
+        ARG_CHECK(gz_off[i] >= gz_off[i - 1] && out_off[i] >= out_off[i - 1], "gunzip_batch: offsets decrease at %lld", (long long)i);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const int n_dev = (int)std::min<int64_t>((int64_t)ctx->devs.size(), std::max<int64_t>(1, n_blob / 64));
+    std::vector<int64_t> part((size_t)n_dev + 1);
+    int32_t rc = gams_cuda_partition(n_blob, gz_off, n_dev, part.data());
+    if (rc) return rc;
+    rc = run_on_devices(n_dev, [&](int d) {
+        const int64_t b0 = part[d], b1 = part[d + 1];
+        return gunzip_one(ctx, d, b1 - b0, gz_concat, gz_off + b0, out_off + b0, out_concat, status + b0);
+    });
+    if (rc) return rc;
     for (int64_t i = 0; i < n_blob; ++i)
         if (status[i] != 0) {
             set_error("gunzip_batch: blob %lld failed with inflate status %d", (long long)i, (int)status[i]);

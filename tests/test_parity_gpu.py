@@ -923,3 +923,32 @@ def test_gunzip_corrupt_input_is_reported(ctx, orc):
         api.gunzip_batch(ctx, cat, goff, ooff)
     _, _, st = api.gunzip_batch(ctx, *api.pack_blobs([good]), np.array([0, len(dna) - 1], np.uint64), raise_on_error=False)
     assert st.tolist() == [3] or st.tolist() == [5]
+
+
+def test_multi_device_new_host_paths(orc):
+    """Window counts, gunzip and the index build through a context over every visible device: ctgs / blobs / segments are
+    split over the devices and the gathered result equals the single-device one (and the oracle on samples)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    rng = np.random.default_rng(91)
+    lens = [int(x) for x in rng.integers(150_000, 400_000, 140)]          # 140 ctgs, ~3.8 M windows at 100/10
+    chr_start = [1 + 7 * k for k in range(len(lens))]
+    st, sp, off = synth.rg_index(lens, [int(x) for x in rng.integers(10_000, 30_000, len(lens))], seed=92, max_len=40)
+    st = (st.astype(np.int64) + np.repeat(np.asarray(chr_start) - 1, np.diff(off.astype(np.int64)))).astype(np.uint32)
+    sp = (sp.astype(np.int64) + np.repeat(np.asarray(chr_start) - 1, np.diff(off.astype(np.int64)))).astype(np.uint32)
+    woff, ref = _ref_count_windows(orc, chr_start, lens, 100, 10, st, sp, off)
+    g = synth.genome(sum(lens), seed=93)
+    cuts = np.concatenate(([0], np.cumsum(lens)))
+    blobs = [orc.encode_gz(g[a:b].tobytes()) for a, b in zip(cuts[:-1], cuts[1:])]
+    cat, goff = api.pack_blobs(blobs)
+    with api.Context() as mctx, api.Context([0]) as one:
+        assert mctx.num_devices >= 2
+        _eq("multi-device window counts", api.count_windows(mctx, chr_start, woff, 100, 10, st, sp, off), ref)
+        out, ooff, status = api.gunzip_batch(mctx, cat, goff)
+        assert not status.any() and out.tobytes() == g.tobytes()
+        perm = np.concatenate([a + rng.permutation(b - a) for a, b in zip(off[:-1].astype(np.int64), off[1:].astype(np.int64))])
+        m, s1 = api.build_idx_rg(mctx, st[perm], sp[perm], off), api.build_idx_rg(one, st[perm], sp[perm], off)
+        for k in ("iv_start", "iv_stop", "starts", "stops", "max_len", "blob"):
+            _eq(f"multi-device index {k}", m[k], s1[k])
+        _eq("index starts", m["starts"], st)
