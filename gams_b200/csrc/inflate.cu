@@ -84,6 +84,13 @@ struct BitReader {
     __device__ __forceinline__ uint64_t consumed_bits() const { return 32ull * (wi - 2) + o - 8ull * mis; }
 };
 
+// bits [pos, pos + len) of x, len <= 15 (BFE)
+__device__ __forceinline__ uint32_t inf_bfe(uint32_t x, uint32_t pos, uint32_t len) {
+    uint32_t r;
+    asm("bfe.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(pos), "r"(len));
+    return r;
+}
+
 // canonical decoding of a code longer than the primary index (or of the code-length alphabet), one bit at a time from the
 // peeked 32 bits; returns the symbol (or -1) and the code length
 __device__ __forceinline__ int inf_decode_slow(uint32_t pk, const uint16_t *cnt, const uint16_t *sym, int max_sym, uint32_t *code_len) {
@@ -276,6 +283,7 @@ gunzip_kernel(const uint8_t *__restrict__ gz, const uint64_t *__restrict__ gz_of
         const bool ok2 = inf_build<INF_DBITS, true>(T.lens + (type == 1 ? 288 : nlen), ndist, T.dcnt, T.dsym, T.dtab, lane);
         if (!ok1 || !ok2) { err = INF_ECODE; break; }
         // ---- symbols
+        uint8_t *const out_lane = out + lane;
         for (;;) {
             uint32_t pk = br.peek();
             uint32_t e = T.ltab[pk & ((1u << INF_LBITS) - 1u)];
@@ -284,46 +292,45 @@ gunzip_kernel(const uint8_t *__restrict__ gz, const uint64_t *__restrict__ gz_of
                 const int s = inf_decode_slow(pk, T.lcnt, T.lsym, nlen, &cl);
                 e = (s < 0 ? INF_KBAD : inf_lit_entry(s)) | cl;
             }
-            const uint32_t cl = e & 15u, ex = (e >> 4) & 15u, kind = e & (3u << 8);
-            const uint32_t val = (e >> 16) + ((pk >> cl) & ((1u << ex) - 1u));
+            const uint32_t cl = e & 15u, ex = (e >> 4) & 15u;
+            const uint32_t val = (e >> 16) + inf_bfe(pk, cl, ex);
             br.drop(cl + ex);
-            if (kind == INF_KLIT) {
-                if (pos >= cap) { err = INF_EOVERFLOW; break; }
-                if (lane == 0) out[pos] = (uint8_t)val;
-                ++pos;
+            if (e & INF_KLEN) {         // a length (kind 1) or an invalid code (kind 3)
+                if (e & (2u << 8)) { err = INF_ECODE; break; }
+                pk = br.peek();
+                uint32_t d = T.dtab[pk & ((1u << INF_DBITS) - 1u)];
+                if ((d & 15u) == 0u) {
+                    uint32_t dl;
+                    const int s = inf_decode_slow(pk, T.dcnt, T.dsym, ndist, &dl);
+                    d = (s < 0 ? INF_KBAD : inf_dist_entry(s)) | dl;
+                }
+                const uint32_t dl = d & 15u, dx = (d >> 4) & 15u;
+                const uint32_t dist = (d >> 16) + inf_bfe(pk, dl, dx);
+                br.drop(dl + dx);
+                const uint32_t len = val;
+                if ((d & (3u << 8)) != 0u) { err = INF_ECODE; break; }
+                if (dist > pos) { err = INF_EDIST; break; }
+                if (len > cap - pos) { err = INF_EOVERFLOW; break; }
+                __syncwarp();           // the bytes written so far (lane 0's literals, every lane's copies) are visible
+                uint8_t *dst = out_lane + pos;
+                const uint8_t *src = dst - dist;
+                if (dist >= len) {
+                    if (lane < len) dst[0] = src[0];
+                    if (len > 32u)
+                        for (uint32_t i = 32; i + lane < len; i += 32) dst[i] = src[i];
+                } else if (dist == 1) {
+                    const uint8_t v = out[pos - 1];
+                    for (uint32_t i = lane; i < len; i += 32) out[pos + i] = v;
+                } else {
+                    for (uint32_t i = lane; i < len; i += 32) out[pos + i] = out[pos - dist + i % dist];   // the period repeats
+                }
+                pos += len;
                 continue;
             }
-            if (kind != INF_KLEN) {
-                if (kind != INF_KEOB) err = INF_ECODE;
-                break;
-            }
-            pk = br.peek();
-            uint32_t d = T.dtab[pk & ((1u << INF_DBITS) - 1u)];
-            if ((d & 15u) == 0u) {
-                uint32_t dl;
-                const int s = inf_decode_slow(pk, T.dcnt, T.dsym, ndist, &dl);
-                d = (s < 0 ? INF_KBAD : inf_dist_entry(s)) | dl;
-            }
-            if ((d & (3u << 8)) != 0u) { err = INF_ECODE; break; }
-            const uint32_t dl = d & 15u, dx = (d >> 4) & 15u;
-            const uint32_t dist = (d >> 16) + ((pk >> dl) & ((1u << dx) - 1u));
-            br.drop(dl + dx);
-            const uint32_t len = val;
-            if (dist > pos) { err = INF_EDIST; break; }
-            if (len > cap - pos) { err = INF_EOVERFLOW; break; }
-            __syncwarp();               // the bytes written so far (lane 0's literals, every lane's copies) are visible
-            const uint8_t *src = out + (pos - dist);
-            uint8_t *dst = out + pos;
-            if (dist >= len) {
-                if (lane < len) dst[lane] = src[lane];
-                for (uint32_t i = lane + 32; i < len; i += 32) dst[i] = src[i];
-            } else if (dist == 1) {
-                const uint8_t v = src[0];
-                for (uint32_t i = lane; i < len; i += 32) dst[i] = v;
-            } else {
-                for (uint32_t i = lane; i < len; i += 32) dst[i] = src[i % dist];   // the period repeats
-            }
-            pos += len;
+            if (e & (2u << 8)) break;   // end of block
+            if (pos >= cap) { err = INF_EOVERFLOW; break; }
+            if (lane == 0) out[pos] = (uint8_t)val;
+            ++pos;
         }
     }
     // ---- trailer: ISIZE (RFC 1952: size of the original input modulo 2^32) and the size the caller expects
