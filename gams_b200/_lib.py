@@ -82,6 +82,7 @@ def load() -> C.CDLL:
         "gams_cuda_count_plan_destroy": (None, [vp]),
         "gams_cuda_count_overlaps_dev": (i32, [vp, vp, vp, vp, i64, vp, vp, vp, i32, vp]),
         "gams_cuda_count_plan_launches": (u64, [vp]),
+        "gams_cuda_count_plan_invalidate": (None, [vp]),
         "gams_cuda_count_windows": (i32, [vp, i64, vp, vp, i32, i32, vp, vp, vp, vp]),
         "gams_cuda_cwin_plan_create": (i32, [vp, i32, i64, vp, vp, i32, i32, vp, C.POINTER(vp)]),
         "gams_cuda_cwin_plan_destroy": (None, [vp]),

@@ -376,6 +376,10 @@ class CountPlan:
     def launches(self) -> int:
         return int(self._L.gams_cuda_count_plan_launches(self._h))
 
+    def invalidate(self):
+        """Forget the tables derived from the index (after rewriting it in place under the same device pointers)."""
+        self._L.gams_cuda_count_plan_invalidate(self._h)
+
     def close(self):
         if getattr(self, "_h", None):
             self._L.gams_cuda_count_plan_destroy(self._h)

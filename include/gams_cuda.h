@@ -248,6 +248,9 @@ int32_t gams_cuda_count_overlaps_dev(gams_cuda_count_plan *plan, void *stream, c
                                      const uint32_t *d_q_start, const uint32_t *d_q_stop,
                                      int32_t grouped, uint32_t *d_out);
 uint64_t gams_cuda_count_plan_launches(const gams_cuda_count_plan *plan);
+/* The plan keeps the tables it derives from an index (rank nodes, compact per-segment tables) per (d_starts, d_stops)
+ * pointer pair; call this after rewriting the index in place under the same pointers. */
+void gams_cuda_count_plan_invalidate(gams_cuda_count_plan *plan);
 
 /* Conn::get_seq's decode_gz (src/libs/redis.rs:142-161: flate2 GzDecoder over the `seq:{ctg}` value), batched, on the
  * device: one gzip member (RFC 1952, deflate RFC 1951: stored / fixed / dynamic blocks) per blob, blobs back to back in
@@ -259,7 +262,9 @@ uint64_t gams_cuda_count_plan_launches(const gams_cuda_count_plan *plan);
 int32_t gams_cuda_gz_sizes(int64_t n_blob, const uint8_t *gz_concat, const uint64_t *gz_off, uint64_t *out_len);
 int32_t gams_cuda_gunzip_batch(gams_cuda_ctx *ctx, int64_t n_blob, const uint8_t *gz_concat, const uint64_t *gz_off,
                                const uint64_t *out_off, uint8_t *out_concat, int32_t *status);
-/* Device API: all pointers device memory (offsets relative to d_gz / d_out), asynchronous on `stream`. */
+/* Device API: all pointers device memory (offsets relative to d_gz / d_out), asynchronous on `stream`.  The reader loads
+ * aligned 32-bit words: the allocation behind d_gz must be readable from d_gz rounded down to a multiple of 4 up to the
+ * end rounded up to a multiple of 4 (any cudaMalloc'ed buffer is). */
 int32_t gams_cuda_gunzip_dev(gams_cuda_ctx *ctx, int32_t dev_index, void *stream, int64_t n_blob, const uint8_t *d_gz,
                              const uint64_t *d_gz_off, uint8_t *d_out, const uint64_t *d_out_off, int32_t *d_status);
 

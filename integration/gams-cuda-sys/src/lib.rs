@@ -126,6 +126,7 @@ extern "C" {
         d_q_seg: *const i32, d_q_start: *const u32, d_q_stop: *const u32, grouped: i32, d_out: *mut u32,
     ) -> i32;
     pub fn gams_cuda_count_plan_launches(plan: *const gams_cuda_count_plan) -> u64;
+    pub fn gams_cuda_count_plan_invalidate(plan: *mut gams_cuda_count_plan);
     pub fn gams_cuda_gz_sizes(n_blob: i64, gz_concat: *const u8, gz_off: *const u64, out_len: *mut u64) -> i32;
     pub fn gams_cuda_gunzip_batch(
         ctx: *mut gams_cuda_ctx, n_blob: i64, gz_concat: *const u8, gz_off: *const u64, out_off: *const u64,

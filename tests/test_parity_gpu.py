@@ -952,3 +952,37 @@ def test_multi_device_new_host_paths(orc):
         for k in ("iv_start", "iv_stop", "starts", "stops", "max_len", "blob"):
             _eq(f"multi-device index {k}", m[k], s1[k])
         _eq("index starts", m["starts"], st)
+
+
+def test_plans_follow_an_index_rewritten_in_place(ctx, orc):
+    """Count plans keep tables derived from the index per device-pointer pair; after the index is rewritten in place,
+    invalidate() makes the next call rebuild them (grouped and any-order overlap counts, window counts)."""
+    import torch
+    lens = [400_000 + 11 * k for k in range(40)]
+    st, sp, off = synth.rg_index(lens, [9000] * 40, seed=5, max_len=30)
+    seg, qs, qe = synth.queries(lens, 300_000, seed=6, grouped=True)
+    dev = torch.device("cuda", 0)
+    t = lambda a: torch.as_tensor(a.view(np.int32) if a.dtype != np.int32 else a, device=dev)
+    d_st, d_sp, d_seg, d_qs, d_qe = t(st), t(sp), t(seg), t(qs), t(qe)
+    out = torch.empty(seg.size, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    woff = np.concatenate(([0], np.cumsum([orc.nwin(n, 100, 10) for n in lens]))).astype(np.uint64)
+    wout = torch.empty(int(woff[-1]), dtype=torch.int32, device=dev)
+    plan, wplan = api.CountPlan(ctx, off), api.CountWindowsPlan(ctx, np.ones(40, np.int32), woff, 100, 10, off)
+    for rnd in range(2):
+        if rnd == 1:                                  # a different index under the same pointers
+            st2, sp2, _ = synth.rg_index(lens, [9000] * 40, seed=77, max_len=30)
+            d_st.copy_(t(st2)); d_sp.copy_(t(sp2))
+            st, sp = st2, sp2
+            plan.invalidate(); wplan.invalidate()
+        ref = orc.count_batch(st, sp, off, seg, qs, qe, threads=8)
+        for grouped in (True, False):
+            out.zero_()
+            plan.count(stream, d_st, d_sp, d_seg, d_qs, d_qe, out, grouped=grouped)
+            torch.cuda.synchronize()
+            _eq(f"round {rnd} grouped={grouped}", out.cpu().numpy().view(np.uint32), ref)
+        wplan.count(stream, d_st, d_sp, wout)
+        torch.cuda.synchronize()
+        _, wref = _ref_count_windows(orc, [1] * 40, lens, 100, 10, st, sp, off)
+        _eq(f"round {rnd} window counts", wout.cpu().numpy().view(np.uint32), wref)
+    plan.close(); wplan.close()
