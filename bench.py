@@ -679,6 +679,9 @@ def bench_count(args, ctx, L, dev, rank, world, g_off, barrier, max_over_ranks, 
                             "kernel": "seg_query_bounds_kernel + seg_items_kernel + count_overlaps_staged_kernel" if grouped else "count_overlaps_ranked_kernel",
                             "traffic": ncu_traffic("count_overlaps:grouped_by_ctg" if grouped else "count_overlaps:arbitrary_order") if n_q == 100_000_000 else None,
                             "algorithmic_bytes_per_launch": alg, "peak_source": peak_src}}
+        tr = res["roofline"]["traffic"]
+        if tr:   # the same time against the bytes DRAM really moved (ncu): what the kernel achieves on its own traffic
+            res["roofline"]["frac_of_peak_on_dram_traffic"] = tr / (ms * 1e-3) / 1e9 / hbm_peak
         if rank == 0:
             from oracle import oracle as orc
             k = 200_000
