@@ -179,7 +179,10 @@ count_overlaps_ranked_kernel(const uint32_t *__restrict__ starts, const uint32_t
 // its queries with one cum2 word and an 8-byte window of low[] per endpoint, compared SIMD-in-register.
 // DRAM traffic: the query stream once + ~6 B per interval (neighbouring chunks of a segment hit L2).
 // Arrays that do not fit the form (l > 7, n > ST_MAX_N) are binary-searched in global memory by the same CTA.
-constexpr int ST_THREADS = 512;
+#ifndef ST_THREADS_N
+#define ST_THREADS_N 1024   // two CTAs per SM = 64 warps: the two-table lookups of general intervals are latency-bound (0.673 -> 0.594 ms)
+#endif
+constexpr int ST_THREADS = ST_THREADS_N;
 constexpr int ST_NB = 8192;          // buckets per endpoint array
 constexpr int ST_MAX_N = 24576;      // elements per endpoint array
 constexpr int ST_CHUNK = 16384;      // queries per work item
@@ -422,7 +425,7 @@ __device__ __forceinline__ uint32_t staged_lower_bound(const SegCompact &P, cons
 }
 
 #ifndef ST_MIN_CTAS
-#define ST_MIN_CTAS 4
+#define ST_MIN_CTAS 2
 #endif
 // E8 format: #elements < key with one 64-bit load.  Entry b: cum | overflow << 15 | six low bytes (0xFF = empty slot).
 // Entry nb is a sentinel (cum = n, no elements): every key past the last bucket lands there, so key > hi needs no
