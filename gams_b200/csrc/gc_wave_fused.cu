@@ -25,7 +25,7 @@
 namespace gams {
 
 #ifndef FW_MIN_CTAS
-#define FW_MIN_CTAS 6
+#define FW_MIN_CTAS 8   // 64 warps per SM at 32 registers (a few spilled bytes): 0.928 -> 0.913 ms; 5 CTAs per SM: 1.109 ms
 #endif
 constexpr int FW_NCH = GC_THREADS * FW_K;  // 16-byte chunks per tile
 constexpr int FW_NBLK = ((FW_MAX_EL + FW_MAX_R + GC_THREADS - 1) / GC_THREADS) * GC_THREADS;  // block sums per tile
