@@ -101,7 +101,7 @@ __host__ inline uint32_t cw_magic(int32_t step) {
 }
 
 #ifndef CW_MIN_CTAS
-#define CW_MIN_CTAS 6
+#define CW_MIN_CTAS 8
 #endif
 #ifndef CW_PRE
 #define CW_PRE 6
