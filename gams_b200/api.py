@@ -468,3 +468,25 @@ def gunzip_batch(ctx: Context, gz_concat, gz_off, out_off=None, raise_on_error=T
     if rc != 0 and (raise_on_error or not status.any()):
         check(rc)
     return out, out_off, status
+
+
+# --------------------------------------------------------------- locate.rs:111-117, utils.rs:39-52 (Range::from_str per line)
+def parse_ranges(ctx: Context, text: bytes, chr_names):
+    """The lines of a range file parsed on the device → dict(line_off, chr, start, end): chr >= 0 index into chr_names,
+    -1 unknown chromosome, -2 invalid range (skipped by the reference), -3 outside the strict form (hand to Range::from_str)."""
+    t = np.frombuffer(text, dtype=np.uint8)
+    names = [n.encode() if isinstance(n, str) else n for n in chr_names]
+    noff = np.zeros(len(names) + 1, dtype=np.uint32)
+    noff[1:] = np.cumsum([len(n) for n in names])
+    ncat = np.frombuffer(b"".join(names), dtype=np.uint8) if names else np.zeros(0, np.uint8)
+    L = load()
+    n = C.c_uint64()
+    rc = L.gams_cuda_parse_ranges(ctx.handle, _p(t), t.size, len(names), _p(ncat), _p(noff), 0, C.byref(n), None, None, None, None)
+    if rc not in (0, -7):
+        check(rc)
+    k = int(n.value)
+    out = dict(line_off=np.zeros(k + 1, np.uint64), chr=np.empty(k, np.int32), start=np.empty(k, np.uint32), end=np.empty(k, np.uint32))
+    if k:
+        check(L.gams_cuda_parse_ranges(ctx.handle, _p(t), t.size, len(names), _p(ncat), _p(noff), k, C.byref(n), _p(out["line_off"]),
+                                       _p(out["chr"]), _p(out["start"]), _p(out["end"])))
+    return out

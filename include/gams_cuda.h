@@ -306,6 +306,21 @@ int32_t gams_cuda_build_idx_rg(gams_cuda_ctx *ctx, int64_t n_seg, const uint32_t
                                const uint64_t *iv_off, uint32_t *iv_start, uint32_t *iv_stop, uint32_t *starts,
                                uint32_t *stops, uint32_t *max_len, uint8_t *blob /* NULL: no blobs */);
 
+/* The front end of `gams locate` (src/cmd_gams/locate.rs:111-117) and read_range (src/libs/utils.rs:39-52): the lines of
+ * a range file parsed on the device instead of one intspan::Range::from_str (a regex) per line.
+ * text: n_bytes, lines end in '\n' (a '\r' before it is dropped, as BufRead::lines does; a last line without '\n' counts).
+ * chr names: n_chr names back to back in chr_names, name c = [chr_name_off[c], chr_name_off[c+1]).
+ * Per line i (0 .. *n_lines): line_off[i] (byte offset; line_off[*n_lines] = n_bytes), q_start / q_end (1-based inclusive) and
+ *   q_chr[i] >= 0  index of the chromosome in the name table
+ *            -1   a valid range on a chromosome that is not in the table
+ *            -2   not a valid range (Range::from_str(..).is_valid() is false: no ':', start == 0, end < start) - skipped
+ *            -3   outside the strict form  [name.]chr[(+)|(-)]:start[-end|_end]  anchored at the start of the line: the
+ *                 regex might still match somewhere; the caller passes exactly these lines to Range::from_str.
+ * Output arrays hold cap_lines entries (line_off: cap_lines + 1); GAMS_CUDA_ECAP with *n_lines set if that is too few. */
+int32_t gams_cuda_parse_ranges(gams_cuda_ctx *ctx, const uint8_t *text, uint64_t n_bytes, int64_t n_chr,
+                               const uint8_t *chr_names, const uint32_t *chr_name_off, uint64_t cap_lines,
+                               uint64_t *n_lines, uint64_t *line_off, int32_t *q_chr, uint32_t *q_start, uint32_t *q_end);
+
 /* gams::find_one_idx (utils.rs:7-22) -> Lapper::find(start, stop).next() on the idx:ctg:{chr}
  * index: ctg intervals [chr_start, chr_end+1) sorted by start within each chromosome segment.
  * out[q] = global index of the first ctg (in start order) with ctg_start < q_stop && ctg_stop >

@@ -135,6 +135,8 @@ def test_new_entry_points_reject_bad_arguments_without_a_device():
     assert L.gams_cuda_build_idx_rg(None, 1, None, None, p(z), None, None, None, None, None, None) == -1
     assert L.gams_cuda_count_windows(None, 1, None, p(z), 100, 10, None, None, p(z), None) == -1
     assert L.gams_cuda_gunzip_batch(None, 1, None, p(z), p(z), None, None) == -1
+    n = C.c_uint64(7)
+    assert L.gams_cuda_parse_ranges(None, None, 10, 0, None, None, 0, C.byref(n), None, None, None, None) == -1
     assert L.gams_cuda_gunzip_dev(None, 0, None, 1, None, None, None, None, None) == -1
     h = C.c_void_p()
     assert L.gams_cuda_cwin_plan_create(None, 0, 1, None, p(z), 100, 10, p(z), C.byref(h)) == -1 and not h.value

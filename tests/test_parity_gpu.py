@@ -986,3 +986,67 @@ def test_plans_follow_an_index_rewritten_in_place(ctx, orc):
         _, wref = _ref_count_windows(orc, [1] * 40, lens, 100, 10, st, sp, off)
         _eq(f"round {rnd} window counts", wout.cpu().numpy().view(np.uint32), wref)
     plan.close(); wplan.close()
+
+
+# ------------------------------------------------------------------------------------------------ range-file parsing
+def _check_parse(ctx, orc, lines, names, text=None, allow_complex=True):
+    text = ("\n".join(lines) + "\n").encode() if text is None else text
+    got = api.parse_ranges(ctx, text, names)
+    assert got["chr"].size == len(lines), (got["chr"].size, len(lines))
+    offs = got["line_off"].tolist()
+    n_complex = 0
+    for i, ln in enumerate(lines):
+        raw = text[offs[i]:offs[i + 1]].rstrip(b"\n").rstrip(b"\r").decode(errors="replace")
+        assert raw == ln, (i, raw, ln)
+        ref = orc.range_from_str(ln)
+        c = int(got["chr"][i])
+        if c == -3:
+            n_complex += 1
+            assert allow_complex, f"line {i} {ln!r} was handed back although it has the strict form"
+            continue
+        if ref is None:
+            assert c == -2, (i, ln, c)
+        else:
+            assert c != -2, (i, ln, ref)
+            assert (int(got["start"][i]), int(got["end"][i])) == (ref[2], ref[3]), (i, ln, ref)
+            assert c == (names.index(ref[0]) if ref[0] in names else -1), (i, ln, c, ref)
+    return n_complex
+
+
+def test_parse_ranges_fixture_and_canonical_forms(ctx, orc, s288c):
+    """tests/S288c/SK1.snp.rg and spo11_hot.rg (what `gams locate -f` / `gams rg` read) and every canonical spelling:
+    all parsed on the device, none handed back, values equal to Range::from_str's."""
+    names = ["I", "II", "Mito", "chr1", "scaffold_12", "2L", "HLA-A", "a/b"]
+    for key in ("snp_rg", "spo11_rg"):
+        lines = bytes(s288c[key]).decode().splitlines()
+        assert _check_parse(ctx, orc, lines, names, allow_complex=False) == 0
+    lines = ["I:1000-2000", "I:1000", "S288c.I(+):1000-2000", "S288c.II(-):5", "Mito:1_85779", "chr1:7-", "HLA-A:5-9", "a/b:3-4",
+             "2L:12-12", "unknown:1-2", "I:0-5", "I:5-3", "I:2147483647", "I:1000-2000\textra\tcolumns", "I:10 20", "II:1-2 # c",
+             "I(+):3-4", "scaffold_12:100-200", "no colon here", "", "I:00012-00013"]
+    assert _check_parse(ctx, orc, lines, names, allow_complex=False) == 0
+    # no trailing newline, CRLF, a single line, an empty file
+    assert _check_parse(ctx, orc, ["I:1-2", "II:3-4"], names, text=b"I:1-2\nII:3-4", allow_complex=False) == 0
+    assert _check_parse(ctx, orc, ["I:1-2", "II:3-4"], names, text=b"I:1-2\r\nII:3-4\r\n", allow_complex=False) == 0
+    assert api.parse_ranges(ctx, b"", names)["chr"].size == 0
+    assert api.parse_ranges(ctx, b"\n\n", names)["chr"].tolist() == [-2, -2]
+
+
+def test_parse_ranges_random_and_hostile_lines(ctx, orc):
+    """Random well-formed lines (many tiles of text, long and short lines) must all be parsed; hostile ones (second colon,
+    greedy strand, dots, leading blanks, non-ASCII, huge numbers) are either parsed exactly as the regex does or handed back."""
+    rng = np.random.default_rng(23)
+    names = [f"chr{k}" for k in range(1, 25)] + ["X_1", "s/7"]
+    lines = []
+    for _ in range(60_000):
+        c = names[int(rng.integers(0, len(names)))] if rng.random() < 0.9 else "other"
+        s = int(rng.integers(1, 250_000_000))
+        e = s + int(rng.integers(0, 10_000))
+        form = int(rng.integers(0, 6))
+        lines.append([f"{c}:{s}-{e}", f"{c}:{s}", f"Hs.{c}(+):{s}-{e}", f"{c}(-):{s}_{e}", f"{c}:{s}-{e}\t{int(rng.integers(0, 99))}",
+                      f"{c}:{e + 1}-{s}"][form])
+    assert _check_parse(ctx, orc, lines, names, allow_complex=False) == 0
+    hostile = ["I(+):1-2(x):3-4", "a.b.c:1-2", " I:1-2", "x y:5", "I:abc", "I::5", "a-b.c:1", "é:1-2", "I:99999999999", "I(+-):1", "I(:1",
+               ":5", "I:", "I(+)1-2:3", "..:1", "I:1-2:3-4", "I(+):1-2)", "1:1-1", "_:_1", "I:5-99999999999"]
+    names2 = ["I", "c", "b", "y", "1", "_"]
+    n_complex = _check_parse(ctx, orc, hostile, names2)
+    assert n_complex >= 8
