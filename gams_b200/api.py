@@ -481,12 +481,18 @@ def parse_ranges(ctx: Context, text: bytes, chr_names):
     ncat = np.frombuffer(b"".join(names), dtype=np.uint8) if names else np.zeros(0, np.uint8)
     L = load()
     n = C.c_uint64()
-    rc = L.gams_cuda_parse_ranges(ctx.handle, _p(t), t.size, len(names), _p(ncat), _p(noff), 0, C.byref(n), None, None, None, None)
-    if rc not in (0, -7):
+    # room for the lines: estimated from the head of the text, retried with the exact count if that was too small
+    head = text[:1 << 16]
+    cap = int(len(text) / max(1.0, len(head) / (head.count(b"\n") + 1)) * 1.25) + 16
+    while True:
+        out = dict(line_off=np.zeros(cap + 1, np.uint64), chr=np.empty(cap, np.int32), start=np.empty(cap, np.uint32), end=np.empty(cap, np.uint32))
+        rc = L.gams_cuda_parse_ranges(ctx.handle, _p(t), t.size, len(names), _p(ncat), _p(noff), cap, C.byref(n), _p(out["line_off"]),
+                                      _p(out["chr"]), _p(out["start"]), _p(out["end"]))
+        if rc == -7:
+            cap = int(n.value)
+            continue
         check(rc)
+        break
     k = int(n.value)
-    out = dict(line_off=np.zeros(k + 1, np.uint64), chr=np.empty(k, np.int32), start=np.empty(k, np.uint32), end=np.empty(k, np.uint32))
-    if k:
-        check(L.gams_cuda_parse_ranges(ctx.handle, _p(t), t.size, len(names), _p(ncat), _p(noff), k, C.byref(n), _p(out["line_off"]),
-                                       _p(out["chr"]), _p(out["start"]), _p(out["end"])))
+    out = {"line_off": out["line_off"][:k + 1], "chr": out["chr"][:k], "start": out["start"][:k], "end": out["end"][:k]}
     return out
