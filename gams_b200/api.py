@@ -496,3 +496,24 @@ def parse_ranges(ctx: Context, text: bytes, chr_names):
     k = int(n.value)
     out = {"line_off": out["line_off"][:k + 1], "chr": out["chr"][:k], "start": out["start"][:k], "end": out["end"][:k]}
     return out
+
+
+def locate_count_text(ctx: Context, text: bytes, chr_names, ctg_start, ctg_stop, chr_off, starts, stops, iv_off):
+    """`gams locate --count -f file`, text in → (output text, n_lines, n_printed, n_handed_back)."""
+    t = np.frombuffer(text, dtype=np.uint8)
+    names = [n.encode() if isinstance(n, str) else n for n in chr_names]
+    noff = np.zeros(len(names) + 1, dtype=np.uint32)
+    noff[1:] = np.cumsum([len(n) for n in names])
+    ncat = np.frombuffer(b"".join(names), dtype=np.uint8) if names else np.zeros(0, np.uint8)
+    ctg_start, ctg_stop, chr_off = _arr(ctg_start, np.uint32), _arr(ctg_stop, np.uint32), _arr(chr_off, np.uint64)
+    starts, stops, iv_off = _arr(starts, np.uint32), _arr(stops, np.uint32), _arr(iv_off, np.uint64)
+    L = load()
+    out, n, nl, npr, nb = C.c_void_p(), C.c_size_t(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+    check(L.gams_cuda_locate_count_text(ctx.handle, _p(t), t.size, len(names), _p(ncat), _p(noff), _p(ctg_start), _p(ctg_stop),
+                                        _p(chr_off), _p(starts), _p(stops), _p(iv_off), C.byref(out), C.byref(n), C.byref(nl),
+                                        C.byref(npr), C.byref(nb)))
+    try:
+        s = C.string_at(out, n.value) if out.value else b""
+    finally:
+        L.gams_cuda_free(out)
+    return s, int(nl.value), int(npr.value), int(nb.value)

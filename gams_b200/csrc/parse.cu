@@ -190,18 +190,108 @@ parse_lines_kernel(const uint8_t *__restrict__ text, uint64_t n_bytes, const uin
     }
 }
 
+// ---- `locate --count` output: "{rg}\t{cnt}\n" per located line (locate.rs:136-139), rg = the input line itself ----------------
+__device__ __forceinline__ uint32_t dec_digits(uint32_t v) {
+    uint32_t d = 1;
+    while (v >= 10u) { v /= 10u; ++d; }
+    return d;
+}
+// [p, e) of line i without its '\n' / '\r\n'
+__device__ __forceinline__ void line_span(const uint8_t *__restrict__ text, uint64_t n_bytes, const uint64_t *__restrict__ line_off,
+                                          uint64_t n_lines, uint64_t i, uint64_t &p, uint64_t &e) {
+    p = line_off[i];
+    e = (i + 1 < n_lines) ? line_off[i + 1] - 1 : n_bytes;
+    if (i + 1 == n_lines && e > p && text[e - 1] == '\n') --e;
+    if (e > p && text[e - 1] == '\r') --e;
+}
+constexpr int FM_THREADS = 256;
+
+// bytes each tile of FM_THREADS lines prints; counters[0] += printed lines, counters[1] += lines handed back (q_chr == -3)
+__global__ void __launch_bounds__(FM_THREADS)
+fmt_len_kernel(const uint8_t *__restrict__ text, uint64_t n_bytes, const uint64_t *__restrict__ line_off, uint64_t n_lines,
+               const int32_t *__restrict__ q_chr, const int32_t *__restrict__ seg, const uint32_t *__restrict__ cnt,
+               uint32_t *__restrict__ tile_len, unsigned long long *__restrict__ counters) {
+    __shared__ uint32_t ws[FM_THREADS / 32];
+    const uint64_t i = (uint64_t)blockIdx.x * FM_THREADS + threadIdx.x;
+    uint32_t len = 0;
+    bool printed = false, back = false;
+    if (i < n_lines) {
+        back = q_chr[i] == -3;
+        if (seg[i] >= 0) {
+            uint64_t p, e;
+            line_span(text, n_bytes, line_off, n_lines, i, p, e);
+            len = (uint32_t)(e - p) + 2u + dec_digits(cnt[i]);
+            printed = true;
+        }
+    }
+    const uint32_t np = __popc(__ballot_sync(0xFFFFFFFFu, printed)), nb = __popc(__ballot_sync(0xFFFFFFFFu, back));
+    const uint32_t sum = __reduce_add_sync(0xFFFFFFFFu, len);
+    if ((threadIdx.x & 31) == 0) {
+        ws[threadIdx.x >> 5] = sum;
+        if (np) atomicAdd(&counters[0], (unsigned long long)np);
+        if (nb) atomicAdd(&counters[1], (unsigned long long)nb);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < FM_THREADS / 32; ++w) t += ws[w];
+        tile_len[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(FM_THREADS)
+fmt_write_kernel(const uint8_t *__restrict__ text, uint64_t n_bytes, const uint64_t *__restrict__ line_off, uint64_t n_lines,
+                 const int32_t *__restrict__ seg, const uint32_t *__restrict__ cnt, const uint64_t *__restrict__ tile_base,
+                 uint8_t *__restrict__ out) {
+    __shared__ uint32_t ws[FM_THREADS / 32];
+    const uint64_t i = (uint64_t)blockIdx.x * FM_THREADS + threadIdx.x;
+    uint32_t len = 0, c = 0, nd = 0;
+    uint64_t p = 0, e = 0;
+    if (i < n_lines && seg[i] >= 0) {
+        line_span(text, n_bytes, line_off, n_lines, i, p, e);
+        c = cnt[i];
+        nd = dec_digits(c);
+        len = (uint32_t)(e - p) + 2u + nd;
+    }
+    uint32_t inc = len;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+        if ((threadIdx.x & 31) >= d) inc += t;
+    }
+    if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = inc;
+    __syncthreads();
+    uint64_t o = tile_base[blockIdx.x] + inc - len;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) o += ws[w];
+    if (len) {
+        for (uint64_t k = p; k < e; ++k) out[o++] = text[k];
+        out[o++] = '\t';
+        for (uint32_t k = nd; k-- > 0;) {
+            out[o + k] = (uint8_t)('0' + c % 10u);
+            c /= 10u;
+        }
+        out[o + nd] = '\n';
+    }
+}
+
 }  // namespace gams
 
 using namespace gams;
 
-GAMS_API int32_t gams_cuda_parse_ranges(gams_cuda_ctx *ctx, const uint8_t *text, uint64_t n_bytes, int64_t n_chr,
-                                        const uint8_t *chr_names, const uint32_t *chr_name_off, uint64_t cap_lines,
-                                        uint64_t *n_lines, uint64_t *line_off, int32_t *q_chr, uint32_t *q_start, uint32_t *q_end) {
-    ARG_CHECK(ctx && n_lines && n_chr >= 0 && n_chr < (1ll << 30), "parse_ranges: bad argument");
-    ARG_CHECK(n_chr == 0 || (chr_names && chr_name_off), "parse_ranges: NULL name table");
-    *n_lines = 0;
-    if (n_bytes == 0) return GAMS_CUDA_OK;
-    ARG_CHECK(text != nullptr, "parse_ranges: text is NULL");
+namespace {
+// the text, its line table and the parsed columns, resident on one device
+struct ParsedText {
+    DevBuf text, tiles, names, lines;
+    uint64_t n_lines = 0, n_tiles = 0;
+    uint8_t *d_text = nullptr;
+    uint64_t *d_loff = nullptr, *d_tile_base = nullptr, *d_total = nullptr;
+    int32_t *d_qc = nullptr;
+    uint32_t *d_qs = nullptr, *d_qe = nullptr;
+    void release() { text.release(); tiles.release(); names.release(); lines.release(); }
+};
+
+int32_t parse_on_device(PerDevice &pd, cudaStream_t st, const uint8_t *text, uint64_t n_bytes, int64_t n_chr, const uint8_t *chr_names,
+                        const uint32_t *chr_name_off, ParsedText &P) {
     // the name table: open addressing, FNV-1a, load factor <= 1/2 (host work: n_chr names)
     uint32_t hsize = 16;
     while (hsize < 2 * (uint64_t)n_chr + 2) hsize <<= 1;
@@ -214,24 +304,23 @@ GAMS_API int32_t gams_cuda_parse_ranges(gams_cuda_ctx *ctx, const uint8_t *text,
         while (htab[s] >= 0) s = (s + 1) & (hsize - 1);
         htab[s] = (int32_t)c;
     }
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    PerDevice &pd = ctx->devs[0];
-    DeviceGuard g(pd.device);
-    cudaStream_t st = pd.stream;
     const uint64_t n_tiles = (n_bytes + PR_TILE - 1) / PR_TILE;
     ARG_CHECK(n_tiles < (1ull << 31), "parse_ranges: text too large for one call");
     const uint64_t names_bytes = n_chr ? chr_name_off[n_chr] : 0;
+    P.text.cache = P.tiles.cache = P.names.cache = P.lines.cache = pd.cache;
+    P.n_tiles = n_tiles;
     int32_t rc;
-    if ((rc = pd.scratch[0].reserve(n_bytes + 64))) return rc;
-    if ((rc = pd.scratch[1].reserve(n_tiles * 12 + 64))) return rc;
-    if ((rc = pd.scratch[2].reserve(names_bytes + (size_t)(n_chr + 1) * 4 + (size_t)hsize * 4 + 64))) return rc;
-    uint8_t *d_text = pd.scratch[0].as<uint8_t>();
-    uint64_t *d_tile_base = pd.scratch[1].as<uint64_t>(), *d_total = d_tile_base + n_tiles;
-    uint32_t *d_tile_cnt = reinterpret_cast<uint32_t *>(d_total + 1);
-    int32_t *d_htab = pd.scratch[2].as<int32_t>();
+    if ((rc = P.text.reserve(n_bytes + 64))) return rc;
+    if ((rc = P.tiles.reserve(n_tiles * 12 + 64))) return rc;
+    if ((rc = P.names.reserve(names_bytes + (size_t)(n_chr + 1) * 4 + (size_t)hsize * 4 + 64))) return rc;
+    P.d_text = P.text.as<uint8_t>();
+    P.d_tile_base = P.tiles.as<uint64_t>();
+    P.d_total = P.d_tile_base + n_tiles;
+    uint32_t *d_tile_cnt = reinterpret_cast<uint32_t *>(P.d_total + 1);
+    int32_t *d_htab = P.names.as<int32_t>();
     uint32_t *d_noff = reinterpret_cast<uint32_t *>(d_htab + hsize);
     uint8_t *d_names = reinterpret_cast<uint8_t *>(d_noff + (n_chr + 1));
-    CUDA_TRY(cudaMemcpyAsync(d_text, text, n_bytes, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(P.d_text, text, n_bytes, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d_htab, htab.data(), (size_t)hsize * 4, cudaMemcpyHostToDevice, st));
     if (n_chr) {
         CUDA_TRY(cudaMemcpyAsync(d_noff, chr_name_off, (size_t)(n_chr + 1) * 4, cudaMemcpyHostToDevice, st));
@@ -240,14 +329,43 @@ GAMS_API int32_t gams_cuda_parse_ranges(gams_cuda_ctx *ctx, const uint8_t *text,
         const uint32_t zero = 0;
         CUDA_TRY(cudaMemcpyAsync(d_noff, &zero, 4, cudaMemcpyHostToDevice, st));
     }
-    nl_count_kernel<<<(unsigned)n_tiles, PR_THREADS, 0, st>>>(d_text, n_bytes, d_tile_cnt);
-    nl_scan_kernel<<<1, 1024, 0, st>>>(d_tile_cnt, n_tiles, d_tile_base, d_total);
+    nl_count_kernel<<<(unsigned)n_tiles, PR_THREADS, 0, st>>>(P.d_text, n_bytes, d_tile_cnt);
+    nl_scan_kernel<<<1, 1024, 0, st>>>(d_tile_cnt, n_tiles, P.d_tile_base, P.d_total);
     uint64_t n_nl = 0;
-    uint8_t last = 0;
-    CUDA_TRY(cudaMemcpyAsync(&n_nl, d_total, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(&n_nl, P.d_total, 8, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));   // also: htab is a local
-    last = text[n_bytes - 1];
-    const uint64_t nl = n_nl + (last == '\n' ? 0 : 1);
+    const uint64_t nl = n_nl + (text[n_bytes - 1] == '\n' ? 0 : 1);
+    P.n_lines = nl;
+    if ((rc = P.lines.reserve((nl + 2) * 8 + nl * 12 + 64))) return rc;
+    P.d_loff = P.lines.as<uint64_t>();
+    P.d_qc = reinterpret_cast<int32_t *>(P.d_loff + nl + 2);
+    P.d_qs = reinterpret_cast<uint32_t *>(P.d_qc + nl);
+    P.d_qe = P.d_qs + nl;
+    nl_scatter_kernel<<<(unsigned)n_tiles, PR_THREADS, 0, st>>>(P.d_text, n_bytes, P.d_tile_base, nl, P.d_loff);
+    const unsigned pb = (unsigned)std::min<uint64_t>((nl + 255) / 256, 148ull * 32);
+    parse_lines_kernel<<<pb, 256, 0, st>>>(P.d_text, n_bytes, P.d_loff, nl, d_names, d_noff, d_htab, hsize - 1, P.d_qc, P.d_qs, P.d_qe);
+    CUDA_TRY(cudaGetLastError());
+    return GAMS_CUDA_OK;
+}
+}  // namespace
+
+GAMS_API int32_t gams_cuda_parse_ranges(gams_cuda_ctx *ctx, const uint8_t *text, uint64_t n_bytes, int64_t n_chr,
+                                        const uint8_t *chr_names, const uint32_t *chr_name_off, uint64_t cap_lines,
+                                        uint64_t *n_lines, uint64_t *line_off, int32_t *q_chr, uint32_t *q_start, uint32_t *q_end) {
+    ARG_CHECK(ctx && n_lines && n_chr >= 0 && n_chr < (1ll << 30), "parse_ranges: bad argument");
+    ARG_CHECK(n_chr == 0 || (chr_names && chr_name_off), "parse_ranges: NULL name table");
+    *n_lines = 0;
+    if (n_bytes == 0) return GAMS_CUDA_OK;
+    ARG_CHECK(text != nullptr, "parse_ranges: text is NULL");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    PerDevice &pd = ctx->devs[0];
+    DeviceGuard g(pd.device);
+    cudaStream_t st = pd.stream;
+    ParsedText P;
+    struct Rel { ParsedText &p; ~Rel() { cudaDeviceSynchronize(); p.release(); } } rel{P};
+    int32_t rc = parse_on_device(pd, st, text, n_bytes, n_chr, chr_names, chr_name_off, P);
+    if (rc) return rc;
+    const uint64_t nl = P.n_lines;
     *n_lines = nl;
     if (nl > cap_lines) {
         set_error("parse_ranges: %llu lines, room for %llu (call again with larger arrays)", (unsigned long long)nl,
@@ -255,19 +373,105 @@ GAMS_API int32_t gams_cuda_parse_ranges(gams_cuda_ctx *ctx, const uint8_t *text,
         return GAMS_CUDA_ECAP;
     }
     ARG_CHECK(line_off && q_chr && q_start && q_end, "parse_ranges: NULL output");
-    if ((rc = pd.scratch[3].reserve((nl + 2) * 8 + nl * 12 + 64))) return rc;
-    uint64_t *d_loff = pd.scratch[3].as<uint64_t>();
-    int32_t *d_qc = reinterpret_cast<int32_t *>(d_loff + nl + 2);
-    uint32_t *d_qs = reinterpret_cast<uint32_t *>(d_qc + nl), *d_qe = d_qs + nl;
-    nl_scatter_kernel<<<(unsigned)n_tiles, PR_THREADS, 0, st>>>(d_text, n_bytes, d_tile_base, nl, d_loff);
-    const unsigned pb = (unsigned)std::min<uint64_t>((nl + 255) / 256, 148ull * 32);
-    parse_lines_kernel<<<pb, 256, 0, st>>>(d_text, n_bytes, d_loff, nl, d_names, d_noff, d_htab, hsize - 1, d_qc, d_qs, d_qe);
-    CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpyAsync(line_off, d_loff, nl * 8, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(q_chr, d_qc, nl * 4, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(q_start, d_qs, nl * 4, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(q_end, d_qe, nl * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(line_off, P.d_loff, nl * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(q_chr, P.d_qc, nl * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(q_start, P.d_qs, nl * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(q_end, P.d_qe, nl * 4, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     line_off[nl] = n_bytes;
+    return GAMS_CUDA_OK;
+}
+
+// The whole loop of `gams locate --count -f file` (locate.rs:111-141) on the device: text in, text out.
+GAMS_API int32_t gams_cuda_locate_count_text(gams_cuda_ctx *ctx, const uint8_t *text, uint64_t n_bytes, int64_t n_chr,
+                                             const uint8_t *chr_names, const uint32_t *chr_name_off, const uint32_t *ctg_start,
+                                             const uint32_t *ctg_stop, const uint64_t *chr_off, const uint32_t *starts,
+                                             const uint32_t *stops, const uint64_t *iv_off, char **out_text, size_t *out_len,
+                                             uint64_t *n_lines, uint64_t *n_printed, uint64_t *n_handed_back) {
+    ARG_CHECK(ctx && out_text && out_len && n_chr >= 0 && n_chr < (1ll << 30) && chr_off && iv_off, "locate_count_text: bad argument");
+    ARG_CHECK(n_chr == 0 || (chr_names && chr_name_off), "locate_count_text: NULL name table");
+    *out_text = nullptr;
+    *out_len = 0;
+    if (n_lines) *n_lines = 0;
+    if (n_printed) *n_printed = 0;
+    if (n_handed_back) *n_handed_back = 0;
+    if (n_bytes == 0) return GAMS_CUDA_OK;
+    ARG_CHECK(text != nullptr, "locate_count_text: text is NULL");
+    ARG_CHECK(chr_off[0] == 0 && iv_off[0] == 0, "locate_count_text: chr_off[0] and iv_off[0] must be 0");
+    const uint64_t n_ctg = chr_off[n_chr], n_iv = iv_off[n_ctg];
+    ARG_CHECK(n_ctg < (1ull << 31), "locate_count_text: too many ctgs");
+    ARG_CHECK((ctg_start && ctg_stop) || n_ctg == 0, "locate_count_text: NULL ctg index");
+    ARG_CHECK((starts && stops) || n_iv == 0, "locate_count_text: NULL rg index");
+    std::vector<uint32_t> maxlen((size_t)std::max<int64_t>(n_chr, 1), 0);  // Lapper::new: max(stop - start)
+    for (int64_t c = 0; c < n_chr; ++c)
+        for (uint64_t k = chr_off[c]; k < chr_off[c + 1]; ++k)
+            if (ctg_stop[k] > ctg_start[k]) maxlen[c] = std::max(maxlen[c], ctg_stop[k] - ctg_start[k]);
+    gams_cuda_count_plan *plan = nullptr;
+    int32_t rc = gams_cuda_count_plan_create(ctx, 0, (int64_t)n_ctg, iv_off, &plan);
+    if (rc) return rc;
+    std::unique_ptr<gams_cuda_count_plan, void (*)(gams_cuda_count_plan *)> pguard(plan, gams_cuda_count_plan_destroy);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    PerDevice &pd = ctx->devs[0];
+    DeviceGuard g(pd.device);
+    cudaStream_t st = pd.stream;
+    ParsedText P;
+    DevBuf idx, work, outb;
+    idx.cache = work.cache = outb.cache = pd.cache;
+    struct Rel { ParsedText &p; DevBuf &a, &b, &c; ~Rel() { cudaDeviceSynchronize(); p.release(); a.release(); b.release(); c.release(); } } rel{P, idx, work, outb};
+    if ((rc = parse_on_device(pd, st, text, n_bytes, n_chr, chr_names, chr_name_off, P))) return rc;
+    const uint64_t nl = P.n_lines;
+    if (n_lines) *n_lines = nl;
+    // the two indexes
+    const uint64_t nc = std::max<uint64_t>(n_ctg, 1), ni = std::max<uint64_t>(n_iv, 1);
+    if ((rc = idx.reserve((uint64_t)(n_chr + 1) * 8 + nc * 8 + (uint64_t)std::max<int64_t>(n_chr, 1) * 4 + ni * 8 + 64))) return rc;
+    uint64_t *d_chr_off = idx.as<uint64_t>();
+    uint32_t *d_cs = reinterpret_cast<uint32_t *>(d_chr_off + (n_chr + 1)), *d_ce = d_cs + nc, *d_ml = d_ce + nc;
+    uint32_t *d_st = d_ml + std::max<int64_t>(n_chr, 1), *d_sp = d_st + ni;
+    CUDA_TRY(cudaMemcpyAsync(d_chr_off, chr_off, (uint64_t)(n_chr + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (n_ctg) {
+        CUDA_TRY(cudaMemcpyAsync(d_cs, ctg_start, n_ctg * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d_ce, ctg_stop, n_ctg * 4, cudaMemcpyHostToDevice, st));
+    }
+    CUDA_TRY(cudaMemcpyAsync(d_ml, maxlen.data(), maxlen.size() * 4, cudaMemcpyHostToDevice, st));
+    if (n_iv) {
+        CUDA_TRY(cudaMemcpyAsync(d_st, starts, n_iv * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d_sp, stops, n_iv * 4, cudaMemcpyHostToDevice, st));
+    }
+    // locate -> count -> lengths -> offsets -> bytes
+    const uint64_t n_ft = (nl + FM_THREADS - 1) / FM_THREADS;
+    if ((rc = work.reserve(nl * 8 + 8 + n_ft * 12 + 32 + 64))) return rc;
+    int32_t *d_seg = work.as<int32_t>();
+    uint32_t *d_cnt = reinterpret_cast<uint32_t *>(d_seg + nl);
+    uint64_t *d_fbase = reinterpret_cast<uint64_t *>(d_cnt + nl), *d_ftotal = d_fbase + n_ft;   // 8 nl bytes in: aligned
+    unsigned long long *d_counters = reinterpret_cast<unsigned long long *>(d_ftotal + 1);
+    uint32_t *d_flen = reinterpret_cast<uint32_t *>(d_counters + 2);
+    CUDA_TRY(cudaMemsetAsync(d_counters, 0, 16, st));
+    if ((rc = launch_locate_ctg(st, n_chr, d_cs, d_ce, d_chr_off, d_ml, (int64_t)nl, P.d_qc, P.d_qs, P.d_qe, d_seg))) return rc;
+    if ((rc = launch_count_overlaps(plan, st, d_st, d_sp, (int64_t)nl, d_seg, P.d_qs, P.d_qe, 0, d_cnt))) return rc;
+    fmt_len_kernel<<<(unsigned)n_ft, FM_THREADS, 0, st>>>(P.d_text, n_bytes, P.d_loff, nl, P.d_qc, d_seg, d_cnt, d_flen, d_counters);
+    nl_scan_kernel<<<1, 1024, 0, st>>>(d_flen, n_ft, d_fbase, d_ftotal);
+    uint64_t h[3] = {0, 0, 0};
+    CUDA_TRY(cudaMemcpyAsync(&h[0], d_ftotal, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(&h[1], d_counters, 16, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (n_printed) *n_printed = h[1];
+    if (n_handed_back) *n_handed_back = h[2];
+    const uint64_t total = h[0];
+    char *host = static_cast<char *>(malloc(total + 1));
+    if (!host) {
+        set_error("locate_count_text: cannot allocate %llu bytes for the output", (unsigned long long)total);
+        return GAMS_CUDA_ENOMEM;
+    }
+    if (total) {
+        if ((rc = outb.reserve(total + 64))) { free(host); return rc; }
+        fmt_write_kernel<<<(unsigned)n_ft, FM_THREADS, 0, st>>>(P.d_text, n_bytes, P.d_loff, nl, d_seg, d_cnt, d_fbase, outb.as<uint8_t>());
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpyAsync(host, outb.p, total, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { free(host); return cuda_fail(e, "locate_count_text output", __FILE__, __LINE__); }
+    }
+    host[total] = 0;
+    *out_text = host;
+    *out_len = (size_t)total;
     return GAMS_CUDA_OK;
 }

@@ -321,6 +321,20 @@ int32_t gams_cuda_parse_ranges(gams_cuda_ctx *ctx, const uint8_t *text, uint64_t
                                const uint8_t *chr_names, const uint32_t *chr_name_off, uint64_t cap_lines,
                                uint64_t *n_lines, uint64_t *line_off, int32_t *q_chr, uint32_t *q_start, uint32_t *q_end);
 
+/* The whole loop of `gams locate --count -f file` (src/cmd_gams/locate.rs:111-141) on the device, text in, text out:
+ * Range::from_str per line -> find_one_idx -> count_rg -> "{rg}\t{cnt}\n" for every line that is a valid range on a known
+ * ctg, in input order, rg being the input line itself (as locate.rs:139 prints it).
+ * ctg index: as gams_cuda_locate_ctg takes it (ctgs of chromosome c = [chr_off[c], chr_off[c+1]), sorted by start, stop
+ * exclusive); rg index: segment k of starts / stops / iv_off belongs to ctg k of that same order.
+ * Lines outside the strict form (see gams_cuda_parse_ranges) are NOT printed; *n_handed_back counts them, and a caller that
+ * sees a non-zero count runs those lines (gams_cuda_parse_ranges marks them) through the reference path.
+ * *out_text: malloc'ed, NUL-terminated, *out_len bytes; free with gams_cuda_free. */
+int32_t gams_cuda_locate_count_text(gams_cuda_ctx *ctx, const uint8_t *text, uint64_t n_bytes, int64_t n_chr,
+                                    const uint8_t *chr_names, const uint32_t *chr_name_off, const uint32_t *ctg_start,
+                                    const uint32_t *ctg_stop, const uint64_t *chr_off, const uint32_t *starts,
+                                    const uint32_t *stops, const uint64_t *iv_off, char **out_text, size_t *out_len,
+                                    uint64_t *n_lines, uint64_t *n_printed, uint64_t *n_handed_back);
+
 /* gams::find_one_idx (utils.rs:7-22) -> Lapper::find(start, stop).next() on the idx:ctg:{chr}
  * index: ctg intervals [chr_start, chr_end+1) sorted by start within each chromosome segment.
  * out[q] = global index of the first ctg (in start order) with ctg_start < q_stop && ctg_stop >

@@ -1050,3 +1050,46 @@ def test_parse_ranges_random_and_hostile_lines(ctx, orc):
     names2 = ["I", "c", "b", "y", "1", "_"]
     n_complex = _check_parse(ctx, orc, hostile, names2)
     assert n_complex >= 8
+
+
+def _locate_count_reference(orc, lines, idx_ctg, idx_rg):
+    out = []
+    for ln in lines:                                     # locate.rs:111-141
+        rg = orc.range_from_str(ln)
+        if rg is None:
+            continue
+        cid = orc.find_one_idx(idx_ctg, rg)
+        if not cid:
+            continue
+        out.append(f"{ln}\t{orc.count_rg(idx_rg, cid, rg)}\n")
+    return "".join(out)
+
+
+def test_locate_count_text_fixture(ctx, orc, s288c):
+    """`gams locate --count` text in, text out: the README / cli.rs:426-454 queries (`I:1000-2000\\t12`, `Mito:1000-2000\\t0`, II
+    dropped) and the whole SK1.snp.rg file as queries, byte for byte against the oracle's locate loop."""
+    ctgs, ids, idx_ctg, idx_rg, starts, stops, iv_off = _fixture_index(orc, s288c)
+    chrs = sorted({c[1] for c in ctgs})
+    order = [c for ch in chrs for c in sorted((c for c in ctgs if c[1] == ch), key=lambda c: c[2])]
+    chr_off = np.concatenate(([0], np.cumsum([sum(1 for c in ctgs if c[1] == ch) for ch in chrs]))).astype(np.uint64)
+    cs = np.array([c[2] for c in order], dtype=np.uint32)
+    ce = np.array([c[3] + 1 for c in order], dtype=np.uint32)
+    # the rg index in the ctg order of the locate arrays
+    lps = [idx_rg.get(c[0], orc.lapper_new([])) for c in order]
+    st = np.concatenate([lp["starts"] for lp in lps]).astype(np.uint32)
+    sp = np.concatenate([lp["stops"] for lp in lps]).astype(np.uint32)
+    off = np.concatenate(([0], np.cumsum([lp["starts"].size for lp in lps]))).astype(np.uint64)
+    qs = ["I:1000-2000", "II:1001-2000", "Mito:1000-2000", "I:100000-100001", "I:100001", "I:1", "I:230218-230300", "bad line", "I:5-1",
+          "S288c.I(+):1000-2000", "I:1000-2000\tcomment"]
+    text = ("\n".join(qs) + "\n").encode()
+    got, nl, npr, nb = api.locate_count_text(ctx, text, chrs, cs, ce, chr_off, st, sp, off)
+    ref = _locate_count_reference(orc, qs, idx_ctg, idx_rg)
+    assert got.decode() == ref and nl == len(qs) and nb == 0 and npr == ref.count("\n")
+    assert got.decode().splitlines()[:2] == ["I:1000-2000\t12", "Mito:1000-2000\t0"]
+    lines = bytes(s288c["snp_rg"]).decode().splitlines()
+    got, nl, npr, nb = api.locate_count_text(ctx, bytes(s288c["snp_rg"]), chrs, cs, ce, chr_off, st, sp, off)
+    assert got.decode() == _locate_count_reference(orc, lines, idx_ctg, idx_rg) and nb == 0 and nl == len(lines)
+    # a hostile line is counted, not printed
+    got, nl, npr, nb = api.locate_count_text(ctx, b"I:1000-2000\n I:1-2\nI:5\n", chrs, cs, ce, chr_off, st, sp, off)
+    assert nb == 1 and nl == 3 and got.decode() == _locate_count_reference(orc, ["I:1000-2000", "I:5"], idx_ctg, idx_rg)
+    assert api.locate_count_text(ctx, b"", chrs, cs, ce, chr_off, st, sp, off)[0] == b""
