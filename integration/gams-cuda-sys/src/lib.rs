@@ -155,6 +155,12 @@ extern "C" {
         ctx: *mut gams_cuda_ctx, text: *const u8, n_bytes: u64, n_chr: i64, chr_names: *const u8, chr_name_off: *const u32,
         cap_lines: u64, n_lines: *mut u64, line_off: *mut u64, q_chr: *mut i32, q_start: *mut u32, q_end: *mut u32,
     ) -> i32;
+    pub fn gams_cuda_locate_count_text(
+        ctx: *mut gams_cuda_ctx, text: *const u8, n_bytes: u64, n_chr: i64, chr_names: *const u8, chr_name_off: *const u32,
+        ctg_start: *const u32, ctg_stop: *const u32, chr_off: *const u64, starts: *const u32, stops: *const u32,
+        iv_off: *const u64, out_text: *mut *mut c_char, out_len: *mut usize, n_lines: *mut u64, n_printed: *mut u64,
+        n_handed_back: *mut u64,
+    ) -> i32;
     pub fn gams_cuda_build_idx_rg(
         ctx: *mut gams_cuda_ctx, n_seg: i64, start: *const u32, stop: *const u32, iv_off: *const u64,
         iv_start: *mut u32, iv_stop: *mut u32, starts: *mut u32, stops: *mut u32, max_len: *mut u32, blob: *mut u8,
