@@ -603,16 +603,23 @@ static int32_t wave_on_device(gams_cuda_ctx *ctx, int d, int64_t c0, int64_t c1,
     for (size_t k = n_pre; k < n_sl; ++k)
         if ((rc = enqueue_h2d(k))) return rc;
     trace_stage("wave: reserve");
+    // The sequential z-score kernel (influence != 1: one warp per ctg) needs thousands of ctgs in flight to hide its
+    // latency; on a 64 MB slice (~130 ctgs) it takes as long as on a quarter of a genome.  So it runs once per GROUP of
+    // slices (four groups: the first three overlap the upload of the next), 321 -> ~90 ms per 3.1 Gbp end to end.
+    const bool fused = want_sig && wave_fused_ok(plan, threshold, influence);
+    const bool deferred = want_sig && !fused && need_filt;
+    const size_t n_grp = deferred ? std::min<size_t>(4, n_sl) : 0;
+    size_t grp_first = 0;
     for (size_t k = 0; k < n_sl; ++k) {
         const int64_t a = cut[k], b = cut[k + 1];
         const uint64_t w0 = plan->h_win_off[a], w1 = plan->h_win_off[b];
         CUDA_TRY(cudaStreamWaitEvent(pd.stream, ev_in[k], 0));
-        if (want_sig && wave_fused_ok(plan, threshold, influence)) {
+        if (fused) {
             if ((rc = launch_gc_wave_fused(plan, pd.stream, d_seq, threshold, d_cnt, d_gc, d_sig, pd.d_zstats, a, b))) return rc;
         } else {
             if ((rc = launch_gc_windows(plan, pd.stream, d_seq, d_cnt, d_gc, &plan->launches, a, b))) return rc;
-            if (want_sig && (rc = launch_zscore(plan->win, pd.stream, d_gc, lag, threshold, influence, d_filt, d_sig,
-                                                &plan->launches, ctx->zscore_mode, pd.d_zstats, a, b)))
+            if (want_sig && !deferred && (rc = launch_zscore(plan->win, pd.stream, d_gc, lag, threshold, influence, d_filt, d_sig,
+                                                             &plan->launches, ctx->zscore_mode, pd.d_zstats, a, b)))
                 return rc;
         }
         CUDA_TRY(cudaEventRecord(ev_k[k], pd.stream));
@@ -621,7 +628,20 @@ static int32_t wave_on_device(gams_cuda_ctx *ctx, int d, int64_t c0, int64_t c1,
             CUDA_TRY(cudaMemcpyAsync(gc + wo + w0, d_gc + w0, (w1 - w0) * sizeof(float), cudaMemcpyDeviceToHost, pd.copy_out));
             if (gc_count)
                 CUDA_TRY(cudaMemcpyAsync(gc_count + wo + w0, d_cnt + w0, (w1 - w0) * sizeof(uint32_t), cudaMemcpyDeviceToHost, pd.copy_out));
-            if (signal) CUDA_TRY(cudaMemcpyAsync(signal + wo + w0, d_sig + w0, w1 - w0, cudaMemcpyDeviceToHost, pd.copy_out));
+            if (signal && !deferred) CUDA_TRY(cudaMemcpyAsync(signal + wo + w0, d_sig + w0, w1 - w0, cudaMemcpyDeviceToHost, pd.copy_out));
+        }
+        if (deferred && (k + 1 == n_sl || (k + 1) * n_grp / n_sl != k * n_grp / n_sl)) {   // last slice of its group
+            const int64_t ga = cut[grp_first];
+            const uint64_t gw0 = plan->h_win_off[ga];
+            if ((rc = launch_zscore(plan->win, pd.stream, d_gc, lag, threshold, influence, d_filt, d_sig, &plan->launches,
+                                    ctx->zscore_mode, pd.d_zstats, ga, b)))
+                return rc;
+            if (signal && w1 > gw0) {
+                CUDA_TRY(cudaEventRecord(ev_k[k], pd.stream));   // re-recorded behind the group's z-score kernel
+                CUDA_TRY(cudaStreamWaitEvent(pd.copy_out, ev_k[k], 0));
+                CUDA_TRY(cudaMemcpyAsync(signal + wo + gw0, d_sig + gw0, w1 - gw0, cudaMemcpyDeviceToHost, pd.copy_out));
+            }
+            grp_first = k + 1;
         }
     }
     trace_stage("wave: enqueue slices");
