@@ -372,6 +372,71 @@ zscore_seq_kernel(const float *__restrict__ x_all, const uint64_t *__restrict__ 
     }
 }
 
+// The same walk with the history in SHARED memory: a ring of P floats per warp (P a power of two >= lag + 65) holds the
+// committed filtered values of the last lag + 1 positions and the speculated x of the next 32, so a lane's 2 * lag
+// reads per window are shared-memory loads of consecutive addresses (conflict-free across the lanes) and nothing but x is read
+// from, and nothing but the signals written to, global memory (the kernel above moves ~400 global loads per window).
+constexpr int ZSEQ_WARPS = 4;
+template <int P>
+__global__ void __launch_bounds__(ZSEQ_WARPS * 32)
+zscore_seq_ring_kernel(const float *__restrict__ x_all, const uint64_t *__restrict__ off, int64_t s_begin, int64_t s_end,
+                       uint64_t lag, float threshold, float influence, int8_t *__restrict__ signal) {
+    __shared__ float ring_all[ZSEQ_WARPS][P];
+    const int lane = threadIdx.x & 31;
+    const int64_t c = s_begin + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (c >= s_end) return;
+    float *ring = ring_all[threadIdx.x >> 5];
+    const uint64_t base = off[c];
+    const int64_t n = (int64_t)(off[c + 1] - base);
+    const float *x = x_all + base;
+    int8_t *sg = signal + base;
+    const int64_t L = (int64_t)lag;
+    for (int64_t j = lane; j < L && j < n; j += 32) {
+        ring[j & (P - 1)] = x[j];           // filtered == data for the first lag values (stat.rs:24-27)
+        sg[j] = 0;
+    }
+    const float flag = __ull2float_rn((unsigned long long)lag);
+    const float flagm1 = __fsub_rn(flag, 1.0f);
+    const float one_minus = __fsub_rn(1.0f, influence);
+    int64_t i = L, front = L;               // ring holds positions [i - L - 1 (or 0), front): committed below i, speculated x from i on
+    while (i < n) {
+        for (int64_t pos = front + lane; pos < i + 32 && pos < n; pos += 32) ring[pos & (P - 1)] = x[pos];
+        front = (i + 32 < n) ? i + 32 : n;
+        __syncwarp();
+        const int64_t w = i + lane;
+        const bool active = w < n;
+        int my = 0;
+        float xv = 0.0f;
+        if (active) {
+            xv = ring[w & (P - 1)];
+            const int64_t a = (w - 1 - L > 0) ? (w - 1 - L) : 0;
+            auto ld = [&](int64_t e) { return ring[e & (P - 1)]; };
+            my = zscore_decide(ld, a, lag, flag, flagm1, xv, threshold);
+        }
+        const unsigned ballot = __ballot_sync(0xFFFFFFFFu, my != 0);
+        const int first = ballot ? (__ffs(ballot) - 1) : 32;
+        // lanes <= first+1 saw only correctly speculated values (the stats window of w ends at w-2)
+        int n_commit = (first >= 31) ? 32 : first + 2;
+        if ((int64_t)n_commit > n - i) n_commit = (int)(n - i);
+        // filtered value of the first signalling lane
+        const float prev_x = __shfl_up_sync(0xFFFFFFFFu, xv, 1);
+        float fw = xv;
+        if (lane == first) {
+            const float prev = (lane == 0) ? ring[(i - 1) & (P - 1)] : prev_x;  // predecessor did not signal => filtered == x
+            fw = __fadd_rn(__fmul_rn(influence, xv), __fmul_rn(one_minus, prev));
+        }
+        const float f_first = __shfl_sync(0xFFFFFFFFu, fw, first & 31);
+        if (lane == first + 1 && my != 0) fw = __fadd_rn(__fmul_rn(influence, xv), __fmul_rn(one_minus, f_first));
+        __syncwarp();                        // every lane has read the ring
+        if (lane < n_commit) {
+            ring[w & (P - 1)] = fw;          // committed: the filtered value replaces the speculated x
+            sg[w] = (int8_t)my;
+        }
+        __syncwarp();
+        i += n_commit;
+    }
+}
+
 int32_t launch_zscore(const SeriesLayout &L, cudaStream_t st, const float *d_x, uint64_t lag, float threshold,
                       float influence, float *d_filtered, int8_t *d_signal, uint64_t *launches, int mode,
                       unsigned long long *d_stats, int64_t s0, int64_t s1) {
@@ -406,8 +471,13 @@ int32_t launch_zscore(const SeriesLayout &L, cudaStream_t st, const float *d_x, 
             set_error("thresholding: influence != 1 (or lag too large for the tiled path) needs the d_filtered scratch");
             return GAMS_CUDA_EINVAL;
         }
-        const unsigned grid = (unsigned)((s1 - s0 + 3) / 4);
-        zscore_seq_kernel<<<grid, 128, 0, st>>>(d_x, L.d_off, s0, s1, lag, threshold, influence, d_filtered, d_signal);
+        const unsigned grid = (unsigned)((s1 - s0 + ZSEQ_WARPS - 1) / ZSEQ_WARPS);
+        if (lag + 65 <= 256)
+            zscore_seq_ring_kernel<256><<<grid, ZSEQ_WARPS * 32, 0, st>>>(d_x, L.d_off, s0, s1, lag, threshold, influence, d_signal);
+        else if (lag + 65 <= 1024)
+            zscore_seq_ring_kernel<1024><<<grid, ZSEQ_WARPS * 32, 0, st>>>(d_x, L.d_off, s0, s1, lag, threshold, influence, d_signal);
+        else
+            zscore_seq_kernel<<<grid, 128, 0, st>>>(d_x, L.d_off, s0, s1, lag, threshold, influence, d_filtered, d_signal);
     }
     if (launches) ++*launches;
     CUDA_TRY(cudaGetLastError());
