@@ -423,6 +423,7 @@ def main():
 
         # context for the e2e number: what this box's PCIe link gives for one plain pinned copy each way
         tpc = []
+        api.check(L.gams_cuda_memcpy_probe(ctx.handle, h_seq_ptr, min(n_bases, 1 << 30), 1))   # untimed: reserves the device scratch
         for kind in (1, 2):
             torch.cuda.synchronize()
             t0 = time.perf_counter()
