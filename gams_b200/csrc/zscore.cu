@@ -437,6 +437,93 @@ zscore_seq_ring_kernel(const float *__restrict__ x_all, const uint64_t *__restri
     }
 }
 
+// influence != 1 without walking every window.  filtered differs from data only AT signals (stat.rs:40-48), so a window whose
+// stats window holds no signal sees plain data and its decision is the influence-1 decision D1 (a pure function of the data,
+// computed for all windows in parallel by zscore_indep_kernel beforehand, in `signal`).  The walk therefore alternates:
+//   clean  - no signal among the last lag + 1 windows: jump to the next window with D1 != 0 (32 windows per ballot); every
+//            window passed keeps D1 = 0, and the one found signals exactly as D1 says (its stats window is clean too);
+//   dirty  - from there on windows are replayed in order with the true filtered history (the ring of the kernel above),
+//            until lag + 1 windows in a row have not signalled.
+// Only the dirty stretches (~40 % of a genome at threshold 3) pay the sequential replay.
+template <int P>
+__global__ void __launch_bounds__(ZSEQ_WARPS * 32)
+zscore_seq_skip_kernel(const float *__restrict__ x_all, const uint64_t *__restrict__ off, int64_t s_begin, int64_t s_end,
+                       uint64_t lag, float threshold, float influence, int8_t *signal) {
+    __shared__ float ring_all[ZSEQ_WARPS][P];
+    const int lane = threadIdx.x & 31;
+    const int64_t c = s_begin + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (c >= s_end) return;
+    float *ring = ring_all[threadIdx.x >> 5];
+    const uint64_t base = off[c];
+    const int64_t n = (int64_t)(off[c + 1] - base);
+    const float *x = x_all + base;
+    int8_t *sg = signal + base;
+    const int64_t L = (int64_t)lag;
+    const float flag = __ull2float_rn((unsigned long long)lag);
+    const float flagm1 = __fsub_rn(flag, 1.0f);
+    const float one_minus = __fsub_rn(1.0f, influence);
+    int64_t i = L;                          // next window to decide; windows < L never signal (D1 wrote 0 there)
+    while (i < n) {
+        // ---- clean: the next window whose D1 is a signal
+        int64_t p = -1;
+        while (i < n) {
+            const int64_t w = i + lane;
+            const unsigned b = __ballot_sync(0xFFFFFFFFu, w < n && sg[w] != 0);
+            if (b) { p = i + (__ffs(b) - 1); break; }
+            i += 32;
+        }
+        if (p < 0) break;
+        // window p signals as D1 says; the ring takes the data of [p - L - 1, p) and the filtered value of p
+        {
+            const int64_t a = (p - L - 1 > 0) ? p - L - 1 : 0;
+            for (int64_t e = a + lane; e < p; e += 32) ring[e & (P - 1)] = x[e];
+            if (lane == 0) ring[p & (P - 1)] = __fadd_rn(__fmul_rn(influence, x[p]), __fmul_rn(one_minus, x[p - 1]));
+        }
+        int64_t last_sig = p, front = p + 1;
+        i = p + 1;
+        __syncwarp();
+        // ---- dirty: sequential replay until the stats window of window i is clean again
+        while (i < n && last_sig >= i - 1 - L) {
+            for (int64_t pos = front + lane; pos < i + 32 && pos < n; pos += 32) ring[pos & (P - 1)] = x[pos];
+            front = (i + 32 < n) ? i + 32 : n;
+            __syncwarp();
+            const int64_t w = i + lane;
+            const bool active = w < n;
+            int my = 0;
+            float xv = 0.0f;
+            if (active) {
+                xv = ring[w & (P - 1)];
+                const int64_t a = (w - 1 - L > 0) ? (w - 1 - L) : 0;
+                auto ld = [&](int64_t e) { return ring[e & (P - 1)]; };
+                my = zscore_decide(ld, a, lag, flag, flagm1, xv, threshold);
+            }
+            const unsigned ballot = __ballot_sync(0xFFFFFFFFu, my != 0);
+            const int first = ballot ? (__ffs(ballot) - 1) : 32;
+            int n_commit = (first >= 31) ? 32 : first + 2;     // lanes <= first + 1 saw only correctly speculated values
+            if ((int64_t)n_commit > n - i) n_commit = (int)(n - i);
+            const float prev_x = __shfl_up_sync(0xFFFFFFFFu, xv, 1);
+            float fw = xv;
+            if (lane == first) {
+                const float prev = (lane == 0) ? ring[(i - 1) & (P - 1)] : prev_x;
+                fw = __fadd_rn(__fmul_rn(influence, xv), __fmul_rn(one_minus, prev));
+            }
+            const float f_first = __shfl_sync(0xFFFFFFFFu, fw, first & 31);
+            if (lane == first + 1 && my != 0) fw = __fadd_rn(__fmul_rn(influence, xv), __fmul_rn(one_minus, f_first));
+            if (first < n_commit) {
+                last_sig = i + first;
+                if (first + 1 < n_commit && ((ballot >> (first + 1)) & 1u)) last_sig = i + first + 1;
+            }
+            __syncwarp();
+            if (lane < n_commit) {
+                ring[w & (P - 1)] = fw;
+                sg[w] = (int8_t)my;
+            }
+            __syncwarp();
+            i += n_commit;
+        }
+    }
+}
+
 int32_t launch_zscore(const SeriesLayout &L, cudaStream_t st, const float *d_x, uint64_t lag, float threshold,
                       float influence, float *d_filtered, int8_t *d_signal, uint64_t *launches, int mode,
                       unsigned long long *d_stats, int64_t s0, int64_t s1) {
@@ -451,7 +538,10 @@ int32_t launch_zscore(const SeriesLayout &L, cudaStream_t st, const float *d_x, 
         return GAMS_CUDA_ELAG;
     }
     const bool tiled = influence == 1.0f && lag <= ZS_MAX_TILED_LAG;
-    if (tiled) {
+    // influence != 1 with a lag the shared-memory ring holds: the influence-1 decisions of every window first (parallel),
+    // then the walk that replays only the stretches behind a signal
+    const bool skip = !tiled && lag <= ZS_MAX_TILED_LAG && lag + 65 <= 1024 && mode == 0;
+    if (tiled || skip) {
         const int n_el_max = ZS_TILE + (int)lag + 1;
         const size_t smem_need = (size_t)(n_el_max + 1) * 16 + (size_t)(zs_swz(n_el_max) + 1) * sizeof(float) + 2 * ZS_TILE;
         const ZsConst zc = make_zs_const(lag, threshold);
@@ -466,6 +556,14 @@ int32_t launch_zscore(const SeriesLayout &L, cudaStream_t st, const float *d_x, 
         };
         int32_t rc = mode == 1 ? go(zscore_indep_kernel<1>) : mode == 2 ? go(zscore_indep_kernel<2>) : go(zscore_indep_kernel<0>);
         if (rc) return rc;
+        if (skip) {
+            const unsigned grid = (unsigned)((s1 - s0 + ZSEQ_WARPS - 1) / ZSEQ_WARPS);
+            if (lag + 65 <= 256)
+                zscore_seq_skip_kernel<256><<<grid, ZSEQ_WARPS * 32, 0, st>>>(d_x, L.d_off, s0, s1, lag, threshold, influence, d_signal);
+            else
+                zscore_seq_skip_kernel<1024><<<grid, ZSEQ_WARPS * 32, 0, st>>>(d_x, L.d_off, s0, s1, lag, threshold, influence, d_signal);
+            if (launches) ++*launches;
+        }
     } else {
         if (!d_filtered) {
             set_error("thresholding: influence != 1 (or lag too large for the tiled path) needs the d_filtered scratch");
