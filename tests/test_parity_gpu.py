@@ -1093,3 +1093,27 @@ def test_locate_count_text_fixture(ctx, orc, s288c):
     got, nl, npr, nb = api.locate_count_text(ctx, b"I:1000-2000\n I:1-2\nI:5\n", chrs, cs, ce, chr_off, st, sp, off)
     assert nb == 1 and nl == 3 and got.decode() == _locate_count_reference(orc, ["I:1000-2000", "I:5"], idx_ctg, idx_rg)
     assert api.locate_count_text(ctx, b"", chrs, cs, ce, chr_off, st, sp, off)[0] == b""
+
+
+@pytest.mark.parametrize("infl", [0.0, 0.3, 0.9, 2.0])
+def test_thresholding_influence_clean_dirty_transitions(ctx, orc, infl):
+    """The influence != 1 walk jumps between influence-1 signals and replays only behind them: series built to sit on its
+    edges - isolated spikes exactly lag, lag + 1 and lag + 2 apart, bursts, a step (every window after it signals until
+    the filtered history catches up - or never, for influence 0), a spike in the last window, GC-like quantised data."""
+    rng = np.random.default_rng(int(infl * 100) + 5)
+    for lag in (5, 30, 100):
+        series = []
+        for gap in (lag - 1, lag, lag + 1, lag + 2, lag + 3, 2 * lag + 5):
+            s = rng.normal(0.4, 0.01, 40 * gap + 3 * lag + 7).astype(np.float32)
+            s[lag + 3::gap] += 1.0
+            series.append(s)
+        s = rng.normal(0.4, 0.01, 5000).astype(np.float32); s[2500:] += 0.5; series.append(s)                 # a step
+        s = rng.normal(0.4, 0.01, 3000).astype(np.float32); s[1000:1040] += rng.normal(0.5, 0.3, 40).astype(np.float32); s[-1] += 2; series.append(s)
+        s = (rng.integers(30, 60, 6000) / np.float32(100)).astype(np.float32); s[rng.integers(0, 6000, 40)] = np.float32(0.9); series.append(s)
+        s = np.full(2000, 0.25, np.float32); s[700] = 0.5; s[1500:1510] = 0.1; series.append(s)               # constant: std == 0
+        data = np.concatenate(series)
+        off = np.concatenate(([0], np.cumsum([x.size for x in series]))).astype(np.uint64)
+        for thr in (3.0, 1.0):
+            got = api.thresholding_batch(ctx, data, off, lag, thr, infl)
+            ref = np.concatenate([orc.thresholding_algo(x, lag, thr, infl) for x in series])
+            _eq(f"clean/dirty lag {lag} infl {infl} thr {thr}", got, ref)
