@@ -475,6 +475,14 @@ GAMS_API int32_t gams_cuda_wave_dev(gams_cuda_wave_plan *p, void *stream, const 
     if (aligned && wave_fused_ok(p, threshold, influence))
         return launch_gc_wave_fused(p, (cudaStream_t)stream, d_seq, threshold, d_gc_count, d_gc, d_signal,
                                     p->ctx->devs[p->dev_index].d_zstats, 0, p->n_ctg);
+    // influence != 1 on a fused-eligible geometry: the fused kernel gives GC and the influence-1 decisions, the walk replays
+    // the stretches behind the signals
+    if (aligned && influence != 1.0f && wave_fused_ok(p, threshold, 1.0f) && zscore_skip_ok(p->lag)) {
+        int32_t rc = launch_gc_wave_fused(p, (cudaStream_t)stream, d_seq, threshold, d_gc_count, d_gc, d_signal,
+                                          p->ctx->devs[p->dev_index].d_zstats, 0, p->n_ctg);
+        if (rc) return rc;
+        return launch_zscore_skip(p->win, (cudaStream_t)stream, d_gc, p->lag, threshold, influence, d_signal, &p->launches, 0, p->n_ctg);
+    }
     int32_t rc = launch_gc_windows(p, (cudaStream_t)stream, d_seq, d_gc_count, d_gc, &p->launches, 0, p->n_ctg);
     if (rc) return rc;
     return launch_zscore(p->win, (cudaStream_t)stream, d_gc, p->lag, threshold, influence, d_filtered, d_signal,
@@ -606,8 +614,9 @@ static int32_t wave_on_device(gams_cuda_ctx *ctx, int d, int64_t c0, int64_t c1,
     // The sequential z-score kernel (influence != 1: one warp per ctg) needs thousands of ctgs in flight to hide its
     // latency; on a 64 MB slice (~130 ctgs) it takes as long as on a quarter of a genome.  So it runs once per GROUP of
     // slices (four groups: the first three overlap the upload of the next), 321 -> ~90 ms per 3.1 Gbp end to end.
-    const bool fused = want_sig && wave_fused_ok(plan, threshold, influence);
-    const bool deferred = want_sig && !fused && need_filt;
+    const bool fused_walk = want_sig && influence != 1.0f && wave_fused_ok(plan, threshold, 1.0f) && zscore_skip_ok(lag);
+    const bool fused = want_sig && (wave_fused_ok(plan, threshold, influence) || fused_walk);
+    const bool deferred = want_sig && (fused_walk || (!fused && need_filt));
     const size_t n_grp = deferred ? std::min<size_t>(4, n_sl) : 0;
     size_t grp_first = 0;
     for (size_t k = 0; k < n_sl; ++k) {
@@ -633,9 +642,10 @@ static int32_t wave_on_device(gams_cuda_ctx *ctx, int d, int64_t c0, int64_t c1,
         if (deferred && (k + 1 == n_sl || (k + 1) * n_grp / n_sl != k * n_grp / n_sl)) {   // last slice of its group
             const int64_t ga = cut[grp_first];
             const uint64_t gw0 = plan->h_win_off[ga];
-            if ((rc = launch_zscore(plan->win, pd.stream, d_gc, lag, threshold, influence, d_filt, d_sig, &plan->launches,
-                                    ctx->zscore_mode, pd.d_zstats, ga, b)))
-                return rc;
+            if (fused_walk) rc = launch_zscore_skip(plan->win, pd.stream, d_gc, lag, threshold, influence, d_sig, &plan->launches, ga, b);
+            else rc = launch_zscore(plan->win, pd.stream, d_gc, lag, threshold, influence, d_filt, d_sig, &plan->launches,
+                                    ctx->zscore_mode, pd.d_zstats, ga, b);
+            if (rc) return rc;
             if (signal && w1 > gw0) {
                 CUDA_TRY(cudaEventRecord(ev_k[k], pd.stream));   // re-recorded behind the group's z-score kernel
                 CUDA_TRY(cudaStreamWaitEvent(pd.copy_out, ev_k[k], 0));

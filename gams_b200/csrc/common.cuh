@@ -269,4 +269,7 @@ int32_t launch_gc_wave_fused(gams_cuda_wave_plan *p, cudaStream_t st, const uint
 void fused_tiles_for_ctg(std::vector<FusedTile> &out, uint64_t seq_off, uint64_t win_off, uint64_t n_c, int32_t step,
                          uint64_t lag, int wt);
 bool wave_fused_ok(const gams_cuda_wave_plan *p, float threshold, float influence);
+bool zscore_skip_ok(uint64_t lag);
+int32_t launch_zscore_skip(const SeriesLayout &L, cudaStream_t st, const float *d_x, uint64_t lag, float threshold, float influence,
+                           int8_t *d_signal, uint64_t *launches, int64_t s0, int64_t s1);
 }  // namespace gams

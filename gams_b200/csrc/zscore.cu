@@ -524,6 +524,21 @@ zscore_seq_skip_kernel(const float *__restrict__ x_all, const uint64_t *__restri
     }
 }
 
+// the walk alone: d_signal holds the influence-1 decisions of every window (from zscore_indep_kernel or the fused GC-wave kernel)
+bool zscore_skip_ok(uint64_t lag) { return lag >= 1 && lag + 65 <= 1024; }
+int32_t launch_zscore_skip(const SeriesLayout &L, cudaStream_t st, const float *d_x, uint64_t lag, float threshold, float influence,
+                           int8_t *d_signal, uint64_t *launches, int64_t s0, int64_t s1) {
+    if (L.n_series == 0 || s1 <= s0) return GAMS_CUDA_OK;
+    const unsigned grid = (unsigned)((s1 - s0 + ZSEQ_WARPS - 1) / ZSEQ_WARPS);
+    if (lag + 65 <= 256)
+        zscore_seq_skip_kernel<256><<<grid, ZSEQ_WARPS * 32, 0, st>>>(d_x, L.d_off, s0, s1, lag, threshold, influence, d_signal);
+    else
+        zscore_seq_skip_kernel<1024><<<grid, ZSEQ_WARPS * 32, 0, st>>>(d_x, L.d_off, s0, s1, lag, threshold, influence, d_signal);
+    if (launches) ++*launches;
+    CUDA_TRY(cudaGetLastError());
+    return GAMS_CUDA_OK;
+}
+
 int32_t launch_zscore(const SeriesLayout &L, cudaStream_t st, const float *d_x, uint64_t lag, float threshold,
                       float influence, float *d_filtered, int8_t *d_signal, uint64_t *launches, int mode,
                       unsigned long long *d_stats, int64_t s0, int64_t s1) {
@@ -540,7 +555,7 @@ int32_t launch_zscore(const SeriesLayout &L, cudaStream_t st, const float *d_x, 
     const bool tiled = influence == 1.0f && lag <= ZS_MAX_TILED_LAG;
     // influence != 1 with a lag the shared-memory ring holds: the influence-1 decisions of every window first (parallel),
     // then the walk that replays only the stretches behind a signal
-    const bool skip = !tiled && lag <= ZS_MAX_TILED_LAG && lag + 65 <= 1024 && mode == 0;
+    const bool skip = !tiled && lag <= ZS_MAX_TILED_LAG && zscore_skip_ok(lag) && mode == 0;
     if (tiled || skip) {
         const int n_el_max = ZS_TILE + (int)lag + 1;
         const size_t smem_need = (size_t)(n_el_max + 1) * 16 + (size_t)(zs_swz(n_el_max) + 1) * sizeof(float) + 2 * ZS_TILE;
@@ -556,14 +571,7 @@ int32_t launch_zscore(const SeriesLayout &L, cudaStream_t st, const float *d_x, 
         };
         int32_t rc = mode == 1 ? go(zscore_indep_kernel<1>) : mode == 2 ? go(zscore_indep_kernel<2>) : go(zscore_indep_kernel<0>);
         if (rc) return rc;
-        if (skip) {
-            const unsigned grid = (unsigned)((s1 - s0 + ZSEQ_WARPS - 1) / ZSEQ_WARPS);
-            if (lag + 65 <= 256)
-                zscore_seq_skip_kernel<256><<<grid, ZSEQ_WARPS * 32, 0, st>>>(d_x, L.d_off, s0, s1, lag, threshold, influence, d_signal);
-            else
-                zscore_seq_skip_kernel<1024><<<grid, ZSEQ_WARPS * 32, 0, st>>>(d_x, L.d_off, s0, s1, lag, threshold, influence, d_signal);
-            if (launches) ++*launches;
-        }
+        if (skip && (rc = launch_zscore_skip(L, st, d_x, lag, threshold, influence, d_signal, launches, s0, s1))) return rc;
     } else {
         if (!d_filtered) {
             set_error("thresholding: influence != 1 (or lag too large for the tiled path) needs the d_filtered scratch");
