@@ -372,6 +372,36 @@ zscore_seq_kernel(const float *__restrict__ x_all, const uint64_t *__restrict__ 
     }
 }
 
+// zscore_decide on a ring of P floats, the window [a, a + L) cut where the ring wraps: two runs of consecutive addresses,
+// so an element costs one LDS + one FADD in the first pass and LDS + FSUB + FMUL + FADD in the second (same order, same
+// operations as zscore_decide)
+template <int P>
+__device__ __forceinline__ int ring_decide(const float *ring, int64_t a, uint32_t l32, float flag, float flagm1, float xv, float threshold) {
+    const uint32_t r0 = (uint32_t)a & (uint32_t)(P - 1);
+    const uint32_t n1 = min(l32, (uint32_t)P - r0), n2 = l32 - n1;
+    const float *p1 = ring + r0;
+    float s = 0.0f;
+#pragma unroll 4
+    for (uint32_t t = 0; t < n1; ++t) s = __fadd_rn(s, p1[t]);
+#pragma unroll 4
+    for (uint32_t t = 0; t < n2; ++t) s = __fadd_rn(s, ring[t]);
+    const float m = __fdiv_rn(s, flag);
+    float q = 0.0f;
+#pragma unroll 4
+    for (uint32_t t = 0; t < n1; ++t) {
+        const float d = __fsub_rn(p1[t], m);
+        q = __fadd_rn(q, __fmul_rn(d, d));
+    }
+#pragma unroll 4
+    for (uint32_t t = 0; t < n2; ++t) {
+        const float d = __fsub_rn(ring[t], m);
+        q = __fadd_rn(q, __fmul_rn(d, d));
+    }
+    const float sd = __fsqrt_rn(__fdiv_rn(q, flagm1));
+    if (fabsf(__fsub_rn(xv, m)) > __fmul_rn(threshold, sd)) return (xv > m) ? 1 : -1;
+    return 0;
+}
+
 // The same walk with the history in SHARED memory: a ring of P floats per warp (P a power of two >= lag + 65) holds the
 // committed filtered values of the last lag + 1 positions and the speculated x of the next 32, so a lane's 2 * lag
 // reads per window are shared-memory loads of consecutive addresses (conflict-free across the lanes) and nothing but x is read
@@ -410,8 +440,7 @@ zscore_seq_ring_kernel(const float *__restrict__ x_all, const uint64_t *__restri
         if (active) {
             xv = ring[w & (P - 1)];
             const int64_t a = (w - 1 - L > 0) ? (w - 1 - L) : 0;
-            auto ld = [&](int64_t e) { return ring[e & (P - 1)]; };
-            my = zscore_decide(ld, a, lag, flag, flagm1, xv, threshold);
+            my = ring_decide<P>(ring, a, (uint32_t)lag, flag, flagm1, xv, threshold);
         }
         const unsigned ballot = __ballot_sync(0xFFFFFFFFu, my != 0);
         const int first = ballot ? (__ffs(ballot) - 1) : 32;
@@ -494,8 +523,7 @@ zscore_seq_skip_kernel(const float *__restrict__ x_all, const uint64_t *__restri
             if (active) {
                 xv = ring[w & (P - 1)];
                 const int64_t a = (w - 1 - L > 0) ? (w - 1 - L) : 0;
-                auto ld = [&](int64_t e) { return ring[e & (P - 1)]; };
-                my = zscore_decide(ld, a, lag, flag, flagm1, xv, threshold);
+                my = ring_decide<P>(ring, a, (uint32_t)lag, flag, flagm1, xv, threshold);
             }
             const unsigned ballot = __ballot_sync(0xFFFFFFFFu, my != 0);
             const int first = ballot ? (__ffs(ballot) - 1) : 32;
