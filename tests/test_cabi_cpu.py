@@ -145,3 +145,17 @@ def test_new_entry_points_reject_bad_arguments_without_a_device():
     L.gams_cuda_cwin_plan_destroy(None)
     L.gams_cuda_cwin_plan_invalidate(None)
     assert b"NULL" in L.gams_cuda_last_error() or b"bad" in L.gams_cuda_last_error()
+
+
+def test_window_count_binning_multiply_high_is_exact():
+    """count_windows.cu bins an index element with floor(d / step) computed as (d * ceil(2^32 / step)) >> 32 for step < 1024 and
+    d < 4096 * step (a tile's span).  The claim in the kernel's comment, checked here for every step on the values around every
+    multiple of step (where a wrong quotient would first show) and on random ones."""
+    rng = np.random.default_rng(0)
+    for step in range(2, 1024):
+        magic = ((1 << 32) + step - 1) // step
+        k = np.arange(0, 4096, dtype=np.uint64)
+        d = np.concatenate([k * step, k * step + (step - 1), np.maximum(k * step, 1) - 1,
+                            rng.integers(0, 4096 * step, 2000).astype(np.uint64)])
+        d = d[d < 4096 * step]
+        assert np.array_equal((d * np.uint64(magic)) >> np.uint64(32), d // np.uint64(step)), step
