@@ -1156,3 +1156,19 @@ def test_gunzip_fuzzed_blobs_are_contained(ctx, orc):
         else:
             n_bad += 1
     assert n_bad > 150
+
+
+def test_parse_ranges_fuzzed_text(ctx, orc):
+    """Random text over the characters that matter to the grammar: whatever the device does not hand back (-3) must agree with the
+    reference expression, line by line; nothing crashes on binary junk either."""
+    rng = np.random.default_rng(31)
+    alphabet = list("I:-_().+ 0123456789chrX/ab\t") + ["II", "10", "000", "chr1", "(+)", "(-)", ":", ":", "-"]
+    lines = ["".join(rng.choice(alphabet, int(rng.integers(0, 14)))) for _ in range(30_000)]
+    lines = [ln.replace("\n", "").replace("\r", "") for ln in lines]
+    names = ["I", "II", "chr1", "X", "a", "b", "chrX", "c", "h", "r"]
+    n_complex = _check_parse(ctx, orc, lines, names)
+    assert n_complex < len(lines)
+    junk = bytes(rng.integers(0, 256, 200_000, dtype=np.uint8))
+    got = api.parse_ranges(ctx, junk, names)
+    assert got["chr"].size == junk.count(b"\n") + (0 if junk.endswith(b"\n") else 1)
+    assert set(np.unique(got["chr"]).tolist()) <= set(range(-3, len(names)))
