@@ -863,7 +863,7 @@ GAMS_API void gams_cuda_count_plan_destroy(gams_cuda_count_plan *p) {
 GAMS_API uint64_t gams_cuda_count_plan_launches(const gams_cuda_count_plan *p) { return p ? p->launches : 0; }
 
 GAMS_API void gams_cuda_count_plan_invalidate(gams_cuda_count_plan *p) {
-    if (p) p->idx_valid = p->cidx_valid = false;
+    if (p) p->idx_valid = p->cidx_valid = p->part_valid = false;
 }
 
 GAMS_API int32_t gams_cuda_count_overlaps_dev(gams_cuda_count_plan *p, void *stream, const uint32_t *d_starts,

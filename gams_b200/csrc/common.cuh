@@ -209,7 +209,7 @@ struct gams_cuda_count_plan {
     uint64_t max_seg = 0;
     std::vector<uint64_t> h_iv_off;
     uint64_t *d_iv_off = nullptr;
-    gams::DevBuf tmp[6];             // [0] SegRank per segment, [1]/[2] rank tables of starts[] / stops[]
+    gams::DevBuf tmp[9];             // [0] SegRank per segment, [1]/[2] rank tables of starts[] / stops[]; [6]-[8]: overlap_part.cu
     const uint32_t *idx_starts = nullptr, *idx_stops = nullptr;  // arrays the rank tables were built for
     bool idx_valid = false;
     // compact per-segment index of the staged kernel (queries grouped by segment): tmp[4] = offsets + parameters, tmp[5] = data
@@ -217,7 +217,10 @@ struct gams_cuda_count_plan {
     bool cidx_valid = false;
     size_t cpar_off = 0;
     size_t st_smem = 0;              // dynamic shared memory of the staged kernel: the largest staged segment
-    int mode = 0;                    // 0 ranked (default), 1 plain binary search (GAMS_CUDA_COUNT_MODE)
+    int mode = 0;                    // 0 default (partitioned / ranked / staged), 1 plain binary search, 2 ranked only (GAMS_CUDA_COUNT_MODE)
+    // partitioned path for queries in arbitrary order (overlap_part.cu): bucket tables in tmp[7], valid for the compact index
+    bool part_valid = false;
+    int part_nbkt = 0, part_sb = 0;
     uint64_t launches = 0;
 };
 
@@ -235,6 +238,11 @@ int32_t launch_count_overlaps(gams_cuda_count_plan *p, cudaStream_t st, const ui
                               uint32_t *d_out);
 int32_t build_count_index(gams_cuda_count_plan *p, cudaStream_t st, const uint32_t *d_starts, const uint32_t *d_stops);
 int32_t build_compact_index(gams_cuda_count_plan *p, cudaStream_t st, const uint32_t *d_starts, const uint32_t *d_stops);
+// overlap_part.cu: queries in arbitrary order through a coarse partition; *done = false: not eligible, nothing was enqueued
+bool count_part_eligible(const gams_cuda_count_plan *p, int64_t n_q);
+int32_t launch_count_overlaps_part(gams_cuda_count_plan *p, cudaStream_t st, const uint32_t *d_starts, const uint32_t *d_stops,
+                                   int64_t n_q, const int32_t *d_q_seg, const uint32_t *d_q_start, const uint32_t *d_q_stop,
+                                   uint32_t *d_out, bool *done);
 int32_t launch_locate_ctg(cudaStream_t st, int64_t n_chr, const uint32_t *d_ctg_start, const uint32_t *d_ctg_stop,
                           const uint64_t *d_chr_off, const uint32_t *d_chr_maxlen, int64_t n_q,
                           const int32_t *d_q_chr, const uint32_t *d_q_start, const uint32_t *d_q_stop, int32_t *d_out);
