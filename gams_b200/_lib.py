@@ -96,6 +96,8 @@ def load() -> C.CDLL:
         "gams_cuda_parse_ranges": (i32, [vp, vp, u64, i64, vp, vp, u64, C.POINTER(u64), vp, vp, vp, vp]),
         "gams_cuda_locate_count_text": (i32, [vp, vp, u64, i64, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(vp), C.POINTER(sz),
                                               C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]),
+        "gams_cuda_locate_count_lines": (i32, [vp, vp, u64, i64, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(vp), C.POINTER(sz),
+                                               C.POINTER(vp), C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]),
         "gams_cuda_build_idx_rg": (i32, [vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "gams_cuda_locate_ctg": (i32, [vp, i64, vp, vp, vp, i64, vp, vp, vp, vp]),
         "gams_cuda_lapper_blob_view": (i32, [vp, sz, C.POINTER(u64), C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_uint32)]),

@@ -8,6 +8,7 @@ libgams_cuda.so; nothing here computes on the CPU.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 
 import numpy as np
 
@@ -35,6 +36,7 @@ class Context:
             check(L.gams_cuda_create(_p(ids), ids.size, C.byref(h)))
         self._h = h
         self._L = L
+        self._plans = weakref.WeakSet()   # plans keep pointers into the context: they are closed before it goes
 
     @property
     def handle(self):
@@ -56,6 +58,8 @@ class Context:
 
     def close(self):
         if getattr(self, "_h", None):
+            for plan in list(self._plans):
+                plan.close()
             self._L.gams_cuda_destroy(self._h)
             self._h = None
 
@@ -318,6 +322,7 @@ class WavePlan:
         h = C.c_void_p()
         check(self._L.gams_cuda_wave_plan_create(ctx.handle, dev_index, seq_off.size - 1, _p(seq_off), size, step, lag,
                                                  C.byref(h)))
+        ctx._plans.add(self)
         self._h, self._ctx = h, ctx
         self.total_windows = int(self._L.gams_cuda_wave_plan_total_windows(h))
         self.total_bases = int(self._L.gams_cuda_wave_plan_total_bases(h))
@@ -365,6 +370,7 @@ class CountPlan:
         iv_off = _arr(iv_off, np.uint64)
         h = C.c_void_p()
         check(self._L.gams_cuda_count_plan_create(ctx.handle, dev_index, iv_off.size - 1, _p(iv_off), C.byref(h)))
+        ctx._plans.add(self)
         self._h, self._ctx = h, ctx
 
     def count(self, stream: int, d_starts, d_stops, d_q_seg, d_q_start, d_q_stop, d_out, grouped=False):
@@ -412,6 +418,7 @@ class CountWindowsPlan:
         h = C.c_void_p()
         check(self._L.gams_cuda_cwin_plan_create(ctx.handle, dev_index, chr_start.size, _p(chr_start), _p(win_off), size, step,
                                                  _p(iv_off), C.byref(h)))
+        ctx._plans.add(self)
         self._h, self._ctx = h, ctx
 
     @property
@@ -498,8 +505,8 @@ def parse_ranges(ctx: Context, text: bytes, chr_names):
     return out
 
 
-def locate_count_text(ctx: Context, text: bytes, chr_names, ctg_start, ctg_stop, chr_off, starts, stops, iv_off):
-    """`gams locate --count -f file`, text in → (output text, n_lines, n_printed, n_handed_back)."""
+def locate_count_text(ctx: Context, text: bytes, chr_names, ctg_start, ctg_stop, chr_off, starts, stops, iv_off, want_lines=False):
+    """`gams locate --count -f file`, text in → (output text, n_lines, n_printed, n_handed_back[, input line of every printed line])."""
     t = np.frombuffer(text, dtype=np.uint8)
     names = [n.encode() if isinstance(n, str) else n for n in chr_names]
     noff = np.zeros(len(names) + 1, dtype=np.uint32)
@@ -508,12 +515,21 @@ def locate_count_text(ctx: Context, text: bytes, chr_names, ctg_start, ctg_stop,
     ctg_start, ctg_stop, chr_off = _arr(ctg_start, np.uint32), _arr(ctg_stop, np.uint32), _arr(chr_off, np.uint64)
     starts, stops, iv_off = _arr(starts, np.uint32), _arr(stops, np.uint32), _arr(iv_off, np.uint64)
     L = load()
-    out, n, nl, npr, nb = C.c_void_p(), C.c_size_t(), C.c_uint64(), C.c_uint64(), C.c_uint64()
-    check(L.gams_cuda_locate_count_text(ctx.handle, _p(t), t.size, len(names), _p(ncat), _p(noff), _p(ctg_start), _p(ctg_stop),
-                                        _p(chr_off), _p(starts), _p(stops), _p(iv_off), C.byref(out), C.byref(n), C.byref(nl),
-                                        C.byref(npr), C.byref(nb)))
+    out, n, nl, npr, nb, ol = C.c_void_p(), C.c_size_t(), C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_void_p()
+    common = (ctx.handle, _p(t), t.size, len(names), _p(ncat), _p(noff), _p(ctg_start), _p(ctg_stop), _p(chr_off), _p(starts), _p(stops),
+              _p(iv_off), C.byref(out), C.byref(n))
+    if want_lines:
+        check(L.gams_cuda_locate_count_lines(*common, C.byref(ol), C.byref(nl), C.byref(npr), C.byref(nb)))
+    else:
+        check(L.gams_cuda_locate_count_text(*common, C.byref(nl), C.byref(npr), C.byref(nb)))
     try:
         s = C.string_at(out, n.value) if out.value else b""
+        lines = np.ctypeslib.as_array(C.cast(ol, C.POINTER(C.c_uint64)), shape=(int(npr.value),)).copy() if (want_lines and ol.value and npr.value) \
+            else np.zeros(0, np.uint64)
     finally:
         L.gams_cuda_free(out)
+        if ol.value:
+            L.gams_cuda_free(ol)
+    if want_lines:
+        return s, int(nl.value), int(npr.value), int(nb.value), lines
     return s, int(nl.value), int(npr.value), int(nb.value)

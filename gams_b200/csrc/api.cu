@@ -123,6 +123,8 @@ int32_t SeriesLayout::build(const uint64_t *h_off, int64_t n, cudaStream_t st) {
     int32_t rc;
     if ((rc = dev_alloc(cache, reinterpret_cast<void **>(&d_off), sizeof(uint64_t) * (size_t)(n + 1)))) return rc;
     CUDA_TRY(cudaMemcpyAsync(d_off, rel.data(), sizeof(uint64_t) * (size_t)(n + 1), cudaMemcpyHostToDevice, st));
+    if ((rc = dev_alloc(cache, reinterpret_cast<void **>(&d_nonfinite), sizeof(int) * (size_t)std::max<int64_t>(n, 1)))) return rc;
+    CUDA_TRY(cudaMemsetAsync(d_nonfinite, 0, sizeof(int) * (size_t)std::max<int64_t>(n, 1), st));
     if (n_ztiles) {
         if ((rc = dev_alloc(cache, reinterpret_cast<void **>(&d_ztiles), sizeof(TileDesc) * n_ztiles))) return rc;
         CUDA_TRY(cudaMemcpyAsync(d_ztiles, zt.data(), sizeof(TileDesc) * n_ztiles, cudaMemcpyHostToDevice, st));
@@ -134,6 +136,8 @@ int32_t SeriesLayout::build(const uint64_t *h_off, int64_t n, cudaStream_t st) {
 void SeriesLayout::release() {
     dev_free(cache, d_off, sizeof(uint64_t) * (size_t)(n_series + 1));
     dev_free(cache, d_ztiles, sizeof(TileDesc) * n_ztiles);
+    dev_free(cache, d_nonfinite, sizeof(int) * (size_t)std::max<int64_t>(n_series, 1));
+    d_nonfinite = nullptr;
     d_off = nullptr;
     d_ztiles = nullptr;
 }
@@ -219,7 +223,9 @@ GAMS_API int32_t gams_cuda_create(const int32_t *device_ids, int32_t n_dev, gams
             ids.push_back(device_ids[i]);
         }
     std::unique_ptr<gams_cuda_ctx> ctx(new gams_cuda_ctx);
-    for (int id : ids) {
+    // every device is pushed into the context BEFORE its resources are created, so that a failure half way releases what
+    // the earlier devices (and this one) already own through gams_cuda_destroy
+    auto init_device = [&](int id) -> int32_t {
         cudaDeviceProp prop;
         CUDA_TRY(cudaGetDeviceProperties(&prop, id));
         if (prop.major < 10) {
@@ -228,16 +234,26 @@ GAMS_API int32_t gams_cuda_create(const int32_t *device_ids, int32_t n_dev, gams
             return GAMS_CUDA_ENODEV;
         }
         DeviceGuard g(id);
-        PerDevice pd;
+        ctx->devs.emplace_back();
+        PerDevice &pd = ctx->devs.back();
         pd.device = id;
+        pd.cache = new BlockCache;
+        for (auto &b : pd.scratch) b.cache = pd.cache;
         CUDA_TRY(cudaStreamCreateWithFlags(&pd.stream, cudaStreamNonBlocking));
         CUDA_TRY(cudaStreamCreateWithFlags(&pd.copy_in, cudaStreamNonBlocking));
         CUDA_TRY(cudaStreamCreateWithFlags(&pd.copy_out, cudaStreamNonBlocking));
         CUDA_TRY(cudaMalloc(&pd.d_zstats, 2 * sizeof(unsigned long long)));
         CUDA_TRY(cudaMemset(pd.d_zstats, 0, 2 * sizeof(unsigned long long)));
-        pd.cache = new BlockCache;
-        for (auto &b : pd.scratch) b.cache = pd.cache;
-        ctx->devs.push_back(pd);
+        return GAMS_CUDA_OK;
+    };
+    for (int id : ids) {
+        const int32_t rc = init_device(id);
+        if (rc) {
+            const std::string msg(g_err);
+            gams_cuda_destroy(ctx.release());
+            set_error("%s", msg.c_str());
+            return rc;
+        }
     }
     if (const char *m = getenv("GAMS_CUDA_ZSCORE_MODE")) ctx->zscore_mode = atoi(m);
     *out = ctx.release();
@@ -269,16 +285,16 @@ GAMS_API void gams_cuda_destroy(gams_cuda_ctx *ctx) {
     if (!ctx) return;
     for (auto &pd : ctx->devs) {
         DeviceGuard g(pd.device);
-        cudaStreamSynchronize(pd.stream);
+        if (pd.stream) cudaStreamSynchronize(pd.stream);
         for (auto &b : pd.scratch) b.release();
         if (pd.cache) {
             pd.cache->clear();
             delete pd.cache;
         }
         if (pd.d_zstats) cudaFree(pd.d_zstats);
-        cudaStreamDestroy(pd.stream);
-        cudaStreamDestroy(pd.copy_in);
-        cudaStreamDestroy(pd.copy_out);
+        if (pd.stream) cudaStreamDestroy(pd.stream);       // (a context whose creation failed half way has NULL handles)
+        if (pd.copy_in) cudaStreamDestroy(pd.copy_in);
+        if (pd.copy_out) cudaStreamDestroy(pd.copy_out);
     }
     delete ctx;
 }
@@ -486,7 +502,7 @@ GAMS_API int32_t gams_cuda_wave_dev(gams_cuda_wave_plan *p, void *stream, const 
     int32_t rc = launch_gc_windows(p, (cudaStream_t)stream, d_seq, d_gc_count, d_gc, &p->launches, 0, p->n_ctg);
     if (rc) return rc;
     return launch_zscore(p->win, (cudaStream_t)stream, d_gc, p->lag, threshold, influence, d_filtered, d_signal,
-                         &p->launches, p->ctx->zscore_mode, p->ctx->devs[p->dev_index].d_zstats, 0, p->n_ctg);
+                         &p->launches, p->ctx->zscore_mode, p->ctx->devs[p->dev_index].d_zstats, 0, p->n_ctg, true);
 }
 
 GAMS_API int32_t gams_cuda_wave_plan_fused(const gams_cuda_wave_plan *p, float threshold, float influence) {
@@ -628,7 +644,7 @@ static int32_t wave_on_device(gams_cuda_ctx *ctx, int d, int64_t c0, int64_t c1,
         } else {
             if ((rc = launch_gc_windows(plan, pd.stream, d_seq, d_cnt, d_gc, &plan->launches, a, b))) return rc;
             if (want_sig && !deferred && (rc = launch_zscore(plan->win, pd.stream, d_gc, lag, threshold, influence, d_filt, d_sig,
-                                                             &plan->launches, ctx->zscore_mode, pd.d_zstats, a, b)))
+                                                             &plan->launches, ctx->zscore_mode, pd.d_zstats, a, b, true)))
                 return rc;
         }
         CUDA_TRY(cudaEventRecord(ev_k[k], pd.stream));
@@ -644,7 +660,7 @@ static int32_t wave_on_device(gams_cuda_ctx *ctx, int d, int64_t c0, int64_t c1,
             const uint64_t gw0 = plan->h_win_off[ga];
             if (fused_walk) rc = launch_zscore_skip(plan->win, pd.stream, d_gc, lag, threshold, influence, d_sig, &plan->launches, ga, b);
             else rc = launch_zscore(plan->win, pd.stream, d_gc, lag, threshold, influence, d_filt, d_sig, &plan->launches,
-                                    ctx->zscore_mode, pd.d_zstats, ga, b);
+                                    ctx->zscore_mode, pd.d_zstats, ga, b, true);
             if (rc) return rc;
             if (signal && w1 > gw0) {
                 CUDA_TRY(cudaEventRecord(ev_k[k], pd.stream));   // re-recorded behind the group's z-score kernel

@@ -153,6 +153,7 @@ struct SeriesLayout {
     uint64_t *d_off = nullptr;       // n_series+1
     TileDesc *d_ztiles = nullptr;    // z-score tiles
     uint64_t n_ztiles = 0;
+    int *d_nonfinite = nullptr;      // n_series flags: the series holds Inf / NaN (set by zscore_indep_kernel, see launch_zscore)
     std::vector<uint64_t> h_off;       // n_series+1 (relative to the first series)
     std::vector<uint64_t> h_ztile_off; // n_series+1: first z-score tile of each series
     BlockCache *cache = nullptr;
@@ -220,7 +221,7 @@ struct gams_cuda_count_plan {
     int mode = 0;                    // 0 default (partitioned / ranked / staged), 1 plain binary search, 2 ranked only (GAMS_CUDA_COUNT_MODE)
     // partitioned path for queries in arbitrary order (overlap_part.cu): bucket tables in tmp[7], valid for the compact index
     bool part_valid = false;
-    int part_nbkt = 0, part_sb = 0;
+    int part_nbkt = 0, part_bshift = 0;
     uint64_t launches = 0;
 };
 
@@ -231,7 +232,8 @@ int32_t launch_gc_windows(const gams_cuda_wave_plan *p, cudaStream_t st, const u
                           uint32_t *d_cnt, float *d_gc, uint64_t *launches, int64_t c0, int64_t c1);
 int32_t launch_zscore(const SeriesLayout &L, cudaStream_t st, const float *d_x, uint64_t lag, float threshold,
                       float influence, float *d_filtered, int8_t *d_signal, uint64_t *launches, int mode,
-                      unsigned long long *d_stats, int64_t s0, int64_t s1);
+                      unsigned long long *d_stats, int64_t s0, int64_t s1, bool gc_values = false);
+// gc_values: d_x was produced by the GC kernels of this library (fractions in [0, 1]: no Inf / NaN fix-up pass needed)
 int32_t launch_count_overlaps(gams_cuda_count_plan *p, cudaStream_t st, const uint32_t *d_starts,
                               const uint32_t *d_stops, int64_t n_q, const int32_t *d_q_seg,
                               const uint32_t *d_q_start, const uint32_t *d_q_stop, int32_t grouped,

@@ -423,8 +423,11 @@ FusedConst make_fused_const(int32_t size, uint64_t lag, float threshold) {
 // The fused kernel covers the default statistics only: influence exactly 1 (filtered == data, stat.rs:42,47),
 // a finite non-negative threshold (the certificate squares it) and an eligible geometry.
 bool wave_fused_ok(const gams_cuda_wave_plan *p, float threshold, float influence) {
-    return p->fused_wt > 0 && influence == 1.0f && threshold >= 0.0f && threshold < 1.0e9f && p->ctx->zscore_mode == 0 &&
-           p->win.min_len >= p->lag;
+    // thresholds in [2^-16, 2^30]: k = thr^2 n / (n - 1) and every product with it stay normal f32 numbers, as the error
+    // model of the certificate assumes (GC fractions are in [0, 1]: magnitudes need no guard here); outside that range
+    // Kernel A + Kernel B replay every window exactly
+    return p->fused_wt > 0 && influence == 1.0f && threshold >= 1.52587890625e-5f && threshold <= 1073741824.0f &&
+           p->ctx->zscore_mode == 0 && p->win.min_len >= p->lag;
 }
 
 // Output windows per fused tile, or 0 when the fused path does not apply to this geometry.

@@ -83,7 +83,9 @@ __device__ __forceinline__ uint32_t e8_lower_bound(const SegCompact &P, const ui
     const uint32_t cum = e.x & 0x7FFFu, rr = rem * 0x01010101u;
     // byte < rem <=> bit 7 of (byte | 0x80) - rem is clear; the two cum bytes are forced to 0xFF, empty slots are 0xFF
     uint32_t cnt = cum + (uint32_t)__popc(~((e.x | 0x8080FFFFu) - rr) & 0x80808080u) + (uint32_t)__popc(~((e.y | 0x80808080u) - rr) & 0x80808080u);
-    if (e.x & 0x8000u) {   // rare: more than six elements in the bucket; the seventh and later ones are compared in the raw array
+    // rare: more than six elements in the bucket; the entry holds the six smallest, so the seventh and later ones (compared in
+    // the raw array) matter only for a key beyond the sixth
+    if ((e.x & 0x8000u) && rem > (e.y >> 24)) {
         const uint32_t nxt = ent[b + 1].x & 0x7FFFu;
 #pragma unroll 1
         for (uint32_t i = cum + 6u; i < nxt; ++i) cnt += (__ldg(a + i) < key) ? 1u : 0u;

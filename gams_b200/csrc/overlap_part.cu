@@ -1,357 +1,340 @@
 // overlap_part.cu — Kernel C for queries in ARBITRARY order (the order `gams locate --count -f` walks its input file in,
-// src/cmd_gams/locate.rs:111-141): coarse partition -> lookup through L2 -> un-permute.
+// src/cmd_gams/locate.rs:111-141): sort spans by index bucket -> lookups through L2 -> un-permute spans.
 //
 // Why.  count = lower_bound(starts_seg, stop) - lower_bound(stops_seg, start + 1) (utils.rs:24-36 -> Lapper::count) touches two
 // random places of an index of 10^8 intervals per query.  Answered in input order every touch is a DRAM access, and DRAM hands
 // over 128 bytes for each of them: 25.7 GB of traffic for 2.4 GB of algorithmic bytes (profiles/README.md, r1r).  Here every
-// random access is kept inside L2 instead, and DRAM only sees streams:
-//   P0 part_hist_kernel      q_seg -> per (span, bucket) counts; a bucket is a contiguous range of segments whose compact index
-//                            (overlap_index.cuh) is a few MB; a span is the contiguous run of queries one CTA owns
-//   P1 part_scan_kernel      exclusive scan of the counts in (bucket, span) order = where every (span, bucket) run goes
-//   P2 part_scatter_kernel   queries -> (start, stop, tag) records grouped by bucket; each CTA sorts a sub-tile in shared memory
-//                            first, so a bucket receives runs of consecutive records.  tag = position inside the region << sb |
-//                            segment inside the bucket.
-//   P3 part_lookup_kernel    records in bucket order: the compact forms of ~2 buckets are live in L2 at any time; counts are
-//                            written next to the records, again as a stream
-//   P4 part_unpermute_kernel region by region (a region = 2^rb consecutive queries, its slice of out[] is <= 16 MB and stays
-//                            in L2): the counts of the region's records — a contiguous piece of every bucket, because spans
-//                            never straddle regions — are stored to out[region base + position].
-// DRAM traffic: 4 + 12 + 12 + 12 + 4 + 8 + 4 B per query + the compact index once = 5.6 GB + 0.4 GB for C5.
+// random access stays inside L2 or shared memory, and DRAM only sees streams:
+//   S1 part_sort_kernel       one CTA per span of PT_SPAN consecutive queries: counting sort by BUCKET in shared memory (a bucket
+//                             is a contiguous range of segments whose compact index, overlap_index.cuh, is a few MB), written
+//                             back as (start, stop, tag) records in the span's own slot of the record arrays — linear stores —
+//                             with the span's bucket counts and bases.  tag = position inside the span << sb | segment inside
+//                             the bucket.
+//   S2 part_lookup_kernel     run by run in BUCKET-MAJOR order (run = the records of one bucket in one span, contiguous): at any
+//                             time the CTAs in flight work on one or two buckets, whose compact forms stay in L2; the count goes
+//                             next to its record.
+//   S3 part_unpermute_kernel  one CTA per span: counts to their original positions through shared memory, linear stores to out[].
+// DRAM traffic: 12 + 12 | 12 + 4 | 8 + 4 = 52 B per query + the compact index once: 5.2 GB + 0.4 GB for C5 (10^8 x 10^8).
+// There is no histogram pass and no global scan: a run is found from (bucket, span) alone.
 // Queries whose segment is outside the index go to bucket 0 with the segment field all ones and count 0 (utils.rs:29-32).
 #include "common.cuh"
 #include "overlap_index.cuh"
 
 namespace gams {
 
-constexpr int PT_MAX_B = 256;         // buckets
+constexpr int PT_MAX_B = 256;                 // buckets
 constexpr int PT_THREADS = 512;
-constexpr int PT_PER = 8;             // queries per thread and sub-tile
-constexpr int PT_SUB = PT_THREADS * PT_PER;   // queries sorted in shared memory at a time
-constexpr int PT_MAX_SPANS = 4096;
-constexpr size_t PT_SCATTER_SMEM = (size_t)PT_SUB * 13;
+constexpr int PT_PER = 16;                    // queries per thread
+constexpr int PT_SPAN_SHIFT = 13;
+constexpr int PT_SPAN = 1 << PT_SPAN_SHIFT;   // queries per span = PT_THREADS * PT_PER
+static_assert(PT_SPAN == PT_THREADS * PT_PER, "span geometry");
+constexpr size_t PT_SORT_SMEM = (size_t)PT_SPAN * 12;
 
-// 32 bytes per segment: what one lookup needs, in one load
-struct alignas(32) SegLite {
+// 16 bytes per segment: what one E8 lookup needs, in one load
+struct alignas(16) SegLite {
     uint64_t cofs;    // byte offset of the segment's compact form in the compact buffer
-    uint64_t off;     // first interval of the segment in starts[] / stops[]
-    uint32_t lo, nb, n;
-    uint32_t kind;    // l | fmt << 8 (E8) ; PT_KIND_GENERAL: read the two SegCompact records ; PT_KIND_EMPTY
+    uint32_t lo;      // first element of the segment's starts[]
+    uint32_t nbl;     // E8 form: buckets | l << 16 ; PT_GENERAL: read the two SegCompact records ; PT_EMPTY: no intervals
 };
-constexpr uint32_t PT_KIND_GENERAL = 0xFFFFFFFEu, PT_KIND_EMPTY = 0xFFFFFFFFu;
+constexpr uint32_t PT_GENERAL = 0xFFFFFFFEu, PT_EMPTY = 0xFFFFFFFFu;
 
 __global__ void __launch_bounds__(256)
-part_lite_kernel(const SegCompact *__restrict__ par, const uint64_t *__restrict__ cofs, const uint64_t *__restrict__ iv_off,
-                 int64_t n_seg, SegLite *__restrict__ lite) {
+part_lite_kernel(const SegCompact *__restrict__ par, const uint64_t *__restrict__ cofs, int64_t n_seg, SegLite *__restrict__ lite) {
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_seg) return;
     const SegCompact A = par[2 * s], B = par[2 * s + 1];
     SegLite t;
     t.cofs = cofs[s];
-    t.off = iv_off[s];
-    t.lo = A.lo, t.nb = A.nb, t.n = A.n;
-    if (A.n == 0) t.kind = PT_KIND_EMPTY;
-    else if (A.fmt == 1u && B.l == ST_ALIAS && A.l != ST_PLAIN) t.kind = A.l | (1u << 8);
-    else t.kind = PT_KIND_GENERAL;
+    t.lo = A.lo;
+    if (A.n == 0) t.nbl = PT_EMPTY;
+    else if (A.fmt == 1u && B.l == ST_ALIAS && A.l != ST_PLAIN) t.nbl = A.nb | (A.l << 16);
+    else t.nbl = PT_GENERAL;
     lite[s] = t;
 }
 
 struct PartGeom {
-    int32_t n_bkt;        // buckets
-    int32_t sb;           // bits of the segment-inside-bucket field of a tag
-    int32_t rb;           // log2 of the region size
-    int32_t span_shift;   // log2 of the span size (spans per region = 1 << (rb - span_shift))
-    int32_t n_span;       // spans (n_region << (rb - span_shift))
-    int32_t n_region;
+    int32_t n_bkt;        // buckets: bucket of segment s = s >> bshift
+    int32_t bshift;
+    int32_t sb;           // bits of the segment-inside-bucket field of a tag = bshift + 1 (all ones: segment outside the index)
+    int32_t n_span;       // spans
 };
 
-__device__ __forceinline__ uint32_t bucket_of(int32_t seg, int64_t n_seg, const uint8_t *__restrict__ seg2bkt) {
-    return (seg >= 0 && seg < n_seg) ? (uint32_t)__ldg(seg2bkt + seg) : 0u;
+__device__ __forceinline__ uint32_t ld_stream(const uint32_t *p) {   // read once: do not keep in L1
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint4 ld_stream4(const uint32_t *p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
 }
 
-// P0: one CTA per span
+__device__ __forceinline__ void cp_async4(uint32_t *smem_dst, const uint32_t *gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+
+// S1: one CTA per span
 __global__ void __launch_bounds__(PT_THREADS)
-part_hist_kernel(const int32_t *__restrict__ q_seg, int64_t n_q, int64_t n_seg, const uint8_t *__restrict__ seg2bkt, PartGeom G,
-                 uint32_t *__restrict__ cnt /* [n_bkt][n_span] */) {
-    __shared__ uint32_t hist[PT_MAX_B];
-    for (int b = threadIdx.x; b < PT_MAX_B; b += PT_THREADS) hist[b] = 0;
-    __syncthreads();
-    const int64_t q0 = (int64_t)blockIdx.x << G.span_shift, q1 = min(q0 + ((int64_t)1 << G.span_shift), n_q);
-    for (int64_t q = q0 + threadIdx.x; q < q1; q += (int64_t)PT_THREADS * 4) {
-        int32_t s[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) s[k] = (q + k * PT_THREADS < q1) ? __ldg(q_seg + q + k * PT_THREADS) : 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (q + k * PT_THREADS < q1) atomicAdd(&hist[bucket_of(s[k], n_seg, seg2bkt)], 1u);
-    }
-    __syncthreads();
-    for (int b = threadIdx.x; b < G.n_bkt; b += PT_THREADS) cnt[(size_t)b * G.n_span + blockIdx.x] = hist[b];
-}
-
-// P1: exclusive scan of cnt[0 .. n) in place, total to cnt[n]; one CTA, 4 elements per thread and round
-__global__ void __launch_bounds__(1024)
-part_scan_kernel(uint32_t *__restrict__ cnt, uint32_t n) {
-    __shared__ uint32_t wsum[32];
-    __shared__ uint32_t carry_s;
-    if (threadIdx.x == 0) carry_s = 0;
-    __syncthreads();
-    for (uint32_t base = 0; base < n; base += 4096u) {
-        const uint32_t i = base + threadIdx.x * 4u;
-        uint32_t v[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) v[k] = (i + k < n) ? cnt[i + k] : 0u;
-        const uint32_t tot = v[0] + v[1] + v[2] + v[3];
-        uint32_t inc = tot;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
-            if ((threadIdx.x & 31) >= d) inc += t;
-        }
-        if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = inc;
-        __syncthreads();
-        uint32_t before = carry_s;
-        {
-            const uint32_t w = threadIdx.x >> 5;
-            uint32_t x = (threadIdx.x & 31) < w ? wsum[threadIdx.x & 31] : 0u;
-#pragma unroll
-            for (int d = 16; d; d >>= 1) x += __shfl_xor_sync(0xFFFFFFFFu, x, d);
-            before += x;
-        }
-        uint32_t at = before + inc - tot;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (i + k < n) cnt[i + k] = at;
-            at += v[k];
-        }
-        __syncthreads();
-        if (threadIdx.x == 1023) carry_s = before + inc;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) cnt[n] = carry_s;
-}
-
-// P2: one CTA per span; sub-tiles of PT_SUB queries are grouped by bucket in shared memory and leave as runs
-__global__ void __launch_bounds__(PT_THREADS)
-part_scatter_kernel(const int32_t *__restrict__ q_seg, const uint32_t *__restrict__ q_start, const uint32_t *__restrict__ q_stop,
-                    int64_t n_q, int64_t n_seg, const uint8_t *__restrict__ seg2bkt, const int32_t *__restrict__ bkt_first,
-                    PartGeom G, const uint32_t *__restrict__ off /* scanned cnt */, uint32_t *__restrict__ r_start,
-                    uint32_t *__restrict__ r_stop, uint32_t *__restrict__ r_tag) {
-    __shared__ uint32_t hist[PT_MAX_B], lbase[PT_MAX_B], cursor[PT_MAX_B];
-    __shared__ int32_t first_s[PT_MAX_B];
+part_sort_kernel(const int32_t *__restrict__ q_seg, const uint32_t *__restrict__ q_start, const uint32_t *__restrict__ q_stop,
+                 int64_t n_q, int64_t n_seg, PartGeom G, uint16_t *__restrict__ run_cnt /* [n_bkt][n_span] */,
+                 uint16_t *__restrict__ run_base,
+                 uint32_t *__restrict__ r_start, uint32_t *__restrict__ r_stop, uint32_t *__restrict__ r_tag) {
+    __shared__ uint32_t hist[PT_MAX_B], lbase[PT_MAX_B];
     __shared__ uint32_t wtot[PT_MAX_B / 32];
-    extern __shared__ __align__(16) uint8_t pt_smem[];   // PT_SCATTER_SMEM bytes
-    uint32_t *s_start = reinterpret_cast<uint32_t *>(pt_smem), *s_stop = s_start + PT_SUB, *s_tag = s_stop + PT_SUB;
-    uint8_t *s_b = reinterpret_cast<uint8_t *>(s_tag + PT_SUB);
+    extern __shared__ __align__(16) uint8_t pt_smem[];   // PT_SORT_SMEM bytes
+    uint32_t *s_start = reinterpret_cast<uint32_t *>(pt_smem), *s_stop = s_start + PT_SPAN, *s_tag = s_stop + PT_SPAN;
     const int tid = threadIdx.x;
-    for (int b = tid; b < PT_MAX_B; b += PT_THREADS) {
-        hist[b] = 0;
-        cursor[b] = b < G.n_bkt ? off[(size_t)b * G.n_span + blockIdx.x] : 0u;
-        first_s[b] = b < G.n_bkt ? bkt_first[b] : 0;
-    }
+    for (int b = tid; b < PT_MAX_B; b += PT_THREADS) hist[b] = 0;
     __syncthreads();
-    const int64_t q0 = (int64_t)blockIdx.x << G.span_shift, q1 = min(q0 + ((int64_t)1 << G.span_shift), n_q);
-    const uint32_t region_mask = (1u << G.rb) - 1u, sent = (1u << G.sb) - 1u;
-    for (int64_t base = q0; base < q1; base += PT_SUB) {
-        const uint32_t m = (uint32_t)min((int64_t)PT_SUB, q1 - base);
-        int32_t sg[PT_PER];
-        uint32_t qs[PT_PER], qe[PT_PER], bk[PT_PER], rk[PT_PER];
-#pragma unroll
-        for (int k = 0; k < PT_PER; ++k) {
-            const uint32_t i = k * PT_THREADS + tid;
-            if (i < m) {
-                sg[k] = __ldg(q_seg + base + i);
-                qs[k] = __ldg(q_start + base + i);
-                qe[k] = __ldg(q_stop + base + i);
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < PT_PER; ++k) {
-            const uint32_t i = k * PT_THREADS + tid;
-            if (i < m) {
-                bk[k] = bucket_of(sg[k], n_seg, seg2bkt);
-                rk[k] = atomicAdd(&hist[bk[k]], 1u);
-            }
-        }
-        __syncthreads();
-        // exclusive scan of hist over PT_MAX_B = 256 buckets: the first 8 warps
-        if (tid < PT_MAX_B) {
-            const uint32_t h = hist[tid];
-            uint32_t inc = h;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
-                if ((tid & 31) >= d) inc += t;
-            }
-            if ((tid & 31) == 31) wtot[tid >> 5] = inc;
-            lbase[tid] = inc - h;
-        }
-        __syncthreads();
-        if (tid < PT_MAX_B) {
-            uint32_t add = 0;
-            for (int w = 0; w < (tid >> 5); ++w) add += wtot[w];
-            lbase[tid] += add;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < PT_PER; ++k) {
-            const uint32_t i = k * PT_THREADS + tid;
-            if (i < m) {
-                const uint32_t slot = lbase[bk[k]] + rk[k];
-                const bool valid = sg[k] >= 0 && sg[k] < n_seg;
-                const uint32_t local = valid ? (uint32_t)(sg[k] - first_s[bk[k]]) : sent;
-                s_start[slot] = qs[k];
-                s_stop[slot] = qe[k];
-                s_tag[slot] = (((uint32_t)(base + i) & region_mask) << G.sb) | local;
-                s_b[slot] = (uint8_t)bk[k];
-            }
-        }
-        __syncthreads();
-        for (uint32_t slot = tid; slot < m; slot += PT_THREADS) {
-            const uint32_t b = s_b[slot];
-            const uint32_t dst = cursor[b] + (slot - lbase[b]);
-            r_start[dst] = s_start[slot];
-            r_stop[dst] = s_stop[slot];
-            r_tag[dst] = s_tag[slot];
-        }
-        __syncthreads();
-        if (tid < PT_MAX_B) {
-            cursor[tid] += hist[tid];
-            hist[tid] = 0;
-        }
-        __syncthreads();
-    }
-}
-
-// #elements < key of one endpoint array of a general (two-array) segment, compact form in global memory
-__device__ __forceinline__ uint32_t general_lower_bound(const SegCompact &P, const uint32_t *__restrict__ a,
-                                                        const uint8_t *__restrict__ form, uint32_t key) {
-    return staged_lower_bound(P, a, form, key);
-}
-
-// P3: records in bucket order
-constexpr int PL_THREADS = 256;
-constexpr int PL_PER = 4;
-__global__ void __launch_bounds__(PL_THREADS)
-part_lookup_kernel(const uint32_t *__restrict__ starts, const uint32_t *__restrict__ stops, const SegLite *__restrict__ lite,
-                   const SegCompact *__restrict__ par, const uint8_t *__restrict__ cbuf, const int32_t *__restrict__ bkt_first,
-                   PartGeom G, const uint32_t *__restrict__ off, uint32_t n_rec, const uint32_t *__restrict__ r_start,
-                   const uint32_t *__restrict__ r_stop, const uint32_t *__restrict__ r_tag, uint32_t *__restrict__ r_cnt) {
-    __shared__ uint32_t boff[PT_MAX_B + 1];   // first record of every bucket
-    __shared__ int32_t first_s[PT_MAX_B];
-    for (int b = threadIdx.x; b <= G.n_bkt; b += PL_THREADS) boff[b] = off[(size_t)b * G.n_span];
-    for (int b = threadIdx.x; b < G.n_bkt; b += PL_THREADS) first_s[b] = bkt_first[b];
-    __syncthreads();
-    const uint32_t p0 = blockIdx.x * (uint32_t)(PL_THREADS * PL_PER);
-    if (p0 >= n_rec) return;
-    // bucket of the CTA's first record
-    int lo = 0, hi = G.n_bkt;
-    while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (boff[mid] <= p0) lo = mid; else hi = mid;
-    }
-    uint32_t b = (uint32_t)lo;
+    const int64_t base = (int64_t)blockIdx.x << PT_SPAN_SHIFT;
+    const uint32_t m = (uint32_t)min((int64_t)PT_SPAN, n_q - base);
     const uint32_t sent = (1u << G.sb) - 1u;
-    uint32_t qs[PL_PER], qe[PL_PER], tg[PL_PER];
+    uint32_t br[PT_PER], tg[PT_PER];   // bucket << 16 | rank inside the bucket ; tag
+    {
+        int32_t sg[PT_PER];
 #pragma unroll
-    for (int k = 0; k < PL_PER; ++k) {
-        const uint32_t p = p0 + k * PL_THREADS + threadIdx.x;
-        if (p < n_rec) {
-            qs[k] = __ldg(r_start + p);
-            qe[k] = __ldg(r_stop + p);
-            tg[k] = __ldg(r_tag + p);
+        for (int k = 0; k < PT_PER; ++k) {
+            const uint32_t i = k * PT_THREADS + tid;
+            sg[k] = i < m ? __ldg(q_seg + base + i) : -1;
         }
-    }
 #pragma unroll
-    for (int k = 0; k < PL_PER; ++k) {
-        const uint32_t p = p0 + k * PL_THREADS + threadIdx.x;
-        if (p >= n_rec) break;
-        while (p >= boff[b + 1]) ++b;
-        const uint32_t local = tg[k] & sent;
-        uint32_t r = 0;
-        if (local != sent) {
-            const int64_t s = (int64_t)first_s[b] + local;
-            const uint4 *lp = reinterpret_cast<const uint4 *>(lite + s);
-            const uint4 l0 = __ldg(lp), l1 = __ldg(lp + 1);
-            const uint64_t cofs = (uint64_t)l0.x | ((uint64_t)l0.y << 32), ivo = (uint64_t)l0.z | ((uint64_t)l0.w << 32);
-            const uint32_t kind = l1.w;
-            if (kind == PT_KIND_EMPTY) {
-                r = 0;
-            } else if (kind != PT_KIND_GENERAL) {
-                SegCompact A;
-                A.lo = l1.x, A.nb = l1.y, A.n = l1.z, A.l = kind & 0xFFu;
-                const uint2 *ent = reinterpret_cast<const uint2 *>(cbuf + cofs);
-                const uint32_t *a = starts + ivo;
-                const uint32_t last = e8_lower_bound(A, a, ent, qe[k]);
-                const uint32_t first = (qs[k] + 1u) ? e8_lower_bound(A, a, ent, qs[k]) : 0u;
-                r = last - first;
-            } else {
-                const SegCompact A = par[2 * s];
-                SegCompact B = par[2 * s + 1];
-                const bool alias = B.l == ST_ALIAS;
-                const uint8_t *fA = cbuf + cofs, *fB = fA + st_arr_cap_bytes(A.n);
-                const uint32_t last = general_lower_bound(A, starts + ivo, fA, qe[k]);
-                const uint32_t kb = qs[k] + 1u;
-                uint32_t first;
-                if (alias) first = kb ? general_lower_bound(A, starts + ivo, fA, kb - 1u) : 0u;
-                else first = general_lower_bound(B, stops + ivo, fB, kb);
-                r = last - first;
+        for (int k = 0; k < PT_PER; ++k) {
+            const uint32_t i = k * PT_THREADS + tid;
+            if (i < m) {
+                const bool valid = sg[k] >= 0 && sg[k] < n_seg;
+                const uint32_t b = valid ? (uint32_t)sg[k] >> G.bshift : 0u;
+                br[k] = (b << 16) | atomicAdd(&hist[b], 1u);
+                tg[k] = (i << G.sb) | (valid ? ((uint32_t)sg[k] & (sent >> 1)) : sent);
             }
         }
-        r_cnt[p] = r;
     }
-}
-
-// P4: CTA (region r, part j of PU_PARTS): its share of the region's records, bucket after bucket
-constexpr int PU_THREADS = 256;
-__global__ void __launch_bounds__(PU_THREADS)
-part_unpermute_kernel(PartGeom G, int32_t parts, const uint32_t *__restrict__ off, const uint32_t *__restrict__ r_tag,
-                      const uint32_t *__restrict__ r_cnt, int64_t n_q, uint32_t *__restrict__ out) {
-    __shared__ uint32_t sb_begin[PT_MAX_B], vstart[PT_MAX_B + 1];
-    __shared__ uint32_t wtot[PT_MAX_B / 32];
-    const int r = blockIdx.x / parts, j = blockIdx.x % parts;
-    const int spr = 1 << (G.rb - G.span_shift);   // spans per region
-    const int tid = threadIdx.x;
-    if (tid < PT_MAX_B) {
-        uint32_t len = 0;
-        if (tid < G.n_bkt) {
-            const size_t row = (size_t)tid * G.n_span;
-            const uint32_t a = off[row + (size_t)r * spr], e = off[row + (size_t)(r + 1) * spr];   // the row after the last is the next bucket's first
-            sb_begin[tid] = a;
-            len = e - a;
-        }
-        uint32_t inc = len;
+    __syncthreads();
+    if (tid < PT_MAX_B) {   // exclusive scan of hist over the buckets: the first 8 warps
+        const uint32_t h = hist[tid];
+        uint32_t inc = h;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
             if ((tid & 31) >= d) inc += t;
         }
         if ((tid & 31) == 31) wtot[tid >> 5] = inc;
-        vstart[tid + 1] = inc;
+        lbase[tid] = inc - h;
     }
     __syncthreads();
     if (tid < PT_MAX_B) {
         uint32_t add = 0;
         for (int w = 0; w < (tid >> 5); ++w) add += wtot[w];
-        vstart[tid + 1] += add;
-    }
-    if (tid == 0) vstart[0] = 0;
-    __syncthreads();
-    const uint32_t total = vstart[G.n_bkt];
-    const uint32_t v0 = (uint32_t)((uint64_t)total * j / parts), v1 = (uint32_t)((uint64_t)total * (j + 1) / parts);
-    if (v1 <= v0) return;
-    int lo = 0, hi = G.n_bkt;   // bucket holding v0
-    while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (vstart[mid] <= v0) lo = mid; else hi = mid;
-    }
-    uint32_t *__restrict__ o = out + ((int64_t)r << G.rb);
-    for (int b = lo; b < G.n_bkt && vstart[b] < v1; ++b) {
-        const uint32_t a = max(v0, vstart[b]), e = min(v1, vstart[b + 1]);
-        const uint32_t p0 = sb_begin[b] + (a - vstart[b]), cnt = e - a;
-        for (uint32_t i = tid; i < cnt; i += PU_THREADS) {
-            const uint32_t t = __ldg(r_tag + p0 + i), c = __ldg(r_cnt + p0 + i);
-            o[t >> G.sb] = c;
+        const uint32_t lb = lbase[tid] + add;
+        lbase[tid] = lb;
+        if (tid < G.n_bkt) {
+            run_cnt[(size_t)tid * G.n_span + blockIdx.x] = (uint16_t)hist[tid];   // <= PT_SPAN = 8192
+            run_base[(size_t)tid * G.n_span + blockIdx.x] = (uint16_t)lb;
         }
+    }
+    __syncthreads();
+    // start / stop go from global memory straight to their sorted slot: 4-byte cp.async (LDGSTS) to a computed shared
+    // address — no register staging, all 32 copies of a thread in flight at once
+#pragma unroll
+    for (int k = 0; k < PT_PER; ++k) {
+        const uint32_t i = k * PT_THREADS + tid;
+        if (i < m) {
+            const uint32_t slot = lbase[br[k] >> 16] + (br[k] & 0xFFFFu);
+            cp_async4(s_start + slot, q_start + base + i);
+            cp_async4(s_stop + slot, q_stop + base + i);
+            s_tag[slot] = tg[k];
+        }
+    }
+    asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    // the record arrays are 16-byte aligned and padded to whole spans: linear 16-byte stores
+    uint4 *o_start = reinterpret_cast<uint4 *>(r_start + base), *o_stop = reinterpret_cast<uint4 *>(r_stop + base),
+          *o_tag = reinterpret_cast<uint4 *>(r_tag + base);
+    const uint4 *i_start = reinterpret_cast<const uint4 *>(s_start), *i_stop = reinterpret_cast<const uint4 *>(s_stop),
+                *i_tag = reinterpret_cast<const uint4 *>(s_tag);
+    for (uint32_t j = tid; j < (m + 3u) / 4u; j += PT_THREADS) {
+        o_start[j] = i_start[j];
+        o_stop[j] = i_stop[j];
+        o_tag[j] = i_tag[j];
+    }
+}
+
+// S2: CTA (bucket b, chunk of PL_RUNS spans): each warp takes PL_WRUNS consecutive runs of the bucket as one stream of records
+// and handles it 4 records per lane at a time: 12 record loads, then the 8 index loads, then the 4 stores — the latencies
+// of a phase overlap inside the warp.  The bucket's SegLite records sit in shared memory (CACHE) when they fit.
+constexpr int PL_THREADS = 256;
+constexpr int PL_WRUNS = 8;                              // runs per warp
+constexpr int PL_RUNS = PL_WRUNS * PL_THREADS / 32;      // runs (spans) per CTA
+constexpr int PL_U = 4;                                  // records per lane and round
+constexpr int PL_MAX_CACHE_SEGS = 3072;                  // 48 KB of SegLite
+
+struct LookupArgs {
+    const uint32_t *starts, *stops;
+    const uint64_t *iv_off;
+    const SegLite *lite;
+    const SegCompact *par;
+    const uint8_t *cbuf;
+};
+
+// general (two-array) segments and everything else that is not the E8 form: straight through the shared helpers
+__device__ __noinline__ uint32_t lookup_general(const LookupArgs &A_, int64_t s, uint32_t qs, uint32_t qe) {
+    const SegCompact A = A_.par[2 * s], B = A_.par[2 * s + 1];
+    if (A.n == 0) return 0u;
+    const uint64_t cofs = A_.lite[s].cofs, ivo = A_.iv_off[s];
+    const bool alias = B.l == ST_ALIAS;
+    const uint8_t *fA = A_.cbuf + cofs, *fB = fA + st_arr_cap_bytes(A.n);
+    const uint32_t kb = qs + 1u;
+    if (A.fmt == 1u && alias && A.l != ST_PLAIN) {
+        const uint2 *ent = reinterpret_cast<const uint2 *>(fA);
+        const uint32_t last = e8_lower_bound(A, A_.starts + ivo, ent, qe);
+        return last - (kb ? e8_lower_bound(A, A_.starts + ivo, ent, qs) : 0u);
+    }
+    const uint32_t last = staged_lower_bound(A, A_.starts + ivo, fA, qe);
+    uint32_t first;
+    if (alias) first = kb ? staged_lower_bound(A, A_.starts + ivo, fA, kb - 1u) : 0u;
+    else first = staged_lower_bound(B, A_.stops + ivo, fB, kb);
+    return last - first;
+}
+
+// one E8 entry.  A plain read-only load: with L1::no_allocate the sector is not kept in L2 either (measured: every lookup
+// became a DRAM access, 8.0 GB instead of 1.6 GB), and L2 residency of the bucket's entries is the point of this path
+__device__ __forceinline__ uint2 ld_ent(const uint2 *p) { return __ldg(p); }
+
+// E8 lower bound in two halves: which entry, and what the entry says (see e8_lower_bound, overlap_index.cuh)
+__device__ __forceinline__ uint32_t e8_entry_index(uint32_t lo, uint32_t l, uint32_t nb, uint32_t key) {
+    return min((max(key, lo) - lo) >> l, nb);
+}
+__device__ __forceinline__ uint32_t e8_finish(uint32_t lo, uint32_t l, uint2 e, uint32_t key) {   // the six slots of the entry only
+    const uint32_t d = max(key, lo) - lo, rem = d & ((1u << l) - 1u), rr = rem * 0x01010101u;
+    return (e.x & 0x7FFFu) + (uint32_t)__popc(~((e.x | 0x8080FFFFu) - rr) & 0x80808080u) + (uint32_t)__popc(~((e.y | 0x80808080u) - rr) & 0x80808080u);
+}
+
+template <bool CACHE>
+__global__ void __launch_bounds__(PL_THREADS, 3)
+part_lookup_kernel(LookupArgs A, int64_t n_seg, PartGeom G, uint32_t ctas_per_bkt,
+                   const uint16_t *__restrict__ run_cnt, const uint16_t *__restrict__ run_base, const uint32_t *__restrict__ r_start,
+                   const uint32_t *__restrict__ r_stop, const uint32_t *__restrict__ r_tag, uint32_t *__restrict__ r_cnt) {
+    extern __shared__ __align__(32) uint8_t pl_smem[];
+    const uint32_t b = blockIdx.x / ctas_per_bkt, chunk = blockIdx.x - b * ctas_per_bkt;
+    const int64_t s0 = (int64_t)b << G.bshift;
+    const SegLite *lite = A.lite + s0;
+    if (CACHE) {
+        const uint32_t ns = (uint32_t)min((int64_t)1 << G.bshift, n_seg - s0);
+        const uint4 *src = reinterpret_cast<const uint4 *>(lite);
+        uint4 *dst = reinterpret_cast<uint4 *>(pl_smem);
+        for (uint32_t i = threadIdx.x; i < ns; i += PL_THREADS) dst[i] = __ldg(src + i);
+        __syncthreads();
+        lite = reinterpret_cast<const SegLite *>(pl_smem);
+    }
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t g0 = chunk * PL_RUNS + warp * PL_WRUNS;
+    if (g0 >= (uint32_t)G.n_span) return;
+    // the warp's runs: lane j < PL_WRUNS holds run g0 + j
+    uint32_t c = 0, pb = 0;
+    if (lane < PL_WRUNS && g0 + lane < (uint32_t)G.n_span) {
+        const size_t f = (size_t)b * G.n_span + g0 + lane;
+        c = __ldg(run_cnt + f);
+        pb = ((g0 + lane) << PT_SPAN_SHIFT) + __ldg(run_base + f);
+    }
+    uint32_t inc = c;
+#pragma unroll
+    for (int d = 1; d < PL_WRUNS; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+        if (lane >= (uint32_t)d) inc += t;
+    }
+    const uint32_t total = __shfl_sync(0xFFFFFFFFu, inc, PL_WRUNS - 1);
+    uint32_t pre[PL_WRUNS], phys[PL_WRUNS];   // first record of run j in the warp's stream; where run j starts in the record arrays
+#pragma unroll
+    for (int j = 0; j < PL_WRUNS; ++j) {
+        pre[j] = __shfl_sync(0xFFFFFFFFu, inc - c, j);
+        phys[j] = __shfl_sync(0xFFFFFFFFu, pb, j) - pre[j];   // record v of run j sits at phys[j] + v
+    }
+    const uint32_t sent = (1u << G.sb) - 1u;
+    for (uint32_t v0 = 0; v0 < total; v0 += PL_U * 32) {
+        uint32_t p[PL_U], qs[PL_U], qe[PL_U], loc[PL_U];
+#pragma unroll
+        for (int k = 0; k < PL_U; ++k) {
+            const uint32_t v = v0 + k * 32 + lane;
+            uint32_t ph = phys[0];
+#pragma unroll
+            for (int j = 1; j < PL_WRUNS; ++j) ph = v >= pre[j] ? phys[j] : ph;
+            p[k] = ph + v;
+            loc[k] = sent;
+            if (v < total) {
+                qs[k] = ld_stream(r_start + p[k]);
+                qe[k] = ld_stream(r_stop + p[k]);
+                loc[k] = ld_stream(r_tag + p[k]) & sent;
+            }
+        }
+        uint2 eh[PL_U], el[PL_U];
+        uint32_t lo[PL_U], nbl[PL_U];
+#pragma unroll
+        for (int k = 0; k < PL_U; ++k) {
+            nbl[k] = PT_EMPTY;
+            if (loc[k] != sent) {
+                const uint4 t = *reinterpret_cast<const uint4 *>(lite + loc[k]);   // cofs | lo | nbl
+                lo[k] = t.z, nbl[k] = t.w;
+                if (nbl[k] < PT_GENERAL) {
+                    const uint2 *ent = reinterpret_cast<const uint2 *>(A.cbuf + ((uint64_t)t.x | ((uint64_t)t.y << 32)));
+                    eh[k] = ld_ent(ent + e8_entry_index(lo[k], nbl[k] >> 16, nbl[k] & 0xFFFFu, qe[k]));
+                    el[k] = ld_ent(ent + e8_entry_index(lo[k], nbl[k] >> 16, nbl[k] & 0xFFFFu, qs[k]));
+                }
+            }
+        }
+        uint32_t res[PL_U];
+        uint32_t slow = 0;   // bit k: record k needs the raw array (a crowded bucket) or is not in the E8 form
+#pragma unroll
+        for (int k = 0; k < PL_U; ++k) {
+            res[k] = 0;
+            if (nbl[k] < PT_GENERAL) {
+                const uint32_t l = nbl[k] >> 16;
+                // a bucket with more than six elements (flag) keeps its six smallest in the entry: they decide unless the key is
+                // beyond the sixth
+                const uint32_t mask = (1u << l) - 1u;
+                const uint32_t rem_h = (max(qe[k], lo[k]) - lo[k]) & mask, rem_l = (max(qs[k], lo[k]) - lo[k]) & mask;
+                const bool ov = ((eh[k].x & 0x8000u) && rem_h > (eh[k].y >> 24)) || ((qs[k] + 1u) && (el[k].x & 0x8000u) && rem_l > (el[k].y >> 24));
+                const uint32_t last = e8_finish(lo[k], l, eh[k], qe[k]);
+                const uint32_t first = (qs[k] + 1u) ? e8_finish(lo[k], l, el[k], qs[k]) : 0u;
+                res[k] = last - first;
+                slow |= ov ? (1u << k) : 0u;
+            } else if (nbl[k] == PT_GENERAL) {
+                slow |= 1u << k;
+            }
+        }
+        if (__any_sync(0xFFFFFFFFu, slow != 0)) {   // once per round, not once per record
+#pragma unroll
+            for (int k = 0; k < PL_U; ++k)
+                if (slow & (1u << k)) res[k] = lookup_general(A, s0 + loc[k], qs[k], qe[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < PL_U; ++k)
+            if (v0 + k * 32 + lane < total) r_cnt[p[k]] = res[k];
+    }
+}
+
+// S3: one CTA per span
+constexpr int PU_THREADS = 512;
+__global__ void __launch_bounds__(PU_THREADS)
+part_unpermute_kernel(PartGeom G, const uint32_t *__restrict__ r_tag, const uint32_t *__restrict__ r_cnt, int64_t n_q,
+                      uint32_t *__restrict__ out) {
+    __shared__ __align__(16) uint32_t s_out[PT_SPAN];
+    const int64_t base = (int64_t)blockIdx.x << PT_SPAN_SHIFT;
+    const uint32_t m = (uint32_t)min((int64_t)PT_SPAN, n_q - base);
+    for (uint32_t j = threadIdx.x; j < (m + 3u) / 4u; j += PU_THREADS) {
+        const uint4 t = ld_stream4(r_tag + base + 4 * j), c = ld_stream4(r_cnt + base + 4 * j);
+        const uint32_t k = 4u * j;
+        s_out[t.x >> G.sb] = c.x;                       // (positions of the padding past m are >= m: never read below, but
+        if (k + 1 < m) s_out[t.y >> G.sb] = c.y;        //  their tags are stale, so they are not stored at all)
+        if (k + 2 < m) s_out[t.z >> G.sb] = c.z;
+        if (k + 3 < m) s_out[t.w >> G.sb] = c.w;
+    }
+    __syncthreads();
+    uint32_t *o = out + base;
+    if ((reinterpret_cast<uintptr_t>(o) & 15u) == 0) {
+        for (uint32_t j = threadIdx.x; j < m / 4u; j += PU_THREADS) reinterpret_cast<uint4 *>(o)[j] = reinterpret_cast<const uint4 *>(s_out)[j];
+        for (uint32_t j = (m & ~3u) + threadIdx.x; j < m; j += PU_THREADS) o[j] = s_out[j];
+    } else {
+        for (uint32_t j = threadIdx.x; j < m; j += PU_THREADS) o[j] = s_out[j];
     }
 }
 
@@ -361,8 +344,9 @@ static int32_t env_int(const char *name, int32_t dflt) {
     return v ? atoi(v) : dflt;
 }
 
-// Buckets: contiguous segment ranges of about `target` bytes of compact index each (at most PT_MAX_B of them).
-static void plan_buckets(gams_cuda_count_plan *p, std::vector<uint8_t> &seg2bkt, std::vector<int32_t> &first, int &sb) {
+// Buckets: 2^bshift consecutive segments each, at most PT_MAX_B of them, as large as the target of compact index bytes per
+// bucket allows (a bucket is what has to stay in L2 while its queries are answered).
+static void plan_buckets(const gams_cuda_count_plan *p, int &n_bkt, int &bshift) {
     const int64_t n_seg = p->n_seg;
     std::vector<uint64_t> w((size_t)n_seg + 1, 0);
     for (int64_t s = 0; s < n_seg; ++s) {
@@ -371,22 +355,15 @@ static void plan_buckets(gams_cuda_count_plan *p, std::vector<uint8_t> &seg2bkt,
         w[s + 1] = w[s] + (form ? form : 8 * n) + 64;
     }
     const uint64_t target = (uint64_t)std::max(1, env_int("GAMS_CUDA_PART_MB", 12)) << 20;
-    int n_bkt = (int)std::min<uint64_t>(PT_MAX_B, std::max<uint64_t>(1, (w[n_seg] + target - 1) / target));
-    n_bkt = (int)std::min<int64_t>(n_bkt, std::max<int64_t>(1, n_seg));
-    first.assign((size_t)n_bkt + 1, 0);
-    seg2bkt.assign((size_t)std::max<int64_t>(n_seg, 1), 0);
-    int64_t s = 0;
-    uint64_t max_local = 1;
-    for (int b = 0; b < n_bkt; ++b) {
-        first[b] = (int32_t)s;
-        const uint64_t lim = w[n_seg] * (uint64_t)(b + 1) / (uint64_t)n_bkt;
-        const int64_t s_begin = s;
-        while (s < n_seg && (b == n_bkt - 1 || w[s + 1] <= lim || s == s_begin)) seg2bkt[s++] = (uint8_t)b;
-        max_local = std::max<uint64_t>(max_local, (uint64_t)(s - s_begin));
-    }
-    first[n_bkt] = (int32_t)n_seg;
-    sb = 1;
-    while ((1ull << sb) <= max_local) ++sb;
+    auto heaviest = [&](int sh) {
+        uint64_t mx = 0;
+        for (int64_t s = 0; s < n_seg; s += (int64_t)1 << sh) mx = std::max(mx, w[std::min<int64_t>(n_seg, s + ((int64_t)1 << sh))] - w[s]);
+        return mx;
+    };
+    bshift = 0;
+    while ((((int64_t)std::max<int64_t>(n_seg, 1) - 1) >> bshift) + 1 > PT_MAX_B) ++bshift;
+    while ((((int64_t)std::max<int64_t>(n_seg, 1) - 1) >> bshift) + 1 > 1 && heaviest(bshift + 1) <= target) ++bshift;
+    n_bkt = (int)(((std::max<int64_t>(n_seg, 1) - 1) >> bshift) + 1);
 }
 
 bool count_part_eligible(const gams_cuda_count_plan *p, int64_t n_q) {
@@ -394,7 +371,8 @@ bool count_part_eligible(const gams_cuda_count_plan *p, int64_t n_q) {
     return p->mode == 0 && n_q >= min_q && n_q < (1ll << 31) && p->n_seg > 0 && p->total_iv > 0;
 }
 
-// tmp[6]: records (start, stop, tag, cnt: 16 B per query); tmp[7]: seg2bkt | bkt_first | SegLite table; tmp[8]: counts / offsets
+// tmp[6]: records (start, stop, tag, cnt: 16 B per query, whole spans); tmp[7]: SegLite table;
+// tmp[8]: run counts and bases (2 x u16 per (bucket, span))
 int32_t launch_count_overlaps_part(gams_cuda_count_plan *p, cudaStream_t st, const uint32_t *d_starts, const uint32_t *d_stops,
                                    int64_t n_q, const int32_t *d_q_seg, const uint32_t *d_q_start, const uint32_t *d_q_stop,
                                    uint32_t *d_out, bool *done) {
@@ -404,62 +382,49 @@ int32_t launch_count_overlaps_part(gams_cuda_count_plan *p, cudaStream_t st, con
         if ((rc = build_compact_index(p, st, d_starts, d_stops))) return rc;
         p->part_valid = false;
     }
-    const size_t lite_off = ((size_t)std::max<int64_t>(p->n_seg, 1) + (PT_MAX_B + 1) * sizeof(int32_t) + 63) & ~(size_t)31;
     if (!p->part_valid) {
-        std::vector<uint8_t> seg2bkt;
-        std::vector<int32_t> first;
-        int sb = 1;
-        plan_buckets(p, seg2bkt, first, sb);
-        p->part_nbkt = (int)first.size() - 1;
-        p->part_sb = sb;
-        if ((rc = p->tmp[7].reserve(lite_off + sizeof(SegLite) * (size_t)std::max<int64_t>(p->n_seg, 1)))) return rc;
-        uint8_t *base = p->tmp[7].as<uint8_t>();
-        const size_t first_off = ((size_t)std::max<int64_t>(p->n_seg, 1) + 3) & ~(size_t)3;
-        CUDA_TRY(cudaMemcpyAsync(base, seg2bkt.data(), seg2bkt.size(), cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(base + first_off, first.data(), first.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        plan_buckets(p, p->part_nbkt, p->part_bshift);
+        if ((rc = p->tmp[7].reserve(sizeof(SegLite) * (size_t)std::max<int64_t>(p->n_seg, 1)))) return rc;
         const SegCompact *d_par = reinterpret_cast<const SegCompact *>(p->tmp[4].as<uint8_t>() + p->cpar_off);
-        part_lite_kernel<<<(unsigned)((p->n_seg + 255) / 256), 256, 0, st>>>(d_par, p->tmp[4].as<uint64_t>(), p->d_iv_off, p->n_seg,
-                                                                              reinterpret_cast<SegLite *>(base + lite_off));
+        part_lite_kernel<<<(unsigned)((p->n_seg + 255) / 256), 256, 0, st>>>(d_par, p->tmp[4].as<uint64_t>(), p->n_seg, p->tmp[7].as<SegLite>());
         ++p->launches;
         CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaStreamSynchronize(st));   // seg2bkt / first are locals
+        CUDA_TRY(cudaFuncSetAttribute(part_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SORT_SMEM));
+        CUDA_TRY(cudaFuncSetAttribute(part_lookup_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(PL_MAX_CACHE_SEGS * sizeof(SegLite))));
         p->part_valid = true;
     }
     PartGeom G;
     G.n_bkt = p->part_nbkt;
-    G.sb = p->part_sb;
-    G.rb = std::min(env_int("GAMS_CUDA_PART_RB", 22), 32 - G.sb);
-    if (G.rb < 12) return GAMS_CUDA_OK;   // too many segments per bucket for a 32-bit tag: the caller takes the ranked kernel
-    G.n_region = (int32_t)((n_q + (1ll << G.rb) - 1) >> G.rb);
-    // spans: a power-of-two fraction of a region, at least two sub-tiles each, about 148 * 8 of them in all
-    int span_shift = G.rb;
-    while (span_shift > 13 && ((int64_t)G.n_region << (G.rb - span_shift)) < 148 * 8) --span_shift;
-    while (((int64_t)G.n_region << (G.rb - span_shift)) > PT_MAX_SPANS) ++span_shift;
-    if (span_shift > G.rb) return GAMS_CUDA_OK;
-    G.span_shift = span_shift;
-    G.n_span = G.n_region << (G.rb - span_shift);
-    const size_t n_cnt = (size_t)G.n_bkt * G.n_span;
-    if ((rc = p->tmp[6].reserve((size_t)n_q * 16 + 64))) return rc;
-    if ((rc = p->tmp[8].reserve((n_cnt + 1) * sizeof(uint32_t)))) return rc;
-    uint8_t *base = p->tmp[7].as<uint8_t>();
-    const size_t first_off = ((size_t)std::max<int64_t>(p->n_seg, 1) + 3) & ~(size_t)3;
-    const uint8_t *d_seg2bkt = base;
-    const int32_t *d_first = reinterpret_cast<const int32_t *>(base + first_off);
-    const SegLite *d_lite = reinterpret_cast<const SegLite *>(base + lite_off);
-    uint32_t *d_cnt = p->tmp[8].as<uint32_t>();
-    uint32_t *r_start = p->tmp[6].as<uint32_t>(), *r_stop = r_start + n_q, *r_tag = r_stop + n_q, *r_cnt = r_tag + n_q;
-    part_hist_kernel<<<(unsigned)G.n_span, PT_THREADS, 0, st>>>(d_q_seg, n_q, p->n_seg, d_seg2bkt, G, d_cnt);
-    part_scan_kernel<<<1, 1024, 0, st>>>(d_cnt, (uint32_t)n_cnt);
-    CUDA_TRY(cudaFuncSetAttribute(part_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SCATTER_SMEM));
-    part_scatter_kernel<<<(unsigned)G.n_span, PT_THREADS, PT_SCATTER_SMEM, st>>>(d_q_seg, d_q_start, d_q_stop, n_q, p->n_seg, d_seg2bkt, d_first, G,
-                                                                  d_cnt, r_start, r_stop, r_tag);
-    const SegCompact *d_par = reinterpret_cast<const SegCompact *>(p->tmp[4].as<uint8_t>() + p->cpar_off);
-    const unsigned lgrid = (unsigned)((n_q + PL_THREADS * PL_PER - 1) / (PL_THREADS * PL_PER));
-    part_lookup_kernel<<<lgrid, PL_THREADS, 0, st>>>(d_starts, d_stops, d_lite, d_par, p->tmp[5].as<uint8_t>(), d_first, G, d_cnt,
-                                                    (uint32_t)n_q, r_start, r_stop, r_tag, r_cnt);
-    const int parts = std::max(1, env_int("GAMS_CUDA_PART_UPARTS", 592));
-    part_unpermute_kernel<<<(unsigned)(G.n_region * parts), PU_THREADS, 0, st>>>(G, parts, d_cnt, r_tag, r_cnt, n_q, d_out);
-    p->launches += 5;
+    G.bshift = p->part_bshift;
+    G.sb = G.bshift + 1;
+    if (G.sb + PT_SPAN_SHIFT > 32) return GAMS_CUDA_OK;   // too many segments per bucket for a 32-bit tag: the ranked kernel
+    G.n_span = (int32_t)((n_q + PT_SPAN - 1) >> PT_SPAN_SHIFT);
+    const size_t n_run = (size_t)G.n_bkt * (size_t)G.n_span, n_pad = (size_t)G.n_span << PT_SPAN_SHIFT;
+    if (n_run >= (1ull << 32)) return GAMS_CUDA_OK;
+    if ((rc = p->tmp[6].reserve(n_pad * 16 + 64))) return rc;
+    if ((rc = p->tmp[8].reserve(n_run * 2 * sizeof(uint16_t) + 64))) return rc;
+    uint16_t *d_rcnt = p->tmp[8].as<uint16_t>(), *d_rbase = d_rcnt + n_run;
+    uint32_t *r_start = p->tmp[6].as<uint32_t>(), *r_stop = r_start + n_pad, *r_tag = r_stop + n_pad, *r_cnt = r_tag + n_pad;
+    part_sort_kernel<<<(unsigned)G.n_span, PT_THREADS, PT_SORT_SMEM, st>>>(d_q_seg, d_q_start, d_q_stop, n_q, p->n_seg, G, d_rcnt,
+                                                                           d_rbase, r_start, r_stop, r_tag);
+    LookupArgs A;
+    A.starts = d_starts, A.stops = d_stops;
+    A.iv_off = p->d_iv_off;
+    A.lite = p->tmp[7].as<SegLite>();
+    A.par = reinterpret_cast<const SegCompact *>(p->tmp[4].as<uint8_t>() + p->cpar_off);
+    A.cbuf = p->tmp[5].as<uint8_t>();
+    const uint32_t ctas_per_bkt = (uint32_t)((G.n_span + PL_RUNS - 1) / PL_RUNS);
+    const size_t lgrid = (size_t)ctas_per_bkt * G.n_bkt;
+    if (lgrid >= (1ull << 31)) return GAMS_CUDA_OK;
+    if (((int64_t)1 << G.bshift) <= PL_MAX_CACHE_SEGS)
+        part_lookup_kernel<true><<<(unsigned)lgrid, PL_THREADS, (sizeof(SegLite) << G.bshift), st>>>(
+            A, p->n_seg, G, ctas_per_bkt, d_rcnt, d_rbase, r_start, r_stop, r_tag, r_cnt);
+    else
+        part_lookup_kernel<false><<<(unsigned)lgrid, PL_THREADS, 0, st>>>(A, p->n_seg, G, ctas_per_bkt, d_rcnt, d_rbase, r_start, r_stop,
+                                                                         r_tag, r_cnt);
+    part_unpermute_kernel<<<(unsigned)G.n_span, PU_THREADS, 0, st>>>(G, r_tag, r_cnt, n_q, d_out);
+    p->launches += 3;
     CUDA_TRY(cudaGetLastError());
     *done = true;
     return GAMS_CUDA_OK;

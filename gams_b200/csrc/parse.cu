@@ -122,12 +122,16 @@ __device__ __forceinline__ bool is_word(uint8_t c) {
 __global__ void __launch_bounds__(256)
 parse_lines_kernel(const uint8_t *__restrict__ text, uint64_t n_bytes, const uint64_t *__restrict__ line_off, uint64_t n_lines,
                    const uint8_t *__restrict__ names, const uint32_t *__restrict__ name_off, const int32_t *__restrict__ htab,
-                   uint32_t hmask, int32_t *__restrict__ q_chr, uint32_t *__restrict__ q_start, uint32_t *__restrict__ q_end) {
+                   uint32_t hmask, int32_t first_field, int32_t *__restrict__ q_chr, uint32_t *__restrict__ q_start,
+                   uint32_t *__restrict__ q_end) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_lines; i += stride) {
         uint64_t p = line_off[i], e = (i + 1 < n_lines) ? line_off[i + 1] - 1 : n_bytes;   // [p, e): without the '\n'
         if (i + 1 == n_lines && e > p && text[e - 1] == '\n') --e;                         // the last line may or may not end in '\n'
         if (e > p && text[e - 1] == '\r') --e;
+        if (first_field)                                                                   // locate.rs:87-90: line.split('\t').first()
+            for (uint64_t k = p; k < e; ++k)
+                if (text[k] == '\t') { e = k; break; }
         int32_t res = -3;
         uint32_t start = 0, end = 0;
         // no ':' anywhere: the regex cannot match
@@ -190,19 +194,22 @@ parse_lines_kernel(const uint8_t *__restrict__ text, uint64_t n_bytes, const uin
     }
 }
 
-// ---- `locate --count` output: "{rg}\t{cnt}\n" per located line (locate.rs:136-139), rg = the input line itself ----------------
+// ---- `locate --count -f` output: "{rg}\t{cnt}\n" per located line (locate.rs:136-139), rg = the first TAB-separated field of
+// the input line (locate.rs:87-90) ----------------
 __device__ __forceinline__ uint32_t dec_digits(uint32_t v) {
     uint32_t d = 1;
     while (v >= 10u) { v /= 10u; ++d; }
     return d;
 }
-// [p, e) of line i without its '\n' / '\r\n'
+// [p, e): the first TAB-separated field of line i (the line without its '\n' / '\r\n' when it has no TAB)
 __device__ __forceinline__ void line_span(const uint8_t *__restrict__ text, uint64_t n_bytes, const uint64_t *__restrict__ line_off,
                                           uint64_t n_lines, uint64_t i, uint64_t &p, uint64_t &e) {
     p = line_off[i];
     e = (i + 1 < n_lines) ? line_off[i + 1] - 1 : n_bytes;
     if (i + 1 == n_lines && e > p && text[e - 1] == '\n') --e;
     if (e > p && text[e - 1] == '\r') --e;
+    for (uint64_t k = p; k < e; ++k)
+        if (text[k] == '\t') { e = k; break; }
 }
 constexpr int FM_THREADS = 256;
 
@@ -210,8 +217,8 @@ constexpr int FM_THREADS = 256;
 __global__ void __launch_bounds__(FM_THREADS)
 fmt_len_kernel(const uint8_t *__restrict__ text, uint64_t n_bytes, const uint64_t *__restrict__ line_off, uint64_t n_lines,
                const int32_t *__restrict__ q_chr, const int32_t *__restrict__ seg, const uint32_t *__restrict__ cnt,
-               uint32_t *__restrict__ tile_len, unsigned long long *__restrict__ counters) {
-    __shared__ uint32_t ws[FM_THREADS / 32];
+               uint32_t *__restrict__ tile_len, uint32_t *__restrict__ tile_printed, unsigned long long *__restrict__ counters) {
+    __shared__ uint32_t ws[FM_THREADS / 32], wp[FM_THREADS / 32];
     const uint64_t i = (uint64_t)blockIdx.x * FM_THREADS + threadIdx.x;
     uint32_t len = 0;
     bool printed = false, back = false;
@@ -228,22 +235,24 @@ fmt_len_kernel(const uint8_t *__restrict__ text, uint64_t n_bytes, const uint64_
     const uint32_t sum = __reduce_add_sync(0xFFFFFFFFu, len);
     if ((threadIdx.x & 31) == 0) {
         ws[threadIdx.x >> 5] = sum;
+        wp[threadIdx.x >> 5] = np;
         if (np) atomicAdd(&counters[0], (unsigned long long)np);
         if (nb) atomicAdd(&counters[1], (unsigned long long)nb);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        uint32_t t = 0;
-        for (int w = 0; w < FM_THREADS / 32; ++w) t += ws[w];
+        uint32_t t = 0, tp = 0;
+        for (int w = 0; w < FM_THREADS / 32; ++w) t += ws[w], tp += wp[w];
         tile_len[blockIdx.x] = t;
+        tile_printed[blockIdx.x] = tp;
     }
 }
 
 __global__ void __launch_bounds__(FM_THREADS)
 fmt_write_kernel(const uint8_t *__restrict__ text, uint64_t n_bytes, const uint64_t *__restrict__ line_off, uint64_t n_lines,
                  const int32_t *__restrict__ seg, const uint32_t *__restrict__ cnt, const uint64_t *__restrict__ tile_base,
-                 uint8_t *__restrict__ out) {
-    __shared__ uint32_t ws[FM_THREADS / 32];
+                 const uint64_t *__restrict__ tile_pbase, uint8_t *__restrict__ out, uint64_t *__restrict__ out_line) {
+    __shared__ uint32_t ws[FM_THREADS / 32], wp[FM_THREADS / 32];
     const uint64_t i = (uint64_t)blockIdx.x * FM_THREADS + threadIdx.x;
     uint32_t len = 0, c = 0, nd = 0;
     uint64_t p = 0, e = 0;
@@ -260,9 +269,16 @@ fmt_write_kernel(const uint8_t *__restrict__ text, uint64_t n_bytes, const uint6
         if ((threadIdx.x & 31) >= d) inc += t;
     }
     if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = inc;
+    const uint32_t pm = __ballot_sync(0xFFFFFFFFu, len != 0);
+    if ((threadIdx.x & 31) == 0) wp[threadIdx.x >> 5] = (uint32_t)__popc(pm);
     __syncthreads();
     uint64_t o = tile_base[blockIdx.x] + inc - len;
     for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) o += ws[w];
+    if (len && out_line) {   // which input line each printed line came from
+        uint64_t r = tile_pbase[blockIdx.x] + (uint32_t)__popc(pm & ((1u << (threadIdx.x & 31)) - 1u));
+        for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) r += wp[w];
+        out_line[r] = i;
+    }
     if (len) {
         for (uint64_t k = p; k < e; ++k) out[o++] = text[k];
         out[o++] = '\t';
@@ -291,7 +307,7 @@ struct ParsedText {
 };
 
 int32_t parse_on_device(PerDevice &pd, cudaStream_t st, const uint8_t *text, uint64_t n_bytes, int64_t n_chr, const uint8_t *chr_names,
-                        const uint32_t *chr_name_off, ParsedText &P) {
+                        const uint32_t *chr_name_off, bool first_field, ParsedText &P) {
     // the name table: open addressing, FNV-1a, load factor <= 1/2 (host work: n_chr names)
     uint32_t hsize = 16;
     while (hsize < 2 * (uint64_t)n_chr + 2) hsize <<= 1;
@@ -343,7 +359,8 @@ int32_t parse_on_device(PerDevice &pd, cudaStream_t st, const uint8_t *text, uin
     P.d_qe = P.d_qs + nl;
     nl_scatter_kernel<<<(unsigned)n_tiles, PR_THREADS, 0, st>>>(P.d_text, n_bytes, P.d_tile_base, nl, P.d_loff);
     const unsigned pb = (unsigned)std::min<uint64_t>((nl + 255) / 256, 148ull * 32);
-    parse_lines_kernel<<<pb, 256, 0, st>>>(P.d_text, n_bytes, P.d_loff, nl, d_names, d_noff, d_htab, hsize - 1, P.d_qc, P.d_qs, P.d_qe);
+    parse_lines_kernel<<<pb, 256, 0, st>>>(P.d_text, n_bytes, P.d_loff, nl, d_names, d_noff, d_htab, hsize - 1, first_field ? 1 : 0, P.d_qc,
+                                         P.d_qs, P.d_qe);
     CUDA_TRY(cudaGetLastError());
     return GAMS_CUDA_OK;
 }
@@ -363,7 +380,7 @@ GAMS_API int32_t gams_cuda_parse_ranges(gams_cuda_ctx *ctx, const uint8_t *text,
     cudaStream_t st = pd.stream;
     ParsedText P;
     struct Rel { ParsedText &p; ~Rel() { cudaDeviceSynchronize(); p.release(); } } rel{P};
-    int32_t rc = parse_on_device(pd, st, text, n_bytes, n_chr, chr_names, chr_name_off, P);
+    int32_t rc = parse_on_device(pd, st, text, n_bytes, n_chr, chr_names, chr_name_off, false, P);
     if (rc) return rc;
     const uint64_t nl = P.n_lines;
     *n_lines = nl;
@@ -383,15 +400,16 @@ GAMS_API int32_t gams_cuda_parse_ranges(gams_cuda_ctx *ctx, const uint8_t *text,
 }
 
 // The whole loop of `gams locate --count -f file` (locate.rs:111-141) on the device: text in, text out.
-GAMS_API int32_t gams_cuda_locate_count_text(gams_cuda_ctx *ctx, const uint8_t *text, uint64_t n_bytes, int64_t n_chr,
-                                             const uint8_t *chr_names, const uint32_t *chr_name_off, const uint32_t *ctg_start,
-                                             const uint32_t *ctg_stop, const uint64_t *chr_off, const uint32_t *starts,
-                                             const uint32_t *stops, const uint64_t *iv_off, char **out_text, size_t *out_len,
-                                             uint64_t *n_lines, uint64_t *n_printed, uint64_t *n_handed_back) {
+static int32_t locate_count_text_impl(gams_cuda_ctx *ctx, const uint8_t *text, uint64_t n_bytes, int64_t n_chr,
+                                      const uint8_t *chr_names, const uint32_t *chr_name_off, const uint32_t *ctg_start,
+                                      const uint32_t *ctg_stop, const uint64_t *chr_off, const uint32_t *starts,
+                                      const uint32_t *stops, const uint64_t *iv_off, char **out_text, size_t *out_len,
+                                      uint64_t **out_line, uint64_t *n_lines, uint64_t *n_printed, uint64_t *n_handed_back) {
     ARG_CHECK(ctx && out_text && out_len && n_chr >= 0 && n_chr < (1ll << 30) && chr_off && iv_off, "locate_count_text: bad argument");
     ARG_CHECK(n_chr == 0 || (chr_names && chr_name_off), "locate_count_text: NULL name table");
     *out_text = nullptr;
     *out_len = 0;
+    if (out_line) *out_line = nullptr;
     if (n_lines) *n_lines = 0;
     if (n_printed) *n_printed = 0;
     if (n_handed_back) *n_handed_back = 0;
@@ -406,11 +424,12 @@ GAMS_API int32_t gams_cuda_locate_count_text(gams_cuda_ctx *ctx, const uint8_t *
     for (int64_t c = 0; c < n_chr; ++c)
         for (uint64_t k = chr_off[c]; k < chr_off[c + 1]; ++k)
             if (ctg_stop[k] > ctg_start[k]) maxlen[c] = std::max(maxlen[c], ctg_stop[k] - ctg_start[k]);
+    // the lock first: everything below allocates from the device's block cache; the plan goes before the lock is released
+    std::lock_guard<std::mutex> lk(ctx->mu);
     gams_cuda_count_plan *plan = nullptr;
     int32_t rc = gams_cuda_count_plan_create(ctx, 0, (int64_t)n_ctg, iv_off, &plan);
     if (rc) return rc;
     std::unique_ptr<gams_cuda_count_plan, void (*)(gams_cuda_count_plan *)> pguard(plan, gams_cuda_count_plan_destroy);
-    std::lock_guard<std::mutex> lk(ctx->mu);
     PerDevice &pd = ctx->devs[0];
     DeviceGuard g(pd.device);
     cudaStream_t st = pd.stream;
@@ -418,7 +437,7 @@ GAMS_API int32_t gams_cuda_locate_count_text(gams_cuda_ctx *ctx, const uint8_t *
     DevBuf idx, work, outb;
     idx.cache = work.cache = outb.cache = pd.cache;
     struct Rel { ParsedText &p; DevBuf &a, &b, &c; ~Rel() { cudaDeviceSynchronize(); p.release(); a.release(); b.release(); c.release(); } } rel{P, idx, work, outb};
-    if ((rc = parse_on_device(pd, st, text, n_bytes, n_chr, chr_names, chr_name_off, P))) return rc;
+    if ((rc = parse_on_device(pd, st, text, n_bytes, n_chr, chr_names, chr_name_off, true, P))) return rc;
     const uint64_t nl = P.n_lines;
     if (n_lines) *n_lines = nl;
     // the two indexes
@@ -439,39 +458,67 @@ GAMS_API int32_t gams_cuda_locate_count_text(gams_cuda_ctx *ctx, const uint8_t *
     }
     // locate -> count -> lengths -> offsets -> bytes
     const uint64_t n_ft = (nl + FM_THREADS - 1) / FM_THREADS;
-    if ((rc = work.reserve(nl * 8 + 8 + n_ft * 12 + 32 + 64))) return rc;
+    if ((rc = work.reserve(nl * 8 + 8 + n_ft * 24 + 48 + 64))) return rc;
     int32_t *d_seg = work.as<int32_t>();
     uint32_t *d_cnt = reinterpret_cast<uint32_t *>(d_seg + nl);
     uint64_t *d_fbase = reinterpret_cast<uint64_t *>(d_cnt + nl), *d_ftotal = d_fbase + n_ft;   // 8 nl bytes in: aligned
-    unsigned long long *d_counters = reinterpret_cast<unsigned long long *>(d_ftotal + 1);
-    uint32_t *d_flen = reinterpret_cast<uint32_t *>(d_counters + 2);
+    uint64_t *d_pbase = d_ftotal + 1, *d_ptotal = d_pbase + n_ft;
+    unsigned long long *d_counters = reinterpret_cast<unsigned long long *>(d_ptotal + 1);
+    uint32_t *d_flen = reinterpret_cast<uint32_t *>(d_counters + 2), *d_fprinted = d_flen + n_ft;
     CUDA_TRY(cudaMemsetAsync(d_counters, 0, 16, st));
     if ((rc = launch_locate_ctg(st, n_chr, d_cs, d_ce, d_chr_off, d_ml, (int64_t)nl, P.d_qc, P.d_qs, P.d_qe, d_seg))) return rc;
     if ((rc = launch_count_overlaps(plan, st, d_st, d_sp, (int64_t)nl, d_seg, P.d_qs, P.d_qe, 0, d_cnt))) return rc;
-    fmt_len_kernel<<<(unsigned)n_ft, FM_THREADS, 0, st>>>(P.d_text, n_bytes, P.d_loff, nl, P.d_qc, d_seg, d_cnt, d_flen, d_counters);
+    fmt_len_kernel<<<(unsigned)n_ft, FM_THREADS, 0, st>>>(P.d_text, n_bytes, P.d_loff, nl, P.d_qc, d_seg, d_cnt, d_flen, d_fprinted, d_counters);
     nl_scan_kernel<<<1, 1024, 0, st>>>(d_flen, n_ft, d_fbase, d_ftotal);
+    if (out_line) nl_scan_kernel<<<1, 1024, 0, st>>>(d_fprinted, n_ft, d_pbase, d_ptotal);
     uint64_t h[3] = {0, 0, 0};
     CUDA_TRY(cudaMemcpyAsync(&h[0], d_ftotal, 8, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(&h[1], d_counters, 16, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     if (n_printed) *n_printed = h[1];
     if (n_handed_back) *n_handed_back = h[2];
-    const uint64_t total = h[0];
+    const uint64_t total = h[0], n_pr = h[1];
     char *host = static_cast<char *>(malloc(total + 1));
-    if (!host) {
+    uint64_t *host_line = out_line ? static_cast<uint64_t *>(malloc((n_pr + 1) * sizeof(uint64_t))) : nullptr;
+    if (!host || (out_line && !host_line)) {
+        free(host);
+        free(host_line);
         set_error("locate_count_text: cannot allocate %llu bytes for the output", (unsigned long long)total);
         return GAMS_CUDA_ENOMEM;
     }
     if (total) {
-        if ((rc = outb.reserve(total + 64))) { free(host); return rc; }
-        fmt_write_kernel<<<(unsigned)n_ft, FM_THREADS, 0, st>>>(P.d_text, n_bytes, P.d_loff, nl, d_seg, d_cnt, d_fbase, outb.as<uint8_t>());
+        if ((rc = outb.reserve(total + 64 + (out_line ? n_pr * 8 + 8 : 0)))) { free(host); free(host_line); return rc; }
+        uint64_t *d_line = out_line ? reinterpret_cast<uint64_t *>(outb.as<uint8_t>() + ((total + 15) & ~15ull)) : nullptr;
+        fmt_write_kernel<<<(unsigned)n_ft, FM_THREADS, 0, st>>>(P.d_text, n_bytes, P.d_loff, nl, d_seg, d_cnt, d_fbase, d_pbase, outb.as<uint8_t>(),
+                                                                d_line);
         cudaError_t e = cudaGetLastError();
         if (e == cudaSuccess) e = cudaMemcpyAsync(host, outb.p, total, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess && out_line && n_pr) e = cudaMemcpyAsync(host_line, d_line, n_pr * 8, cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-        if (e != cudaSuccess) { free(host); return cuda_fail(e, "locate_count_text output", __FILE__, __LINE__); }
+        if (e != cudaSuccess) { free(host); free(host_line); return cuda_fail(e, "locate_count_text output", __FILE__, __LINE__); }
     }
     host[total] = 0;
     *out_text = host;
     *out_len = (size_t)total;
+    if (out_line) *out_line = host_line;
     return GAMS_CUDA_OK;
+}
+
+GAMS_API int32_t gams_cuda_locate_count_text(gams_cuda_ctx *ctx, const uint8_t *text, uint64_t n_bytes, int64_t n_chr,
+                                             const uint8_t *chr_names, const uint32_t *chr_name_off, const uint32_t *ctg_start,
+                                             const uint32_t *ctg_stop, const uint64_t *chr_off, const uint32_t *starts,
+                                             const uint32_t *stops, const uint64_t *iv_off, char **out_text, size_t *out_len,
+                                             uint64_t *n_lines, uint64_t *n_printed, uint64_t *n_handed_back) {
+    return locate_count_text_impl(ctx, text, n_bytes, n_chr, chr_names, chr_name_off, ctg_start, ctg_stop, chr_off, starts, stops, iv_off,
+                                  out_text, out_len, nullptr, n_lines, n_printed, n_handed_back);
+}
+
+GAMS_API int32_t gams_cuda_locate_count_lines(gams_cuda_ctx *ctx, const uint8_t *text, uint64_t n_bytes, int64_t n_chr,
+                                              const uint8_t *chr_names, const uint32_t *chr_name_off, const uint32_t *ctg_start,
+                                              const uint32_t *ctg_stop, const uint64_t *chr_off, const uint32_t *starts,
+                                              const uint32_t *stops, const uint64_t *iv_off, char **out_text, size_t *out_len,
+                                              uint64_t **out_line, uint64_t *n_lines, uint64_t *n_printed, uint64_t *n_handed_back) {
+    ARG_CHECK(out_line != nullptr, "locate_count_lines: out_line is NULL");
+    return locate_count_text_impl(ctx, text, n_bytes, n_chr, chr_names, chr_name_off, ctg_start, ctg_stop, chr_off, starts, stops, iv_off,
+                                  out_text, out_len, out_line, n_lines, n_printed, n_handed_back);
 }

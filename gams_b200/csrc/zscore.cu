@@ -149,7 +149,7 @@ template <int MODE>
 __global__ void __launch_bounds__(ZS_THREADS)
 zscore_indep_kernel(const float *__restrict__ x, const uint64_t *__restrict__ off,
                     const TileDesc *__restrict__ tiles, int lag, float threshold, const ZsConst zc,
-                    int8_t *__restrict__ signal, unsigned long long *__restrict__ stats) {
+                    int8_t *__restrict__ signal, unsigned long long *__restrict__ stats, int *__restrict__ nonfinite) {
     extern __shared__ __align__(16) unsigned char zs_smem[];
     const int n_el_max = ZS_TILE + lag + 1;
     double2 *YY = reinterpret_cast<double2 *>(zs_smem);          // n_el_max + 1: exclusive prefixes of (y, y^2)
@@ -174,17 +174,28 @@ zscore_indep_kernel(const float *__restrict__ x, const uint64_t *__restrict__ of
     {
         const float *xt = x + base + (lo0 < 0 ? 0 : lo0);  // element at smem position first_valid
         const float x0 = xt[0];                             // n_el > first_valid always (nw >= 1)
+        int nf = 0;
         for (int p = tid; p < n_el; p += ZS_THREADS) {
             const int q = p - first_valid;
-            sm[zs_swz(p)] = (q >= 0) ? xt[q] : x0;  // positions before the series start are never part of a stats window
+            const float v = (q >= 0) ? xt[q] : x0;  // positions before the series start are never part of a stats window
+            sm[zs_swz(p)] = v;
+            nf |= !(fabsf(v) <= 3.4028234664e38f);
         }
+        // Inf / NaN: `filtered == data` no longer holds at influence 1 (stat.rs:42: 1 * x + 0 * filtered[i-1] is NaN behind a
+        // non-finite value), so the series is walked again in order by the sequential kernel (launch_zscore)
+        if (__syncthreads_or(nf) && tid == 0 && nonfinite) nonfinite[td.item] = 1;
     }
-    __syncthreads();
 
     const float flag = __ull2float_rn((unsigned long long)lag);  // `data.len() as f32`
     const float flagm1 = __fsub_rn(flag, 1.0f);                   // `len - 1.`
-    const bool use_filter = (MODE != 1) && lag >= 2 && threshold >= 0.0f && threshold < 3.0e38f;
+    // The certificate rests on the standard model fl(a op b) = (a op b)(1 + d), |d| <= u, which holds only while nothing the
+    // reference computes in f32 overflows or underflows: thresholds in [2^-16, 2^30] here, and per tile max|x| in
+    // [2^-30, 2^50] below (then sum (x - m)^2 <= 4 n M^2 < 2^116 stays finite, squares that flush to zero are below
+    // 2^-126 against an error budget `extra` >= 1e-7 M^2, and thr * sd is either exactly 0 or a normal number).  Everything
+    // else — huge or tiny magnitudes, Inf, NaN — is replayed exactly (stat.rs:8-14 then gives sd = inf or NaN: no signal).
+    const bool use_filter = (MODE != 1) && lag >= 2 && threshold >= 1.52587890625e-5f && threshold <= 1073741824.0f;
     bool replay_all = !use_filter || MODE == 2;
+    bool cert_ok = use_filter;
 
     if (use_filter) {
         // ---- f64 prefix sums of y = x - xref and y^2 over the tile's elements (thread-contiguous chunks) ----
@@ -199,7 +210,7 @@ zscore_indep_kernel(const float *__restrict__ x, const uint64_t *__restrict__ of
             const double y = (double)xf - xref;
             a1 += y;
             a2 = fma(y, y, a2);
-            mxf = fmaxf(mxf, fabsf(xf));
+            mxf = fmaxf(mxf, (fabsf(xf) <= 3.4028234664e38f) ? fabsf(xf) : __int_as_float(0x7F800000));   // NaN counts as Inf
         }
         double s1 = a1, s2 = a2;
 #pragma unroll
@@ -227,6 +238,8 @@ zscore_indep_kernel(const float *__restrict__ x, const uint64_t *__restrict__ of
         }
         if (pe == n_el && pb < pe) YY[n_el] = make_double2(b1, b2);
         __syncthreads();
+        cert_ok = M >= 9.313225746154785e-10 && M <= 1125899906842624.0;   // block-uniform; false for M = Inf (or NaN data)
+        if (!cert_ok) replay_all = true;
 
         // ---- certificate, one window per thread, branch-free except for the rare inconclusive case ----
         const double slack = fma(zc.c_slack, M, 1e-40);
@@ -235,7 +248,7 @@ zscore_indep_kernel(const float *__restrict__ x, const uint64_t *__restrict__ of
         const int k_min = (w0 >= (int64_t)lag) ? 0 : (int)((int64_t)lag - w0);  // windows before `lag` never signal
         unsigned unc = 0;
 #pragma unroll 2
-        for (int k = tid; k < nw; k += ZS_THREADS) {
+        for (int k = tid; k < nw && cert_ok; k += ZS_THREADS) {
             // a - lo0 with a = max(i-1-lag, 0) (stat.rs:30-31 vs :51-52); the min() only bites for windows before `lag`
             const int pa = min(max(k, first_valid), n_el - lag);
             const double2 A = YY[pa], B = YY[pa + lag];
@@ -264,7 +277,7 @@ zscore_indep_kernel(const float *__restrict__ x, const uint64_t *__restrict__ of
             if (lane == 0 && unc) atomicAdd(&stats[0], (unsigned long long)unc);
         }
         __syncthreads();
-        if (MODE == 0) {
+        if (MODE == 0 && cert_ok) {
             const int cnt = list_n;
             if (cnt > ZS_LIST_CAP) replay_all = true;
             else {
@@ -301,7 +314,7 @@ zscore_indep_kernel(const float *__restrict__ x, const uint64_t *__restrict__ of
 #pragma unroll
             for (int r = 0; r < ZS_R; ++r) {
                 if (p0 + r >= nw) continue;
-                if (MODE == 2 && use_filter && cg[p0 + r] != 2 && cg[p0 + r] != (int8_t)rs[r]) ++bad;
+                if (MODE == 2 && cert_ok && cg[p0 + r] != 2 && cg[p0 + r] != (int8_t)rs[r]) ++bad;
                 sg[p0 + r] = (int8_t)rs[r];
             }
             if (MODE == 2 && bad && stats) atomicAdd(&stats[1], (unsigned long long)bad);
@@ -316,10 +329,12 @@ zscore_indep_kernel(const float *__restrict__ x, const uint64_t *__restrict__ of
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 zscore_seq_kernel(const float *__restrict__ x_all, const uint64_t *__restrict__ off, int64_t s_begin, int64_t s_end,
-                  uint64_t lag, float threshold, float influence, float *filt_all, int8_t *__restrict__ signal) {
+                  uint64_t lag, float threshold, float influence, float *filt_all, int8_t *__restrict__ signal,
+                  const int *__restrict__ only_flagged) {
     const int lane = threadIdx.x & 31;
     const int64_t c = s_begin + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (c >= s_end) return;
+    if (only_flagged && !only_flagged[c]) return;
     const uint64_t base = off[c];
     const int64_t n = (int64_t)(off[c + 1] - base);
     const float *x = x_all + base;
@@ -410,11 +425,13 @@ constexpr int ZSEQ_WARPS = 4;
 template <int P>
 __global__ void __launch_bounds__(ZSEQ_WARPS * 32)
 zscore_seq_ring_kernel(const float *__restrict__ x_all, const uint64_t *__restrict__ off, int64_t s_begin, int64_t s_end,
-                       uint64_t lag, float threshold, float influence, int8_t *__restrict__ signal) {
+                       uint64_t lag, float threshold, float influence, int8_t *__restrict__ signal,
+                       const int *__restrict__ only_flagged) {
     __shared__ float ring_all[ZSEQ_WARPS][P];
     const int lane = threadIdx.x & 31;
     const int64_t c = s_begin + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (c >= s_end) return;
+    if (only_flagged && !only_flagged[c]) return;
     float *ring = ring_all[threadIdx.x >> 5];
     const uint64_t base = off[c];
     const int64_t n = (int64_t)(off[c + 1] - base);
@@ -569,7 +586,7 @@ int32_t launch_zscore_skip(const SeriesLayout &L, cudaStream_t st, const float *
 
 int32_t launch_zscore(const SeriesLayout &L, cudaStream_t st, const float *d_x, uint64_t lag, float threshold,
                       float influence, float *d_filtered, int8_t *d_signal, uint64_t *launches, int mode,
-                      unsigned long long *d_stats, int64_t s0, int64_t s1) {
+                      unsigned long long *d_stats, int64_t s0, int64_t s1, bool gc_values) {
     if (lag == 0) {
         set_error("thresholding: lag must be >= 1 (the reference underflows lag-1, stat.rs:30)");
         return GAMS_CUDA_EINVAL;
@@ -584,6 +601,7 @@ int32_t launch_zscore(const SeriesLayout &L, cudaStream_t st, const float *d_x, 
     // influence != 1 with a lag the shared-memory ring holds: the influence-1 decisions of every window first (parallel),
     // then the walk that replays only the stretches behind a signal
     const bool skip = !tiled && lag <= ZS_MAX_TILED_LAG && zscore_skip_ok(lag) && mode == 0;
+    if (tiled && !gc_values) CUDA_TRY(cudaMemsetAsync(L.d_nonfinite + s0, 0, sizeof(int) * (size_t)(s1 - s0), st));
     if (tiled || skip) {
         const int n_el_max = ZS_TILE + (int)lag + 1;
         const size_t smem_need = (size_t)(n_el_max + 1) * 16 + (size_t)(zs_swz(n_el_max) + 1) * sizeof(float) + 2 * ZS_TILE;
@@ -594,12 +612,25 @@ int32_t launch_zscore(const SeriesLayout &L, cudaStream_t st, const float *d_x, 
             const uint64_t t0 = L.h_ztile_off[s0], t1 = L.h_ztile_off[s1];
             if (t1 > t0)
                 kern<<<(unsigned)(t1 - t0), ZS_THREADS, smem_need, st>>>(d_x, L.d_off, L.d_ztiles + t0, (int)lag, threshold, zc,
-                                                                        d_signal, d_stats);
+                                                                        d_signal, d_stats, tiled ? L.d_nonfinite : nullptr);
             return GAMS_CUDA_OK;
         };
         int32_t rc = mode == 1 ? go(zscore_indep_kernel<1>) : mode == 2 ? go(zscore_indep_kernel<2>) : go(zscore_indep_kernel<0>);
         if (rc) return rc;
         if (skip && (rc = launch_zscore_skip(L, st, d_x, lag, threshold, influence, d_signal, launches, s0, s1))) return rc;
+        if (tiled && !gc_values) {
+            // series flagged as holding Inf / NaN are walked again in the reference's order (a warp per series; warps of
+            // clean series leave at once).  Data known to be GC fractions cannot hold any.
+            const unsigned grid = (unsigned)((s1 - s0 + ZSEQ_WARPS - 1) / ZSEQ_WARPS);
+            if (lag + 65 <= 256)
+                zscore_seq_ring_kernel<256><<<grid, ZSEQ_WARPS * 32, 0, st>>>(d_x, L.d_off, s0, s1, lag, threshold, influence, d_signal, L.d_nonfinite);
+            else if (lag + 65 <= 1024)
+                zscore_seq_ring_kernel<1024><<<grid, ZSEQ_WARPS * 32, 0, st>>>(d_x, L.d_off, s0, s1, lag, threshold, influence, d_signal, L.d_nonfinite);
+            else if (d_filtered)
+                zscore_seq_kernel<<<grid, 128, 0, st>>>(d_x, L.d_off, s0, s1, lag, threshold, influence, d_filtered, d_signal, L.d_nonfinite);
+            // (lag > 959 without the d_filtered scratch: series with Inf / NaN keep the filtered == data decisions)
+            if (launches) ++*launches;
+        }
     } else {
         if (!d_filtered) {
             set_error("thresholding: influence != 1 (or lag too large for the tiled path) needs the d_filtered scratch");
@@ -607,11 +638,11 @@ int32_t launch_zscore(const SeriesLayout &L, cudaStream_t st, const float *d_x, 
         }
         const unsigned grid = (unsigned)((s1 - s0 + ZSEQ_WARPS - 1) / ZSEQ_WARPS);
         if (lag + 65 <= 256)
-            zscore_seq_ring_kernel<256><<<grid, ZSEQ_WARPS * 32, 0, st>>>(d_x, L.d_off, s0, s1, lag, threshold, influence, d_signal);
+            zscore_seq_ring_kernel<256><<<grid, ZSEQ_WARPS * 32, 0, st>>>(d_x, L.d_off, s0, s1, lag, threshold, influence, d_signal, nullptr);
         else if (lag + 65 <= 1024)
-            zscore_seq_ring_kernel<1024><<<grid, ZSEQ_WARPS * 32, 0, st>>>(d_x, L.d_off, s0, s1, lag, threshold, influence, d_signal);
+            zscore_seq_ring_kernel<1024><<<grid, ZSEQ_WARPS * 32, 0, st>>>(d_x, L.d_off, s0, s1, lag, threshold, influence, d_signal, nullptr);
         else
-            zscore_seq_kernel<<<grid, 128, 0, st>>>(d_x, L.d_off, s0, s1, lag, threshold, influence, d_filtered, d_signal);
+            zscore_seq_kernel<<<grid, 128, 0, st>>>(d_x, L.d_off, s0, s1, lag, threshold, influence, d_filtered, d_signal, nullptr);
     }
     if (launches) ++*launches;
     CUDA_TRY(cudaGetLastError());

@@ -307,7 +307,9 @@ int32_t gams_cuda_build_idx_rg(gams_cuda_ctx *ctx, int64_t n_seg, const uint32_t
                                uint32_t *stops, uint32_t *max_len, uint8_t *blob /* NULL: no blobs */);
 
 /* The front end of `gams locate` (src/cmd_gams/locate.rs:111-117) and read_range (src/libs/utils.rs:39-52): the lines of
- * a range file parsed on the device instead of one intspan::Range::from_str (a regex) per line.
+ * a range file parsed on the device instead of one intspan::Range::from_str (a regex) per line.  The whole line is what
+ * read_range hands to the regex (utils.rs:49); `locate -f` hands it the first TAB-separated field only (locate.rs:87-90) —
+ * for lines of the strict form both give the same range (the regex cannot run past a TAB).
  * text: n_bytes, lines end in '\n' (a '\r' before it is dropped, as BufRead::lines does; a last line without '\n' counts).
  * chr names: n_chr names back to back in chr_names, name c = [chr_name_off[c], chr_name_off[c+1]).
  * Per line i (0 .. *n_lines): line_off[i] (byte offset; line_off[*n_lines] = n_bytes), q_start / q_end (1-based inclusive) and
@@ -321,19 +323,30 @@ int32_t gams_cuda_parse_ranges(gams_cuda_ctx *ctx, const uint8_t *text, uint64_t
                                const uint8_t *chr_names, const uint32_t *chr_name_off, uint64_t cap_lines,
                                uint64_t *n_lines, uint64_t *line_off, int32_t *q_chr, uint32_t *q_start, uint32_t *q_end);
 
-/* The whole loop of `gams locate --count -f file` (src/cmd_gams/locate.rs:111-141) on the device, text in, text out:
- * Range::from_str per line -> find_one_idx -> count_rg -> "{rg}\t{cnt}\n" for every line that is a valid range on a known
- * ctg, in input order, rg being the input line itself (as locate.rs:139 prints it).
+/* The whole loop of `gams locate --count -f file` (src/cmd_gams/locate.rs:80-141) on the device, text in, text out:
+ * rg = the first TAB-separated field of each line (locate.rs:87-90: `line.split('\t').first()`), then Range::from_str(rg) ->
+ * find_one_idx -> count_rg -> "{rg}\t{cnt}\n" for every rg that is a valid range on a known ctg, in input order (locate.rs:139).
+ * Only the first field is parsed and only the first field is echoed, so multi-column files (gams' own .tsv outputs, header
+ * rows such as "#range\tgc\tsignal") give exactly the reference's lines.
  * ctg index: as gams_cuda_locate_ctg takes it (ctgs of chromosome c = [chr_off[c], chr_off[c+1]), sorted by start, stop
  * exclusive); rg index: segment k of starts / stops / iv_off belongs to ctg k of that same order.
- * Lines outside the strict form (see gams_cuda_parse_ranges) are NOT printed; *n_handed_back counts them, and a caller that
- * sees a non-zero count runs those lines (gams_cuda_parse_ranges marks them) through the reference path.
+ * First fields outside the strict form (see gams_cuda_parse_ranges) are NOT printed; *n_handed_back counts them.  A caller that
+ * needs byte parity on such input uses gams_cuda_locate_count_lines: it also returns the input line index of every printed
+ * line, so the lines the caller resolves itself (gams_cuda_parse_ranges marks them -3 when given the same first fields) merge
+ * back in input order.
  * *out_text: malloc'ed, NUL-terminated, *out_len bytes; free with gams_cuda_free. */
 int32_t gams_cuda_locate_count_text(gams_cuda_ctx *ctx, const uint8_t *text, uint64_t n_bytes, int64_t n_chr,
                                     const uint8_t *chr_names, const uint32_t *chr_name_off, const uint32_t *ctg_start,
                                     const uint32_t *ctg_stop, const uint64_t *chr_off, const uint32_t *starts,
                                     const uint32_t *stops, const uint64_t *iv_off, char **out_text, size_t *out_len,
                                     uint64_t *n_lines, uint64_t *n_printed, uint64_t *n_handed_back);
+/* The same, plus *out_line: malloc'ed, *n_printed entries, out_line[k] = 0-based input line of the k-th printed line
+ * (free with gams_cuda_free). */
+int32_t gams_cuda_locate_count_lines(gams_cuda_ctx *ctx, const uint8_t *text, uint64_t n_bytes, int64_t n_chr,
+                                     const uint8_t *chr_names, const uint32_t *chr_name_off, const uint32_t *ctg_start,
+                                     const uint32_t *ctg_stop, const uint64_t *chr_off, const uint32_t *starts,
+                                     const uint32_t *stops, const uint64_t *iv_off, char **out_text, size_t *out_len,
+                                     uint64_t **out_line, uint64_t *n_lines, uint64_t *n_printed, uint64_t *n_handed_back);
 
 /* gams::find_one_idx (utils.rs:7-22) -> Lapper::find(start, stop).next() on the idx:ctg:{chr}
  * index: ctg intervals [chr_start, chr_end+1) sorted by start within each chromosome segment.

@@ -29,6 +29,8 @@ pub const GAMS_CUDA_ENOMEM: i32 = -3;
 pub const GAMS_CUDA_ELAG: i32 = -4;
 pub const GAMS_CUDA_ENODEV: i32 = -5;
 pub const GAMS_CUDA_EPARSE: i32 = -6;
+/// Caller-provided output arrays are too small; the needed count is reported (call again with larger arrays).
+pub const GAMS_CUDA_ECAP: i32 = -7;
 
 extern "C" {
     pub fn gams_cuda_version() -> i32;
@@ -39,6 +41,9 @@ extern "C" {
     pub fn gams_cuda_ctx_num_devices(ctx: *const gams_cuda_ctx) -> i32;
     pub fn gams_cuda_host_alloc(bytes: usize) -> *mut c_void;
     pub fn gams_cuda_host_free(p: *mut c_void);
+    pub fn gams_cuda_memcpy_probe(ctx: *mut gams_cuda_ctx, host: *mut c_void, bytes: usize, kind: i32) -> i32;
+    pub fn gams_cuda_set_zscore_mode(ctx: *mut gams_cuda_ctx, mode: i32) -> i32;
+    pub fn gams_cuda_zscore_stats(ctx: *mut gams_cuda_ctx, out2: *mut u64, reset: i32) -> i32;
 
     pub fn gams_cuda_wave_nwin(ctg_len: i64, size: i32, step: i32) -> i64;
     pub fn gams_cuda_wave_win_offsets(n_ctg: i64, seq_off: *const u64, size: i32, step: i32, win_off: *mut u64) -> i32;
@@ -160,6 +165,12 @@ extern "C" {
         ctg_start: *const u32, ctg_stop: *const u32, chr_off: *const u64, starts: *const u32, stops: *const u32,
         iv_off: *const u64, out_text: *mut *mut c_char, out_len: *mut usize, n_lines: *mut u64, n_printed: *mut u64,
         n_handed_back: *mut u64,
+    ) -> i32;
+    pub fn gams_cuda_locate_count_lines(
+        ctx: *mut gams_cuda_ctx, text: *const u8, n_bytes: u64, n_chr: i64, chr_names: *const u8, chr_name_off: *const u32,
+        ctg_start: *const u32, ctg_stop: *const u32, chr_off: *const u64, starts: *const u32, stops: *const u32,
+        iv_off: *const u64, out_text: *mut *mut c_char, out_len: *mut usize, out_line: *mut *mut u64, n_lines: *mut u64,
+        n_printed: *mut u64, n_handed_back: *mut u64,
     ) -> i32;
     pub fn gams_cuda_build_idx_rg(
         ctx: *mut gams_cuda_ctx, n_seg: i64, start: *const u32, stop: *const u32, iv_off: *const u64,

@@ -20,6 +20,30 @@ def test_library_exports_every_declared_symbol():
     assert L.gams_cuda_version() >= 100
 
 
+def test_rust_sys_crate_declares_what_the_header_declares():
+    """integration/gams-cuda-sys/src/lib.rs (the binding a gams maintainer adds) against include/gams_cuda.h: the same
+    functions, the same number of arguments, the same error codes.  (No cargo in this image: the crate is checked as text.)"""
+    import re
+    from pathlib import Path
+    root = Path(_lib.__file__).resolve().parent.parent
+    rs = (root / "integration" / "gams-cuda-sys" / "src" / "lib.rs").read_text()
+    hdr = re.sub(r"/\*.*?\*/", "", (root / "include" / "gams_cuda.h").read_text(), flags=re.S)
+    rs_fns = {m.group(1): m.group(2) for m in re.finditer(r"pub fn (gams_cuda_\w+)\s*\((.*?)\)\s*(?:->\s*[^;]+)?;", rs, flags=re.S)}
+    h_fns = {m.group(1): m.group(2) for m in re.finditer(r"\b(gams_cuda_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", hdr, flags=re.S)}
+    assert set(h_fns) == set(_lib.header_symbols())
+    assert set(rs_fns) == set(h_fns), f"missing in lib.rs: {sorted(set(h_fns) - set(rs_fns))}; extra: {sorted(set(rs_fns) - set(h_fns))}"
+
+    def n_args(a):
+        a = a.strip()
+        return 0 if a in ("", "void") else a.count(",") + 1 - (1 if a.rstrip().endswith(",") else 0)
+
+    for f in h_fns:
+        assert n_args(h_fns[f]) == n_args(rs_fns[f]), f"{f}: {n_args(h_fns[f])} arguments in the header, {n_args(rs_fns[f])} in lib.rs"
+    h_codes = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+(GAMS_CUDA_[A-Z]+)\s+\(?(-?\d+)\)?", hdr)}
+    rs_codes = {m.group(1): int(m.group(2)) for m in re.finditer(r"pub const (GAMS_CUDA_[A-Z]+): i32 = (-?\d+);", rs)}
+    assert h_codes == rs_codes and h_codes["GAMS_CUDA_ECAP"] == -7
+
+
 def test_window_arithmetic_matches_oracle(orc):
     rng = np.random.default_rng(1)
     for _ in range(300):
