@@ -23,9 +23,15 @@
 namespace gams {
 
 constexpr int PT_MAX_B = 256;                 // buckets
-constexpr int PT_THREADS = 512;
-constexpr int PT_PER = 16;                    // queries per thread
-constexpr int PT_SPAN_SHIFT = 13;
+#ifndef PT_THREADS_N
+#define PT_THREADS_N 512
+#endif
+#ifndef PT_SPAN_SHIFT_N
+#define PT_SPAN_SHIFT_N 13
+#endif
+constexpr int PT_THREADS = PT_THREADS_N;
+constexpr int PT_SPAN_SHIFT = PT_SPAN_SHIFT_N;
+constexpr int PT_PER = (1 << PT_SPAN_SHIFT) / PT_THREADS;   // queries per thread
 constexpr int PT_SPAN = 1 << PT_SPAN_SHIFT;   // queries per span = PT_THREADS * PT_PER
 static_assert(PT_SPAN == PT_THREADS * PT_PER, "span geometry");
 constexpr size_t PT_SORT_SMEM = (size_t)PT_SPAN * 12;
@@ -163,9 +169,18 @@ part_sort_kernel(const int32_t *__restrict__ q_seg, const uint32_t *__restrict__
 // and handles it 4 records per lane at a time: 12 record loads, then the 8 index loads, then the 4 stores — the latencies
 // of a phase overlap inside the warp.  The bucket's SegLite records sit in shared memory (CACHE) when they fit.
 constexpr int PL_THREADS = 256;
-constexpr int PL_WRUNS = 8;                              // runs per warp
+#ifndef PL_WRUNS_N
+#define PL_WRUNS_N 8
+#endif
+#ifndef PL_U_N
+#define PL_U_N 4
+#endif
+constexpr int PL_WRUNS = PL_WRUNS_N;                     // runs per warp
 constexpr int PL_RUNS = PL_WRUNS * PL_THREADS / 32;      // runs (spans) per CTA
-constexpr int PL_U = 4;                                  // records per lane and round
+constexpr int PL_U = PL_U_N;                             // records per lane and round
+#ifndef PL_MIN_CTAS
+#define PL_MIN_CTAS 2
+#endif
 constexpr int PL_MAX_CACHE_SEGS = 3072;                  // 48 KB of SegLite
 
 struct LookupArgs {
@@ -209,11 +224,21 @@ __device__ __forceinline__ uint32_t e8_finish(uint32_t lo, uint32_t l, uint2 e, 
     return (e.x & 0x7FFFu) + (uint32_t)__popc(~((e.x | 0x8080FFFFu) - rr) & 0x80808080u) + (uint32_t)__popc(~((e.y | 0x80808080u) - rr) & 0x80808080u);
 }
 
+// crowded E8 bucket (flag set, key beyond the entry's sixth element): the seventh and later elements, in the raw array
+__device__ __noinline__ uint32_t e8_crowded_extra(const uint32_t *__restrict__ a, const uint2 *ent, uint32_t b, uint32_t cum, uint32_t key) {
+    const uint32_t nxt = __ldg(&ent[b + 1].x) & 0x7FFFu;
+    uint32_t cnt = 0;
+    for (uint32_t i = cum + 6u; i < nxt; ++i) cnt += (__ldg(a + i) < key) ? 1u : 0u;
+    return cnt;
+}
+
 template <bool CACHE>
-__global__ void __launch_bounds__(PL_THREADS, 3)
+__global__ void __launch_bounds__(PL_THREADS, PL_MIN_CTAS)
 part_lookup_kernel(LookupArgs A, int64_t n_seg, PartGeom G, uint32_t ctas_per_bkt,
                    const uint16_t *__restrict__ run_cnt, const uint16_t *__restrict__ run_base, const uint32_t *__restrict__ r_start,
                    const uint32_t *__restrict__ r_stop, const uint32_t *__restrict__ r_tag, uint32_t *__restrict__ r_cnt) {
+    // [warp][stage][field][k][lane]: the records of the next round arrive by cp.async while the current round is answered
+    __shared__ uint32_t stage[PL_THREADS / 32][2][3][PL_U][32];
     extern __shared__ __align__(32) uint8_t pl_smem[];
     const uint32_t b = blockIdx.x / ctas_per_bkt, chunk = blockIdx.x - b * ctas_per_bkt;
     const int64_t s0 = (int64_t)b << G.bshift;
@@ -250,20 +275,42 @@ part_lookup_kernel(LookupArgs A, int64_t n_seg, PartGeom G, uint32_t ctas_per_bk
         phys[j] = __shfl_sync(0xFFFFFFFFu, pb, j) - pre[j];   // record v of run j sits at phys[j] + v
     }
     const uint32_t sent = (1u << G.sb) - 1u;
-    for (uint32_t v0 = 0; v0 < total; v0 += PL_U * 32) {
-        uint32_t p[PL_U], qs[PL_U], qe[PL_U], loc[PL_U];
+    uint32_t p_next[PL_U], p[PL_U];
+    auto prefetch = [&](uint32_t v0, int st) {   // where the records of round v0 are, and their copies into stage st
 #pragma unroll
         for (int k = 0; k < PL_U; ++k) {
             const uint32_t v = v0 + k * 32 + lane;
             uint32_t ph = phys[0];
 #pragma unroll
             for (int j = 1; j < PL_WRUNS; ++j) ph = v >= pre[j] ? phys[j] : ph;
-            p[k] = ph + v;
-            loc[k] = sent;
+            p_next[k] = ph + v;
             if (v < total) {
-                qs[k] = ld_stream(r_start + p[k]);
-                qe[k] = ld_stream(r_stop + p[k]);
-                loc[k] = ld_stream(r_tag + p[k]) & sent;
+                cp_async4(&stage[warp][st][0][k][lane], r_start + p_next[k]);
+                cp_async4(&stage[warp][st][1][k][lane], r_stop + p_next[k]);
+                cp_async4(&stage[warp][st][2][k][lane], r_tag + p_next[k]);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    prefetch(0, 0);
+    int st = 0;
+    for (uint32_t v0 = 0; v0 < total; v0 += PL_U * 32, st ^= 1) {
+#pragma unroll
+        for (int k = 0; k < PL_U; ++k) p[k] = p_next[k];
+        if (v0 + PL_U * 32 < total) {
+            prefetch(v0 + PL_U * 32, st ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        uint32_t qs[PL_U], qe[PL_U], loc[PL_U];
+#pragma unroll
+        for (int k = 0; k < PL_U; ++k) {   // every lane reads back what it copied itself
+            loc[k] = sent;
+            if (v0 + k * 32 + lane < total) {
+                qs[k] = stage[warp][st][0][k][lane];
+                qe[k] = stage[warp][st][1][k][lane];
+                loc[k] = stage[warp][st][2][k][lane] & sent;
             }
         }
         uint2 eh[PL_U], el[PL_U];
@@ -282,7 +329,7 @@ part_lookup_kernel(LookupArgs A, int64_t n_seg, PartGeom G, uint32_t ctas_per_bk
             }
         }
         uint32_t res[PL_U];
-        uint32_t slow = 0;   // bit k: record k needs the raw array (a crowded bucket) or is not in the E8 form
+        uint32_t slow = 0;   // bits k / k + 8: the upper / lower endpoint of record k needs the raw array; bit k + 16: not the E8 form
 #pragma unroll
         for (int k = 0; k < PL_U; ++k) {
             res[k] = 0;
@@ -292,19 +339,28 @@ part_lookup_kernel(LookupArgs A, int64_t n_seg, PartGeom G, uint32_t ctas_per_bk
                 // beyond the sixth
                 const uint32_t mask = (1u << l) - 1u;
                 const uint32_t rem_h = (max(qe[k], lo[k]) - lo[k]) & mask, rem_l = (max(qs[k], lo[k]) - lo[k]) & mask;
-                const bool ov = ((eh[k].x & 0x8000u) && rem_h > (eh[k].y >> 24)) || ((qs[k] + 1u) && (el[k].x & 0x8000u) && rem_l > (el[k].y >> 24));
                 const uint32_t last = e8_finish(lo[k], l, eh[k], qe[k]);
                 const uint32_t first = (qs[k] + 1u) ? e8_finish(lo[k], l, el[k], qs[k]) : 0u;
                 res[k] = last - first;
-                slow |= ov ? (1u << k) : 0u;
+                if ((eh[k].x & 0x8000u) && rem_h > (eh[k].y >> 24)) slow |= 1u << k;
+                if ((qs[k] + 1u) && (el[k].x & 0x8000u) && rem_l > (el[k].y >> 24)) slow |= 1u << (k + 8);
             } else if (nbl[k] == PT_GENERAL) {
-                slow |= 1u << k;
+                slow |= 1u << (k + 16);
             }
         }
         if (__any_sync(0xFFFFFFFFu, slow != 0)) {   // once per round, not once per record
 #pragma unroll
-            for (int k = 0; k < PL_U; ++k)
-                if (slow & (1u << k)) res[k] = lookup_general(A, s0 + loc[k], qs[k], qe[k]);
+            for (int k = 0; k < PL_U; ++k) {
+                if (slow & (1u << (k + 16))) res[k] = lookup_general(A, s0 + loc[k], qs[k], qe[k]);
+                if (slow & (0x101u << k)) {
+                    const uint4 t = *reinterpret_cast<const uint4 *>(lite + loc[k]);
+                    const uint2 *ent = reinterpret_cast<const uint2 *>(A.cbuf + ((uint64_t)t.x | ((uint64_t)t.y << 32)));
+                    const uint32_t *a = A.starts + __ldg(A.iv_off + s0 + loc[k]);
+                    const uint32_t l = nbl[k] >> 16, nb = nbl[k] & 0xFFFFu;
+                    if (slow & (1u << k)) res[k] += e8_crowded_extra(a, ent, e8_entry_index(lo[k], l, nb, qe[k]), eh[k].x & 0x7FFFu, qe[k]);
+                    if (slow & (1u << (k + 8))) res[k] -= e8_crowded_extra(a, ent, e8_entry_index(lo[k], l, nb, qs[k]), el[k].x & 0x7FFFu, qs[k]);
+                }
+            }
         }
 #pragma unroll
         for (int k = 0; k < PL_U; ++k)

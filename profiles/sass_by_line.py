@@ -23,12 +23,17 @@ for ln in dis.splitlines():
         continue
     if re.match(r"\s+/\*[0-9a-f]{4}\*/", ln):
         lines.append(cur)
-raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kname.split("IL")[0]], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 h = rows[hi]
 ix = {n: i for i, n in enumerate(h)}
-body = [r for r in rows[hi + 1:] if len(r) >= len(h)]
+body = []
+for r in rows[hi + 1:]:          # the first launch of the kernel only (a report may hold several)
+    if r and r[0] == "Address":
+        break
+    if len(r) >= len(h):
+        body.append(r)
 if len(body) != len(lines):
     print(f"warning: {len(body)} SASS rows in the report vs {len(lines)} instructions in the cubin", file=sys.stderr)
 agg = collections.defaultdict(lambda: [0, 0, collections.Counter()])
