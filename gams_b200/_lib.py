@@ -51,6 +51,7 @@ def load() -> C.CDLL:
         "gams_cuda_ctx_num_devices": (i32, [vp]),
         "gams_cuda_set_zscore_mode": (i32, [vp, i32]),
         "gams_cuda_zscore_stats": (i32, [vp, vp, i32]),
+        "gams_cuda_set_gunzip_options": (i32, [vp, i32, i32]),
         "gams_cuda_host_alloc": (vp, [sz]),
         "gams_cuda_host_free": (None, [vp]),
         "gams_cuda_memcpy_probe": (i32, [vp, vp, sz, i32]),
@@ -77,6 +78,7 @@ def load() -> C.CDLL:
         "gams_cuda_gen_ctgs": (i32, [vp, i64, vp, vp, i32, i32, i32, u64, vp, vp, vp, vp]),
         "gams_cuda_gc_ranges": (i32, [vp, i64, vp, vp, i64, vp, vp, vp, vp]),
         "gams_cuda_sw_batch": (i32, [vp, i64, vp, vp, vp, i64, vp, vp, vp, i32, i32, i32] + [vp] * 9),
+        "gams_cuda_sw_count_batch": (i32, [vp, i64, vp, vp, vp, i64, vp, vp, vp, i32, i32, i32, vp, vp, vp] + [vp] * 10),
         "gams_cuda_count_overlaps": (i32, [vp, i64, vp, vp, vp, i64, vp, vp, vp, vp]),
         "gams_cuda_count_plan_create": (i32, [vp, i32, i64, vp, C.POINTER(vp)]),
         "gams_cuda_count_plan_destroy": (None, [vp]),

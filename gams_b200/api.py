@@ -50,6 +50,10 @@ class Context:
         """0 = certified filter + exact replay (default), 1 = replay every window, 2 = verify."""
         check(self._L.gams_cuda_set_zscore_mode(self._h, mode))
 
+    def set_gunzip_options(self, decoder=0, check_crc=True):
+        """decoder 0 = two-phase (default), 1 = one warp per blob; check_crc: verify the gzip trailer's CRC-32 as GzDecoder does."""
+        check(self._L.gams_cuda_set_gunzip_options(self._h, int(decoder), int(bool(check_crc))))
+
     def zscore_stats(self, reset=True):
         """(windows replayed because the certificate was inconclusive, verify mismatches)."""
         out = np.zeros(2, dtype=np.uint64)
@@ -268,8 +272,9 @@ def gc_ranges(ctx: Context, seq_concat, seq_off, q_ctg, q_from0, q_to0_excl) -> 
     return out
 
 
-def sw_batch(ctx: Context, seq_concat, seq_off, ctg_chr_start, f_ctg, f_start, f_end, size=100, max_=20, resize=500):
-    """Rows of `gams sw --action gc` for a batch of features → dict of arrays + row_off."""
+def sw_batch(ctx: Context, seq_concat, seq_off, ctg_chr_start, f_ctg, f_start, f_end, size=100, max_=20, resize=500, rg_index=None):
+    """Rows of `gams sw --action gc` for a batch of features → dict of arrays + row_off.  rg_index = (starts, stops, iv_off)
+    with segment c = the rg index of ctg c adds `--action count` (sw.rs:28-32): the rg_count column (data.rs:55)."""
     seq_concat, seq_off = _arr(seq_concat, np.uint8), _arr(seq_off, np.uint64)
     ctg_chr_start = _arr(ctg_chr_start, np.int32)
     f_ctg, f_start, f_end = _arr(f_ctg, np.uint32), _arr(f_start, np.int32), _arr(f_end, np.int32)
@@ -279,12 +284,21 @@ def sw_batch(ctx: Context, seq_concat, seq_off, ctg_chr_start, f_ctg, f_start, f
     ws, we, wd = (np.empty(cap, dtype=np.int32) for _ in range(3))
     wt = np.empty(cap, dtype=np.int8)
     gc, gm, gs, gv = (np.empty(cap, dtype=np.float32) for _ in range(4))
-    check(load().gams_cuda_sw_batch(ctx.handle, seq_off.size - 1, _p(seq_concat), _p(seq_off), _p(ctg_chr_start), nf,
-                                    _p(f_ctg), _p(f_start), _p(f_end), size, max_, resize, _p(row_off), _p(ws), _p(we),
-                                    _p(wt), _p(wd), _p(gc), _p(gm), _p(gs), _p(gv)))
+    if rg_index is None:
+        check(load().gams_cuda_sw_batch(ctx.handle, seq_off.size - 1, _p(seq_concat), _p(seq_off), _p(ctg_chr_start), nf,
+                                        _p(f_ctg), _p(f_start), _p(f_end), size, max_, resize, _p(row_off), _p(ws), _p(we),
+                                        _p(wt), _p(wd), _p(gc), _p(gm), _p(gs), _p(gv)))
+        n = int(row_off[-1])
+        return dict(row_off=row_off, start=ws[:n], end=we[:n], type=wt[:n], dist=wd[:n], gc=gc[:n], mean=gm[:n],
+                    sd=gs[:n], cv=gv[:n])
+    starts, stops, iv_off = _arr(rg_index[0], np.uint32), _arr(rg_index[1], np.uint32), _arr(rg_index[2], np.uint64)
+    rc = np.empty(cap, dtype=np.uint32)
+    check(load().gams_cuda_sw_count_batch(ctx.handle, seq_off.size - 1, _p(seq_concat), _p(seq_off), _p(ctg_chr_start), nf,
+                                          _p(f_ctg), _p(f_start), _p(f_end), size, max_, resize, _p(starts), _p(stops), _p(iv_off),
+                                          _p(row_off), _p(ws), _p(we), _p(wt), _p(wd), _p(gc), _p(gm), _p(gs), _p(gv), _p(rc)))
     n = int(row_off[-1])
     return dict(row_off=row_off, start=ws[:n], end=we[:n], type=wt[:n], dist=wd[:n], gc=gc[:n], mean=gm[:n],
-                sd=gs[:n], cv=gv[:n])
+                sd=gs[:n], cv=gv[:n], rg_count=rc[:n])
 
 
 # --------------------------------------------------------------- host-side format helpers (no GPU)

@@ -256,6 +256,8 @@ GAMS_API int32_t gams_cuda_create(const int32_t *device_ids, int32_t n_dev, gams
         }
     }
     if (const char *m = getenv("GAMS_CUDA_ZSCORE_MODE")) ctx->zscore_mode = atoi(m);
+    if (const char *m = getenv("GAMS_CUDA_GUNZIP_MODE")) ctx->gunzip_mode = atoi(m);
+    if (const char *m = getenv("GAMS_CUDA_GUNZIP_CRC")) ctx->gunzip_crc = atoi(m);
     *out = ctx.release();
     return GAMS_CUDA_OK;
 }
@@ -263,6 +265,13 @@ GAMS_API int32_t gams_cuda_create(const int32_t *device_ids, int32_t n_dev, gams
 GAMS_API int32_t gams_cuda_set_zscore_mode(gams_cuda_ctx *ctx, int32_t mode) {
     ARG_CHECK(ctx && mode >= 0 && mode <= 2, "set_zscore_mode: mode must be 0 (filter), 1 (replay) or 2 (verify)");
     ctx->zscore_mode = mode;
+    return GAMS_CUDA_OK;
+}
+
+GAMS_API int32_t gams_cuda_set_gunzip_options(gams_cuda_ctx *ctx, int32_t decoder, int32_t check_crc) {
+    ARG_CHECK(ctx && (decoder == 0 || decoder == 1) && (check_crc == 0 || check_crc == 1), "set_gunzip_options: decoder and check_crc are 0 or 1");
+    ctx->gunzip_mode = decoder;
+    ctx->gunzip_crc = check_crc;
     return GAMS_CUDA_OK;
 }
 
@@ -905,30 +914,67 @@ GAMS_API int32_t gams_cuda_count_overlaps(gams_cuda_ctx *ctx, int64_t n_seg, con
     const uint64_t n_iv = iv_off[n_seg] - iv_off[0];
     ARG_CHECK((starts && stops) || n_iv == 0, "count_overlaps: NULL index pointer");
     std::lock_guard<std::mutex> lk(ctx->mu);
-    // Queries are split evenly over the devices; every device gets the whole (small) index.
     const int n_dev = (int)std::min<int64_t>((int64_t)ctx->devs.size(), std::max<int64_t>(1, n_q / 65536));
+    // Several devices.  Queries grouped by ctg (q_seg non-decreasing: the order read_range's BTreeMap yields, utils.rs:39-79)
+    // shard BY CTG: device d gets a contiguous range of segments, their slice of the index and exactly the queries that name
+    // them — nothing is replicated and nothing is exchanged.  Queries in arbitrary order are split evenly and the
+    // index is replicated: it is small against 180 GB of HBM, and routing 10^8 queries to the owners of their ctgs would be
+    // an all-to-all the path does not otherwise need.
+    bool grouped = false;
+    std::vector<int64_t> qb((size_t)n_dev + 1, 0), sb((size_t)n_dev + 1, 0);
+    if (n_dev > 1) {
+        std::vector<int> ok((size_t)n_dev, 1);
+        run_on_devices(n_dev, [&](int d) -> int32_t {   // (host threads only: the order check of one slice each)
+            const int64_t q0 = n_q * d / n_dev, q1 = n_q * (d + 1) / n_dev;
+            int good = 1;
+            for (int64_t q = std::max<int64_t>(q0, 1); q < q1 && good; ++q) good = q_seg[q - 1] <= q_seg[q];
+            ok[d] = good;
+            return GAMS_CUDA_OK;
+        });
+        grouped = std::all_of(ok.begin(), ok.end(), [](int v) { return v != 0; });
+    }
+    if (grouped) {
+        auto clamp_seg = [&](int32_t v) { return (int64_t)std::min<int64_t>(std::max<int64_t>(v, 0), n_seg); };
+        qb[n_dev] = n_q, sb[n_dev] = n_seg;
+        for (int d = 1; d < n_dev; ++d) {
+            const int64_t q = n_q * d / n_dev;
+            const int32_t sv = q_seg[q];
+            qb[d] = std::max<int64_t>(qb[d - 1], std::lower_bound(q_seg, q_seg + n_q, sv) - q_seg);   // first query of that segment
+            sb[d] = std::max<int64_t>(sb[d - 1], clamp_seg(sv));
+        }
+    }
     return for_each_device(ctx, n_dev, [&](int d) -> int32_t {
-        const int64_t q0 = n_q * d / n_dev, q1 = n_q * (d + 1) / n_dev, nq = q1 - q0;
+        const int64_t q0 = grouped ? qb[d] : n_q * d / n_dev, q1 = grouped ? qb[d + 1] : n_q * (d + 1) / n_dev, nq = q1 - q0;
         if (nq == 0) return GAMS_CUDA_OK;
         PerDevice &pd = ctx->devs[d];
         DeviceGuard g(pd.device);
         gams_cuda_count_plan *plan = nullptr;
         trace_stage("count: enter");
-        int32_t rc = gams_cuda_count_plan_create(ctx, d, n_seg, iv_off, &plan);
+        // this device's view of the index: every segment outside [s_lo, s_hi) is empty
+        const int64_t s_lo = grouped ? sb[d] : 0, s_hi = grouped ? sb[d + 1] : n_seg;
+        const uint64_t iv_lo = iv_off[s_lo], iv_hi = iv_off[s_hi], n_iv_d = iv_hi - iv_lo;
+        std::vector<uint64_t> view;
+        const uint64_t *my_off = iv_off;
+        if (grouped) {
+            view.resize((size_t)n_seg + 1);
+            for (int64_t s = 0; s <= n_seg; ++s) view[s] = std::min(std::max(iv_off[s], iv_lo), iv_hi) - iv_lo;
+            my_off = view.data();
+        }
+        int32_t rc = gams_cuda_count_plan_create(ctx, d, n_seg, my_off, &plan);
         if (rc) return rc;
         trace_stage("count: plan_create");
         std::unique_ptr<gams_cuda_count_plan, void (*)(gams_cuda_count_plan *)> guard(plan, gams_cuda_count_plan_destroy);
-        if ((rc = pd.scratch[0].reserve(std::max<uint64_t>(n_iv, 1) * 4))) return rc;
-        if ((rc = pd.scratch[1].reserve(std::max<uint64_t>(n_iv, 1) * 4))) return rc;
+        if ((rc = pd.scratch[0].reserve(std::max<uint64_t>(n_iv_d, 1) * 4))) return rc;
+        if ((rc = pd.scratch[1].reserve(std::max<uint64_t>(n_iv_d, 1) * 4))) return rc;
         if ((rc = pd.scratch[2].reserve((uint64_t)nq * 4))) return rc;
         if ((rc = pd.scratch[3].reserve((uint64_t)nq * 4))) return rc;
         if ((rc = pd.scratch[4].reserve((uint64_t)nq * 4))) return rc;
         if ((rc = pd.scratch[5].reserve((uint64_t)nq * 4))) return rc;
         cudaStream_t st = pd.stream;
         uint32_t *d_st = pd.scratch[0].as<uint32_t>(), *d_sp = pd.scratch[1].as<uint32_t>();
-        if (n_iv) {
-            CUDA_TRY(cudaMemcpyAsync(d_st, starts + iv_off[0], n_iv * 4, cudaMemcpyHostToDevice, st));
-            CUDA_TRY(cudaMemcpyAsync(d_sp, stops + iv_off[0], n_iv * 4, cudaMemcpyHostToDevice, st));
+        if (n_iv_d) {
+            CUDA_TRY(cudaMemcpyAsync(d_st, starts + iv_lo, n_iv_d * 4, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(d_sp, stops + iv_lo, n_iv_d * 4, cudaMemcpyHostToDevice, st));
         }
         trace_stage("count: reserve + index H2D", st, true);
         // (the index tables - compact form or rank nodes - are built by the first launch that needs them)
@@ -962,7 +1008,7 @@ GAMS_API int32_t gams_cuda_count_overlaps(gams_cuda_ctx *ctx, int64_t n_seg, con
             CUDA_TRY(cudaMemcpyAsync(d_qe + a, q_stop + q0 + a, (uint64_t)m * 4, cudaMemcpyHostToDevice, pd.copy_in));
             CUDA_TRY(cudaEventRecord(ev_in[k], pd.copy_in));
             CUDA_TRY(cudaStreamWaitEvent(st, ev_in[k], 0));
-            if ((rc = launch_count_overlaps(plan, st, d_st, d_sp, m, d_qseg + a, d_qs + a, d_qe + a, 0, d_o + a))) return rc;
+            if ((rc = launch_count_overlaps(plan, st, d_st, d_sp, m, d_qseg + a, d_qs + a, d_qe + a, grouped ? 1 : 0, d_o + a))) return rc;
             CUDA_TRY(cudaEventRecord(ev_k[k], st));
             CUDA_TRY(cudaStreamWaitEvent(pd.copy_out, ev_k[k], 0));
             CUDA_TRY(cudaMemcpyAsync(out + q0 + a, d_o + a, (uint64_t)m * 4, cudaMemcpyDeviceToHost, pd.copy_out));
@@ -1282,12 +1328,22 @@ GAMS_API int32_t gams_cuda_peak_link_batch(gams_cuda_ctx *ctx, int64_t n_ctg, co
     return GAMS_CUDA_OK;
 }
 
-GAMS_API int32_t gams_cuda_sw_batch(gams_cuda_ctx *ctx, int64_t n_ctg, const uint8_t *seq_concat,
-                                    const uint64_t *seq_off, const int32_t *ctg_chr_start, int64_t n_feat,
-                                    const uint32_t *f_ctg, const int32_t *f_start, const int32_t *f_end, int32_t size,
-                                    int32_t max, int32_t resize, uint64_t *row_off, int32_t *w_start, int32_t *w_end,
-                                    int8_t *w_type, int32_t *w_dist, float *gc, float *gc_mean, float *gc_stddev,
-                                    float *gc_cv) {
+// one thread per feature: the ctg (= index segment) of each of its rows
+__global__ void __launch_bounds__(256)
+sw_row_seg_kernel(int64_t n_feat, const uint32_t *__restrict__ f_ctg, const uint64_t *__restrict__ row_off, int32_t *__restrict__ row_seg) {
+    const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_feat) return;
+    const int32_t c = (int32_t)f_ctg[f];
+    for (uint64_t r = row_off[f]; r < row_off[f + 1]; ++r) row_seg[r] = c;
+}
+
+static int32_t sw_batch_impl(gams_cuda_ctx *ctx, int64_t n_ctg, const uint8_t *seq_concat,
+                             const uint64_t *seq_off, const int32_t *ctg_chr_start, int64_t n_feat,
+                             const uint32_t *f_ctg, const int32_t *f_start, const int32_t *f_end, int32_t size,
+                             int32_t max, int32_t resize, uint64_t *row_off, int32_t *w_start, int32_t *w_end,
+                             int8_t *w_type, int32_t *w_dist, float *gc, float *gc_mean, float *gc_stddev,
+                             float *gc_cv, bool want_count, const uint32_t *starts, const uint32_t *stops,
+                             const uint64_t *iv_off, uint32_t *rg_count) {
     ARG_CHECK(ctx && seq_off && ctg_chr_start && row_off && n_ctg >= 0 && n_feat >= 0, "sw_batch: bad argument");
     ARG_CHECK(size > 0 && max >= 0 && resize > 0, "sw_batch: size/resize must be positive and max >= 0");
     trace_stage("sw: enter");
@@ -1295,6 +1351,14 @@ GAMS_API int32_t gams_cuda_sw_batch(gams_cuda_ctx *ctx, int64_t n_ctg, const uin
     if (n_feat == 0) return GAMS_CUDA_OK;
     ARG_CHECK(f_ctg && f_start && f_end && w_start && w_end && w_type && w_dist && gc && gc_mean && gc_stddev && gc_cv,
               "sw_batch: NULL feature/output pointer");
+    uint64_t n_iv = 0;
+    if (want_count) {
+        ARG_CHECK(iv_off && rg_count, "sw_count_batch: NULL index offsets / rg_count");
+        n_iv = iv_off[n_ctg] - iv_off[0];
+        ARG_CHECK((starts && stops) || n_iv == 0, "sw_count_batch: NULL index pointer");
+    }
+    bool grouped = true;   // features sorted by ctg (the reference walks ctg by ctg, sw.rs:95-99): rows are grouped by segment
+    for (int64_t f = 1; f < n_feat && grouped; ++f) grouped = f_ctg[f - 1] <= f_ctg[f];
     // Row counts are pure coordinate arithmetic (window.rs:3-56): 1 + #L + #R.
     for (int64_t f = 0; f < n_feat; ++f) {
         const uint32_t c = f_ctg[f];
@@ -1343,6 +1407,31 @@ GAMS_API int32_t gams_cuda_sw_batch(gams_cuda_ctx *ctx, int64_t n_ctg, const uin
                              d_row_off, n_rows, d_ws, d_we, d_wt, d_wd, d_g, d_m, d_s, d_c)))
         return rc;
     trace_stage("sw: kernel", st, true);
+    std::unique_ptr<gams_cuda_count_plan, void (*)(gams_cuda_count_plan *)> cplan(nullptr, gams_cuda_count_plan_destroy);
+    if (want_count && n_rows) {
+        // sw --action count (sw.rs:28-32, data.rs:55): gams::count_rg of every generated window against the rg index of its ctg,
+        // count(start, end) with the inclusive end as Lapper's exclusive stop exactly as locate.rs:136 calls it (utils.rs:35)
+        gams_cuda_count_plan *cp = nullptr;
+        if ((rc = gams_cuda_count_plan_create(ctx, 0, n_ctg, iv_off, &cp))) return rc;
+        cplan.reset(cp);
+        if ((rc = pd.scratch[3].reserve(std::max<uint64_t>(n_iv, 1) * 4))) return rc;
+        if ((rc = pd.scratch[4].reserve(std::max<uint64_t>(n_iv, 1) * 4))) return rc;
+        if ((rc = pd.scratch[5].reserve(n_rows * 8 + 64))) return rc;
+        uint32_t *d_st = pd.scratch[3].as<uint32_t>(), *d_sp = pd.scratch[4].as<uint32_t>();
+        int32_t *d_rseg = pd.scratch[5].as<int32_t>();
+        uint32_t *d_rcnt = reinterpret_cast<uint32_t *>(d_rseg + n_rows);
+        if (n_iv) {
+            CUDA_TRY(cudaMemcpyAsync(d_st, starts + iv_off[0], n_iv * 4, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(d_sp, stops + iv_off[0], n_iv * 4, cudaMemcpyHostToDevice, st));
+        }
+        sw_row_seg_kernel<<<(unsigned)((n_feat + 255) / 256), 256, 0, st>>>(n_feat, d_f_ctg, d_row_off, d_rseg);
+        CUDA_TRY(cudaGetLastError());
+        if ((rc = launch_count_overlaps(cp, st, d_st, d_sp, (int64_t)n_rows, d_rseg, reinterpret_cast<const uint32_t *>(d_ws),
+                                        reinterpret_cast<const uint32_t *>(d_we), grouped ? 1 : 0, d_rcnt)))
+            return rc;
+        CUDA_TRY(cudaMemcpyAsync(rg_count, d_rcnt, n_rows * 4, cudaMemcpyDeviceToHost, st));
+        trace_stage("sw: rg counts", st, true);
+    }
     CUDA_TRY(cudaMemcpyAsync(w_start, d_ws, n_rows * 4, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(w_end, d_we, n_rows * 4, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(w_dist, d_wd, n_rows * 4, cudaMemcpyDeviceToHost, st));
@@ -1354,4 +1443,25 @@ GAMS_API int32_t gams_cuda_sw_batch(gams_cuda_ctx *ctx, int64_t n_ctg, const uin
     CUDA_TRY(cudaStreamSynchronize(st));
     trace_stage("sw: D2H");
     return GAMS_CUDA_OK;
+}
+
+GAMS_API int32_t gams_cuda_sw_batch(gams_cuda_ctx *ctx, int64_t n_ctg, const uint8_t *seq_concat,
+                                    const uint64_t *seq_off, const int32_t *ctg_chr_start, int64_t n_feat,
+                                    const uint32_t *f_ctg, const int32_t *f_start, const int32_t *f_end, int32_t size,
+                                    int32_t max, int32_t resize, uint64_t *row_off, int32_t *w_start, int32_t *w_end,
+                                    int8_t *w_type, int32_t *w_dist, float *gc, float *gc_mean, float *gc_stddev,
+                                    float *gc_cv) {
+    return sw_batch_impl(ctx, n_ctg, seq_concat, seq_off, ctg_chr_start, n_feat, f_ctg, f_start, f_end, size, max, resize, row_off,
+                         w_start, w_end, w_type, w_dist, gc, gc_mean, gc_stddev, gc_cv, false, nullptr, nullptr, nullptr, nullptr);
+}
+
+GAMS_API int32_t gams_cuda_sw_count_batch(gams_cuda_ctx *ctx, int64_t n_ctg, const uint8_t *seq_concat,
+                                          const uint64_t *seq_off, const int32_t *ctg_chr_start, int64_t n_feat,
+                                          const uint32_t *f_ctg, const int32_t *f_start, const int32_t *f_end, int32_t size,
+                                          int32_t max, int32_t resize, const uint32_t *starts, const uint32_t *stops,
+                                          const uint64_t *iv_off, uint64_t *row_off, int32_t *w_start, int32_t *w_end,
+                                          int8_t *w_type, int32_t *w_dist, float *gc, float *gc_mean, float *gc_stddev,
+                                          float *gc_cv, uint32_t *rg_count) {
+    return sw_batch_impl(ctx, n_ctg, seq_concat, seq_off, ctg_chr_start, n_feat, f_ctg, f_start, f_end, size, max, resize, row_off,
+                         w_start, w_end, w_type, w_dist, gc, gc_mean, gc_stddev, gc_cv, true, starts, stops, iv_off, rg_count);
 }

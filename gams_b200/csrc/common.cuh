@@ -176,6 +176,8 @@ struct gams_cuda_ctx {
     std::vector<gams::PerDevice> devs;
     std::mutex mu;
     int zscore_mode = 0;  // 0 certified filter + exact replay, 1 replay everything, 2 verify
+    int gunzip_mode = 0;  // 0 two-phase decoder (inflate2.cu), 1 warp-per-blob decoder (inflate.cu); GAMS_CUDA_GUNZIP_MODE
+    int gunzip_crc = 1;   // verify the CRC-32 of the gzip trailer as flate2's GzDecoder does; GAMS_CUDA_GUNZIP_CRC=0 skips it
 };
 
 struct gams_cuda_wave_plan {

@@ -16,6 +16,7 @@
 // (L1/L2), no window is staged.
 // Bound: instruction issue (one symbol = one dependent chain), not HBM.
 #include "common.cuh"
+#include "inflate_common.cuh"
 
 namespace gams {
 
@@ -152,15 +153,16 @@ __device__ bool inf_build(const uint8_t *lens, int n, uint16_t *cnt, uint16_t *s
     return ok;
 }
 
-enum { INF_OK = 0, INF_EHEADER = 1, INF_ECODE = 2, INF_EOVERFLOW = 3, INF_EDIST = 4, INF_ESIZE = 5, INF_ETRUNC = 6 };
 
 __global__ void __launch_bounds__(INF_WARPS * 32, 12)
 gunzip_kernel(const uint8_t *__restrict__ gz, const uint64_t *__restrict__ gz_off, int64_t n_blob, uint8_t *out_base,
-              const uint64_t *__restrict__ out_off, int32_t *__restrict__ status) {
+              const uint64_t *__restrict__ out_off, int32_t *__restrict__ status, int32_t only_status,
+              uint32_t *__restrict__ crc_want) {
     __shared__ InfTables tabs[INF_WARPS];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int64_t blob = (int64_t)blockIdx.x * INF_WARPS + wib;
     if (blob >= n_blob) return;
+    if (only_status >= 0 && status[blob] != only_status) return;   // (warp-uniform)
     InfTables &T = tabs[wib];
     uint8_t *out = out_base + out_off[blob];
     const uint64_t cap64 = out_off[blob + 1] - out_off[blob], len64 = gz_off[blob + 1] - gz_off[blob];
@@ -342,21 +344,22 @@ gunzip_kernel(const uint8_t *__restrict__ gz, const uint64_t *__restrict__ gz_of
                 const uint8_t *q = in + t + 4;
                 const uint32_t isize = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24);
                 if (isize != pos || pos != cap) err = INF_ESIZE;
+                if (crc_want) crc_want[blob] = (uint32_t)q[-4] | ((uint32_t)q[-3] << 8) | ((uint32_t)q[-2] << 16) | ((uint32_t)q[-1] << 24);
             }
         }
         status[blob] = err;
     }
 }
 
-int32_t launch_gunzip(cudaStream_t st, const uint8_t *d_gz, const uint64_t *d_gz_off, int64_t n_blob, uint8_t *d_out,
-                      const uint64_t *d_out_off, int32_t *d_status) {
+int32_t launch_gunzip_only(cudaStream_t st, const uint8_t *d_gz, const uint64_t *d_gz_off, int64_t n_blob, uint8_t *d_out,
+                           const uint64_t *d_out_off, int32_t *d_status, int32_t only_status, uint32_t *d_crc_want) {
     if (n_blob == 0) return GAMS_CUDA_OK;
     const int64_t blocks = (n_blob + INF_WARPS - 1) / INF_WARPS;
     if (blocks >= (1ll << 31)) {
         set_error("gunzip: too many blobs for one launch");
         return GAMS_CUDA_EINVAL;
     }
-    gunzip_kernel<<<(unsigned)blocks, INF_WARPS * 32, 0, st>>>(d_gz, d_gz_off, n_blob, d_out, d_out_off, d_status);
+    gunzip_kernel<<<(unsigned)blocks, INF_WARPS * 32, 0, st>>>(d_gz, d_gz_off, n_blob, d_out, d_out_off, d_status, only_status, d_crc_want);
     CUDA_TRY(cudaGetLastError());
     return GAMS_CUDA_OK;
 }
@@ -381,8 +384,17 @@ GAMS_API int32_t gams_cuda_gunzip_dev(gams_cuda_ctx *ctx, int32_t dev_index, voi
                                       const uint64_t *d_gz_off, uint8_t *d_out, const uint64_t *d_out_off, int32_t *d_status) {
     ARG_CHECK(ctx && dev_index >= 0 && dev_index < (int32_t)ctx->devs.size(), "gunzip_dev: bad context / device index");
     ARG_CHECK(n_blob >= 0 && (n_blob == 0 || (d_gz && d_gz_off && d_out && d_out_off && d_status)), "gunzip_dev: NULL device pointer");
-    DeviceGuard g(ctx->devs[dev_index].device);
-    return launch_gunzip(static_cast<cudaStream_t>(stream), d_gz, d_gz_off, n_blob, d_out, d_out_off, d_status);
+    if (n_blob == 0) return GAMS_CUDA_OK;
+    PerDevice &pd = ctx->devs[dev_index];
+    DeviceGuard g(pd.device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // the token buffer of the two-phase decoder is sized from the total output: two offsets come back (the one sync of this call)
+    uint64_t ends[2] = {0, 0};
+    CUDA_TRY(cudaMemcpyAsync(&ends[0], d_out_off, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(&ends[1], d_out_off + n_blob, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    std::lock_guard<std::mutex> lk(ctx->mu);   // the decoder's scratch belongs to the context
+    return launch_gunzip2(pd, st, d_gz, d_gz_off, n_blob, d_out, d_out_off, d_status, ends[1] - ends[0], ctx->gunzip_mode, ctx->gunzip_crc != 0);
 }
 
 static int32_t gunzip_one(gams_cuda_ctx *ctx, int d, int64_t n_blob, const uint8_t *gz_concat, const uint64_t *gz_off,
@@ -407,7 +419,7 @@ static int32_t gunzip_one(gams_cuda_ctx *ctx, int d, int64_t n_blob, const uint8
     CUDA_TRY(cudaMemcpyAsync(d_gz, gz_concat + gz_off[0], n_in, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d_go, go.data(), (size_t)(n_blob + 1) * 8, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d_oo, oo.data(), (size_t)(n_blob + 1) * 8, cudaMemcpyHostToDevice, st));
-    if ((rc = launch_gunzip(st, d_gz, d_go, n_blob, d_out, d_oo, d_status))) return rc;
+    if ((rc = launch_gunzip2(pd, st, d_gz, d_go, n_blob, d_out, d_oo, d_status, n_out, ctx->gunzip_mode, ctx->gunzip_crc != 0))) return rc;
     if (n_out) CUDA_TRY(cudaMemcpyAsync(out_concat + out_off[0], d_out, n_out, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(status, d_status, (size_t)n_blob * 4, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));   // go / oo are locals

@@ -1,0 +1,849 @@
+// inflate2.cu — gunzip of a batch of `seq:{ctg}` blobs in two phases (Conn::get_seq -> decode_gz, src/libs/redis.rs:142-161).
+//
+// A deflate stream is bit-serial: where a symbol starts is known only after the one before it has been decoded.  The first
+// kernel of this library (inflate.cu: one warp per blob, every lane decodes the same symbol, the lanes share the copies) spends
+// ~100 dependent instructions per symbol on that chain, and the chain of the longest blob sets the time (128 ms per 3.1 Gbp).
+// Here the chain carries only what is serial:
+//   T inflate_tokens_kernel   one THREAD per blob: Huffman decoding only, no output byte is read or written.  A symbol becomes
+//                             a 32-bit token (literal byte, or length + distance, or a stored run); the tables of the thread
+//                             live in shared memory (2.4 KB, 16-bit entries); the bit window is a 64-bit register.  The chain
+//                             per symbol is: index -> table load -> field extraction -> shift.
+//   R inflate_resolve_kernel  one WARP per blob, 32 tokens at a time: output positions by a warp scan; then the batch's OUTPUT
+//                             BYTES are dealt to the lanes (byte b of the batch to lane b mod 32): the lane finds the token that
+//                             owns its byte (5 shuffle steps), loads the source byte and stores — 32 consecutive bytes per
+//                             store instruction.  A batch whose matches reach into the batch itself (distance shorter than
+//                             what the batch has produced: runs of N, tandem repeats) is resolved token by token instead.
+// And the chain is cut: a blob of more than 64 KB is decoded as up to TK_MAXP PARTS in parallel.  Where a part may start is
+// not recorded anywhere in a deflate stream, so it is found speculatively (S inflate_split_kernel: the first bit offset behind
+// the part's nominal start that parses as a complete dynamic block header — two complete Huffman codes make a false positive
+// a ~1e-6 event) and VERIFIED afterwards: the part before must end exactly there (R checks the whole chain; a blob whose
+// chain does not close is decoded again by the one-pass kernel, so speculation can cost time but never correctness).
+// The ISIZE trailer and the size the caller expects are checked by R; the CRC-32 of the trailer by crc32_kernel (below) when
+// the caller asks for it (flate2's GzDecoder verifies it, redis.rs:156-161).
+// A blob whose symbols do not fit its token budget (half a token per output byte + 64: anything that compresses worse than
+// 2 bytes per symbol, i.e. not a sequence) keeps status INF_ETOKENS and is decoded by the warp-per-blob kernel of inflate.cu.
+#include "common.cuh"
+#include "inflate_common.cuh"
+
+namespace gams {
+
+constexpr int TK_THREADS = 32;                 // one warp per CTA: 32 blobs
+constexpr int TK_LBITS = 9, TK_DBITS = 9;   // level-1 sequence data: 0.15 % of the literal/length codes and 0.4 % of the distance codes are longer
+// per-thread tables, 16-bit entries; the stride in 32-bit words is odd, so equal indices of different threads fall into
+// different banks
+struct TkTables {
+    uint16_t ltab[1 << TK_LBITS];   // bits 0-3 code length (0: longer than the index), 4-6 extra bits, 7-15 symbol (0..287)
+    uint16_t dtab[1 << TK_DBITS];   // bits 0-3 code length, 4-7 extra bits, 8-12 symbol (0..29), 13: invalid
+    uint16_t lcnt[16], dcnt[16];    // codes per length
+    uint16_t lfirst[16], dfirst[16];  // first canonical code of each length
+    uint16_t loffs[16], doffs[16];    // position of that code's symbol in lsym / dsym
+    uint16_t lsym[288];
+    uint8_t dsym[32];
+    uint8_t lens[320];
+    uint8_t ctab[128];              // code-length alphabet: symbol << 3 | code length (0: no such code)
+    uint8_t clen[20];
+};
+static_assert(sizeof(TkTables) % 4 == 0 && (sizeof(TkTables) / 4) % 2 == 1, "odd word stride");
+
+__constant__ uint16_t TK_LBASE[32] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258, 0, 0, 0};
+__constant__ uint8_t TK_LEXT[32] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0, 0, 0, 0};
+__constant__ uint16_t TK_DBASE[32] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577, 0, 0};
+__constant__ uint8_t TK_DEXT[32] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13, 0, 0};
+__constant__ uint8_t TK_CLORDER[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+
+// The bit window of one thread: three consecutive aligned words of the blob and a bit offset o < 32 into the first — 64 valid
+// bits from the current position in two funnel shifts, enough for a length and a distance symbol with their extra bits (48
+// bits at most) without a refill in between.  Two more words are loaded ahead, so a rotation never waits for memory, and the
+// cache line two lines further down is prefetched.
+struct TkWin {
+    const uint32_t *w;
+    uint32_t n_words, wi, mis;      // w0 w1 w2 = w[wi - 3 .. wi - 1], p0 p1 = w[wi], w[wi + 1]
+    uint32_t w0, w1, w2, p0, p1, o;
+    __device__ __forceinline__ uint32_t ld(uint32_t i) const { return i < n_words ? __ldg(w + i) : 0u; }
+    __device__ __forceinline__ void seek(uint32_t byte) {
+        const uint32_t a = mis + byte, k = a >> 2;
+        o = (a & 3u) * 8u;
+        w0 = ld(k), w1 = ld(k + 1), w2 = ld(k + 2), p0 = ld(k + 3), p1 = ld(k + 4);
+        wi = k + 3;
+    }
+    __device__ __forceinline__ uint32_t peek() const { return __funnelshift_r(w0, w1, o); }      // bits 0..31 from the position
+    __device__ __forceinline__ uint32_t peek_hi() const { return __funnelshift_r(w1, w2, o); }   // bits 32..63
+    __device__ __forceinline__ void rotate() {
+        w0 = w1, w1 = w2, w2 = p0, p0 = p1;
+        ++wi;
+        p1 = ld(wi + 1);
+#ifndef TK_NO_PREFETCH
+        if ((wi & 31u) == 0u && wi + 64u < n_words) asm volatile("prefetch.global.L1 [%0];" ::"l"(w + wi + 64));
+#endif
+    }
+    __device__ __forceinline__ void drop(uint32_t n) {   // n <= 63 (0 is a no-op).  (A branch-free rotation — selects and a
+        o += n;                                          //  predicated load — was measured slower: 120 vs 110 ms.)
+        if (o >= 32u) { rotate(); o -= 32u; }
+        if (o >= 32u) { rotate(); o -= 32u; }
+    }
+    __device__ __forceinline__ void seek_bit(uint64_t bit) {   // position given in bits from the blob's first byte
+        const uint64_t a = 8ull * mis + bit;
+        const uint32_t k = (uint32_t)(a >> 5);
+        o = (uint32_t)(a & 31u);
+        w0 = ld(k), w1 = ld(k + 1), w2 = ld(k + 2), p0 = ld(k + 3), p1 = ld(k + 4);
+        wi = k + 3;
+    }
+    __device__ __forceinline__ uint32_t bits(uint32_t n) { const uint32_t v = peek() & ((1u << n) - 1u); drop(n); return v; }   // n < 32
+    __device__ __forceinline__ uint64_t consumed_bits() const { return 32ull * (wi - 3) + o - 8ull * mis; }
+};
+
+__device__ __forceinline__ uint32_t tk_lit_entry(int s) {   // without the code length
+    return ((uint32_t)s << 7) | ((s >= 257 && s <= 285) ? (uint32_t)TK_LEXT[s - 257] << 4 : 0u);
+}
+__device__ __forceinline__ uint32_t tk_dist_entry(int s) {
+    return s > 29 ? (1u << 13) : (((uint32_t)s << 8) | ((uint32_t)TK_DEXT[s] << 4));
+}
+
+// canonical decoding of a code longer than the primary index (PBITS bits): position of the symbol in canonical order, or -1.
+// The code of length l is the top l bits of the bit-reversed window; it belongs to this length iff it lies in
+// [first[l], first[l] + cnt[l]).
+template <int PBITS>
+__device__ __forceinline__ int tk_decode_slow(uint32_t pk, const uint16_t *cnt, const uint16_t *first, const uint16_t *offs, uint32_t *code_len) {
+    const uint32_t c = __brev(pk);
+#pragma unroll 1
+    for (int len = PBITS + 1; len <= 15; ++len) {
+        const uint32_t idx = (c >> (32 - len)) - first[len];
+        if (idx < cnt[len]) {
+            *code_len = (uint32_t)len;
+            return (int)(offs[len] + idx);
+        }
+    }
+    *code_len = 15;
+    return -1;
+}
+
+// Warp-cooperative build of ONE thread's tables from its code lengths lens[0 .. n): lane L (1..15) owns the codes of length L.
+// false for an over-subscribed code.
+template <int PBITS, bool DIST>
+__device__ bool tk_build(const uint8_t *lens, int n, uint16_t *cnt, uint16_t *first, uint16_t *offs_, void *sym_, uint16_t *tab, int lane) {
+    for (int i = lane; i < (1 << PBITS); i += 32) tab[i] = 0;   // code length 0: longer than the index, or no such code
+    int mine = 0;
+    if (lane >= 1 && lane <= 15)
+        for (int s = 0; s < n; ++s) mine += (lens[s] == lane) ? 1 : 0;
+    if (lane < 16) cnt[lane] = (uint16_t)(lane ? mine : 0);
+    __syncwarp();
+    bool ok = true;
+    if (lane >= 1 && lane <= 15) {
+        int offs = 0, code = 0, left = 1;
+        for (int l = 1; l <= 15; ++l) {
+            left <<= 1;
+            left -= cnt[l];
+            if (left < 0) ok = false;
+        }
+        for (int l = 1; l < lane; ++l) {
+            offs += cnt[l];
+            code = (code + cnt[l]) << 1;
+        }
+        first[lane] = (uint16_t)code;
+        offs_[lane] = (uint16_t)offs;
+        int k = 0;
+        for (int s = 0; s < n && ok; ++s) {
+            if (lens[s] != lane) continue;
+            if (DIST) reinterpret_cast<uint8_t *>(sym_)[offs + k] = (uint8_t)s;
+            else reinterpret_cast<uint16_t *>(sym_)[offs + k] = (uint16_t)s;
+            if (lane <= PBITS) {
+                const uint32_t rev = __brev((uint32_t)(code + k)) >> (32 - lane);
+                const uint16_t e = (uint16_t)((DIST ? tk_dist_entry(s) : tk_lit_entry(s)) | (uint32_t)lane);
+                for (uint32_t j = rev; j < (1u << PBITS); j += (1u << lane)) tab[j] = e;
+            }
+            ++k;
+        }
+    }
+    ok = __all_sync(0xFFFFFFFFu, ok);
+    __syncwarp();
+    return ok;
+}
+
+constexpr int TK_MAXP = 8;                       // parts per blob at most
+constexpr uint32_t TK_NONE = 0xFFFFFFFFu;
+struct alignas(32) PartRec {
+    uint32_t start_bit;    // where the part starts (bits from the blob's first byte); TK_NONE: no such part
+    uint32_t end_bit;      // where it stopped: the start of the next part if the chain closes
+    uint32_t n_tok, out_len;
+    int32_t status;
+    uint32_t isize, crc;   // the trailer (last part only)
+    uint32_t flags;        // 1: the part decoded the final block
+};
+// How many parts for a blob of gz_len compressed bytes.  Finding a part's start costs a scan of ~10 KB of bit offsets, and the
+// time of the token phase is set by its LONGEST serial piece, so blobs are cut only down to the size of the typical piece:
+// the batch's mean blob (a chromosome's last ctg is up to twice the others: two parts), or 1/4096 of the batch when that is
+// larger (a batch of few, large blobs is cut into 8 parts each), never below 32 KB.
+__device__ __forceinline__ uint32_t tk_part_target(const uint64_t *__restrict__ gz_off, int64_t n_blob) {
+    const uint64_t total = gz_off[n_blob] - gz_off[0];
+    const uint64_t mean = total / (uint64_t)n_blob, share = total >> 12;
+    uint64_t t = mean < share ? mean : share;
+    t = t < 32768 ? 32768 : t;
+    return (uint32_t)(t > 0x7FFFFFFFull ? 0x7FFFFFFFull : t);
+}
+__device__ __forceinline__ uint32_t tk_parts(uint64_t gz_len, uint32_t target) {
+    const uint64_t p = (gz_len + target / 2) / target;
+    return (uint32_t)(p < 1 ? 1 : (p > (uint64_t)TK_MAXP ? (uint64_t)TK_MAXP : p));
+}
+
+// HLIT / HDIST / HCLEN and the code lengths of a dynamic block (the 3 header bits are already consumed): lens[0 .. hlit + hdist).
+// ctab / clen: scratch of 128 / 20 bytes.  false: not a valid header.
+__device__ bool tk_dynamic_header(TkWin &br, uint8_t *lens, uint8_t *ctab, uint8_t *clen, int *hlit_, int *hdist_) {
+    const int hlit = (int)br.bits(5) + 257, hdist = (int)br.bits(5) + 1, hclen = (int)br.bits(4) + 4;
+    if (hlit > 286 || hdist > 30) return false;
+    for (int i = 0; i < 19; ++i) clen[i] = 0;
+    for (int i = 0; i < hclen; ++i) clen[TK_CLORDER[i]] = (uint8_t)br.bits(3);
+    {   // the code-length code (lengths <= 7) as a 7-bit table
+        int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, next[8], left = 1;
+        for (int i = 0; i < 19; ++i) cnt[clen[i]]++;
+        cnt[0] = 0;
+        int code = 0;
+        for (int l = 1; l <= 7; ++l) {
+            left = (left << 1) - cnt[l];
+            code = (code + cnt[l - 1]) << 1;
+            next[l] = code;
+        }
+        if (left < 0) return false;
+        for (int i = 0; i < 128; ++i) ctab[i] = 0;
+        for (int i = 0; i < 19; ++i) {
+            const int l = clen[i];
+            if (!l) continue;
+            const uint32_t rev = __brev((uint32_t)next[l]++) >> (32 - l);
+            for (uint32_t j = rev; j < 128u; j += (1u << l)) ctab[j] = (uint8_t)((i << 3) | l);
+        }
+    }
+    int idx = 0, prev = 0;
+    const int total = hlit + hdist;
+    while (idx < total) {
+        const uint32_t ce = ctab[br.peek() & 127u];
+        if (!(ce & 7u)) return false;
+        br.drop(ce & 7u);
+        const int s = (int)(ce >> 3);
+        if (s < 16) {
+            lens[idx++] = (uint8_t)s;
+            prev = s;
+        } else {
+            int rep, v = 0;
+            if (s == 16) {
+                if (idx == 0) return false;
+                v = prev;
+                rep = 3 + (int)br.bits(2);
+            } else if (s == 17) rep = 3 + (int)br.bits(3);
+            else rep = 11 + (int)br.bits(7);
+            if (idx + rep > total) return false;
+            for (int k2 = 0; k2 < rep; ++k2) lens[idx + k2] = (uint8_t)v;
+            idx += rep;
+            prev = v;
+        }
+    }
+    if (lens[256] == 0) return false;      // no end-of-block code
+    *hlit_ = hlit;
+    *hdist_ = hdist;
+    return true;
+}
+
+// ---- phase S: where can a part start? ------------------------------------------------------------------------------------
+// One warp per (blob, part j >= 1): the bit offsets from the part's nominal start (j / parts of the compressed bytes) on are
+// screened 32 at a time — BTYPE = 2, HLIT / HDIST in range, the code-length code complete (Kraft sum exactly 1) — and a
+// survivor is parsed in full by one lane: both codes of the block must be complete too.
+constexpr int SP_WARPS = 4;
+struct SpScratch { uint8_t lens[320]; uint8_t ctab[128]; uint8_t clen[32]; };
+__global__ void __launch_bounds__(SP_WARPS * 32)
+inflate_split_kernel(const uint8_t *__restrict__ gz, const uint64_t *__restrict__ gz_off, int64_t n_blob, PartRec *__restrict__ rec) {
+    __shared__ SpScratch scr[SP_WARPS];
+    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t item = (int64_t)blockIdx.x * SP_WARPS + wib;
+    const int64_t blob = item / (TK_MAXP - 1);
+    const uint32_t j = (uint32_t)(item - blob * (TK_MAXP - 1)) + 1u;
+    if (blob >= n_blob) return;
+    const uint64_t len64 = gz_off[blob + 1] - gz_off[blob];
+    const uint32_t np = tk_parts(len64, tk_part_target(gz_off, n_blob));
+    PartRec &R = rec[blob * TK_MAXP + j];
+    uint32_t found = TK_NONE;
+    if (j < np && len64 < 0x10000000ull) {
+        const uint8_t *in = gz + gz_off[blob];
+        const uint32_t in_len = (uint32_t)len64, mis = (uint32_t)(reinterpret_cast<uintptr_t>(in) & 3u);
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(in - mis);
+        const uint32_t n_words = (mis + in_len + 3u) >> 2;
+        auto ldw = [&](uint32_t i) { return i < n_words ? __ldg(w + i) : 0u; };
+        const uint64_t bit0 = 8ull * ((uint64_t)in_len * j / np);
+        const uint64_t lim = min(8ull * ((uint64_t)in_len * (j + 1) / np), 8ull * (uint64_t)in_len - 160ull);
+        for (uint64_t base = bit0; base < lim && found == TK_NONE; base += 32) {
+            const uint64_t off = base + lane, a = 8ull * mis + off;
+            const uint32_t k = (uint32_t)(a >> 5), sh = (uint32_t)(a & 31u);
+            const uint32_t q0 = ldw(k), q1 = ldw(k + 1), q2 = ldw(k + 2), q3 = ldw(k + 3);
+            const uint32_t x0 = __funnelshift_r(q0, q1, sh), x1 = __funnelshift_r(q1, q2, sh), x2 = __funnelshift_r(q2, q3, sh);
+            const uint32_t type = (x0 >> 1) & 3u, hlit = (x0 >> 3) & 31u, hdist = (x0 >> 8) & 31u, hclen = ((x0 >> 13) & 15u) + 4u;
+            bool cand = off < lim && type == 2u && hlit <= 29u && hdist <= 29u;
+            if (cand) {
+                uint64_t v = ((uint64_t)x1 << 15) | (uint64_t)(x0 >> 17) | ((uint64_t)x2 << 47);   // the 3-bit lengths from bit 17 on
+                uint32_t kraft = 0;
+                for (uint32_t i = 0; i < hclen; ++i, v >>= 3) {
+                    const uint32_t l = (uint32_t)v & 7u;
+                    kraft += l ? (128u >> l) : 0u;
+                }
+                cand = kraft == 128u;
+            }
+            unsigned m = __ballot_sync(0xFFFFFFFFu, cand);
+            while (m && found == TK_NONE) {
+                const uint32_t c = (uint32_t)__ffs(m) - 1u;
+                m &= m - 1;
+                int ok = 0;
+                if (lane == c) {
+                    TkWin br;
+                    br.w = w, br.n_words = n_words, br.mis = mis;
+                    br.seek_bit(off + 3);
+                    int hl = 0, hd = 0;
+                    SpScratch &S = scr[wib];
+                    if (tk_dynamic_header(br, S.lens, S.ctab, S.clen, &hl, &hd)) {
+                        int l1 = 1 << 15, l2 = 1 << 15, nd = 0;
+                        for (int i = 0; i < hl; ++i) l1 -= S.lens[i] ? (1 << (15 - S.lens[i])) : 0;
+                        for (int i = 0; i < hd; ++i) l2 -= S.lens[hl + i] ? (1 << (15 - S.lens[hl + i])) : 0, nd += S.lens[hl + i] != 0;
+                        ok = l1 == 0 && (l2 == 0 || (nd == 1 && l2 == (1 << 14)));
+                    }
+                }
+                ok = __shfl_sync(0xFFFFFFFFu, ok, c);
+                if (ok) found = (uint32_t)(base + c);
+            }
+        }
+    }
+    if (lane == 0) R.start_bit = found;
+}
+
+enum { TS_HEADER = 0, TS_SYMBOLS = 1, TS_DONE = 2, TS_FINISHED = 3, TS_FETCH = 4 };
+constexpr int TK_GROUP = 8;
+
+// token: bits 0-8 length (0: literal, byte in bits 9-16; 3..258: match, distance in bits 9-24).
+// The 32 lanes decode 32 different streams, so the kernel is written to keep them CONVERGED: the symbol loop has one
+// branch-free body (a literal / length symbol and, predicated, the distance symbol behind it) that every lane executes in
+// lock step; what only some lanes need — a block header, a code longer than the table index, the trailer — runs in short
+// divergent sections between votes, and table builds are done by the whole warp for one lane at a time.  (Lanes that each
+// follow their own path share the warp's one instruction stream: a first version written as 32 independent loops took
+// 1 400 cycles per symbol.)
+__global__ void __launch_bounds__(TK_THREADS)
+inflate_tokens_kernel(const uint8_t *__restrict__ gz, const uint64_t *__restrict__ gz_off, int64_t n_blob,
+                      const uint64_t *__restrict__ out_off, uint32_t *__restrict__ tokens, PartRec *__restrict__ rec,
+                      unsigned long long *__restrict__ next_item) {
+    extern __shared__ __align__(16) uint8_t tk_smem[];
+    __shared__ uint16_t s_lbase[32], s_dbase[32];   // (constant memory would serialise the lanes' different indices)
+    const int lane = threadIdx.x;
+    s_lbase[lane] = TK_LBASE[lane];
+    s_dbase[lane] = TK_DBASE[lane];
+    __syncwarp();
+    TkTables *tabs = reinterpret_cast<TkTables *>(tk_smem);
+    TkTables &T = tabs[lane];
+    // The kernel is PERSISTENT: a lane that has finished a part takes the next (blob, part) off a global counter, so the 32
+    // lanes of a warp stay busy although parts differ in length (statically, a warp would wait for its longest part).
+    const uint64_t n_items = (uint64_t)n_blob * TK_MAXP;
+    const uint64_t ob = out_off[0];
+    const uint32_t target = tk_part_target(gz_off, n_blob);
+    // ---- the lane's current part
+    const uint8_t *in = gz;
+    PartRec *R = rec;
+    uint32_t part = 0, next_start = TK_NONE, my_start = 0, cap = 0, in_len = 0, tcap = 0;
+    uint32_t *tok = tokens;
+    uint32_t r_isize = 0, r_crc = 0, r_flags = 0, pos = 0, nt = 0;
+    int err = INF_OK, nlen = 288, ndist = 30;
+    bool last = false;
+    TkWin br;
+    br.w = reinterpret_cast<const uint32_t *>(gz), br.n_words = 0, br.mis = 0;
+    br.seek_bit(0);
+    int state = TS_FETCH;
+    auto fetch = [&]() {     // the next part that exists, or TS_DONE when the counter has run out
+        for (;;) {
+            const uint64_t item = atomicAdd(next_item, 1ull);
+            if (item >= n_items) { state = TS_DONE; return; }
+            // long blobs first would be better still; items run part-major so that the parts of one blob start together
+            const uint64_t blob = item % (uint64_t)n_blob;
+            part = (uint32_t)(item / (uint64_t)n_blob);
+            const uint64_t len64 = gz_off[blob + 1] - gz_off[blob], o0 = out_off[blob] - ob, cap64 = out_off[blob + 1] - out_off[blob];
+            const uint32_t np = tk_parts(len64, target);
+            R = rec + blob * TK_MAXP;
+            if (part >= np || (part > 0 && R[part].start_bit == TK_NONE)) continue;
+            next_start = TK_NONE;
+            for (uint32_t q = part + 1; q < np; ++q)
+                if (R[q].start_bit != TK_NONE) { next_start = R[q].start_bit; break; }
+            in = gz + gz_off[blob];
+            // the blob's token budget: half a token per output byte + 64 (the host sizes the buffer the same way), in equal shares
+            const uint64_t t0 = (o0 >> 1) + 64ull * blob, t1 = ((o0 + cap64) >> 1) + 64ull * (blob + 1);
+            const uint64_t ta = t0 + (t1 - t0) * part / np, tb = t0 + (t1 - t0) * (part + 1) / np;
+            tok = tokens + ta;
+            tcap = (uint32_t)min(tb - ta, (uint64_t)0xFFFFFFF0u);
+            err = INF_OK;
+            if (cap64 > 0xFFFFFF00ull || len64 > 0x0FFFFFFFull) err = INF_ESIZE;     // output positions and bit offsets are 32-bit
+            cap = (uint32_t)cap64, in_len = (uint32_t)len64;
+            br.mis = (uint32_t)(reinterpret_cast<uintptr_t>(in) & 3u);
+            br.w = reinterpret_cast<const uint32_t *>(in - br.mis);
+            br.n_words = (br.mis + in_len + 3u) >> 2;
+            uint32_t p = 10;     // gzip header (RFC 1952): part 0
+            if (!err && part == 0) {
+                if (in_len < 18 || in[0] != 0x1F || in[1] != 0x8B || in[2] != 8) err = INF_EHEADER;
+                else {
+                    const uint32_t flg = in[3];
+                    if (flg & 4u) p += 2 + (p + 2 <= in_len ? (uint32_t)in[p] | ((uint32_t)in[p + 1] << 8) : 0u);   // FEXTRA
+                    if (flg & 8u) { while (p < in_len && in[p]) ++p; ++p; }                                           // FNAME
+                    if (flg & 16u) { while (p < in_len && in[p]) ++p; ++p; }                                          // FCOMMENT
+                    if (flg & 2u) p += 2;                                                                             // FHCRC
+                    if (p + 8 > in_len) err = INF_EHEADER;
+                }
+            }
+            my_start = part == 0 ? 8u * p : R[part].start_bit;
+            r_isize = r_crc = r_flags = 0;
+            pos = nt = 0;
+            last = false;
+            br.seek_bit(err ? 0u : my_start);
+            state = err ? TS_FINISHED : TS_HEADER;
+            return;
+        }
+    };
+    __syncwarp();
+    for (;;) {
+        // ---- parts that are finished are recorded and replaced
+        if (__any_sync(0xFFFFFFFFu, state == TS_FINISHED || state == TS_FETCH)) {
+            while (state == TS_FINISHED || state == TS_FETCH) {
+                if (state == TS_FINISHED) {
+                    PartRec r;
+                    r.start_bit = my_start, r.end_bit = (uint32_t)br.consumed_bits(), r.n_tok = nt, r.out_len = pos, r.status = err;
+                    r.isize = r_isize, r.crc = r_crc, r.flags = r_flags;
+                    R[part] = r;
+                }
+                fetch();
+            }
+            __syncwarp();
+        }
+        // ---- block headers (per lane, divergent), then the table builds (the whole warp for one lane at a time)
+        if (__any_sync(0xFFFFFFFFu, state == TS_HEADER)) {
+            bool build = false;
+            int type = 0;
+            if (state == TS_HEADER && next_start != TK_NONE && (uint32_t)br.consumed_bits() >= next_start) {
+                state = TS_FINISHED;               // the next part takes over here (the resolver checks that it is exactly here)
+            } else if (state == TS_HEADER) {
+                const uint32_t hdr = br.bits(3);
+                last = hdr & 1u;
+                type = (int)(hdr >> 1);
+                if (type == 0) {   // stored: to the byte boundary, LEN / NLEN; the bytes become literal tokens
+                    br.drop((8u - (uint32_t)(br.consumed_bits() & 7u)) & 7u);
+                    const uint32_t ln = br.peek();
+                    br.drop(32);
+                    const uint32_t len = ln & 0xFFFFu;
+                    const uint32_t src = (uint32_t)(br.consumed_bits() >> 3);
+                    if ((len ^ 0xFFFFu) != (ln >> 16) || (uint64_t)src + len > in_len) err = INF_ETRUNC;
+                    else if ((uint64_t)pos + len > cap) err = INF_EOVERFLOW;
+                    else if ((uint64_t)nt + len > tcap) err = INF_ETOKENS;   // (stored data is not what this decoder is for)
+                    else {
+                        for (uint32_t i = 0; i < len; ++i) tok[nt++] = (uint32_t)in[src + i] << 9;
+                        pos += len;
+                        br.seek(src + len);
+                    }
+                    if (err) state = TS_FINISHED;   // else: the next block header, or the trailer (below)
+                } else if (type == 3) {
+                    err = INF_ECODE;
+                    state = TS_FINISHED;
+                } else if (type == 1) {
+                    for (int s = 0; s < 288; ++s) T.lens[s] = s < 144 ? 8 : s < 256 ? 9 : s < 280 ? 7 : 8;
+                    for (int s = 0; s < 30; ++s) T.lens[288 + s] = 5;
+                    nlen = 288, ndist = 30;
+                    build = true;
+                } else {
+                    int hl = 0, hd = 0;
+                    if (!tk_dynamic_header(br, T.lens, T.ctab, T.clen, &hl, &hd)) {
+                        err = INF_ECODE;
+                        state = TS_FINISHED;
+                    } else {
+                        nlen = hl, ndist = hd;
+                        build = true;
+                    }
+                }
+                if (state == TS_HEADER && !build && last) {   // a stored block was the last one: the trailer
+                    const uint64_t t = (br.consumed_bits() + 7) >> 3;
+                    if (t + 8 > in_len) err = INF_ETRUNC;
+                    else {
+                        const uint8_t *q = in + t;
+                        r_crc = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24);
+                        r_isize = (uint32_t)q[4] | ((uint32_t)q[5] << 8) | ((uint32_t)q[6] << 16) | ((uint32_t)q[7] << 24);
+                        r_flags = 1u;
+                    }
+                    state = TS_FINISHED;
+                }
+            }
+            __syncwarp();
+            unsigned bm = __ballot_sync(0xFFFFFFFFu, build);
+            while (bm) {
+                const int j = __ffs(bm) - 1;
+                bm &= bm - 1;
+                const int nl = __shfl_sync(0xFFFFFFFFu, nlen, j), nd = __shfl_sync(0xFFFFFFFFu, ndist, j), ty = __shfl_sync(0xFFFFFFFFu, type, j);
+                TkTables &Tj = tabs[j];
+                const bool ok1 = tk_build<TK_LBITS, false>(Tj.lens, nl, Tj.lcnt, Tj.lfirst, Tj.loffs, Tj.lsym, Tj.ltab, lane);
+                const bool ok2 = tk_build<TK_DBITS, true>(Tj.lens + (ty == 1 ? 288 : nl), nd, Tj.dcnt, Tj.dfirst, Tj.doffs, Tj.dsym, Tj.dtab, lane);
+                if (lane == j) {
+                    if (ok1 && ok2) state = TS_SYMBOLS;
+                    else err = INF_ECODE, state = TS_FINISHED;
+                }
+            }
+            __syncwarp();
+            continue;
+        }
+        if (__all_sync(0xFFFFFFFFu, state == TS_DONE)) break;
+        if (__any_sync(0xFFFFFFFFu, state == TS_FINISHED)) continue;
+        // ---- symbols: groups of TK_GROUP branch-free iterations that every lane executes in lock step.  A lane that meets
+        // something the body does not handle (a code longer than the table index, the end of a block, an error) commits
+        // nothing and sits out the rest of the group; the cases are sorted out between groups.
+        for (;;) {
+            bool act = state == TS_SYMBOLS, slowf = false, eobf = false;
+#pragma unroll 1
+            for (int it = 0; it < TK_GROUP; ++it) {
+                const uint32_t lo = br.peek(), hi = br.peek_hi();
+                const uint32_t e = T.ltab[lo & ((1u << TK_LBITS) - 1u)];
+                const uint32_t cl = e & 15u, sym = e >> 7, ex = (e >> 4) & 7u;
+                const bool is_lit = sym < 256u, is_len = sym - 257u < 29u;
+                const uint32_t len = s_lbase[(sym - 257u) & 31u] + ((lo >> cl) & ((1u << ex) - 1u));
+                const uint32_t n1 = cl + ex;                                  // <= 9 + 5
+                const uint32_t lo2 = __funnelshift_r(lo, hi, n1);             // the window behind the length symbol
+                const uint32_t d = T.dtab[lo2 & ((1u << TK_DBITS) - 1u)];
+                const uint32_t dl = d & 15u, dx = (d >> 4) & 15u;
+                const uint32_t dist = s_dbase[(d >> 8) & 31u] + ((lo2 >> dl) & ((1u << dx) - 1u));
+                const bool slow = cl == 0u || (is_len && dl == 0u);
+                const bool eob = !slow && sym == 256u;
+                int e2 = INF_OK;
+                if (!slow && !eob) {
+                    if (!(is_lit | is_len) || (is_len && (d & (1u << 13)))) e2 = INF_ECODE;
+                    else if (is_len && part == 0u && dist > pos) e2 = INF_EDIST;   // (later parts do not know their position: the resolver checks)
+                    else if (is_lit ? pos >= cap : len > cap - pos) e2 = INF_EOVERFLOW;
+                    else if (nt >= tcap) e2 = INF_ETOKENS;
+                }
+                const bool commit = act && !slow && e2 == INF_OK;
+                br.drop(commit ? n1 + (is_len ? dl + dx : 0u) : 0u);
+                if (commit && !eob) {
+                    tok[nt++] = is_lit ? sym << 9 : ((dist << 9) | len);
+                    pos += is_lit ? 1u : len;
+                }
+                if (act) {
+                    slowf = slow;
+                    eobf = eob;
+                    if (!slow && e2 != INF_OK) err = e2, state = TS_FINISHED;
+                    act = commit && !eob;
+                }
+            }
+            if (__any_sync(0xFFFFFFFFu, slowf)) {   // one symbol (and its distance) through the canonical decoder
+                if (slowf) {
+                    uint32_t pk = br.peek();
+                    uint32_t e = T.ltab[pk & ((1u << TK_LBITS) - 1u)];
+                    if ((e & 15u) == 0u) {
+                        uint32_t cl;
+                        const int k = tk_decode_slow<TK_LBITS>(pk, T.lcnt, T.lfirst, T.loffs, &cl);
+                        e = (k < 0 || k >= nlen) ? ((300u << 7) | 1u) : (tk_lit_entry(T.lsym[k]) | cl);
+                    }
+                    const uint32_t cl = e & 15u, sym = e >> 7, ex = (e >> 4) & 7u;
+                    const bool is_lit = sym < 256u, is_len = sym - 257u < 29u;
+                    const uint32_t len = s_lbase[(sym - 257u) & 31u] + ((pk >> cl) & ((1u << ex) - 1u));
+                    br.drop(cl + ex);
+                    uint32_t dist = 0;
+                    if (is_len) {
+                        pk = br.peek();
+                        uint32_t d = T.dtab[pk & ((1u << TK_DBITS) - 1u)];
+                        if ((d & 15u) == 0u) {
+                            uint32_t dl;
+                            const int k = tk_decode_slow<TK_DBITS>(pk, T.dcnt, T.dfirst, T.doffs, &dl);
+                            d = (k < 0 || k >= ndist) ? ((1u << 13) | 1u) : (tk_dist_entry(T.dsym[k]) | dl);
+                        }
+                        const uint32_t dl = d & 15u, dx = (d >> 4) & 15u;
+                        dist = s_dbase[(d >> 8) & 31u] + ((pk >> dl) & ((1u << dx) - 1u));
+                        br.drop(dl + dx);
+                        if (d & (1u << 13)) err = INF_ECODE;
+                        else if (part == 0u && dist > pos) err = INF_EDIST;
+                    }
+                    if (sym == 256u) eobf = true;
+                    else if (!(is_lit | is_len)) err = INF_ECODE;
+                    else if (!err) {
+                        if (is_lit ? pos >= cap : len > cap - pos) err = INF_EOVERFLOW;
+                        else if (nt >= tcap) err = INF_ETOKENS;
+                        else {
+                            tok[nt++] = is_lit ? sym << 9 : ((dist << 9) | len);
+                            pos += is_lit ? 1u : len;
+                        }
+                    }
+                    if (err) state = TS_FINISHED;
+                }
+                __syncwarp();
+            }
+            if (eobf && state == TS_SYMBOLS) {       // end of block
+                if (!last) state = TS_HEADER;
+                else {
+                    // the trailer: CRC-32 and ISIZE (RFC 1952: size of the original input modulo 2^32); the resolver compares
+                    const uint64_t t = (br.consumed_bits() + 7) >> 3;
+                    if (t + 8 > in_len) err = INF_ETRUNC;
+                    else {
+                        const uint8_t *q = in + t;
+                        r_crc = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24);
+                        r_isize = (uint32_t)q[4] | ((uint32_t)q[5] << 8) | ((uint32_t)q[6] << 16) | ((uint32_t)q[7] << 24);
+                        r_flags = 1u;
+                    }
+                    state = TS_FINISHED;
+                }
+            }
+            __syncwarp();
+            if (__any_sync(0xFFFFFFFFu, state == TS_HEADER || state == TS_FINISHED) || !__any_sync(0xFFFFFFFFu, state == TS_SYMBOLS)) break;
+        }
+    }
+}
+
+// ---- phase R ------------------------------------------------------------------------------------------------------
+constexpr int RS_WARPS = 4;
+__global__ void __launch_bounds__(RS_WARPS * 32)
+inflate_resolve_kernel(const uint64_t *__restrict__ gz_off, int64_t n_blob, uint8_t *out_base, const uint64_t *__restrict__ out_off,
+                       const uint32_t *__restrict__ tokens, const PartRec *__restrict__ rec, int32_t *__restrict__ status,
+                       uint32_t *__restrict__ crc_want) {
+    const uint32_t lane = threadIdx.x & 31;
+    const int64_t blob = (int64_t)blockIdx.x * RS_WARPS + (threadIdx.x >> 5);
+    if (blob >= n_blob) return;
+    const uint64_t o0 = out_off[blob], ob = out_off[0], cap = out_off[blob + 1] - o0;
+    const uint32_t np = tk_parts(gz_off[blob + 1] - gz_off[blob], tk_part_target(gz_off, n_blob));
+    const PartRec *R = rec + blob * TK_MAXP;
+    // ---- the chain: every part ended where the next one started, no part failed, the last one saw the final block, and the
+    // sizes agree with the trailer and with the caller.  Part 0 alone decides real errors (it starts at a known place);
+    // anything else that does not fit sends the blob to the one-pass decoder (INF_ETOKENS), which reports what is wrong.
+    int st = INF_OK;
+    {
+        uint32_t prev_end = 0, total = 0, last_flags = 0, isize = 0, crc = 0;
+        bool first = true;
+        for (uint32_t q = 0; q < np; ++q) {
+            const PartRec r = R[q];
+            if (q > 0 && r.start_bit == TK_NONE) continue;
+            if (r.status != INF_OK) { st = (q == 0 && r.status != INF_ETOKENS) ? r.status : INF_ETOKENS; break; }
+            if (!first && r.start_bit != prev_end) { st = INF_ETOKENS; break; }
+            first = false;
+            prev_end = r.end_bit;
+            total += r.out_len;
+            last_flags = r.flags, isize = r.isize, crc = r.crc;
+        }
+        if (st == INF_OK && !(last_flags & 1u)) st = INF_ETOKENS;
+        if (st == INF_OK && (isize != total || (uint64_t)total != cap)) st = np > 1 ? INF_ETOKENS : INF_ESIZE;
+        if (st == INF_OK && crc_want && lane == 0) crc_want[blob] = crc;
+    }
+    if (st != INF_OK) {
+        if (lane == 0) status[blob] = st;
+        return;
+    }
+    uint8_t *out = out_base + o0;
+    const uint64_t t0 = ((o0 - ob) >> 1) + 64ull * (uint64_t)blob, t1 = ((o0 - ob + cap) >> 1) + 64ull * (uint64_t)(blob + 1);
+    uint32_t P0 = 0;                                  // bytes written so far
+    bool bad = false;                                 // a distance that reaches before the start of the output
+    for (uint32_t q = 0; q < np; ++q) {
+      if (q > 0 && R[q].start_bit == TK_NONE) continue;
+      const uint32_t *tok = tokens + (t0 + (t1 - t0) * q / np);
+      const uint32_t nt = R[q].n_tok;
+      uint32_t t_next = lane < nt ? __ldg(tok + lane) : 0u;
+      for (uint32_t k0 = 0; k0 < nt; k0 += 32) {
+        const uint32_t t = t_next;
+        t_next = (k0 + 32 + lane < nt) ? __ldg(tok + k0 + 32 + lane) : 0u;   // the next batch's tokens are on their way
+        const bool have = k0 + lane < nt;
+        const uint32_t len_f = t & 511u, hi = t >> 9;
+        const uint32_t n_out = !have ? 0u : (len_f == 0u ? 1u : len_f);
+        uint32_t end = n_out;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, end, d);
+            if (lane >= (uint32_t)d) end += v;
+        }
+        const uint32_t total = __shfl_sync(0xFFFFFFFFu, end, 31);
+        const uint32_t start = end - n_out;          // inside the batch
+        if (have && len_f != 0u && hi > P0 + start) bad = true;
+        if ((uint64_t)P0 + total > cap) bad = true;
+        if (__any_sync(0xFFFFFFFFu, bad)) break;
+        // the batch's bytes, 32 at a time and in order: byte b belongs to the first token whose end is > b.  A match byte is
+        // copied from b - distance: before the round (written, possibly by an earlier round of this batch) or inside the
+        // round itself — then the lane follows the chain of sources (each step moves at least one byte back) until it
+        // leaves the round or ends at a literal.
+        const uint32_t rounds = (total + 31u) >> 5;
+        for (uint32_t r = 0; r < rounds; ++r) {
+            const uint32_t r0 = r * 32u, b = r0 + lane;
+            uint32_t lo = 0;
+#pragma unroll
+            for (int s = 16; s; s >>= 1) {
+                const uint32_t e_mid = __shfl_sync(0xFFFFFFFFu, end, (lo + s - 1) & 31u);
+                if (e_mid <= b) lo += s;
+            }
+            const uint32_t o_tok = __shfl_sync(0xFFFFFFFFu, t, lo & 31u);
+            const bool valid = b < total, lit = (o_tok & 511u) == 0u;
+            // src: where the byte comes from, relative to the batch (negative: before it); literals carry their value
+            int32_t src = (int32_t)b - (int32_t)(o_tok >> 9);
+            uint32_t val = o_tok >> 9;
+            bool done = !valid || lit;
+            while (__any_sync(0xFFFFFFFFu, !done && src >= (int32_t)r0)) {
+                const uint32_t from = (uint32_t)(src - (int32_t)r0) & 31u;
+                const int32_t s2 = __shfl_sync(0xFFFFFFFFu, src, from);
+                const uint32_t v2 = __shfl_sync(0xFFFFFFFFu, val, from);
+                const bool d2 = __shfl_sync(0xFFFFFFFFu, (int)done, from) != 0;
+                if (!done && src >= (int32_t)r0) {
+                    if (d2) val = v2, done = true;     // the source lane holds a literal (or a value it has already resolved)
+                    else src = s2;                     // its source is further back
+                }
+            }
+            if (valid) {
+                if (!done) val = out[(int64_t)P0 + src];
+                out[P0 + b] = (uint8_t)val;
+            }
+            __syncwarp();
+        }
+        P0 += total;
+      }
+      if (__any_sync(0xFFFFFFFFu, bad)) break;
+    }
+    const bool any_bad = __any_sync(0xFFFFFFFFu, bad);   // (the one-pass decoder names the error)
+    if (lane == 0) status[blob] = any_bad ? INF_ETOKENS : INF_OK;
+}
+
+// piece_off[b] = pieces of CRC_PIECE bytes before blob b (one CTA; blobs in chunks of 1024)
+constexpr uint32_t CRC_PIECE = 1024;
+__global__ void __launch_bounds__(1024)
+crc32_piece_offsets_kernel(const uint64_t *__restrict__ out_off, int64_t n_blob, uint64_t *__restrict__ piece_off) {
+    __shared__ uint64_t ws[32];
+    __shared__ uint64_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < n_blob; base += 1024) {
+        const int64_t b = base + threadIdx.x;
+        const uint64_t v = b < n_blob ? (out_off[b + 1] - out_off[b] + CRC_PIECE - 1) / CRC_PIECE : 0;
+        uint64_t inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint64_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+            if ((threadIdx.x & 31) >= d) inc += t;
+        }
+        if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = inc;
+        __syncthreads();
+        uint64_t before = carry;
+        for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) before += ws[w];
+        if (b < n_blob) piece_off[b] = before + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = before + inc;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) piece_off[n_blob] = carry;
+}
+
+// ---- CRC-32 (IEEE 802.3, reflected 0xEDB88320: RFC 1952 section 8) of every blob's output ----------------------------
+// One thread per 1024-byte piece, byte-wise through a 256-entry table in shared memory; then one thread per blob folds the
+// piece values in order: crc(A || B) = shift(crc(A), |B|) ^ crc(B) with the all-ones pre/post conditioning handled as zlib's
+// crc32_combine does, the shift by |B| zero bytes being a multiplication by x^(8|B|) mod P (square-and-multiply over the
+// bits of |B|, carry-less arithmetic in 32-bit registers).
+__device__ __forceinline__ uint32_t gf2_mulmod(uint32_t a, uint32_t b) {   // reflected polynomials, modulo 0xEDB88320
+    uint32_t p = 0;
+    for (int i = 0; i < 32; ++i) {
+        if (a & 0x80000000u) p ^= b;      // bit 31 of a reflected polynomial is the coefficient of x^0
+        a <<= 1;
+        b = (b >> 1) ^ ((b & 1u) ? 0xEDB88320u : 0u);   // b *= x
+    }
+    return p;
+}
+__device__ uint32_t gf2_x_pow_8n(uint64_t n_bytes) {   // x^(8 n) mod P, reflected
+    uint32_t r = 0x80000000u;                          // 1
+    uint32_t sq = 0x00800000u;                         // x^8: coefficient of x^8 is bit 31 - 8
+    while (n_bytes) {
+        if (n_bytes & 1ull) r = gf2_mulmod(r, sq);
+        sq = gf2_mulmod(sq, sq);
+        n_bytes >>= 1;
+    }
+    return r;
+}
+
+__global__ void __launch_bounds__(256)
+crc32_pieces_kernel(const uint8_t *__restrict__ data, const uint64_t *__restrict__ out_off, int64_t n_blob,
+                    const uint64_t *__restrict__ piece_off /* n_blob + 1 */, uint32_t *__restrict__ piece_crc) {
+    __shared__ uint32_t tab[256];
+    {
+        uint32_t c = threadIdx.x;
+        for (int k = 0; k < 8; ++k) c = (c >> 1) ^ ((c & 1u) ? 0xEDB88320u : 0u);
+        tab[threadIdx.x] = c;
+    }
+    __syncthreads();
+    const uint64_t n_piece = piece_off[n_blob];
+    for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_piece; p += (uint64_t)gridDim.x * blockDim.x) {
+        int64_t lo = 0, hi = n_blob;     // the blob of piece p
+        while (hi - lo > 1) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (piece_off[mid] <= p) lo = mid; else hi = mid;
+        }
+        const uint64_t b0 = out_off[lo] + (p - piece_off[lo]) * CRC_PIECE, b1 = min(b0 + CRC_PIECE, out_off[lo + 1]);
+        uint32_t c = 0;                  // raw register value (no pre / post inversion): pieces combine linearly
+        uint64_t i = b0;
+        for (; i < b1 && (i & 3ull); ++i) c = tab[(c ^ data[i]) & 0xFFu] ^ (c >> 8);
+        for (; i + 4 <= b1; i += 4) {
+            uint32_t w = *reinterpret_cast<const uint32_t *>(data + i);
+            c ^= w;
+            c = tab[c & 0xFFu] ^ (c >> 8);
+            c = tab[c & 0xFFu] ^ (c >> 8);
+            c = tab[c & 0xFFu] ^ (c >> 8);
+            c = tab[c & 0xFFu] ^ (c >> 8);
+        }
+        for (; i < b1; ++i) c = tab[(c ^ data[i]) & 0xFFu] ^ (c >> 8);
+        piece_crc[p] = c;
+    }
+}
+
+__global__ void __launch_bounds__(128)
+crc32_fold_kernel(const uint64_t *__restrict__ out_off, int64_t n_blob, const uint64_t *__restrict__ piece_off,
+                  const uint32_t *__restrict__ piece_crc, const uint32_t *__restrict__ crc_want, int32_t *__restrict__ status) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_blob || status[b] != INF_OK) return;
+    const uint64_t len = out_off[b + 1] - out_off[b], np = piece_off[b + 1] - piece_off[b];
+    const uint32_t xfull = gf2_x_pow_8n(CRC_PIECE);
+    // register after the whole message when it starts from all ones: the all-ones state advanced over len bytes, plus the
+    // pieces (each started from zero) advanced over what follows them
+    uint32_t c = 0;
+    for (uint64_t k = 0; k < np; ++k) {
+        const uint64_t plen = (k + 1 < np) ? CRC_PIECE : len - k * CRC_PIECE;
+        c = gf2_mulmod(c, plen == CRC_PIECE ? xfull : gf2_x_pow_8n(plen)) ^ piece_crc[piece_off[b] + k];
+    }
+    c ^= gf2_mulmod(0xFFFFFFFFu, gf2_x_pow_8n(len));
+    c ^= 0xFFFFFFFFu;
+    if (c != crc_want[b]) status[b] = INF_ECRC;
+}
+
+int32_t launch_gunzip2(PerDevice &pd, cudaStream_t st, const uint8_t *d_gz, const uint64_t *d_gz_off, int64_t n_blob, uint8_t *d_out,
+                       const uint64_t *d_out_off, int32_t *d_status, uint64_t total_out, int decoder, bool check_crc) {
+    if (n_blob == 0) return GAMS_CUDA_OK;
+    const int64_t items = n_blob * TK_MAXP, blocks = (items + TK_THREADS - 1) / TK_THREADS;
+    if (blocks >= (1ll << 31)) {
+        set_error("gunzip: too many blobs for one launch");
+        return GAMS_CUDA_EINVAL;
+    }
+    // scratch: tokens | part records | crc_want | piece_off | piece_crc
+    const uint64_t n_tokens = decoder == 0 ? (total_out >> 1) + 64ull * (uint64_t)(n_blob + 1) + 64 : 0;
+    const uint64_t n_piece_max = total_out / CRC_PIECE + (uint64_t)n_blob + 1;
+    const size_t o_rec = ((size_t)n_tokens * 4 + 31) & ~(size_t)31, o_crc = o_rec + (decoder == 0 ? (size_t)items * sizeof(PartRec) : 0),
+                 o_poff = (o_crc + (size_t)n_blob * 4 + 15) & ~(size_t)15, o_pcrc = o_poff + (size_t)(n_blob + 1) * 8,
+                 bytes = o_pcrc + (check_crc ? (size_t)n_piece_max * 4 : 0) + 64;
+    int32_t rc;
+    if ((rc = pd.scratch[7].reserve(bytes))) return rc;
+    uint8_t *base = pd.scratch[7].as<uint8_t>();
+    uint32_t *d_tok = reinterpret_cast<uint32_t *>(base), *d_crc = reinterpret_cast<uint32_t *>(base + o_crc),
+             *d_pcrc = reinterpret_cast<uint32_t *>(base + o_pcrc);
+    PartRec *d_rec = reinterpret_cast<PartRec *>(base + o_rec);
+    uint64_t *d_poff = reinterpret_cast<uint64_t *>(base + o_poff);
+    unsigned long long *d_counter = reinterpret_cast<unsigned long long *>(base + ((bytes - 16) & ~(size_t)7));
+    if (decoder == 0) {
+        const size_t smem = sizeof(TkTables) * TK_THREADS;
+        CUDA_TRY(cudaFuncSetAttribute(inflate_tokens_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int64_t s_items = n_blob * (TK_MAXP - 1);
+        inflate_split_kernel<<<(unsigned)((s_items + SP_WARPS - 1) / SP_WARPS), SP_WARPS * 32, 0, st>>>(d_gz, d_gz_off, n_blob, d_rec);
+        CUDA_TRY(cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), st));
+        const int64_t t_blocks = std::min<int64_t>(blocks, 148 * 2);   // two warps of 32 lanes per SM hold their tables in shared memory
+        inflate_tokens_kernel<<<(unsigned)t_blocks, TK_THREADS, smem, st>>>(d_gz, d_gz_off, n_blob, d_out_off, d_tok, d_rec, d_counter);
+        inflate_resolve_kernel<<<(unsigned)((n_blob + RS_WARPS - 1) / RS_WARPS), RS_WARPS * 32, 0, st>>>(d_gz_off, n_blob, d_out, d_out_off, d_tok,
+                                                                                                     d_rec, d_status, check_crc ? d_crc : nullptr);
+        // blobs that did not fit their token budget, or whose chain of parts did not close: the one-pass kernel
+        if ((rc = launch_gunzip_only(st, d_gz, d_gz_off, n_blob, d_out, d_out_off, d_status, INF_ETOKENS, check_crc ? d_crc : nullptr))) return rc;
+    } else {
+        if ((rc = launch_gunzip_only(st, d_gz, d_gz_off, n_blob, d_out, d_out_off, d_status, -1, check_crc ? d_crc : nullptr))) return rc;
+    }
+    if (check_crc) {
+        crc32_piece_offsets_kernel<<<1, 1024, 0, st>>>(d_out_off, n_blob, d_poff);
+        const unsigned pb = (unsigned)std::min<uint64_t>((n_piece_max + 255) / 256, 148ull * 16);
+        crc32_pieces_kernel<<<pb, 256, 0, st>>>(d_out, d_out_off, n_blob, d_poff, d_pcrc);
+        crc32_fold_kernel<<<(unsigned)((n_blob + 127) / 128), 128, 0, st>>>(d_out_off, n_blob, d_poff, d_pcrc, d_crc, d_status);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return GAMS_CUDA_OK;
+}
+
+}  // namespace gams

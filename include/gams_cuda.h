@@ -220,6 +220,21 @@ int32_t gams_cuda_sw_batch(gams_cuda_ctx *ctx, int64_t n_ctg, const uint8_t *seq
                            int32_t *w_start, int32_t *w_end, int8_t *w_type, int32_t *w_dist,
                            float *gc, float *gc_mean, float *gc_stddev, float *gc_cv);
 
+/* `gams sw --action gc --action count` (src/cmd_gams/sw.rs:22-35): the rows of gams_cuda_sw_batch plus the rg_count column of
+ * gams::Sw (src/libs/data.rs:55, printed last by its Display, data.rs:72-82).  The reference accepts the action and leaves the
+ * column empty (sw.rs:155-184 never fills rg_count); what the action names is gams::count_rg (src/libs/utils.rs:24-36) of every
+ * generated window against the rg index of its ctg, called as locate.rs:136 calls it:
+ *   rg_count[row] = lower_bound(starts_c, w_end) - lower_bound(stops_c, w_start + 1)
+ * starts / stops / iv_off: the rg index as gams_cuda_count_overlaps takes it, segment c = ctg c (an empty segment counts 0).
+ * Features sorted by ctg (the order sw walks them in, sw.rs:95-99, 141) take the staged kernel; any other order works too. */
+int32_t gams_cuda_sw_count_batch(gams_cuda_ctx *ctx, int64_t n_ctg, const uint8_t *seq_concat,
+                                 const uint64_t *seq_off, const int32_t *ctg_chr_start, int64_t n_feat,
+                                 const uint32_t *f_ctg, const int32_t *f_start, const int32_t *f_end,
+                                 int32_t size, int32_t max, int32_t resize, const uint32_t *starts,
+                                 const uint32_t *stops, const uint64_t *iv_off, uint64_t *row_off,
+                                 int32_t *w_start, int32_t *w_end, int8_t *w_type, int32_t *w_dist,
+                                 float *gc, float *gc_mean, float *gc_stddev, float *gc_cv, uint32_t *rg_count);
+
 /* ---------------------------------------------------------------- overlap counting --------- */
 /* Replaces the count loop of locate::execute, src/cmd_gams/locate.rs:111-141, i.e.
  * gams::count_rg (src/libs/utils.rs:24-36) -> rust_lapper::Lapper::count(start, stop):
@@ -256,13 +271,20 @@ void gams_cuda_count_plan_invalidate(gams_cuda_count_plan *plan);
  * device: one gzip member (RFC 1952, deflate RFC 1951: stored / fixed / dynamic blocks) per blob, blobs back to back in
  * gz_concat at gz_off[n_blob + 1].  Blob i inflates to out_concat[out_off[i] .. out_off[i+1]); the caller knows the sizes
  * (ctg lengths) or reads them from the trailers with gams_cuda_gz_sizes.  Like GzDecoder only the first member of a blob is
- * read.  ISIZE and the expected size are checked; the CRC-32 of the trailer is NOT verified (GzDecoder does verify it).
+ * read.  ISIZE, the expected size and the CRC-32 of the trailer are checked, as GzDecoder checks them (decode_gz(..).unwrap()
+ * panics on a mismatch, redis.rs:144); gams_cuda_set_gunzip_options can switch the CRC pass off.
  * status[i]: 0 ok, 1 bad gzip header, 2 invalid code / block, 3 output larger than expected, 4 distance before the start,
- * 5 size mismatch, 6 truncated input.  Returns GAMS_CUDA_EINVAL if any blob failed (the good ones are still written). */
+ * 5 size mismatch, 6 truncated input, 7 CRC-32 mismatch.  Returns GAMS_CUDA_EINVAL if any blob failed (the good ones are
+ * still written). */
 int32_t gams_cuda_gz_sizes(int64_t n_blob, const uint8_t *gz_concat, const uint64_t *gz_off, uint64_t *out_len);
 int32_t gams_cuda_gunzip_batch(gams_cuda_ctx *ctx, int64_t n_blob, const uint8_t *gz_concat, const uint64_t *gz_off,
                                const uint64_t *out_off, uint8_t *out_concat, int32_t *status);
-/* Device API: all pointers device memory (offsets relative to d_gz / d_out), asynchronous on `stream`.  The reader loads
+/* decoder: 0 = two-phase (one thread per blob turns the Huffman stream into tokens, one warp per blob turns tokens into bytes;
+ * default), 1 = one warp per blob in a single pass (the round-1 kernel; also what a blob falls back to when it compresses worse
+ * than 2 bytes per deflate symbol).  check_crc: 1 = verify the CRC-32 (default), 0 = skip that pass.  Results are identical. */
+int32_t gams_cuda_set_gunzip_options(gams_cuda_ctx *ctx, int32_t decoder, int32_t check_crc);
+/* Device API: all pointers device memory (offsets relative to d_gz / d_out), enqueued on `stream` (which is synchronised once
+ * at entry: the total output size comes back to size the decoder's scratch; one call per context device at a time).  The reader loads
  * aligned 32-bit words: the allocation behind d_gz must be readable from d_gz rounded down to a multiple of 4 up to the
  * end rounded up to a multiple of 4 (any cudaMalloc'ed buffer is). */
 int32_t gams_cuda_gunzip_dev(gams_cuda_ctx *ctx, int32_t dev_index, void *stream, int64_t n_blob, const uint8_t *d_gz,

@@ -44,6 +44,7 @@ extern "C" {
     pub fn gams_cuda_memcpy_probe(ctx: *mut gams_cuda_ctx, host: *mut c_void, bytes: usize, kind: i32) -> i32;
     pub fn gams_cuda_set_zscore_mode(ctx: *mut gams_cuda_ctx, mode: i32) -> i32;
     pub fn gams_cuda_zscore_stats(ctx: *mut gams_cuda_ctx, out2: *mut u64, reset: i32) -> i32;
+    pub fn gams_cuda_set_gunzip_options(ctx: *mut gams_cuda_ctx, decoder: i32, check_crc: i32) -> i32;
 
     pub fn gams_cuda_wave_nwin(ctg_len: i64, size: i32, step: i32) -> i64;
     pub fn gams_cuda_wave_win_offsets(n_ctg: i64, seq_off: *const u64, size: i32, step: i32, win_off: *mut u64) -> i32;
@@ -116,6 +117,14 @@ extern "C" {
         n_feat: i64, f_ctg: *const u32, f_start: *const i32, f_end: *const i32, size: i32, max: i32, resize: i32,
         row_off: *mut u64, w_start: *mut i32, w_end: *mut i32, w_type: *mut i8, w_dist: *mut i32, gc: *mut f32,
         gc_mean: *mut f32, gc_stddev: *mut f32, gc_cv: *mut f32,
+    ) -> i32;
+
+    pub fn gams_cuda_sw_count_batch(
+        ctx: *mut gams_cuda_ctx, n_ctg: i64, seq_concat: *const u8, seq_off: *const u64, ctg_chr_start: *const i32,
+        n_feat: i64, f_ctg: *const u32, f_start: *const i32, f_end: *const i32, size: i32, max: i32, resize: i32,
+        starts: *const u32, stops: *const u32, iv_off: *const u64, row_off: *mut u64, w_start: *mut i32, w_end: *mut i32,
+        w_type: *mut i8, w_dist: *mut i32, gc: *mut f32, gc_mean: *mut f32, gc_stddev: *mut f32, gc_cv: *mut f32,
+        rg_count: *mut u32,
     ) -> i32;
 
     pub fn gams_cuda_count_overlaps(

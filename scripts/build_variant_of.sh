@@ -8,6 +8,6 @@ base=${file%.cu}
 mkdir -p build/variants /tmp/variant_$name
 fm=""; case $base in zscore|gc_wave_fused|peaks|ranges) fm="-fmad=false";; esac
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-fvisibility=hidden $fm -I. "$@" -c $file -o /tmp/variant_$name/v.o
-objs=""; for o in api gc_window gc_wave_fused zscore overlap overlap_part ranges peaks gen idx_build count_windows inflate parse host; do if [ $o = $base ]; then objs="$objs /tmp/variant_$name/v.o"; else objs="$objs build/$o.o"; fi; done
+objs=""; for o in api gc_window gc_wave_fused zscore overlap overlap_part ranges peaks gen idx_build count_windows inflate inflate2 parse host; do if [ $o = $base ]; then objs="$objs /tmp/variant_$name/v.o"; else objs="$objs build/$o.o"; fi; done
 nvcc -gencode arch=compute_100a,code=sm_100a -shared -o build/variants/lib_$name.so $objs -Xlinker --exclude-libs,ALL
 echo built build/variants/lib_$name.so

@@ -3,6 +3,7 @@ import sys, time, zlib
 from concurrent.futures import ThreadPoolExecutor
 import ctypes as C
 import numpy as np, torch
+sys.path.insert(0, str(__import__("pathlib").Path(__file__).resolve().parent.parent))
 from gams_b200 import api, synth, _lib
 import bench
 
@@ -10,7 +11,7 @@ n = int(float(sys.argv[1])) if len(sys.argv) > 1 else int(3.1e9)
 L = _lib.load()
 dev = torch.device("cuda", 0)
 ctx = api.Context([0])
-seq_off, _ = bench.layout(n)
+seq_off, _ = bench.layout(n)  # noqa
 n_ctg = seq_off.size - 1
 d_seq = synth.genome_torch(n, seed=20240613, device=dev, capacity=n + 64)
 h = d_seq[:n].cpu().numpy()
@@ -33,8 +34,12 @@ def run():
 run(); torch.cuda.synchronize()
 assert int(d_st.abs().sum()) == 0 and torch.equal(d_out[:n], d_seq[:n])
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-for _ in range(3): run()
-e1.record(); torch.cuda.synchronize()
-ms = e0.elapsed_time(e1) / 3
-print(f"gunzip_dev: {ms:.2f} ms per {n / 1e9:.2f} Gbp = {n / ms / 1e6:.1f} Gbp/s out, {cat.size / ms / 1e6:.1f} GB/s in; bit-exact")
+for dec, crc in ((0, True), (0, False), (1, False)):
+    ctx.set_gunzip_options(dec, crc)
+    run(); torch.cuda.synchronize()
+    assert int(d_st.abs().sum()) == 0 and torch.equal(d_out[:n], d_seq[:n])
+    e0.record()
+    for _ in range(3): run()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    print(f"gunzip_dev decoder {dec} crc {crc}: {ms:.2f} ms per {n / 1e9:.2f} Gbp = {n / ms / 1e6:.1f} Gbp/s out, {cat.size / ms / 1e6:.1f} GB/s in; bit-exact")

@@ -168,3 +168,155 @@ def test_thresholding_extreme_magnitudes(ctx, orc, infl):
     # the reference really gives no signal at all once the squares overflow
     with np.errstate(all="ignore"):
         assert not orc.thresholding_algo(series["N(0,1e25)"], lag, 3.0, 1.0).any()
+
+
+# --------------------------------------------------------------- sw --action count: rg_count per sw row
+def _sw_count_reference(orc, ctgs, idx_rg, f_ctg, f_s, f_e, size=100, max_=20, resize=500):
+    """sw.rs:141-191 per feature with the rg_count column filled by gams::count_rg (utils.rs:24-36) as locate.rs:136 calls it."""
+    rows = []
+    for f in range(len(f_ctg)):
+        c = ctgs[f_ctg[f]]
+        ref = orc.sw_feature(c[4], c[2], c[3], f_s[f], f_e[f], size, max_, resize)
+        cnt = [orc.count_rg(idx_rg, c[0], (c[1], "", int(s), int(e))) for s, e in zip(ref["start"], ref["end"])]
+        rows.append((ref, np.asarray(cnt, dtype=np.uint32)))
+    return rows
+
+
+@pytest.mark.parametrize("order", ["by_ctg", "shuffled"])
+def test_sw_count_batch_fixture(ctx, orc, s288c, order):
+    """`gams sw --action gc --action count` for the spo11 features against the SK1 SNP index of tests/S288c: every gc column as
+    gams_cuda_sw_batch gives it, rg_count = count_rg of the row's window (oracle: sw_feature composed with count_rg)."""
+    from conftest import cut_ctgs
+    ctgs = cut_ctgs(orc, s288c, 100000)
+    idx_ctg = orc.build_idx_ctg([c[:4] for c in ctgs])
+    idx_rg = orc.build_idx_rg(orc.read_range(bytes(s288c["snp_rg"]).decode().splitlines(), idx_ctg))
+    lps = [idx_rg.get(c[0], orc.lapper_new([])) for c in ctgs]
+    starts = np.concatenate([lp["starts"] for lp in lps]).astype(np.uint32)
+    stops = np.concatenate([lp["stops"] for lp in lps]).astype(np.uint32)
+    iv_off = np.concatenate(([0], np.cumsum([lp["starts"].size for lp in lps]))).astype(np.uint64)
+    feats = orc.read_range(bytes(s288c["spo11_rg"]).decode().splitlines(), idx_ctg)
+    cat, off = orc.pack_ctgs([c[4] for c in ctgs])
+    f_ctg, f_s, f_e = [], [], []
+    for k, c in enumerate(ctgs):
+        for rg in feats.get(c[0], []):
+            f_ctg.append(k), f_s.append(rg[2]), f_e.append(rg[3])
+        for s, e in ((c[2], c[2]), (c[3], c[3]), (c[2], c[2] + 49), (c[3] - 20, c[3]), (c[2] + 1000, c[2] + 1001), (c[2], c[3])):
+            f_ctg.append(k), f_s.append(s), f_e.append(e)
+    if order == "shuffled":
+        perm = np.random.default_rng(5).permutation(len(f_ctg))
+        f_ctg, f_s, f_e = [f_ctg[i] for i in perm], [f_s[i] for i in perm], [f_e[i] for i in perm]
+    r = api.sw_batch(ctx, cat, off, [c[2] for c in ctgs], f_ctg, f_s, f_e, rg_index=(starts, stops, iv_off))
+    plain = api.sw_batch(ctx, cat, off, [c[2] for c in ctgs], f_ctg, f_s, f_e)
+    for key in ("start", "end", "type", "dist"):
+        _eq(f"sw_count {key} vs sw_batch", r[key], plain[key])
+    for key in ("gc", "mean", "sd", "cv"):
+        _eq(f"sw_count {key} vs sw_batch", r[key].view(np.uint32), plain[key].view(np.uint32))
+    assert int(r["row_off"][-1]) > 2000 and int(r["rg_count"].sum()) > 0
+    for f, (ref, cnt) in enumerate(_sw_count_reference(orc, ctgs, idx_rg, f_ctg, f_s, f_e)):
+        a, b = int(r["row_off"][f]), int(r["row_off"][f + 1])
+        assert b - a == len(ref["gc"])
+        _eq(f"rg_count feature {f}", r["rg_count"][a:b], cnt)
+        _eq(f"gc feature {f}", r["gc"][a:b].view(np.uint32), ref["gc"].view(np.uint32))
+
+
+def test_sw_count_batch_synthetic_c3_shape(ctx, orc):
+    """The configs[2] shape at small scale: point features on ragged ctgs, SNP and range rgs, ctgs without any rg."""
+    rng = np.random.default_rng(41)
+    g = synth.genome(1_500_000, seed=42)
+    cuts = [0, 300_000, 300_050, 900_001, 1_500_000]
+    seqs = [g[a:b] for a, b in zip(cuts[:-1], cuts[1:])]
+    chr_start = [1, 300_001, 1, 600_000]
+    lens = [s.size for s in seqs]
+    cat, off = orc.pack_ctgs(seqs)
+    for max_len in (1, 200):
+        st, sp, ioff = synth.rg_index(lens, [9000, 0, 20000, 15000], seed=43, max_len=max_len)
+        # the index holds chr coordinates: shift every segment to its ctg's chr_start
+        for c in range(4):
+            a, b = int(ioff[c]), int(ioff[c + 1])
+            st[a:b] += np.uint32(chr_start[c] - 1)
+            sp[a:b] += np.uint32(chr_start[c] - 1)
+        n_feat = 3000
+        f_ctg = np.sort(rng.integers(0, 4, n_feat)).astype(np.uint32)
+        f_s = np.array([chr_start[c] + int(rng.integers(0, lens[c])) for c in f_ctg], dtype=np.int32)
+        f_e = np.minimum(f_s + rng.integers(0, 3, n_feat), [chr_start[c] + lens[c] - 1 for c in f_ctg]).astype(np.int32)
+        r = api.sw_batch(ctx, cat, off, chr_start, f_ctg, f_s, f_e, rg_index=(st, sp, ioff))
+        seg = np.repeat(f_ctg.astype(np.int32), np.diff(r["row_off"]).astype(np.int64))
+        ref = orc.count_batch(st, sp, ioff, seg, r["start"].astype(np.uint32), r["end"].astype(np.uint32), threads=8)
+        _eq(f"rg_count, max_len {max_len}", r["rg_count"], ref)
+        assert not r["rg_count"][seg == 1].any()
+
+
+# --------------------------------------------------------------- gunzip: two-phase decoder (inflate2.cu) and the CRC-32 check
+def _gzb(data, level=1, strategy=0, mem=8):
+    import zlib
+    o = zlib.compressobj(level, zlib.DEFLATED, 31, mem, strategy)
+    return o.compress(data) + o.flush()
+
+
+def test_gunzip_crc32_mismatch_is_status_7(ctx, orc):
+    """flate2's GzDecoder verifies the CRC-32 of the trailer (redis.rs:156-161 unwraps the error): a blob whose payload was
+    corrupted with ISIZE preserved, or whose trailer CRC was altered, ends in status 7; its neighbours are untouched."""
+    import zlib
+    dna = synth.genome(120_000, seed=21).tobytes()
+    good = _gzb(dna)
+    # (a) stored block: flipping a payload byte keeps the stream valid and the size right
+    stored = bytearray(_gzb(dna[:30_000], level=0))
+    stored[200] ^= 0x04
+    # (b) the trailer's CRC itself
+    bad_crc = bytearray(good)
+    bad_crc[-8] ^= 0x01
+    # (c) a literal changed inside a fixed-Huffman block: swap two equal-length codes by re-encoding other data with the trailer of the first
+    other = dna[:5000].replace(b"A", b"C", 1)
+    swapped = bytearray(_gzb(other, strategy=zlib.Z_FIXED))
+    swapped[-8:] = _gzb(dna[:5000], strategy=zlib.Z_FIXED)[-8:]
+    blobs = [good, bytes(stored), bytes(bad_crc), bytes(swapped), good]
+    sizes = [len(dna), 30_000, len(dna), 5000, len(dna)]
+    ooff = np.concatenate(([0], np.cumsum(sizes))).astype(np.uint64)
+    for decoder in (0, 1):
+        ctx.set_gunzip_options(decoder, True)
+        try:
+            out, off, st = api.gunzip_batch(ctx, *api.pack_blobs(blobs), ooff, raise_on_error=False)
+            assert st.tolist() == [0, 7, 7, 7, 0], (decoder, st.tolist())
+            assert out[:len(dna)].tobytes() == dna and out[int(ooff[4]):].tobytes() == dna
+            ctx.set_gunzip_options(decoder, False)
+            _, _, st = api.gunzip_batch(ctx, *api.pack_blobs(blobs), ooff, raise_on_error=False)
+            assert st.tolist() == [0, 0, 0, 0, 0]
+        finally:
+            ctx.set_gunzip_options(0, True)
+
+
+def test_gunzip_two_decoders_agree(ctx, orc):
+    """The two-phase decoder against the warp-per-blob decoder and zlib on the shapes that stress token resolution: runs of
+    one base (distance 1, length 258), tandem repeats with periods 2..40, matches that start inside the batch being resolved,
+    literals only, stored data (token budget exceeded: falls back), > 32 blobs (several thread blocks), ragged sizes."""
+    import zlib
+    rng = np.random.default_rng(31)
+    dna = synth.genome(700_000, seed=33).tobytes()
+    plain = [dna[:300_001], b"N" * 70_000, (b"AC" * 9 + b"G") * 3000, b"".join(bytes([65 + (i % p)]) for p in (2, 3, 5, 7, 40) for i in range(9000)),
+             dna[1000:1040] * 2000, rng.integers(0, 256, 40_000, dtype=np.uint8).tobytes(), b"", b"A", dna[:257], dna[:258] * 3]
+    for k in range(60):
+        a = int(rng.integers(0, 600_000))
+        plain.append(dna[a:a + int(rng.integers(1, 90_000))])
+    # N gaps inside sequence, soft-masked stretches
+    mixed = bytearray(dna[400_000:600_000])
+    for a in range(5000, 190_000, 17_000):
+        mixed[a:a + int(rng.integers(1, 3000))] = b"N" * len(mixed[a:a + int(rng.integers(1, 3000))])
+    plain.append(bytes(mixed))
+    blobs = [_gzb(p, level=(1, 6, 9)[i % 3]) for i, p in enumerate(plain)]
+    blobs[3] = _gzb(plain[3], strategy=zlib.Z_RLE)
+    blobs[5] = _gzb(plain[5], level=0)
+    cat, goff = api.pack_blobs(blobs)
+    ooff = np.concatenate(([0], np.cumsum([len(p) for p in plain]))).astype(np.uint64)
+    res = {}
+    for decoder in (0, 1):
+        ctx.set_gunzip_options(decoder, True)
+        try:
+            out, off, st = api.gunzip_batch(ctx, cat, goff, ooff)
+        finally:
+            ctx.set_gunzip_options(0, True)
+        assert not st.any(), (decoder, st.tolist())
+        res[decoder] = out
+        for i, p in enumerate(plain):
+            got = out[int(off[i]):int(off[i + 1])].tobytes()
+            assert got == p, f"decoder {decoder}, blob {i}: first difference at {next((k for k in range(min(len(got), len(p))) if got[k] != p[k]), None)}"
+    assert np.array_equal(res[0], res[1])
