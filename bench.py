@@ -1,12 +1,16 @@
 #!/usr/bin/env python3
 """bench.py — the gams hot path on B200: GC-wave Gbp/s (headline) and rg overlap counts/s.
 
-One "step" = one pass of the hot path over one batch of synthetic input:
-  wave  : Kernel A (sequence bytes -> per-window GC) + Kernel B (z-score signals) over a human-scale
+One "step" = `passes_per_step` passes of the hot path over the synthetic batch (so many that K steps keep the device
+busy for >= 0.6 s: one pass takes under a millisecond, and a timed region of a few ms sees neither sustained clocks nor
+more than one NVML sample):
+  wave  : the fused GC-wave kernel (sequence bytes -> per-window GC + z-score signals) over a human-scale
           synthetic genome (3.1 Gbp, 24 chromosomes, `gen --piece 500000` ctgs, wave 100/10, lag 100,
           threshold 3, influence 1) resident in HBM  -> `value` (Gbp/s);
           the same through the host C-ABI call gams_cuda_wave_batch with pinned HOST buffers, H2D of the
-          sequence and D2H of gc+signal inside the timed region                      -> `e2e`.
+          sequence and D2H of gc+signal inside the timed region                      -> `e2e`;
+          and through gams_cuda_wave_gz_batch, fed with the gzip blobs Redis holds (seq:{ctg}), which are
+          inflated on the device                                                      -> `e2e_gz`.
   count : batched `locate --count`: 1e8 query ranges against 1e8 SNP intervals on the same ctg layout,
           device-resident and end-to-end, reported under "overlap" in the same JSON line.
 
@@ -15,7 +19,8 @@ used only for the barrier and the max-over-ranks of the device time.  scaling "w
 processes its own 3.1 Gbp genome (a cohort of N genomes); --scaling strong splits one genome by ctg.
 
 `--impl reference` times the reference's CPU algorithm (the oracle port: the reference is Rust and
-cannot be built in this image) on the box's host cores on a bounded sample of the same workload.
+cannot be built in this image) on the box's host cores on a bounded sample of the same workload, the
+per-ctg gunzip of Conn::get_seq (redis.rs:142-161) included, as `gams wave` pays it.
 """
 from __future__ import annotations
 
@@ -55,6 +60,9 @@ def parse():
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-gz", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-frontend", action="store_true", help="skip the parse / locate-text / index-build records")
+    ap.add_argument("--skip-multi", action="store_true", help="skip the strong-scaling and single-process records (N > 1)")
+    ap.add_argument("--passes", type=int, default=0, help="passes over the genome per step (0: as many as make K steps >= 0.6 s)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     return ap.parse_args()
 
@@ -152,10 +160,17 @@ class ClockSampler:
 
 
 def ncu_traffic(kernel: str):
-    """DRAM bytes per launch from the committed ncu --set full capture (profiles/traffic.json), or None."""
+    """DRAM bytes per launch from the committed ncu --set full capture (profiles/traffic.json), or None.  An entry names the
+    source files of its kernel with their sha1 at capture time: if one of them has changed since, the number is stale and
+    None is returned instead (the capture is repeated with scripts/round_profile.sh)."""
+    import hashlib
     try:
         d = json.loads((ROOT / "profiles" / "traffic.json").read_text())
-        return float(d[kernel]["dram_bytes_per_launch"])
+        ent = d[kernel]
+        for f, h in (ent.get("source_sha1") or {}).items():
+            if hashlib.sha1((ROOT / "gams_b200" / "csrc" / f).read_bytes()).hexdigest() != h:
+                return None
+        return float(ent["dram_bytes_per_launch"])
     except Exception:
         return None
 
@@ -198,8 +213,34 @@ def cpu_wave_rate(seq_host: np.ndarray, seq_off: np.ndarray, threads: int, targe
     return bases / dt / 1e9, f"first {k} ctgs ({bases / 1e6:.1f} Mbp) of the workload, wave {SIZE}/{STEP} lag {LAG}, {dt:.1f} s wall"
 
 
+def gz_blobs(h_seq: np.ndarray, seq_off: np.ndarray, threads: int):
+    """The seq:{ctg} values as encode_gz writes them (redis.rs:149-154: gzip, Compression::fast() = level 1), one per ctg."""
+    import zlib
+    from concurrent.futures import ThreadPoolExecutor
+
+    def comp(c):
+        o = zlib.compressobj(1, zlib.DEFLATED, 31)
+        return o.compress(h_seq[int(seq_off[c]):int(seq_off[c + 1])].tobytes()) + o.flush()
+
+    with ThreadPoolExecutor(max(1, threads)) as ex:
+        return list(ex.map(comp, range(seq_off.size - 1)))
+
+
+def cpu_gunzip_into(blobs, out: np.ndarray, seq_off: np.ndarray, threads: int):
+    """decode_gz per ctg (redis.rs:156-161) with zlib on `threads` host threads (zlib releases the GIL), into `out`."""
+    import zlib
+    from concurrent.futures import ThreadPoolExecutor
+
+    def dec(c):
+        out[int(seq_off[c]):int(seq_off[c + 1])] = np.frombuffer(zlib.decompress(blobs[c], 31), dtype=np.uint8)
+
+    with ThreadPoolExecutor(max(1, threads)) as ex:
+        list(ex.map(dec, range(len(blobs))))
+
+
 def run_reference(args, rank):
-    """bench.py --impl reference: the reference's CPU path (oracle port) with all host threads."""
+    """bench.py --impl reference: the reference's CPU path (oracle port) with all host threads: per step every ctg of the
+    sample is gunzipped (Conn::get_seq -> decode_gz, redis.rs:142-161: zlib here, flate2 there) and goes through wave."""
     if rank != 0:
         return
     from gams_b200 import synth
@@ -215,24 +256,39 @@ def run_reference(args, rank):
     k = int(min(seq_off.size - 1, max(n_cal, rate * 1e9 * per_step_s / PIECE), max(n_cal, 600e6 / PIECE)))  # <= 600 Mbp
     g = synth.genome(int(seq_off[k]), seed=20240613)
     sub_off = seq_off[:k + 1].astype(np.uint64)
+    blobs = gz_blobs(g, sub_off, cores)
+    buf = np.empty_like(g)
+    t_gz = 0.0
+
+    def step():
+        nonlocal t_gz
+        t = time.perf_counter()
+        cpu_gunzip_into(blobs, buf, sub_off, cores)
+        t_gz += time.perf_counter() - t
+        orc.wave_batch(buf, sub_off, SIZE, STEP, LAG, THRESHOLD, args.influence, threads=cores)
+
     for _ in range(args.warmup):
-        orc.wave_batch(g, sub_off, SIZE, STEP, LAG, THRESHOLD, args.influence, threads=cores)
+        step()
+    t_gz = 0.0
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        orc.wave_batch(g, sub_off, SIZE, STEP, LAG, THRESHOLD, args.influence, threads=cores)
+        step()
     dt = time.perf_counter() - t0
+    assert np.array_equal(buf, g)
     bases = int(sub_off[-1])
     val = bases * args.steps / dt / 1e9
-    sample = f"{k} ctgs ({bases / 1e6:.1f} Mbp) per step of the {args.bases / 1e9:.2f} Gbp workload"
+    sample = f"{k} ctgs ({bases / 1e6:.1f} Mbp) per step of the {args.bases / 1e9:.2f} Gbp workload, gunzip of the seq blobs included"
     line = {
         "impl": "reference", "metric": "gc_wave_throughput", "value": val, "unit": "Gbp/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": args.scaling, "vs_baseline": None, "dtype": "u8->u32 counts, f32 statistics", "data": "synthetic",
         "config": workload_config(args),
-        "cpu_baseline": {"value": val, "unit": "Gbp/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "Gbp/s", "cores": cores, "kind": "port", "sample": sample,
+                         "gunzip_share_of_time": t_gz / dt},
         "e2e": {"value": val, "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference is Rust (no cargo in this image): timed the faithful C port oracle/gams_oracle.c, "
-                "one worker per ctg over all host threads (the reference's --parallel model), inputs in memory",
+                "one worker per ctg over all host threads (the reference's --parallel model); the seq blobs are in memory "
+                "(no Redis GET) and are inflated per step with zlib, as Conn::get_seq does with flate2",
     }
     print(json.dumps(line), flush=True)
 
@@ -265,8 +321,10 @@ def main():
         raise SystemExit("bench.py needs a CUDA device; gams_b200 has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    gloo = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        gloo = dist.new_group(backend="gloo")   # a barrier that keeps the GPUs idle (an NCCL barrier is a kernel on every device)
 
     def barrier():
         if world > 1:
@@ -292,7 +350,7 @@ def main():
     hbm_peak, peak_src, peaks_json = peaks()
 
     # ---- workload: this rank's ctgs ------------------------------------------------------------
-    g_off, _ = layout(int(args.bases))
+    g_off, g_ctgs = layout(int(args.bases))
     if args.scaling == "strong" and world > 1:
         from gams_b200 import shard
         _, _, seq_off = shard.shard_for_rank(g_off, rank, world)
@@ -309,10 +367,27 @@ def main():
 
     fused = plan.fused(THRESHOLD, args.influence)
 
-    def step():
+    def one_pass():
         # one pass of the hot path over the rank's genome: the fused kernel when the statistics are the defaults
         # (influence 1), else Kernel A followed by Kernel B
         plan.wave(stream, d_seq, THRESHOLD, args.influence, d_gc, d_sig, None, d_filt)
+
+    # passes per step: so many that the K timed steps keep the device busy for >= 0.6 s (sustained clocks, a clock record of
+    # more than one sample); every rank uses the same number
+    one_pass()
+    torch.cuda.synchronize()
+    c0e, c1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0e.record()
+    for _ in range(3):
+        one_pass()
+    c1e.record()
+    torch.cuda.synchronize()
+    ms_cal = max_over_ranks(c0e.elapsed_time(c1e) / 3)
+    passes = args.passes if args.passes > 0 else int(min(256, max(1, np.ceil(600.0 / max(args.steps, 1) / max(ms_cal, 1e-3)))))
+
+    def step():
+        for _ in range(passes):
+            one_pass()
 
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
     with ClockSampler(local) as clk:
@@ -333,11 +408,11 @@ def main():
         barrier()
     launches = plan.launches - l0
     z_uncertain, _ = ctx.zscore_stats(reset=True)
-    z_uncertain /= max(1, args.steps + args.warmup)
+    z_uncertain /= max(1, (args.steps + args.warmup) * passes + 4)
     ms_total = max_over_ranks(t_start.elapsed_time(t_end))
-    ms_step = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
+    ms_step = float(np.mean([e[0].elapsed_time(e[1]) for e in ev])) / passes     # one pass = one launch of the fused kernel
     total_bases = sum_over_ranks(float(n_bases))
-    value = total_bases * args.steps / (ms_total * 1e-3) / 1e9
+    value = total_bases * args.steps * passes / (ms_total * 1e-3) / 1e9
     clocks = clk.summary()
 
     # the two-kernel path (Kernel A, Kernel B) timed separately, outside the headline region, for the per-kernel table
@@ -406,7 +481,7 @@ def main():
         parity = {"ctgs_checked": pick, "bit_exact": ok}
 
     # ---- e2e: host C-ABI call, pinned host buffers, H2D + D2H inside the timed region --------------
-    e2e = None
+    e2e = e2e_gz = gz_host = None
     h_seq_ptr = None
     if not args.skip_e2e:
         woff = api.win_offsets(seq_off, SIZE, STEP)
@@ -449,6 +524,43 @@ def main():
                "d2h_bytes_per_step": int(n_win * 5), "steps": n_e2e, "ms_per_step": dt / n_e2e * 1e3,
                "pcie_probe_gbs": {"h2d": tpc[0], "d2h": tpc[1]}, "ms_each_step_rank0": [round(x, 2) for x in per_step],
                "api": "gams_cuda_wave_batch (host pointers, pinned)", "timer": "host wall clock around the blocking call, max over ranks"}
+        # ---- e2e_gz: the same step fed with what Redis holds: the gzip blobs of Conn::get_seq (redis.rs:142-161), inflated on the
+        # device.  A third of the bytes cross the link; the decode costs GPU time instead (see `feed`).
+        if not args.skip_gz:
+            cores = os.cpu_count() or 1
+            t = time.perf_counter()
+            blobs = gz_blobs(h_seq, seq_off, max(1, cores // max(1, world)))
+            t_comp = time.perf_counter() - t
+            goff = np.zeros(n_ctg + 1, dtype=np.uint64)
+            goff[1:] = np.cumsum([len(b) for b in blobs])
+            n_gz = int(goff[-1])
+            p_gz = pinned(n_gz, L)
+            as_np(p_gz, n_gz, np.uint8)[:] = np.frombuffer(b"".join(blobs), dtype=np.uint8)
+            del blobs
+            st_gz = np.zeros(n_ctg, dtype=np.int32)
+            as_np(h_sig_ptr, n_win, np.int8)[:] = 77
+            vp = lambda a: a.ctypes.data_as(C.c_void_p)
+
+            def gz_step():
+                api.check(L.gams_cuda_wave_gz_batch(ctx.handle, n_ctg, p_gz, vp(goff), vp(seq_off), SIZE, STEP, LAG, THRESHOLD,
+                                                    args.influence, vp(woff), None, h_gc_ptr, h_sig_ptr, vp(st_gz)))
+
+            for _ in range(2):
+                gz_step()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(n_e2e):
+                gz_step()
+            torch.cuda.synchronize()
+            dtg = max_over_ranks(time.perf_counter() - t0)
+            same = bool(np.array_equal(as_np(h_sig_ptr, n_win, np.int8), d_sig.cpu().numpy()) and np.array_equal(
+                as_np(h_gc_ptr, n_win, np.float32).view(np.uint32), d_gc.cpu().numpy().view(np.uint32)))
+            e2e_gz = {"value": total_bases * n_e2e / dtg / 1e9, "unit": "Gbp/s", "ms_per_step": dtg / n_e2e * 1e3,
+                      "h2d_bytes_per_step": n_gz, "d2h_bytes_per_step": int(n_win * 5 + n_ctg * 4), "steps": n_e2e,
+                      "compressed_bytes": n_gz, "ratio": n_bases / n_gz, "matches_device_path": same,
+                      "api": "gams_cuda_wave_gz_batch (seq:{ctg} gzip blobs in pinned host memory -> device gunzip incl. CRC-32 -> fused GC-wave)",
+                      "host_compress_s": t_comp}
+            gz_host = (p_gz, goff, n_gz)
         L.gams_cuda_host_free(h_gc_ptr)
         L.gams_cuda_host_free(h_sig_ptr)
 
@@ -474,8 +586,10 @@ def main():
 
     # ---- feed step (a18): the seq:{ctg} blobs as Redis holds them (gzip, level 1) inflated on the device ------------
     feed = None
-    if rank == 0 and world == 1 and h_seq_ptr is not None and not args.skip_gz:
-        feed = bench_gunzip(args, ctx, L, dev, as_np(h_seq_ptr, n_bases, np.uint8), seq_off, d_seq, n_bases)
+    if rank == 0 and world == 1 and gz_host is not None:
+        feed = bench_gunzip(args, ctx, L, dev, gz_host, seq_off, d_seq, n_bases)
+    if gz_host is not None:
+        L.gams_cuda_host_free(gz_host[0])
 
     # ---- CPU baseline (rank 0, N = 1 only) --------------------------------------------------------
     cpu = None
@@ -498,13 +612,22 @@ def main():
     if rank == 0 and not args.skip_sw and not args.skip_e2e:
         sw = bench_sw(args, ctx, L, dev)
 
+    frontend = None
+    if rank == 0 and world == 1 and not args.skip_frontend and not args.skip_e2e:
+        frontend = bench_frontend(args, ctx, L, dev, g_off, g_ctgs)
+
+    multi = None
+    if world > 1 and not args.skip_multi:
+        multi = bench_multi(args, ctx, L, dev, rank, world, g_off, d_seq, barrier, max_over_ranks, gloo)
+
     if rank == 0:
         line = {
             "metric": "gc_wave_throughput", "value": value, "unit": "Gbp/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": args.scaling,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "passes_per_step": passes, "ms_per_pass": ms_total / args.steps / passes,
+            "timed_region_ms": ms_total, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "u8->u32 counts, f32 statistics", "data": "synthetic",
-            "config": workload_config(args), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roof_main, "kernels": kern, "path": "fused (gc_wave_fused_kernel)" if fused else ("gc_wave_fused_kernel + zscore_seq_skip_kernel (influence != 1)" if args.influence != 1.0 and plan.fused(THRESHOLD, 1.0) else "gc_window_kernel + zscore kernel"), "cpu_baseline": cpu, "overlap": overlap, "sw": sw, "feed": feed, "parity_spot_check": parity,
+            "config": workload_config(args), "clocks": clocks, "e2e": e2e, "e2e_gz": e2e_gz, "gpu_launches": int(launches),
+            "roofline": roof_main, "kernels": kern, "path": "fused (gc_wave_fused_kernel)" if fused else ("gc_wave_fused_kernel + zscore_seq_skip_kernel (influence != 1)" if args.influence != 1.0 and plan.fused(THRESHOLD, 1.0) else "gc_window_kernel + zscore kernel"), "cpu_baseline": cpu, "overlap": overlap, "sw": sw, "feed": feed, "frontend": frontend, "multi_gpu": multi, "parity_spot_check": parity,
             "windows_per_step": int(n_win), "bases_per_rank": int(n_bases),
         }
         print(json.dumps(line), flush=True)
@@ -512,35 +635,24 @@ def main():
         dist.destroy_process_group()
 
 
-def bench_gunzip(args, ctx, L, dev, h_seq, seq_off, d_seq, n_bases):
-    """SURVEY a18 (Conn::get_seq -> decode_gz): every ctg compressed as encode_gz does (gzip level 1), inflated by
-    gunzip_kernel with blobs and output resident in HBM; checked byte for byte against the genome it was made from."""
+def bench_gunzip(args, ctx, L, dev, gz_host, seq_off, d_seq, n_bases):
+    """SURVEY a18 (Conn::get_seq -> decode_gz): every ctg compressed as encode_gz does (gzip level 1), inflated on the device
+    with blobs and output resident in HBM; checked byte for byte against the genome it was made from.  Both decoders."""
     import zlib
-    from concurrent.futures import ThreadPoolExecutor
 
     import torch
 
     from gams_b200 import api
 
+    p_gz, goff, n_gz = gz_host
     n_ctg = seq_off.size - 1
-    cores = os.cpu_count() or 1
-
-    def comp(c):
-        o = zlib.compressobj(1, zlib.DEFLATED, 31)
-        return o.compress(h_seq[int(seq_off[c]):int(seq_off[c + 1])].tobytes()) + o.flush()
-
-    t = time.perf_counter()
-    with ThreadPoolExecutor(cores) as ex:
-        blobs = list(ex.map(comp, range(n_ctg)))
-    t_comp = time.perf_counter() - t
-    cat, goff = api.pack_blobs(blobs)
+    cat = as_np(p_gz, n_gz, np.uint8)
     k = min(n_ctg, 400)
     t = time.perf_counter()
-    for b in blobs[:k]:
-        zlib.decompress(b, 31)
+    for c in range(k):
+        zlib.decompress(cat[int(goff[c]):int(goff[c + 1])].tobytes(), 31)
     cpu_rate = float(seq_off[k]) / (time.perf_counter() - t) / 1e9
-    del blobs
-    d_gz = torch.from_numpy(cat.copy()).to(dev)
+    d_gz = torch.from_numpy(cat).to(dev)
     d_goff = torch.from_numpy(goff.astype(np.int64)).to(dev)
     d_ooff = torch.from_numpy(seq_off.astype(np.int64)).to(dev)
     d_out = torch.zeros(n_bases + 64, dtype=torch.uint8, device=dev)
@@ -551,24 +663,32 @@ def bench_gunzip(args, ctx, L, dev, h_seq, seq_off, d_seq, n_bases):
         api.check(L.gams_cuda_gunzip_dev(ctx.handle, 0, stream, n_ctg, d_gz.data_ptr(), d_goff.data_ptr(), d_out.data_ptr(),
                                          d_ooff.data_ptr(), d_st.data_ptr()))
 
-    run()
-    torch.cuda.synchronize()
-    ok = bool(int(d_st.abs().sum()) == 0 and torch.equal(d_out[:n_bases], d_seq[:n_bases]))
+    res = {}
     n = max(1, min(args.steps, 3))
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(n):
+    for name, dec, crc in (("two_phase_crc", 0, True), ("two_phase", 0, False), ("one_pass", 1, False)):
+        ctx.set_gunzip_options(dec, crc)
+        d_out.zero_()
         run()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / n
-    return {"what": "gunzip of the seq:{ctg} blobs on the device (gams_cuda_gunzip_dev), blobs and output in HBM",
-            "value": n_bases / (ms * 1e-3) / 1e9, "unit": "Gbp/s", "ms_per_step": ms, "blobs": int(n_ctg),
-            "compressed_bytes": int(cat.size), "ratio": n_bases / cat.size, "bit_exact": ok, "gpu_launches": n,
-            "bound": "instruction issue: one dependent chain per deflate symbol, one warp per blob; the longest blob sets the time",
+        torch.cuda.synchronize()
+        ok = bool(int(d_st.abs().sum()) == 0 and torch.equal(d_out[:n_bases], d_seq[:n_bases]))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        res[name] = {"ms_per_step": ms, "value": n_bases / (ms * 1e-3) / 1e9, "bit_exact": ok}
+    ctx.set_gunzip_options(0, True)
+    main = res["two_phase_crc"]
+    return {"what": "gunzip of the seq:{ctg} blobs on the device (gams_cuda_gunzip_dev), blobs and output in HBM; default decoder: tokens "
+                    "(one thread per part) -> bytes (one warp per blob) -> CRC-32",
+            "value": main["value"], "unit": "Gbp/s", "ms_per_step": main["ms_per_step"], "blobs": int(n_ctg),
+            "compressed_bytes": int(n_gz), "ratio": n_bases / n_gz, "bit_exact": all(r["bit_exact"] for r in res.values()),
+            "decoders": res,
+            "bound": "latency of the serial chain of one deflate symbol (index -> table load -> shift); the longest blob sets the time",
             "cpu_baseline": {"value": cpu_rate, "unit": "Gbp/s", "cores": 1, "kind": "zlib",
-                             "sample": f"zlib.decompress of the first {k} blobs, one thread"},
-            "host_compress_s": t_comp}
+                             "sample": f"zlib.decompress of the first {k} blobs, one thread"}}
 
 
 def bench_sw(args, ctx, L, dev):
@@ -629,9 +749,36 @@ def bench_sw(args, ctx, L, dev):
             ok &= bool(b - a == len(ref["gc"]) and all(np.array_equal(r[key][a:b].view(np.uint32), ref[key].view(np.uint32))
                                                       for key in ("gc", "mean", "sd", "cv")))
     dt_cpu = time.perf_counter() - t0
+    # sw --action count: the same rows plus rg_count against 10^6 SNPs (chr coordinates), one call
+    per = max(1, 1_000_000 // len(ctgs))
+    st, sp, ioff = synth.rg_index(lens, [per] * len(ctgs), seed=9)
+    shift = np.repeat((chr_start - 1).astype(np.uint32), per)
+    st, sp = st + shift, sp + shift
+    p_cnt = pinned(cap * 4, L)
+
+    def sw_count_step():
+        api.check(L.gams_cuda_sw_count_batch(ctx.handle, len(ctgs), p_seq, vp(seq_off), vp(chr_start), n_feat, vp(f_ctg), vp(f_s), vp(f_e),
+                                             100, 20, 500, vp(st), vp(sp), vp(ioff), vp(row_off), ptrs["start"], ptrs["end"], ptrs["type"],
+                                             ptrs["dist"], ptrs["gc"], ptrs["mean"], ptrs["sd"], ptrs["cv"], p_cnt))
+
+    sw_count_step()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        sw_count_step()
+    dt_cnt = (time.perf_counter() - t0) / reps
+    got_cnt = as_np(p_cnt, n_rows, np.uint32)
+    sel = np.sort(rng.choice(n_rows, min(n_rows, 200_000), replace=False))
+    seg_of_row = np.repeat(f_ctg.astype(np.int32), np.diff(row_off).astype(np.int64))
+    ref_cnt = orc.count_batch(st, sp, ioff, seg_of_row[sel], r["start"][sel].astype(np.uint32), r["end"][sel].astype(np.uint32),
+                              threads=os.cpu_count() or 1)
+    sw_count = {"value": n_rows / dt_cnt, "unit": "sw rows/s", "ms_per_step": dt_cnt * 1e3, "rg_intervals": int(st.size),
+                "d2h_bytes_per_step": int(n_rows * 33 + (n_feat + 1) * 8), "bit_exact_sample": bool(np.array_equal(got_cnt[sel], ref_cnt)),
+                "api": "gams_cuda_sw_count_batch (sw rows + rg_count = count_rg of every row, staged Kernel C on the rows)"}
+    L.gams_cuda_host_free(p_cnt)
     for pp in list(ptrs.values()) + [p_seq]:
         L.gams_cuda_host_free(pp)
-    return {"workload": "Arabidopsis-scale synthetic genome (119.7 Mbp) + sw --size 100 --max 20 --resize 500 around "
+    return {"sw_count": sw_count,
+            "workload": "Arabidopsis-scale synthetic genome (119.7 Mbp) + sw --size 100 --max 20 --resize 500 around "
                         f"{n_feat} point features (configs[2])",
             "value": n_rows / dt, "unit": "sw rows/s", "features_per_s": n_feat / dt, "rows": n_rows, "ms_per_step": dt * 1e3,
             "h2d_bytes_per_step": int(n + n_feat * 12), "d2h_bytes_per_step": int(n_rows * 29 + (n_feat + 1) * 8),
@@ -641,9 +788,220 @@ def bench_sw(args, ctx, L, dev):
                              "sample": f"{k} of the features through the oracle (ctypes call per feature)"}}
 
 
+def bench_frontend(args, ctx, L, dev, g_off, ctgs):
+    """The rows either side of the count kernel at scale, through the host C ABI (text / host arrays in, text / arrays out):
+    a17 range-file parsing and `locate --count -f` text in / text out (locate.rs:80-141), a14 / f3 the rg index build
+    (build_idx_rg, redis.rs:276-305), each with the oracle timed on a sample beside it."""
+    import torch
+
+    from gams_b200 import api, synth
+    from oracle import oracle as orc
+
+    out = {}
+    rng = np.random.default_rng(3)
+    lens = np.diff(g_off.astype(np.int64))
+    n_ctg = lens.size
+    chr_of = np.array([c[0] for c in ctgs])
+    names = [f"chr{k + 1}" for k in range(int(chr_of.max()) + 1)]
+    cs = np.array([c[1] for c in ctgs], dtype=np.uint32)
+    ce = np.array([c[2] + 1 for c in ctgs], dtype=np.uint32)   # stop exclusive
+    chr_off = np.concatenate(([0], np.cumsum(np.bincount(chr_of, minlength=len(names))))).astype(np.uint64)
+    chr_len = np.array([int(ce[chr_of == k].max()) - 1 for k in range(len(names))])
+    # ---- query text: 2e7 lines `chr:start-end`, arbitrary order
+    n_lines, m = 20_000_000, 1_000_000
+    c = rng.integers(0, len(names), m)
+    qs = (rng.random(m) * chr_len[c]).astype(np.int64) + 1
+    qe = np.minimum(qs + rng.integers(0, 10_000, m), chr_len[c])
+    block = "\n".join(f"{names[a]}:{b}-{d}" for a, b, d in zip(c.tolist(), qs.tolist(), qe.tolist())) + "\n"
+    text = (block * (n_lines // m)).encode()
+    api.parse_ranges(ctx, text[:100_000], names)
+    t = time.perf_counter()
+    got = api.parse_ranges(ctx, text, names)
+    dt = time.perf_counter() - t
+    k = 100_000
+    lines = block.splitlines()[:k]
+    t = time.perf_counter()
+    ref = [orc.range_from_str(ln) for ln in lines]
+    dtc = time.perf_counter() - t
+    ok = all(r is not None and (int(got["start"][i]), int(got["end"][i])) == (r[2], r[3]) and names[int(got["chr"][i])] == r[0]
+             for i, r in enumerate(ref))
+    out["parse_ranges"] = {"value": n_lines / dt, "unit": "lines/s", "ms_per_step": dt * 1e3, "lines": n_lines, "text_bytes": len(text),
+                           "handed_back": int((got["chr"] == -3).sum()), "matches_oracle_sample": bool(ok),
+                           "api": "gams_cuda_parse_ranges (host text in, arrays out, copies inside)",
+                           "cpu_baseline": {"value": k / dtc, "unit": "lines/s", "cores": 1, "kind": "port",
+                                            "sample": f"{k} lines through the oracle's Range::from_str restatement (python re)"}}
+    del got
+    # ---- the rg index: 1e8 SNPs in chr coordinates, unsorted as the loader sees them, built on the device
+    per = max(1, int(args.intervals) // n_ctg)
+    d_st, _, iv_off = synth.rg_index_torch(lens, per, seed=7, device=dev)
+    d_st = d_st.view(n_ctg, per) + torch.as_tensor((cs.astype(np.int64) - 1), device=dev)[:, None].to(torch.int32)
+    g = torch.Generator(device=dev)
+    g.manual_seed(4)
+    perm = torch.argsort(torch.rand(n_ctg, per, generator=g, device=dev), dim=1)
+    h_start = torch.gather(d_st, 1, perm).reshape(-1).cpu().numpy().view(np.uint32)     # file order inside each ctg
+    h_sorted = d_st.reshape(-1).cpu().numpy().view(np.uint32)
+    del d_st, perm
+    h_stop = h_start + np.uint32(1)
+    api.build_idx_rg(ctx, h_start[:int(iv_off[8])], h_stop[:int(iv_off[8])], iv_off[:9], want_blob=False)
+    t = time.perf_counter()
+    ix = api.build_idx_rg(ctx, h_start, h_stop, iv_off, want_blob=False)
+    dt = time.perf_counter() - t
+    ok = bool(np.array_equal(ix["starts"], h_sorted) and np.array_equal(ix["stops"], h_sorted + np.uint32(1)))
+    kseg = 64
+    t = time.perf_counter()
+    for sgm in range(kseg):
+        a, b = int(iv_off[sgm]), int(iv_off[sgm + 1])
+        orc.lapper_new([(int(x), int(x) + 1, "") for x in h_start[a:b]])
+    dtc = time.perf_counter() - t
+    n_iv = int(iv_off[-1])
+    out["build_idx_rg"] = {"value": n_iv / dt, "unit": "intervals/s", "ms_per_step": dt * 1e3, "intervals": n_iv, "segments": int(n_ctg),
+                           "h2d_bytes_per_step": n_iv * 8, "d2h_bytes_per_step": n_iv * 16, "sorted_arrays_match": ok,
+                           "api": "gams_cuda_build_idx_rg (host arrays in; sorted intervals, starts[], stops[], max_len out; no blob)",
+                           "cpu_baseline": {"value": kseg * per / dtc, "unit": "intervals/s", "cores": 1, "kind": "port",
+                                            "sample": f"Lapper::new restated (oracle.lapper_new) on the first {kseg} ctgs"}}
+    # ---- locate --count -f: text in, text out, against that index
+    st, sp = ix["starts"], ix["stops"]
+    api.locate_count_text(ctx, text[:100_000], names, cs, ce, chr_off, st, sp, iv_off)
+    t = time.perf_counter()
+    txt, nl, npr, nb = api.locate_count_text(ctx, text, names, cs, ce, chr_off, st, sp, iv_off)
+    dt = time.perf_counter() - t
+    k = 2000
+    ok = True
+    for ln, gline in zip(lines[:k], txt[:200_000].decode().splitlines()[:k]):
+        rg = orc.range_from_str(ln)
+        ci = names.index(rg[0])
+        j = int(np.searchsorted(ce[int(chr_off[ci]):int(chr_off[ci + 1])], rg[2], side="right")) + int(chr_off[ci])
+        refc = orc.lapper_count(st[int(iv_off[j]):int(iv_off[j + 1])], sp[int(iv_off[j]):int(iv_off[j + 1])], rg[2], rg[3])
+        ok &= gline == f"{ln}\t{refc}"
+    out["locate_count_text"] = {"value": nl / dt, "unit": "lines/s", "ms_per_step": dt * 1e3, "lines": int(nl), "printed": int(npr),
+                                "handed_back": int(nb), "h2d_bytes_per_step": len(text) + n_iv * 8, "d2h_bytes_per_step": len(txt),
+                                "first_lines_match_oracle": bool(ok),
+                                "api": "gams_cuda_locate_count_text (range-file text in, `rg\\tcount` text out; parse, find_one_idx, count_rg, "
+                                       "formatting on the device)"}
+    return out
+
+
+def bench_multi(args, ctx, L, dev, rank, world, g_off, d_seq, barrier, max_over_ranks, gloo):
+    """N > 1, next to the weak-scaling headline: (1) STRONG scaling as BASELINE configs[3] words it — ONE 3.1 Gbp genome, its ctgs
+    sharded over the N ranks (shard.shard_for_rank = gams_cuda_partition), device-resident and end to end; (2) the library's own
+    multi-device context, as a Rust host would use it: ONE process (rank 0) owns all N devices through gams_cuda_create and calls
+    gams_cuda_wave_batch / gams_cuda_count_overlaps once; the other ranks wait on a CPU barrier with their GPUs idle."""
+    import torch
+    import torch.distributed as dist
+
+    from gams_b200 import api, shard, synth
+
+    out = {}
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    stream = torch.cuda.current_stream().cuda_stream
+    # ---- (1) strong scaling: this rank's contiguous, byte-balanced run of ctgs of the one genome
+    c0, c1, s_off = shard.shard_for_rank(g_off, rank, world)
+    plan = api.WavePlan(ctx, s_off, SIZE, STEP, LAG)
+    nb, nw = plan.total_bases, plan.total_windows
+    d_gc = torch.empty(nw, dtype=torch.float32, device=dev)
+    d_sig = torch.empty(nw, dtype=torch.int8, device=dev)
+    d_filt = torch.empty(nw, dtype=torch.float32, device=dev) if args.influence != 1.0 else None
+    seq = d_seq[:plan.seq_capacity]
+    passes = 64
+    for _ in range(3):
+        plan.wave(stream, seq, THRESHOLD, args.influence, d_gc, d_sig, None, d_filt)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(passes):
+        plan.wave(stream, seq, THRESHOLD, args.influence, d_gc, d_sig, None, d_filt)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / passes
+    total = float(g_off[-1])
+    woff = api.win_offsets(s_off, SIZE, STEP)
+    h_seq_ptr, h_gc_ptr, h_sig_ptr = pinned(nb, L), pinned(nw * 4, L), pinned(nw, L)
+    torch.from_numpy(as_np(h_seq_ptr, nb, np.uint8)).copy_(d_seq[:nb])
+    torch.cuda.synchronize()
+
+    def e2e_step():
+        api.check(L.gams_cuda_wave_batch(ctx.handle, s_off.size - 1, h_seq_ptr, vp(s_off), SIZE, STEP, LAG, THRESHOLD, args.influence,
+                                         vp(woff), None, h_gc_ptr, h_sig_ptr))
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        e2e_step()
+    torch.cuda.synchronize()
+    dt = max_over_ranks(time.perf_counter() - t0) / 3
+    out["strong"] = {"workload": f"ONE {total / 1e9:.2f} Gbp genome, ctgs {c0}..{c1} of {g_off.size - 1} on rank {rank} (contiguous, byte-balanced)",
+                     "value": total / (ms * 1e-3) / 1e9, "unit": "Gbp/s", "ms_per_pass": ms, "scaling": "strong",
+                     "e2e": {"value": total / dt / 1e9, "unit": "Gbp/s", "ms_per_step": dt * 1e3, "h2d_bytes_per_step_per_rank": int(nb),
+                             "d2h_bytes_per_step_per_rank": int(nw * 5)},
+                     "timer": "max over ranks (CUDA events for the resident passes, host clock around the blocking host calls)"}
+    for pp in (h_seq_ptr, h_gc_ptr, h_sig_ptr):
+        L.gams_cuda_host_free(pp)
+    plan.close()
+    del d_gc, d_sig, d_filt
+    # ---- (2) one process, N devices (rank 0; the others wait with idle GPUs)
+    torch.cuda.synchronize()
+    dist.barrier(group=gloo)
+    if rank == 0:
+        n_ctg = g_off.size - 1
+        n_bases = int(g_off[-1])
+        gw = api.win_offsets(g_off, SIZE, STEP)
+        n_win = int(gw[-1])
+        p_seq, p_gc, p_sig, p_sig1 = pinned(n_bases, L), pinned(n_win * 4, L), pinned(n_win, L), pinned(n_win, L)
+        torch.from_numpy(as_np(p_seq, n_bases, np.uint8)).copy_(d_seq[:n_bases])
+        torch.cuda.synchronize()
+        mctx = api.Context(list(range(world)))
+
+        def call(c, sig_ptr):
+            api.check(L.gams_cuda_wave_batch(c.handle, n_ctg, p_seq, vp(g_off), SIZE, STEP, LAG, THRESHOLD, args.influence, vp(gw), None,
+                                             p_gc, sig_ptr))
+
+        call(mctx, p_sig)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            call(mctx, p_sig)
+        dtm = (time.perf_counter() - t0) / 3
+        call(ctx, p_sig1)                   # the single-device result of the same call
+        same = bool(np.array_equal(as_np(p_sig, n_win, np.int8), as_np(p_sig1, n_win, np.int8)))
+        rec = {"devices": world, "wave_batch": {"value": n_bases / dtm / 1e9, "unit": "Gbp/s", "ms_per_step": dtm * 1e3,
+                                                "h2d_bytes_per_step": n_bases, "d2h_bytes_per_step": n_win * 5,
+                                                "equals_single_device_result": same}}
+        for pp in (p_seq, p_gc, p_sig, p_sig1):
+            L.gams_cuda_host_free(pp)
+        # overlap counts through the same context: grouped queries shard by ctg, arbitrary ones replicate the index
+        lens = np.diff(g_off.astype(np.int64))
+        per = max(1, int(args.intervals) // lens.size)
+        d_st, d_sp, iv_off = synth.rg_index_torch(lens, per, seed=7, device=dev)
+        h_st, h_sp = d_st.cpu().numpy().view(np.uint32), d_sp.cpu().numpy().view(np.uint32)
+        del d_st, d_sp
+        n_q = int(args.queries)
+        for name, grouped in (("grouped_by_ctg", True), ("arbitrary_order", False)):
+            q_seg, q_s, q_e = synth.queries_torch(lens, n_q, seed=11, grouped=grouped, device=dev)
+            hq = [t.cpu().numpy() for t in (q_seg, q_s, q_e)]
+            del q_seg, q_s, q_e
+            res = {}
+            for label, c in (("multi", mctx), ("single", ctx)):
+                o = np.empty(n_q, dtype=np.uint32)
+                api.check(L.gams_cuda_count_overlaps(c.handle, iv_off.size - 1, vp(h_st), vp(h_sp), vp(iv_off), n_q, vp(hq[0]),
+                                                     vp(hq[1].view(np.uint32)), vp(hq[2].view(np.uint32)), vp(o)))
+                t0 = time.perf_counter()
+                api.check(L.gams_cuda_count_overlaps(c.handle, iv_off.size - 1, vp(h_st), vp(h_sp), vp(iv_off), n_q, vp(hq[0]),
+                                                     vp(hq[1].view(np.uint32)), vp(hq[2].view(np.uint32)), vp(o)))
+                res[label] = (time.perf_counter() - t0, o)
+            rec[f"count_overlaps_{name}"] = {"value": n_q / res["multi"][0], "unit": "counts/s", "ms_per_step": res["multi"][0] * 1e3,
+                                             "ms_per_step_one_device": res["single"][0] * 1e3,
+                                             "equals_single_device_result": bool(np.array_equal(res["multi"][1], res["single"][1])),
+                                             "host_buffers": "pageable numpy arrays (not pinned)"}
+        mctx.close()
+        out["single_process_ctx"] = rec
+    dist.barrier(group=gloo)
+    return out
+
+
 def bench_count(args, ctx, L, dev, rank, world, g_off, barrier, max_over_ranks, sum_over_ranks, hbm_peak, peak_src):
-    """configs[4]: batched `locate --count` — queries grouped by ctg (the order read_range yields) and in
-    arbitrary order, against SNP intervals; index resident in HBM as it is in the reference's BTreeMap."""
+    """configs[4]: batched `locate --count` — queries in ARBITRARY order (the order locate.rs:111-141 walks the range file in:
+    this is the configs[4] distribution, uniform random starts) and, for comparison, grouped by ctg (the order the `gams rg`
+    loader's read_range yields); SNP intervals; index resident in HBM as it is in the reference's BTreeMap."""
     import torch
 
     from gams_b200 import api, synth
@@ -677,7 +1035,7 @@ def bench_count(args, ctx, L, dev, rank, world, g_off, barrier, max_over_ranks, 
                "gpu_launches": int(plan.launches - l0),
                "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                             "frac": alg / (ms * 1e-3) / 1e9 / hbm_peak,
-                            "kernel": "seg_query_bounds_kernel + seg_items_kernel + count_overlaps_staged_kernel" if grouped else "count_overlaps_ranked_kernel",
+                            "kernel": "seg_query_bounds_kernel + seg_items_kernel + count_overlaps_staged_kernel" if grouped else "part_sort_kernel + part_lookup_kernel + part_unpermute_kernel",
                             "traffic": ncu_traffic("count_overlaps:grouped_by_ctg" if grouped else "count_overlaps:arbitrary_order") if n_q == 100_000_000 else None,
                             "algorithmic_bytes_per_launch": alg, "peak_source": peak_src}}
         tr = res["roofline"]["traffic"]

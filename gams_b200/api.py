@@ -125,6 +125,23 @@ def wave_batch(ctx: Context, seq_concat, seq_off, size=100, step=10, lag=100, th
     return woff, cnt, gc, sig
 
 
+def wave_gz_batch(ctx: Context, gz_concat, gz_off, seq_off, size=100, step=10, lag=100, threshold=3.0, influence=1.0,
+                  want_count=True, want_signal=True, raise_on_error=True):
+    """get_seq + wave for a batch of ctgs held as seq:{ctg} gzip blobs → (win_off, gc_count, gc, signal, inflate status)."""
+    gz_concat, gz_off, seq_off = _arr(gz_concat, np.uint8), _arr(gz_off, np.uint64), _arr(seq_off, np.uint64)
+    woff = win_offsets(seq_off, size, step)
+    n = int(woff[-1])
+    cnt = np.empty(n, dtype=np.uint32) if want_count else None
+    gc = np.empty(n, dtype=np.float32)
+    sig = np.empty(n, dtype=np.int8) if want_signal else None
+    status = np.zeros(seq_off.size - 1, dtype=np.int32)
+    rc = load().gams_cuda_wave_gz_batch(ctx.handle, seq_off.size - 1, _p(gz_concat), _p(gz_off), _p(seq_off), size, step, lag,
+                                        threshold, influence, _p(woff), _p(cnt), _p(gc), _p(sig), _p(status))
+    if rc and (raise_on_error or not status.any()):
+        check(rc)
+    return woff, cnt, gc, sig, status
+
+
 # --------------------------------------------------------------- anno.rs:128-139
 def anno_coverage(ctx: Context, run_start, run_end, run_off, q_chr, q_ctg_start, q_ctg_end, q_start, q_end) -> np.ndarray:
     """`gams anno`: proportion of each range covered by the runlist of its chromosome inside its ctg (f32)."""

@@ -7,6 +7,7 @@
 #include <thread>
 
 #include "common.cuh"
+#include "inflate_common.cuh"
 
 namespace gams {
 
@@ -548,10 +549,16 @@ struct PeakSink {   // per-device results of gams_cuda_wave_peaks_batch
     std::vector<int8_t> sig;
 };
 
+struct GzSource {   // gams_cuda_wave_gz_batch: the ctgs arrive as the gzip blobs Redis holds (seq:{ctg}), not as bases
+    const uint8_t *gz_concat = nullptr;
+    const uint64_t *gz_off = nullptr;   // n_ctg + 1
+    int32_t *status = nullptr;          // n_ctg inflate status codes
+};
+
 static int32_t wave_on_device(gams_cuda_ctx *ctx, int d, int64_t c0, int64_t c1, const uint8_t *seq_concat,
                               const uint64_t *seq_off, int32_t size, int32_t step, uint64_t lag, float threshold,
                               float influence, const uint64_t *win_off, uint32_t *gc_count, float *gc, int8_t *signal,
-                              PeakSink *sink = nullptr) {
+                              PeakSink *sink = nullptr, const GzSource *gzs = nullptr) {
     if (c1 <= c0) return GAMS_CUDA_OK;
     PerDevice &pd = ctx->devs[d];
     DeviceGuard g(pd.device);
@@ -587,10 +594,25 @@ static int32_t wave_on_device(gams_cuda_ctx *ctx, int d, int64_t c0, int64_t c1,
             for (auto e : b) cudaEventDestroy(e);
         }
     } ev_guard{ev_in, ev_k, pd.copy_in};
-    const uint8_t *h_seq = seq_concat + base0;
+    const uint8_t *h_seq = gzs ? nullptr : seq_concat + base0;
+    // gz source: the compressed bytes go up instead (a third of the bases), in the same slices of ctgs; they are inflated on
+    // the device once all of them have arrived (the decoder wants the whole batch: its time is the serial chain of the longest
+    // blob, not the number of blobs)
+    uint8_t *d_gz = nullptr;
+    uint64_t gz_base = 0, gz_bytes = 0;
+    if (gzs) {
+        gz_base = gzs->gz_off[c0], gz_bytes = gzs->gz_off[c1] - gz_base;
+        if ((rc = pd.scratch[6].reserve(gz_bytes + 64 + (size_t)(n + 1) * 16 + (size_t)n * 4 + 64))) return rc;
+        d_gz = pd.scratch[6].as<uint8_t>();
+    }
     auto enqueue_h2d = [&](size_t k) -> int32_t {
-        const uint64_t b0 = seq_off[c0 + cut[k]] - base0, b1 = seq_off[c0 + cut[k + 1]] - base0;
-        if (b1 > b0) CUDA_TRY(cudaMemcpyAsync(d_seq + b0, h_seq + b0, b1 - b0, cudaMemcpyHostToDevice, pd.copy_in));
+        if (gzs) {
+            const uint64_t b0 = gzs->gz_off[c0 + cut[k]] - gz_base, b1 = gzs->gz_off[c0 + cut[k + 1]] - gz_base;
+            if (b1 > b0) CUDA_TRY(cudaMemcpyAsync(d_gz + b0, gzs->gz_concat + gz_base + b0, b1 - b0, cudaMemcpyHostToDevice, pd.copy_in));
+        } else {
+            const uint64_t b0 = seq_off[c0 + cut[k]] - base0, b1 = seq_off[c0 + cut[k + 1]] - base0;
+            if (b1 > b0) CUDA_TRY(cudaMemcpyAsync(d_seq + b0, h_seq + b0, b1 - b0, cudaMemcpyHostToDevice, pd.copy_in));
+        }
         CUDA_TRY(cudaEventRecord(ev_in[k], pd.copy_in));
         return GAMS_CUDA_OK;
     };
@@ -636,6 +658,24 @@ static int32_t wave_on_device(gams_cuda_ctx *ctx, int d, int64_t c0, int64_t c1,
     for (size_t k = n_pre; k < n_sl; ++k)
         if ((rc = enqueue_h2d(k))) return rc;
     trace_stage("wave: reserve");
+    std::vector<uint64_t> gz_rel, seq_rel;
+    if (gzs) {
+        // offsets of the blobs / ctgs relative to this device's buffers, then the decoder behind the last slice of the upload
+        gz_rel.resize((size_t)n + 1), seq_rel.resize((size_t)n + 1);
+        for (int64_t c = 0; c <= n; ++c) {
+            gz_rel[c] = gzs->gz_off[c0 + c] - gz_base;
+            seq_rel[c] = seq_off[c0 + c] - base0;
+        }
+        uint8_t *meta = d_gz + ((gz_bytes + 63) & ~63ull);
+        uint64_t *d_goff = reinterpret_cast<uint64_t *>(meta), *d_ooff = d_goff + (n + 1);
+        int32_t *d_status = reinterpret_cast<int32_t *>(d_ooff + (n + 1));
+        CUDA_TRY(cudaMemcpyAsync(d_goff, gz_rel.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, pd.stream));
+        CUDA_TRY(cudaMemcpyAsync(d_ooff, seq_rel.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, pd.stream));
+        if (n_sl) CUDA_TRY(cudaStreamWaitEvent(pd.stream, ev_in[n_sl - 1], 0));
+        if ((rc = launch_gunzip2(pd, pd.stream, d_gz, d_goff, n, d_seq, d_ooff, d_status, nb, ctx->gunzip_mode, ctx->gunzip_crc != 0))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(gzs->status + c0, d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, pd.stream));
+        trace_stage("wave: gunzip", pd.stream, true);
+    }
     // The sequential z-score kernel (influence != 1: one warp per ctg) needs thousands of ctgs in flight to hide its
     // latency; on a 64 MB slice (~130 ctgs) it takes as long as on a quarter of a genome.  So it runs once per GROUP of
     // slices (four groups: the first three overlap the upload of the next), 321 -> ~90 ms per 3.1 Gbp end to end.
@@ -754,6 +794,40 @@ GAMS_API int32_t gams_cuda_wave_batch(gams_cuda_ctx *ctx, int64_t n_ctg, const u
         return wave_on_device(ctx, d, part[d], part[d + 1], seq_concat, seq_off, size, step, lag, threshold, influence,
                               win_off, gc_count, gc, signal);
     });
+}
+
+// Conn::get_seq + wave::proc_ctg in one call (src/libs/redis.rs:142-161, src/cmd_gams/wave.rs:138-155): the ctgs arrive as the
+// gzip blobs Redis holds under seq:{ctg}; they are inflated on the device and go straight into the GC-wave kernels.
+GAMS_API int32_t gams_cuda_wave_gz_batch(gams_cuda_ctx *ctx, int64_t n_ctg, const uint8_t *gz_concat, const uint64_t *gz_off,
+                                         const uint64_t *seq_off, int32_t size, int32_t step, uint64_t lag, float threshold,
+                                         float influence, const uint64_t *win_off, uint32_t *gc_count, float *gc, int8_t *signal,
+                                         int32_t *status) {
+    ARG_CHECK(ctx, "wave_gz_batch: ctx is NULL");
+    ARG_CHECK(n_ctg >= 0 && gz_off && seq_off && win_off, "wave_gz_batch: NULL offsets");
+    ARG_CHECK(size > 0 && step > 0, "wave_gz_batch: size and step must be positive (got %d, %d)", size, step);
+    if (n_ctg == 0) return GAMS_CUDA_OK;
+    ARG_CHECK(gz_concat && status, "wave_gz_batch: NULL blobs / status");
+    ARG_CHECK(gc || win_off[n_ctg] == 0, "wave_gz_batch: gc is NULL");
+    for (int64_t c = 0; c < n_ctg; ++c)
+        ARG_CHECK(gz_off[c + 1] >= gz_off[c], "wave_gz_batch: gz_off decreases at %lld", (long long)c);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const int n_dev = (int)std::min<int64_t>((int64_t)ctx->devs.size(), n_ctg);
+    std::vector<int64_t> part((size_t)n_dev + 1);
+    int32_t rc = gams_cuda_partition(n_ctg, seq_off, n_dev, part.data());
+    if (rc) return rc;
+    GzSource src;
+    src.gz_concat = gz_concat, src.gz_off = gz_off, src.status = status;
+    rc = for_each_device(ctx, n_dev, [&](int d) {
+        return wave_on_device(ctx, d, part[d], part[d + 1], nullptr, seq_off, size, step, lag, threshold, influence, win_off, gc_count, gc,
+                              signal, nullptr, &src);
+    });
+    if (rc) return rc;
+    for (int64_t c = 0; c < n_ctg; ++c)
+        if (status[c] != 0) {
+            set_error("wave_gz_batch: seq blob %lld failed with inflate status %d (its windows are undefined)", (long long)c, (int)status[c]);
+            return GAMS_CUDA_EINVAL;
+        }
+    return GAMS_CUDA_OK;
 }
 
 GAMS_API int32_t gams_cuda_wave_peaks_batch(gams_cuda_ctx *ctx, int64_t n_ctg, const uint8_t *seq_concat,

@@ -102,6 +102,16 @@ int32_t gams_cuda_wave_batch(gams_cuda_ctx *ctx, int64_t n_ctg, const uint8_t *s
                              float threshold, float influence, const uint64_t *win_off,
                              uint32_t *gc_count, float *gc, int8_t *signal);
 
+/* The same with the feed step inside: Conn::get_seq (src/libs/redis.rs:142-146: GET seq:{ctg} -> decode_gz, redis.rs:156-161) +
+ * wave::proc_ctg (wave.rs:138-155).  The ctgs arrive as the gzip blobs Redis holds (gz_concat / gz_off as gams_cuda_gunzip_batch
+ * takes them), a third of the bytes of the bases; they are inflated on the device (ISIZE and CRC-32 checked) and never visit the
+ * host.  seq_off: the ctg lengths as offsets (chr_end - chr_start + 1 of the ctg records, src/libs/data.rs:5-16), win_off from
+ * them.  status[c]: inflate status of blob c (see gams_cuda_gunzip_batch); GAMS_CUDA_EINVAL if any blob failed. */
+int32_t gams_cuda_wave_gz_batch(gams_cuda_ctx *ctx, int64_t n_ctg, const uint8_t *gz_concat, const uint64_t *gz_off,
+                                const uint64_t *seq_off, int32_t size, int32_t step, uint64_t lag, float threshold,
+                                float influence, const uint64_t *win_off, uint32_t *gc_count, float *gc, int8_t *signal,
+                                int32_t *status);
+
 /* `gams wave` without --signal, src/cmd_gams/wave.rs:138-212: the same computation as gams_cuda_wave_batch followed by
  * merge_ints (wave.rs:217-252) ON THE DEVICE, so that only the peaks cross PCIe (a few MB instead of 5 B per window).
  * One record per line wave prints, ctgs in input order, lines of a ctg in the reference's order:

@@ -55,6 +55,11 @@ extern "C" {
         lag: u64, threshold: f32, influence: f32, win_off: *const u64, gc_count: *mut u32, gc: *mut f32,
         signal: *mut i8,
     ) -> i32;
+    pub fn gams_cuda_wave_gz_batch(
+        ctx: *mut gams_cuda_ctx, n_ctg: i64, gz_concat: *const u8, gz_off: *const u64, seq_off: *const u64, size: i32,
+        step: i32, lag: u64, threshold: f32, influence: f32, win_off: *const u64, gc_count: *mut u32, gc: *mut f32,
+        signal: *mut i8, status: *mut i32,
+    ) -> i32;
     pub fn gams_cuda_thresholding_batch(
         ctx: *mut gams_cuda_ctx, n_series: i64, data: *const f32, off: *const u64, lag: u64, threshold: f32,
         influence: f32, signal: *mut i8,

@@ -320,3 +320,44 @@ def test_gunzip_two_decoders_agree(ctx, orc):
             got = out[int(off[i]):int(off[i + 1])].tobytes()
             assert got == p, f"decoder {decoder}, blob {i}: first difference at {next((k for k in range(min(len(got), len(p))) if got[k] != p[k]), None)}"
     assert np.array_equal(res[0], res[1])
+
+
+# --------------------------------------------------------------- chained feed: seq:{ctg} gzip blobs -> gunzip -> GC-wave
+@pytest.mark.parametrize("infl", [1.0, 0.5])
+def test_wave_gz_batch_equals_wave_batch(ctx, orc, infl):
+    """gams_cuda_wave_gz_batch (Conn::get_seq + wave::proc_ctg, redis.rs:142-161 + wave.rs:138-155) on the blobs encode_gz writes
+    (Compression::fast) gives bit for bit what gams_cuda_wave_batch gives on the bases, and what the oracle gives."""
+    g = synth.genome(2_400_000, seed=91)
+    cuts = [0, 500_000, 1_000_003, 1_000_903, 1_900_000, 2_400_000]
+    seqs = [g[a:b] for a, b in zip(cuts[:-1], cuts[1:])]
+    cat, off = orc.pack_ctgs(seqs)
+    blobs = [orc.encode_gz(s.tobytes()) for s in seqs]
+    gcat, goff = api.pack_blobs(blobs)
+    woff, cnt, gc, sig, st = api.wave_gz_batch(ctx, gcat, goff, off, 100, 10, 50, 3.0, infl)
+    assert not st.any()
+    rw, rc, rg, rs = orc.wave_batch(cat, off, 100, 10, 50, 3.0, infl, threads=8)
+    _eq("win_off", woff, rw)
+    _eq("gc_count", cnt, rc)
+    _eq("gc", gc.view(np.uint32), rg.view(np.uint32))
+    _eq("signal", sig, rs)
+    w2, c2, g2, s2 = api.wave_batch(ctx, cat, off, 100, 10, 50, 3.0, infl)
+    assert np.array_equal(c2, cnt) and np.array_equal(s2, sig)
+
+
+def test_wave_gz_batch_reports_a_bad_blob(ctx, orc):
+    """A corrupted blob (payload changed, CRC-32 no longer matches) and a blob of the wrong length fail the call with their
+    status; the other ctgs' statuses stay 0."""
+    g = synth.genome(600_000, seed=92)
+    seqs = [g[:200_000], g[200_000:400_000], g[400_000:]]
+    cat, off = orc.pack_ctgs(seqs)
+    blobs = [bytearray(orc.encode_gz(s.tobytes())) for s in seqs]
+    blobs[1][-8] ^= 0x10                                    # the trailer's CRC
+    gcat, goff = api.pack_blobs([bytes(b) for b in blobs])
+    with pytest.raises(api.GamsCudaError):
+        api.wave_gz_batch(ctx, gcat, goff, off)
+    _, _, _, _, st = api.wave_gz_batch(ctx, gcat, goff, off, raise_on_error=False)
+    assert st.tolist() == [0, 7, 0]
+    off2 = off.copy()
+    off2[1:] += 5                                           # the caller expects 5 bases more in the first ctg
+    _, _, _, _, st = api.wave_gz_batch(ctx, *api.pack_blobs([orc.encode_gz(s.tobytes()) for s in seqs]), off2, raise_on_error=False)
+    assert st[0] != 0
