@@ -8,32 +8,84 @@
 // What leaves the device is exactly what gams_cuda_count_overlaps consumes (starts[] / stops[] per segment), so the
 // index never has to round-trip through the host when queries follow.
 //
-// Sorting is cub::DeviceSegmentedSort (CUDA toolkit, library code: segments of any size in one call) on 64-bit keys
-// start << 32 | stop; everything around it (key packing, unpacking, per-segment max_len, the blob bytes) is written here.
-// Bound: HBM; ~56 B moved per interval by our kernels + the sort's passes.  Not on BASELINE's timed path.
+// Sorting: idx_sort_kernel, one CTA per segment.  A ctg's intervals (16 K SNPs at C5 scale) fit shared memory: 64-bit keys
+// start << 32 | stop, a bitonic network whose every comparison is ascending (partner i ^ (2k - 1) in the first step of a
+// merge, i ^ stride in the others: the array may then be padded with +inf virtually, any n works), then the stops alone as
+// 32-bit keys in the same shared memory.  Each interval is read once and each output written once (8 B in, 16 B out); the
+// O(n log^2 n) compare-exchanges stay on chip.  A segment too large for shared memory is sorted by the same network in global
+// memory by its CTA (correct for any size; slow, and rare: a ctg is at most a few hundred kbp).
+// Bound: shared-memory bandwidth / barriers (105 network steps for 16 K keys), not HBM.  Not on BASELINE's timed path.
 #include "common.cuh"
-#include <cub/device/device_segmented_sort.cuh>
 
 namespace gams {
 
-__global__ void __launch_bounds__(256)
-idx_pack_kernel(const uint32_t *__restrict__ start, const uint32_t *__restrict__ stop, uint64_t n, uint64_t *__restrict__ key) {
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-        key[i] = ((uint64_t)start[i] << 32) | (uint64_t)stop[i];
+constexpr int IS_THREADS = 1024;
+constexpr uint32_t IS_CAP = 16384;            // 64-bit keys in shared memory (128 KB: one CTA per SM)
+
+// ascending bitonic network over a[0 .. n) (virtually padded with +inf to a power of two); CTA-wide
+template <class T>
+__device__ void bitonic_sort_cta(T *a, uint32_t n) {
+    uint32_t p = 1;
+    while (p < n) p <<= 1;
+    for (uint32_t k = 2; k <= p; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            const bool first = j == (k >> 1);
+            for (uint32_t t = threadIdx.x; t < (p >> 1); t += blockDim.x) {
+                // pair t of this step: lo below its partner
+                const uint32_t lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const uint32_t hi = first ? (lo ^ (k - 1)) : (lo | j);     // mirror inside the block of k for the first step
+                if (hi < n) {                                             // (lo < hi always; a partner past n is +inf: no exchange)
+                    const T x = a[lo], y = a[hi];
+                    if (y < x) { a[lo] = y; a[hi] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    }
 }
 
-// sorted keys -> the interval columns; starts[] is the start column itself (sorted by start first)
-__global__ void __launch_bounds__(256)
-idx_unpack_kernel(const uint64_t *__restrict__ key, uint64_t n, uint32_t *__restrict__ iv_start, uint32_t *__restrict__ iv_stop,
-                  uint32_t *__restrict__ starts) {
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const uint64_t k = key[i];
-        const uint32_t s = (uint32_t)(k >> 32), e = (uint32_t)k;
-        iv_start[i] = s;
-        iv_stop[i] = e;
-        starts[i] = s;
+// one CTA per segment (grid-stride): Lapper::new's three sorted views of the segment
+__global__ void __launch_bounds__(IS_THREADS)
+idx_sort_kernel(const uint32_t *__restrict__ start, const uint32_t *__restrict__ stop, const uint64_t *__restrict__ iv_off, int64_t n_seg,
+                uint64_t *__restrict__ big_keys /* n u64: workspace of the segments that do not fit shared memory */,
+                uint32_t *__restrict__ iv_start, uint32_t *__restrict__ iv_stop, uint32_t *__restrict__ starts, uint32_t *__restrict__ stops) {
+    extern __shared__ __align__(16) uint8_t is_smem[];
+    uint64_t *k64 = reinterpret_cast<uint64_t *>(is_smem);
+    uint32_t *k32 = reinterpret_cast<uint32_t *>(is_smem);
+    for (int64_t s = blockIdx.x; s < n_seg; s += gridDim.x) {
+        const uint64_t o = iv_off[s], n64 = iv_off[s + 1] - o;
+        const uint32_t n = (uint32_t)n64;
+        if (n64 <= IS_CAP) {
+            for (uint32_t i = threadIdx.x; i < n; i += IS_THREADS) k64[i] = ((uint64_t)start[o + i] << 32) | (uint64_t)stop[o + i];
+            __syncthreads();
+            bitonic_sort_cta(k64, n);
+            for (uint32_t i = threadIdx.x; i < n; i += IS_THREADS) {
+                const uint64_t k = k64[i];
+                iv_start[o + i] = (uint32_t)(k >> 32);
+                iv_stop[o + i] = (uint32_t)k;
+                starts[o + i] = (uint32_t)(k >> 32);
+            }
+            __syncthreads();
+            for (uint32_t i = threadIdx.x; i < n; i += IS_THREADS) k32[i] = stop[o + i];
+            __syncthreads();
+            bitonic_sort_cta(k32, n);
+            for (uint32_t i = threadIdx.x; i < n; i += IS_THREADS) stops[o + i] = k32[i];
+            __syncthreads();
+        } else {   // in global memory (n < 2^31 per call)
+            uint64_t *g = big_keys + o;
+            for (uint32_t i = threadIdx.x; i < n; i += IS_THREADS) g[i] = ((uint64_t)start[o + i] << 32) | (uint64_t)stop[o + i];
+            __syncthreads();
+            bitonic_sort_cta(g, n);
+            for (uint32_t i = threadIdx.x; i < n; i += IS_THREADS) {
+                const uint64_t k = g[i];
+                iv_start[o + i] = (uint32_t)(k >> 32);
+                iv_stop[o + i] = (uint32_t)k;
+                starts[o + i] = (uint32_t)(k >> 32);
+                stops[o + i] = stop[o + i];
+            }
+            __syncthreads();
+            bitonic_sort_cta(stops + o, n);
+        }
     }
 }
 
@@ -93,29 +145,16 @@ idx_blob_kernel(const uint32_t *__restrict__ iv_start, const uint32_t *__restric
     }
 }
 
-// All pointers device memory.  d_key_a / d_key_b: n u64 each; d_tmp_stop: n u32; d_cub: cub_bytes of sort workspace.
-size_t idx_sort_workspace(uint64_t n, int64_t n_seg) {
-    size_t a = 0, b = 0;
-    cub::DeviceSegmentedSort::SortKeys(nullptr, a, (const uint64_t *)nullptr, (uint64_t *)nullptr, (int)n, (int)n_seg,
-                                       (const uint64_t *)nullptr, (const uint64_t *)nullptr);
-    cub::DeviceSegmentedSort::SortKeys(nullptr, b, (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)n, (int)n_seg,
-                                       (const uint64_t *)nullptr, (const uint64_t *)nullptr);
-    return std::max(a, b) + 256;
-}
-
+// All pointers device memory.  d_key_a: n u64 of workspace (touched only for segments of more than IS_CAP intervals).
 int32_t launch_build_idx(cudaStream_t st, int64_t n_seg, uint64_t n, const uint32_t *d_start, const uint32_t *d_stop,
-                         const uint64_t *d_iv_off, uint64_t *d_key_a, uint64_t *d_key_b, void *d_cub, size_t cub_bytes,
-                         uint32_t *d_iv_start, uint32_t *d_iv_stop, uint32_t *d_starts, uint32_t *d_stops, uint32_t *d_max_len,
-                         uint8_t *d_blob) {
+                         const uint64_t *d_iv_off, uint64_t *d_key_a, uint32_t *d_iv_start, uint32_t *d_iv_stop, uint32_t *d_starts,
+                         uint32_t *d_stops, uint32_t *d_max_len, uint8_t *d_blob) {
     if (n_seg == 0) return GAMS_CUDA_OK;
     if (n) {
-        const unsigned blocks = (unsigned)std::min<uint64_t>((n + 255) / 256, 148ull * 32);
-        idx_pack_kernel<<<blocks, 256, 0, st>>>(d_start, d_stop, n, d_key_a);
-        size_t wb = cub_bytes;
-        CUDA_TRY(cub::DeviceSegmentedSort::SortKeys(d_cub, wb, d_key_a, d_key_b, (int)n, (int)n_seg, d_iv_off, d_iv_off + 1, st));
-        idx_unpack_kernel<<<blocks, 256, 0, st>>>(d_key_b, n, d_iv_start, d_iv_stop, d_starts);
-        wb = cub_bytes;
-        CUDA_TRY(cub::DeviceSegmentedSort::SortKeys(d_cub, wb, d_stop, d_stops, (int)n, (int)n_seg, d_iv_off, d_iv_off + 1, st));
+        const size_t smem = (size_t)IS_CAP * 8;
+        CUDA_TRY(cudaFuncSetAttribute(idx_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const unsigned blocks = (unsigned)std::min<int64_t>(n_seg, 148 * 4);
+        idx_sort_kernel<<<blocks, IS_THREADS, smem, st>>>(d_start, d_stop, d_iv_off, n_seg, d_key_a, d_iv_start, d_iv_stop, d_starts, d_stops);
     }
     const unsigned sb = (unsigned)std::min<int64_t>(n_seg, 148 * 8);
     idx_blob_kernel<<<sb, 256, 0, st>>>(d_iv_start, d_iv_stop, d_starts, d_stops, d_iv_off, n_seg, d_max_len, d_blob);
@@ -139,18 +178,19 @@ static int32_t build_idx_one(gams_cuda_ctx *ctx, int dv, int64_t n_seg, uint64_t
     DeviceGuard g(pd.device);
     cudaStream_t st = pd.stream;
     const uint64_t np = std::max<uint64_t>(n, 1);
-    const size_t cub_bytes = idx_sort_workspace(n, n_seg);
     const uint64_t blob_bytes = blob ? 24 * n + 30 * (uint64_t)n_seg : 0;
     int32_t rc;
-    // [1] inputs + offsets, [2] keys (two u64 buffers), [3] outputs (4 u32 columns + max_len), [4] sort workspace, [5] blob
+    // [1] inputs + offsets, [2] key workspace (only when a segment does not fit shared memory), [3] outputs (4 u32 columns +
+    // max_len), [5] blob
+    bool big = false;
+    for (int64_t s = 0; s < n_seg && !big; ++s) big = rel[s + 1] - rel[s] > 16384;
     if ((rc = pd.scratch[1].reserve(np * 8 + (uint64_t)(n_seg + 1) * 8 + 64))) return rc;
-    if ((rc = pd.scratch[2].reserve(np * 16 + 64))) return rc;
+    if ((rc = pd.scratch[2].reserve((big ? np * 8 : 8) + 64))) return rc;
     if ((rc = pd.scratch[3].reserve(np * 16 + (uint64_t)n_seg * 4 + 64))) return rc;
-    if ((rc = pd.scratch[4].reserve(cub_bytes))) return rc;
     if ((rc = pd.scratch[5].reserve(blob_bytes + 64))) return rc;
     uint64_t *d_off = pd.scratch[1].as<uint64_t>();
     uint32_t *d_start = reinterpret_cast<uint32_t *>(d_off + (n_seg + 1)), *d_stop = d_start + np;
-    uint64_t *d_ka = pd.scratch[2].as<uint64_t>(), *d_kb = d_ka + np;
+    uint64_t *d_ka = pd.scratch[2].as<uint64_t>();
     uint32_t *d_ivs = pd.scratch[3].as<uint32_t>(), *d_ive = d_ivs + np, *d_sts = d_ive + np, *d_sps = d_sts + np, *d_ml = d_sps + np;
     uint8_t *d_blob = blob ? pd.scratch[5].as<uint8_t>() : nullptr;
     CUDA_TRY(cudaMemcpyAsync(d_off, rel.data(), (uint64_t)(n_seg + 1) * 8, cudaMemcpyHostToDevice, st));
@@ -158,8 +198,7 @@ static int32_t build_idx_one(gams_cuda_ctx *ctx, int dv, int64_t n_seg, uint64_t
         CUDA_TRY(cudaMemcpyAsync(d_start, start + base, n * 4, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(d_stop, stop + base, n * 4, cudaMemcpyHostToDevice, st));
     }
-    if ((rc = launch_build_idx(st, n_seg, n, d_start, d_stop, d_off, d_ka, d_kb, pd.scratch[4].p, cub_bytes, d_ivs, d_ive, d_sts,
-                               d_sps, d_ml, d_blob)))
+    if ((rc = launch_build_idx(st, n_seg, n, d_start, d_stop, d_off, d_ka, d_ivs, d_ive, d_sts, d_sps, d_ml, d_blob)))
         return rc;
     if (n) {
         CUDA_TRY(cudaMemcpyAsync(iv_start + base, d_ivs, n * 4, cudaMemcpyDeviceToHost, st));

@@ -106,13 +106,16 @@ def _wave_properties(ctx, orc, n_bases, chr_lengths, seed, n_spot):
         assert int(sig[first + k].abs().max()) == 0
     assert set(torch.unique(sig).tolist()) <= {-1, 0, 1}
     rng = np.random.default_rng(seed)
-    for c in rng.choice(n_ctg, n_spot, replace=False):
-        s = d_seq[int(seq_off[c]):int(seq_off[c + 1])].cpu().numpy()
-        _, rc, rg, rs = orc.wave_batch(s, np.array([0, s.size], dtype=np.uint64), 100, 10, 100, 3.0, 1.0)
+    pick = np.sort(rng.choice(n_ctg, min(n_spot, n_ctg), replace=False))
+    cat, off = orc.pack_ctgs([d_seq[int(seq_off[c]):int(seq_off[c + 1])].cpu().numpy() for c in pick])
+    _, rc, rg, rs = orc.wave_batch(cat, off, 100, 10, 100, 3.0, 1.0, threads=16)
+    rw = orc.win_offsets(off, 100, 10).astype(np.int64)
+    for k, c in enumerate(pick):
         a, b = int(w100[c]), int(w100[c + 1])
-        assert np.array_equal(cnt100[a:b].cpu().numpy().view(np.uint32), rc), f"ctg {c} counts"
-        assert np.array_equal(gc100[a:b].cpu().numpy().view(np.uint32), rg.view(np.uint32)), f"ctg {c} gc"
-        assert np.array_equal(sig[a:b].cpu().numpy(), rs), f"ctg {c} signals"
+        ra, rb = int(rw[k]), int(rw[k + 1])
+        assert np.array_equal(cnt100[a:b].cpu().numpy().view(np.uint32), rc[ra:rb]), f"ctg {c} counts"
+        assert np.array_equal(gc100[a:b].cpu().numpy().view(np.uint32), rg[ra:rb].view(np.uint32)), f"ctg {c} gc"
+        assert np.array_equal(sig[a:b].cpu().numpy(), rs[ra:rb]), f"ctg {c} signals"
     frac = float((sig != 0).float().mean())
     assert 1e-4 < frac < 0.2, frac
     return d_seq, seq_off, ctgs
@@ -171,11 +174,63 @@ def _peaks_properties(ctx, orc, d_seq, seq_off, n_bases):
     torch.cuda.empty_cache()
 
 
+def _influence_properties(ctx, orc, d_seq, seq_off, influence, n_spot):
+    """`wave --influence x` (x != 1) at full size: the walk of zscore_seq_skip_kernel behind the fused kernel.
+    (P7) filtered differs from data only AT signals (stat.rs:40-48), so a window whose statistics window [i-1-lag, i-1) holds no
+    signal of the result decides exactly as the influence-1 process does: wherever the influence-x result has no signal among
+    the lag+1 windows before i, its decision at i equals the influence-1 decision at i — for every window of the genome.
+    (P8) oracle-exact on n_spot random ctgs."""
+    dev = d_seq.device
+    st = torch.cuda.current_stream().cuda_stream
+    lag = 100
+    plan = api.WavePlan(ctx, seq_off, 100, 10, lag)
+    n = plan.total_windows
+    d_gc = torch.empty(n, dtype=torch.float32, device=dev)
+    d1 = torch.empty(n, dtype=torch.int8, device=dev)
+    dx = torch.empty(n, dtype=torch.int8, device=dev)
+    d_filt = torch.empty(n, dtype=torch.float32, device=dev)
+    plan.wave(st, d_seq, 3.0, 1.0, d_gc, d1)
+    plan.wave(st, d_seq, 3.0, influence, d_gc, dx, None, d_filt)
+    torch.cuda.synchronize()
+    del d_filt
+    w = api.win_offsets(seq_off, 100, 10).astype(np.int64)
+    woff = torch.as_tensor(w, device=dev)
+    # windows since the last signal of dx inside the same ctg (a running maximum of the signal positions)
+    idx = torch.arange(n, device=dev)
+    last_sig = torch.where(dx != 0, idx, torch.full_like(idx, -1))
+    last_sig = torch.cummax(last_sig, 0).values
+    prev = torch.full_like(idx, -1)
+    prev[1:] = last_sig[:-1]                                     # the last signal strictly before i
+    cid = torch.searchsorted(woff, idx, right=True) - 1
+    prev = torch.where(prev >= woff[cid], prev, torch.full_like(prev, -(1 << 40)))   # signals of earlier ctgs do not count
+    clean = (idx - prev) > (lag + 1)
+    nbad = int(((dx != d1) & clean).sum())
+    assert nbad == 0, f"{nbad} windows with a clean statistics window differ from the influence-1 decision"
+    assert int((dx != d1).sum()) > 1000                          # not vacuous: the influence does change decisions behind signals
+    first = woff[:-1]
+    for k in (0, 50, 99):
+        assert int(dx[first + k].abs().max()) == 0
+    rng = np.random.default_rng(77)
+    n_ctg = seq_off.size - 1
+    pick = np.sort(rng.choice(n_ctg, min(n_spot, n_ctg), replace=False))
+    cat, off = orc.pack_ctgs([d_seq[int(seq_off[c]):int(seq_off[c + 1])].cpu().numpy() for c in pick])
+    _, _, _, rs = orc.wave_batch(cat, off, 100, 10, lag, 3.0, influence, threads=16)
+    rw = orc.win_offsets(off, 100, 10).astype(np.int64)
+    for k, c in enumerate(pick):
+        a, b = int(w[c]), int(w[c + 1])
+        assert np.array_equal(dx[a:b].cpu().numpy(), rs[int(rw[k]):int(rw[k + 1])]), f"ctg {c}: influence {influence} signals"
+    plan.close()
+    del d_gc, d1, dx, idx, last_sig, prev, cid, clean
+    torch.cuda.empty_cache()
+
+
 def test_c4_human_scale_wave(ctx, orc):
     n = 3_100_000_000
-    d_seq, seq_off, _ = _wave_properties(ctx, orc, n, synth.human_like_lengths(n), seed=20240613, n_spot=12)
+    d_seq, seq_off, _ = _wave_properties(ctx, orc, n, synth.human_like_lengths(n), seed=20240613, n_spot=240)
     torch.cuda.empty_cache()
     _peaks_properties(ctx, orc, d_seq, seq_off, n)
+    torch.cuda.empty_cache()
+    _influence_properties(ctx, orc, d_seq, seq_off, 0.5, n_spot=64)
     torch.cuda.empty_cache()
 
 

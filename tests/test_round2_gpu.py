@@ -361,3 +361,33 @@ def test_wave_gz_batch_reports_a_bad_blob(ctx, orc):
     off2[1:] += 5                                           # the caller expects 5 bases more in the first ctg
     _, _, _, _, st = api.wave_gz_batch(ctx, *api.pack_blobs([orc.encode_gz(s.tobytes()) for s in seqs]), off2, raise_on_error=False)
     assert st[0] != 0
+
+
+# --------------------------------------------------------------- rg index build: the hand-written segmented sort (idx_build.cu)
+def test_build_idx_rg_segment_sizes(ctx, orc):
+    """Lapper::new on the device for segments of every size class: empty, 1, 2, 3, powers of two and their neighbours, the
+    shared-memory capacity (16384) and its neighbours, segments that are sorted in global memory (40 000, 70 001), heavy
+    duplicates, already sorted and reversed input, stops that sort differently from the starts."""
+    rng = np.random.default_rng(71)
+    sizes = [0, 1, 2, 3, 31, 32, 33, 1000, 4095, 4096, 4097, 16383, 16384, 16385, 40_000, 0, 70_001, 5]
+    st, sp, off = [], [], [0]
+    for k, n in enumerate(sizes):
+        a = rng.integers(1, 5_000_000, n).astype(np.uint32)
+        if k % 4 == 1:
+            a = np.resize(np.repeat(a[: max(1, n // 50)], 50), n) if n else a   # heavy duplicates
+        if k % 5 == 2:
+            a = np.sort(a)[::-1].copy()                                        # reversed
+        e = a + rng.integers(1, 3000, n).astype(np.uint32)
+        st.append(a), sp.append(e), off.append(off[-1] + n)
+    st, sp, off = np.concatenate(st), np.concatenate(sp), np.asarray(off, dtype=np.uint64)
+    ix = api.build_idx_rg(ctx, st, sp, off)
+    for s in range(len(sizes)):
+        a, b = int(off[s]), int(off[s + 1])
+        order = np.lexsort((sp[a:b], st[a:b]))
+        _eq(f"segment {s} (n = {sizes[s]}) iv_start", ix["iv_start"][a:b], st[a:b][order])
+        _eq(f"segment {s} iv_stop", ix["iv_stop"][a:b], sp[a:b][order])
+        _eq(f"segment {s} starts", ix["starts"][a:b], np.sort(st[a:b]))
+        _eq(f"segment {s} stops", ix["stops"][a:b], np.sort(sp[a:b]))
+        assert int(ix["max_len"][s]) == (int((sp[a:b] - st[a:b]).max()) if b > a else 0)
+    lp = orc.lapper_new([(int(x), int(y), "") for x, y in zip(st[int(off[7]):int(off[8])], sp[int(off[7]):int(off[8])])])
+    assert ix["blob"][int(ix["blob_off"][7]):int(ix["blob_off"][8])].tobytes() == orc.lapper_to_bincode(lp)
