@@ -1,39 +1,54 @@
-// inflate2.cu — gunzip of a batch of `seq:{ctg}` blobs in two phases (Conn::get_seq -> decode_gz, src/libs/redis.rs:142-161).
+// inflate2.cu — gunzip of a batch of `seq:{ctg}` blobs in three phases (Conn::get_seq -> decode_gz, src/libs/redis.rs:142-161).
 //
 // A deflate stream is bit-serial: where a symbol starts is known only after the one before it has been decoded.  The first
 // kernel of this library (inflate.cu: one warp per blob, every lane decodes the same symbol, the lanes share the copies) spends
 // ~100 dependent instructions per symbol on that chain, and the chain of the longest blob sets the time (128 ms per 3.1 Gbp).
-// Here the chain carries only what is serial:
-//   T inflate_tokens_kernel   one THREAD per blob: Huffman decoding only, no output byte is read or written.  A symbol becomes
-//                             a 32-bit token (literal byte, or length + distance, or a stored run); the tables of the thread
-//                             live in shared memory (2.4 KB, 16-bit entries); the bit window is a 64-bit register.  The chain
-//                             per symbol is: index -> table load -> field extraction -> shift.
-//   R inflate_resolve_kernel  one WARP per blob, 32 tokens at a time: output positions by a warp scan; then the batch's OUTPUT
-//                             BYTES are dealt to the lanes (byte b of the batch to lane b mod 32): the lane finds the token that
+// Here the chain carries only what is serial, and it is cut at every deflate block:
+//   P inflate_parts_kernel    part_off[]: every blob is divided into RANGES of ~8 KB of compressed bytes (a level-1 block of
+//                             sequence is ~22 KB, so a range holds at most one block header)
+//   S inflate_split_kernel    one warp per range: where could a block start in it?  A deflate stream does not record that, so
+//                             it is found speculatively — the first bit offset in the range that parses as a complete
+//                             dynamic block header — in three stages of rising cost, each fed densely by the one before:
+//                             (1) 32 offsets per lane and a dozen bit operations: BTYPE = 2, HLIT and HDIST in range (22 %
+//                             pass); (2) the code-length code is complete, Kraft sum exactly 1, by table lookups of three
+//                             lengths at a time (0.4 % pass); (3) the survivors of ~32 chunks are parsed in full, one per
+//                             lane: both Huffman codes of the block must be complete too (none of 8.6e9 random offsets pass).
+//   T inflate_tokens_kernel   one THREAD per part (the stretch from one found header to the next): Huffman decoding only, no
+//                             output byte is read or written.  A symbol becomes a 32-bit token (literal byte, or length +
+//                             distance); the two tables of a thread live in shared memory (6-bit literal/length index, 8-bit
+//                             distance index: 640 bytes, 11 warps per SM), the bit window is three registers.  A part ends
+//                             at the block header where the next part starts.
+//   R inflate_resolve_kernel  one WARP per blob walks the chain of its parts — VERIFYING that every part ended exactly where
+//                             the next one began, that the last one saw the final block and that the sizes agree with the
+//                             trailer — 32 tokens at a time: output positions by a warp scan; then the batch's OUTPUT BYTES
+//                             are dealt to the lanes (byte b of the batch to lane b mod 32): the lane finds the token that
 //                             owns its byte (5 shuffle steps), loads the source byte and stores — 32 consecutive bytes per
-//                             store instruction.  A batch whose matches reach into the batch itself (distance shorter than
-//                             what the batch has produced: runs of N, tandem repeats) is resolved token by token instead.
-// And the chain is cut: a blob of more than 64 KB is decoded as up to TK_MAXP PARTS in parallel.  Where a part may start is
-// not recorded anywhere in a deflate stream, so it is found speculatively (S inflate_split_kernel: the first bit offset behind
-// the part's nominal start that parses as a complete dynamic block header — two complete Huffman codes make a false positive
-// a ~1e-6 event) and VERIFIED afterwards: the part before must end exactly there (R checks the whole chain; a blob whose
-// chain does not close is decoded again by the one-pass kernel, so speculation can cost time but never correctness).
-// The ISIZE trailer and the size the caller expects are checked by R; the CRC-32 of the trailer by crc32_kernel (below) when
-// the caller asks for it (flate2's GzDecoder verifies it, redis.rs:156-161).
-// A blob whose symbols do not fit its token budget (half a token per output byte + 64: anything that compresses worse than
-// 2 bytes per symbol, i.e. not a sequence) keeps status INF_ETOKENS and is decoded by the warp-per-blob kernel of inflate.cu.
+//                             store instruction.
+// A blob whose chain does not close (a false start, a token budget exceeded, any error) keeps status INF_ETOKENS and is
+// decoded again by the one-pass kernel of inflate.cu, which also names the error: speculation can cost time, never
+// correctness.  The token budget is half a token per output byte (+ 64): anything that compresses worse than 2 bytes per
+// symbol is not a sequence.  The CRC-32 of the trailer is checked by crc32_*_kernel (below) when the caller asks for it
+// (flate2's GzDecoder verifies it, redis.rs:156-161).
 #include "common.cuh"
 #include "inflate_common.cuh"
 
 namespace gams {
 
-constexpr int TK_THREADS = 32;                 // one warp per CTA: 32 blobs
-constexpr int TK_LBITS = 9, TK_DBITS = 9;   // level-1 sequence data: 0.15 % of the literal/length codes and 0.4 % of the distance codes are longer
-// per-thread tables, 16-bit entries; the stride in 32-bit words is odd, so equal indices of different threads fall into
-// different banks
-struct TkTables {
-    uint16_t ltab[1 << TK_LBITS];   // bits 0-3 code length (0: longer than the index), 4-6 extra bits, 7-15 symbol (0..287)
-    uint16_t dtab[1 << TK_DBITS];   // bits 0-3 code length, 4-7 extra bits, 8-12 symbol (0..29), 13: invalid
+constexpr int TK_WARPS = 11;                   // warps per CTA, one CTA per SM: 352 parts in flight per SM
+constexpr int TK_THREADS = TK_WARPS * 32;
+constexpr int TK_LBITS = 6, TK_DBITS = 8;      // level-1 sequence data: 0.4 % of the literal/length codes and 0.6 % of the distance codes are longer
+// per-thread tables in shared memory, 16-bit entries; the stride in 32-bit words is odd, so equal indices of different threads
+// fall into different banks
+struct TkFast {
+    uint16_t ltab[1 << TK_LBITS];   // bits 0-3 code length + extra bits (0: not in this table — a longer code, end of block, no such code),
+                                    //   4-6 extra bits, 7: a length symbol, 8-15 the literal byte or the base length - 3
+    uint16_t dtab[1 << TK_DBITS];   // bits 0-4 code length + extra bits (0: not in this table), 5-8 extra bits, 9-13 symbol (0..29)
+    uint32_t pad;
+};
+static_assert(sizeof(TkFast) % 4 == 0 && (sizeof(TkFast) / 4) % 2 == 1, "odd word stride");
+// per-thread scratch in global memory: what a block header needs while it is parsed, and the canonical decoder of the codes
+// that are longer than a table index
+struct TkSlow {
     uint16_t lcnt[16], dcnt[16];    // codes per length
     uint16_t lfirst[16], dfirst[16];  // first canonical code of each length
     uint16_t loffs[16], doffs[16];    // position of that code's symbol in lsym / dsym
@@ -42,8 +57,9 @@ struct TkTables {
     uint8_t lens[320];
     uint8_t ctab[128];              // code-length alphabet: symbol << 3 | code length (0: no such code)
     uint8_t clen[20];
+    uint8_t pad[12];
 };
-static_assert(sizeof(TkTables) % 4 == 0 && (sizeof(TkTables) / 4) % 2 == 1, "odd word stride");
+static_assert(sizeof(TkSlow) % 16 == 0, "TkSlow alignment");
 
 __constant__ uint16_t TK_LBASE[32] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258, 0, 0, 0};
 __constant__ uint8_t TK_LEXT[32] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0, 0, 0, 0};
@@ -54,24 +70,26 @@ __constant__ uint8_t TK_CLORDER[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 
 // The bit window of one thread: three consecutive aligned words of the blob and a bit offset o < 32 into the first — 64 valid
 // bits from the current position in two funnel shifts, enough for a length and a distance symbol with their extra bits (48
 // bits at most) without a refill in between.  Two more words are loaded ahead, so a rotation never waits for memory, and the
-// cache line two lines further down is prefetched.
+// cache line two lines further down is prefetched.  Loads are clamped to the blob's last word, not predicated: bits behind
+// the end of a blob are never part of a valid stream (the trailer is 8 bytes), and a decoder that runs into them stops at
+// the checks of its caller.
 struct TkWin {
     const uint32_t *w;
-    uint32_t n_words, wi, mis;      // w0 w1 w2 = w[wi - 3 .. wi - 1], p0 p1 = w[wi], w[wi + 1]
-    uint32_t w0, w1, w2, p0, p1, o;
-    __device__ __forceinline__ uint32_t ld(uint32_t i) const { return i < n_words ? __ldg(w + i) : 0u; }
+    uint32_t n_words, wi, mis;      // w0 w1 w2 = w[wi - 3 .. wi - 1], p0 p1 p2 = w[wi .. wi + 2]
+    uint32_t w0, w1, w2, p0, p1, p2, o;
+    __device__ __forceinline__ uint32_t ld(uint32_t i) const { return __ldg(w + min(i, n_words - 1u)); }   // n_words >= 1
     __device__ __forceinline__ void seek(uint32_t byte) {
         const uint32_t a = mis + byte, k = a >> 2;
         o = (a & 3u) * 8u;
-        w0 = ld(k), w1 = ld(k + 1), w2 = ld(k + 2), p0 = ld(k + 3), p1 = ld(k + 4);
+        w0 = ld(k), w1 = ld(k + 1), w2 = ld(k + 2), p0 = ld(k + 3), p1 = ld(k + 4), p2 = ld(k + 5);
         wi = k + 3;
     }
     __device__ __forceinline__ uint32_t peek() const { return __funnelshift_r(w0, w1, o); }      // bits 0..31 from the position
     __device__ __forceinline__ uint32_t peek_hi() const { return __funnelshift_r(w1, w2, o); }   // bits 32..63
     __device__ __forceinline__ void rotate() {
-        w0 = w1, w1 = w2, w2 = p0, p0 = p1;
+        w0 = w1, w1 = w2, w2 = p0, p0 = p1, p1 = p2;
         ++wi;
-        p1 = ld(wi + 1);
+        p2 = ld(wi + 2);      // (used three rotations from now: the load is not waited for)
 #ifndef TK_NO_PREFETCH
         if ((wi & 31u) == 0u && wi + 64u < n_words) asm volatile("prefetch.global.L1 [%0];" ::"l"(w + wi + 64));
 #endif
@@ -85,28 +103,34 @@ struct TkWin {
         const uint64_t a = 8ull * mis + bit;
         const uint32_t k = (uint32_t)(a >> 5);
         o = (uint32_t)(a & 31u);
-        w0 = ld(k), w1 = ld(k + 1), w2 = ld(k + 2), p0 = ld(k + 3), p1 = ld(k + 4);
+        w0 = ld(k), w1 = ld(k + 1), w2 = ld(k + 2), p0 = ld(k + 3), p1 = ld(k + 4), p2 = ld(k + 5);
         wi = k + 3;
     }
     __device__ __forceinline__ uint32_t bits(uint32_t n) { const uint32_t v = peek() & ((1u << n) - 1u); drop(n); return v; }   // n < 32
     __device__ __forceinline__ uint64_t consumed_bits() const { return 32ull * (wi - 3) + o - 8ull * mis; }
+    __device__ __forceinline__ bool past_end() const { return wi > n_words + 3u; }   // the position is behind the blob's last word
 };
 
-__device__ __forceinline__ uint32_t tk_lit_entry(int s) {   // without the code length
-    return ((uint32_t)s << 7) | ((s >= 257 && s <= 285) ? (uint32_t)TK_LEXT[s - 257] << 4 : 0u);
+__device__ __forceinline__ uint32_t tk_lit_entry(int s, int code_len) {
+    if (s < 256) return ((uint32_t)s << 8) | (uint32_t)code_len;
+    if (s >= 257 && s <= 285) {
+        const uint32_t ex = TK_LEXT[s - 257];
+        return ((uint32_t)(TK_LBASE[s - 257] - 3) << 8) | 128u | (ex << 4) | ((uint32_t)code_len + ex);
+    }
+    return 0u;     // end of block, 286, 287: the careful path
 }
-__device__ __forceinline__ uint32_t tk_dist_entry(int s) {
-    return s > 29 ? (1u << 13) : (((uint32_t)s << 8) | ((uint32_t)TK_DEXT[s] << 4));
+__device__ __forceinline__ uint32_t tk_dist_entry(int s, int code_len) {
+    if (s > 29) return 0u;
+    const uint32_t dx = TK_DEXT[s];
+    return ((uint32_t)s << 9) | (dx << 5) | ((uint32_t)code_len + dx);
 }
 
-// canonical decoding of a code longer than the primary index (PBITS bits): position of the symbol in canonical order, or -1.
-// The code of length l is the top l bits of the bit-reversed window; it belongs to this length iff it lies in
-// [first[l], first[l] + cnt[l]).
-template <int PBITS>
+// canonical decoding of a code of any length: position of the symbol in canonical order, or -1.  The code of length l is the
+// top l bits of the bit-reversed window; it belongs to this length iff it lies in [first[l], first[l] + cnt[l]).
 __device__ __forceinline__ int tk_decode_slow(uint32_t pk, const uint16_t *cnt, const uint16_t *first, const uint16_t *offs, uint32_t *code_len) {
     const uint32_t c = __brev(pk);
 #pragma unroll 1
-    for (int len = PBITS + 1; len <= 15; ++len) {
+    for (int len = 1; len <= 15; ++len) {
         const uint32_t idx = (c >> (32 - len)) - first[len];
         if (idx < cnt[len]) {
             *code_len = (uint32_t)len;
@@ -121,7 +145,7 @@ __device__ __forceinline__ int tk_decode_slow(uint32_t pk, const uint16_t *cnt, 
 // false for an over-subscribed code.
 template <int PBITS, bool DIST>
 __device__ bool tk_build(const uint8_t *lens, int n, uint16_t *cnt, uint16_t *first, uint16_t *offs_, void *sym_, uint16_t *tab, int lane) {
-    for (int i = lane; i < (1 << PBITS); i += 32) tab[i] = 0;   // code length 0: longer than the index, or no such code
+    for (int i = lane; i < (1 << PBITS); i += 32) tab[i] = 0;   // not in this table
     int mine = 0;
     if (lane >= 1 && lane <= 15)
         for (int s = 0; s < n; ++s) mine += (lens[s] == lane) ? 1 : 0;
@@ -148,7 +172,7 @@ __device__ bool tk_build(const uint8_t *lens, int n, uint16_t *cnt, uint16_t *fi
             else reinterpret_cast<uint16_t *>(sym_)[offs + k] = (uint16_t)s;
             if (lane <= PBITS) {
                 const uint32_t rev = __brev((uint32_t)(code + k)) >> (32 - lane);
-                const uint16_t e = (uint16_t)((DIST ? tk_dist_entry(s) : tk_lit_entry(s)) | (uint32_t)lane);
+                const uint16_t e = (uint16_t)(DIST ? tk_dist_entry(s, lane) : tk_lit_entry(s, lane));
                 for (uint32_t j = rev; j < (1u << PBITS); j += (1u << lane)) tab[j] = e;
             }
             ++k;
@@ -159,30 +183,78 @@ __device__ bool tk_build(const uint8_t *lens, int n, uint16_t *cnt, uint16_t *fi
     return ok;
 }
 
-constexpr int TK_MAXP = 8;                       // parts per blob at most
 constexpr uint32_t TK_NONE = 0xFFFFFFFFu;
+constexpr uint32_t TK_RANGE = 8192;              // compressed bytes per range, at least
 struct alignas(32) PartRec {
     uint32_t start_bit;    // where the part starts (bits from the blob's first byte); TK_NONE: no such part
     uint32_t end_bit;      // where it stopped: the start of the next part if the chain closes
     uint32_t n_tok, out_len;
-    int32_t status;
+    int32_t status;        // bit 16: the part decoded the final block
     uint32_t isize, crc;   // the trailer (last part only)
-    uint32_t flags;        // 1: the part decoded the final block
+    uint32_t tok_off;      // where its tokens are, from the blob's first token
 };
-// How many parts for a blob of gz_len compressed bytes.  Finding a part's start costs a scan of ~10 KB of bit offsets, and the
-// time of the token phase is set by its LONGEST serial piece, so blobs are cut only down to the size of the typical piece:
-// the batch's mean blob (a chromosome's last ctg is up to twice the others: two parts), or 1/4096 of the batch when that is
-// larger (a batch of few, large blobs is cut into 8 parts each), never below 32 KB.
-__device__ __forceinline__ uint32_t tk_part_target(const uint64_t *__restrict__ gz_off, int64_t n_blob) {
+
+// ---- phase P: ranges per blob -----------------------------------------------------------------------------------------
+// The batch has room for p_cap part records; the range size is TK_RANGE, or larger when the batch would need more records.
+__device__ __forceinline__ uint64_t tk_range_bytes(const uint64_t *__restrict__ gz_off, int64_t n_blob, uint64_t p_cap) {
     const uint64_t total = gz_off[n_blob] - gz_off[0];
-    const uint64_t mean = total / (uint64_t)n_blob, share = total >> 12;
-    uint64_t t = mean < share ? mean : share;
-    t = t < 32768 ? 32768 : t;
-    return (uint32_t)(t > 0x7FFFFFFFull ? 0x7FFFFFFFull : t);
+    const uint64_t room = p_cap > (uint64_t)n_blob + 1 ? p_cap - (uint64_t)n_blob - 1 : 1;
+    const uint64_t t = (total + room - 1) / room;
+    return t < TK_RANGE ? TK_RANGE : t;
 }
-__device__ __forceinline__ uint32_t tk_parts(uint64_t gz_len, uint32_t target) {
-    const uint64_t p = (gz_len + target / 2) / target;
-    return (uint32_t)(p < 1 ? 1 : (p > (uint64_t)TK_MAXP ? (uint64_t)TK_MAXP : p));
+// the first token of blob b (a multiple of 8) — the budget of a blob is half a token per output byte + 64
+__device__ __forceinline__ uint64_t tk_tok_base(uint64_t o0_rel, uint64_t blob) { return ((o0_rel >> 1) + 64ull * blob) & ~7ull; }
+// where the tokens of the part that is range j of np and starts at bit s go, from the blob's first token: in proportion to
+// the position in the compressed stream, a multiple of 8, and at least 8 tokens behind any earlier part
+__device__ __forceinline__ uint32_t tk_tok_off(uint64_t budget, uint32_t np, uint64_t nbits, uint64_t s, uint32_t j) {
+    return (uint32_t)((((budget - 8ull * np) * s / nbits) & ~7ull) + 8ull * j);
+}
+
+__global__ void __launch_bounds__(1024)
+inflate_parts_kernel(const uint64_t *__restrict__ gz_off, const uint64_t *__restrict__ out_off, int64_t n_blob, uint64_t p_cap,
+                     uint32_t *__restrict__ part_off) {
+    __shared__ uint32_t ws[32];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const uint64_t range = tk_range_bytes(gz_off, n_blob, p_cap), ob = out_off[0];
+    for (int64_t base = 0; base < n_blob; base += 1024) {
+        const int64_t b = base + threadIdx.x;
+        uint32_t v = 0;
+        if (b < n_blob) {
+            const uint64_t len = gz_off[b + 1] - gz_off[b];
+            const uint64_t budget = tk_tok_base(out_off[b + 1] - ob, (uint64_t)b + 1) - tk_tok_base(out_off[b] - ob, (uint64_t)b);
+            uint64_t np = (len + range - 1) / range;
+            if (np < 1 || len >= 0x10000000ull) np = 1;        // (bit offsets are 32-bit)
+            if (16ull * np > budget) np = 1;
+            v = (uint32_t)np;
+        }
+        uint32_t inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+            if ((threadIdx.x & 31) >= d) inc += t;
+        }
+        if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = inc;
+        __syncthreads();
+        uint32_t before = carry;
+        for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) before += ws[w];
+        if (b < n_blob) part_off[b] = before + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = before + inc;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) part_off[n_blob] = carry;
+}
+
+// the blob of part item: the last b with part_off[b] <= item
+__device__ __forceinline__ int64_t tk_blob_of(const uint32_t *__restrict__ part_off, int64_t n_blob, uint32_t item) {
+    int64_t lo = 0, hi = n_blob;
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (__ldg(part_off + mid) <= item) lo = mid; else hi = mid;
+    }
+    return lo;
 }
 
 // HLIT / HDIST / HCLEN and the code lengths of a dynamic block (the 3 header bits are already consumed): lens[0 .. hlit + hdist).
@@ -242,75 +314,206 @@ __device__ bool tk_dynamic_header(TkWin &br, uint8_t *lens, uint8_t *ctab, uint8
 }
 
 // ---- phase S: where can a part start? ------------------------------------------------------------------------------------
-// One warp per (blob, part j >= 1): the bit offsets from the part's nominal start (j / parts of the compressed bytes) on are
-// screened 32 at a time — BTYPE = 2, HLIT / HDIST in range, the code-length code complete (Kraft sum exactly 1) — and a
-// survivor is parsed in full by one lane: both codes of the block must be complete too.
 constexpr int SP_WARPS = 4;
-struct SpScratch { uint8_t lens[320]; uint8_t ctab[128]; uint8_t clen[32]; };
+struct SpWarp {
+    uint32_t words[36];         // the chunk: 32 words of bit offsets + the 3 words the last offsets reach into
+    uint16_t cand[1024];        // stage 1 survivors of the chunk: word << 5 | bit
+    uint32_t surv[64];          // stage 2 survivors: bit offset from the blob's first byte
+    uint8_t ctab[32][128];      // stage 3: the code-length code of each lane's candidate
+};
+// Stage 3, one candidate per lane: the whole dynamic header at bit `bit` (BFINAL) of the blob, Kraft sums kept on the fly —
+// true iff the literal/length code is complete and has an end-of-block code, and the distance code is complete (or a single code)
+__device__ bool sp_verify(const uint32_t *__restrict__ w, uint32_t n_words, uint32_t mis, uint32_t bit, uint8_t *ctab) {
+    uint64_t a = 8ull * mis + bit + 3;     // absolute bit in w[]
+    auto peek = [&]() -> uint32_t {        // 32 bits from a
+        const uint32_t k = (uint32_t)(a >> 5), sh = (uint32_t)(a & 31u);
+        const uint32_t q0 = __ldg(w + min(k, n_words - 1u)), q1 = __ldg(w + min(k + 1u, n_words - 1u));
+        return __funnelshift_r(q0, q1, sh);
+    };
+    uint32_t x = peek();
+    const int hlit = (int)(x & 31u) + 257, hdist = (int)((x >> 5) & 31u) + 1, hclen = (int)((x >> 10) & 15u) + 4;
+    if (hlit > 286 || hdist > 30) return false;
+    const uint64_t a_len = 8ull * mis + bit + 17;     // the 3-bit lengths of the code-length code
+    uint64_t cl = 0;                       // 3 bits per symbol of the code-length alphabet
+    uint64_t cnt = 0;                      // 8 bits per length
+    for (int i = 0; i < hclen; ++i) {
+        if (i % 8 == 0) a = a_len + 3ull * i, x = peek();
+        const uint32_t l = (x >> (3 * (i % 8))) & 7u;
+        cl |= (uint64_t)l << (3 * TK_CLORDER[i]);
+        if (l) cnt += 1ull << (8 * l);
+    }
+    a = a_len + 3ull * hclen;
+    uint64_t next = 0;                     // first canonical code of each length, 8 bits per length
+    {
+        int code = 0, left = 1, prevc = 0;
+        for (int l = 1; l <= 7; ++l) {
+            const int c = (int)((cnt >> (8 * l)) & 255u);
+            left = (left << 1) - c;
+            code = (code + prevc) << 1;
+            prevc = c;
+            next |= (uint64_t)(code & 255) << (8 * l);
+        }
+        if (left < 0) return false;
+    }
+    for (int i = 0; i < 128; i += 4) *reinterpret_cast<uint32_t *>(ctab + i) = 0u;
+    for (int i = 0; i < 19; ++i) {
+        const int l = (int)((cl >> (3 * i)) & 7u);
+        if (!l) continue;
+        const uint32_t code = (uint32_t)((next >> (8 * l)) & 255u);
+        next += 1ull << (8 * l);
+        const uint32_t rev = __brev(code) >> (32 - l);
+        for (uint32_t j = rev; j < 128u; j += (1u << l)) ctab[j] = (uint8_t)((i << 3) | l);
+    }
+    const int total = hlit + hdist;
+    int idx = 0, prev = 0, nd = 0;
+    int kl = 0, kd = 0;                    // Kraft sums in units of 2^-15
+    bool eob = false;
+    while (idx < total) {
+        x = peek();
+        const uint32_t ce = ctab[x & 127u];
+        if (!(ce & 7u)) return false;
+        a += ce & 7u;
+        x >>= ce & 7u;
+        const int s = (int)(ce >> 3);
+        int rep = 1, v = s;
+        if (s == 16) {
+            if (idx == 0) return false;
+            v = prev, rep = 3 + (int)(x & 3u), a += 2;
+        } else if (s == 17) v = 0, rep = 3 + (int)(x & 7u), a += 3;
+        else if (s == 18) v = 0, rep = 11 + (int)(x & 127u), a += 7;
+        if (idx + rep > total) return false;
+        if (v) {
+            const int unit = 1 << (15 - v);
+            const int in_l = min(rep, max(hlit - idx, 0));      // how many of the run fall into the literal/length alphabet
+            kl += in_l * unit;
+            kd += (rep - in_l) * unit;
+            nd += rep - in_l;
+            if (idx <= 256 && 256 < idx + rep) eob = true;
+            if (kl > (1 << 15) || kd > (1 << 15)) return false;
+        }
+        idx += rep;
+        prev = v;
+    }
+    return eob && kl == (1 << 15) && (kd == (1 << 15) || (nd == 1 && kd == (1 << 14)));
+}
+
 __global__ void __launch_bounds__(SP_WARPS * 32)
-inflate_split_kernel(const uint8_t *__restrict__ gz, const uint64_t *__restrict__ gz_off, int64_t n_blob, PartRec *__restrict__ rec) {
-    __shared__ SpScratch scr[SP_WARPS];
+inflate_split_kernel(const uint8_t *__restrict__ gz, const uint64_t *__restrict__ gz_off, int64_t n_blob,
+                     const uint32_t *__restrict__ part_off, PartRec *__restrict__ rec) {
+    __shared__ SpWarp sw_[SP_WARPS];
+    __shared__ uint8_t kraft3[512];        // Kraft sum (units of 1/128) of three 3-bit code lengths
+    for (int i = threadIdx.x; i < 512; i += SP_WARPS * 32) {
+        uint32_t s = 0;
+        for (int f = 0; f < 3; ++f) {
+            const uint32_t l = (i >> (3 * f)) & 7u;
+            s += l ? (128u >> l) : 0u;
+        }
+        kraft3[i] = (uint8_t)s;            // <= 192
+    }
+    __syncthreads();
     const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int64_t item = (int64_t)blockIdx.x * SP_WARPS + wib;
-    const int64_t blob = item / (TK_MAXP - 1);
-    const uint32_t j = (uint32_t)(item - blob * (TK_MAXP - 1)) + 1u;
-    if (blob >= n_blob) return;
-    const uint64_t len64 = gz_off[blob + 1] - gz_off[blob];
-    const uint32_t np = tk_parts(len64, tk_part_target(gz_off, n_blob));
-    PartRec &R = rec[blob * TK_MAXP + j];
-    uint32_t found = TK_NONE;
-    if (j < np && len64 < 0x10000000ull) {
+    SpWarp &S = sw_[wib];
+    const uint32_t n_items = part_off[n_blob];
+    for (uint32_t item = blockIdx.x * SP_WARPS + wib; item < n_items; item += gridDim.x * SP_WARPS) {
+        const int64_t blob = tk_blob_of(part_off, n_blob, item);
+        const uint32_t j = item - part_off[blob], np = part_off[blob + 1] - part_off[blob];
+        if (j == 0) continue;              // part 0 starts behind the gzip header
+        const uint64_t len64 = gz_off[blob + 1] - gz_off[blob];
         const uint8_t *in = gz + gz_off[blob];
         const uint32_t in_len = (uint32_t)len64, mis = (uint32_t)(reinterpret_cast<uintptr_t>(in) & 3u);
         const uint32_t *w = reinterpret_cast<const uint32_t *>(in - mis);
         const uint32_t n_words = (mis + in_len + 3u) >> 2;
-        auto ldw = [&](uint32_t i) { return i < n_words ? __ldg(w + i) : 0u; };
         const uint64_t bit0 = 8ull * ((uint64_t)in_len * j / np);
-        const uint64_t lim = min(8ull * ((uint64_t)in_len * (j + 1) / np), 8ull * (uint64_t)in_len - 160ull);
-        for (uint64_t base = bit0; base < lim && found == TK_NONE; base += 32) {
-            const uint64_t off = base + lane, a = 8ull * mis + off;
-            const uint32_t k = (uint32_t)(a >> 5), sh = (uint32_t)(a & 31u);
-            const uint32_t q0 = ldw(k), q1 = ldw(k + 1), q2 = ldw(k + 2), q3 = ldw(k + 3);
-            const uint32_t x0 = __funnelshift_r(q0, q1, sh), x1 = __funnelshift_r(q1, q2, sh), x2 = __funnelshift_r(q2, q3, sh);
-            const uint32_t type = (x0 >> 1) & 3u, hlit = (x0 >> 3) & 31u, hdist = (x0 >> 8) & 31u, hclen = ((x0 >> 13) & 15u) + 4u;
-            bool cand = off < lim && type == 2u && hlit <= 29u && hdist <= 29u;
-            if (cand) {
-                uint64_t v = ((uint64_t)x1 << 15) | (uint64_t)(x0 >> 17) | ((uint64_t)x2 << 47);   // the 3-bit lengths from bit 17 on
-                uint32_t kraft = 0;
-                for (uint32_t i = 0; i < hclen; ++i, v >>= 3) {
-                    const uint32_t l = (uint32_t)v & 7u;
-                    kraft += l ? (128u >> l) : 0u;
-                }
-                cand = kraft == 128u;
+        const uint64_t lim = min(8ull * ((uint64_t)in_len * (j + 1) / np), 8ull * (uint64_t)in_len > 160ull ? 8ull * (uint64_t)in_len - 160ull : 0ull);
+        uint32_t found = TK_NONE, n_surv = 0;
+        // stage 3 on the first min(n_surv, 32) survivors; the list is in rising order, so the lowest valid one is the answer
+        auto verify = [&]() {
+            const uint32_t n = min(n_surv, 32u);
+            const bool ok = lane < n && sp_verify(w, n_words, mis, S.surv[lane], S.ctab[lane]);
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, ok);
+            if (m) found = S.surv[__ffs(m) - 1];
+            __syncwarp();
+            const uint32_t rest = n_surv - n;
+            const uint32_t mv = lane < rest ? S.surv[n + lane] : 0u;
+            __syncwarp();
+            if (lane < rest) S.surv[lane] = mv;
+            n_surv = rest;
+            __syncwarp();
+        };
+        const uint64_t a0 = 8ull * mis + bit0, a1 = 8ull * mis + lim;           // absolute bits in w[]
+        for (uint64_t kc = a0 >> 5; (kc << 5) < a1 && found == TK_NONE; kc += 32) {
+            // ---- the chunk's words
+            {
+                const uint64_t k = kc + lane;
+                S.words[lane] = __ldg(w + min(k, (uint64_t)n_words - 1u));
+                if (lane < 4) S.words[32 + lane] = __ldg(w + min(k + 32, (uint64_t)n_words - 1u));
             }
-            unsigned m = __ballot_sync(0xFFFFFFFFu, cand);
-            while (m && found == TK_NONE) {
-                const uint32_t c = (uint32_t)__ffs(m) - 1u;
-                m &= m - 1;
-                int ok = 0;
-                if (lane == c) {
-                    TkWin br;
-                    br.w = w, br.n_words = n_words, br.mis = mis;
-                    br.seek_bit(off + 3);
-                    int hl = 0, hd = 0;
-                    SpScratch &S = scr[wib];
-                    if (tk_dynamic_header(br, S.lens, S.ctab, S.clen, &hl, &hd)) {
-                        int l1 = 1 << 15, l2 = 1 << 15, nd = 0;
-                        for (int i = 0; i < hl; ++i) l1 -= S.lens[i] ? (1 << (15 - S.lens[i])) : 0;
-                        for (int i = 0; i < hd; ++i) l2 -= S.lens[hl + i] ? (1 << (15 - S.lens[hl + i])) : 0, nd += S.lens[hl + i] != 0;
-                        ok = l1 == 0 && (l2 == 0 || (nd == 1 && l2 == (1 << 14)));
-                    }
+            __syncwarp();
+            // ---- stage 1: bit i of m is set iff offset 32 * (kc + lane) + i can be a dynamic block header
+            const uint64_t v = (uint64_t)S.words[lane] | ((uint64_t)S.words[lane + 1] << 32);
+            uint32_t m = (uint32_t)(~(v >> 1) & (v >> 2) & ~((v >> 4) & (v >> 5) & (v >> 6) & (v >> 7)) & ~((v >> 9) & (v >> 10) & (v >> 11) & (v >> 12)));
+            {
+                const uint64_t wa = (kc + lane) << 5;           // absolute bit of the lane's word
+                if (wa + 32 <= a0 || wa >= a1) m = 0;
+                else {
+                    if (wa < a0) m &= ~0u << (uint32_t)(a0 - wa);
+                    if (wa + 32 > a1) m &= ~0u >> (uint32_t)(wa + 32 - a1);
                 }
-                ok = __shfl_sync(0xFFFFFFFFu, ok, c);
-                if (ok) found = (uint32_t)(base + c);
+            }
+            const uint32_t cnt = __popc(m);
+            uint32_t inc = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+                if (lane >= (uint32_t)d) inc += t;
+            }
+            const uint32_t n_cand = __shfl_sync(0xFFFFFFFFu, inc, 31);
+            uint32_t at = inc - cnt;
+            while (m) {
+                const uint32_t i = (uint32_t)__ffs(m) - 1u;
+                m &= m - 1;
+                S.cand[at++] = (uint16_t)((lane << 5) | i);
+            }
+            __syncwarp();
+            // ---- stage 2: the code-length code is complete
+            for (uint32_t c0 = 0; c0 < n_cand && found == TK_NONE; c0 += 32) {
+                const uint32_t c = c0 + lane;
+                bool pass = false;
+                uint32_t bit = 0;
+                if (c < n_cand) {
+                    const uint32_t id = S.cand[c], wl = id >> 5, i = id & 31u;
+                    const uint32_t q0 = S.words[wl], q1 = S.words[wl + 1], q2 = S.words[wl + 2], q3 = S.words[wl + 3];
+                    const uint32_t x0 = __funnelshift_r(q0, q1, i), x1 = __funnelshift_r(q1, q2, i), x2 = __funnelshift_r(q2, q3, i);
+                    const uint32_t hclen = ((x0 >> 13) & 15u) + 4u;
+                    uint64_t f = ((uint64_t)x1 << 15) | (uint64_t)(x0 >> 17) | ((uint64_t)x2 << 47);     // the 3-bit lengths from bit 17 on
+                    f &= (1ull << (3u * hclen)) - 1ull;
+                    const uint32_t flo = (uint32_t)f, fhi = (uint32_t)(f >> 32);
+                    const uint32_t k = kraft3[flo & 511u] + kraft3[(flo >> 9) & 511u] + kraft3[(flo >> 18) & 511u] +
+                                       kraft3[__funnelshift_r(flo, fhi, 27) & 511u] + kraft3[(fhi >> 4) & 511u] + kraft3[(fhi >> 13) & 511u] +
+                                       kraft3[(fhi >> 22) & 511u];
+                    pass = k == 128u;
+                    bit = (uint32_t)((((kc + wl) << 5) + i) - 8ull * mis);
+                }
+                const unsigned pm = __ballot_sync(0xFFFFFFFFu, pass);
+                if (pass) S.surv[n_surv + __popc(pm & ((1u << lane) - 1u))] = bit;
+                n_surv += __popc(pm);
+                __syncwarp();
+                if (n_surv >= 32) verify();
             }
         }
+        while (n_surv && found == TK_NONE) verify();
+        if (lane == 0) rec[item].start_bit = found;
+        __syncwarp();
     }
-    if (lane == 0) R.start_bit = found;
 }
 
 enum { TS_HEADER = 0, TS_SYMBOLS = 1, TS_DONE = 2, TS_FINISHED = 3, TS_FETCH = 4 };
 constexpr int TK_GROUP = 8;
+#ifndef TK_UNROLL_N
+#define TK_UNROLL_N 8
+#endif
+constexpr int TK_UNROLL = TK_UNROLL_N;
+constexpr int32_t TK_FINAL = 1 << 16;
 
 // token: bits 0-8 length (0: literal, byte in bits 9-16; 3..258: match, distance in bits 9-24).
 // The 32 lanes decode 32 different streams, so the kernel is written to keep them CONVERGED: the symbol loop has one
@@ -318,62 +521,63 @@ constexpr int TK_GROUP = 8;
 // lock step; what only some lanes need — a block header, a code longer than the table index, the trailer — runs in short
 // divergent sections between votes, and table builds are done by the whole warp for one lane at a time.  (Lanes that each
 // follow their own path share the warp's one instruction stream: a first version written as 32 independent loops took
-// 1 400 cycles per symbol.)
-__global__ void __launch_bounds__(TK_THREADS)
+// 1 400 cycles per symbol.)  Whatever does not fit — a distance before the start of the output, an output or a token
+// budget exceeded, the end of the input — ends the part with a status; the resolver then hands the blob to the one-pass decoder.
+__global__ void __launch_bounds__(TK_THREADS, 1)
 inflate_tokens_kernel(const uint8_t *__restrict__ gz, const uint64_t *__restrict__ gz_off, int64_t n_blob,
-                      const uint64_t *__restrict__ out_off, uint32_t *__restrict__ tokens, PartRec *__restrict__ rec,
-                      unsigned long long *__restrict__ next_item) {
+                      const uint64_t *__restrict__ out_off, const uint32_t *__restrict__ part_off, uint32_t *__restrict__ tokens,
+                      PartRec *__restrict__ rec, TkSlow *__restrict__ slow, unsigned long long *__restrict__ next_item) {
     extern __shared__ __align__(16) uint8_t tk_smem[];
     __shared__ uint16_t s_lbase[32], s_dbase[32];   // (constant memory would serialise the lanes' different indices)
-    const int lane = threadIdx.x;
-    s_lbase[lane] = TK_LBASE[lane];
-    s_dbase[lane] = TK_DBASE[lane];
-    __syncwarp();
-    TkTables *tabs = reinterpret_cast<TkTables *>(tk_smem);
-    TkTables &T = tabs[lane];
-    // The kernel is PERSISTENT: a lane that has finished a part takes the next (blob, part) off a global counter, so the 32
-    // lanes of a warp stay busy although parts differ in length (statically, a warp would wait for its longest part).
-    const uint64_t n_items = (uint64_t)n_blob * TK_MAXP;
+    __shared__ uint8_t s_lext[32];
+    if (threadIdx.x < 32) {
+        s_lbase[threadIdx.x] = TK_LBASE[threadIdx.x];
+        s_dbase[threadIdx.x] = TK_DBASE[threadIdx.x];
+        s_lext[threadIdx.x] = TK_LEXT[threadIdx.x];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    TkFast *tabs = reinterpret_cast<TkFast *>(tk_smem) + (threadIdx.x & ~31);      // the warp's 32 tables
+    TkFast &F = tabs[lane];
+    TkSlow *slows = slow + ((size_t)blockIdx.x * TK_THREADS + (threadIdx.x & ~31));
+    TkSlow &T = slows[lane];
+    // The kernel is PERSISTENT: a lane that has finished a part takes the next one off a global counter, so the 32 lanes of
+    // a warp stay busy although parts differ in length (statically, a warp would wait for its longest part).
+    const uint32_t n_items = part_off[n_blob];
     const uint64_t ob = out_off[0];
-    const uint32_t target = tk_part_target(gz_off, n_blob);
     // ---- the lane's current part
     const uint8_t *in = gz;
     PartRec *R = rec;
-    uint32_t part = 0, next_start = TK_NONE, my_start = 0, cap = 0, in_len = 0, tcap = 0;
+    uint32_t next_start = TK_NONE, my_start = 0, cap = 0, in_len = 0, tcap = 0, tok_off = 0;
     uint32_t *tok = tokens;
-    uint32_t r_isize = 0, r_crc = 0, r_flags = 0, pos = 0, nt = 0;
+    uint32_t r_isize = 0, r_crc = 0, r_final = 0, pos = 0, nt = 0;
     int err = INF_OK, nlen = 288, ndist = 30;
     bool last = false;
     TkWin br;
-    br.w = reinterpret_cast<const uint32_t *>(gz), br.n_words = 0, br.mis = 0;
-    br.seek_bit(0);
+    br.w = reinterpret_cast<const uint32_t *>(gz), br.n_words = 1, br.mis = 0;
+    br.w0 = br.w1 = br.w2 = br.p0 = br.p1 = br.p2 = 0, br.o = 0, br.wi = 3;
     int state = TS_FETCH;
     auto fetch = [&]() {     // the next part that exists, or TS_DONE when the counter has run out
         for (;;) {
-            const uint64_t item = atomicAdd(next_item, 1ull);
-            if (item >= n_items) { state = TS_DONE; return; }
-            // long blobs first would be better still; items run part-major so that the parts of one blob start together
-            const uint64_t blob = item % (uint64_t)n_blob;
-            part = (uint32_t)(item / (uint64_t)n_blob);
-            const uint64_t len64 = gz_off[blob + 1] - gz_off[blob], o0 = out_off[blob] - ob, cap64 = out_off[blob + 1] - out_off[blob];
-            const uint32_t np = tk_parts(len64, target);
-            R = rec + blob * TK_MAXP;
-            if (part >= np || (part > 0 && R[part].start_bit == TK_NONE)) continue;
+            const unsigned long long item64 = atomicAdd(next_item, 1ull);
+            if (item64 >= n_items) { state = TS_DONE; return; }
+            const uint32_t item = (uint32_t)item64;
+            const int64_t blob = tk_blob_of(part_off, n_blob, item);
+            const uint32_t p0 = part_off[blob], part = item - p0, np = part_off[blob + 1] - p0;
+            R = rec + item;
+            if (part > 0 && R->start_bit == TK_NONE) continue;
             next_start = TK_NONE;
+            uint32_t next_j = np;
             for (uint32_t q = part + 1; q < np; ++q)
-                if (R[q].start_bit != TK_NONE) { next_start = R[q].start_bit; break; }
+                if (R[q - part].start_bit != TK_NONE) { next_start = R[q - part].start_bit, next_j = q; break; }
+            const uint64_t len64 = gz_off[blob + 1] - gz_off[blob], o0 = out_off[blob] - ob, cap64 = out_off[blob + 1] - out_off[blob];
             in = gz + gz_off[blob];
-            // the blob's token budget: half a token per output byte + 64 (the host sizes the buffer the same way), in equal shares
-            const uint64_t t0 = (o0 >> 1) + 64ull * blob, t1 = ((o0 + cap64) >> 1) + 64ull * (blob + 1);
-            const uint64_t ta = t0 + (t1 - t0) * part / np, tb = t0 + (t1 - t0) * (part + 1) / np;
-            tok = tokens + ta;
-            tcap = (uint32_t)min(tb - ta, (uint64_t)0xFFFFFFF0u);
             err = INF_OK;
-            if (cap64 > 0xFFFFFF00ull || len64 > 0x0FFFFFFFull) err = INF_ESIZE;     // output positions and bit offsets are 32-bit
+            if (cap64 > 0xFFFF0000ull || len64 > 0x0FFFFFFFull || len64 == 0) err = INF_ETOKENS;     // output positions and bit offsets are 32-bit
             cap = (uint32_t)cap64, in_len = (uint32_t)len64;
             br.mis = (uint32_t)(reinterpret_cast<uintptr_t>(in) & 3u);
             br.w = reinterpret_cast<const uint32_t *>(in - br.mis);
-            br.n_words = (br.mis + in_len + 3u) >> 2;
+            br.n_words = max((br.mis + in_len + 3u) >> 2, 1u);
             uint32_t p = 10;     // gzip header (RFC 1952): part 0
             if (!err && part == 0) {
                 if (in_len < 18 || in[0] != 0x1F || in[1] != 0x8B || in[2] != 8) err = INF_EHEADER;
@@ -386,14 +590,35 @@ inflate_tokens_kernel(const uint8_t *__restrict__ gz, const uint64_t *__restrict
                     if (p + 8 > in_len) err = INF_EHEADER;
                 }
             }
-            my_start = part == 0 ? 8u * p : R[part].start_bit;
-            r_isize = r_crc = r_flags = 0;
+            my_start = part == 0 ? 8u * p : R->start_bit;
+            // the part's tokens: from its own place to the next part's
+            const uint64_t tb = tk_tok_base(o0, (uint64_t)blob), budget = tk_tok_base(o0 + cap64, (uint64_t)blob + 1) - tb, nbits = 8ull * len64;
+            tok_off = 0, tcap = 0;
+            if (!err) {
+                tok_off = tk_tok_off(budget, np, nbits, my_start, part);
+                const uint32_t tok_end = next_start == TK_NONE ? (uint32_t)budget : tk_tok_off(budget, np, nbits, next_start, next_j);
+                tcap = tok_end - tok_off - 8u;      // a group of TK_GROUP symbols may start at nt <= tcap
+            }
+            tok = tokens + tb + tok_off;
+            r_isize = r_crc = r_final = 0;
             pos = nt = 0;
             last = false;
-            br.seek_bit(err ? 0u : my_start);
+            if (err) br.w0 = br.w1 = br.w2 = br.p0 = br.p1 = br.p2 = 0, br.o = 0, br.wi = 3, br.mis = 0;
+            else br.seek_bit(my_start);
             state = err ? TS_FINISHED : TS_HEADER;
             return;
         }
+    };
+    auto trailer = [&]() {   // CRC-32 and ISIZE (RFC 1952: size of the original input modulo 2^32); the resolver compares
+        const uint64_t t = (br.consumed_bits() + 7) >> 3;
+        if (t + 8 > in_len) err = INF_ETRUNC;
+        else {
+            const uint8_t *q = in + t;
+            r_crc = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24);
+            r_isize = (uint32_t)q[4] | ((uint32_t)q[5] << 8) | ((uint32_t)q[6] << 16) | ((uint32_t)q[7] << 24);
+            r_final = 1u;
+        }
+        state = TS_FINISHED;
     };
     __syncwarp();
     for (;;) {
@@ -402,9 +627,10 @@ inflate_tokens_kernel(const uint8_t *__restrict__ gz, const uint64_t *__restrict
             while (state == TS_FINISHED || state == TS_FETCH) {
                 if (state == TS_FINISHED) {
                     PartRec r;
-                    r.start_bit = my_start, r.end_bit = (uint32_t)br.consumed_bits(), r.n_tok = nt, r.out_len = pos, r.status = err;
-                    r.isize = r_isize, r.crc = r_crc, r.flags = r_flags;
-                    R[part] = r;
+                    r.start_bit = my_start, r.end_bit = (uint32_t)br.consumed_bits(), r.n_tok = nt, r.out_len = pos;
+                    r.status = err | (r_final ? TK_FINAL : 0);
+                    r.isize = r_isize, r.crc = r_crc, r.tok_off = tok_off;
+                    *R = r;
                 }
                 fetch();
             }
@@ -414,7 +640,8 @@ inflate_tokens_kernel(const uint8_t *__restrict__ gz, const uint64_t *__restrict
         if (__any_sync(0xFFFFFFFFu, state == TS_HEADER)) {
             bool build = false;
             int type = 0;
-            if (state == TS_HEADER && next_start != TK_NONE && (uint32_t)br.consumed_bits() >= next_start) {
+            if (state == TS_HEADER && (br.past_end() || (next_start != TK_NONE && (uint32_t)br.consumed_bits() >= next_start))) {
+                if (br.past_end()) err = INF_ETOKENS;
                 state = TS_FINISHED;               // the next part takes over here (the resolver checks that it is exactly here)
             } else if (state == TS_HEADER) {
                 const uint32_t hdr = br.bits(3);
@@ -453,17 +680,7 @@ inflate_tokens_kernel(const uint8_t *__restrict__ gz, const uint64_t *__restrict
                         build = true;
                     }
                 }
-                if (state == TS_HEADER && !build && last) {   // a stored block was the last one: the trailer
-                    const uint64_t t = (br.consumed_bits() + 7) >> 3;
-                    if (t + 8 > in_len) err = INF_ETRUNC;
-                    else {
-                        const uint8_t *q = in + t;
-                        r_crc = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24);
-                        r_isize = (uint32_t)q[4] | ((uint32_t)q[5] << 8) | ((uint32_t)q[6] << 16) | ((uint32_t)q[7] << 24);
-                        r_flags = 1u;
-                    }
-                    state = TS_FINISHED;
-                }
+                if (state == TS_HEADER && !build && last) trailer();   // a stored block was the last one
             }
             __syncwarp();
             unsigned bm = __ballot_sync(0xFFFFFFFFu, build);
@@ -471,9 +688,10 @@ inflate_tokens_kernel(const uint8_t *__restrict__ gz, const uint64_t *__restrict
                 const int j = __ffs(bm) - 1;
                 bm &= bm - 1;
                 const int nl = __shfl_sync(0xFFFFFFFFu, nlen, j), nd = __shfl_sync(0xFFFFFFFFu, ndist, j), ty = __shfl_sync(0xFFFFFFFFu, type, j);
-                TkTables &Tj = tabs[j];
-                const bool ok1 = tk_build<TK_LBITS, false>(Tj.lens, nl, Tj.lcnt, Tj.lfirst, Tj.loffs, Tj.lsym, Tj.ltab, lane);
-                const bool ok2 = tk_build<TK_DBITS, true>(Tj.lens + (ty == 1 ? 288 : nl), nd, Tj.dcnt, Tj.dfirst, Tj.doffs, Tj.dsym, Tj.dtab, lane);
+                TkSlow &Tj = slows[j];
+                TkFast &Fj = tabs[j];
+                const bool ok1 = tk_build<TK_LBITS, false>(Tj.lens, nl, Tj.lcnt, Tj.lfirst, Tj.loffs, Tj.lsym, Fj.ltab, lane);
+                const bool ok2 = tk_build<TK_DBITS, true>(Tj.lens + (ty == 1 ? 288 : nl), nd, Tj.dcnt, Tj.dfirst, Tj.doffs, Tj.dsym, Fj.dtab, lane);
                 if (lane == j) {
                     if (ok1 && ok2) state = TS_SYMBOLS;
                     else err = INF_ECODE, state = TS_FINISHED;
@@ -485,77 +703,56 @@ inflate_tokens_kernel(const uint8_t *__restrict__ gz, const uint64_t *__restrict
         if (__all_sync(0xFFFFFFFFu, state == TS_DONE)) break;
         if (__any_sync(0xFFFFFFFFu, state == TS_FINISHED)) continue;
         // ---- symbols: groups of TK_GROUP branch-free iterations that every lane executes in lock step.  A lane that meets
-        // something the body does not handle (a code longer than the table index, the end of a block, an error) commits
-        // nothing and sits out the rest of the group; the cases are sorted out between groups.
+        // something the body does not handle (a code that is not in its tables, the end of a block) commits nothing and sits
+        // out the rest of the group; the cases are sorted out between groups.
         for (;;) {
-            bool act = state == TS_SYMBOLS, slowf = false, eobf = false;
-#pragma unroll 1
+            if (state == TS_SYMBOLS && (nt > tcap || pos > cap || br.past_end())) err = INF_ETOKENS, state = TS_FINISHED;
+            bool act = state == TS_SYMBOLS;
+            const bool was = act;
+#pragma unroll TK_UNROLL
             for (int it = 0; it < TK_GROUP; ++it) {
                 const uint32_t lo = br.peek(), hi = br.peek_hi();
-                const uint32_t e = T.ltab[lo & ((1u << TK_LBITS) - 1u)];
-                const uint32_t cl = e & 15u, sym = e >> 7, ex = (e >> 4) & 7u;
-                const bool is_lit = sym < 256u, is_len = sym - 257u < 29u;
-                const uint32_t len = s_lbase[(sym - 257u) & 31u] + ((lo >> cl) & ((1u << ex) - 1u));
-                const uint32_t n1 = cl + ex;                                  // <= 9 + 5
+                const uint32_t e = F.ltab[lo & ((1u << TK_LBITS) - 1u)];
+                const uint32_t n1 = e & 15u, ex = (e >> 4) & 7u, v = e >> 8;
+                const bool is_len = (e & 128u) != 0u;
+                const uint32_t len = v + 3u + ((lo >> (n1 - ex)) & ((1u << ex) - 1u));
                 const uint32_t lo2 = __funnelshift_r(lo, hi, n1);             // the window behind the length symbol
-                const uint32_t d = T.dtab[lo2 & ((1u << TK_DBITS) - 1u)];
-                const uint32_t dl = d & 15u, dx = (d >> 4) & 15u;
-                const uint32_t dist = s_dbase[(d >> 8) & 31u] + ((lo2 >> dl) & ((1u << dx) - 1u));
-                const bool slow = cl == 0u || (is_len && dl == 0u);
-                const bool eob = !slow && sym == 256u;
-                int e2 = INF_OK;
-                if (!slow && !eob) {
-                    if (!(is_lit | is_len) || (is_len && (d & (1u << 13)))) e2 = INF_ECODE;
-                    else if (is_len && part == 0u && dist > pos) e2 = INF_EDIST;   // (later parts do not know their position: the resolver checks)
-                    else if (is_lit ? pos >= cap : len > cap - pos) e2 = INF_EOVERFLOW;
-                    else if (nt >= tcap) e2 = INF_ETOKENS;
+                const uint32_t d = F.dtab[lo2 & ((1u << TK_DBITS) - 1u)];
+                const uint32_t n2 = d & 31u, dx = (d >> 5) & 15u;
+                const uint32_t dist = s_dbase[d >> 9] + ((lo2 >> (n2 - dx)) & ((1u << dx) - 1u));
+                const bool commit = act && n1 != 0u && !(is_len && n2 == 0u);
+                br.drop(commit ? n1 + (is_len ? n2 : 0u) : 0u);
+                if (commit) {
+                    tok[nt++] = is_len ? ((dist << 9) | len) : (v << 9);
+                    pos += is_len ? len : 1u;
                 }
-                const bool commit = act && !slow && e2 == INF_OK;
-                br.drop(commit ? n1 + (is_len ? dl + dx : 0u) : 0u);
-                if (commit && !eob) {
-                    tok[nt++] = is_lit ? sym << 9 : ((dist << 9) | len);
-                    pos += is_lit ? 1u : len;
-                }
-                if (act) {
-                    slowf = slow;
-                    eobf = eob;
-                    if (!slow && e2 != INF_OK) err = e2, state = TS_FINISHED;
-                    act = commit && !eob;
-                }
+                act = commit;
             }
-            if (__any_sync(0xFFFFFFFFu, slowf)) {   // one symbol (and its distance) through the canonical decoder
-                if (slowf) {
-                    uint32_t pk = br.peek();
-                    uint32_t e = T.ltab[pk & ((1u << TK_LBITS) - 1u)];
-                    if ((e & 15u) == 0u) {
-                        uint32_t cl;
-                        const int k = tk_decode_slow<TK_LBITS>(pk, T.lcnt, T.lfirst, T.loffs, &cl);
-                        e = (k < 0 || k >= nlen) ? ((300u << 7) | 1u) : (tk_lit_entry(T.lsym[k]) | cl);
-                    }
-                    const uint32_t cl = e & 15u, sym = e >> 7, ex = (e >> 4) & 7u;
+            bool eobf = false;
+            if (__any_sync(0xFFFFFFFFu, was && !act)) {   // one symbol (and its distance) through the canonical decoder
+                if (was && !act) {
+                    uint32_t pk = br.peek(), cl;
+                    const int k = tk_decode_slow(pk, T.lcnt, T.lfirst, T.loffs, &cl);
+                    const uint32_t sym = (k < 0 || k >= nlen) ? 300u : T.lsym[k];
                     const bool is_lit = sym < 256u, is_len = sym - 257u < 29u;
+                    const uint32_t ex = s_lext[(sym - 257u) & 31u];
                     const uint32_t len = s_lbase[(sym - 257u) & 31u] + ((pk >> cl) & ((1u << ex) - 1u));
-                    br.drop(cl + ex);
+                    br.drop(cl + (is_len ? ex : 0u));
                     uint32_t dist = 0;
                     if (is_len) {
                         pk = br.peek();
-                        uint32_t d = T.dtab[pk & ((1u << TK_DBITS) - 1u)];
-                        if ((d & 15u) == 0u) {
-                            uint32_t dl;
-                            const int k = tk_decode_slow<TK_DBITS>(pk, T.dcnt, T.dfirst, T.doffs, &dl);
-                            d = (k < 0 || k >= ndist) ? ((1u << 13) | 1u) : (tk_dist_entry(T.dsym[k]) | dl);
-                        }
-                        const uint32_t dl = d & 15u, dx = (d >> 4) & 15u;
-                        dist = s_dbase[(d >> 8) & 31u] + ((pk >> dl) & ((1u << dx) - 1u));
+                        uint32_t dl;
+                        const int k2 = tk_decode_slow(pk, T.dcnt, T.dfirst, T.doffs, &dl);
+                        const uint32_t ds = (k2 < 0 || k2 >= ndist) ? 31u : T.dsym[k2];
+                        if (ds > 29u) err = INF_ECODE;
+                        const uint32_t dx = TK_DEXT[ds];
+                        dist = s_dbase[ds] + ((pk >> dl) & ((1u << dx) - 1u));
                         br.drop(dl + dx);
-                        if (d & (1u << 13)) err = INF_ECODE;
-                        else if (part == 0u && dist > pos) err = INF_EDIST;
                     }
                     if (sym == 256u) eobf = true;
                     else if (!(is_lit | is_len)) err = INF_ECODE;
-                    else if (!err) {
-                        if (is_lit ? pos >= cap : len > cap - pos) err = INF_EOVERFLOW;
-                        else if (nt >= tcap) err = INF_ETOKENS;
+                    else if (!err) {      // (nt <= tcap + TK_GROUP - 1 here, and the part's room is tcap + 8)
+                        if (nt >= tcap + 8u) err = INF_ETOKENS;
                         else {
                             tok[nt++] = is_lit ? sym << 9 : ((dist << 9) | len);
                             pos += is_lit ? 1u : len;
@@ -567,18 +764,8 @@ inflate_tokens_kernel(const uint8_t *__restrict__ gz, const uint64_t *__restrict
             }
             if (eobf && state == TS_SYMBOLS) {       // end of block
                 if (!last) state = TS_HEADER;
-                else {
-                    // the trailer: CRC-32 and ISIZE (RFC 1952: size of the original input modulo 2^32); the resolver compares
-                    const uint64_t t = (br.consumed_bits() + 7) >> 3;
-                    if (t + 8 > in_len) err = INF_ETRUNC;
-                    else {
-                        const uint8_t *q = in + t;
-                        r_crc = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24);
-                        r_isize = (uint32_t)q[4] | ((uint32_t)q[5] << 8) | ((uint32_t)q[6] << 16) | ((uint32_t)q[7] << 24);
-                        r_flags = 1u;
-                    }
-                    state = TS_FINISHED;
-                }
+                else if (pos > cap) err = INF_ETOKENS, state = TS_FINISHED;
+                else trailer();
             }
             __syncwarp();
             if (__any_sync(0xFFFFFFFFu, state == TS_HEADER || state == TS_FINISHED) || !__any_sync(0xFFFFFFFFu, state == TS_SYMBOLS)) break;
@@ -590,32 +777,35 @@ inflate_tokens_kernel(const uint8_t *__restrict__ gz, const uint64_t *__restrict
 constexpr int RS_WARPS = 4;
 __global__ void __launch_bounds__(RS_WARPS * 32)
 inflate_resolve_kernel(const uint64_t *__restrict__ gz_off, int64_t n_blob, uint8_t *out_base, const uint64_t *__restrict__ out_off,
-                       const uint32_t *__restrict__ tokens, const PartRec *__restrict__ rec, int32_t *__restrict__ status,
-                       uint32_t *__restrict__ crc_want) {
+                       const uint32_t *__restrict__ part_off, const uint32_t *__restrict__ tokens, const PartRec *__restrict__ rec,
+                       int32_t *__restrict__ status, uint32_t *__restrict__ crc_want) {
     const uint32_t lane = threadIdx.x & 31;
     const int64_t blob = (int64_t)blockIdx.x * RS_WARPS + (threadIdx.x >> 5);
     if (blob >= n_blob) return;
     const uint64_t o0 = out_off[blob], ob = out_off[0], cap = out_off[blob + 1] - o0;
-    const uint32_t np = tk_parts(gz_off[blob + 1] - gz_off[blob], tk_part_target(gz_off, n_blob));
-    const PartRec *R = rec + blob * TK_MAXP;
+    const uint32_t np = part_off[blob + 1] - part_off[blob];
+    const PartRec *R = rec + part_off[blob];
     // ---- the chain: every part ended where the next one started, no part failed, the last one saw the final block, and the
     // sizes agree with the trailer and with the caller.  Part 0 alone decides real errors (it starts at a known place);
     // anything else that does not fit sends the blob to the one-pass decoder (INF_ETOKENS), which reports what is wrong.
     int st = INF_OK;
     {
-        uint32_t prev_end = 0, total = 0, last_flags = 0, isize = 0, crc = 0;
-        bool first = true;
+        uint32_t prev_end = 0, total = 0, isize = 0, crc = 0;
+        bool first = true, final_seen = false;
         for (uint32_t q = 0; q < np; ++q) {
             const PartRec r = R[q];
             if (q > 0 && r.start_bit == TK_NONE) continue;
-            if (r.status != INF_OK) { st = (q == 0 && r.status != INF_ETOKENS) ? r.status : INF_ETOKENS; break; }
+            const int rs = r.status & 0xFFFF;
+            if (rs != INF_OK) { st = (q == 0 && rs != INF_ETOKENS) ? rs : INF_ETOKENS; break; }
             if (!first && r.start_bit != prev_end) { st = INF_ETOKENS; break; }
+            if (final_seen) { st = INF_ETOKENS; break; }      // a part behind the final block
             first = false;
             prev_end = r.end_bit;
             total += r.out_len;
-            last_flags = r.flags, isize = r.isize, crc = r.crc;
+            final_seen = (r.status & TK_FINAL) != 0;
+            isize = r.isize, crc = r.crc;
         }
-        if (st == INF_OK && !(last_flags & 1u)) st = INF_ETOKENS;
+        if (st == INF_OK && !final_seen) st = INF_ETOKENS;
         if (st == INF_OK && (isize != total || (uint64_t)total != cap)) st = np > 1 ? INF_ETOKENS : INF_ESIZE;
         if (st == INF_OK && crc_want && lane == 0) crc_want[blob] = crc;
     }
@@ -624,12 +814,12 @@ inflate_resolve_kernel(const uint64_t *__restrict__ gz_off, int64_t n_blob, uint
         return;
     }
     uint8_t *out = out_base + o0;
-    const uint64_t t0 = ((o0 - ob) >> 1) + 64ull * (uint64_t)blob, t1 = ((o0 - ob + cap) >> 1) + 64ull * (uint64_t)(blob + 1);
+    const uint64_t t0 = tk_tok_base(o0 - ob, (uint64_t)blob);
     uint32_t P0 = 0;                                  // bytes written so far
     bool bad = false;                                 // a distance that reaches before the start of the output
     for (uint32_t q = 0; q < np; ++q) {
       if (q > 0 && R[q].start_bit == TK_NONE) continue;
-      const uint32_t *tok = tokens + (t0 + (t1 - t0) * q / np);
+      const uint32_t *tok = tokens + t0 + R[q].tok_off;
       const uint32_t nt = R[q].n_tok;
       uint32_t t_next = lane < nt ? __ldg(tok + lane) : 0u;
       for (uint32_t k0 = 0; k0 < nt; k0 += 32) {
@@ -646,7 +836,7 @@ inflate_resolve_kernel(const uint64_t *__restrict__ gz_off, int64_t n_blob, uint
         }
         const uint32_t total = __shfl_sync(0xFFFFFFFFu, end, 31);
         const uint32_t start = end - n_out;          // inside the batch
-        if (have && len_f != 0u && hi > P0 + start) bad = true;
+        if (have && len_f != 0u && (hi > P0 + start || hi == 0u)) bad = true;
         if ((uint64_t)P0 + total > cap) bad = true;
         if (__any_sync(0xFFFFFFFFu, bad)) break;
         // the batch's bytes, 32 at a time and in order: byte b belongs to the first token whose end is > b.  A match byte is
@@ -802,35 +992,44 @@ crc32_fold_kernel(const uint64_t *__restrict__ out_off, int64_t n_blob, const ui
 int32_t launch_gunzip2(PerDevice &pd, cudaStream_t st, const uint8_t *d_gz, const uint64_t *d_gz_off, int64_t n_blob, uint8_t *d_out,
                        const uint64_t *d_out_off, int32_t *d_status, uint64_t total_out, int decoder, bool check_crc) {
     if (n_blob == 0) return GAMS_CUDA_OK;
-    const int64_t items = n_blob * TK_MAXP, blocks = (items + TK_THREADS - 1) / TK_THREADS;
-    if (blocks >= (1ll << 31)) {
+    if (n_blob >= (1ll << 30)) {
         set_error("gunzip: too many blobs for one launch");
         return GAMS_CUDA_EINVAL;
     }
-    // scratch: tokens | part records | crc_want | piece_off | piece_crc
+    static int n_sm = 0;
+    if (!n_sm) CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, pd.device));
+    // part records: sequence compresses ~3:1, so ranges of TK_RANGE compressed bytes are ~total_out / (3 TK_RANGE); room for a
+    // ratio of 2, and the range grows when the batch compresses worse (tk_range_bytes)
+    const uint64_t p_cap = std::min<uint64_t>(total_out / (2ull * TK_RANGE) + 2ull * (uint64_t)n_blob + 64, 0x7FFFFFF0ull);
+    const uint64_t n_lanes = (uint64_t)n_sm * TK_THREADS;
+    // scratch: tokens | part records | part_off | per-lane header scratch | crc_want | piece_off | piece_crc | counter
     const uint64_t n_tokens = decoder == 0 ? (total_out >> 1) + 64ull * (uint64_t)(n_blob + 1) + 64 : 0;
     const uint64_t n_piece_max = total_out / CRC_PIECE + (uint64_t)n_blob + 1;
-    const size_t o_rec = ((size_t)n_tokens * 4 + 31) & ~(size_t)31, o_crc = o_rec + (decoder == 0 ? (size_t)items * sizeof(PartRec) : 0),
+    const size_t o_rec = ((size_t)n_tokens * 4 + 31) & ~(size_t)31, o_poffs = o_rec + (decoder == 0 ? (size_t)p_cap * sizeof(PartRec) : 0),
+                 o_slow = (o_poffs + (decoder == 0 ? (size_t)(n_blob + 1) * 4 : 0) + 15) & ~(size_t)15,
+                 o_crc = o_slow + (decoder == 0 ? (size_t)n_lanes * sizeof(TkSlow) : 0),
                  o_poff = (o_crc + (size_t)n_blob * 4 + 15) & ~(size_t)15, o_pcrc = o_poff + (size_t)(n_blob + 1) * 8,
                  bytes = o_pcrc + (check_crc ? (size_t)n_piece_max * 4 : 0) + 64;
     int32_t rc;
     if ((rc = pd.scratch[7].reserve(bytes))) return rc;
     uint8_t *base = pd.scratch[7].as<uint8_t>();
     uint32_t *d_tok = reinterpret_cast<uint32_t *>(base), *d_crc = reinterpret_cast<uint32_t *>(base + o_crc),
-             *d_pcrc = reinterpret_cast<uint32_t *>(base + o_pcrc);
+             *d_pcrc = reinterpret_cast<uint32_t *>(base + o_pcrc), *d_parts = reinterpret_cast<uint32_t *>(base + o_poffs);
     PartRec *d_rec = reinterpret_cast<PartRec *>(base + o_rec);
+    TkSlow *d_slow = reinterpret_cast<TkSlow *>(base + o_slow);
     uint64_t *d_poff = reinterpret_cast<uint64_t *>(base + o_poff);
     unsigned long long *d_counter = reinterpret_cast<unsigned long long *>(base + ((bytes - 16) & ~(size_t)7));
     if (decoder == 0) {
-        const size_t smem = sizeof(TkTables) * TK_THREADS;
+        const size_t smem = sizeof(TkFast) * TK_THREADS;
         CUDA_TRY(cudaFuncSetAttribute(inflate_tokens_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const int64_t s_items = n_blob * (TK_MAXP - 1);
-        inflate_split_kernel<<<(unsigned)((s_items + SP_WARPS - 1) / SP_WARPS), SP_WARPS * 32, 0, st>>>(d_gz, d_gz_off, n_blob, d_rec);
+        inflate_parts_kernel<<<1, 1024, 0, st>>>(d_gz_off, d_out_off, n_blob, p_cap, d_parts);
+        const unsigned s_blocks = (unsigned)std::min<uint64_t>((p_cap + SP_WARPS - 1) / SP_WARPS, (uint64_t)n_sm * 16);
+        inflate_split_kernel<<<s_blocks, SP_WARPS * 32, 0, st>>>(d_gz, d_gz_off, n_blob, d_parts, d_rec);
         CUDA_TRY(cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), st));
-        const int64_t t_blocks = std::min<int64_t>(blocks, 148 * 2);   // two warps of 32 lanes per SM hold their tables in shared memory
-        inflate_tokens_kernel<<<(unsigned)t_blocks, TK_THREADS, smem, st>>>(d_gz, d_gz_off, n_blob, d_out_off, d_tok, d_rec, d_counter);
-        inflate_resolve_kernel<<<(unsigned)((n_blob + RS_WARPS - 1) / RS_WARPS), RS_WARPS * 32, 0, st>>>(d_gz_off, n_blob, d_out, d_out_off, d_tok,
-                                                                                                     d_rec, d_status, check_crc ? d_crc : nullptr);
+        const unsigned t_blocks = (unsigned)std::min<uint64_t>((p_cap + TK_THREADS - 1) / TK_THREADS, (uint64_t)n_sm);
+        inflate_tokens_kernel<<<t_blocks, TK_THREADS, smem, st>>>(d_gz, d_gz_off, n_blob, d_out_off, d_parts, d_tok, d_rec, d_slow, d_counter);
+        inflate_resolve_kernel<<<(unsigned)((n_blob + RS_WARPS - 1) / RS_WARPS), RS_WARPS * 32, 0, st>>>(d_gz_off, n_blob, d_out, d_out_off, d_parts,
+                                                                                                     d_tok, d_rec, d_status, check_crc ? d_crc : nullptr);
         // blobs that did not fit their token budget, or whose chain of parts did not close: the one-pass kernel
         if ((rc = launch_gunzip_only(st, d_gz, d_gz_off, n_blob, d_out, d_out_off, d_status, INF_ETOKENS, check_crc ? d_crc : nullptr))) return rc;
     } else {
