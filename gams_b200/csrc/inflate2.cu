@@ -34,17 +34,25 @@
 
 namespace gams {
 
-constexpr int TK_WARPS = 11;                   // warps per CTA, one CTA per SM: 352 parts in flight per SM
+#ifndef TK_WARPS_N
+#define TK_WARPS_N 15
+#endif
+constexpr int TK_WARPS = TK_WARPS_N;           // warps per CTA, one CTA per SM: 480 parts in flight per SM
 constexpr int TK_THREADS = TK_WARPS * 32;
-constexpr int TK_LBITS = 6, TK_DBITS = 8;      // level-1 sequence data: 0.4 % of the literal/length codes and 0.6 % of the distance codes are longer
-// per-thread tables in shared memory, 16-bit entries; the stride in 32-bit words is odd, so equal indices of different threads
-// fall into different banks
+constexpr int TK_LBITS = 6, TK_DBITS = 7;      // level-1 sequence data: 0.4 % of the literal/length codes and 1.8 % of the distance codes are longer
+constexpr int TK_RING = 16;                    // words of the compressed stream staged ahead in shared memory
+// per-thread state in shared memory; the stride in 32-bit words is odd, so equal indices of different threads fall into
+// different banks
 struct TkFast {
-    uint16_t ltab[1 << TK_LBITS];   // bits 0-3 code length + extra bits (0: not in this table — a longer code, end of block, no such code),
-                                    //   4-6 extra bits, 7: a length symbol, 8-15 the literal byte or the base length - 3
-    uint16_t dtab[1 << TK_DBITS];   // bits 0-4 code length + extra bits (0: not in this table), 5-8 extra bits, 9-13 symbol (0..29)
+    uint16_t ltab[1 << TK_LBITS];   // bits 0-3 code length + extra bits, 4-6 extra bits, 7: a length symbol, 8-15 the literal byte or the
+                                    //   base length - 3.  Bits 0-3 zero: not for the branch-free body — 0: a longer code (or none),
+                                    //   0x8000 | code length << 4: end of block, 0x4000: a symbol that must not occur (286, 287)
+    uint16_t dtab[1 << TK_DBITS];   // bits 0-4 code length + extra bits, 5-8 extra bits, 9-13 symbol (0..29); 0: a longer code (or
+                                    //   none), 0x8000: a symbol that must not occur (30, 31)
     uint32_t pad;
 };
+// (and a ring of TK_RING words per thread behind the tables, 16-byte aligned for cp.async)
+constexpr size_t TK_SMEM = (sizeof(TkFast) + 4 * TK_RING) * TK_THREADS;
 static_assert(sizeof(TkFast) % 4 == 0 && (sizeof(TkFast) / 4) % 2 == 1, "odd word stride");
 // per-thread scratch in global memory: what a block header needs while it is parsed, and the canonical decoder of the codes
 // that are longer than a table index
@@ -69,42 +77,63 @@ __constant__ uint8_t TK_CLORDER[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 
 
 // The bit window of one thread: three consecutive aligned words of the blob and a bit offset o < 32 into the first — 64 valid
 // bits from the current position in two funnel shifts, enough for a length and a distance symbol with their extra bits (48
-// bits at most) without a refill in between.  Two more words are loaded ahead, so a rotation never waits for memory, and the
-// cache line two lines further down is prefetched.  Loads are clamped to the blob's last word, not predicated: bits behind
-// the end of a blob are never part of a valid stream (the trailer is 8 bytes), and a decoder that runs into them stops at
-// the checks of its caller.
+// bits at most) without a refill in between — and one more word in a register.  What follows is staged in a ring of 16 words
+// in shared memory by cp.async, 16 bytes at a time and 8 to 11 words (some 30 symbols) ahead of the window: the copy needs no
+// register, so nothing in the symbol loop ever waits for global memory.  (With the next words loaded into registers the
+// compiler's register moves at the loop's joins read the loaded register an iteration later, and with 227 KB of the SM
+// configured as shared memory the L1 is too small to hold a prefetched line per thread: 17 % of the kernel's samples.)
+// Bytes behind the blob's end read as zero (cp.async src-size), never part of a valid stream: the trailer is 8 bytes.
 struct TkWin {
-    const uint32_t *w;
-    uint32_t n_words, wi, mis;      // w0 w1 w2 = w[wi - 3 .. wi - 1], p0 p1 p2 = w[wi .. wi + 2]
-    uint32_t w0, w1, w2, p0, p1, p2, o;
-    __device__ __forceinline__ uint32_t ld(uint32_t i) const { return __ldg(w + min(i, n_words - 1u)); }   // n_words >= 1
-    __device__ __forceinline__ void seek(uint32_t byte) {
-        const uint32_t a = mis + byte, k = a >> 2;
-        o = (a & 3u) * 8u;
-        w0 = ld(k), w1 = ld(k + 1), w2 = ld(k + 2), p0 = ld(k + 3), p1 = ld(k + 4), p2 = ld(k + 5);
-        wi = k + 3;
+    const uint8_t *base;             // the blob's first byte rounded down to 16 bytes
+    uint32_t n_bytes, n_words;       // from base to the blob's end
+    uint32_t wi, mis;                // w0 w1 w2 p0 = words wi - 3 .. wi of base; mis: bytes between base and the blob's first byte
+    uint32_t w0, w1, w2, p0, o;
+    uint32_t ring;                   // shared-memory address of the lane's ring; word k of the stream lives in slot k & 15
+    __device__ __forceinline__ void set_blob(const uint8_t *in, uint32_t in_len) {
+        mis = (uint32_t)(reinterpret_cast<uintptr_t>(in) & 15u);
+        base = in - mis;
+        n_bytes = mis + in_len;
+        n_words = (n_bytes + 3u) >> 2;
     }
-    __device__ __forceinline__ uint32_t peek() const { return __funnelshift_r(w0, w1, o); }      // bits 0..31 from the position
-    __device__ __forceinline__ uint32_t peek_hi() const { return __funnelshift_r(w1, w2, o); }   // bits 32..63
-    __device__ __forceinline__ void rotate() {
-        w0 = w1, w1 = w2, w2 = p0, p0 = p1, p1 = p2;
-        ++wi;
-        p2 = ld(wi + 2);      // (used three rotations from now: the load is not waited for)
-#ifndef TK_NO_PREFETCH
-        if ((wi & 31u) == 0u && wi + 64u < n_words) asm volatile("prefetch.global.L1 [%0];" ::"l"(w + wi + 64));
-#endif
+    __device__ __forceinline__ void fetch4(uint32_t k4) const {     // words k4 .. k4 + 3 (k4 a multiple of 4) into their slots
+        const uint32_t byte = 4u * k4;
+        const uint32_t have = byte < n_bytes ? min(n_bytes - byte, 16u) : 0u;
+        const uint8_t *src = base + (have ? byte : 0u);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(ring + 4u * (k4 & (TK_RING - 1u))), "l"(src), "r"(have) : "memory");
     }
-    __device__ __forceinline__ void drop(uint32_t n) {   // n <= 63 (0 is a no-op).  (A branch-free rotation — selects and a
-        o += n;                                          //  predicated load — was measured slower: 120 vs 110 ms.)
-        if (o >= 32u) { rotate(); o -= 32u; }
-        if (o >= 32u) { rotate(); o -= 32u; }
+    __device__ __forceinline__ uint32_t slot(uint32_t k) const {
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(ring + 4u * (k & (TK_RING - 1u))) : "memory");
+        return v;
     }
     __device__ __forceinline__ void seek_bit(uint64_t bit) {   // position given in bits from the blob's first byte
         const uint64_t a = 8ull * mis + bit;
-        const uint32_t k = (uint32_t)(a >> 5);
+        const uint32_t k = (uint32_t)(a >> 5), k4 = k & ~3u;
         o = (uint32_t)(a & 31u);
-        w0 = ld(k), w1 = ld(k + 1), w2 = ld(k + 2), p0 = ld(k + 3), p1 = ld(k + 4), p2 = ld(k + 5);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");     // (nothing of an earlier position may land in the ring later)
+        fetch4(k4), fetch4(k4 + 4), fetch4(k4 + 8), fetch4(k4 + 12);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        w0 = slot(k), w1 = slot(k + 1), w2 = slot(k + 2), p0 = slot(k + 3);
         wi = k + 3;
+    }
+    __device__ __forceinline__ void seek(uint32_t byte) { seek_bit(8ull * byte); }
+    __device__ __forceinline__ uint32_t peek() const { return __funnelshift_r(w0, w1, o); }      // bits 0..31 from the position
+    __device__ __forceinline__ uint32_t peek_hi() const { return __funnelshift_r(w1, w2, o); }   // bits 32..63
+    __device__ __forceinline__ void rotate() {
+        w0 = w1, w1 = w2, w2 = p0;
+        ++wi;
+        p0 = slot(wi);
+        if ((wi & 3u) == 0u) {       // words wi .. wi + 7 are in the ring (or on their way); wi + 8 .. wi + 11 replace wi - 8 .. wi - 5
+            fetch4(wi + 8);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 1;" ::: "memory");   // the copy before this one (four rotations ago) has landed
+        }
+    }
+    __device__ __forceinline__ void drop(uint32_t n) {   // n <= 63 (0 is a no-op)
+        o += n;
+        if (o >= 32u) { rotate(); o -= 32u; }
+        if (o >= 32u) { rotate(); o -= 32u; }
     }
     __device__ __forceinline__ uint32_t bits(uint32_t n) { const uint32_t v = peek() & ((1u << n) - 1u); drop(n); return v; }   // n < 32
     __device__ __forceinline__ uint64_t consumed_bits() const { return 32ull * (wi - 3) + o - 8ull * mis; }
@@ -113,32 +142,34 @@ struct TkWin {
 
 __device__ __forceinline__ uint32_t tk_lit_entry(int s, int code_len) {
     if (s < 256) return ((uint32_t)s << 8) | (uint32_t)code_len;
-    if (s >= 257 && s <= 285) {
+    if (s == 256) return 0x8000u | ((uint32_t)code_len << 4);
+    if (s <= 285) {
         const uint32_t ex = TK_LEXT[s - 257];
         return ((uint32_t)(TK_LBASE[s - 257] - 3) << 8) | 128u | (ex << 4) | ((uint32_t)code_len + ex);
     }
-    return 0u;     // end of block, 286, 287: the careful path
+    return 0x4000u;
 }
 __device__ __forceinline__ uint32_t tk_dist_entry(int s, int code_len) {
-    if (s > 29) return 0u;
+    if (s > 29) return 0x8000u;
     const uint32_t dx = TK_DEXT[s];
     return ((uint32_t)s << 9) | (dx << 5) | ((uint32_t)code_len + dx);
 }
 
-// canonical decoding of a code of any length: position of the symbol in canonical order, or -1.  The code of length l is the
-// top l bits of the bit-reversed window; it belongs to this length iff it lies in [first[l], first[l] + cnt[l]).
-__device__ __forceinline__ int tk_decode_slow(uint32_t pk, const uint16_t *cnt, const uint16_t *first, const uint16_t *offs, uint32_t *code_len) {
+// canonical decoding of a code that is longer than the table index (PBITS): fc[k] holds, for length PBITS + 1 + k, the first
+// canonical code (bits 0-15) and the number of codes (bits 16-31).  The code of length l is the top l bits of the bit-reversed
+// window; it belongs to this length iff it lies in [first, first + count).  Returns the length (0: no such code) and the
+// code's rank among the codes of its length.
+template <int PBITS>
+__device__ __forceinline__ uint32_t tk_decode_long(uint32_t pk, const uint32_t (&fc)[15 - PBITS], uint32_t *rank) {
     const uint32_t c = __brev(pk);
-#pragma unroll 1
-    for (int len = 1; len <= 15; ++len) {
-        const uint32_t idx = (c >> (32 - len)) - first[len];
-        if (idx < cnt[len]) {
-            *code_len = (uint32_t)len;
-            return (int)(offs[len] + idx);
-        }
+    uint32_t len = 0, r = 0;
+#pragma unroll
+    for (int k = 15 - PBITS - 1; k >= 0; --k) {          // (downwards, so that the shortest length that fits stays)
+        const uint32_t idx = (c >> (32 - (PBITS + 1 + k))) - (fc[k] & 0xFFFFu);
+        if (idx < (fc[k] >> 16)) len = PBITS + 1 + k, r = idx;
     }
-    *code_len = 15;
-    return -1;
+    *rank = r;
+    return len;
 }
 
 // Warp-cooperative build of ONE thread's tables from its code lengths lens[0 .. n): lane L (1..15) owns the codes of length L.
@@ -315,34 +346,44 @@ __device__ bool tk_dynamic_header(TkWin &br, uint8_t *lens, uint8_t *ctab, uint8
 
 // ---- phase S: where can a part start? ------------------------------------------------------------------------------------
 constexpr int SP_WARPS = 4;
+constexpr int SP_STEPS = 32;
 struct SpWarp {
     uint32_t words[36];         // the chunk: 32 words of bit offsets + the 3 words the last offsets reach into
     uint16_t cand[1024];        // stage 1 survivors of the chunk: word << 5 | bit
     uint32_t surv[64];          // stage 2 survivors: bit offset from the blob's first byte
+    uint32_t slow[64];          // ... of them, those whose header is still undecided after SP_STEPS code-length symbols
     uint8_t ctab[32][128];      // stage 3: the code-length code of each lane's candidate
 };
-// Stage 3, one candidate per lane: the whole dynamic header at bit `bit` (BFINAL) of the blob, Kraft sums kept on the fly —
-// true iff the literal/length code is complete and has an end-of-block code, and the distance code is complete (or a single code)
-__device__ bool sp_verify(const uint32_t *__restrict__ w, uint32_t n_words, uint32_t mis, uint32_t bit, uint8_t *ctab) {
+// Stage 3, one candidate per lane: the whole dynamic header at bit `bit` (BFINAL) of the blob, Kraft sums kept on the fly.
+// 1: the literal/length code is complete and has an end-of-block code, and the distance code is complete (or a single code);
+// 0: not a header; 2: undecided after max_steps code-length symbols (the caller asks again with the full budget).
+__device__ int sp_verify(const uint32_t *__restrict__ w, uint32_t n_words, uint32_t mis, uint32_t bit, uint8_t *ctab, int max_steps) {
+    // the reader: three words in registers, reloaded a word ahead
     uint64_t a = 8ull * mis + bit + 3;     // absolute bit in w[]
-    auto peek = [&]() -> uint32_t {        // 32 bits from a
-        const uint32_t k = (uint32_t)(a >> 5), sh = (uint32_t)(a & 31u);
-        const uint32_t q0 = __ldg(w + min(k, n_words - 1u)), q1 = __ldg(w + min(k + 1u, n_words - 1u));
-        return __funnelshift_r(q0, q1, sh);
+    uint32_t kw = (uint32_t)(a >> 5), sh = (uint32_t)(a & 31u);
+    auto ldw = [&](uint32_t k) { return __ldg(w + min(k, n_words - 1u)); };
+    uint32_t q0 = ldw(kw), q1 = ldw(kw + 1), q2 = ldw(kw + 2);
+    auto peek = [&]() -> uint32_t { return __funnelshift_r(q0, q1, sh); };
+    auto skip = [&](uint32_t n) {          // n <= 32
+        sh += n;
+        if (sh >= 32u) {
+            sh -= 32u;
+            ++kw;
+            q0 = q1, q1 = q2, q2 = ldw(kw + 2);
+        }
     };
     uint32_t x = peek();
     const int hlit = (int)(x & 31u) + 257, hdist = (int)((x >> 5) & 31u) + 1, hclen = (int)((x >> 10) & 15u) + 4;
-    if (hlit > 286 || hdist > 30) return false;
-    const uint64_t a_len = 8ull * mis + bit + 17;     // the 3-bit lengths of the code-length code
+    skip(14);
+    if (hlit > 286 || hdist > 30) return 0;
     uint64_t cl = 0;                       // 3 bits per symbol of the code-length alphabet
     uint64_t cnt = 0;                      // 8 bits per length
     for (int i = 0; i < hclen; ++i) {
-        if (i % 8 == 0) a = a_len + 3ull * i, x = peek();
+        if (i % 8 == 0) x = peek(), skip(min(24, 3 * (hclen - i)));
         const uint32_t l = (x >> (3 * (i % 8))) & 7u;
         cl |= (uint64_t)l << (3 * TK_CLORDER[i]);
         if (l) cnt += 1ull << (8 * l);
     }
-    a = a_len + 3ull * hclen;
     uint64_t next = 0;                     // first canonical code of each length, 8 bits per length
     {
         int code = 0, left = 1, prevc = 0;
@@ -353,7 +394,7 @@ __device__ bool sp_verify(const uint32_t *__restrict__ w, uint32_t n_words, uint
             prevc = c;
             next |= (uint64_t)(code & 255) << (8 * l);
         }
-        if (left < 0) return false;
+        if (left < 0) return 0;
     }
     for (int i = 0; i < 128; i += 4) *reinterpret_cast<uint32_t *>(ctab + i) = 0u;
     for (int i = 0; i < 19; ++i) {
@@ -368,20 +409,22 @@ __device__ bool sp_verify(const uint32_t *__restrict__ w, uint32_t n_words, uint
     int idx = 0, prev = 0, nd = 0;
     int kl = 0, kd = 0;                    // Kraft sums in units of 2^-15
     bool eob = false;
-    while (idx < total) {
+    for (int step = 0; idx < total; ++step) {
+        if (step >= max_steps) return 2;
         x = peek();
         const uint32_t ce = ctab[x & 127u];
-        if (!(ce & 7u)) return false;
-        a += ce & 7u;
+        if (!(ce & 7u)) return 0;
         x >>= ce & 7u;
         const int s = (int)(ce >> 3);
         int rep = 1, v = s;
+        uint32_t used = ce & 7u;
         if (s == 16) {
-            if (idx == 0) return false;
-            v = prev, rep = 3 + (int)(x & 3u), a += 2;
-        } else if (s == 17) v = 0, rep = 3 + (int)(x & 7u), a += 3;
-        else if (s == 18) v = 0, rep = 11 + (int)(x & 127u), a += 7;
-        if (idx + rep > total) return false;
+            if (idx == 0) return 0;
+            v = prev, rep = 3 + (int)(x & 3u), used += 2;
+        } else if (s == 17) v = 0, rep = 3 + (int)(x & 7u), used += 3;
+        else if (s == 18) v = 0, rep = 11 + (int)(x & 127u), used += 7;
+        skip(used);
+        if (idx + rep > total) return 0;
         if (v) {
             const int unit = 1 << (15 - v);
             const int in_l = min(rep, max(hlit - idx, 0));      // how many of the run fall into the literal/length alphabet
@@ -389,12 +432,12 @@ __device__ bool sp_verify(const uint32_t *__restrict__ w, uint32_t n_words, uint
             kd += (rep - in_l) * unit;
             nd += rep - in_l;
             if (idx <= 256 && 256 < idx + rep) eob = true;
-            if (kl > (1 << 15) || kd > (1 << 15)) return false;
+            if (kl > (1 << 15) || kd > (1 << 15)) return 0;
         }
         idx += rep;
         prev = v;
     }
-    return eob && kl == (1 << 15) && (kd == (1 << 15) || (nd == 1 && kd == (1 << 14)));
+    return (eob && kl == (1 << 15) && (kd == (1 << 15) || (nd == 1 && kd == (1 << 14)))) ? 1 : 0;
 }
 
 __global__ void __launch_bounds__(SP_WARPS * 32)
@@ -425,19 +468,24 @@ inflate_split_kernel(const uint8_t *__restrict__ gz, const uint64_t *__restrict_
         const uint32_t n_words = (mis + in_len + 3u) >> 2;
         const uint64_t bit0 = 8ull * ((uint64_t)in_len * j / np);
         const uint64_t lim = min(8ull * ((uint64_t)in_len * (j + 1) / np), 8ull * (uint64_t)in_len > 160ull ? 8ull * (uint64_t)in_len - 160ull : 0ull);
-        uint32_t found = TK_NONE, n_surv = 0;
-        // stage 3 on the first min(n_surv, 32) survivors; the list is in rising order, so the lowest valid one is the answer
-        auto verify = [&]() {
-            const uint32_t n = min(n_surv, 32u);
-            const bool ok = lane < n && sp_verify(w, n_words, mis, S.surv[lane], S.ctab[lane]);
-            const unsigned m = __ballot_sync(0xFFFFFFFFu, ok);
-            if (m) found = S.surv[__ffs(m) - 1];
+        uint32_t found = TK_NONE, n_surv = 0, n_slow = 0;
+        // stage 3 on the first min(n, 32) entries of a list (any header of the range will do: the token phase stops at the
+        // first one at or behind the start it was given): first with a budget of SP_STEPS code-length symbols — a warp
+        // takes as long as its longest lane, and half of the candidates are refuted by then —, the undecided ones in
+        // batches of their own with the full budget
+        auto verify = [&](uint32_t *list, uint32_t &n_list, int max_steps) {
+            const uint32_t n = min(n_list, 32u);
+            const int r = lane < n ? sp_verify(w, n_words, mis, list[lane], S.ctab[lane], max_steps) : 0;
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, r == 1), m2 = __ballot_sync(0xFFFFFFFFu, r == 2);
+            if (m) found = list[__ffs(m) - 1];
             __syncwarp();
-            const uint32_t rest = n_surv - n;
-            const uint32_t mv = lane < rest ? S.surv[n + lane] : 0u;
+            const uint32_t rest = n_list - n;
+            const uint32_t mv = lane < rest ? list[n + lane] : 0u, mine = lane < n ? list[lane] : 0u;
             __syncwarp();
-            if (lane < rest) S.surv[lane] = mv;
-            n_surv = rest;
+            if (lane < rest) list[lane] = mv;
+            n_list = rest;
+            if (r == 2) S.slow[n_slow + __popc(m2 & ((1u << lane) - 1u))] = mine;     // (never from the slow list itself: full budget)
+            n_slow += __popc(m2);
             __syncwarp();
         };
         const uint64_t a0 = 8ull * mis + bit0, a1 = 8ull * mis + lim;           // absolute bits in w[]
@@ -498,10 +546,12 @@ inflate_split_kernel(const uint8_t *__restrict__ gz, const uint64_t *__restrict_
                 if (pass) S.surv[n_surv + __popc(pm & ((1u << lane) - 1u))] = bit;
                 n_surv += __popc(pm);
                 __syncwarp();
-                if (n_surv >= 32) verify();
+                if (n_surv >= 32) verify(S.surv, n_surv, SP_STEPS);
+                if (n_slow >= 32 && found == TK_NONE) verify(S.slow, n_slow, 1 << 20);
             }
         }
-        while (n_surv && found == TK_NONE) verify();
+        while (n_surv && found == TK_NONE) verify(S.surv, n_surv, SP_STEPS);
+        while (n_slow && found == TK_NONE) verify(S.slow, n_slow, 1 << 20);
         if (lane == 0) rec[item].start_bit = found;
         __syncwarp();
     }
@@ -529,11 +579,12 @@ inflate_tokens_kernel(const uint8_t *__restrict__ gz, const uint64_t *__restrict
                       PartRec *__restrict__ rec, TkSlow *__restrict__ slow, unsigned long long *__restrict__ next_item) {
     extern __shared__ __align__(16) uint8_t tk_smem[];
     __shared__ uint16_t s_lbase[32], s_dbase[32];   // (constant memory would serialise the lanes' different indices)
-    __shared__ uint8_t s_lext[32];
+    __shared__ uint8_t s_lext[32], s_dext[32];
     if (threadIdx.x < 32) {
         s_lbase[threadIdx.x] = TK_LBASE[threadIdx.x];
         s_dbase[threadIdx.x] = TK_DBASE[threadIdx.x];
         s_lext[threadIdx.x] = TK_LEXT[threadIdx.x];
+        s_dext[threadIdx.x] = TK_DEXT[threadIdx.x];
     }
     __syncthreads();
     const int lane = threadIdx.x & 31;
@@ -554,8 +605,14 @@ inflate_tokens_kernel(const uint8_t *__restrict__ gz, const uint64_t *__restrict
     int err = INF_OK, nlen = 288, ndist = 30;
     bool last = false;
     TkWin br;
-    br.w = reinterpret_cast<const uint32_t *>(gz), br.n_words = 1, br.mis = 0;
-    br.w0 = br.w1 = br.w2 = br.p0 = br.p1 = br.p2 = 0, br.o = 0, br.wi = 3;
+    br.base = gz, br.n_bytes = 0, br.n_words = 0, br.mis = 0;
+    br.w0 = br.w1 = br.w2 = br.p0 = 0, br.o = 0, br.wi = 3;
+    br.ring = (uint32_t)__cvta_generic_to_shared(tk_smem + sizeof(TkFast) * TK_THREADS + 4 * TK_RING * threadIdx.x);
+    uint32_t lfc[15 - TK_LBITS], dfc[15 - TK_DBITS];      // the codes that are longer than a table index (tk_decode_long)
+#pragma unroll
+    for (int k = 0; k < 15 - TK_LBITS; ++k) lfc[k] = 0;
+#pragma unroll
+    for (int k = 0; k < 15 - TK_DBITS; ++k) dfc[k] = 0;
     int state = TS_FETCH;
     auto fetch = [&]() {     // the next part that exists, or TS_DONE when the counter has run out
         for (;;) {
@@ -575,9 +632,7 @@ inflate_tokens_kernel(const uint8_t *__restrict__ gz, const uint64_t *__restrict
             err = INF_OK;
             if (cap64 > 0xFFFF0000ull || len64 > 0x0FFFFFFFull || len64 == 0) err = INF_ETOKENS;     // output positions and bit offsets are 32-bit
             cap = (uint32_t)cap64, in_len = (uint32_t)len64;
-            br.mis = (uint32_t)(reinterpret_cast<uintptr_t>(in) & 3u);
-            br.w = reinterpret_cast<const uint32_t *>(in - br.mis);
-            br.n_words = max((br.mis + in_len + 3u) >> 2, 1u);
+            br.set_blob(in, in_len);
             uint32_t p = 10;     // gzip header (RFC 1952): part 0
             if (!err && part == 0) {
                 if (in_len < 18 || in[0] != 0x1F || in[1] != 0x8B || in[2] != 8) err = INF_EHEADER;
@@ -603,7 +658,7 @@ inflate_tokens_kernel(const uint8_t *__restrict__ gz, const uint64_t *__restrict
             r_isize = r_crc = r_final = 0;
             pos = nt = 0;
             last = false;
-            if (err) br.w0 = br.w1 = br.w2 = br.p0 = br.p1 = br.p2 = 0, br.o = 0, br.wi = 3, br.mis = 0;
+            if (err) br.w0 = br.w1 = br.w2 = br.p0 = 0, br.o = 0, br.wi = 3, br.mis = 0;
             else br.seek_bit(my_start);
             state = err ? TS_FINISHED : TS_HEADER;
             return;
@@ -698,6 +753,12 @@ inflate_tokens_kernel(const uint8_t *__restrict__ gz, const uint64_t *__restrict
                 }
             }
             __syncwarp();
+            if (build) {
+#pragma unroll
+                for (int k = 0; k < 15 - TK_LBITS; ++k) lfc[k] = (uint32_t)T.lfirst[TK_LBITS + 1 + k] | ((uint32_t)T.lcnt[TK_LBITS + 1 + k] << 16);
+#pragma unroll
+                for (int k = 0; k < 15 - TK_DBITS; ++k) dfc[k] = (uint32_t)T.dfirst[TK_DBITS + 1 + k] | ((uint32_t)T.dcnt[TK_DBITS + 1 + k] << 16);
+            }
             continue;
         }
         if (__all_sync(0xFFFFFFFFu, state == TS_DONE)) break;
@@ -719,7 +780,7 @@ inflate_tokens_kernel(const uint8_t *__restrict__ gz, const uint64_t *__restrict
                 const uint32_t lo2 = __funnelshift_r(lo, hi, n1);             // the window behind the length symbol
                 const uint32_t d = F.dtab[lo2 & ((1u << TK_DBITS) - 1u)];
                 const uint32_t n2 = d & 31u, dx = (d >> 5) & 15u;
-                const uint32_t dist = s_dbase[d >> 9] + ((lo2 >> (n2 - dx)) & ((1u << dx) - 1u));
+                const uint32_t dist = s_dbase[(d >> 9) & 31u] + ((lo2 >> (n2 - dx)) & ((1u << dx) - 1u));
                 const bool commit = act && n1 != 0u && !(is_len && n2 == 0u);
                 br.drop(commit ? n1 + (is_len ? n2 : 0u) : 0u);
                 if (commit) {
@@ -731,21 +792,43 @@ inflate_tokens_kernel(const uint8_t *__restrict__ gz, const uint64_t *__restrict
             bool eobf = false;
             if (__any_sync(0xFFFFFFFFu, was && !act)) {   // one symbol (and its distance) through the canonical decoder
                 if (was && !act) {
-                    uint32_t pk = br.peek(), cl;
-                    const int k = tk_decode_slow(pk, T.lcnt, T.lfirst, T.loffs, &cl);
-                    const uint32_t sym = (k < 0 || k >= nlen) ? 300u : T.lsym[k];
-                    const bool is_lit = sym < 256u, is_len = sym - 257u < 29u;
-                    const uint32_t ex = s_lext[(sym - 257u) & 31u];
-                    const uint32_t len = s_lbase[(sym - 257u) & 31u] + ((pk >> cl) & ((1u << ex) - 1u));
+                    uint32_t pk = br.peek();
+                    const uint32_t e = F.ltab[pk & ((1u << TK_LBITS) - 1u)];
+                    uint32_t sym = 300u, cl = 1;
+                    if (e & 15u) {            // a symbol of the table whose distance code is not in the distance table
+                        cl = (e & 15u) - ((e >> 4) & 7u);
+                        sym = 1000u;          // (a length symbol: base and extra bits from the entry)
+                    } else if (e & 0x8000u) sym = 256u, cl = (e >> 4) & 15u;
+                    else if (e == 0u) {
+                        uint32_t rank;
+                        cl = tk_decode_long<TK_LBITS>(pk, lfc, &rank);
+                        if (cl) {
+                            const uint32_t k = T.loffs[cl] + rank;
+                            if (k < (uint32_t)nlen) sym = T.lsym[k];
+                        } else cl = 1;
+                    }
+                    const bool from_tab = sym == 1000u;
+                    const bool is_lit = sym < 256u, is_len = from_tab || sym - 257u < 29u;
+                    const uint32_t ex = from_tab ? (e >> 4) & 7u : s_lext[(sym - 257u) & 31u];
+                    const uint32_t len = (from_tab ? (e >> 8) + 3u : s_lbase[(sym - 257u) & 31u]) + ((pk >> cl) & ((1u << ex) - 1u));
+                    if (from_tab) sym = 257u;
                     br.drop(cl + (is_len ? ex : 0u));
                     uint32_t dist = 0;
                     if (is_len) {
                         pk = br.peek();
-                        uint32_t dl;
-                        const int k2 = tk_decode_slow(pk, T.dcnt, T.dfirst, T.doffs, &dl);
-                        const uint32_t ds = (k2 < 0 || k2 >= ndist) ? 31u : T.dsym[k2];
-                        if (ds > 29u) err = INF_ECODE;
-                        const uint32_t dx = TK_DEXT[ds];
+                        const uint32_t d = F.dtab[pk & ((1u << TK_DBITS) - 1u)];
+                        uint32_t dl = 1, ds = 31u;
+                        if (d & 31u) dl = (d & 31u) - ((d >> 5) & 15u), ds = d >> 9;
+                        else if (d == 0u) {
+                            uint32_t rank;
+                            dl = tk_decode_long<TK_DBITS>(pk, dfc, &rank);
+                            if (dl) {
+                                const uint32_t k2 = T.doffs[dl] + rank;
+                                if (k2 < (uint32_t)ndist) ds = T.dsym[k2];
+                            } else dl = 1;
+                        }
+                        if (ds > 29u) err = INF_ECODE, ds = 0;
+                        const uint32_t dx = s_dext[ds];
                         dist = s_dbase[ds] + ((pk >> dl) & ((1u << dx) - 1u));
                         br.drop(dl + dx);
                     }
@@ -775,13 +858,16 @@ inflate_tokens_kernel(const uint8_t *__restrict__ gz, const uint64_t *__restrict
 
 // ---- phase R ------------------------------------------------------------------------------------------------------
 constexpr int RS_WARPS = 4;
+constexpr uint32_t RS_WIN = 4096;      // bytes of a blob's latest output kept in shared memory
 __global__ void __launch_bounds__(RS_WARPS * 32)
 inflate_resolve_kernel(const uint64_t *__restrict__ gz_off, int64_t n_blob, uint8_t *out_base, const uint64_t *__restrict__ out_off,
                        const uint32_t *__restrict__ part_off, const uint32_t *__restrict__ tokens, const PartRec *__restrict__ rec,
                        int32_t *__restrict__ status, uint32_t *__restrict__ crc_want) {
+    __shared__ uint8_t rings[RS_WARPS][RS_WIN];
     const uint32_t lane = threadIdx.x & 31;
     const int64_t blob = (int64_t)blockIdx.x * RS_WARPS + (threadIdx.x >> 5);
     if (blob >= n_blob) return;
+    uint8_t *ring = rings[threadIdx.x >> 5];
     const uint64_t o0 = out_off[blob], ob = out_off[0], cap = out_off[blob + 1] - o0;
     const uint32_t np = part_off[blob + 1] - part_off[blob];
     const PartRec *R = rec + part_off[blob];
@@ -839,24 +925,26 @@ inflate_resolve_kernel(const uint64_t *__restrict__ gz_off, int64_t n_blob, uint
         if (have && len_f != 0u && (hi > P0 + start || hi == 0u)) bad = true;
         if ((uint64_t)P0 + total > cap) bad = true;
         if (__any_sync(0xFFFFFFFFu, bad)) break;
-        // the batch's bytes, 32 at a time and in order: byte b belongs to the first token whose end is > b.  A match byte is
-        // copied from b - distance: before the round (written, possibly by an earlier round of this batch) or inside the
-        // round itself — then the lane follows the chain of sources (each step moves at least one byte back) until it
-        // leaves the round or ends at a literal.
+        // the batch's bytes, 32 at a time and in order: byte b belongs to the last token that starts at or before b — the
+        // tokens mark their first bytes in a 32-bit mask (one warp-wide OR), and a lane counts the marks up to its own byte.
+        // A match byte is copied from b - distance: before the round (written: the last RS_WIN bytes also sit in a ring in
+        // shared memory, so the serial chain round -> round does not wait for the L2) or inside the round itself — then
+        // the lane follows the chain of sources (each step moves at least one byte back) until it leaves the round or
+        // ends at a literal.
         const uint32_t rounds = (total + 31u) >> 5;
+        uint32_t n_before = 0;                       // tokens of the batch that start before the round
         for (uint32_t r = 0; r < rounds; ++r) {
             const uint32_t r0 = r * 32u, b = r0 + lane;
-            uint32_t lo = 0;
-#pragma unroll
-            for (int s = 16; s; s >>= 1) {
-                const uint32_t e_mid = __shfl_sync(0xFFFFFFFFu, end, (lo + s - 1) & 31u);
-                if (e_mid <= b) lo += s;
-            }
-            const uint32_t o_tok = __shfl_sync(0xFFFFFFFFu, t, lo & 31u);
+            const uint32_t s_rel = start - r0;
+            const uint32_t marks = __reduce_or_sync(0xFFFFFFFFu, (have && s_rel < 32u) ? 1u << s_rel : 0u);
+            const uint32_t owner = n_before + (uint32_t)__popc(marks & ((2u << lane) - 1u)) - 1u;
+            n_before += (uint32_t)__popc(marks);
+            const uint32_t o_tok = __shfl_sync(0xFFFFFFFFu, t, owner & 31u);
             const bool valid = b < total, lit = (o_tok & 511u) == 0u;
             // src: where the byte comes from, relative to the batch (negative: before it); literals carry their value
-            int32_t src = (int32_t)b - (int32_t)(o_tok >> 9);
-            uint32_t val = o_tok >> 9;
+            const uint32_t dist = o_tok >> 9;
+            int32_t src = (int32_t)b - (int32_t)dist;
+            uint32_t val = dist;
             bool done = !valid || lit;
             while (__any_sync(0xFFFFFFFFu, !done && src >= (int32_t)r0)) {
                 const uint32_t from = (uint32_t)(src - (int32_t)r0) & 31u;
@@ -868,8 +956,13 @@ inflate_resolve_kernel(const uint64_t *__restrict__ gz_off, int64_t n_blob, uint
                     else src = s2;                     // its source is further back
                 }
             }
+            if (valid && !done) {
+                const uint32_t back = b - (uint32_t)src;               // how far behind this byte the source lies
+                val = back <= RS_WIN - 32u ? ring[(P0 + (uint32_t)src) & (RS_WIN - 1u)] : out[(int64_t)P0 + src];
+            }
+            __syncwarp();
             if (valid) {
-                if (!done) val = out[(int64_t)P0 + src];
+                ring[(P0 + b) & (RS_WIN - 1u)] = (uint8_t)val;
                 out[P0 + b] = (uint8_t)val;
             }
             __syncwarp();
@@ -939,11 +1032,19 @@ __device__ uint32_t gf2_x_pow_8n(uint64_t n_bytes) {   // x^(8 n) mod P, reflect
 __global__ void __launch_bounds__(256)
 crc32_pieces_kernel(const uint8_t *__restrict__ data, const uint64_t *__restrict__ out_off, int64_t n_blob,
                     const uint64_t *__restrict__ piece_off /* n_blob + 1 */, uint32_t *__restrict__ piece_crc) {
-    __shared__ uint32_t tab[256];
+    __shared__ uint32_t tab[4][256];     // slicing-by-4: tab[k][v] = the register after byte v and k zero bytes
     {
         uint32_t c = threadIdx.x;
         for (int k = 0; k < 8; ++k) c = (c >> 1) ^ ((c & 1u) ? 0xEDB88320u : 0u);
-        tab[threadIdx.x] = c;
+        tab[0][threadIdx.x] = c;
+    }
+    __syncthreads();
+    {
+        uint32_t c = tab[0][threadIdx.x];
+        for (int k = 1; k < 4; ++k) {
+            c = tab[0][c & 0xFFu] ^ (c >> 8);
+            tab[k][threadIdx.x] = c;
+        }
     }
     __syncthreads();
     const uint64_t n_piece = piece_off[n_blob];
@@ -956,16 +1057,19 @@ crc32_pieces_kernel(const uint8_t *__restrict__ data, const uint64_t *__restrict
         const uint64_t b0 = out_off[lo] + (p - piece_off[lo]) * CRC_PIECE, b1 = min(b0 + CRC_PIECE, out_off[lo + 1]);
         uint32_t c = 0;                  // raw register value (no pre / post inversion): pieces combine linearly
         uint64_t i = b0;
-        for (; i < b1 && (i & 3ull); ++i) c = tab[(c ^ data[i]) & 0xFFu] ^ (c >> 8);
-        for (; i + 4 <= b1; i += 4) {
-            uint32_t w = *reinterpret_cast<const uint32_t *>(data + i);
-            c ^= w;
-            c = tab[c & 0xFFu] ^ (c >> 8);
-            c = tab[c & 0xFFu] ^ (c >> 8);
-            c = tab[c & 0xFFu] ^ (c >> 8);
-            c = tab[c & 0xFFu] ^ (c >> 8);
+        for (; i < b1 && (reinterpret_cast<uintptr_t>(data + i) & 15u); ++i) c = tab[0][(c ^ data[i]) & 0xFFu] ^ (c >> 8);
+        for (; i + 16 <= b1; i += 16) {
+            const uint4 q = *reinterpret_cast<const uint4 *>(data + i);
+            c ^= q.x;
+            c = tab[3][c & 0xFFu] ^ tab[2][(c >> 8) & 0xFFu] ^ tab[1][(c >> 16) & 0xFFu] ^ tab[0][c >> 24];
+            c ^= q.y;
+            c = tab[3][c & 0xFFu] ^ tab[2][(c >> 8) & 0xFFu] ^ tab[1][(c >> 16) & 0xFFu] ^ tab[0][c >> 24];
+            c ^= q.z;
+            c = tab[3][c & 0xFFu] ^ tab[2][(c >> 8) & 0xFFu] ^ tab[1][(c >> 16) & 0xFFu] ^ tab[0][c >> 24];
+            c ^= q.w;
+            c = tab[3][c & 0xFFu] ^ tab[2][(c >> 8) & 0xFFu] ^ tab[1][(c >> 16) & 0xFFu] ^ tab[0][c >> 24];
         }
-        for (; i < b1; ++i) c = tab[(c ^ data[i]) & 0xFFu] ^ (c >> 8);
+        for (; i < b1; ++i) c = tab[0][(c ^ data[i]) & 0xFFu] ^ (c >> 8);
         piece_crc[p] = c;
     }
 }
@@ -1020,7 +1124,7 @@ int32_t launch_gunzip2(PerDevice &pd, cudaStream_t st, const uint8_t *d_gz, cons
     uint64_t *d_poff = reinterpret_cast<uint64_t *>(base + o_poff);
     unsigned long long *d_counter = reinterpret_cast<unsigned long long *>(base + ((bytes - 16) & ~(size_t)7));
     if (decoder == 0) {
-        const size_t smem = sizeof(TkFast) * TK_THREADS;
+        const size_t smem = TK_SMEM;
         CUDA_TRY(cudaFuncSetAttribute(inflate_tokens_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         inflate_parts_kernel<<<1, 1024, 0, st>>>(d_gz_off, d_out_off, n_blob, p_cap, d_parts);
         const unsigned s_blocks = (unsigned)std::min<uint64_t>((p_cap + SP_WARPS - 1) / SP_WARPS, (uint64_t)n_sm * 16);
