@@ -35,12 +35,12 @@
 namespace gams {
 
 #ifndef TK_WARPS_N
-#define TK_WARPS_N 15
+#define TK_WARPS_N 12
 #endif
-constexpr int TK_WARPS = TK_WARPS_N;           // warps per CTA, one CTA per SM: 480 parts in flight per SM
+constexpr int TK_WARPS = TK_WARPS_N;           // warps per CTA, one CTA per SM: 384 parts in flight per SM
 constexpr int TK_THREADS = TK_WARPS * 32;
 constexpr int TK_LBITS = 6, TK_DBITS = 7;      // level-1 sequence data: 0.4 % of the literal/length codes and 1.8 % of the distance codes are longer
-constexpr int TK_RING = 16;                    // words of the compressed stream staged ahead in shared memory
+constexpr uint32_t TK_RING = 32;               // words of the compressed stream staged ahead in shared memory
 // per-thread state in shared memory; the stride in 32-bit words is odd, so equal indices of different threads fall into
 // different banks
 struct TkFast {
@@ -49,11 +49,12 @@ struct TkFast {
                                     //   0x8000 | code length << 4: end of block, 0x4000: a symbol that must not occur (286, 287)
     uint16_t dtab[1 << TK_DBITS];   // bits 0-4 code length + extra bits, 5-8 extra bits, 9-13 symbol (0..29); 0: a longer code (or
                                     //   none), 0x8000: a symbol that must not occur (30, 31)
+    uint8_t dsym[32];               // the distance symbols in canonical order (for the codes that are longer than the table index)
     uint32_t pad;
 };
+static_assert(sizeof(TkFast) % 4 == 0 && (sizeof(TkFast) / 4) % 2 == 1, "odd word stride");
 // (and a ring of TK_RING words per thread behind the tables, 16-byte aligned for cp.async)
 constexpr size_t TK_SMEM = (sizeof(TkFast) + 4 * TK_RING) * TK_THREADS;
-static_assert(sizeof(TkFast) % 4 == 0 && (sizeof(TkFast) / 4) % 2 == 1, "odd word stride");
 // per-thread scratch in global memory: what a block header needs while it is parsed, and the canonical decoder of the codes
 // that are longer than a table index
 struct TkSlow {
@@ -77,18 +78,22 @@ __constant__ uint8_t TK_CLORDER[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 
 
 // The bit window of one thread: three consecutive aligned words of the blob and a bit offset o < 32 into the first — 64 valid
 // bits from the current position in two funnel shifts, enough for a length and a distance symbol with their extra bits (48
-// bits at most) without a refill in between — and one more word in a register.  What follows is staged in a ring of 16 words
-// in shared memory by cp.async, 16 bytes at a time and 8 to 11 words (some 30 symbols) ahead of the window: the copy needs no
-// register, so nothing in the symbol loop ever waits for global memory.  (With the next words loaded into registers the
-// compiler's register moves at the loop's joins read the loaded register an iteration later, and with 227 KB of the SM
-// configured as shared memory the L1 is too small to hold a prefetched line per thread: 17 % of the kernel's samples.)
+// bits at most) without a refill in between — and one more word in a register.  What follows is staged in a ring of 32 words
+// in shared memory by cp.async, 16 bytes at a time: the copy needs no register, so the symbol loop never waits for global
+// memory.  The ring is topped up ONCE PER GROUP of symbols, by all lanes in the same instruction (top_up): a warp has one
+// set of scoreboards, so a wait that only some lanes execute also waits for the copies the other lanes have just issued —
+// with per-lane refills inside the loop (or with loads into registers, whose results the compiler's register moves at the
+// loop's joins read) a sixth of the kernel's samples sat on that wait.  After a top-up at least 29 words lie ahead of the
+// window, all but the newest copies have landed, and a group consumes at most 13: rotate_fast() needs no check.  Outside
+// the symbol loop (block headers, stored blocks) rotate() checks and refills with a blocking wait.
 // Bytes behind the blob's end read as zero (cp.async src-size), never part of a valid stream: the trailer is 8 bytes.
 struct TkWin {
     const uint8_t *base;             // the blob's first byte rounded down to 16 bytes
     uint32_t n_bytes, n_words;       // from base to the blob's end
     uint32_t wi, mis;                // w0 w1 w2 p0 = words wi - 3 .. wi of base; mis: bytes between base and the blob's first byte
     uint32_t w0, w1, w2, p0, o;
-    uint32_t ring;                   // shared-memory address of the lane's ring; word k of the stream lives in slot k & 15
+    uint32_t ring;                   // shared-memory address of the lane's ring; word k of the stream lives in slot k & 31
+    uint32_t fetched, landed;        // words < fetched are in the ring or on their way, words < landed have arrived (both multiples of 4)
     __device__ __forceinline__ void set_blob(const uint8_t *in, uint32_t in_len) {
         mis = (uint32_t)(reinterpret_cast<uintptr_t>(in) & 15u);
         base = in - mis;
@@ -106,34 +111,68 @@ struct TkWin {
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(ring + 4u * (k & (TK_RING - 1u))) : "memory");
         return v;
     }
+    __device__ __forceinline__ void fill() {     // every free slot of the ring: slots of words <= wi are free
+#pragma unroll
+        for (uint32_t k = 0; k < TK_RING / 4; ++k)
+            if (fetched + 3u <= wi + TK_RING) fetch4(fetched), fetched += 4u;
+    }
+    // all lanes of the warp together (active says whether this lane has a stream): fill, and everything but the copies
+    // issued just now has arrived
+    __device__ __forceinline__ void top_up(bool active) {
+        const uint32_t before = fetched;
+        if (active) {
+#pragma unroll
+            for (uint32_t k = 0; k < 4; ++k)         // (a group consumes 13 words at most)
+                if (fetched + 3u <= wi + TK_RING) fetch4(fetched), fetched += 4u;
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        landed = before;
+        if (active && landed < wi + 16u) {      // (the first group behind a block header: the ring was refilled word by word)
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            landed = fetched;
+        }
+    }
     __device__ __forceinline__ void seek_bit(uint64_t bit) {   // position given in bits from the blob's first byte
         const uint64_t a = 8ull * mis + bit;
-        const uint32_t k = (uint32_t)(a >> 5), k4 = k & ~3u;
+        const uint32_t k = (uint32_t)(a >> 5);
         o = (uint32_t)(a & 31u);
         asm volatile("cp.async.wait_group 0;" ::: "memory");     // (nothing of an earlier position may land in the ring later)
-        fetch4(k4), fetch4(k4 + 4), fetch4(k4 + 8), fetch4(k4 + 12);
+        fetched = k & ~3u;
+        wi = fetched > 0u ? fetched - 1u : 0u;                  // (every slot is free)
+        fill();
         asm volatile("cp.async.commit_group;" ::: "memory");
         asm volatile("cp.async.wait_group 0;" ::: "memory");
+        landed = fetched;
         w0 = slot(k), w1 = slot(k + 1), w2 = slot(k + 2), p0 = slot(k + 3);
         wi = k + 3;
     }
     __device__ __forceinline__ void seek(uint32_t byte) { seek_bit(8ull * byte); }
     __device__ __forceinline__ uint32_t peek() const { return __funnelshift_r(w0, w1, o); }      // bits 0..31 from the position
     __device__ __forceinline__ uint32_t peek_hi() const { return __funnelshift_r(w1, w2, o); }   // bits 32..63
-    __device__ __forceinline__ void rotate() {
+    __device__ __forceinline__ void rotate_fast() {
         w0 = w1, w1 = w2, w2 = p0;
         ++wi;
         p0 = slot(wi);
-        if ((wi & 3u) == 0u) {       // words wi .. wi + 7 are in the ring (or on their way); wi + 8 .. wi + 11 replace wi - 8 .. wi - 5
-            fetch4(wi + 8);
+    }
+    __device__ __forceinline__ void rotate() {
+        if (wi + 1u >= landed) {
+            fill();
             asm volatile("cp.async.commit_group;" ::: "memory");
-            asm volatile("cp.async.wait_group 1;" ::: "memory");   // the copy before this one (four rotations ago) has landed
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            landed = fetched;
         }
+        rotate_fast();
     }
     __device__ __forceinline__ void drop(uint32_t n) {   // n <= 63 (0 is a no-op)
         o += n;
         if (o >= 32u) { rotate(); o -= 32u; }
         if (o >= 32u) { rotate(); o -= 32u; }
+    }
+    __device__ __forceinline__ void drop_fast(uint32_t n) {   // inside a group of symbols, after top_up()
+        o += n;
+        if (o >= 32u) { rotate_fast(); o -= 32u; }
+        if (o >= 32u) { rotate_fast(); o -= 32u; }
     }
     __device__ __forceinline__ uint32_t bits(uint32_t n) { const uint32_t v = peek() & ((1u << n) - 1u); drop(n); return v; }   // n < 32
     __device__ __forceinline__ uint64_t consumed_bits() const { return 32ull * (wi - 3) + o - 8ull * mis; }
@@ -155,20 +194,23 @@ __device__ __forceinline__ uint32_t tk_dist_entry(int s, int code_len) {
     return ((uint32_t)s << 9) | (dx << 5) | ((uint32_t)code_len + dx);
 }
 
-// canonical decoding of a code that is longer than the table index (PBITS): fc[k] holds, for length PBITS + 1 + k, the first
-// canonical code (bits 0-15) and the number of codes (bits 16-31).  The code of length l is the top l bits of the bit-reversed
-// window; it belongs to this length iff it lies in [first, first + count).  Returns the length (0: no such code) and the
-// code's rank among the codes of its length.
+// canonical decoding of a code that is longer than the table index (PBITS): fc[k] holds, for length l = PBITS + 1 + k, the
+// first canonical code (bits 0-15) and the position of its symbol in canonical order (bits 16-31); the number of codes of the
+// length follows from the next length's first code, first(l + 1) = (first(l) + count(l)) << 1, and is given for length 15.
+// The code of length l is the top l bits of the bit-reversed window; it belongs to this length iff it lies in
+// [first, first + count).  Returns the length (0: no such code) and the symbol's position.
 template <int PBITS>
-__device__ __forceinline__ uint32_t tk_decode_long(uint32_t pk, const uint32_t (&fc)[15 - PBITS], uint32_t *rank) {
+__device__ __forceinline__ uint32_t tk_decode_long(uint32_t pk, const uint32_t (&fc)[15 - PBITS], uint32_t cnt15, uint32_t *pos) {
     const uint32_t c = __brev(pk);
     uint32_t len = 0, r = 0;
 #pragma unroll
     for (int k = 15 - PBITS - 1; k >= 0; --k) {          // (downwards, so that the shortest length that fits stays)
-        const uint32_t idx = (c >> (32 - (PBITS + 1 + k))) - (fc[k] & 0xFFFFu);
-        if (idx < (fc[k] >> 16)) len = PBITS + 1 + k, r = idx;
+        const uint32_t first = fc[k] & 0xFFFFu;
+        const uint32_t cnt = k == 15 - PBITS - 1 ? cnt15 : ((fc[k == 15 - PBITS - 1 ? k : k + 1] & 0xFFFFu) >> 1) - first;
+        const uint32_t idx = (c >> (32 - (PBITS + 1 + k))) - first;
+        if (idx < cnt) len = PBITS + 1 + k, r = (fc[k] >> 16) + idx;
     }
-    *rank = r;
+    *pos = r;
     return len;
 }
 
@@ -241,12 +283,13 @@ __device__ __forceinline__ uint32_t tk_tok_off(uint64_t budget, uint32_t np, uin
     return (uint32_t)((((budget - 8ull * np) * s / nbits) & ~7ull) + 8ull * j);
 }
 
+constexpr uint32_t SP_GROUP = 64;      // ranges per warp of the split kernel
 __global__ void __launch_bounds__(1024)
 inflate_parts_kernel(const uint64_t *__restrict__ gz_off, const uint64_t *__restrict__ out_off, int64_t n_blob, uint64_t p_cap,
-                     uint32_t *__restrict__ part_off) {
-    __shared__ uint32_t ws[32];
-    __shared__ uint32_t carry;
-    if (threadIdx.x == 0) carry = 0;
+                     uint32_t *__restrict__ part_off, uint32_t *__restrict__ group_off) {
+    __shared__ uint32_t ws[32], ws2[32];
+    __shared__ uint32_t carry, carry2;
+    if (threadIdx.x == 0) carry = carry2 = 0;
     __syncthreads();
     const uint64_t range = tk_range_bytes(gz_off, n_blob, p_cap), ob = out_off[0];
     for (int64_t base = 0; base < n_blob; base += 1024) {
@@ -260,22 +303,23 @@ inflate_parts_kernel(const uint64_t *__restrict__ gz_off, const uint64_t *__rest
             if (16ull * np > budget) np = 1;
             v = (uint32_t)np;
         }
-        uint32_t inc = v;
+        const uint32_t v2 = (v + SP_GROUP - 1) / SP_GROUP;
+        uint32_t inc = v, inc2 = v2;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
-            if ((threadIdx.x & 31) >= d) inc += t;
+            const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d), t2 = __shfl_up_sync(0xFFFFFFFFu, inc2, d);
+            if ((threadIdx.x & 31) >= d) inc += t, inc2 += t2;
         }
-        if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = inc;
+        if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = inc, ws2[threadIdx.x >> 5] = inc2;
         __syncthreads();
-        uint32_t before = carry;
-        for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) before += ws[w];
-        if (b < n_blob) part_off[b] = before + inc - v;
+        uint32_t before = carry, before2 = carry2;
+        for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) before += ws[w], before2 += ws2[w];
+        if (b < n_blob) part_off[b] = before + inc - v, group_off[b] = before2 + inc2 - v2;
         __syncthreads();
-        if (threadIdx.x == 1023) carry = before + inc;
+        if (threadIdx.x == 1023) carry = before + inc, carry2 = before2 + inc2;
         __syncthreads();
     }
-    if (threadIdx.x == 0) part_off[n_blob] = carry;
+    if (threadIdx.x == 0) part_off[n_blob] = carry, group_off[n_blob] = carry2;
 }
 
 // the blob of part item: the last b with part_off[b] <= item
@@ -346,12 +390,10 @@ __device__ bool tk_dynamic_header(TkWin &br, uint8_t *lens, uint8_t *ctab, uint8
 
 // ---- phase S: where can a part start? ------------------------------------------------------------------------------------
 constexpr int SP_WARPS = 4;
-constexpr int SP_STEPS = 32;
 struct SpWarp {
     uint32_t words[36];         // the chunk: 32 words of bit offsets + the 3 words the last offsets reach into
     uint16_t cand[1024];        // stage 1 survivors of the chunk: word << 5 | bit
     uint32_t surv[64];          // stage 2 survivors: bit offset from the blob's first byte
-    uint32_t slow[64];          // ... of them, those whose header is still undecided after SP_STEPS code-length symbols
     uint8_t ctab[32][128];      // stage 3: the code-length code of each lane's candidate
 };
 // Stage 3, one candidate per lane: the whole dynamic header at bit `bit` (BFINAL) of the blob, Kraft sums kept on the fly.
@@ -440,9 +482,15 @@ __device__ int sp_verify(const uint32_t *__restrict__ w, uint32_t n_words, uint3
     return (eob && kl == (1 << 15) && (kd == (1 << 15) || (nd == 1 && kd == (1 << 14)))) ? 1 : 0;
 }
 
+// One warp per GROUP of SP_GROUP consecutive ranges of a blob.  The warp walks its stretch of the stream from header to
+// header: scan() finds the first header at or behind a position; two headers in a row give the size of a block, and
+// encoders cut blocks at a fixed number of symbols (zlib: 16 383), so the next header is looked for from 13/16 of that size
+// behind the last one on — a block whose header lies before that point is simply not found and stays part of the block
+// before it (a longer part, nothing else).  Headers go into the record of the range they lie in (the first one per range).
+// Scanned: a whole block once per group to learn the size, then ~1/5 of every block, instead of 4/5 of the stream.
 __global__ void __launch_bounds__(SP_WARPS * 32)
 inflate_split_kernel(const uint8_t *__restrict__ gz, const uint64_t *__restrict__ gz_off, int64_t n_blob,
-                     const uint32_t *__restrict__ part_off, PartRec *__restrict__ rec) {
+                     const uint32_t *__restrict__ part_off, const uint32_t *__restrict__ group_off, PartRec *__restrict__ rec) {
     __shared__ SpWarp sw_[SP_WARPS];
     __shared__ uint8_t kraft3[512];        // Kraft sum (units of 1/128) of three 3-bit code lengths
     for (int i = threadIdx.x; i < 512; i += SP_WARPS * 32) {
@@ -456,103 +504,116 @@ inflate_split_kernel(const uint8_t *__restrict__ gz, const uint64_t *__restrict_
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     SpWarp &S = sw_[wib];
-    const uint32_t n_items = part_off[n_blob];
+    const uint32_t n_items = group_off[n_blob];
     for (uint32_t item = blockIdx.x * SP_WARPS + wib; item < n_items; item += gridDim.x * SP_WARPS) {
-        const int64_t blob = tk_blob_of(part_off, n_blob, item);
-        const uint32_t j = item - part_off[blob], np = part_off[blob + 1] - part_off[blob];
-        if (j == 0) continue;              // part 0 starts behind the gzip header
+        const int64_t blob = tk_blob_of(group_off, n_blob, item);
+        const uint32_t np = part_off[blob + 1] - part_off[blob];
+        const uint32_t j0 = (item - group_off[blob]) * SP_GROUP, j1 = min(j0 + SP_GROUP, np);
+        PartRec *R = rec + part_off[blob];
+        for (uint32_t j = max(j0, 1u) + lane; j < j1; j += 32) R[j].start_bit = TK_NONE;      // part 0 starts behind the gzip header
+        __syncwarp();
+        if (np == 1) continue;
         const uint64_t len64 = gz_off[blob + 1] - gz_off[blob];
         const uint8_t *in = gz + gz_off[blob];
         const uint32_t in_len = (uint32_t)len64, mis = (uint32_t)(reinterpret_cast<uintptr_t>(in) & 3u);
         const uint32_t *w = reinterpret_cast<const uint32_t *>(in - mis);
         const uint32_t n_words = (mis + in_len + 3u) >> 2;
-        const uint64_t bit0 = 8ull * ((uint64_t)in_len * j / np);
-        const uint64_t lim = min(8ull * ((uint64_t)in_len * (j + 1) / np), 8ull * (uint64_t)in_len > 160ull ? 8ull * (uint64_t)in_len - 160ull : 0ull);
-        uint32_t found = TK_NONE, n_surv = 0, n_slow = 0;
-        // stage 3 on the first min(n, 32) entries of a list (any header of the range will do: the token phase stops at the
-        // first one at or behind the start it was given): first with a budget of SP_STEPS code-length symbols — a warp
-        // takes as long as its longest lane, and half of the candidates are refuted by then —, the undecided ones in
-        // batches of their own with the full budget
-        auto verify = [&](uint32_t *list, uint32_t &n_list, int max_steps) {
-            const uint32_t n = min(n_list, 32u);
-            const int r = lane < n ? sp_verify(w, n_words, mis, list[lane], S.ctab[lane], max_steps) : 0;
-            const unsigned m = __ballot_sync(0xFFFFFFFFu, r == 1), m2 = __ballot_sync(0xFFFFFFFFu, r == 2);
-            if (m) found = list[__ffs(m) - 1];
-            __syncwarp();
-            const uint32_t rest = n_list - n;
-            const uint32_t mv = lane < rest ? list[n + lane] : 0u, mine = lane < n ? list[lane] : 0u;
-            __syncwarp();
-            if (lane < rest) list[lane] = mv;
-            n_list = rest;
-            if (r == 2) S.slow[n_slow + __popc(m2 & ((1u << lane) - 1u))] = mine;     // (never from the slow list itself: full budget)
-            n_slow += __popc(m2);
-            __syncwarp();
-        };
-        const uint64_t a0 = 8ull * mis + bit0, a1 = 8ull * mis + lim;           // absolute bits in w[]
-        for (uint64_t kc = a0 >> 5; (kc << 5) < a1 && found == TK_NONE; kc += 32) {
-            // ---- the chunk's words
-            {
-                const uint64_t k = kc + lane;
-                S.words[lane] = __ldg(w + min(k, (uint64_t)n_words - 1u));
-                if (lane < 4) S.words[32 + lane] = __ldg(w + min(k + 32, (uint64_t)n_words - 1u));
-            }
-            __syncwarp();
-            // ---- stage 1: bit i of m is set iff offset 32 * (kc + lane) + i can be a dynamic block header
-            const uint64_t v = (uint64_t)S.words[lane] | ((uint64_t)S.words[lane + 1] << 32);
-            uint32_t m = (uint32_t)(~(v >> 1) & (v >> 2) & ~((v >> 4) & (v >> 5) & (v >> 6) & (v >> 7)) & ~((v >> 9) & (v >> 10) & (v >> 11) & (v >> 12)));
-            {
-                const uint64_t wa = (kc + lane) << 5;           // absolute bit of the lane's word
-                if (wa + 32 <= a0 || wa >= a1) m = 0;
-                else {
-                    if (wa < a0) m &= ~0u << (uint32_t)(a0 - wa);
-                    if (wa + 32 > a1) m &= ~0u >> (uint32_t)(wa + 32 - a1);
-                }
-            }
-            const uint32_t cnt = __popc(m);
-            uint32_t inc = cnt;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
-                if (lane >= (uint32_t)d) inc += t;
-            }
-            const uint32_t n_cand = __shfl_sync(0xFFFFFFFFu, inc, 31);
-            uint32_t at = inc - cnt;
-            while (m) {
-                const uint32_t i = (uint32_t)__ffs(m) - 1u;
-                m &= m - 1;
-                S.cand[at++] = (uint16_t)((lane << 5) | i);
-            }
-            __syncwarp();
-            // ---- stage 2: the code-length code is complete
-            for (uint32_t c0 = 0; c0 < n_cand && found == TK_NONE; c0 += 32) {
-                const uint32_t c = c0 + lane;
-                bool pass = false;
-                uint32_t bit = 0;
-                if (c < n_cand) {
-                    const uint32_t id = S.cand[c], wl = id >> 5, i = id & 31u;
-                    const uint32_t q0 = S.words[wl], q1 = S.words[wl + 1], q2 = S.words[wl + 2], q3 = S.words[wl + 3];
-                    const uint32_t x0 = __funnelshift_r(q0, q1, i), x1 = __funnelshift_r(q1, q2, i), x2 = __funnelshift_r(q2, q3, i);
-                    const uint32_t hclen = ((x0 >> 13) & 15u) + 4u;
-                    uint64_t f = ((uint64_t)x1 << 15) | (uint64_t)(x0 >> 17) | ((uint64_t)x2 << 47);     // the 3-bit lengths from bit 17 on
-                    f &= (1ull << (3u * hclen)) - 1ull;
-                    const uint32_t flo = (uint32_t)f, fhi = (uint32_t)(f >> 32);
-                    const uint32_t k = kraft3[flo & 511u] + kraft3[(flo >> 9) & 511u] + kraft3[(flo >> 18) & 511u] +
-                                       kraft3[__funnelshift_r(flo, fhi, 27) & 511u] + kraft3[(fhi >> 4) & 511u] + kraft3[(fhi >> 13) & 511u] +
-                                       kraft3[(fhi >> 22) & 511u];
-                    pass = k == 128u;
-                    bit = (uint32_t)((((kc + wl) << 5) + i) - 8ull * mis);
-                }
-                const unsigned pm = __ballot_sync(0xFFFFFFFFu, pass);
-                if (pass) S.surv[n_surv + __popc(pm & ((1u << lane) - 1u))] = bit;
-                n_surv += __popc(pm);
+        const uint64_t g_bit0 = j0 == 0 ? 80ull : 8ull * ((uint64_t)in_len * j0 / np);        // (a gzip header is 10 bytes at least)
+        const uint64_t g_lim = min(8ull * ((uint64_t)in_len * j1 / np), 8ull * (uint64_t)in_len > 160ull ? 8ull * (uint64_t)in_len - 160ull : 0ull);
+        // ---- the first header at a bit offset in [bit0, lim), or TK_NONE
+        auto scan = [&](uint64_t bit0, uint64_t lim) -> uint32_t {
+            uint32_t found = TK_NONE, n_surv = 0;
+            // stage 3 on the first min(n_surv, 32) survivors; the list is in rising order, so the lowest valid one is the answer
+            auto verify = [&]() {
+                const uint32_t n = min(n_surv, 32u);
+                const bool ok = lane < n && sp_verify(w, n_words, mis, S.surv[lane], S.ctab[lane], 1 << 20) == 1;
+                const unsigned m = __ballot_sync(0xFFFFFFFFu, ok);
+                if (m) found = S.surv[__ffs(m) - 1];
                 __syncwarp();
-                if (n_surv >= 32) verify(S.surv, n_surv, SP_STEPS);
-                if (n_slow >= 32 && found == TK_NONE) verify(S.slow, n_slow, 1 << 20);
+                const uint32_t rest = n_surv - n;
+                const uint32_t mv = lane < rest ? S.surv[n + lane] : 0u;
+                __syncwarp();
+                if (lane < rest) S.surv[lane] = mv;
+                n_surv = rest;
+                __syncwarp();
+            };
+            const uint64_t a0 = 8ull * mis + bit0, a1 = 8ull * mis + lim;           // absolute bits in w[]
+            for (uint64_t kc = a0 >> 5; (kc << 5) < a1 && found == TK_NONE; kc += 32) {
+                // ---- the chunk's words
+                {
+                    const uint64_t k = kc + lane;
+                    S.words[lane] = __ldg(w + min(k, (uint64_t)n_words - 1u));
+                    if (lane < 4) S.words[32 + lane] = __ldg(w + min(k + 32, (uint64_t)n_words - 1u));
+                }
+                __syncwarp();
+                // ---- stage 1: bit i of m is set iff offset 32 * (kc + lane) + i can be a dynamic block header
+                const uint64_t v = (uint64_t)S.words[lane] | ((uint64_t)S.words[lane + 1] << 32);
+                uint32_t m = (uint32_t)(~(v >> 1) & (v >> 2) & ~((v >> 4) & (v >> 5) & (v >> 6) & (v >> 7)) & ~((v >> 9) & (v >> 10) & (v >> 11) & (v >> 12)));
+                {
+                    const uint64_t wa = (kc + lane) << 5;           // absolute bit of the lane's word
+                    if (wa + 32 <= a0 || wa >= a1) m = 0;
+                    else {
+                        if (wa < a0) m &= ~0u << (uint32_t)(a0 - wa);
+                        if (wa + 32 > a1) m &= ~0u >> (uint32_t)(wa + 32 - a1);
+                    }
+                }
+                const uint32_t cnt = __popc(m);
+                uint32_t inc = cnt;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+                    if (lane >= (uint32_t)d) inc += t;
+                }
+                const uint32_t n_cand = __shfl_sync(0xFFFFFFFFu, inc, 31);
+                uint32_t at = inc - cnt;
+                while (m) {
+                    const uint32_t i = (uint32_t)__ffs(m) - 1u;
+                    m &= m - 1;
+                    S.cand[at++] = (uint16_t)((lane << 5) | i);
+                }
+                __syncwarp();
+                // ---- stage 2: the code-length code is complete
+                for (uint32_t c0 = 0; c0 < n_cand && found == TK_NONE; c0 += 32) {
+                    const uint32_t c = c0 + lane;
+                    bool pass = false;
+                    uint32_t bit = 0;
+                    if (c < n_cand) {
+                        const uint32_t id = S.cand[c], wl = id >> 5, i = id & 31u;
+                        const uint32_t q0 = S.words[wl], q1 = S.words[wl + 1], q2 = S.words[wl + 2], q3 = S.words[wl + 3];
+                        const uint32_t x0 = __funnelshift_r(q0, q1, i), x1 = __funnelshift_r(q1, q2, i), x2 = __funnelshift_r(q2, q3, i);
+                        const uint32_t hclen = ((x0 >> 13) & 15u) + 4u;
+                        uint64_t f = ((uint64_t)x1 << 15) | (uint64_t)(x0 >> 17) | ((uint64_t)x2 << 47);     // the 3-bit lengths from bit 17 on
+                        f &= (1ull << (3u * hclen)) - 1ull;
+                        const uint32_t flo = (uint32_t)f, fhi = (uint32_t)(f >> 32);
+                        const uint32_t k = kraft3[flo & 511u] + kraft3[(flo >> 9) & 511u] + kraft3[(flo >> 18) & 511u] +
+                                           kraft3[__funnelshift_r(flo, fhi, 27) & 511u] + kraft3[(fhi >> 4) & 511u] + kraft3[(fhi >> 13) & 511u] +
+                                           kraft3[(fhi >> 22) & 511u];
+                        pass = k == 128u;
+                        bit = (uint32_t)((((kc + wl) << 5) + i) - 8ull * mis);
+                    }
+                    const unsigned pm = __ballot_sync(0xFFFFFFFFu, pass);
+                    if (pass) S.surv[n_surv + __popc(pm & ((1u << lane) - 1u))] = bit;
+                    n_surv += __popc(pm);
+                    __syncwarp();
+                    if (n_surv >= 32) verify();
+                }
             }
+            while (n_surv && found == TK_NONE) verify();
+            return found;
+        };
+        // ---- from header to header
+        uint64_t cur = g_bit0;
+        uint32_t prev = TK_NONE;
+        while (cur < g_lim) {
+            const uint32_t h = scan(cur, g_lim);
+            if (h == TK_NONE) break;
+            const uint32_t j = (uint32_t)((uint64_t)h * np / (8ull * in_len));     // (h < 8 in_len: j < np)
+            if (lane == 0 && j >= 1 && j >= j0 && j < j1 && R[j].start_bit == TK_NONE) R[j].start_bit = h;
+            uint64_t skip = 64;                                                       // (a dynamic header is longer than this)
+            if (prev != TK_NONE) skip = max((unsigned long long)skip, (unsigned long long)(h - prev) * 13ull / 16ull);
+            prev = h;
+            cur = (uint64_t)h + skip;
         }
-        while (n_surv && found == TK_NONE) verify(S.surv, n_surv, SP_STEPS);
-        while (n_slow && found == TK_NONE) verify(S.slow, n_slow, 1 << 20);
-        if (lane == 0) rec[item].start_bit = found;
         __syncwarp();
     }
 }
@@ -606,9 +667,9 @@ inflate_tokens_kernel(const uint8_t *__restrict__ gz, const uint64_t *__restrict
     bool last = false;
     TkWin br;
     br.base = gz, br.n_bytes = 0, br.n_words = 0, br.mis = 0;
-    br.w0 = br.w1 = br.w2 = br.p0 = 0, br.o = 0, br.wi = 3;
+    br.w0 = br.w1 = br.w2 = br.p0 = 0, br.o = 0, br.wi = 3, br.fetched = br.landed = 0;
     br.ring = (uint32_t)__cvta_generic_to_shared(tk_smem + sizeof(TkFast) * TK_THREADS + 4 * TK_RING * threadIdx.x);
-    uint32_t lfc[15 - TK_LBITS], dfc[15 - TK_DBITS];      // the codes that are longer than a table index (tk_decode_long)
+    uint32_t lfc[15 - TK_LBITS], dfc[15 - TK_DBITS], lc15 = 0, dc15 = 0;      // the codes that are longer than a table index (tk_decode_long)
 #pragma unroll
     for (int k = 0; k < 15 - TK_LBITS; ++k) lfc[k] = 0;
 #pragma unroll
@@ -746,7 +807,7 @@ inflate_tokens_kernel(const uint8_t *__restrict__ gz, const uint64_t *__restrict
                 TkSlow &Tj = slows[j];
                 TkFast &Fj = tabs[j];
                 const bool ok1 = tk_build<TK_LBITS, false>(Tj.lens, nl, Tj.lcnt, Tj.lfirst, Tj.loffs, Tj.lsym, Fj.ltab, lane);
-                const bool ok2 = tk_build<TK_DBITS, true>(Tj.lens + (ty == 1 ? 288 : nl), nd, Tj.dcnt, Tj.dfirst, Tj.doffs, Tj.dsym, Fj.dtab, lane);
+                const bool ok2 = tk_build<TK_DBITS, true>(Tj.lens + (ty == 1 ? 288 : nl), nd, Tj.dcnt, Tj.dfirst, Tj.doffs, Fj.dsym, Fj.dtab, lane);
                 if (lane == j) {
                     if (ok1 && ok2) state = TS_SYMBOLS;
                     else err = INF_ECODE, state = TS_FINISHED;
@@ -755,9 +816,10 @@ inflate_tokens_kernel(const uint8_t *__restrict__ gz, const uint64_t *__restrict
             __syncwarp();
             if (build) {
 #pragma unroll
-                for (int k = 0; k < 15 - TK_LBITS; ++k) lfc[k] = (uint32_t)T.lfirst[TK_LBITS + 1 + k] | ((uint32_t)T.lcnt[TK_LBITS + 1 + k] << 16);
+                for (int k = 0; k < 15 - TK_LBITS; ++k) lfc[k] = (uint32_t)T.lfirst[TK_LBITS + 1 + k] | ((uint32_t)T.loffs[TK_LBITS + 1 + k] << 16);
 #pragma unroll
-                for (int k = 0; k < 15 - TK_DBITS; ++k) dfc[k] = (uint32_t)T.dfirst[TK_DBITS + 1 + k] | ((uint32_t)T.dcnt[TK_DBITS + 1 + k] << 16);
+                for (int k = 0; k < 15 - TK_DBITS; ++k) dfc[k] = (uint32_t)T.dfirst[TK_DBITS + 1 + k] | ((uint32_t)T.doffs[TK_DBITS + 1 + k] << 16);
+                lc15 = T.lcnt[15], dc15 = T.dcnt[15];
             }
             continue;
         }
@@ -769,6 +831,7 @@ inflate_tokens_kernel(const uint8_t *__restrict__ gz, const uint64_t *__restrict
         for (;;) {
             if (state == TS_SYMBOLS && (nt > tcap || pos > cap || br.past_end())) err = INF_ETOKENS, state = TS_FINISHED;
             bool act = state == TS_SYMBOLS;
+            br.top_up(act);
             const bool was = act;
 #pragma unroll TK_UNROLL
             for (int it = 0; it < TK_GROUP; ++it) {
@@ -782,7 +845,7 @@ inflate_tokens_kernel(const uint8_t *__restrict__ gz, const uint64_t *__restrict
                 const uint32_t n2 = d & 31u, dx = (d >> 5) & 15u;
                 const uint32_t dist = s_dbase[(d >> 9) & 31u] + ((lo2 >> (n2 - dx)) & ((1u << dx) - 1u));
                 const bool commit = act && n1 != 0u && !(is_len && n2 == 0u);
-                br.drop(commit ? n1 + (is_len ? n2 : 0u) : 0u);
+                br.drop_fast(commit ? n1 + (is_len ? n2 : 0u) : 0u);
                 if (commit) {
                     tok[nt++] = is_len ? ((dist << 9) | len) : (v << 9);
                     pos += is_len ? len : 1u;
@@ -800,10 +863,9 @@ inflate_tokens_kernel(const uint8_t *__restrict__ gz, const uint64_t *__restrict
                         sym = 1000u;          // (a length symbol: base and extra bits from the entry)
                     } else if (e & 0x8000u) sym = 256u, cl = (e >> 4) & 15u;
                     else if (e == 0u) {
-                        uint32_t rank;
-                        cl = tk_decode_long<TK_LBITS>(pk, lfc, &rank);
+                        uint32_t k;
+                        cl = tk_decode_long<TK_LBITS>(pk, lfc, lc15, &k);
                         if (cl) {
-                            const uint32_t k = T.loffs[cl] + rank;
                             if (k < (uint32_t)nlen) sym = T.lsym[k];
                         } else cl = 1;
                     }
@@ -820,11 +882,10 @@ inflate_tokens_kernel(const uint8_t *__restrict__ gz, const uint64_t *__restrict
                         uint32_t dl = 1, ds = 31u;
                         if (d & 31u) dl = (d & 31u) - ((d >> 5) & 15u), ds = d >> 9;
                         else if (d == 0u) {
-                            uint32_t rank;
-                            dl = tk_decode_long<TK_DBITS>(pk, dfc, &rank);
+                            uint32_t k2;
+                            dl = tk_decode_long<TK_DBITS>(pk, dfc, dc15, &k2);
                             if (dl) {
-                                const uint32_t k2 = T.doffs[dl] + rank;
-                                if (k2 < (uint32_t)ndist) ds = T.dsym[k2];
+                                if (k2 < (uint32_t)ndist) ds = F.dsym[k2];
                             } else dl = 1;
                         }
                         if (ds > 29u) err = INF_ECODE, ds = 0;
@@ -1110,7 +1171,7 @@ int32_t launch_gunzip2(PerDevice &pd, cudaStream_t st, const uint8_t *d_gz, cons
     const uint64_t n_tokens = decoder == 0 ? (total_out >> 1) + 64ull * (uint64_t)(n_blob + 1) + 64 : 0;
     const uint64_t n_piece_max = total_out / CRC_PIECE + (uint64_t)n_blob + 1;
     const size_t o_rec = ((size_t)n_tokens * 4 + 31) & ~(size_t)31, o_poffs = o_rec + (decoder == 0 ? (size_t)p_cap * sizeof(PartRec) : 0),
-                 o_slow = (o_poffs + (decoder == 0 ? (size_t)(n_blob + 1) * 4 : 0) + 15) & ~(size_t)15,
+                 o_slow = (o_poffs + (decoder == 0 ? (size_t)(n_blob + 1) * 8 : 0) + 15) & ~(size_t)15,
                  o_crc = o_slow + (decoder == 0 ? (size_t)n_lanes * sizeof(TkSlow) : 0),
                  o_poff = (o_crc + (size_t)n_blob * 4 + 15) & ~(size_t)15, o_pcrc = o_poff + (size_t)(n_blob + 1) * 8,
                  bytes = o_pcrc + (check_crc ? (size_t)n_piece_max * 4 : 0) + 64;
@@ -1118,7 +1179,7 @@ int32_t launch_gunzip2(PerDevice &pd, cudaStream_t st, const uint8_t *d_gz, cons
     if ((rc = pd.scratch[7].reserve(bytes))) return rc;
     uint8_t *base = pd.scratch[7].as<uint8_t>();
     uint32_t *d_tok = reinterpret_cast<uint32_t *>(base), *d_crc = reinterpret_cast<uint32_t *>(base + o_crc),
-             *d_pcrc = reinterpret_cast<uint32_t *>(base + o_pcrc), *d_parts = reinterpret_cast<uint32_t *>(base + o_poffs);
+             *d_pcrc = reinterpret_cast<uint32_t *>(base + o_pcrc), *d_parts = reinterpret_cast<uint32_t *>(base + o_poffs), *d_groups = d_parts + (n_blob + 1);
     PartRec *d_rec = reinterpret_cast<PartRec *>(base + o_rec);
     TkSlow *d_slow = reinterpret_cast<TkSlow *>(base + o_slow);
     uint64_t *d_poff = reinterpret_cast<uint64_t *>(base + o_poff);
@@ -1126,9 +1187,9 @@ int32_t launch_gunzip2(PerDevice &pd, cudaStream_t st, const uint8_t *d_gz, cons
     if (decoder == 0) {
         const size_t smem = TK_SMEM;
         CUDA_TRY(cudaFuncSetAttribute(inflate_tokens_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        inflate_parts_kernel<<<1, 1024, 0, st>>>(d_gz_off, d_out_off, n_blob, p_cap, d_parts);
-        const unsigned s_blocks = (unsigned)std::min<uint64_t>((p_cap + SP_WARPS - 1) / SP_WARPS, (uint64_t)n_sm * 16);
-        inflate_split_kernel<<<s_blocks, SP_WARPS * 32, 0, st>>>(d_gz, d_gz_off, n_blob, d_parts, d_rec);
+        inflate_parts_kernel<<<1, 1024, 0, st>>>(d_gz_off, d_out_off, n_blob, p_cap, d_parts, d_groups);
+        const unsigned s_blocks = (unsigned)std::min<uint64_t>((p_cap / SP_GROUP + (uint64_t)n_blob + SP_WARPS) / SP_WARPS, (uint64_t)n_sm * 16);
+        inflate_split_kernel<<<s_blocks, SP_WARPS * 32, 0, st>>>(d_gz, d_gz_off, n_blob, d_parts, d_groups, d_rec);
         CUDA_TRY(cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), st));
         const unsigned t_blocks = (unsigned)std::min<uint64_t>((p_cap + TK_THREADS - 1) / TK_THREADS, (uint64_t)n_sm);
         inflate_tokens_kernel<<<t_blocks, TK_THREADS, smem, st>>>(d_gz, d_gz_off, n_blob, d_out_off, d_parts, d_tok, d_rec, d_slow, d_counter);
