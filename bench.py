@@ -583,6 +583,31 @@ def main():
         e2e["peaks_only"] = {"value": total_bases * n_e2e / dtp / 1e9, "unit": "Gbp/s", "ms_per_step": dtp / n_e2e * 1e3,
                              "h2d_bytes_per_step": int(n_bases), "d2h_bytes_per_step": int(n_pk.value * 17 + 8),
                              "peak_records": int(n_pk.value), "api": "gams_cuda_wave_peaks_batch (host pointers, pinned; merge_ints on the device)"}
+        if gz_host is not None:
+            # ... and fed with the gzip blobs: `gams wave` between its GET and its print (get_seq + proc_ctg + merge_ints)
+            pk2 = [np.empty(cap, dtype=dt) for dt in (np.uint32, np.uint32, np.uint32, np.float32, np.int8)]
+            n_pk2 = C.c_uint64()
+            st_gz2 = np.zeros(n_ctg, dtype=np.int32)
+            vp = lambda a: a.ctypes.data_as(C.c_void_p)
+
+            def peaks_gz_step():
+                api.check(L.gams_cuda_wave_peaks_gz_batch(ctx.handle, n_ctg, gz_host[0], vp(gz_host[1]), vp(seq_off), SIZE, STEP, LAG,
+                                                          THRESHOLD, args.influence, 0.2, vp(woff), cap, *[vp(a) for a in pk2],
+                                                          C.byref(n_pk2), vp(st_gz2)))
+
+            peaks_gz_step()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(n_e2e):
+                peaks_gz_step()
+            dtq = max_over_ranks(time.perf_counter() - t0)
+            k = int(n_pk.value)
+            same_pk = bool(n_pk2.value == n_pk.value and all(np.array_equal(a[:k], b[:k]) for a, b in zip(pk, pk2)))
+            e2e_gz["peaks_only"] = {"value": total_bases * n_e2e / dtq / 1e9, "unit": "Gbp/s", "ms_per_step": dtq / n_e2e * 1e3,
+                                    "h2d_bytes_per_step": int(gz_host[2]), "d2h_bytes_per_step": int(n_pk2.value * 17 + 8 + n_ctg * 4),
+                                    "peak_records": int(n_pk2.value), "equals_peaks_from_bases": same_pk,
+                                    "api": "gams_cuda_wave_peaks_gz_batch (gzip blobs in pinned host memory -> device gunzip incl. CRC-32 -> "
+                                           "fused GC-wave -> merge_ints on the device; peak records out)"}
 
     # ---- feed step (a18): the seq:{ctg} blobs as Redis holds them (gzip, level 1) inflated on the device ------------
     feed = None

@@ -62,6 +62,7 @@ def load() -> C.CDLL:
         "gams_cuda_wave_gz_batch": (i32, [vp, i64, vp, vp, vp, i32, i32, u64, f32, f32, vp, vp, vp, vp, vp]),
         "gams_cuda_thresholding_batch": (i32, [vp, i64, vp, vp, u64, f32, f32, vp]),
         "gams_cuda_wave_peaks_batch": (i32, [vp, i64, vp, vp, i32, i32, u64, f32, f32, f32, vp, u64, vp, vp, vp, vp, vp, vp]),
+        "gams_cuda_wave_peaks_gz_batch": (i32, [vp, i64, vp, vp, vp, i32, i32, u64, f32, f32, f32, vp, u64, vp, vp, vp, vp, vp, vp, vp]),
         "gams_cuda_wave_peaks_dev": (i32, [vp, vp, vp, vp, f32, u64, vp, vp, vp, vp, vp, vp]),
         "gams_cuda_peak_link_batch": (i32, [vp, i64, vp, vp, vp, i64] + [vp] * 11),
         "gams_cuda_wave_peaks_text": (i32, [C.c_char_p, i32, i32, i32, i64, vp, vp, vp, vp, C.POINTER(vp), C.POINTER(sz)]),

@@ -194,6 +194,29 @@ def wave_peaks_batch(ctx: Context, seq_concat, seq_off, size=100, step=10, lag=1
         return dict(ctg=ctg[:k], first=first[:k], last=last[:k], gc=gc[:k], signal=sig[:k])
 
 
+def wave_peaks_gz_batch(ctx: Context, gz_concat, gz_off, seq_off, size=100, step=10, lag=100, threshold=3.0, influence=1.0,
+                        coverage=0.2, cap=None, raise_on_error=True):
+    """get_seq + `gams wave` (merged peaks) for ctgs held as seq:{ctg} gzip blobs → (records as wave_peaks_batch, inflate status)."""
+    gz_concat, gz_off, seq_off = _arr(gz_concat, np.uint8), _arr(gz_off, np.uint64), _arr(seq_off, np.uint64)
+    woff = win_offsets(seq_off, size, step)
+    L = load()
+    cap = int(cap if cap is not None else max(4096, int(woff[-1]) // 32))
+    status = np.zeros(seq_off.size - 1, dtype=np.int32)
+    while True:
+        ctg, first, last = (np.empty(cap, dtype=np.uint32) for _ in range(3))
+        gc, sig, n = np.empty(cap, dtype=np.float32), np.empty(cap, dtype=np.int8), C.c_uint64()
+        rc = L.gams_cuda_wave_peaks_gz_batch(ctx.handle, seq_off.size - 1, _p(gz_concat), _p(gz_off), _p(seq_off), size, step, lag,
+                                             threshold, influence, coverage, _p(woff), cap, _p(ctg), _p(first), _p(last), _p(gc),
+                                             _p(sig), C.byref(n), _p(status))
+        if rc == -7 and n.value > cap:  # ECAP: the call reports how many records there are
+            cap = int(n.value)
+            continue
+        if rc and (raise_on_error or not status.any()):
+            check(rc)
+        k = 0 if rc else int(n.value)
+        return dict(ctg=ctg[:k], first=first[:k], last=last[:k], gc=gc[:k], signal=sig[:k]), status
+
+
 def wave_peaks_text(chr_id: str, chr_start: int, size: int, step: int, first, last, gc, signal) -> str:
     """The per-ctg stdout block of `gams wave` from the peak records of that ctg."""
     first, last = _arr(first, np.uint32), _arr(last, np.uint32)

@@ -671,8 +671,17 @@ static int32_t wave_on_device(gams_cuda_ctx *ctx, int d, int64_t c0, int64_t c1,
         int32_t *d_status = reinterpret_cast<int32_t *>(d_ooff + (n + 1));
         CUDA_TRY(cudaMemcpyAsync(d_goff, gz_rel.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, pd.stream));
         CUDA_TRY(cudaMemcpyAsync(d_ooff, seq_rel.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, pd.stream));
-        if (n_sl) CUDA_TRY(cudaStreamWaitEvent(pd.stream, ev_in[n_sl - 1], 0));
-        if ((rc = launch_gunzip2(pd, pd.stream, d_gz, d_goff, n, d_seq, d_ooff, d_status, nb, ctx->gunzip_mode, ctx->gunzip_crc != 0))) return rc;
+        // the decoder's header search follows the upload in (up to) four stretches; the last event is the whole batch
+        std::vector<int64_t> arrive_end;
+        std::vector<cudaEvent_t> arrive_ev;
+        for (size_t q = 1; q <= 4 && n_sl; ++q) {
+            const size_t k = n_sl * q / 4;
+            if (k == 0 || (!arrive_end.empty() && cut[k] == arrive_end.back())) continue;
+            arrive_end.push_back(cut[k]), arrive_ev.push_back(ev_in[k - 1]);
+        }
+        if ((rc = launch_gunzip2(pd, pd.stream, d_gz, d_goff, n, d_seq, d_ooff, d_status, nb, ctx->gunzip_mode, ctx->gunzip_crc != 0,
+                                 (int)arrive_end.size(), arrive_end.data(), arrive_ev.data())))
+            return rc;
         CUDA_TRY(cudaMemcpyAsync(gzs->status + c0, d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, pd.stream));
         trace_stage("wave: gunzip", pd.stream, true);
     }
@@ -830,18 +839,11 @@ GAMS_API int32_t gams_cuda_wave_gz_batch(gams_cuda_ctx *ctx, int64_t n_ctg, cons
     return GAMS_CUDA_OK;
 }
 
-GAMS_API int32_t gams_cuda_wave_peaks_batch(gams_cuda_ctx *ctx, int64_t n_ctg, const uint8_t *seq_concat,
-                                            const uint64_t *seq_off, int32_t size, int32_t step, uint64_t lag,
-                                            float threshold, float influence, float coverage, const uint64_t *win_off,
-                                            uint64_t cap, uint32_t *pk_ctg, uint32_t *pk_first, uint32_t *pk_last,
-                                            float *pk_gc, int8_t *pk_signal, uint64_t *n_peaks) {
-    ARG_CHECK(ctx && n_peaks, "wave_peaks_batch: NULL argument");
-    ARG_CHECK(n_ctg >= 0 && seq_off && win_off, "wave_peaks_batch: NULL offsets");
-    ARG_CHECK(size > 0 && step > 0, "wave_peaks_batch: size and step must be positive (got %d, %d)", size, step);
-    ARG_CHECK(cap == 0 || (pk_ctg && pk_first && pk_last && pk_gc && pk_signal), "wave_peaks_batch: NULL output");
-    *n_peaks = 0;
-    if (n_ctg == 0) return GAMS_CUDA_OK;
-    ARG_CHECK(seq_concat || seq_off[n_ctg] == seq_off[0], "wave_peaks_batch: seq_concat is NULL");
+// gams_cuda_wave_peaks_batch / gams_cuda_wave_peaks_gz_batch: the bases, or the gzip blobs that hold them (gzs)
+static int32_t wave_peaks_impl(gams_cuda_ctx *ctx, const char *who, int64_t n_ctg, const uint8_t *seq_concat, GzSource *gzs,
+                               const uint64_t *seq_off, int32_t size, int32_t step, uint64_t lag, float threshold, float influence,
+                               float coverage, const uint64_t *win_off, uint64_t cap, uint32_t *pk_ctg, uint32_t *pk_first,
+                               uint32_t *pk_last, float *pk_gc, int8_t *pk_signal, uint64_t *n_peaks) {
     std::lock_guard<std::mutex> lk(ctx->mu);
     const int n_dev = (int)std::min<int64_t>((int64_t)ctx->devs.size(), n_ctg);
     std::vector<int64_t> part((size_t)n_dev + 1);
@@ -856,14 +858,20 @@ GAMS_API int32_t gams_cuda_wave_peaks_batch(gams_cuda_ctx *ctx, int64_t n_ctg, c
     }
     rc = for_each_device(ctx, n_dev, [&](int d) {
         return wave_on_device(ctx, d, part[d], part[d + 1], seq_concat, seq_off, size, step, lag, threshold, influence, win_off,
-                              nullptr, nullptr, nullptr, &sinks[d]);
+                              nullptr, nullptr, nullptr, &sinks[d], gzs);
     });
     if (rc) return rc;
+    if (gzs)
+        for (int64_t c = 0; c < n_ctg; ++c)
+            if (gzs->status[c] != 0) {
+                set_error("%s: seq blob %lld failed with inflate status %d (its peaks are undefined)", who, (long long)c, (int)gzs->status[c]);
+                return GAMS_CUDA_EINVAL;
+            }
     uint64_t total = 0;
     for (auto &sk : sinks) total += sk.n;
     *n_peaks = total;
     if (total > cap) {
-        set_error("wave_peaks_batch: %llu peak records, room for %llu (n_peaks is set: call again with larger arrays)",
+        set_error("%s: %llu peak records, room for %llu (n_peaks is set: call again with larger arrays)", who,
                   (unsigned long long)total, (unsigned long long)cap);
         return GAMS_CUDA_ECAP;
     }
@@ -880,6 +888,44 @@ GAMS_API int32_t gams_cuda_wave_peaks_batch(gams_cuda_ctx *ctx, int64_t n_ctg, c
         }
     }
     return GAMS_CUDA_OK;
+}
+
+GAMS_API int32_t gams_cuda_wave_peaks_batch(gams_cuda_ctx *ctx, int64_t n_ctg, const uint8_t *seq_concat,
+                                            const uint64_t *seq_off, int32_t size, int32_t step, uint64_t lag,
+                                            float threshold, float influence, float coverage, const uint64_t *win_off,
+                                            uint64_t cap, uint32_t *pk_ctg, uint32_t *pk_first, uint32_t *pk_last,
+                                            float *pk_gc, int8_t *pk_signal, uint64_t *n_peaks) {
+    ARG_CHECK(ctx && n_peaks, "wave_peaks_batch: NULL argument");
+    ARG_CHECK(n_ctg >= 0 && seq_off && win_off, "wave_peaks_batch: NULL offsets");
+    ARG_CHECK(size > 0 && step > 0, "wave_peaks_batch: size and step must be positive (got %d, %d)", size, step);
+    ARG_CHECK(cap == 0 || (pk_ctg && pk_first && pk_last && pk_gc && pk_signal), "wave_peaks_batch: NULL output");
+    *n_peaks = 0;
+    if (n_ctg == 0) return GAMS_CUDA_OK;
+    ARG_CHECK(seq_concat || seq_off[n_ctg] == seq_off[0], "wave_peaks_batch: seq_concat is NULL");
+    return wave_peaks_impl(ctx, "wave_peaks_batch", n_ctg, seq_concat, nullptr, seq_off, size, step, lag, threshold, influence, coverage,
+                           win_off, cap, pk_ctg, pk_first, pk_last, pk_gc, pk_signal, n_peaks);
+}
+
+// `gams wave` without --signal from the seq:{ctg} values as Redis holds them: Conn::get_seq (redis.rs:142-161) + proc_ctg
+// (wave.rs:138-212) + merge_ints (wave.rs:217-252); a third of the bytes go up, a few MB of peak records come back.
+GAMS_API int32_t gams_cuda_wave_peaks_gz_batch(gams_cuda_ctx *ctx, int64_t n_ctg, const uint8_t *gz_concat, const uint64_t *gz_off,
+                                               const uint64_t *seq_off, int32_t size, int32_t step, uint64_t lag, float threshold,
+                                               float influence, float coverage, const uint64_t *win_off, uint64_t cap,
+                                               uint32_t *pk_ctg, uint32_t *pk_first, uint32_t *pk_last, float *pk_gc,
+                                               int8_t *pk_signal, uint64_t *n_peaks, int32_t *status) {
+    ARG_CHECK(ctx && n_peaks, "wave_peaks_gz_batch: NULL argument");
+    ARG_CHECK(n_ctg >= 0 && gz_off && seq_off && win_off, "wave_peaks_gz_batch: NULL offsets");
+    ARG_CHECK(size > 0 && step > 0, "wave_peaks_gz_batch: size and step must be positive (got %d, %d)", size, step);
+    ARG_CHECK(cap == 0 || (pk_ctg && pk_first && pk_last && pk_gc && pk_signal), "wave_peaks_gz_batch: NULL output");
+    *n_peaks = 0;
+    if (n_ctg == 0) return GAMS_CUDA_OK;
+    ARG_CHECK(gz_concat && status, "wave_peaks_gz_batch: NULL blobs / status");
+    for (int64_t c = 0; c < n_ctg; ++c)
+        ARG_CHECK(gz_off[c + 1] >= gz_off[c], "wave_peaks_gz_batch: gz_off decreases at %lld", (long long)c);
+    GzSource src;
+    src.gz_concat = gz_concat, src.gz_off = gz_off, src.status = status;
+    return wave_peaks_impl(ctx, "wave_peaks_gz_batch", n_ctg, nullptr, &src, seq_off, size, step, lag, threshold, influence, coverage,
+                           win_off, cap, pk_ctg, pk_first, pk_last, pk_gc, pk_signal, n_peaks);
 }
 
 GAMS_API int32_t gams_cuda_thresholding_batch(gams_cuda_ctx *ctx, int64_t n_series, const float *data,

@@ -490,7 +490,8 @@ __device__ int sp_verify(const uint32_t *__restrict__ w, uint32_t n_words, uint3
 // Scanned: a whole block once per group to learn the size, then ~1/5 of every block, instead of 4/5 of the stream.
 __global__ void __launch_bounds__(SP_WARPS * 32)
 inflate_split_kernel(const uint8_t *__restrict__ gz, const uint64_t *__restrict__ gz_off, int64_t n_blob,
-                     const uint32_t *__restrict__ part_off, const uint32_t *__restrict__ group_off, PartRec *__restrict__ rec) {
+                     const uint32_t *__restrict__ part_off, const uint32_t *__restrict__ group_off, PartRec *__restrict__ rec,
+                     int64_t blob0, int64_t blob1) {      // the groups of blobs blob0 .. blob1 - 1
     __shared__ SpWarp sw_[SP_WARPS];
     __shared__ uint8_t kraft3[512];        // Kraft sum (units of 1/128) of three 3-bit code lengths
     for (int i = threadIdx.x; i < 512; i += SP_WARPS * 32) {
@@ -504,8 +505,8 @@ inflate_split_kernel(const uint8_t *__restrict__ gz, const uint64_t *__restrict_
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     SpWarp &S = sw_[wib];
-    const uint32_t n_items = group_off[n_blob];
-    for (uint32_t item = blockIdx.x * SP_WARPS + wib; item < n_items; item += gridDim.x * SP_WARPS) {
+    const uint32_t n_items = group_off[blob1];
+    for (uint32_t item = group_off[blob0] + blockIdx.x * SP_WARPS + wib; item < n_items; item += gridDim.x * SP_WARPS) {
         const int64_t blob = tk_blob_of(group_off, n_blob, item);
         const uint32_t np = part_off[blob + 1] - part_off[blob];
         const uint32_t j0 = (item - group_off[blob]) * SP_GROUP, j1 = min(j0 + SP_GROUP, np);
@@ -1155,7 +1156,8 @@ crc32_fold_kernel(const uint64_t *__restrict__ out_off, int64_t n_blob, const ui
 }
 
 int32_t launch_gunzip2(PerDevice &pd, cudaStream_t st, const uint8_t *d_gz, const uint64_t *d_gz_off, int64_t n_blob, uint8_t *d_out,
-                       const uint64_t *d_out_off, int32_t *d_status, uint64_t total_out, int decoder, bool check_crc) {
+                       const uint64_t *d_out_off, int32_t *d_status, uint64_t total_out, int decoder, bool check_crc, int n_arrive,
+                       const int64_t *arrive_end, const cudaEvent_t *arrive_ev) {
     if (n_blob == 0) return GAMS_CUDA_OK;
     if (n_blob >= (1ll << 30)) {
         set_error("gunzip: too many blobs for one launch");
@@ -1188,8 +1190,18 @@ int32_t launch_gunzip2(PerDevice &pd, cudaStream_t st, const uint8_t *d_gz, cons
         const size_t smem = TK_SMEM;
         CUDA_TRY(cudaFuncSetAttribute(inflate_tokens_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         inflate_parts_kernel<<<1, 1024, 0, st>>>(d_gz_off, d_out_off, n_blob, p_cap, d_parts, d_groups);
-        const unsigned s_blocks = (unsigned)std::min<uint64_t>((p_cap / SP_GROUP + (uint64_t)n_blob + SP_WARPS) / SP_WARPS, (uint64_t)n_sm * 16);
-        inflate_split_kernel<<<s_blocks, SP_WARPS * 32, 0, st>>>(d_gz, d_gz_off, n_blob, d_parts, d_groups, d_rec);
+        // the header search needs nothing but the compressed bytes: it runs on each stretch of blobs as soon as that stretch
+        // has arrived (arrive_ev[i] fires when blobs < arrive_end[i] are on the device), while the rest is still on the link
+        int64_t b0 = 0;
+        for (int i = 0; i <= n_arrive; ++i) {
+            const int64_t b1 = i < n_arrive ? std::min<int64_t>(arrive_end[i], n_blob) : n_blob;
+            if (i < n_arrive) CUDA_TRY(cudaStreamWaitEvent(st, arrive_ev[i], 0));
+            if (b1 <= b0) continue;
+            const uint64_t share = (p_cap / SP_GROUP) * (uint64_t)(b1 - b0) / (uint64_t)n_blob + (uint64_t)(b1 - b0);
+            const unsigned s_blocks = (unsigned)std::min<uint64_t>((share + SP_WARPS) / SP_WARPS, (uint64_t)n_sm * 16);
+            inflate_split_kernel<<<s_blocks, SP_WARPS * 32, 0, st>>>(d_gz, d_gz_off, n_blob, d_parts, d_groups, d_rec, b0, b1);
+            b0 = b1;
+        }
         CUDA_TRY(cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), st));
         const unsigned t_blocks = (unsigned)std::min<uint64_t>((p_cap + TK_THREADS - 1) / TK_THREADS, (uint64_t)n_sm);
         inflate_tokens_kernel<<<t_blocks, TK_THREADS, smem, st>>>(d_gz, d_gz_off, n_blob, d_out_off, d_parts, d_tok, d_rec, d_slow, d_counter);

@@ -127,6 +127,16 @@ int32_t gams_cuda_wave_peaks_batch(gams_cuda_ctx *ctx, int64_t n_ctg, const uint
                                    uint64_t cap, uint32_t *pk_ctg, uint32_t *pk_first, uint32_t *pk_last,
                                    float *pk_gc, int8_t *pk_signal, uint64_t *n_peaks);
 
+/* The same from the seq:{ctg} values as Redis holds them (gams_cuda_wave_gz_batch's input): Conn::get_seq
+ * (src/libs/redis.rs:142-161) + wave::proc_ctg without --signal (wave.rs:138-212) + merge_ints (wave.rs:217-252) in one call —
+ * what `gams wave` does per ctg between its GET and its print.  A third of the bytes of the bases go up, the peak records come
+ * back.  status[c]: inflate status of blob c; GAMS_CUDA_EINVAL if any blob failed. */
+int32_t gams_cuda_wave_peaks_gz_batch(gams_cuda_ctx *ctx, int64_t n_ctg, const uint8_t *gz_concat, const uint64_t *gz_off,
+                                      const uint64_t *seq_off, int32_t size, int32_t step, uint64_t lag, float threshold,
+                                      float influence, float coverage, const uint64_t *win_off, uint64_t cap,
+                                      uint32_t *pk_ctg, uint32_t *pk_first, uint32_t *pk_last, float *pk_gc,
+                                      int8_t *pk_signal, uint64_t *n_peaks, int32_t *status);
+
 /* `gams peak`, src/cmd_gams/peak.rs:66-160, for peaks sorted by (ctg, start): GC content of each peak range
  * (cache_gc_content, utils.rs:141-162: rounded to 4 decimals) and its links to the previous / next peak of the ctg:
  *   left_wave_length  = start - prev_end + 1   (prev_end = the ctg's chr_start for the first peak)

@@ -92,6 +92,11 @@ extern "C" {
         threshold: f32, influence: f32, coverage: f32, win_off: *const u64, cap: u64, pk_ctg: *mut u32, pk_first: *mut u32,
         pk_last: *mut u32, pk_gc: *mut f32, pk_signal: *mut i8, n_peaks: *mut u64,
     ) -> i32;
+    pub fn gams_cuda_wave_peaks_gz_batch(
+        ctx: *mut gams_cuda_ctx, n_ctg: i64, gz_concat: *const u8, gz_off: *const u64, seq_off: *const u64, size: i32, step: i32,
+        lag: u64, threshold: f32, influence: f32, coverage: f32, win_off: *const u64, cap: u64, pk_ctg: *mut u32,
+        pk_first: *mut u32, pk_last: *mut u32, pk_gc: *mut f32, pk_signal: *mut i8, n_peaks: *mut u64, status: *mut i32,
+    ) -> i32;
     pub fn gams_cuda_wave_peaks_dev(
         plan: *mut gams_cuda_wave_plan, stream: *mut c_void, d_gc: *const f32, d_signal: *const i8, coverage: f32, cap: u64,
         d_pk_ctg: *mut u32, d_pk_first: *mut u32, d_pk_last: *mut u32, d_pk_gc: *mut f32, d_pk_signal: *mut i8,

@@ -363,6 +363,101 @@ def test_wave_gz_batch_reports_a_bad_blob(ctx, orc):
     assert st[0] != 0
 
 
+def _multi_block_gz(rng, dna, pieces, header_extra=b""):
+    """One gzip member whose deflate stream is cut into blocks of the given (length, mode): dynamic blocks of level 1 / 6 / 9,
+    fixed-Huffman blocks (Z_FIXED), stored blocks (level 0), empty stored blocks (Z_SYNC_FLUSH) and byte-aligned restarts
+    (Z_FULL_FLUSH) — block boundaries at irregular distances, headers of every type, some of them only a few bytes apart."""
+    import struct, zlib
+    raw, body = bytearray(), bytearray()
+    comp = None
+    for n, mode in pieces:
+        a = int(rng.integers(0, len(dna) - n))
+        chunk = dna[a:a + n]
+        raw += chunk
+        level, strategy = {"l1": (1, 0), "l6": (6, 0), "l9": (9, 0), "fixed": (1, zlib.Z_FIXED), "stored": (0, 0)}[mode]
+        if comp is None:
+            comp = zlib.compressobj(level, zlib.DEFLATED, -15, 8, strategy)
+            cur = (level, strategy)
+        elif cur != (level, strategy):
+            # a new compressor for the new parameters: the stream so far ends at a byte boundary (Z_FULL_FLUSH), the next
+            # compressor continues it — its first match may not reach back, which zlib guarantees for a fresh object
+            body += comp.flush(zlib.Z_FULL_FLUSH)
+            comp = zlib.compressobj(level, zlib.DEFLATED, -15, 8, strategy)
+            cur = (level, strategy)
+        body += comp.compress(chunk)
+        body += comp.flush(zlib.Z_SYNC_FLUSH if rng.random() < 0.5 else zlib.Z_FULL_FLUSH)
+    body += comp.flush(zlib.Z_FINISH)
+    flg = 8 if header_extra else 0
+    head = b"\x1f\x8b\x08" + bytes([flg]) + b"\0\0\0\0\0\xff" + (header_extra + b"\0" if header_extra else b"")
+    return bytes(raw), head + bytes(body) + struct.pack("<II", zlib.crc32(bytes(raw)) & 0xFFFFFFFF, len(raw) & 0xFFFFFFFF)
+
+
+def test_gunzip_parts_at_irregular_block_boundaries(ctx, orc):
+    """The part-parallel decoder (a part per deflate block found by the header search) on streams it cannot predict: blocks
+    of 40 bytes to 400 KB in one member, dynamic / fixed / stored / empty blocks in any order, a 30 KB FNAME in front of the
+    first block, text and random bytes next to sequence — byte for byte what zlib gives, and the same from both decoders."""
+    import zlib
+    rng = np.random.default_rng(77)
+    dna = synth.genome(1_500_000, seed=78).tobytes()
+    text = (b"The quick brown fox jumps over the lazy dog. " * 64 + bytes(rng.integers(32, 127, 4096, dtype=np.uint8))) * 40
+    modes = ["l1", "l1", "l1", "l6", "l9", "fixed", "stored"]
+    plain, blobs = [], []
+    for k in range(24):
+        pieces = [(int(rng.choice([40, 300, 5_000, 30_000, 70_000, 200_000, 400_000], p=[.1, .1, .15, .2, .25, .15, .05])), str(rng.choice(modes)))
+                  for _ in range(int(rng.integers(2, 14)))]
+        raw, gz = _multi_block_gz(rng, dna if k % 4 else text, pieces, header_extra=b"n" * 30_000 if k == 5 else b"")
+        assert zlib.decompress(gz, 31) == raw
+        plain.append(raw), blobs.append(gz)
+    big = dna[:1_400_000]                        # one long member of plain level-1 blocks among them (~21 blocks)
+    plain.append(big), blobs.append(_gzb(big))
+    gcat, goff = api.pack_blobs(blobs)
+    for decoder in (0, 1):
+        ctx.set_gunzip_options(decoder, True)
+        out, off, st = api.gunzip_batch(ctx, gcat, goff)
+        assert not st.any(), st
+        for i, p in enumerate(plain):
+            assert out[int(off[i]):int(off[i + 1])].tobytes() == p, f"decoder {decoder}, blob {i}"
+    ctx.set_gunzip_options(0, True)
+
+
+def test_gunzip_one_huge_blob_and_many_tiny(ctx, orc):
+    """Batches at the two ends of the part table: one 12 Mbp member alone (hundreds of ranges, several groups of the header
+    search), and 3000 members of 0..300 bases (one range each)."""
+    rng = np.random.default_rng(79)
+    dna = synth.genome(12_000_000, seed=80).tobytes()
+    out, off, st = api.gunzip_batch(ctx, *api.pack_blobs([_gzb(dna)]))
+    assert not st.any() and out.tobytes() == dna
+    cuts = np.concatenate(([0], np.cumsum(rng.integers(0, 301, 3000))))
+    small = [dna[int(a):int(b)] for a, b in zip(cuts[:-1], cuts[1:])]
+    out, off, st = api.gunzip_batch(ctx, *api.pack_blobs([_gzb(s) for s in small]))
+    assert not st.any() and out.tobytes() == b"".join(small)
+
+
+def test_wave_peaks_gz_batch_equals_wave_peaks_batch(ctx, orc):
+    """gams_cuda_wave_peaks_gz_batch (get_seq + wave without --signal + merge_ints) gives the records gams_cuda_wave_peaks_batch
+    gives on the bases; a corrupted blob fails the call with its status."""
+    g = synth.genome(2_400_000, seed=93)
+    cuts = [0, 500_000, 1_000_003, 1_000_903, 1_900_000, 2_400_000]
+    seqs = [g[a:b] for a, b in zip(cuts[:-1], cuts[1:])]
+    cat, off = orc.pack_ctgs(seqs)
+    blobs = [orc.encode_gz(s.tobytes()) for s in seqs]
+    gcat, goff = api.pack_blobs(blobs)
+    ref = api.wave_peaks_batch(ctx, cat, off, 100, 10, 50, 3.0, 1.0, 0.2)
+    got, st = api.wave_peaks_gz_batch(ctx, gcat, goff, off, 100, 10, 50, 3.0, 1.0, 0.2)
+    assert not st.any() and ref["ctg"].size > 0
+    for k in ("ctg", "first", "last", "signal"):
+        _eq(k, got[k], ref[k])
+    _eq("gc", got["gc"].view(np.uint32), ref["gc"].view(np.uint32))
+    got2, _ = api.wave_peaks_gz_batch(ctx, gcat, goff, off, 100, 10, 50, 3.0, 1.0, 0.2, cap=8)     # ECAP, then the exact size
+    _eq("first (small cap)", got2["first"], ref["first"])
+    bad = [bytearray(b) for b in blobs]
+    bad[3][len(bad[3]) // 2] ^= 0x55
+    with pytest.raises(api.GamsCudaError):
+        api.wave_peaks_gz_batch(ctx, *api.pack_blobs([bytes(b) for b in bad]), off, 100, 10, 50)
+    _, st = api.wave_peaks_gz_batch(ctx, *api.pack_blobs([bytes(b) for b in bad]), off, 100, 10, 50, raise_on_error=False)
+    assert st[3] != 0 and not st[:3].any() and st[4] == 0
+
+
 # --------------------------------------------------------------- rg index build: the hand-written segmented sort (idx_build.cu)
 def test_build_idx_rg_segment_sizes(ctx, orc):
     """Lapper::new on the device for segments of every size class: empty, 1, 2, 3, powers of two and their neighbours, the
