@@ -1210,6 +1210,7 @@ int32_t launch_gunzip2(PerDevice &pd, cudaStream_t st, const uint8_t *d_gz, cons
         // blobs that did not fit their token budget, or whose chain of parts did not close: the one-pass kernel
         if ((rc = launch_gunzip_only(st, d_gz, d_gz_off, n_blob, d_out, d_out_off, d_status, INF_ETOKENS, check_crc ? d_crc : nullptr))) return rc;
     } else {
+        if (n_arrive) CUDA_TRY(cudaStreamWaitEvent(st, arrive_ev[n_arrive - 1], 0));
         if ((rc = launch_gunzip_only(st, d_gz, d_gz_off, n_blob, d_out, d_out_off, d_status, -1, check_crc ? d_crc : nullptr))) return rc;
     }
     if (check_crc) {
