@@ -134,7 +134,56 @@ int32_t SeriesLayout::build(const uint64_t *h_off, int64_t n, cudaStream_t st) {
     return GAMS_CUDA_OK;
 }
 
+// segment tables of series s0 .. s1 - 1 for segments of `seg` values (kept until another range or length is asked for)
+int32_t SeriesLayout::seg_tables(int64_t s0, int64_t s1, int64_t seg, uint64_t lag, cudaStream_t st) const {
+    int32_t rc;
+    if (seg_s0 != s0 || seg_s1 != s1 || seg_len != seg) {
+        h_seg_off.assign((size_t)(s1 - s0) + 1, 0);
+        for (int64_t c = s0; c < s1; ++c) {
+            const uint64_t len = h_off[c + 1] - h_off[c];
+            const uint64_t k = h_seg_off[c - s0] + std::max<uint64_t>((len + (uint64_t)seg - 1) / (uint64_t)seg, 1);
+            if (k > 0x7FFFFFFFull) {
+                set_error("thresholding: too many segments");
+                return GAMS_CUDA_EINVAL;
+            }
+            h_seg_off[c - s0 + 1] = (uint32_t)k;
+        }
+        const size_t need = h_seg_off.size() * sizeof(uint32_t);
+        if (need > seg_off_bytes) {
+            dev_free(cache, d_seg_off, seg_off_bytes);
+            d_seg_off = nullptr, seg_off_bytes = 0;
+            if ((rc = dev_alloc(cache, reinterpret_cast<void **>(&d_seg_off), need))) return rc;
+            seg_off_bytes = need;
+        }
+        CUDA_TRY(cudaMemcpyAsync(d_seg_off, h_seg_off.data(), need, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaStreamSynchronize(st));     // (h_seg_off may be rebuilt by the next call)
+        seg_s0 = s0, seg_s1 = s1, seg_len = seg;
+    }
+    const size_t n_seg = h_seg_off.back();
+    const size_t need_last = std::max<size_t>(n_seg, 1) * sizeof(long long), need_ring = std::max<size_t>(n_seg, 1) * (size_t)(lag + 1) * sizeof(float);
+    if (need_last > seg_last_bytes) {
+        dev_free(cache, d_seg_last, seg_last_bytes);
+        d_seg_last = nullptr, seg_last_bytes = 0;
+        if ((rc = dev_alloc(cache, reinterpret_cast<void **>(&d_seg_last), need_last))) return rc;
+        seg_last_bytes = need_last;
+    }
+    if (need_ring > seg_ring_bytes) {
+        dev_free(cache, d_seg_ring, seg_ring_bytes);
+        d_seg_ring = nullptr, seg_ring_bytes = 0;
+        if ((rc = dev_alloc(cache, reinterpret_cast<void **>(&d_seg_ring), need_ring))) return rc;
+        seg_ring_bytes = need_ring;
+    }
+    return GAMS_CUDA_OK;
+}
+
 void SeriesLayout::release() {
+    dev_free(cache, d_seg_off, seg_off_bytes);
+    dev_free(cache, d_seg_last, seg_last_bytes);
+    dev_free(cache, d_seg_ring, seg_ring_bytes);
+    d_seg_off = nullptr, d_seg_last = nullptr, d_seg_ring = nullptr;
+    seg_off_bytes = seg_last_bytes = seg_ring_bytes = 0;
+    seg_s0 = seg_s1 = -1;
+
     dev_free(cache, d_off, sizeof(uint64_t) * (size_t)(n_series + 1));
     dev_free(cache, d_ztiles, sizeof(TileDesc) * n_ztiles);
     dev_free(cache, d_nonfinite, sizeof(int) * (size_t)std::max<int64_t>(n_series, 1));

@@ -157,6 +157,15 @@ struct SeriesLayout {
     std::vector<uint64_t> h_off;       // n_series+1 (relative to the first series)
     std::vector<uint64_t> h_ztile_off; // n_series+1: first z-score tile of each series
     BlockCache *cache = nullptr;
+    // the segmented walk of influence != 1 (zscore.cu): first segment of each series of the last range asked for, what every
+    // segment's walk left behind (window of its last signal; filtered history of its last lag + 1 windows)
+    mutable std::vector<uint32_t> h_seg_off;
+    mutable uint32_t *d_seg_off = nullptr;
+    mutable long long *d_seg_last = nullptr;
+    mutable float *d_seg_ring = nullptr;
+    mutable size_t seg_off_bytes = 0, seg_last_bytes = 0, seg_ring_bytes = 0;
+    mutable int64_t seg_s0 = -1, seg_s1 = -1, seg_len = 0;
+    int32_t seg_tables(int64_t s0, int64_t s1, int64_t seg, uint64_t lag, cudaStream_t st) const;
     int32_t build(const uint64_t *h_off, int64_t n, cudaStream_t st);
     void release();
 };

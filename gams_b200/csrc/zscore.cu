@@ -491,14 +491,142 @@ zscore_seq_ring_kernel(const float *__restrict__ x_all, const uint64_t *__restri
 //   dirty  - from there on windows are replayed in order with the true filtered history (the ring of the kernel above),
 //            until lag + 1 windows in a row have not signalled.
 // Only the dirty stretches (~40 % of a genome at threshold 3) pay the sequential replay.
+// ---- the walk, cut into SEGMENTS -------------------------------------------------------------------------------------------
+// One warp per series would leave the GPU to the longest series (a chromosome's last ctg is up to twice the others: warps active
+// 44 %).  The walk of a series can be cut wherever the process is CLEAN — no signal among the last lag + 1 windows: the
+// history is plain data there, whatever happened before.  Where that is cannot be known without walking, so it is assumed
+// at every multiple of `seg` windows and checked afterwards:
+//   zscore_seg_walk_kernel  one warp per segment [s, e): the walk above, started clean at s, stopped at e; it leaves the window
+//                           of its last signal and, if that is within lag + 1 windows of e, the filtered history of
+//                           [e - lag - 1, e)
+//   zscore_seg_fix_kernel   one warp per series, boundary by boundary.  Segment 0 started truly clean, so what it left is the
+//                           true state at the first boundary.  If that state is clean the next segment's assumption held and
+//                           its results (and what IT left) are true as well.  If not, the warp takes the true history over
+//                           and replays the windows behind the boundary in order — reading the assumed walk's signals before
+//                           it overwrites them — until the true process AND the assumed one are clean at the same window:
+//                           from there on both see plain data, so the rest of the segment is right as it stands.  A replay
+//                           that reaches the end of its segment simply goes on into the next one.
+// The replays are short (the rest of one dirty stretch per failed boundary), the walk itself runs on 6 - 12 times as many warps.
+constexpr int64_t ZS_NEVER = -(1ll << 40);
+
+// one step of the replay: the next <= 32 windows from i on, evaluated as in zscore_seq_ring_kernel; commits n_commit <= room windows.
+// Returns n_commit; last_sig / spec_last are updated (spec_last from the signals that stood in sg before: track_old).
+template <int P, bool TRACK_OLD>
+__device__ __forceinline__ int zs_replay_step(float *ring, const float *__restrict__ x, int8_t *sg, int64_t n, int64_t i, int64_t &front,
+                                              int64_t room, int64_t L, uint32_t lag32, float flag, float flagm1, float threshold,
+                                              float influence, float one_minus, int lane, int64_t &last_sig, int64_t &spec_last) {
+    for (int64_t pos = front + lane; pos < i + 32 && pos < n; pos += 32) ring[pos & (P - 1)] = x[pos];
+    front = (i + 32 < n) ? i + 32 : n;
+    __syncwarp();
+    const int64_t w = i + lane;
+    const bool active = w < n;
+    int my = 0;
+    float xv = 0.0f;
+    if (active) {
+        xv = ring[w & (P - 1)];
+        const int64_t a = (w - 1 - L > 0) ? (w - 1 - L) : 0;
+        my = ring_decide<P>(ring, a, lag32, flag, flagm1, xv, threshold);
+    }
+    const unsigned ballot = __ballot_sync(0xFFFFFFFFu, my != 0);
+    const int first = ballot ? (__ffs(ballot) - 1) : 32;
+    int n_commit = (first >= 31) ? 32 : first + 2;     // lanes <= first + 1 saw only correctly speculated values
+    if ((int64_t)n_commit > room) n_commit = (int)room;
+    const float prev_x = __shfl_up_sync(0xFFFFFFFFu, xv, 1);
+    float fw = xv;
+    if (lane == first) {
+        const float prev = (lane == 0) ? ring[(i - 1) & (P - 1)] : prev_x;
+        fw = __fadd_rn(__fmul_rn(influence, xv), __fmul_rn(one_minus, prev));
+    }
+    const float f_first = __shfl_sync(0xFFFFFFFFu, fw, first & 31);
+    if (lane == first + 1 && my != 0) fw = __fadd_rn(__fmul_rn(influence, xv), __fmul_rn(one_minus, f_first));
+    if (first < n_commit) {
+        last_sig = i + first;
+        if (first + 1 < n_commit && ((ballot >> (first + 1)) & 1u)) last_sig = i + first + 1;
+    }
+    if (TRACK_OLD) {
+        const unsigned ob = __ballot_sync(0xFFFFFFFFu, lane < n_commit && sg[w] != 0);
+        if (ob) spec_last = i + (31 - __clz(ob));
+    }
+    __syncwarp();
+    if (lane < n_commit) {
+        ring[w & (P - 1)] = fw;
+        sg[w] = (int8_t)my;
+    }
+    __syncwarp();
+    return n_commit;
+}
+
 template <int P>
 __global__ void __launch_bounds__(ZSEQ_WARPS * 32)
-zscore_seq_skip_kernel(const float *__restrict__ x_all, const uint64_t *__restrict__ off, int64_t s_begin, int64_t s_end,
-                       uint64_t lag, float threshold, float influence, int8_t *signal) {
+zscore_seg_walk_kernel(const float *__restrict__ x_all, const uint64_t *__restrict__ off, const uint32_t *__restrict__ seg_off,
+                       int64_t s_begin, int64_t s_end, int64_t seg, uint64_t lag, float threshold, float influence, int8_t *signal,
+                       long long *__restrict__ seg_last, float *__restrict__ seg_ring) {
     __shared__ float ring_all[ZSEQ_WARPS][P];
     const int lane = threadIdx.x & 31;
-    const int64_t c = s_begin + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    if (c >= s_end) return;
+    const int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (g >= (int64_t)seg_off[s_end - s_begin]) return;
+    int64_t lo = 0, hi = s_end - s_begin;            // the series of segment g
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if ((int64_t)seg_off[mid] <= g) lo = mid; else hi = mid;
+    }
+    const int64_t c = s_begin + lo;
+    float *ring = ring_all[threadIdx.x >> 5];
+    const uint64_t base = off[c];
+    const int64_t n = (int64_t)(off[c + 1] - base);
+    const float *x = x_all + base;
+    int8_t *sg = signal + base;
+    const int64_t L = (int64_t)lag;
+    const int64_t s = (g - (int64_t)seg_off[lo]) * seg, e = (s + seg < n) ? s + seg : n;
+    const float flag = __ull2float_rn((unsigned long long)lag);
+    const float flagm1 = __fsub_rn(flag, 1.0f);
+    const float one_minus = __fsub_rn(1.0f, influence);
+    int64_t i = s > L ? s : L;              // next window to decide; windows < L never signal (D1 wrote 0 there)
+    int64_t last_sig = ZS_NEVER, spec_unused = ZS_NEVER;
+    while (i < e) {
+        // ---- clean: the next window whose D1 is a signal
+        int64_t p = -1;
+        while (i < e) {
+            const int64_t w = i + lane;
+            const unsigned b = __ballot_sync(0xFFFFFFFFu, w < e && sg[w] != 0);
+            if (b) { p = i + (__ffs(b) - 1); break; }
+            i += 32;
+        }
+        if (p < 0) break;
+        // window p signals as D1 says; the ring takes the data of [p - L - 1, p) and the filtered value of p
+        {
+            const int64_t a = (p - L - 1 > 0) ? p - L - 1 : 0;
+            for (int64_t q = a + lane; q < p; q += 32) ring[q & (P - 1)] = x[q];
+            if (lane == 0) ring[p & (P - 1)] = __fadd_rn(__fmul_rn(influence, x[p]), __fmul_rn(one_minus, x[p - 1]));
+        }
+        last_sig = p;
+        int64_t front = p + 1;
+        i = p + 1;
+        __syncwarp();
+        // ---- dirty: sequential replay until the stats window of window i is clean again
+        while (i < e && last_sig >= i - 1 - L)
+            i += zs_replay_step<P, false>(ring, x, sg, n, i, front, e - i, L, (uint32_t)lag, flag, flagm1, threshold, influence, one_minus,
+                                          lane, last_sig, spec_unused);
+    }
+    // ---- what the next segment has to know
+    if (lane == 0) seg_last[g] = last_sig;
+    if (e < n && last_sig >= e - 1 - L) {       // (the ring holds the filtered values of [e - L - 1, e): the replay ran up to e)
+        float *dst = seg_ring + (size_t)g * (size_t)(L + 1);
+        for (int64_t j = lane; j <= L; j += 32) dst[j] = ring[(e - L - 1 + j) & (P - 1)];
+    }
+}
+
+template <int P>
+__global__ void __launch_bounds__(ZSEQ_WARPS * 32)
+zscore_seg_fix_kernel(const float *__restrict__ x_all, const uint64_t *__restrict__ off, const uint32_t *__restrict__ seg_off,
+                      int64_t s_begin, int64_t s_end, int64_t seg, uint64_t lag, float threshold, float influence, int8_t *signal,
+                      const long long *__restrict__ seg_last, const float *__restrict__ seg_ring) {
+    __shared__ float ring_all[ZSEQ_WARPS][P];
+    const int lane = threadIdx.x & 31;
+    const int64_t ci = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (ci >= s_end - s_begin) return;
+    const int64_t c = s_begin + ci, g0 = (int64_t)seg_off[ci], n_seg = (int64_t)seg_off[ci + 1] - g0;
+    if (n_seg < 2) return;
     float *ring = ring_all[threadIdx.x >> 5];
     const uint64_t base = off[c];
     const int64_t n = (int64_t)(off[c + 1] - base);
@@ -508,64 +636,29 @@ zscore_seq_skip_kernel(const float *__restrict__ x_all, const uint64_t *__restri
     const float flag = __ull2float_rn((unsigned long long)lag);
     const float flagm1 = __fsub_rn(flag, 1.0f);
     const float one_minus = __fsub_rn(1.0f, influence);
-    int64_t i = L;                          // next window to decide; windows < L never signal (D1 wrote 0 there)
-    while (i < n) {
-        // ---- clean: the next window whose D1 is a signal
-        int64_t p = -1;
-        while (i < n) {
-            const int64_t w = i + lane;
-            const unsigned b = __ballot_sync(0xFFFFFFFFu, w < n && sg[w] != 0);
-            if (b) { p = i + (__ffs(b) - 1); break; }
-            i += 32;
-        }
-        if (p < 0) break;
-        // window p signals as D1 says; the ring takes the data of [p - L - 1, p) and the filtered value of p
+    int64_t k = 1;
+    while (k < n_seg) {
+        const int64_t s = k * seg;
+        int64_t last_sig = seg_last[g0 + k - 1];
+        if (last_sig < s - 1 - L) { ++k; continue; }       // the true process is clean at s: segment k is right as it stands
+        // the true filtered history of [s - L - 1, s)
         {
-            const int64_t a = (p - L - 1 > 0) ? p - L - 1 : 0;
-            for (int64_t e = a + lane; e < p; e += 32) ring[e & (P - 1)] = x[e];
-            if (lane == 0) ring[p & (P - 1)] = __fadd_rn(__fmul_rn(influence, x[p]), __fmul_rn(one_minus, x[p - 1]));
+            const float *src = seg_ring + (size_t)(g0 + k - 1) * (size_t)(L + 1);
+            for (int64_t j = lane; j <= L; j += 32) ring[(s - L - 1 + j) & (P - 1)] = src[j];
         }
-        int64_t last_sig = p, front = p + 1;
-        i = p + 1;
         __syncwarp();
-        // ---- dirty: sequential replay until the stats window of window i is clean again
-        while (i < n && last_sig >= i - 1 - L) {
-            for (int64_t pos = front + lane; pos < i + 32 && pos < n; pos += 32) ring[pos & (P - 1)] = x[pos];
-            front = (i + 32 < n) ? i + 32 : n;
-            __syncwarp();
-            const int64_t w = i + lane;
-            const bool active = w < n;
-            int my = 0;
-            float xv = 0.0f;
-            if (active) {
-                xv = ring[w & (P - 1)];
-                const int64_t a = (w - 1 - L > 0) ? (w - 1 - L) : 0;
-                my = ring_decide<P>(ring, a, (uint32_t)lag, flag, flagm1, xv, threshold);
+        int64_t i = s, front = s, kk = k, seg_end = (s + seg < n) ? s + seg : n, spec_last = ZS_NEVER;
+        while (i < n) {
+            if (i == seg_end) {             // into the next segment with the TRUE state: its walk assumed a clean one
+                ++kk;
+                seg_end = (seg_end + seg < n) ? seg_end + seg : n;
+                spec_last = ZS_NEVER;
             }
-            const unsigned ballot = __ballot_sync(0xFFFFFFFFu, my != 0);
-            const int first = ballot ? (__ffs(ballot) - 1) : 32;
-            int n_commit = (first >= 31) ? 32 : first + 2;     // lanes <= first + 1 saw only correctly speculated values
-            if ((int64_t)n_commit > n - i) n_commit = (int)(n - i);
-            const float prev_x = __shfl_up_sync(0xFFFFFFFFu, xv, 1);
-            float fw = xv;
-            if (lane == first) {
-                const float prev = (lane == 0) ? ring[(i - 1) & (P - 1)] : prev_x;
-                fw = __fadd_rn(__fmul_rn(influence, xv), __fmul_rn(one_minus, prev));
-            }
-            const float f_first = __shfl_sync(0xFFFFFFFFu, fw, first & 31);
-            if (lane == first + 1 && my != 0) fw = __fadd_rn(__fmul_rn(influence, xv), __fmul_rn(one_minus, f_first));
-            if (first < n_commit) {
-                last_sig = i + first;
-                if (first + 1 < n_commit && ((ballot >> (first + 1)) & 1u)) last_sig = i + first + 1;
-            }
-            __syncwarp();
-            if (lane < n_commit) {
-                ring[w & (P - 1)] = fw;
-                sg[w] = (int8_t)my;
-            }
-            __syncwarp();
-            i += n_commit;
+            if (last_sig < i - 1 - L && spec_last < i - 1 - L) break;     // both clean: identical from here on
+            i += zs_replay_step<P, true>(ring, x, sg, n, i, front, seg_end - i, L, (uint32_t)lag, flag, flagm1, threshold, influence,
+                                         one_minus, lane, last_sig, spec_last);
         }
+        k = kk + 1;     // segment kk is right from i on, and so is what its walk left for the boundary behind it
     }
 }
 
@@ -574,12 +667,24 @@ bool zscore_skip_ok(uint64_t lag) { return lag >= 1 && lag + 65 <= 1024; }
 int32_t launch_zscore_skip(const SeriesLayout &L, cudaStream_t st, const float *d_x, uint64_t lag, float threshold, float influence,
                            int8_t *d_signal, uint64_t *launches, int64_t s0, int64_t s1) {
     if (L.n_series == 0 || s1 <= s0) return GAMS_CUDA_OK;
-    const unsigned grid = (unsigned)((s1 - s0 + ZSEQ_WARPS - 1) / ZSEQ_WARPS);
-    if (lag + 65 <= 256)
-        zscore_seq_skip_kernel<256><<<grid, ZSEQ_WARPS * 32, 0, st>>>(d_x, L.d_off, s0, s1, lag, threshold, influence, d_signal);
-    else
-        zscore_seq_skip_kernel<1024><<<grid, ZSEQ_WARPS * 32, 0, st>>>(d_x, L.d_off, s0, s1, lag, threshold, influence, d_signal);
-    if (launches) ++*launches;
+    static const int64_t seg_env = getenv("GAMS_CUDA_ZSEG") ? atoll(getenv("GAMS_CUDA_ZSEG")) : 0;   // (tests: boundaries every few hundred windows)
+    const int64_t seg = std::max<int64_t>(seg_env > 0 ? seg_env : 4096, (int64_t)lag + 34);   // (16384: 8.3 ms, 4096: 7.5, 1024: 7.8 per 3.1e8 windows)
+    int32_t rc;
+    if ((rc = L.seg_tables(s0, s1, seg, lag, st))) return rc;
+    const int64_t n_seg = (int64_t)L.h_seg_off.back();
+    const unsigned grid = (unsigned)((n_seg + ZSEQ_WARPS - 1) / ZSEQ_WARPS), grid2 = (unsigned)((s1 - s0 + ZSEQ_WARPS - 1) / ZSEQ_WARPS);
+    if (lag + 65 <= 256) {
+        zscore_seg_walk_kernel<256><<<grid, ZSEQ_WARPS * 32, 0, st>>>(d_x, L.d_off, L.d_seg_off, s0, s1, seg, lag, threshold, influence, d_signal,
+                                                                     L.d_seg_last, L.d_seg_ring);
+        zscore_seg_fix_kernel<256><<<grid2, ZSEQ_WARPS * 32, 0, st>>>(d_x, L.d_off, L.d_seg_off, s0, s1, seg, lag, threshold, influence, d_signal,
+                                                                     L.d_seg_last, L.d_seg_ring);
+    } else {
+        zscore_seg_walk_kernel<1024><<<grid, ZSEQ_WARPS * 32, 0, st>>>(d_x, L.d_off, L.d_seg_off, s0, s1, seg, lag, threshold, influence, d_signal,
+                                                                      L.d_seg_last, L.d_seg_ring);
+        zscore_seg_fix_kernel<1024><<<grid2, ZSEQ_WARPS * 32, 0, st>>>(d_x, L.d_off, L.d_seg_off, s0, s1, seg, lag, threshold, influence, d_signal,
+                                                                      L.d_seg_last, L.d_seg_ring);
+    }
+    if (launches) *launches += 2;
     CUDA_TRY(cudaGetLastError());
     return GAMS_CUDA_OK;
 }

@@ -175,7 +175,7 @@ def _peaks_properties(ctx, orc, d_seq, seq_off, n_bases):
 
 
 def _influence_properties(ctx, orc, d_seq, seq_off, influence, n_spot):
-    """`wave --influence x` (x != 1) at full size: the walk of zscore_seq_skip_kernel behind the fused kernel.
+    """`wave --influence x` (x != 1) at full size: the segmented walk (zscore_seg_walk_kernel, zscore_seg_fix_kernel) behind the fused kernel.
     (P7) filtered differs from data only AT signals (stat.rs:40-48), so a window whose statistics window [i-1-lag, i-1) holds no
     signal of the result decides exactly as the influence-1 process does: wherever the influence-x result has no signal among
     the lag+1 windows before i, its decision at i equals the influence-1 decision at i — for every window of the genome.
