@@ -35,9 +35,9 @@
 namespace gams {
 
 #ifndef TK_WARPS_N
-#define TK_WARPS_N 12
+#define TK_WARPS_N 11
 #endif
-constexpr int TK_WARPS = TK_WARPS_N;           // warps per CTA, one CTA per SM: 384 parts in flight per SM
+constexpr int TK_WARPS = TK_WARPS_N;           // warps per CTA, one CTA per SM: 352 parts in flight per SM
 constexpr int TK_THREADS = TK_WARPS * 32;
 constexpr int TK_LBITS = 6, TK_DBITS = 7;      // level-1 sequence data: 0.4 % of the literal/length codes and 1.8 % of the distance codes are longer
 constexpr uint32_t TK_RING = 32;               // words of the compressed stream staged ahead in shared memory
@@ -53,8 +53,9 @@ struct TkFast {
     uint32_t pad;
 };
 static_assert(sizeof(TkFast) % 4 == 0 && (sizeof(TkFast) / 4) % 2 == 1, "odd word stride");
-// (and a ring of TK_RING words per thread behind the tables, 16-byte aligned for cp.async)
-constexpr size_t TK_SMEM = (sizeof(TkFast) + 4 * TK_RING) * TK_THREADS;
+// (and, behind the tables, a ring of TK_RING words per thread, 16-byte aligned for cp.async, and TK_STAGE tokens per thread)
+constexpr uint32_t TK_STAGE = 16;
+constexpr size_t TK_SMEM = (sizeof(TkFast) + 4 * TK_RING + 4 * TK_STAGE) * TK_THREADS;
 // per-thread scratch in global memory: what a block header needs while it is parsed, and the canonical decoder of the codes
 // that are longer than a table index
 struct TkSlow {
@@ -91,7 +92,7 @@ struct TkWin {
     const uint8_t *base;             // the blob's first byte rounded down to 16 bytes
     uint32_t n_bytes, n_words;       // from base to the blob's end
     uint32_t wi, mis;                // w0 w1 w2 p0 = words wi - 3 .. wi of base; mis: bytes between base and the blob's first byte
-    uint32_t w0, w1, w2, p0, o;
+    uint32_t w0, w1, w2, p0, p1, o;  // p1: word wi + 1, read from the ring a rotation before it is needed
     uint32_t ring;                   // shared-memory address of the lane's ring; word k of the stream lives in slot k & 31
     uint32_t fetched, landed;        // words < fetched are in the ring or on their way, words < landed have arrived (both multiples of 4)
     __device__ __forceinline__ void set_blob(const uint8_t *in, uint32_t in_len) {
@@ -128,7 +129,7 @@ struct TkWin {
         asm volatile("cp.async.commit_group;" ::: "memory");
         asm volatile("cp.async.wait_group 1;" ::: "memory");
         landed = before;
-        if (active && landed < wi + 16u) {      // (the first group behind a block header: the ring was refilled word by word)
+        if (active && landed < wi + 17u) {      // (the first group behind a block header: the ring was refilled word by word)
             asm volatile("cp.async.wait_group 0;" ::: "memory");
             landed = fetched;
         }
@@ -144,19 +145,19 @@ struct TkWin {
         asm volatile("cp.async.commit_group;" ::: "memory");
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         landed = fetched;
-        w0 = slot(k), w1 = slot(k + 1), w2 = slot(k + 2), p0 = slot(k + 3);
+        w0 = slot(k), w1 = slot(k + 1), w2 = slot(k + 2), p0 = slot(k + 3), p1 = slot(k + 4);
         wi = k + 3;
     }
     __device__ __forceinline__ void seek(uint32_t byte) { seek_bit(8ull * byte); }
     __device__ __forceinline__ uint32_t peek() const { return __funnelshift_r(w0, w1, o); }      // bits 0..31 from the position
     __device__ __forceinline__ uint32_t peek_hi() const { return __funnelshift_r(w1, w2, o); }   // bits 32..63
     __device__ __forceinline__ void rotate_fast() {
-        w0 = w1, w1 = w2, w2 = p0;
+        w0 = w1, w1 = w2, w2 = p0, p0 = p1;
         ++wi;
-        p0 = slot(wi);
+        p1 = slot(wi + 1);
     }
     __device__ __forceinline__ void rotate() {
-        if (wi + 1u >= landed) {
+        if (wi + 2u >= landed) {
             fill();
             asm volatile("cp.async.commit_group;" ::: "memory");
             asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -620,7 +621,10 @@ inflate_split_kernel(const uint8_t *__restrict__ gz, const uint64_t *__restrict_
 }
 
 enum { TS_HEADER = 0, TS_SYMBOLS = 1, TS_DONE = 2, TS_FINISHED = 3, TS_FETCH = 4 };
-constexpr int TK_GROUP = 8;
+#ifndef TK_GROUP_N
+#define TK_GROUP_N 8
+#endif
+constexpr int TK_GROUP = TK_GROUP_N;
 #ifndef TK_UNROLL_N
 #define TK_UNROLL_N 8
 #endif
@@ -663,12 +667,30 @@ inflate_tokens_kernel(const uint8_t *__restrict__ gz, const uint64_t *__restrict
     PartRec *R = rec;
     uint32_t next_start = TK_NONE, my_start = 0, cap = 0, in_len = 0, tcap = 0, tok_off = 0;
     uint32_t *tok = tokens;
-    uint32_t r_isize = 0, r_crc = 0, r_final = 0, pos = 0, nt = 0;
+    uint32_t r_isize = 0, r_crc = 0, r_final = 0, pos = 0, nt = 0, flushed = 0;
+    // Tokens are staged in shared memory, 16 per lane, and leave as whole sectors: 8 tokens = 32 bytes, two 128-bit stores
+    // per lane.  (One 4-byte store per token from 32 lanes into 32 different lines held the memory pipe for 32 cycles per
+    // symbol: the kernel took 12.7 ms with those stores and 6.4 ms without any.)  Token regions start and end at multiples
+    // of 8 tokens, so the last sector of a part may carry up to 7 slots of padding.
+    const uint32_t stage = (uint32_t)__cvta_generic_to_shared(tk_smem + (sizeof(TkFast) + 4 * TK_RING) * TK_THREADS + 4 * TK_STAGE * threadIdx.x);
+    auto put = [&](uint32_t t) {
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(stage + 4u * (nt & (TK_STAGE - 1u))), "r"(t) : "memory");
+        ++nt;
+    };
+    auto flush8 = [&]() {        // tokens flushed .. flushed + 7
+        uint4 a, b;
+        const uint32_t at = stage + 4u * (flushed & (TK_STAGE - 1u));
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "r"(at) : "memory");
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "r"(at + 16u) : "memory");
+        uint4 *dst = reinterpret_cast<uint4 *>(tok + flushed);
+        dst[0] = a, dst[1] = b;
+        flushed += 8u;
+    };
     int err = INF_OK, nlen = 288, ndist = 30;
     bool last = false;
     TkWin br;
     br.base = gz, br.n_bytes = 0, br.n_words = 0, br.mis = 0;
-    br.w0 = br.w1 = br.w2 = br.p0 = 0, br.o = 0, br.wi = 3, br.fetched = br.landed = 0;
+    br.w0 = br.w1 = br.w2 = br.p0 = br.p1 = 0, br.o = 0, br.wi = 3, br.fetched = br.landed = 0;
     br.ring = (uint32_t)__cvta_generic_to_shared(tk_smem + sizeof(TkFast) * TK_THREADS + 4 * TK_RING * threadIdx.x);
     uint32_t lfc[15 - TK_LBITS], dfc[15 - TK_DBITS], lc15 = 0, dc15 = 0;      // the codes that are longer than a table index (tk_decode_long)
 #pragma unroll
@@ -718,9 +740,9 @@ inflate_tokens_kernel(const uint8_t *__restrict__ gz, const uint64_t *__restrict
             }
             tok = tokens + tb + tok_off;
             r_isize = r_crc = r_final = 0;
-            pos = nt = 0;
+            pos = nt = flushed = 0;
             last = false;
-            if (err) br.w0 = br.w1 = br.w2 = br.p0 = 0, br.o = 0, br.wi = 3, br.mis = 0;
+            if (err) br.w0 = br.w1 = br.w2 = br.p0 = br.p1 = 0, br.o = 0, br.wi = 3, br.mis = 0;
             else br.seek_bit(my_start);
             state = err ? TS_FINISHED : TS_HEADER;
             return;
@@ -743,6 +765,7 @@ inflate_tokens_kernel(const uint8_t *__restrict__ gz, const uint64_t *__restrict
         if (__any_sync(0xFFFFFFFFu, state == TS_FINISHED || state == TS_FETCH)) {
             while (state == TS_FINISHED || state == TS_FETCH) {
                 if (state == TS_FINISHED) {
+                    while (flushed < nt) flush8();
                     PartRec r;
                     r.start_bit = my_start, r.end_bit = (uint32_t)br.consumed_bits(), r.n_tok = nt, r.out_len = pos;
                     r.status = err | (r_final ? TK_FINAL : 0);
@@ -774,7 +797,10 @@ inflate_tokens_kernel(const uint8_t *__restrict__ gz, const uint64_t *__restrict
                     else if ((uint64_t)pos + len > cap) err = INF_EOVERFLOW;
                     else if ((uint64_t)nt + len > tcap) err = INF_ETOKENS;   // (stored data is not what this decoder is for)
                     else {
-                        for (uint32_t i = 0; i < len; ++i) tok[nt++] = (uint32_t)in[src + i] << 9;
+                        for (uint32_t i = 0; i < len; ++i) {
+                            put((uint32_t)in[src + i] << 9);
+                            if ((int32_t)(nt - flushed) >= 8) flush8();
+                        }
                         pos += len;
                         br.seek(src + len);
                     }
@@ -848,7 +874,7 @@ inflate_tokens_kernel(const uint8_t *__restrict__ gz, const uint64_t *__restrict
                 const bool commit = act && n1 != 0u && !(is_len && n2 == 0u);
                 br.drop_fast(commit ? n1 + (is_len ? n2 : 0u) : 0u);
                 if (commit) {
-                    tok[nt++] = is_len ? ((dist << 9) | len) : (v << 9);
+                    put(is_len ? ((dist << 9) | len) : (v << 9));
                     pos += is_len ? len : 1u;
                 }
                 act = commit;
@@ -899,7 +925,7 @@ inflate_tokens_kernel(const uint8_t *__restrict__ gz, const uint64_t *__restrict
                     else if (!err) {      // (nt <= tcap + TK_GROUP - 1 here, and the part's room is tcap + 8)
                         if (nt >= tcap + 8u) err = INF_ETOKENS;
                         else {
-                            tok[nt++] = is_lit ? sym << 9 : ((dist << 9) | len);
+                            put(is_lit ? sym << 9 : ((dist << 9) | len));
                             pos += is_lit ? 1u : len;
                         }
                     }
@@ -907,6 +933,10 @@ inflate_tokens_kernel(const uint8_t *__restrict__ gz, const uint64_t *__restrict
                 }
                 __syncwarp();
             }
+            // ---- full sectors of tokens leave (all lanes together; a group and its careful symbol add 9 tokens at most)
+#pragma unroll
+            for (int q = 0; q < 2; ++q)
+                if ((int32_t)(nt - flushed) >= 8) flush8();
             if (eobf && state == TS_SYMBOLS) {       // end of block
                 if (!last) state = TS_HEADER;
                 else if (pos > cap) err = INF_ETOKENS, state = TS_FINISHED;

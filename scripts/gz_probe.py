@@ -31,15 +31,17 @@ d_st = torch.zeros(n_ctg, dtype=torch.int32, device=dev)
 stream = torch.cuda.current_stream().cuda_stream
 def run():
     api.check(L.gams_cuda_gunzip_dev(ctx.handle, 0, stream, n_ctg, d_gz.data_ptr(), d_goff.data_ptr(), d_out.data_ptr(), d_ooff.data_ptr(), d_st.data_ptr()))
+import os
+NOCHECK = bool(os.environ.get("GAMS_GZ_PROBE_NOCHECK"))     # timing experiments with kernels that are wrong on purpose
 run(); torch.cuda.synchronize()
-assert int(d_st.abs().sum()) == 0 and torch.equal(d_out[:n], d_seq[:n])
+assert NOCHECK or (int(d_st.abs().sum()) == 0 and torch.equal(d_out[:n], d_seq[:n]))
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 for dec, crc in ((0, True), (0, False), (1, False)):
     ctx.set_gunzip_options(dec, crc)
     run(); torch.cuda.synchronize()
-    assert int(d_st.abs().sum()) == 0 and torch.equal(d_out[:n], d_seq[:n])
+    assert NOCHECK or (int(d_st.abs().sum()) == 0 and torch.equal(d_out[:n], d_seq[:n]))
     e0.record()
     for _ in range(3): run()
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 3
-    print(f"gunzip_dev decoder {dec} crc {crc}: {ms:.2f} ms per {n / 1e9:.2f} Gbp = {n / ms / 1e6:.1f} Gbp/s out, {cat.size / ms / 1e6:.1f} GB/s in; bit-exact")
+    print(f"gunzip_dev decoder {dec} crc {crc}: {ms:.2f} ms per {n / 1e9:.2f} Gbp = {n / ms / 1e6:.1f} Gbp/s out, {cat.size / ms / 1e6:.1f} GB/s in; {"NOT CHECKED" if NOCHECK else "bit-exact"}")
