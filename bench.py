@@ -706,12 +706,14 @@ def bench_gunzip(args, ctx, L, dev, gz_host, seq_off, d_seq, n_bases):
         res[name] = {"ms_per_step": ms, "value": n_bases / (ms * 1e-3) / 1e9, "bit_exact": ok}
     ctx.set_gunzip_options(0, True)
     main = res["two_phase_crc"]
-    return {"what": "gunzip of the seq:{ctg} blobs on the device (gams_cuda_gunzip_dev), blobs and output in HBM; default decoder: tokens "
-                    "(one thread per part) -> bytes (one warp per blob) -> CRC-32",
+    return {"what": "gunzip of the seq:{ctg} blobs on the device (gams_cuda_gunzip_dev), blobs and output in HBM; default decoder: block headers "
+                    "found by a speculative search (one warp per group of 8 KB ranges) -> tokens (one thread per deflate block, verified "
+                    "hand-over from block to block) -> bytes (one warp per blob) -> CRC-32",
             "value": main["value"], "unit": "Gbp/s", "ms_per_step": main["ms_per_step"], "blobs": int(n_ctg),
             "compressed_bytes": int(n_gz), "ratio": n_bases / n_gz, "bit_exact": all(r["bit_exact"] for r in res.values()),
             "decoders": res,
-            "bound": "latency of the serial chain of one deflate symbol (index -> table load -> shift); the longest blob sets the time",
+            "bound": "tokens: latency of the serial chain of one deflate symbol (index -> table load -> shift) over the longest block; bytes: "
+                     "instruction issue (~96 warp instructions per 32 output bytes) and the serial chain of the longest blob",
             "cpu_baseline": {"value": cpu_rate, "unit": "Gbp/s", "cores": 1, "kind": "zlib",
                              "sample": f"zlib.decompress of the first {k} blobs, one thread"}}
 
