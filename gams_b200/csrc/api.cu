@@ -225,11 +225,12 @@ using namespace gams;
 
 // GAMS_CUDA_TRACE=1: host-clock stage timings of the host API on stderr (synchronises; for debugging only)
 #include <chrono>
-static bool trace_on() {
+namespace gams {
+bool trace_on() {
     static const bool on = getenv("GAMS_CUDA_TRACE") != nullptr;
     return on;
 }
-static void trace_stage(const char *what, cudaStream_t st = nullptr, bool sync = false) {
+void trace_stage(const char *what, cudaStream_t st, bool sync) {
     if (!trace_on()) return;
     static thread_local auto last = std::chrono::steady_clock::now();
     if (sync) cudaStreamSynchronize(st);
@@ -237,6 +238,7 @@ static void trace_stage(const char *what, cudaStream_t st = nullptr, bool sync =
     fprintf(stderr, "[gams_cuda] %-28s +%8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - last).count());
     last = now;
 }
+}  // namespace gams
 
 // ================================================================================ lifecycle =====
 GAMS_API int32_t gams_cuda_version(void) { return 100; /* 0.1.0 */ }
@@ -292,6 +294,7 @@ GAMS_API int32_t gams_cuda_create(const int32_t *device_ids, int32_t n_dev, gams
         CUDA_TRY(cudaStreamCreateWithFlags(&pd.stream, cudaStreamNonBlocking));
         CUDA_TRY(cudaStreamCreateWithFlags(&pd.copy_in, cudaStreamNonBlocking));
         CUDA_TRY(cudaStreamCreateWithFlags(&pd.copy_out, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&pd.aux, cudaStreamNonBlocking));
         CUDA_TRY(cudaMalloc(&pd.d_zstats, 2 * sizeof(unsigned long long)));
         CUDA_TRY(cudaMemset(pd.d_zstats, 0, 2 * sizeof(unsigned long long)));
         return GAMS_CUDA_OK;
@@ -354,6 +357,7 @@ GAMS_API void gams_cuda_destroy(gams_cuda_ctx *ctx) {
         if (pd.stream) cudaStreamDestroy(pd.stream);       // (a context whose creation failed half way has NULL handles)
         if (pd.copy_in) cudaStreamDestroy(pd.copy_in);
         if (pd.copy_out) cudaStreamDestroy(pd.copy_out);
+        if (pd.aux) cudaStreamDestroy(pd.aux);
     }
     delete ctx;
 }
@@ -636,13 +640,16 @@ static int32_t wave_on_device(gams_cuda_ctx *ctx, int d, int64_t c0, int64_t c1,
     }
     struct EvGuard {
         std::vector<cudaEvent_t> &a, &b;
-        cudaStream_t in;
+        cudaStream_t in, aux;
+        cudaEvent_t gz_done = nullptr;
         ~EvGuard() {
             cudaStreamSynchronize(in);   // an early error return must not leave copies from the caller's buffer in flight
+            cudaStreamSynchronize(aux);  // ... nor the decoder writing the caller's status array
             for (auto e : a) cudaEventDestroy(e);
             for (auto e : b) cudaEventDestroy(e);
+            if (gz_done) cudaEventDestroy(gz_done);
         }
-    } ev_guard{ev_in, ev_k, pd.copy_in};
+    } ev_guard{ev_in, ev_k, pd.copy_in, pd.aux};
     const uint8_t *h_seq = gzs ? nullptr : seq_concat + base0;
     // gz source: the compressed bytes go up instead (a third of the bases), in the same slices of ctgs; they are inflated on
     // the device once all of them have arrived (the decoder wants the whole batch: its time is the serial chain of the longest
@@ -665,11 +672,42 @@ static int32_t wave_on_device(gams_cuda_ctx *ctx, int d, int64_t c0, int64_t c1,
         CUDA_TRY(cudaEventRecord(ev_in[k], pd.copy_in));
         return GAMS_CUDA_OK;
     };
-    // ~10 ms of link time up front (the plan's own table uploads must not queue behind the whole genome)
-    const size_t n_pre = std::min<size_t>(n_sl, 8);
+    // ~10 ms of link time up front (the plan's own table uploads must not queue behind the whole genome); compressed blobs
+    // are a third of that and go up at once
+    const size_t n_pre = gzs ? n_sl : std::min<size_t>(n_sl, 8);
     for (size_t k = 0; k < n_pre; ++k)
         if ((rc = enqueue_h2d(k))) return rc;
     trace_stage("wave: H2D enqueued");
+    std::vector<uint64_t> gz_rel, seq_rel;
+    if (gzs) {
+        // The decoder starts NOW, on its own stream, before the plan is built (8 ms of host work): its header search follows the
+        // upload in (up to) four stretches, and the token and byte phases run as soon as the last blob has arrived.
+        // Offsets of the blobs / ctgs relative to this device's buffers first.
+        gz_rel.resize((size_t)n + 1), seq_rel.resize((size_t)n + 1);
+        for (int64_t c = 0; c <= n; ++c) {
+            gz_rel[c] = gzs->gz_off[c0 + c] - gz_base;
+            seq_rel[c] = seq_off[c0 + c] - base0;
+        }
+        uint8_t *meta = d_gz + ((gz_bytes + 63) & ~63ull);
+        uint64_t *d_goff = reinterpret_cast<uint64_t *>(meta), *d_ooff = d_goff + (n + 1);
+        int32_t *d_status = reinterpret_cast<int32_t *>(d_ooff + (n + 1));
+        CUDA_TRY(cudaMemcpyAsync(d_goff, gz_rel.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, pd.aux));
+        CUDA_TRY(cudaMemcpyAsync(d_ooff, seq_rel.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, pd.aux));
+        std::vector<int64_t> arrive_end;
+        std::vector<cudaEvent_t> arrive_ev;
+        for (size_t q = 1; q <= 4 && n_sl; ++q) {
+            const size_t k = n_sl * q / 4;
+            if (k == 0 || (!arrive_end.empty() && cut[k] == arrive_end.back())) continue;
+            arrive_end.push_back(cut[k]), arrive_ev.push_back(ev_in[k - 1]);
+        }
+        if ((rc = launch_gunzip2(pd, pd.aux, d_gz, d_goff, n, d_seq, d_ooff, d_status, nb, ctx->gunzip_mode, ctx->gunzip_crc != 0,
+                                 (int)arrive_end.size(), arrive_end.data(), arrive_ev.data())))
+            return rc;
+        // (the status codes are fetched at the end: a copy into pageable host memory blocks the host until the decoder is through)
+        CUDA_TRY(cudaEventCreateWithFlags(&ev_guard.gz_done, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventRecord(ev_guard.gz_done, pd.aux));
+        trace_stage("wave: gunzip enqueued");
+    }
     // 2. the plan
     gams_cuda_wave_plan *plan = nullptr;
     rc = gams_cuda_wave_plan_create(ctx, d, c1 - c0, seq_off + c0, size, step, lag, &plan);
@@ -707,33 +745,7 @@ static int32_t wave_on_device(gams_cuda_ctx *ctx, int d, int64_t c0, int64_t c1,
     for (size_t k = n_pre; k < n_sl; ++k)
         if ((rc = enqueue_h2d(k))) return rc;
     trace_stage("wave: reserve");
-    std::vector<uint64_t> gz_rel, seq_rel;
-    if (gzs) {
-        // offsets of the blobs / ctgs relative to this device's buffers, then the decoder behind the last slice of the upload
-        gz_rel.resize((size_t)n + 1), seq_rel.resize((size_t)n + 1);
-        for (int64_t c = 0; c <= n; ++c) {
-            gz_rel[c] = gzs->gz_off[c0 + c] - gz_base;
-            seq_rel[c] = seq_off[c0 + c] - base0;
-        }
-        uint8_t *meta = d_gz + ((gz_bytes + 63) & ~63ull);
-        uint64_t *d_goff = reinterpret_cast<uint64_t *>(meta), *d_ooff = d_goff + (n + 1);
-        int32_t *d_status = reinterpret_cast<int32_t *>(d_ooff + (n + 1));
-        CUDA_TRY(cudaMemcpyAsync(d_goff, gz_rel.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, pd.stream));
-        CUDA_TRY(cudaMemcpyAsync(d_ooff, seq_rel.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, pd.stream));
-        // the decoder's header search follows the upload in (up to) four stretches; the last event is the whole batch
-        std::vector<int64_t> arrive_end;
-        std::vector<cudaEvent_t> arrive_ev;
-        for (size_t q = 1; q <= 4 && n_sl; ++q) {
-            const size_t k = n_sl * q / 4;
-            if (k == 0 || (!arrive_end.empty() && cut[k] == arrive_end.back())) continue;
-            arrive_end.push_back(cut[k]), arrive_ev.push_back(ev_in[k - 1]);
-        }
-        if ((rc = launch_gunzip2(pd, pd.stream, d_gz, d_goff, n, d_seq, d_ooff, d_status, nb, ctx->gunzip_mode, ctx->gunzip_crc != 0,
-                                 (int)arrive_end.size(), arrive_end.data(), arrive_ev.data())))
-            return rc;
-        CUDA_TRY(cudaMemcpyAsync(gzs->status + c0, d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, pd.stream));
-        trace_stage("wave: gunzip", pd.stream, true);
-    }
+    if (gzs) CUDA_TRY(cudaStreamWaitEvent(pd.stream, ev_guard.gz_done, 0));     // the bases are there once the decoder is through
     // The sequential z-score kernel (influence != 1: one warp per ctg) needs thousands of ctgs in flight to hide its
     // latency; on a 64 MB slice (~130 ctgs) it takes as long as on a quarter of a genome.  So it runs once per GROUP of
     // slices (four groups: the first three overlap the upload of the next), 321 -> ~90 ms per 3.1 Gbp end to end.
@@ -825,6 +837,11 @@ static int32_t wave_on_device(gams_cuda_ctx *ctx, int d, int64_t c0, int64_t c1,
         }
     }
     CUDA_TRY(cudaStreamSynchronize(pd.copy_out));
+    if (gzs) {
+        const int32_t *d_status = reinterpret_cast<const int32_t *>(reinterpret_cast<const uint64_t *>(d_gz + ((gz_bytes + 63) & ~63ull)) + 2 * (n + 1));
+        CUDA_TRY(cudaMemcpyAsync(gzs->status + c0, d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, pd.aux));
+        CUDA_TRY(cudaStreamSynchronize(pd.aux));
+    }
     trace_stage("wave: sync copy_out");
     CUDA_TRY(cudaStreamSynchronize(pd.stream));
     trace_stage("wave: all streams idle");

@@ -174,6 +174,7 @@ struct PerDevice {
     int device = -1;
     cudaStream_t stream = nullptr;   // library-owned stream for the host API
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    cudaStream_t aux = nullptr;      // the decoder of the chained gzip path (runs beside the plan build)
     DevBuf scratch[8];
     unsigned long long *d_zstats = nullptr;  // [0] windows replayed after an inconclusive certificate, [1] verify mismatches
     BlockCache *cache = nullptr;             // owned by the context
@@ -290,6 +291,9 @@ int32_t launch_gc_wave_fused(gams_cuda_wave_plan *p, cudaStream_t st, const uint
 void fused_tiles_for_ctg(std::vector<FusedTile> &out, uint64_t seq_off, uint64_t win_off, uint64_t n_c, int32_t step,
                          uint64_t lag, int wt);
 bool wave_fused_ok(const gams_cuda_wave_plan *p, float threshold, float influence);
+// GAMS_CUDA_TRACE=1: host-clock stage timings on stderr (sync: after synchronising st; for debugging only)
+bool trace_on();
+void trace_stage(const char *what, cudaStream_t st = nullptr, bool sync = false);
 bool zscore_skip_ok(uint64_t lag);
 int32_t launch_zscore_skip(const SeriesLayout &L, cudaStream_t st, const float *d_x, uint64_t lag, float threshold, float influence,
                            int8_t *d_signal, uint64_t *launches, int64_t s0, int64_t s1);

@@ -1232,11 +1232,14 @@ int32_t launch_gunzip2(PerDevice &pd, cudaStream_t st, const uint8_t *d_gz, cons
             inflate_split_kernel<<<s_blocks, SP_WARPS * 32, 0, st>>>(d_gz, d_gz_off, n_blob, d_parts, d_groups, d_rec, b0, b1);
             b0 = b1;
         }
+        trace_stage("gunzip: header search", st, true);
         CUDA_TRY(cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), st));
         const unsigned t_blocks = (unsigned)std::min<uint64_t>((p_cap + TK_THREADS - 1) / TK_THREADS, (uint64_t)n_sm);
         inflate_tokens_kernel<<<t_blocks, TK_THREADS, smem, st>>>(d_gz, d_gz_off, n_blob, d_out_off, d_parts, d_tok, d_rec, d_slow, d_counter);
+        trace_stage("gunzip: tokens", st, true);
         inflate_resolve_kernel<<<(unsigned)((n_blob + RS_WARPS - 1) / RS_WARPS), RS_WARPS * 32, 0, st>>>(d_gz_off, n_blob, d_out, d_out_off, d_parts,
                                                                                                      d_tok, d_rec, d_status, check_crc ? d_crc : nullptr);
+        trace_stage("gunzip: bytes", st, true);
         // blobs that did not fit their token budget, or whose chain of parts did not close: the one-pass kernel
         if ((rc = launch_gunzip_only(st, d_gz, d_gz_off, n_blob, d_out, d_out_off, d_status, INF_ETOKENS, check_crc ? d_crc : nullptr))) return rc;
     } else {
