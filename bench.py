@@ -566,7 +566,9 @@ def main():
 
         # the same through gams_cuda_wave_peaks_batch: what `gams wave` prints (merged peaks), so only the peak records come back
         cap = max(4096, n_win // 16)
-        pk = [np.empty(cap, dtype=dt) for dt in (np.uint32, np.uint32, np.uint32, np.float32, np.int8)]
+        pk_dt = (np.uint32, np.uint32, np.uint32, np.float32, np.int8)
+        pk_ptr = [pinned(cap * np.dtype(dt).itemsize, L) for dt in pk_dt]          # pinned, like the sequence and the window arrays
+        pk = [as_np(p_, cap, dt) for p_, dt in zip(pk_ptr, pk_dt)]
         n_pk = C.c_uint64()
 
         def peaks_step():
@@ -585,7 +587,8 @@ def main():
                              "peak_records": int(n_pk.value), "api": "gams_cuda_wave_peaks_batch (host pointers, pinned; merge_ints on the device)"}
         if gz_host is not None:
             # ... and fed with the gzip blobs: `gams wave` between its GET and its print (get_seq + proc_ctg + merge_ints)
-            pk2 = [np.empty(cap, dtype=dt) for dt in (np.uint32, np.uint32, np.uint32, np.float32, np.int8)]
+            pk2_ptr = [pinned(cap * np.dtype(dt).itemsize, L) for dt in pk_dt]
+            pk2 = [as_np(p_, cap, dt) for p_, dt in zip(pk2_ptr, pk_dt)]
             n_pk2 = C.c_uint64()
             st_gz2 = np.zeros(n_ctg, dtype=np.int32)
             vp = lambda a: a.ctypes.data_as(C.c_void_p)
@@ -608,6 +611,10 @@ def main():
                                     "peak_records": int(n_pk2.value), "equals_peaks_from_bases": same_pk,
                                     "api": "gams_cuda_wave_peaks_gz_batch (gzip blobs in pinned host memory -> device gunzip incl. CRC-32 -> "
                                            "fused GC-wave -> merge_ints on the device; peak records out)"}
+            for p_ in pk2_ptr:
+                L.gams_cuda_host_free(p_)
+        for p_ in pk_ptr:
+            L.gams_cuda_host_free(p_)
 
     # ---- feed step (a18): the seq:{ctg} blobs as Redis holds them (gzip, level 1) inflated on the device ------------
     feed = None
