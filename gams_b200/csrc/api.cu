@@ -700,12 +700,12 @@ static int32_t wave_on_device(gams_cuda_ctx *ctx, int d, int64_t c0, int64_t c1,
             if (k == 0 || (!arrive_end.empty() && cut[k] == arrive_end.back())) continue;
             arrive_end.push_back(cut[k]), arrive_ev.push_back(ev_in[k - 1]);
         }
-        if ((rc = launch_gunzip2(pd, pd.aux, d_gz, d_goff, n, d_seq, d_ooff, d_status, nb, ctx->gunzip_mode, ctx->gunzip_crc != 0,
-                                 (int)arrive_end.size(), arrive_end.data(), arrive_ev.data())))
-            return rc;
-        // (the status codes are fetched at the end: a copy into pageable host memory blocks the host until the decoder is through)
+        // gz_done fires when the bases are final: the GC-wave kernels run beside the CRC-32 pass, which only sets status codes
+        // (fetched at the end: a copy into pageable host memory blocks the host until the decoder is through)
         CUDA_TRY(cudaEventCreateWithFlags(&ev_guard.gz_done, cudaEventDisableTiming));
-        CUDA_TRY(cudaEventRecord(ev_guard.gz_done, pd.aux));
+        if ((rc = launch_gunzip2(pd, pd.aux, d_gz, d_goff, n, d_seq, d_ooff, d_status, nb, ctx->gunzip_mode, ctx->gunzip_crc != 0,
+                                 (int)arrive_end.size(), arrive_end.data(), arrive_ev.data(), ev_guard.gz_done)))
+            return rc;
         trace_stage("wave: gunzip enqueued");
     }
     // 2. the plan

@@ -171,8 +171,7 @@ struct TkWin {
         if (o >= 32u) { rotate(); o -= 32u; }
     }
     __device__ __forceinline__ void drop_fast(uint32_t n) {   // inside a group of symbols, after top_up()
-        o += n;
-        if (o >= 32u) { rotate_fast(); o -= 32u; }
+        o += n;                                               // n <= 31: a table symbol is 11 bits at most, a table distance 20
         if (o >= 32u) { rotate_fast(); o -= 32u; }
     }
     __device__ __forceinline__ uint32_t bits(uint32_t n) { const uint32_t v = peek() & ((1u << n) - 1u); drop(n); return v; }   // n < 32
@@ -1187,7 +1186,7 @@ crc32_fold_kernel(const uint64_t *__restrict__ out_off, int64_t n_blob, const ui
 
 int32_t launch_gunzip2(PerDevice &pd, cudaStream_t st, const uint8_t *d_gz, const uint64_t *d_gz_off, int64_t n_blob, uint8_t *d_out,
                        const uint64_t *d_out_off, int32_t *d_status, uint64_t total_out, int decoder, bool check_crc, int n_arrive,
-                       const int64_t *arrive_end, const cudaEvent_t *arrive_ev) {
+                       const int64_t *arrive_end, const cudaEvent_t *arrive_ev, cudaEvent_t decoded_ev) {
     if (n_blob == 0) return GAMS_CUDA_OK;
     if (n_blob >= (1ll << 30)) {
         set_error("gunzip: too many blobs for one launch");
@@ -1246,6 +1245,7 @@ int32_t launch_gunzip2(PerDevice &pd, cudaStream_t st, const uint8_t *d_gz, cons
         if (n_arrive) CUDA_TRY(cudaStreamWaitEvent(st, arrive_ev[n_arrive - 1], 0));
         if ((rc = launch_gunzip_only(st, d_gz, d_gz_off, n_blob, d_out, d_out_off, d_status, -1, check_crc ? d_crc : nullptr))) return rc;
     }
+    if (decoded_ev) CUDA_TRY(cudaEventRecord(decoded_ev, st));     // the bytes are final; what follows only reads them
     if (check_crc) {
         crc32_piece_offsets_kernel<<<1, 1024, 0, st>>>(d_out_off, n_blob, d_poff);
         const unsigned pb = (unsigned)std::min<uint64_t>((n_piece_max + 255) / 256, 148ull * 16);

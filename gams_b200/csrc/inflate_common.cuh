@@ -16,8 +16,9 @@ int32_t launch_gunzip_only(cudaStream_t st, const uint8_t *d_gz, const uint64_t 
 // then the CRC-32 pass when asked for.  Scratch comes from pd.scratch[7]
 int32_t launch_gunzip2(PerDevice &pd, cudaStream_t st, const uint8_t *d_gz, const uint64_t *d_gz_off, int64_t n_blob, uint8_t *d_out,
                        const uint64_t *d_out_off, int32_t *d_status, uint64_t total_out, int decoder, bool check_crc, int n_arrive = 0,
-                       const int64_t *arrive_end = nullptr, const cudaEvent_t *arrive_ev = nullptr);
+                       const int64_t *arrive_end = nullptr, const cudaEvent_t *arrive_ev = nullptr, cudaEvent_t decoded_ev = nullptr);
 // n_arrive > 0: the blobs are still being uploaded; arrive_ev[i] fires once blobs < arrive_end[i] (rising) are on the device, and
 // the caller has NOT made `st` wait for the upload.  The header search follows the upload stretch by stretch.
+// decoded_ev: recorded on `st` once the output bytes are final, before the CRC-32 pass (which only reads them and sets status codes).
 
 }  // namespace gams

@@ -1,8 +1,10 @@
-"""Small calls through the round-2 kernels (part-parallel gunzip, chained gzip paths, segmented influence walk) for compute-sanitizer:
-`PYTHONPATH=. compute-sanitizer --tool memcheck python scripts/sanitize_gz.py` (also --tool racecheck / initcheck is too slow).  Results are
-checked against zlib and the oracle as well."""
+"""Small calls through the round-2 kernels (part-parallel gunzip, chained gzip paths, segmented influence walk), checked against zlib and
+the oracle: `python scripts/sanitize_gz.py` (written for `compute-sanitizer --tool memcheck`, which this pool no longer runs)."""
 import os
+import sys
 import zlib
+
+sys.path.insert(0, str(__import__("pathlib").Path(__file__).resolve().parent.parent))
 
 import numpy as np
 
