@@ -420,6 +420,20 @@ def test_gunzip_parts_at_irregular_block_boundaries(ctx, orc):
     ctx.set_gunzip_options(0, True)
 
 
+@pytest.mark.parametrize("mem", [1, 3, 6, 9])
+def test_gunzip_block_sizes_of_other_encoders(ctx, orc, mem):
+    """Deflate blocks of 128 symbols (memLevel 1: a header every ~170 compressed bytes, dozens per search range) up to 32 768
+    symbols (memLevel 9: twice zlib's default, a header every ~44 KB): the header search learns the block size from the stream,
+    whatever the encoder's buffer was.  flate2's miniz_oxide cuts at ~20 000 symbols; zlib's default (memLevel 8) is 16 383."""
+    rng = np.random.default_rng(100 + mem)
+    dna = synth.genome(2_000_000, seed=101).tobytes()
+    plain = [dna[:1_000_000], dna[1_000_000:1_300_000], dna[1_300_000:1_300_700], dna[1_400_000:2_000_000]]
+    blobs = [_gzb(p, level=1, mem=mem) for p in plain]
+    out, off, st = api.gunzip_batch(ctx, *api.pack_blobs(blobs))
+    assert not st.any(), st
+    assert out.tobytes() == b"".join(plain)
+
+
 def test_gunzip_one_huge_blob_and_many_tiny(ctx, orc):
     """Batches at the two ends of the part table: one 12 Mbp member alone (hundreds of ranges, several groups of the header
     search), and 3000 members of 0..300 bases (one range each)."""
