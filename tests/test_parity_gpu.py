@@ -952,6 +952,21 @@ def test_multi_device_new_host_paths(orc):
         for k in ("iv_start", "iv_stop", "starts", "stops", "max_len", "blob"):
             _eq(f"multi-device index {k}", m[k], s1[k])
         _eq("index starts", m["starts"], st)
+        # the chained paths (gzip blobs -> windows / peaks): every device inflates and walks its own ctgs
+        soff = cuts.astype(np.uint64)
+        for infl in (1.0, 0.5):
+            a = api.wave_gz_batch(mctx, cat, goff, soff, 100, 10, 100, 3.0, infl)
+            b = api.wave_gz_batch(one, cat, goff, soff, 100, 10, 100, 3.0, infl)
+            assert not a[4].any() and not b[4].any()
+            for name, x, y in zip(("win_off", "gc_count", "gc", "signal"), a[:4], b[:4]):
+                _eq(f"multi-device wave_gz {name} (influence {infl})", x.view(np.uint32) if x.dtype == np.float32 else x,
+                    y.view(np.uint32) if y.dtype == np.float32 else y)
+        pm, stm = api.wave_peaks_gz_batch(mctx, cat, goff, soff, 100, 10, 100, 3.0, 1.0, 0.2)
+        p1 = api.wave_peaks_batch(one, g, soff, 100, 10, 100, 3.0, 1.0, 0.2)
+        assert not stm.any() and p1["ctg"].size > 0
+        for k in ("ctg", "first", "last", "signal"):
+            _eq(f"multi-device peaks from gz: {k}", pm[k], p1[k])
+        _eq("multi-device peaks from gz: gc", pm["gc"].view(np.uint32), p1["gc"].view(np.uint32))
 
 
 def test_plans_follow_an_index_rewritten_in_place(ctx, orc):
