@@ -581,8 +581,7 @@ GAMS_API int32_t gams_cuda_wave_peaks_dev(gams_cuda_wave_plan *p, void *stream, 
               "wave_peaks_dev: with coverage %g some intersecting windows are not merged (wave.rs:229-231): components are "
               "not runs; use gams_cuda_wave_text on the per-window arrays", (double)coverage);
     DeviceGuard g(p->device);
-    const uint64_t tiles = (p->win.total + 2047) / 2048;
-    int32_t rc = p->peak_tmp.reserve(sizeof(uint64_t) * 2 * (tiles + 2));
+    int32_t rc = p->peak_tmp.reserve(peak_tmp_bytes(p->win.total));
     if (rc) return rc;
     p->launches += 3;
     return launch_peak_runs((cudaStream_t)stream, d_signal, d_gc, p->win.d_off, p->n_ctg, 0, p->win.total, p->size, p->step,

@@ -276,6 +276,7 @@ int32_t launch_valid_runs(cudaStream_t st, const uint8_t *d_seq, uint64_t total,
                           uint64_t *d_tmp, uint64_t cap, uint64_t *d_run_start, uint64_t *d_run_end, uint64_t *d_n_runs);
 // peaks.cu
 bool peak_merge_is_runs(int32_t size, int32_t step, float coverage);
+size_t peak_tmp_bytes(uint64_t n_win);
 int32_t launch_peak_runs(cudaStream_t st, const int8_t *d_sig, const float *d_gc, const uint64_t *d_win_off, int64_t n_ctg,
                          uint64_t g0, uint64_t g1, int32_t size, int32_t step, uint64_t *d_tmp, uint64_t cap,
                          uint32_t *pk_ctg, uint32_t *pk_first, uint32_t *pk_last, float *pk_gc, int8_t *pk_sig,
