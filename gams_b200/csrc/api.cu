@@ -660,10 +660,18 @@ static int32_t wave_on_device(gams_cuda_ctx *ctx, int d, int64_t c0, int64_t c1,
         if ((rc = pd.scratch[6].reserve(gz_bytes + 64 + (size_t)(n + 1) * 16 + (size_t)n * 4 + 64))) return rc;
         d_gz = pd.scratch[6].as<uint8_t>();
     }
+    size_t gz_from = 0;      // first slice whose blobs have not been handed to the copy engine yet
     auto enqueue_h2d = [&](size_t k) -> int32_t {
         if (gzs) {
-            const uint64_t b0 = gzs->gz_off[c0 + cut[k]] - gz_base, b1 = gzs->gz_off[c0 + cut[k + 1]] - gz_base;
-            if (b1 > b0) CUDA_TRY(cudaMemcpyAsync(d_gz + b0, gzs->gz_concat + gz_base + b0, b1 - b0, cudaMemcpyHostToDevice, pd.copy_in));
+            // the blobs go up in (up to) four copies, one per stretch the decoder's header search waits for (48 copies of 21 MB
+            // reached 49 GB/s of the link's 55); ev_in[k] of a slice inside a stretch fires early and is not waited for
+            bool stretch_end = false;
+            for (size_t q = 1; q <= 4; ++q) stretch_end |= k + 1 == n_sl * q / 4;
+            if (stretch_end) {
+                const uint64_t b0 = gzs->gz_off[c0 + cut[gz_from]] - gz_base, b1 = gzs->gz_off[c0 + cut[k + 1]] - gz_base;
+                if (b1 > b0) CUDA_TRY(cudaMemcpyAsync(d_gz + b0, gzs->gz_concat + gz_base + b0, b1 - b0, cudaMemcpyHostToDevice, pd.copy_in));
+                gz_from = k + 1;
+            }
         } else {
             const uint64_t b0 = seq_off[c0 + cut[k]] - base0, b1 = seq_off[c0 + cut[k + 1]] - base0;
             if (b1 > b0) CUDA_TRY(cudaMemcpyAsync(d_seq + b0, h_seq + b0, b1 - b0, cudaMemcpyHostToDevice, pd.copy_in));
