@@ -72,6 +72,41 @@ void BlockCache::clear() {
     free_blocks.clear();
 }
 
+BlockCache::~BlockCache() {
+    if (h_stage) cudaFreeHost(h_stage);
+}
+
+__global__ void __launch_bounds__(256)
+upload_table_kernel(uint4 *__restrict__ dst, const uint4 *__restrict__ src, size_t n16) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+int32_t upload_table(BlockCache *cache, void *d_dst, const void *h_src, size_t bytes, cudaStream_t st) {
+    if (bytes == 0) return GAMS_CUDA_OK;
+    if (!cache || (reinterpret_cast<uintptr_t>(d_dst) & 15u)) {
+        CUDA_TRY(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        return GAMS_CUDA_OK;
+    }
+    std::lock_guard<std::mutex> lk(cache->mu);
+    const size_t padded = (bytes + 15) & ~(size_t)15;     // (device blocks are rounded up to 256 bytes and more: the padding fits)
+    if (padded > cache->stage_cap) {
+        if (cache->h_stage) cudaFreeHost(cache->h_stage);
+        cache->h_stage = cache->d_stage = nullptr, cache->stage_cap = 0;
+        const size_t cap = std::max<size_t>(padded + padded / 2, 1 << 20);
+        CUDA_TRY(cudaHostAlloc(&cache->h_stage, cap, cudaHostAllocMapped));
+        CUDA_TRY(cudaHostGetDevicePointer(&cache->d_stage, cache->h_stage, 0));
+        cache->stage_cap = cap;
+    }
+    std::memcpy(cache->h_stage, h_src, bytes);
+    const size_t n16 = padded / 16;
+    const unsigned grid = (unsigned)std::min<size_t>((n16 + 255) / 256, 148 * 4);
+    upload_table_kernel<<<grid, 256, 0, st>>>(static_cast<uint4 *>(d_dst), static_cast<const uint4 *>(cache->d_stage), n16);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return GAMS_CUDA_OK;
+}
+
 int32_t dev_alloc(BlockCache *cache, void **p, size_t bytes) {
     if (cache) return cache->get(p, bytes);
     CUDA_TRY(cudaMalloc(p, bytes ? bytes : 1));
@@ -123,12 +158,12 @@ int32_t SeriesLayout::build(const uint64_t *h_off, int64_t n, cudaStream_t st) {
     n_ztiles = zt.size();
     int32_t rc;
     if ((rc = dev_alloc(cache, reinterpret_cast<void **>(&d_off), sizeof(uint64_t) * (size_t)(n + 1)))) return rc;
-    CUDA_TRY(cudaMemcpyAsync(d_off, rel.data(), sizeof(uint64_t) * (size_t)(n + 1), cudaMemcpyHostToDevice, st));
+    if ((rc = upload_table(cache, d_off, rel.data(), sizeof(uint64_t) * (size_t)(n + 1), st))) return rc;
     if ((rc = dev_alloc(cache, reinterpret_cast<void **>(&d_nonfinite), sizeof(int) * (size_t)std::max<int64_t>(n, 1)))) return rc;
     CUDA_TRY(cudaMemsetAsync(d_nonfinite, 0, sizeof(int) * (size_t)std::max<int64_t>(n, 1), st));
     if (n_ztiles) {
         if ((rc = dev_alloc(cache, reinterpret_cast<void **>(&d_ztiles), sizeof(TileDesc) * n_ztiles))) return rc;
-        CUDA_TRY(cudaMemcpyAsync(d_ztiles, zt.data(), sizeof(TileDesc) * n_ztiles, cudaMemcpyHostToDevice, st));
+        if ((rc = upload_table(cache, d_ztiles, zt.data(), sizeof(TileDesc) * n_ztiles, st))) return rc;
     }
     CUDA_TRY(cudaStreamSynchronize(st));
     return GAMS_CUDA_OK;
@@ -485,21 +520,18 @@ GAMS_API int32_t gams_cuda_wave_plan_create(gams_cuda_ctx *ctx, int32_t dev_inde
     int32_t arc;
     if (!ft.empty()) {
         if ((arc = dev_alloc(cache, reinterpret_cast<void **>(&p->d_ftiles), sizeof(FusedTile) * ft.size()))) return arc;
-        CUDA_TRY(cudaMemcpyAsync(p->d_ftiles, ft.data(), sizeof(FusedTile) * ft.size(), cudaMemcpyHostToDevice, pd.stream));
-        CUDA_TRY(cudaStreamSynchronize(pd.stream));
+        if ((arc = upload_table(cache, p->d_ftiles, ft.data(), sizeof(FusedTile) * ft.size(), pd.stream))) return arc;
     }
     if ((arc = dev_alloc(cache, reinterpret_cast<void **>(&p->d_seq_off), sizeof(uint64_t) * (size_t)(n_ctg + 1)))) return arc;
-    CUDA_TRY(cudaMemcpyAsync(p->d_seq_off, p->h_seq_off.data(), sizeof(uint64_t) * (size_t)(n_ctg + 1),
-                             cudaMemcpyHostToDevice, pd.stream));
+    if ((arc = upload_table(cache, p->d_seq_off, p->h_seq_off.data(), sizeof(uint64_t) * (size_t)(n_ctg + 1), pd.stream))) return arc;
     if (!gt.empty()) {
         if ((arc = dev_alloc(cache, reinterpret_cast<void **>(&p->d_gtiles), sizeof(TileDesc) * gt.size()))) return arc;
-        CUDA_TRY(cudaMemcpyAsync(p->d_gtiles, gt.data(), sizeof(TileDesc) * gt.size(), cudaMemcpyHostToDevice, pd.stream));
+        if ((arc = upload_table(cache, p->d_gtiles, gt.data(), sizeof(TileDesc) * gt.size(), pd.stream))) return arc;
         std::vector<float> tab((size_t)size + 1);
         const float fs = (float)size;
         for (int32_t c = 0; c <= size; ++c) tab[c] = (float)c / fs;  // `count as f32 / l as f32`, one IEEE divide
         if ((arc = dev_alloc(cache, reinterpret_cast<void **>(&p->d_gc_tab), sizeof(float) * tab.size()))) return arc;
-        CUDA_TRY(cudaMemcpyAsync(p->d_gc_tab, tab.data(), sizeof(float) * tab.size(), cudaMemcpyHostToDevice, pd.stream));
-        CUDA_TRY(cudaStreamSynchronize(pd.stream));
+        if ((arc = upload_table(cache, p->d_gc_tab, tab.data(), sizeof(float) * tab.size(), pd.stream))) return arc;
     }
     int32_t rc = p->win.build(p->h_win_off.data(), n_ctg, pd.stream);
     if (rc) return rc;

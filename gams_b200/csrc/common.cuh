@@ -70,7 +70,16 @@ struct BlockCache {
     int32_t get(void **p, size_t bytes);      // *p has round_up(bytes) bytes
     void put(void *p, size_t bytes);
     void clear();
+    // pinned, device-mapped staging for upload_table (grow-only; one table at a time)
+    void *h_stage = nullptr, *d_stage = nullptr;
+    size_t stage_cap = 0;
+    ~BlockCache();
 };
+// Small tables (tile descriptors, offsets) go up by a KERNEL that reads them from pinned host memory, not by the copy engine: a
+// cudaMemcpyAsync queues behind the 64 MB slices of sequence the host paths have in flight (the plan build waited 9 ms for them),
+// a kernel only shares the link with them.  Blocks until the table is on the device (the staging buffer is reused).
+// cache == nullptr: plain cudaMemcpyAsync + synchronise.
+int32_t upload_table(BlockCache *cache, void *d_dst, const void *h_src, size_t bytes, cudaStream_t st);
 int32_t dev_alloc(BlockCache *cache, void **p, size_t bytes);   // cache == nullptr: plain cudaMalloc
 void dev_free(BlockCache *cache, void *p, size_t bytes);
 
