@@ -654,7 +654,8 @@ static int32_t wave_on_device(gams_cuda_ctx *ctx, int d, int64_t c0, int64_t c1,
     const uint64_t base0 = seq_off[c0], nb = seq_off[c1] - base0;
     if ((rc = pd.scratch[0].reserve(((nb + 31) & ~31ull) + 32))) return rc;
     uint8_t *d_seq = pd.scratch[0].as<uint8_t>();
-    const uint64_t slice_bytes = 64ull << 20;
+    uint64_t slice_bytes = 64ull << 20;
+    if (const char *e = getenv("GAMS_CUDA_WAVE_SLICE")) slice_bytes = std::max<uint64_t>(1, strtoull(e, nullptr, 10));   // tests: many slices on small inputs
     std::vector<int64_t> cut{0};
     for (int64_t c = 0; c < n; ++c) {
         if (seq_off[c0 + c + 1] < seq_off[c0 + c]) {
@@ -664,41 +665,60 @@ static int32_t wave_on_device(gams_cuda_ctx *ctx, int d, int64_t c0, int64_t c1,
         if (seq_off[c0 + c + 1] - seq_off[c0 + cut.back()] >= slice_bytes || c + 1 == n) cut.push_back(c + 1);
     }
     const size_t n_sl = cut.size() - 1;
-    std::vector<cudaEvent_t> ev_in(n_sl), ev_k(n_sl);
+    // GAMS_CUDA_TIMELINE=1: the events carry times, and the call prints when each slice had arrived, was computed and was back
+    // (device clock, ms after the first copy was enqueued); for measurements, nothing is synchronised on the way
+    const bool timeline = getenv("GAMS_CUDA_TIMELINE") != nullptr;
+    const unsigned ev_flags = timeline ? cudaEventDefault : cudaEventDisableTiming;
+    std::vector<cudaEvent_t> ev_in(n_sl), ev_k(n_sl), ev_out(timeline ? n_sl + 1 : 0);
     for (size_t k = 0; k < n_sl; ++k) {
-        CUDA_TRY(cudaEventCreateWithFlags(&ev_in[k], cudaEventDisableTiming));
-        CUDA_TRY(cudaEventCreateWithFlags(&ev_k[k], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&ev_in[k], ev_flags));
+        CUDA_TRY(cudaEventCreateWithFlags(&ev_k[k], ev_flags));
     }
+    for (auto &e : ev_out) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDefault));
+    if (timeline) CUDA_TRY(cudaEventRecord(ev_out[n_sl], pd.copy_in));   // time zero
     struct EvGuard {
-        std::vector<cudaEvent_t> &a, &b;
+        std::vector<cudaEvent_t> &a, &b, &c;
         cudaStream_t in, aux;
-        cudaEvent_t gz_done = nullptr;
+        std::vector<cudaEvent_t> gz_done;   // one per piece of the gz path
         ~EvGuard() {
             cudaStreamSynchronize(in);   // an early error return must not leave copies from the caller's buffer in flight
             cudaStreamSynchronize(aux);  // ... nor the decoder writing the caller's status array
             for (auto e : a) cudaEventDestroy(e);
             for (auto e : b) cudaEventDestroy(e);
-            if (gz_done) cudaEventDestroy(gz_done);
+            for (auto e : c) cudaEventDestroy(e);
+            for (auto e : gz_done) cudaEventDestroy(e);
         }
-    } ev_guard{ev_in, ev_k, pd.copy_in, pd.aux};
+    } ev_guard{ev_in, ev_k, ev_out, pd.copy_in, pd.aux, {}};
     const uint8_t *h_seq = gzs ? nullptr : seq_concat + base0;
-    // gz source: the compressed bytes go up instead (a third of the bases), in the same slices of ctgs; they are inflated on
-    // the device once all of them have arrived (the decoder wants the whole batch: its time is the serial chain of the longest
-    // blob, not the number of blobs)
+    // gz source: the compressed bytes go up instead (a third of the bases), in the same slices of ctgs, and are inflated on the
+    // device.  When only peak records come back, the whole batch is decoded at once (the decoder's time is the serial chain of
+    // its longest blob rather than the number of blobs).  When all windows come back (1.55 GB per 3.1 Gbp: longer on the link
+    // than the blobs going up), the batch is decoded in pieces, so that the windows of piece q go down while piece q + 1 is
+    // being decoded: upload, decode and download overlap instead of following one another.
     uint8_t *d_gz = nullptr;
     uint64_t gz_base = 0, gz_bytes = 0;
+    size_t n_piece = 1;
     if (gzs) {
         gz_base = gzs->gz_off[c0], gz_bytes = gzs->gz_off[c1] - gz_base;
         if ((rc = pd.scratch[6].reserve(gz_bytes + 64 + (size_t)(n + 1) * 16 + (size_t)n * 4 + 64))) return rc;
         d_gz = pd.scratch[6].as<uint8_t>();
+        if (!sink && gc) {
+            // GAMS_CUDA_GZ_PIECES: the number of pieces, for tests and measurements; by default three, and none below ~128 MB
+            // of bases per piece, which is all floor (one deflate block per thread, one blob per warp)
+            const char *e = getenv("GAMS_CUDA_GZ_PIECES");
+            n_piece = e ? (size_t)std::max<long>(1, std::min<long>(atol(e), 16)) : std::min<size_t>(2, (size_t)(nb >> 27));
+            n_piece = std::max<size_t>(1, std::min<size_t>(n_piece, n_sl));
+        }
     }
+    // slices [n_sl q / n_str, n_sl (q + 1) / n_str) form stretch q: one upload each; a piece is a stretch when there are pieces
+    const size_t n_str = n_piece > 1 ? n_piece : 4;
     size_t gz_from = 0;      // first slice whose blobs have not been handed to the copy engine yet
     auto enqueue_h2d = [&](size_t k) -> int32_t {
         if (gzs) {
             // the blobs go up in (up to) four copies, one per stretch the decoder's header search waits for (48 copies of 21 MB
             // reached 49 GB/s of the link's 55); ev_in[k] of a slice inside a stretch fires early and is not waited for
             bool stretch_end = false;
-            for (size_t q = 1; q <= 4; ++q) stretch_end |= k + 1 == n_sl * q / 4;
+            for (size_t q = 1; q <= n_str; ++q) stretch_end |= k + 1 == n_sl * q / n_str;
             if (stretch_end) {
                 const uint64_t b0 = gzs->gz_off[c0 + cut[gz_from]] - gz_base, b1 = gzs->gz_off[c0 + cut[k + 1]] - gz_base;
                 if (b1 > b0) CUDA_TRY(cudaMemcpyAsync(d_gz + b0, gzs->gz_concat + gz_base + b0, b1 - b0, cudaMemcpyHostToDevice, pd.copy_in));
@@ -732,19 +752,36 @@ static int32_t wave_on_device(gams_cuda_ctx *ctx, int d, int64_t c0, int64_t c1,
         int32_t *d_status = reinterpret_cast<int32_t *>(d_ooff + (n + 1));
         CUDA_TRY(cudaMemcpyAsync(d_goff, gz_rel.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, pd.aux));
         CUDA_TRY(cudaMemcpyAsync(d_ooff, seq_rel.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, pd.aux));
-        std::vector<int64_t> arrive_end;
-        std::vector<cudaEvent_t> arrive_ev;
-        for (size_t q = 1; q <= 4 && n_sl; ++q) {
-            const size_t k = n_sl * q / 4;
-            if (k == 0 || (!arrive_end.empty() && cut[k] == arrive_end.back())) continue;
-            arrive_end.push_back(cut[k]), arrive_ev.push_back(ev_in[k - 1]);
+        // gz_done[q] fires when the bases of piece q are final: the GC-wave kernels run beside the CRC-32 pass, which only sets
+        // status codes (fetched at the end: a copy into pageable host memory blocks the host until the decoder is through)
+        ev_guard.gz_done.assign(n_piece, nullptr);
+        for (auto &e : ev_guard.gz_done) CUDA_TRY(cudaEventCreateWithFlags(&e, ev_flags));
+        if (n_piece == 1) {
+            std::vector<int64_t> arrive_end;
+            std::vector<cudaEvent_t> arrive_ev;
+            for (size_t q = 1; q <= n_str && n_sl; ++q) {
+                const size_t k = n_sl * q / n_str;
+                if (k == 0 || (!arrive_end.empty() && cut[k] == arrive_end.back())) continue;
+                arrive_end.push_back(cut[k]), arrive_ev.push_back(ev_in[k - 1]);
+            }
+            if ((rc = launch_gunzip2(pd, pd.aux, d_gz, d_goff, n, d_seq, d_ooff, d_status, nb, ctx->gunzip_mode, ctx->gunzip_crc != 0,
+                                     (int)arrive_end.size(), arrive_end.data(), arrive_ev.data(), ev_guard.gz_done[0])))
+                return rc;
+        } else {
+            // The pieces follow one another on pd.aux and share the decoder's scratch, sized here for the whole batch (no piece
+            // needs more).  Pieces side by side on streams of their own were measured and are no faster (profiles/README.md, r2h):
+            // a later piece's kernels only get on the device in the tail of the earlier one's.
+            size_t by = 0;
+            if ((rc = gunzip2_scratch_bytes(pd, n, nb, ctx->gunzip_mode, ctx->gunzip_crc != 0, &by))) return rc;
+            if ((rc = pd.scratch[7].reserve(by))) return rc;
+            for (size_t q = 0; q < n_piece; ++q) {
+                const size_t k0 = n_sl * q / n_piece, k1 = n_sl * (q + 1) / n_piece;   // k1 > k0: n_piece <= n_sl
+                const int64_t a = cut[k0], b = cut[k1], all = b - a;
+                if ((rc = launch_gunzip2(pd, pd.aux, d_gz, d_goff + a, b - a, d_seq, d_ooff + a, d_status + a, seq_rel[b] - seq_rel[a],
+                                         ctx->gunzip_mode, ctx->gunzip_crc != 0, 1, &all, &ev_in[k1 - 1], ev_guard.gz_done[q])))
+                    return rc;
+            }
         }
-        // gz_done fires when the bases are final: the GC-wave kernels run beside the CRC-32 pass, which only sets status codes
-        // (fetched at the end: a copy into pageable host memory blocks the host until the decoder is through)
-        CUDA_TRY(cudaEventCreateWithFlags(&ev_guard.gz_done, cudaEventDisableTiming));
-        if ((rc = launch_gunzip2(pd, pd.aux, d_gz, d_goff, n, d_seq, d_ooff, d_status, nb, ctx->gunzip_mode, ctx->gunzip_crc != 0,
-                                 (int)arrive_end.size(), arrive_end.data(), arrive_ev.data(), ev_guard.gz_done)))
-            return rc;
         trace_stage("wave: gunzip enqueued");
     }
     // 2. the plan
@@ -784,7 +821,6 @@ static int32_t wave_on_device(gams_cuda_ctx *ctx, int d, int64_t c0, int64_t c1,
     for (size_t k = n_pre; k < n_sl; ++k)
         if ((rc = enqueue_h2d(k))) return rc;
     trace_stage("wave: reserve");
-    if (gzs) CUDA_TRY(cudaStreamWaitEvent(pd.stream, ev_guard.gz_done, 0));     // the bases are there once the decoder is through
     // The sequential z-score kernel (influence != 1: one warp per ctg) needs thousands of ctgs in flight to hide its
     // latency; on a 64 MB slice (~130 ctgs) it takes as long as on a quarter of a genome.  So it runs once per GROUP of
     // slices (four groups: the first three overlap the upload of the next), 321 -> ~90 ms per 3.1 Gbp end to end.
@@ -796,7 +832,11 @@ static int32_t wave_on_device(gams_cuda_ctx *ctx, int d, int64_t c0, int64_t c1,
     for (size_t k = 0; k < n_sl; ++k) {
         const int64_t a = cut[k], b = cut[k + 1];
         const uint64_t w0 = plan->h_win_off[a], w1 = plan->h_win_off[b];
-        CUDA_TRY(cudaStreamWaitEvent(pd.stream, ev_in[k], 0));
+        if (gzs) {   // the bases of slice k are there once the decoder is through with its piece
+            size_t q = 0;
+            while (q + 1 < n_piece && k >= n_sl * (q + 1) / n_piece) ++q;
+            CUDA_TRY(cudaStreamWaitEvent(pd.stream, ev_guard.gz_done[q], 0));
+        } else CUDA_TRY(cudaStreamWaitEvent(pd.stream, ev_in[k], 0));
         if (fused) {
             if ((rc = launch_gc_wave_fused(plan, pd.stream, d_seq, threshold, d_cnt, d_gc, d_sig, pd.d_zstats, a, b))) return rc;
         } else {
@@ -813,6 +853,7 @@ static int32_t wave_on_device(gams_cuda_ctx *ctx, int d, int64_t c0, int64_t c1,
                 CUDA_TRY(cudaMemcpyAsync(gc_count + wo + w0, d_cnt + w0, (w1 - w0) * sizeof(uint32_t), cudaMemcpyDeviceToHost, pd.copy_out));
             if (signal && !deferred) CUDA_TRY(cudaMemcpyAsync(signal + wo + w0, d_sig + w0, w1 - w0, cudaMemcpyDeviceToHost, pd.copy_out));
         }
+        if (timeline) CUDA_TRY(cudaEventRecord(ev_out[k], pd.copy_out));
         if (deferred && (k + 1 == n_sl || (k + 1) * n_grp / n_sl != k * n_grp / n_sl)) {   // last slice of its group
             const int64_t ga = cut[grp_first];
             const uint64_t gw0 = plan->h_win_off[ga];
@@ -876,6 +917,15 @@ static int32_t wave_on_device(gams_cuda_ctx *ctx, int d, int64_t c0, int64_t c1,
         }
     }
     CUDA_TRY(cudaStreamSynchronize(pd.copy_out));
+    if (timeline && !deferred) {
+        CUDA_TRY(cudaStreamSynchronize(pd.copy_in));
+        CUDA_TRY(cudaStreamSynchronize(pd.stream));
+        auto at = [&](cudaEvent_t e) { float ms = -1.0f; cudaEventElapsedTime(&ms, ev_out[n_sl], e); return ms; };
+        for (size_t q = 0; q < ev_guard.gz_done.size(); ++q) fprintf(stderr, "[gams_cuda] timeline: piece %zu decoded at %.2f ms\n", q, at(ev_guard.gz_done[q]));
+        for (size_t k = 0; k < n_sl; ++k)
+            if (k % 4 == 3 || k + 1 == n_sl || n_sl <= 8)
+                fprintf(stderr, "[gams_cuda] timeline: slice %3zu arrived %7.2f computed %7.2f back %7.2f ms\n", k, at(ev_in[k]), at(ev_k[k]), at(ev_out[k]));
+    }
     if (gzs) {
         const int32_t *d_status = reinterpret_cast<const int32_t *>(reinterpret_cast<const uint64_t *>(d_gz + ((gz_bytes + 63) & ~63ull)) + 2 * (n + 1));
         CUDA_TRY(cudaMemcpyAsync(gzs->status + c0, d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, pd.aux));

@@ -128,8 +128,12 @@ struct GcGeom {
 };
 
 // Kernel AB (gc_wave_fused.cu): tile geometry and the host-computed bounds of its certificate (make_fused_const)
+#ifndef FW_THREADS_N
+#define FW_THREADS_N 256                       // threads per Kernel-AB tile (a compile-time knob of gc_wave_fused.cu only; A/B: profiles/README.md)
+#endif
+constexpr int FW_THREADS = FW_THREADS_N;
 constexpr int FW_E = 8;                        // consecutive windows per thread in the statistics phases
-constexpr int FW_MAX_EL = 256 * FW_E;          // windows per tile, lag+1 halo windows included
+constexpr int FW_MAX_EL = FW_THREADS * FW_E;   // windows per tile, lag+1 halo windows included
 constexpr int FW_K = 6;                        // 16-byte chunks per thread: 24 576 bytes of sequence per tile
 constexpr int FW_PAD = 416;                    // front padding of the prefix arrays (>= FW_MAX_LAG, multiple of 8)
 constexpr int FW_MAX_LAG = 400;

@@ -1184,6 +1184,42 @@ crc32_fold_kernel(const uint64_t *__restrict__ out_off, int64_t n_blob, const ui
     if (c != crc_want[b]) status[b] = INF_ECRC;
 }
 
+// Layout of the decoder's scratch (pd.scratch[7]): tokens | part records | part_off | per-lane header scratch | crc_want |
+// piece_off | piece_crc | counter.  Every offset grows with n_blob and total_out, so a buffer reserved for a whole batch also
+// holds any piece of it.
+struct Gz2Layout {
+    uint64_t p_cap, n_lanes, n_piece_max;
+    size_t o_rec, o_poffs, o_slow, o_crc, o_poff, o_pcrc, bytes;
+};
+static int32_t gz2_layout(PerDevice &pd, int64_t n_blob, uint64_t total_out, int decoder, bool check_crc, Gz2Layout &L, int &n_sm_out) {
+    static int n_sm = 0;
+    if (!n_sm) CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, pd.device));
+    n_sm_out = n_sm;
+    // part records: sequence compresses ~3:1, so ranges of TK_RANGE compressed bytes are ~total_out / (3 TK_RANGE); room for a
+    // ratio of 2, and the range grows when the batch compresses worse (tk_range_bytes)
+    L.p_cap = std::min<uint64_t>(total_out / (2ull * TK_RANGE) + 2ull * (uint64_t)n_blob + 64, 0x7FFFFFF0ull);
+    L.n_lanes = (uint64_t)n_sm * TK_THREADS;
+    const uint64_t n_tokens = decoder == 0 ? (total_out >> 1) + 64ull * (uint64_t)(n_blob + 1) + 64 : 0;
+    L.n_piece_max = total_out / CRC_PIECE + (uint64_t)n_blob + 1;
+    L.o_rec = ((size_t)n_tokens * 4 + 31) & ~(size_t)31;
+    L.o_poffs = L.o_rec + (decoder == 0 ? (size_t)L.p_cap * sizeof(PartRec) : 0);
+    L.o_slow = (L.o_poffs + (decoder == 0 ? (size_t)(n_blob + 1) * 8 : 0) + 15) & ~(size_t)15;
+    L.o_crc = L.o_slow + (decoder == 0 ? (size_t)L.n_lanes * sizeof(TkSlow) : 0);
+    L.o_poff = (L.o_crc + (size_t)n_blob * 4 + 15) & ~(size_t)15;
+    L.o_pcrc = L.o_poff + (size_t)(n_blob + 1) * 8;
+    L.bytes = L.o_pcrc + (check_crc ? (size_t)L.n_piece_max * 4 : 0) + 64;
+    return GAMS_CUDA_OK;
+}
+
+int32_t gunzip2_scratch_bytes(PerDevice &pd, int64_t n_blob, uint64_t total_out, int decoder, bool check_crc, size_t *bytes) {
+    Gz2Layout L;
+    int n_sm;
+    int32_t rc = gz2_layout(pd, n_blob, total_out, decoder, check_crc, L, n_sm);
+    if (rc) return rc;
+    *bytes = (L.bytes + 255) & ~(size_t)255;
+    return GAMS_CUDA_OK;
+}
+
 int32_t launch_gunzip2(PerDevice &pd, cudaStream_t st, const uint8_t *d_gz, const uint64_t *d_gz_off, int64_t n_blob, uint8_t *d_out,
                        const uint64_t *d_out_off, int32_t *d_status, uint64_t total_out, int decoder, bool check_crc, int n_arrive,
                        const int64_t *arrive_end, const cudaEvent_t *arrive_ev, cudaEvent_t decoded_ev) {
@@ -1192,21 +1228,12 @@ int32_t launch_gunzip2(PerDevice &pd, cudaStream_t st, const uint8_t *d_gz, cons
         set_error("gunzip: too many blobs for one launch");
         return GAMS_CUDA_EINVAL;
     }
-    static int n_sm = 0;
-    if (!n_sm) CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, pd.device));
-    // part records: sequence compresses ~3:1, so ranges of TK_RANGE compressed bytes are ~total_out / (3 TK_RANGE); room for a
-    // ratio of 2, and the range grows when the batch compresses worse (tk_range_bytes)
-    const uint64_t p_cap = std::min<uint64_t>(total_out / (2ull * TK_RANGE) + 2ull * (uint64_t)n_blob + 64, 0x7FFFFFF0ull);
-    const uint64_t n_lanes = (uint64_t)n_sm * TK_THREADS;
-    // scratch: tokens | part records | part_off | per-lane header scratch | crc_want | piece_off | piece_crc | counter
-    const uint64_t n_tokens = decoder == 0 ? (total_out >> 1) + 64ull * (uint64_t)(n_blob + 1) + 64 : 0;
-    const uint64_t n_piece_max = total_out / CRC_PIECE + (uint64_t)n_blob + 1;
-    const size_t o_rec = ((size_t)n_tokens * 4 + 31) & ~(size_t)31, o_poffs = o_rec + (decoder == 0 ? (size_t)p_cap * sizeof(PartRec) : 0),
-                 o_slow = (o_poffs + (decoder == 0 ? (size_t)(n_blob + 1) * 8 : 0) + 15) & ~(size_t)15,
-                 o_crc = o_slow + (decoder == 0 ? (size_t)n_lanes * sizeof(TkSlow) : 0),
-                 o_poff = (o_crc + (size_t)n_blob * 4 + 15) & ~(size_t)15, o_pcrc = o_poff + (size_t)(n_blob + 1) * 8,
-                 bytes = o_pcrc + (check_crc ? (size_t)n_piece_max * 4 : 0) + 64;
+    Gz2Layout L;
+    int n_sm;
     int32_t rc;
+    if ((rc = gz2_layout(pd, n_blob, total_out, decoder, check_crc, L, n_sm))) return rc;
+    const uint64_t p_cap = L.p_cap, n_piece_max = L.n_piece_max;
+    const size_t o_rec = L.o_rec, o_poffs = L.o_poffs, o_slow = L.o_slow, o_crc = L.o_crc, o_poff = L.o_poff, o_pcrc = L.o_pcrc, bytes = L.bytes;
     if ((rc = pd.scratch[7].reserve(bytes))) return rc;
     uint8_t *base = pd.scratch[7].as<uint8_t>();
     uint32_t *d_tok = reinterpret_cast<uint32_t *>(base), *d_crc = reinterpret_cast<uint32_t *>(base + o_crc),

@@ -20,5 +20,8 @@ int32_t launch_gunzip2(PerDevice &pd, cudaStream_t st, const uint8_t *d_gz, cons
 // n_arrive > 0: the blobs are still being uploaded; arrive_ev[i] fires once blobs < arrive_end[i] (rising) are on the device, and
 // the caller has NOT made `st` wait for the upload.  The header search follows the upload stretch by stretch.
 // decoded_ev: recorded on `st` once the output bytes are final, before the CRC-32 pass (which only reads them and sets status codes).
+// gunzip2_scratch_bytes: what a batch of (n_blob, total_out) takes of pd.scratch[7]; every piece of the batch takes less, so a
+// caller that decodes a batch piece by piece on one stream reserves this first and no piece re-allocates the buffer.
+int32_t gunzip2_scratch_bytes(PerDevice &pd, int64_t n_blob, uint64_t total_out, int decoder, bool check_crc, size_t *bytes);
 
 }  // namespace gams

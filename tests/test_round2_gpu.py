@@ -344,6 +344,36 @@ def test_wave_gz_batch_equals_wave_batch(ctx, orc, infl):
     assert np.array_equal(c2, cnt) and np.array_equal(s2, sig)
 
 
+@pytest.mark.parametrize("pieces,infl", [(2, 1.0), (3, 1.0), (5, 1.0), (16, 1.0), (3, 0.5)])
+def test_wave_gz_batch_in_pieces(ctx, orc, monkeypatch, pieces, infl):
+    """With all windows coming back the chained path decodes the batch in pieces (the windows of one go down while the next is
+    decoded).  Small slices force several pieces on a small input: same bits as one piece and as the oracle, a bad blob in the
+    later piece keeps its status; a ctg of 61 windows and pieces of a single ctg included."""
+    g = synth.genome(1_500_000, seed=93)
+    cuts = [0, 130_000, 260_017, 390_000, 520_000, 650_000, 780_001, 910_000, 1_040_000, 1_170_000, 1_170_700, 1_300_000, 1_500_000]
+    seqs = [g[a:b] for a, b in zip(cuts[:-1], cuts[1:])]
+    cat, off = orc.pack_ctgs(seqs)
+    blobs = [orc.encode_gz(s.tobytes()) for s in seqs]
+    gcat, goff = api.pack_blobs(blobs)
+    monkeypatch.setenv("GAMS_CUDA_WAVE_SLICE", "100000")      # one ctg per slice
+    monkeypatch.setenv("GAMS_CUDA_GZ_PIECES", "1")
+    w1, c1, g1, s1, st1 = api.wave_gz_batch(ctx, gcat, goff, off, 100, 10, 50, 3.0, infl)
+    monkeypatch.setenv("GAMS_CUDA_GZ_PIECES", str(pieces))
+    woff, cnt, gc, sig, st = api.wave_gz_batch(ctx, gcat, goff, off, 100, 10, 50, 3.0, infl)
+    assert not st.any() and not st1.any()
+    rw, rc, rg, rs = orc.wave_batch(cat, off, 100, 10, 50, 3.0, infl, threads=8)
+    for name, a, b, r in (("win_off", woff, w1, rw), ("gc_count", cnt, c1, rc), ("gc", gc.view(np.uint32), g1.view(np.uint32), rg.view(np.uint32)),
+                          ("signal", sig, s1, rs)):
+        _eq(name, a, r)
+        _eq(name + " (one piece)", b, r)
+    bad = [bytearray(b) for b in blobs]
+    bad[7][-8] ^= 0x10                                        # CRC of a blob in a later piece
+    gcat2, goff2 = api.pack_blobs([bytes(b) for b in bad])
+    _, c2, _, s2, st2 = api.wave_gz_batch(ctx, gcat2, goff2, off, 100, 10, 50, 3.0, infl, raise_on_error=False)
+    assert st2.tolist() == [0] * 7 + [7] + [0] * (len(blobs) - 8)
+    assert np.array_equal(c2, rc) and np.array_equal(s2, rs)  # the payload itself was intact
+
+
 def test_wave_gz_batch_reports_a_bad_blob(ctx, orc):
     """A corrupted blob (payload changed, CRC-32 no longer matches) and a blob of the wrong length fail the call with their
     status; the other ctgs' statuses stay 0."""
