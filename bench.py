@@ -659,7 +659,7 @@ def main():
             "timed_region_ms": ms_total, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "u8->u32 counts, f32 statistics", "data": "synthetic",
             "config": workload_config(args), "clocks": clocks, "e2e": e2e, "e2e_gz": e2e_gz, "gpu_launches": int(launches),
-            "roofline": roof_main, "kernels": kern, "path": "fused (gc_wave_fused_kernel)" if fused else ("gc_wave_fused_kernel + zscore_seg_walk_kernel + zscore_seg_fix_kernel (influence != 1)" if args.influence != 1.0 and plan.fused(THRESHOLD, 1.0) else "gc_window_kernel + zscore kernel"), "cpu_baseline": cpu, "overlap": overlap, "sw": sw, "feed": feed, "frontend": frontend, "multi_gpu": multi, "parity_spot_check": parity,
+            "roofline": roof_main, "kernels": kern, "path": "fused (gc_wave_fused_kernel)" if fused else ("gc_wave_fused_kernel + zscore_tseg_walk_kernel + zscore_tseg_fix_kernel (influence != 1; GAMS_CUDA_ZWALK_WARPS=1: the warp-per-segment kernels)" if args.influence != 1.0 and plan.fused(THRESHOLD, 1.0) else "gc_window_kernel + zscore kernel"), "cpu_baseline": cpu, "overlap": overlap, "sw": sw, "feed": feed, "frontend": frontend, "multi_gpu": multi, "parity_spot_check": parity,
             "windows_per_step": int(n_win), "bases_per_rank": int(n_bases),
         }
         print(json.dumps(line), flush=True)

@@ -592,7 +592,7 @@ GAMS_API int32_t gams_cuda_wave_dev(gams_cuda_wave_plan *p, void *stream, const 
         int32_t rc = launch_gc_wave_fused(p, (cudaStream_t)stream, d_seq, threshold, d_gc_count, d_gc, d_signal,
                                           p->ctx->devs[p->dev_index].d_zstats, 0, p->n_ctg);
         if (rc) return rc;
-        return launch_zscore_skip(p->win, (cudaStream_t)stream, d_gc, p->lag, threshold, influence, d_signal, &p->launches, 0, p->n_ctg);
+        return launch_zscore_skip(p->win, (cudaStream_t)stream, d_gc, p->lag, threshold, influence, d_signal, &p->launches, 0, p->n_ctg, true);
     }
     int32_t rc = launch_gc_windows(p, (cudaStream_t)stream, d_seq, d_gc_count, d_gc, &p->launches, 0, p->n_ctg);
     if (rc) return rc;
@@ -857,7 +857,7 @@ static int32_t wave_on_device(gams_cuda_ctx *ctx, int d, int64_t c0, int64_t c1,
         if (deferred && (k + 1 == n_sl || (k + 1) * n_grp / n_sl != k * n_grp / n_sl)) {   // last slice of its group
             const int64_t ga = cut[grp_first];
             const uint64_t gw0 = plan->h_win_off[ga];
-            if (fused_walk) rc = launch_zscore_skip(plan->win, pd.stream, d_gc, lag, threshold, influence, d_sig, &plan->launches, ga, b);
+            if (fused_walk) rc = launch_zscore_skip(plan->win, pd.stream, d_gc, lag, threshold, influence, d_sig, &plan->launches, ga, b, true);
             else rc = launch_zscore(plan->win, pd.stream, d_gc, lag, threshold, influence, d_filt, d_sig, &plan->launches,
                                     ctx->zscore_mode, pd.d_zstats, ga, b, true);
             if (rc) return rc;

@@ -310,5 +310,5 @@ bool trace_on();
 void trace_stage(const char *what, cudaStream_t st = nullptr, bool sync = false);
 bool zscore_skip_ok(uint64_t lag);
 int32_t launch_zscore_skip(const SeriesLayout &L, cudaStream_t st, const float *d_x, uint64_t lag, float threshold, float influence,
-                           int8_t *d_signal, uint64_t *launches, int64_t s0, int64_t s1);
+                           int8_t *d_signal, uint64_t *launches, int64_t s0, int64_t s1, bool gc_values);
 }  // namespace gams

@@ -25,12 +25,12 @@
 namespace gams {
 
 #ifndef FW_MIN_CTAS
-#define FW_MIN_CTAS (2048 / FW_THREADS_N)   // 8 tiles of 256 threads: 64 warps per SM at 32 registers (a few spilled bytes): 0.928 -> 0.913 ms; 5 CTAs per SM: 1.109 ms
+#define FW_MIN_CTAS 8   // 64 warps per SM at 32 registers (a few spilled bytes): 0.928 -> 0.913 ms; 5 CTAs per SM: 1.109 ms
 #endif
-constexpr int FW_NCH = FW_THREADS * FW_K;  // 16-byte chunks per tile
-constexpr int FW_NBLK = ((FW_MAX_EL + FW_MAX_R + FW_THREADS - 1) / FW_THREADS) * FW_THREADS;  // block sums per tile
+constexpr int FW_NCH = GC_THREADS * FW_K;  // 16-byte chunks per tile
+constexpr int FW_NBLK = ((FW_MAX_EL + FW_MAX_R + GC_THREADS - 1) / GC_THREADS) * GC_THREADS;  // block sums per tile
 static_assert((31 + (FW_NBLK - 1) * 16) / 16 < FW_NBLK + 4, "stale block reads stay inside WW");
-static_assert(FW_MAX_EL == FW_THREADS * FW_E && FW_E == 8 && FW_PAD % 8 == 0 && FW_PAD >= FW_MAX_LAG, "fused tile geometry");
+static_assert(FW_MAX_EL == GC_THREADS * FW_E && FW_E == 8 && FW_PAD % 8 == 0 && FW_PAD >= FW_MAX_LAG, "fused tile geometry");
 
 // v + (value of lane - d, if that lane exists): one SHFL and one predicated add
 __device__ __forceinline__ uint32_t scan_step(uint32_t v, int d) {
@@ -116,7 +116,7 @@ __device__ __forceinline__ uint32_t popc_in_minus_out_plus10(const uint32_t (&x)
 // S10: size == 100 and step == 10 (the reference's documented geometry, README `gams wave --size 100 --step 10`): the
 // window counts come straight out of the bit array, without the per-block sums and their barrier.
 template <bool WRITE_CNT, bool LAG4, int R, bool S10>
-__global__ void __launch_bounds__(FW_THREADS, FW_MIN_CTAS)
+__global__ void __launch_bounds__(GC_THREADS, FW_MIN_CTAS)
 gc_wave_fused_kernel(const uint8_t *__restrict__ seq, const FusedTile *__restrict__ tiles,
                      const float *__restrict__ gc_tab, int size, int step, int r_rt, int lag, float threshold,
                      uint32_t one, const FusedConst fc, uint32_t *__restrict__ cnt_out, float *__restrict__ gc_out,
@@ -128,7 +128,7 @@ gc_wave_fused_kernel(const uint8_t *__restrict__ seq, const FusedTile *__restric
     __shared__ __align__(16) uint16_t cwp[FW_PAD + FW_MAX_EL + 8];  // window counts c_e at cwp[FW_PAD + e]
     __shared__ __align__(16) uint2 Pq[(FW_PAD + FW_MAX_EL) / 4];    // (sum c, sum c^2) over elements < 4 m, at Pq[FW_PAD/4 + m]
     __shared__ float stab[FW_STAB];                                 // gc_tab when size < FW_STAB
-    __shared__ uint32_t ws1[FW_THREADS / 32], ws2[FW_THREADS / 32];
+    __shared__ uint32_t ws1[GC_THREADS / 32], ws2[GC_THREADS / 32];
     static_assert(FW_NBLK + 4 >= FW_NCH + 1, "WW holds the bit array");
     uint16_t *const WW16 = reinterpret_cast<uint16_t *>(WW);
     uint16_t *const cw = cwp + FW_PAD;
@@ -155,12 +155,12 @@ gc_wave_fused_kernel(const uint8_t *__restrict__ seq, const FusedTile *__restric
         Bytes32 v[FW_K / 2];
 #pragma unroll
         for (int j = 0; j < FW_K / 2; ++j) {
-            const uint32_t pi = j * FW_THREADS + tid;
+            const uint32_t pi = j * GC_THREADS + tid;
             if (2u * pi < nch && pi >= td.pi_min) v[j] = ld_stream32(src + 32u * pi);
         }
 #pragma unroll
         for (int j = 0; j < FW_K / 2; ++j) {
-            const uint32_t pi = j * FW_THREADS + tid;
+            const uint32_t pi = j * GC_THREADS + tid;
             if (2u * (pi - lane) < nch) {                           // warp-uniform
                 const uint32_t m = gc_mask32(v[j], one);
                 if (S10) {                                          // plain bit array: word pi = bits [32 pi, 32 pi + 32)
@@ -184,12 +184,12 @@ gc_wave_fused_kernel(const uint8_t *__restrict__ seq, const FusedTile *__restric
     if (!S10) {
         const uint32_t smask = (1u << step) - 1u;                   // step <= 16
         const uint32_t p0 = lead + (uint32_t)tid * (uint32_t)step;
-        const uint32_t sh = p0 & 15u;                               // FW_THREADS * step is a multiple of 16: the same for every j
+        const uint32_t sh = p0 & 15u;                               // 256 * step is a multiple of 16: the same for every j
         const uint32_t *wp = WW + (p0 >> 4);
-        const uint32_t dw = (uint32_t)(FW_THREADS / 16) * (uint32_t)step;   // words between blocks m and m + FW_THREADS
+        const uint32_t dw = 16u * (uint32_t)step;                   // words between blocks m and m + 256
 #pragma unroll
-        for (int j = 0; j < FW_NBLK / FW_THREADS; ++j, wp += dw)
-            bsum[j * FW_THREADS + tid] = (uint8_t)__popc((*wp >> sh) & smask);
+        for (int j = 0; j < FW_NBLK / GC_THREADS; ++j, wp += dw)
+            bsum[j * GC_THREADS + tid] = (uint8_t)__popc((*wp >> sh) & smask);
         __syncthreads();
     }
 
@@ -251,7 +251,7 @@ gc_wave_fused_kernel(const uint8_t *__restrict__ seq, const FusedTile *__restric
         }
         if (lane == 31) { ws1[warp] = s1; ws2[warp] = s2; }
         __syncthreads();
-        const uint32_t o1 = (lane < warp) ? ws1[lane & (FW_THREADS / 32 - 1)] : 0u, o2 = (lane < warp) ? ws2[lane & (FW_THREADS / 32 - 1)] : 0u;
+        const uint32_t o1 = (lane < warp) ? ws1[lane & 7] : 0u, o2 = (lane < warp) ? ws2[lane & 7] : 0u;
         q1 = s1 - a1 + __reduce_add_sync(0xFFFFFFFFu, o1);
         q2 = s2 - a2 + __reduce_add_sync(0xFFFFFFFFu, o2);
         reinterpret_cast<uint4 *>(Pq + FW_PAD / 4)[tid] = make_uint4(q1, q2, q1 + h1, q2 + h2);
@@ -480,7 +480,7 @@ int32_t launch_gc_wave_fused(gams_cuda_wave_plan *p, cudaStream_t st, const uint
     const FusedTile *tiles = p->d_ftiles + t0;
     const int r = p->size / p->step;
 #define GAMS_FUSED_LAUNCH(WC, L4, RR, S)                                                                                \
-    gc_wave_fused_kernel<WC, L4, RR, S><<<grid, FW_THREADS, 0, st>>>(d_seq, tiles, p->d_gc_tab, p->size, p->step, r,      \
+    gc_wave_fused_kernel<WC, L4, RR, S><<<grid, GC_THREADS, 0, st>>>(d_seq, tiles, p->d_gc_tab, p->size, p->step, r,      \
                                                                   (int)p->lag, threshold, 1u, fc, d_cnt, d_gc, d_sig, d_stats)
 #define GAMS_FUSED_LAUNCH_R(WC, L4)                                                                                     \
     do {                                                                                                               \

@@ -662,16 +662,281 @@ zscore_seg_fix_kernel(const float *__restrict__ x_all, const uint64_t *__restric
     }
 }
 
+// ---- the segmented walk with ONE THREAD per segment and O(1) certified steps (GC fractions) ---------------------------------------
+// The warp-per-segment walk above pays 2 * lag shared-memory loads and 4 * lag flops per replayed window, and inside a run of
+// signals 32 evaluated windows commit two.  For data known to lie in [0, 1] (GC fractions) and 0 <= influence <= 1 a window needs
+// none of that: the filtered history is bounded by M = 1.125 (zw_const), so the certificate of zscore_indep_kernel applies with a
+// constant M, and its exact quantities — sum and sum of squares of the lag filtered values in the stats window — SLIDE: one value
+// leaves, one enters (f64; the rounding of at most 3 * seg + 2 * lag + 64 such updates is part of the error budget).  A thread
+// therefore walks its segment window by window: ring of the last lag + 1 filtered values in shared memory (column of the
+// thread: conflict-free), S1 / S2 in registers, certificate, and only where that is inconclusive (a few windows per million) the
+// reference's sums over the ring in the reference's order.  While the process is clean the decision is D1, as above.
+//   zscore_tseg_walk_kernel  one thread per segment, assumed clean at its start; leaves seg_last / seg_ring as the kernels above
+//   zscore_tseg_fix_kernel   one thread per boundary whose true state (left by the previous segment's walk) is dirty: replays
+//                            behind the boundary until the true and the assumed process are clean at the same window.  A replay
+//                            that is still dirty at the end of its segment would have to carry on into the next one, whose own
+//                            boundary thread meanwhile started from what the assumed walk left: the series is flagged instead
+//                            and walked again from scratch by zscore_seq_ring_kernel (one warp, the plain sequential walk).
+//                            That takes a stretch of a whole segment (4096 windows) without lag + 1 quiet windows in a row.
+struct ZwConst {
+    double k_hi, k_lo, slack, err_S, extra, inv_n;
+};
+
+static ZwConst make_zw_const(uint64_t lag, float threshold, int64_t seg) {
+    const double u = 5.9604644775390625e-8, u64e = 1.1102230246251565e-16;
+    const float flag = (float)lag, flagm1 = flag - 1.0f;  // `data.len() as f32`, `len - 1.`
+    const double dn = (double)lag, dnm1 = (double)flagm1;
+    // M bounds every value of the filtered series: x in [0, 1], and f = fl(fl(a x) + fl(b f')) with a = influence in [2^-20, 1] or 0,
+    // b = fl(1 - a): f <= (a + b f')(1 + u)^2 has its fixed point below 1 + 2^-4 + 2^-20
+    const double M = 1.125;
+    const double K = 3.0 * (double)seg + 2.0 * dn + 64.0;     // f64 operations that went into S1 / S2 since they were summed afresh
+    const double cE = 1.01 * (dn + 2.0) * u;                  // E_m    = cE M
+    const double cMu = 1.01 * (K * (dn + 1.0) / dn + 6.0) * u64e;          // err_mu = cMu M   (partial sums <= (n + 1) M)
+    const double cS = (4.0 * K * (dn + 1.0) + 16.0 * dn) * u64e;           // err_S  = cS M^2
+    const double R = (0.6 * dn + 8.0) * u;
+    const double t2 = (double)threshold * (double)threshold;
+    ZwConst c;
+    c.k_hi = t2 * (1.0 + R) * (1.0 + R) * (1.0 + 5.0 * u) / dnm1;
+    c.k_lo = t2 * (1.0 - R) * (1.0 - R) * (1.0 - 5.0 * u) / dnm1;
+    c.slack = (cE + cMu) * (1.0 + 1e-9) * M + 1e-40;
+    c.err_S = cS * M * M + 1e-40;
+    c.extra = (cS + dn * cE * cE) * (1.0 + 1e-9) * M * M + 2e-40;
+    c.inv_n = 1.0 / dn;
+    return c;
+}
+
+// what a walking thread carries from window to window
+struct ZwState {
+    double S1, S2;       // sum / sum of squares of the filtered values in the stats window of the next window
+    float prev;          // filtered value of the window before the next one
+    int h;               // ring slot of the oldest value = the one that leaves next
+    int64_t last_sig;
+};
+
+// window i (>= lag + 1): decision (D1 while the process is clean and D1 is known: d1 in {-1, 0, 1}; d1 = 2: always certify), then
+// the slide to the stats window of i + 1.  ring: this thread's column (stride NT), RP = lag + 1 slots.
+template <int NT>
+__device__ __forceinline__ int zw_step(float *ring, int RP, ZwState &st, int64_t i, int64_t L, float xi, int d1, const ZwConst &zc,
+                                       float flag, float flagm1, float threshold, float influence, float one_minus) {
+    int dec;
+    if (d1 != 2 && st.last_sig < i - 1 - L) dec = d1;
+    else {
+        const double mu = st.S1 * zc.inv_n;
+        const double S = fma(-st.S1, mu, st.S2);
+        const double d = (double)xi - mu;
+        const double dev = fabs(d);
+        const double lo = dev - zc.slack, hi = dev + zc.slack;
+        const bool yes = (lo > 0.0) & (lo * lo > zc.k_hi * (S + zc.extra));
+        const bool no = hi * hi < zc.k_lo * fmax(S - zc.err_S, 0.0);
+        dec = yes ? (d > 0.0 ? 1 : -1) : (no ? 0 : 2);
+        if (dec == 2) {      // the reference's own sums, in its order, over the ring (oldest value first)
+            const int h = st.h;
+            auto ld = [&](int64_t t) {
+                int sl = h + (int)t;
+                if (sl >= RP) sl -= RP;
+                return ring[sl * NT];
+            };
+            dec = zscore_decide(ld, 0, (uint64_t)L, flag, flagm1, xi, threshold);
+        }
+    }
+    const float fi = dec ? __fadd_rn(__fmul_rn(influence, xi), __fmul_rn(one_minus, st.prev)) : xi;
+    const float old = ring[st.h * NT];
+    const double dp = (double)st.prev, dold = (double)old;
+    st.S1 += dp - dold;
+    st.S2 = fma(-dold, dold, fma(dp, dp, st.S2));
+    ring[st.h * NT] = fi;
+    st.h = (st.h + 1 == RP) ? 0 : st.h + 1;
+    st.prev = fi;
+    if (dec) st.last_sig = i;
+    return dec;
+}
+
+// series of segment g (seg_off: first segment of every series of the range)
+__device__ __forceinline__ int64_t zw_series_of(const uint32_t *__restrict__ seg_off, int64_t n_series, int64_t g) {
+    int64_t lo = 0, hi = n_series;
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if ((int64_t)seg_off[mid] <= g) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT)
+zscore_tseg_walk_kernel(const float *__restrict__ x_all, const uint64_t *__restrict__ off, const uint32_t *__restrict__ seg_off,
+                        int64_t s_begin, int64_t s_end, int64_t seg, uint64_t lag, float threshold, float influence, const ZwConst zc,
+                        int8_t *signal, long long *__restrict__ seg_last, float *__restrict__ seg_ring) {
+    extern __shared__ float zw_ring[];      // (lag + 1) * NT
+    const int64_t g = (int64_t)blockIdx.x * NT + threadIdx.x;
+    if (g >= (int64_t)seg_off[s_end - s_begin]) return;
+    const int64_t lo = zw_series_of(seg_off, s_end - s_begin, g);
+    const int64_t c = s_begin + lo;
+    const uint64_t base = off[c];
+    const int64_t n = (int64_t)(off[c + 1] - base);
+    const float *x = x_all + base;
+    int8_t *sg = signal + base;
+    const int64_t L = (int64_t)lag;
+    const int RP = (int)lag + 1;
+    float *ring = zw_ring + threadIdx.x;
+    const int64_t s = (g - (int64_t)seg_off[lo]) * seg, e = (s + seg < n) ? s + seg : n;
+    const float flag = __ull2float_rn((unsigned long long)lag);
+    const float flagm1 = __fsub_rn(flag, 1.0f);
+    const float one_minus = __fsub_rn(1.0f, influence);
+    ZwState st;
+    st.S1 = 0.0, st.S2 = 0.0, st.h = 0, st.last_sig = ZS_NEVER, st.prev = 0.0f;
+    int64_t i;
+    if (s > L) {            // clean at s by assumption: the history [s - 1 - L, s - 1] is plain data
+        if (s >= e) { seg_last[g] = ZS_NEVER; return; }
+        const float *xs = x + (s - 1 - L);
+        for (int j = 0; j <= (int)L; ++j) {
+            const float v = xs[j];
+            ring[j * NT] = v;
+            if (j < (int)L) {
+                st.S1 += (double)v;
+                st.S2 = fma((double)v, (double)v, st.S2);
+            }
+            st.prev = v;
+        }
+        i = s;
+    } else {                // the first segment of a series: windows < L never signal, window L sees [0, L) (stat.rs:30-31) and is D1
+        if (L >= e) { seg_last[g] = ZS_NEVER; return; }
+        for (int j = 0; j < (int)L; ++j) {
+            const float v = x[j];
+            ring[j * NT] = v;
+            st.S1 += (double)v;
+            st.S2 = fma((double)v, (double)v, st.S2);
+        }
+        const float xl = x[L];
+        const int dl = sg[L];
+        const float fl = dl ? __fadd_rn(__fmul_rn(influence, xl), __fmul_rn(one_minus, x[L - 1])) : xl;
+        ring[L * NT] = fl;
+        st.prev = fl;
+        if (dl) st.last_sig = L;
+        i = L + 1;          // its stats window is [0, L) as well
+    }
+    // windows one by one up to an 8-aligned place of the arrays, then eight per 32-byte load of x and 8-byte load / store of the signals
+    const uint64_t gi0 = base + (uint64_t)i;
+    int64_t head = (int64_t)((8u - (uint32_t)(gi0 & 7u)) & 7u);
+    if (head > e - i) head = e - i;
+    for (const int64_t stop = i + head; i < stop; ++i) sg[i] = (int8_t)zw_step<NT>(ring, RP, st, i, L, x[i], sg[i], zc, flag, flagm1, threshold, influence, one_minus);
+    for (; i + 8 <= e; i += 8) {
+        const float4 xa = __ldg(reinterpret_cast<const float4 *>(x + i)), xb = __ldg(reinterpret_cast<const float4 *>(x + i) + 1);
+        const uint2 dd = *reinterpret_cast<const uint2 *>(sg + i);
+        const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+        uint32_t o0 = 0u, o1 = 0u;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int d1 = (int)(int8_t)(((j < 4) ? dd.x : dd.y) >> (8 * (j & 3)));
+            const uint32_t dec = (uint32_t)zw_step<NT>(ring, RP, st, i + j, L, xv[j], d1, zc, flag, flagm1, threshold, influence, one_minus) & 0xFFu;
+            if (j < 4) o0 |= dec << (8 * j); else o1 |= dec << (8 * (j - 4));
+        }
+        *reinterpret_cast<uint2 *>(sg + i) = make_uint2(o0, o1);
+    }
+    for (; i < e; ++i) sg[i] = (int8_t)zw_step<NT>(ring, RP, st, i, L, x[i], sg[i], zc, flag, flagm1, threshold, influence, one_minus);
+    // ---- what the next segment has to know: the ring holds the filtered values of [e - L - 1, e), oldest at slot h
+    seg_last[g] = st.last_sig;
+    if (e < n && st.last_sig >= e - 1 - L) {
+        float *dst = seg_ring + (size_t)g * (size_t)(L + 1);
+        int sl = st.h;
+        for (int j = 0; j <= (int)L; ++j) {
+            dst[j] = ring[sl * NT];
+            sl = (sl + 1 == RP) ? 0 : sl + 1;
+        }
+    }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT)
+zscore_tseg_fix_kernel(const float *__restrict__ x_all, const uint64_t *__restrict__ off, const uint32_t *__restrict__ seg_off,
+                       int64_t s_begin, int64_t s_end, int64_t seg, uint64_t lag, float threshold, float influence, const ZwConst zc,
+                       int8_t *signal, const long long *__restrict__ seg_last, const float *__restrict__ seg_ring, int *__restrict__ redo) {
+    extern __shared__ float zw_ring[];      // (lag + 1) * NT
+    const int64_t g = (int64_t)blockIdx.x * NT + threadIdx.x;
+    if (g >= (int64_t)seg_off[s_end - s_begin]) return;
+    const int64_t lo = zw_series_of(seg_off, s_end - s_begin, g);
+    const int64_t k = g - (int64_t)seg_off[lo];
+    if (k == 0) return;                     // the first segment of a series started truly clean
+    const int64_t L = (int64_t)lag;
+    const int64_t s = k * seg;
+    ZwState st;
+    st.last_sig = seg_last[g - 1];
+    if (st.last_sig < s - 1 - L) return;    // the true process is clean at s: the segment is right as it stands
+    const int64_t c = s_begin + lo;
+    const uint64_t base = off[c];
+    const int64_t n = (int64_t)(off[c + 1] - base);
+    const float *x = x_all + base;
+    int8_t *sg = signal + base;
+    const int RP = (int)lag + 1;
+    float *ring = zw_ring + threadIdx.x;
+    const int64_t e = (s + seg < n) ? s + seg : n;
+    const float flag = __ull2float_rn((unsigned long long)lag);
+    const float flagm1 = __fsub_rn(flag, 1.0f);
+    const float one_minus = __fsub_rn(1.0f, influence);
+    // the true filtered history of [s - L - 1, s)
+    st.S1 = 0.0, st.S2 = 0.0, st.h = 0, st.prev = 0.0f;
+    {
+        const float *src = seg_ring + (size_t)(g - 1) * (size_t)(L + 1);
+        for (int j = 0; j <= (int)L; ++j) {
+            const float v = src[j];
+            ring[j * NT] = v;
+            if (j < (int)L) {
+                st.S1 += (double)v;
+                st.S2 = fma((double)v, (double)v, st.S2);
+            }
+            st.prev = v;
+        }
+    }
+    int64_t i = s, spec_last = ZS_NEVER;
+    for (; i < e; ++i) {
+        if (st.last_sig < i - 1 - L && spec_last < i - 1 - L) break;      // both clean: identical from here on
+        if (sg[i] != 0) spec_last = i;                                     // what the assumed walk decided here
+        sg[i] = (int8_t)zw_step<NT>(ring, RP, st, i, L, x[i], 2, zc, flag, flagm1, threshold, influence, one_minus);
+    }
+    // still dirty at the end of the segment: the next boundary's thread started from what the assumed walk left, which is not the
+    // true state — the series is walked again from scratch
+    if (i == e && e < n && !(st.last_sig < e - 1 - L && spec_last < e - 1 - L)) redo[c] = 1;
+}
+
 // the walk alone: d_signal holds the influence-1 decisions of every window (from zscore_indep_kernel or the fused GC-wave kernel)
 bool zscore_skip_ok(uint64_t lag) { return lag >= 1 && lag + 65 <= 1024; }
 int32_t launch_zscore_skip(const SeriesLayout &L, cudaStream_t st, const float *d_x, uint64_t lag, float threshold, float influence,
-                           int8_t *d_signal, uint64_t *launches, int64_t s0, int64_t s1) {
+                           int8_t *d_signal, uint64_t *launches, int64_t s0, int64_t s1, bool gc_values) {
     if (L.n_series == 0 || s1 <= s0) return GAMS_CUDA_OK;
-    static const int64_t seg_env = getenv("GAMS_CUDA_ZSEG") ? atoll(getenv("GAMS_CUDA_ZSEG")) : 0;   // (tests: boundaries every few hundred windows)
+    const char *seg_e = getenv("GAMS_CUDA_ZSEG");       // (tests: boundaries every few hundred windows)
+    const int64_t seg_env = seg_e ? atoll(seg_e) : 0;
     const int64_t seg = std::max<int64_t>(seg_env > 0 ? seg_env : 4096, (int64_t)lag + 34);   // (16384: 8.3 ms, 4096: 7.5, 1024: 7.8 per 3.1e8 windows)
     int32_t rc;
     if ((rc = L.seg_tables(s0, s1, seg, lag, st))) return rc;
     const int64_t n_seg = (int64_t)L.h_seg_off.back();
+    // GC fractions (values in [0, 1]), an influence the bound of zw_const covers, a certificate-friendly threshold: one thread per segment
+    const int nt = (lag + 1) * 4 * 128 <= 56 * 1024 ? 128 : ((lag + 1) * 4 * 64 <= 75 * 1024 ? 64 : 0);
+    const bool threads = gc_values && nt && lag >= 2 && (influence == 0.0f || (influence >= 9.5367431640625e-7f && influence <= 1.0f)) &&
+                         threshold >= 1.52587890625e-5f && threshold <= 1073741824.0f && seg < (1ll << 24) &&
+                         (reinterpret_cast<uintptr_t>(d_x) & 31u) == 0 && (reinterpret_cast<uintptr_t>(d_signal) & 7u) == 0 &&
+                         !getenv("GAMS_CUDA_ZWALK_WARPS");
+    if (threads) {
+        const ZwConst zc = make_zw_const(lag, threshold, seg);
+        const size_t smem = (size_t)(lag + 1) * 4 * (size_t)nt;
+        const unsigned grid = (unsigned)((n_seg + nt - 1) / nt), grid3 = (unsigned)((s1 - s0 + ZSEQ_WARPS - 1) / ZSEQ_WARPS);
+        CUDA_TRY(cudaMemsetAsync(L.d_nonfinite + s0, 0, sizeof(int) * (size_t)(s1 - s0), st));
+        auto go = [&](auto walk, auto fix) -> int32_t {
+            CUDA_TRY(cudaFuncSetAttribute(walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CUDA_TRY(cudaFuncSetAttribute(fix, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            walk<<<grid, nt, smem, st>>>(d_x, L.d_off, L.d_seg_off, s0, s1, seg, lag, threshold, influence, zc, d_signal, L.d_seg_last, L.d_seg_ring);
+            fix<<<grid, nt, smem, st>>>(d_x, L.d_off, L.d_seg_off, s0, s1, seg, lag, threshold, influence, zc, d_signal, L.d_seg_last, L.d_seg_ring,
+                                        L.d_nonfinite);
+            return GAMS_CUDA_OK;
+        };
+        if ((rc = nt == 128 ? go(zscore_tseg_walk_kernel<128>, zscore_tseg_fix_kernel<128>) : go(zscore_tseg_walk_kernel<64>, zscore_tseg_fix_kernel<64>))) return rc;
+        // series whose replay ran through a whole segment: the plain sequential walk, one warp each (warps of other series leave at once)
+        if (lag + 65 <= 256)
+            zscore_seq_ring_kernel<256><<<grid3, ZSEQ_WARPS * 32, 0, st>>>(d_x, L.d_off, s0, s1, lag, threshold, influence, d_signal, L.d_nonfinite);
+        else
+            zscore_seq_ring_kernel<1024><<<grid3, ZSEQ_WARPS * 32, 0, st>>>(d_x, L.d_off, s0, s1, lag, threshold, influence, d_signal, L.d_nonfinite);
+        if (launches) *launches += 3;
+        CUDA_TRY(cudaGetLastError());
+        return GAMS_CUDA_OK;
+    }
     const unsigned grid = (unsigned)((n_seg + ZSEQ_WARPS - 1) / ZSEQ_WARPS), grid2 = (unsigned)((s1 - s0 + ZSEQ_WARPS - 1) / ZSEQ_WARPS);
     if (lag + 65 <= 256) {
         zscore_seg_walk_kernel<256><<<grid, ZSEQ_WARPS * 32, 0, st>>>(d_x, L.d_off, L.d_seg_off, s0, s1, seg, lag, threshold, influence, d_signal,
@@ -722,7 +987,7 @@ int32_t launch_zscore(const SeriesLayout &L, cudaStream_t st, const float *d_x, 
         };
         int32_t rc = mode == 1 ? go(zscore_indep_kernel<1>) : mode == 2 ? go(zscore_indep_kernel<2>) : go(zscore_indep_kernel<0>);
         if (rc) return rc;
-        if (skip && (rc = launch_zscore_skip(L, st, d_x, lag, threshold, influence, d_signal, launches, s0, s1))) return rc;
+        if (skip && (rc = launch_zscore_skip(L, st, d_x, lag, threshold, influence, d_signal, launches, s0, s1, gc_values))) return rc;
         if (tiled && !gc_values) {
             // series flagged as holding Inf / NaN are walked again in the reference's order (a warp per series; warps of
             // clean series leave at once).  Data known to be GC fractions cannot hold any.

@@ -246,6 +246,34 @@ def test_sw_count_batch_synthetic_c3_shape(ctx, orc):
         assert not r["rg_count"][seg == 1].any()
 
 
+# --------------------------------------------------------------- influence != 1 on GC fractions: one thread per segment, O(1) certified steps
+@pytest.mark.parametrize("zseg", [0, 137, 700])
+@pytest.mark.parametrize("infl", [0.0, 9.5367431640625e-07, 0.001, 0.5, 0.999])
+def test_wave_influence_thread_walk(ctx, orc, zseg, infl):
+    """zscore_tseg_walk_kernel / zscore_tseg_fix_kernel (stat.rs:40-48 with influence in [0, 1], data = GC fractions) against the
+    oracle and against the warp-per-segment walk: segment boundaries every 137 / 700 / 4096 windows, thresholds that make the
+    process dirty almost everywhere (1.0: replays run through whole segments, the series is walked again by the sequential
+    kernel) or rarely (4.0), constant-GC runs (every certificate inconclusive), a GC shift every 3 kb, lags 2 .. 200."""
+    rng = np.random.default_rng(17)
+    g = synth.genome(900_000, seed=55)
+    shifty = g[:300_000].copy()
+    for a in range(0, 300_000, 6000):                          # alternate GC-rich / AT-rich blocks: many long runs of signals
+        blk = shifty[a:a + 3000]
+        blk[rng.random(blk.size) < 0.5] = ord("G")
+    flat = np.tile(np.frombuffer(b"ACATTTTTAT" * 5 + b"GCGCGCGCGATATATATATATATATATATATATATATATATATATATATA", dtype=np.uint8), 1500)
+    seqs = [g[300_000:700_000], shifty, np.concatenate([flat, g[700_000:780_000], flat[:40_000]]), g[780_000:782_511]]
+    cat, off = orc.pack_ctgs(seqs)
+    env = {"GAMS_CUDA_ZSEG": zseg} if zseg else {}
+    for size, step, lag, thr in ((100, 10, 100, 3.0), (100, 10, 100, 1.0), (100, 10, 50, 4.0), (100, 20, 2, 2.0), (50, 10, 200, 2.5), (100, 10, 7, 1.5)):
+        _, _, _, ref = orc.wave_batch(cat, off, size, step, lag, thr, infl, threads=8)
+        with _Env(**env):
+            _, _, _, got = api.wave_batch(ctx, cat, off, size, step, lag, thr, infl)
+        with _Env(GAMS_CUDA_ZWALK_WARPS=1, **env):
+            _, _, _, old = api.wave_batch(ctx, cat, off, size, step, lag, thr, infl)
+        _eq(f"thread walk {size}/{step} lag {lag} thr {thr} infl {infl} zseg {zseg}", got, ref)
+        _eq(f"warp walk {size}/{step} lag {lag} thr {thr} infl {infl} zseg {zseg}", old, ref)
+
+
 # --------------------------------------------------------------- gunzip: two-phase decoder (inflate2.cu) and the CRC-32 check
 def _gzb(data, level=1, strategy=0, mem=8):
     import zlib
