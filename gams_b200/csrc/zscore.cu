@@ -678,8 +678,12 @@ zscore_seg_fix_kernel(const float *__restrict__ x_all, const uint64_t *__restric
 //                            boundary thread meanwhile started from what the assumed walk left: the series is flagged instead
 //                            and walked again from scratch by zscore_seq_ring_kernel (one warp, the plain sequential walk).
 //                            That takes a stretch of a whole segment (4096 windows) without lag + 1 quiet windows in a row.
+// The certificate of zscore_indep_kernel multiplied through by n (D = n (x - mu) = n x - S1 and V = n S = n S2 - S1^2 are one
+// operation away from the sliding sums, so a decision is four dependent f64 operations behind S1):
+//   signal certainly      (|D| - ns)^2 > nk_hi V + c_hi   and |D| > ns           ns = n slack, nk_hi = n k_hi, c_hi = n^2 k_hi extra
+//   certainly none        (|D| + ns)^2 < nk_lo max(V - n_errS, 0)                n_errS = n err_S
 struct ZwConst {
-    double k_hi, k_lo, slack, err_S, extra, inv_n;
+    double dn, ns, nk_hi, c_hi, nk_lo, n_errS;
 };
 
 static ZwConst make_zw_const(uint64_t lag, float threshold, int64_t seg) {
@@ -695,60 +699,94 @@ static ZwConst make_zw_const(uint64_t lag, float threshold, int64_t seg) {
     const double cS = (4.0 * K * (dn + 1.0) + 16.0 * dn) * u64e;           // err_S  = cS M^2
     const double R = (0.6 * dn + 8.0) * u;
     const double t2 = (double)threshold * (double)threshold;
+    const double k_hi = t2 * (1.0 + R) * (1.0 + R) * (1.0 + 5.0 * u) / dnm1;
+    const double k_lo = t2 * (1.0 - R) * (1.0 - R) * (1.0 - 5.0 * u) / dnm1;
+    const double slack = (cE + cMu) * (1.0 + 1e-9) * M + 1e-40;      // on |x - mu|: E_m + the f64 error of mu (and of D / n)
+    const double err_S = cS * M * M + 1e-40;                         // the f64 error of S (and of V / n)
+    const double extra = (cS + dn * cE * cE) * (1.0 + 1e-9) * M * M + 2e-40;
+    // scaled by n; every product below is rounded once more (relative 2^-53): widened by 1e-12 in the safe direction
     ZwConst c;
-    c.k_hi = t2 * (1.0 + R) * (1.0 + R) * (1.0 + 5.0 * u) / dnm1;
-    c.k_lo = t2 * (1.0 - R) * (1.0 - R) * (1.0 - 5.0 * u) / dnm1;
-    c.slack = (cE + cMu) * (1.0 + 1e-9) * M + 1e-40;
-    c.err_S = cS * M * M + 1e-40;
-    c.extra = (cS + dn * cE * cE) * (1.0 + 1e-9) * M * M + 2e-40;
-    c.inv_n = 1.0 / dn;
+    c.dn = dn;
+    c.ns = dn * slack * (1.0 + 1e-12);
+    c.nk_hi = dn * k_hi * (1.0 + 1e-12);
+    c.c_hi = dn * dn * k_hi * extra * (1.0 + 1e-12);
+    c.nk_lo = dn * k_lo * (1.0 - 1e-12);
+    c.n_errS = dn * err_S * (1.0 + 1e-12);
     return c;
 }
 
-// what a walking thread carries from window to window
+// what a walking thread carries from window to window (window indices are relative to the series: < 2^31)
+constexpr int ZW_NEVER = -(1 << 30);
 struct ZwState {
     double S1, S2;       // sum / sum of squares of the filtered values in the stats window of the next window
     float prev;          // filtered value of the window before the next one
+    double dprev;        // ... as a double
     int h;               // ring slot of the oldest value = the one that leaves next
-    int64_t last_sig;
+    int last_sig;
 };
 
-// window i (>= lag + 1): decision (D1 while the process is clean and D1 is known: d1 in {-1, 0, 1}; d1 = 2: always certify), then
-// the slide to the stats window of i + 1.  ring: this thread's column (stride NT), RP = lag + 1 slots.
-template <int NT>
-__device__ __forceinline__ int zw_step(float *ring, int RP, ZwState &st, int64_t i, int64_t L, float xi, int d1, const ZwConst &zc,
-                                       float flag, float flagm1, float threshold, float influence, float one_minus) {
-    int dec;
-    if (d1 != 2 && st.last_sig < i - 1 - L) dec = d1;
-    else {
-        const double mu = st.S1 * zc.inv_n;
-        const double S = fma(-st.S1, mu, st.S2);
-        const double d = (double)xi - mu;
-        const double dev = fabs(d);
-        const double lo = dev - zc.slack, hi = dev + zc.slack;
-        const bool yes = (lo > 0.0) & (lo * lo > zc.k_hi * (S + zc.extra));
-        const bool no = hi * hi < zc.k_lo * fmax(S - zc.err_S, 0.0);
-        dec = yes ? (d > 0.0 ? 1 : -1) : (no ? 0 : 2);
-        if (dec == 2) {      // the reference's own sums, in its order, over the ring (oldest value first)
-            const int h = st.h;
-            auto ld = [&](int64_t t) {
-                int sl = h + (int)t;
-                if (sl >= RP) sl -= RP;
-                return ring[sl * NT];
-            };
-            dec = zscore_decide(ld, 0, (uint64_t)L, flag, flagm1, xi, threshold);
-        }
+// Window i (>= lag + 1): decision, then the slide to the stats window of i + 1.  HAVE_D1: while the process is clean the decision is
+// d1 (the influence-1 decision), otherwise (and always without HAVE_D1) the certificate, and where that is inconclusive the
+// reference's own sums in its order over the ring (oldest value first).  ring: this thread's column (stride NT), RP = lag + 1
+// slots; `old` / `dold`: the value in slot st.h, which leaves (the caller may have loaded it long before: a slot is written only
+// by the step that retires it).  One basic block but for the rare replay, and nothing of the next window's certificate waits
+// for this window's decision except through S1 / S2 two windows on: consecutive steps overlap.
+// f32 -> f64 by integer operations (the conversion unit takes 3 such conversions per window and is the slowest pipe of the walk):
+// exact for zero and for normal positive numbers; anything else (a subnormal: a filtered value that decayed through a hundred
+// signals in a row; negative, Inf, NaN: not GC data) raises `redo`
+__device__ __forceinline__ double zw_f2d(float f, bool &redo) {
+    const uint32_t b = __float_as_uint(f);
+    redo |= ((b - 0x00800000u) >= 0x7F000000u) & (b != 0u);
+    return __hiloint2double((int)(b ? (b >> 3) + 0x38000000u : 0u), (int)(b << 29));
+}
+
+// FAST: an inconclusive certificate only raises `redo` (the caller rolls the block back and walks it again with FAST = false): the
+// step is one basic block, and eight of them in a row leave the compiler free to run the certificates side by side.
+template <int NT, bool HAVE_D1, bool FAST = false>
+__device__ __forceinline__ int zw_step(float *ring, int RP, ZwState &st, int i, int L, float xi, double dxi, float old, double dold, int d1,
+                                       const ZwConst &zc, float flag, float flagm1, float threshold, float influence, float one_minus,
+                                       bool *redo = nullptr) {
+    const double D = fma(zc.dn, dxi, -st.S1);
+    const double V = fma(-st.S1, st.S1, zc.dn * st.S2);
+    const double dev = fabs(D);
+    const double lo = dev - zc.ns, hi = dev + zc.ns;
+    const bool yes = (lo > 0.0) & (lo * lo > fma(zc.nk_hi, V, zc.c_hi));
+    const bool no = hi * hi < zc.nk_lo * fmax(V - zc.n_errS, 0.0);
+    int dec = yes ? (D > 0.0 ? 1 : -1) : (no ? 0 : 2);
+    if (HAVE_D1 && st.last_sig < i - 1 - L) dec = d1;
+    if (FAST) {
+        *redo |= dec == 2;
+        dec = dec == 2 ? 0 : dec;
+    } else if (dec == 2) {
+        const int h = st.h;
+        auto ld = [&](int64_t t) {
+            int sl = h + (int)t;
+            if (sl >= RP) sl -= RP;
+            return ring[sl * NT];
+        };
+        dec = zscore_decide(ld, 0, (uint64_t)L, flag, flagm1, xi, threshold);
     }
-    const float fi = dec ? __fadd_rn(__fmul_rn(influence, xi), __fmul_rn(one_minus, st.prev)) : xi;
-    const float old = ring[st.h * NT];
-    const double dp = (double)st.prev, dold = (double)old;
-    st.S1 += dp - dold;
-    st.S2 = fma(-dold, dold, fma(dp, dp, st.S2));
+    const float blend = __fadd_rn(__fmul_rn(influence, xi), __fmul_rn(one_minus, st.prev));
+    double dblend;
+    if (FAST) dblend = zw_f2d(blend, *redo);
+    else dblend = (double)blend;
+    const float fi = dec ? blend : xi;
+    st.S1 = (st.S1 - dold) + st.dprev;
+    st.S2 = fma(st.dprev, st.dprev, fma(-dold, dold, st.S2));
     ring[st.h * NT] = fi;
     st.h = (st.h + 1 == RP) ? 0 : st.h + 1;
     st.prev = fi;
-    if (dec) st.last_sig = i;
+    st.dprev = dec ? dblend : dxi;
+    st.last_sig = dec ? i : st.last_sig;
+    (void)old;
     return dec;
+}
+// the same with the leaving value loaded here
+template <int NT, bool HAVE_D1>
+__device__ __forceinline__ int zw_step1(float *ring, int RP, ZwState &st, int i, int L, float xi, int d1, const ZwConst &zc, float flag,
+                                        float flagm1, float threshold, float influence, float one_minus) {
+    const float old = ring[st.h * NT];
+    return zw_step<NT, HAVE_D1>(ring, RP, st, i, L, xi, (double)xi, old, (double)old, d1, zc, flag, flagm1, threshold, influence, one_minus);
 }
 
 // series of segment g (seg_off: first segment of every series of the range)
@@ -762,7 +800,7 @@ __device__ __forceinline__ int64_t zw_series_of(const uint32_t *__restrict__ seg
 }
 
 template <int NT>
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, 512 / NT)
 zscore_tseg_walk_kernel(const float *__restrict__ x_all, const uint64_t *__restrict__ off, const uint32_t *__restrict__ seg_off,
                         int64_t s_begin, int64_t s_end, int64_t seg, uint64_t lag, float threshold, float influence, const ZwConst zc,
                         int8_t *signal, long long *__restrict__ seg_last, float *__restrict__ seg_ring) {
@@ -775,32 +813,33 @@ zscore_tseg_walk_kernel(const float *__restrict__ x_all, const uint64_t *__restr
     const int64_t n = (int64_t)(off[c + 1] - base);
     const float *x = x_all + base;
     int8_t *sg = signal + base;
-    const int64_t L = (int64_t)lag;
+    const int L = (int)lag;
     const int RP = (int)lag + 1;
     float *ring = zw_ring + threadIdx.x;
-    const int64_t s = (g - (int64_t)seg_off[lo]) * seg, e = (s + seg < n) ? s + seg : n;
+    const int s = (int)((g - (int64_t)seg_off[lo]) * seg), e = (int)(((int64_t)s + seg < n) ? (int64_t)s + seg : n);
     const float flag = __ull2float_rn((unsigned long long)lag);
     const float flagm1 = __fsub_rn(flag, 1.0f);
     const float one_minus = __fsub_rn(1.0f, influence);
     ZwState st;
-    st.S1 = 0.0, st.S2 = 0.0, st.h = 0, st.last_sig = ZS_NEVER, st.prev = 0.0f;
-    int64_t i;
+    st.S1 = 0.0, st.S2 = 0.0, st.h = 0, st.last_sig = ZW_NEVER, st.prev = 0.0f, st.dprev = 0.0;
+    int i;
     if (s > L) {            // clean at s by assumption: the history [s - 1 - L, s - 1] is plain data
         if (s >= e) { seg_last[g] = ZS_NEVER; return; }
         const float *xs = x + (s - 1 - L);
-        for (int j = 0; j <= (int)L; ++j) {
+        for (int j = 0; j <= L; ++j) {
             const float v = xs[j];
             ring[j * NT] = v;
-            if (j < (int)L) {
+            if (j < L) {
                 st.S1 += (double)v;
                 st.S2 = fma((double)v, (double)v, st.S2);
             }
             st.prev = v;
         }
+        st.dprev = (double)st.prev;
         i = s;
     } else {                // the first segment of a series: windows < L never signal, window L sees [0, L) (stat.rs:30-31) and is D1
         if (L >= e) { seg_last[g] = ZS_NEVER; return; }
-        for (int j = 0; j < (int)L; ++j) {
+        for (int j = 0; j < L; ++j) {
             const float v = x[j];
             ring[j * NT] = v;
             st.S1 += (double)v;
@@ -811,34 +850,78 @@ zscore_tseg_walk_kernel(const float *__restrict__ x_all, const uint64_t *__restr
         const float fl = dl ? __fadd_rn(__fmul_rn(influence, xl), __fmul_rn(one_minus, x[L - 1])) : xl;
         ring[L * NT] = fl;
         st.prev = fl;
+        st.dprev = (double)fl;
         if (dl) st.last_sig = L;
         i = L + 1;          // its stats window is [0, L) as well
     }
-    // windows one by one up to an 8-aligned place of the arrays, then eight per 32-byte load of x and 8-byte load / store of the signals
+    // windows one by one up to an 8-aligned place of the arrays, then eight per 32-byte load of x and 8-byte load / store of the
+    // signals.  The next eight are requested before the current eight are walked (a thread has nothing else to hide the latency
+    // with), and the eight values that leave the ring during a block are loaded and converted up front: slot h + j is written
+    // only by step j itself (RP >= 8).
     const uint64_t gi0 = base + (uint64_t)i;
-    int64_t head = (int64_t)((8u - (uint32_t)(gi0 & 7u)) & 7u);
+    int head = (int)((8u - (uint32_t)(gi0 & 7u)) & 7u);
     if (head > e - i) head = e - i;
-    for (const int64_t stop = i + head; i < stop; ++i) sg[i] = (int8_t)zw_step<NT>(ring, RP, st, i, L, x[i], sg[i], zc, flag, flagm1, threshold, influence, one_minus);
+    for (const int stop = i + head; i < stop; ++i)
+        sg[i] = (int8_t)zw_step1<NT, true>(ring, RP, st, i, L, x[i], sg[i], zc, flag, flagm1, threshold, influence, one_minus);
+    float4 xa = make_float4(0.f, 0.f, 0.f, 0.f), xb = xa;
+    uint2 dd = make_uint2(0u, 0u);
+    if (i + 8 <= e) {
+        xa = __ldg(reinterpret_cast<const float4 *>(x + i)), xb = __ldg(reinterpret_cast<const float4 *>(x + i) + 1);
+        dd = *reinterpret_cast<const uint2 *>(sg + i);
+    }
     for (; i + 8 <= e; i += 8) {
-        const float4 xa = __ldg(reinterpret_cast<const float4 *>(x + i)), xb = __ldg(reinterpret_cast<const float4 *>(x + i) + 1);
-        const uint2 dd = *reinterpret_cast<const uint2 *>(sg + i);
         const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
-        uint32_t o0 = 0u, o1 = 0u;
+        const uint2 dcur = dd;
+        if (i + 16 <= e) {
+            xa = __ldg(reinterpret_cast<const float4 *>(x + i + 8)), xb = __ldg(reinterpret_cast<const float4 *>(x + i + 8) + 1);
+            dd = *reinterpret_cast<const uint2 *>(sg + i + 8);
+        }
+        float ov[8];
+        double dxv[8], dov[8];
+        // (volatile: the compiler cannot tell that the steps' stores go to other slots, and would leave every load next to its use)
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const int d1 = (int)(int8_t)(((j < 4) ? dd.x : dd.y) >> (8 * (j & 3)));
-            const uint32_t dec = (uint32_t)zw_step<NT>(ring, RP, st, i + j, L, xv[j], d1, zc, flag, flagm1, threshold, influence, one_minus) & 0xFFu;
+            int sl = st.h + j;
+            if (sl >= RP) sl -= RP;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(ov[j]) : "r"((uint32_t)__cvta_generic_to_shared(ring + sl * NT)) : "memory");
+        }
+        bool redo = false;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dxv[j] = zw_f2d(xv[j], redo), dov[j] = zw_f2d(ov[j], redo);
+        uint32_t o0 = 0u, o1 = 0u;
+        const ZwState save = st;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int d1 = (int)(int8_t)(((j < 4) ? dcur.x : dcur.y) >> (8 * (j & 3)));
+            const uint32_t dec = (uint32_t)zw_step<NT, true, true>(ring, RP, st, i + j, L, xv[j], dxv[j], ov[j], dov[j], d1, zc, flag, flagm1,
+                                                                   threshold, influence, one_minus, &redo) & 0xFFu;
             if (j < 4) o0 |= dec << (8 * j); else o1 |= dec << (8 * (j - 4));
+        }
+        if (redo) {          // a few blocks per million: back to the state and the ring of the block's start, and once more with replays
+            st = save;
+            o0 = 0u, o1 = 0u;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                int sl = save.h + j;
+                if (sl >= RP) sl -= RP;
+                ring[sl * NT] = ov[j];
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int d1 = (int)(int8_t)(((j < 4) ? dcur.x : dcur.y) >> (8 * (j & 3)));
+                const uint32_t dec = (uint32_t)zw_step1<NT, true>(ring, RP, st, i + j, L, xv[j], d1, zc, flag, flagm1, threshold, influence, one_minus) & 0xFFu;
+                if (j < 4) o0 |= dec << (8 * j); else o1 |= dec << (8 * (j - 4));
+            }
         }
         *reinterpret_cast<uint2 *>(sg + i) = make_uint2(o0, o1);
     }
-    for (; i < e; ++i) sg[i] = (int8_t)zw_step<NT>(ring, RP, st, i, L, x[i], sg[i], zc, flag, flagm1, threshold, influence, one_minus);
+    for (; i < e; ++i) sg[i] = (int8_t)zw_step1<NT, true>(ring, RP, st, i, L, x[i], sg[i], zc, flag, flagm1, threshold, influence, one_minus);
     // ---- what the next segment has to know: the ring holds the filtered values of [e - L - 1, e), oldest at slot h
-    seg_last[g] = st.last_sig;
+    seg_last[g] = st.last_sig == ZW_NEVER ? ZS_NEVER : (long long)st.last_sig;
     if (e < n && st.last_sig >= e - 1 - L) {
         float *dst = seg_ring + (size_t)g * (size_t)(L + 1);
         int sl = st.h;
-        for (int j = 0; j <= (int)L; ++j) {
+        for (int j = 0; j <= L; ++j) {
             dst[j] = ring[sl * NT];
             sl = (sl + 1 == RP) ? 0 : sl + 1;
         }
@@ -856,11 +939,12 @@ zscore_tseg_fix_kernel(const float *__restrict__ x_all, const uint64_t *__restri
     const int64_t lo = zw_series_of(seg_off, s_end - s_begin, g);
     const int64_t k = g - (int64_t)seg_off[lo];
     if (k == 0) return;                     // the first segment of a series started truly clean
-    const int64_t L = (int64_t)lag;
-    const int64_t s = k * seg;
+    const int L = (int)lag;
+    const int s = (int)(k * seg);
     ZwState st;
-    st.last_sig = seg_last[g - 1];
-    if (st.last_sig < s - 1 - L) return;    // the true process is clean at s: the segment is right as it stands
+    const long long ls = seg_last[g - 1];
+    if (ls < (long long)s - 1 - L) return;
+    st.last_sig = (int)ls;    // the true process is clean at s: the segment is right as it stands
     const int64_t c = s_begin + lo;
     const uint64_t base = off[c];
     const int64_t n = (int64_t)(off[c + 1] - base);
@@ -868,29 +952,30 @@ zscore_tseg_fix_kernel(const float *__restrict__ x_all, const uint64_t *__restri
     int8_t *sg = signal + base;
     const int RP = (int)lag + 1;
     float *ring = zw_ring + threadIdx.x;
-    const int64_t e = (s + seg < n) ? s + seg : n;
+    const int e = (int)(((int64_t)s + seg < n) ? (int64_t)s + seg : n);
     const float flag = __ull2float_rn((unsigned long long)lag);
     const float flagm1 = __fsub_rn(flag, 1.0f);
     const float one_minus = __fsub_rn(1.0f, influence);
     // the true filtered history of [s - L - 1, s)
-    st.S1 = 0.0, st.S2 = 0.0, st.h = 0, st.prev = 0.0f;
+    st.S1 = 0.0, st.S2 = 0.0, st.h = 0, st.prev = 0.0f, st.dprev = 0.0;
     {
         const float *src = seg_ring + (size_t)(g - 1) * (size_t)(L + 1);
-        for (int j = 0; j <= (int)L; ++j) {
+        for (int j = 0; j <= L; ++j) {
             const float v = src[j];
             ring[j * NT] = v;
-            if (j < (int)L) {
+            if (j < L) {
                 st.S1 += (double)v;
                 st.S2 = fma((double)v, (double)v, st.S2);
             }
             st.prev = v;
         }
+        st.dprev = (double)st.prev;
     }
-    int64_t i = s, spec_last = ZS_NEVER;
+    int i = s, spec_last = ZW_NEVER;
     for (; i < e; ++i) {
         if (st.last_sig < i - 1 - L && spec_last < i - 1 - L) break;      // both clean: identical from here on
         if (sg[i] != 0) spec_last = i;                                     // what the assumed walk decided here
-        sg[i] = (int8_t)zw_step<NT>(ring, RP, st, i, L, x[i], 2, zc, flag, flagm1, threshold, influence, one_minus);
+        sg[i] = (int8_t)zw_step1<NT, false>(ring, RP, st, i, L, x[i], 2, zc, flag, flagm1, threshold, influence, one_minus);
     }
     // still dirty at the end of the segment: the next boundary's thread started from what the assumed walk left, which is not the
     // true state — the series is walked again from scratch
@@ -904,19 +989,53 @@ int32_t launch_zscore_skip(const SeriesLayout &L, cudaStream_t st, const float *
     if (L.n_series == 0 || s1 <= s0) return GAMS_CUDA_OK;
     const char *seg_e = getenv("GAMS_CUDA_ZSEG");       // (tests: boundaries every few hundred windows)
     const int64_t seg_env = seg_e ? atoll(seg_e) : 0;
-    const int64_t seg = std::max<int64_t>(seg_env > 0 ? seg_env : 4096, (int64_t)lag + 34);   // (16384: 8.3 ms, 4096: 7.5, 1024: 7.8 per 3.1e8 windows)
+    int64_t seg = std::max<int64_t>(seg_env > 0 ? seg_env : 4096, (int64_t)lag + 34);   // (16384: 8.3 ms, 4096: 7.5, 1024: 7.8 per 3.1e8 windows)
     int32_t rc;
-    if ((rc = L.seg_tables(s0, s1, seg, lag, st))) return rc;
-    const int64_t n_seg = (int64_t)L.h_seg_off.back();
     // GC fractions (values in [0, 1]), an influence the bound of zw_const covers, a certificate-friendly threshold: one thread per segment
     const int nt = (lag + 1) * 4 * 128 <= 56 * 1024 ? 128 : ((lag + 1) * 4 * 64 <= 75 * 1024 ? 64 : 0);
-    const bool threads = gc_values && nt && lag >= 2 && (influence == 0.0f || (influence >= 9.5367431640625e-7f && influence <= 1.0f)) &&
-                         threshold >= 1.52587890625e-5f && threshold <= 1073741824.0f && seg < (1ll << 24) &&
+    const bool threads = gc_values && nt && lag >= 8 && (influence == 0.0f || (influence >= 9.5367431640625e-7f && influence <= 1.0f)) &&
+                         threshold >= 1.52587890625e-5f && threshold <= 1073741824.0f &&
                          (reinterpret_cast<uintptr_t>(d_x) & 31u) == 0 && (reinterpret_cast<uintptr_t>(d_signal) & 7u) == 0 &&
                          !getenv("GAMS_CUDA_ZWALK_WARPS");
+    const size_t smem = (size_t)(lag + 1) * 4 * (size_t)nt;
+    if (threads && seg_env <= 0) {
+        // Every thread walks one segment and all segments take about as long, so the kernel's time is (waves of CTAs) x (segment
+        // length): the segments are made just long enough for the CTAs to fit the device in one wave (4096 windows gave 593
+        // CTAs on 592 places for the bench genome: two waves), or in the fewest waves that keep a segment below 8192 windows;
+        // not below 4096 windows: a replay that is still dirty at the end of its segment sends the whole series to the sequential
+        // kernel, and stretches of 1000 windows without lag + 1 quiet ones in a row do occur (a few per cent of them at threshold 3).
+        int dev = 0, n_sm = 0, occ = 0;
+        CUDA_TRY(cudaGetDevice(&dev));
+        CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+        if (nt == 128) {
+            CUDA_TRY(cudaFuncSetAttribute(zscore_tseg_walk_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, zscore_tseg_walk_kernel<128>, nt, smem));
+        } else {
+            CUDA_TRY(cudaFuncSetAttribute(zscore_tseg_walk_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, zscore_tseg_walk_kernel<64>, nt, smem));
+        }
+        const int64_t places = (int64_t)std::max(occ, 1) * n_sm * nt;
+        const int64_t seg_min = std::max<int64_t>(4096, (int64_t)lag + 34);
+        auto count = [&](int64_t sg_len) {
+            int64_t k = 0;
+            for (int64_t c = s0; c < s1; ++c) k += std::max<int64_t>(((int64_t)(L.h_off[c + 1] - L.h_off[c]) + sg_len - 1) / sg_len, 1);
+            return k;
+        };
+        for (int64_t waves = 1;; ++waves) {
+            int64_t lo = seg_min, hi = 8192;             // the shortest segment whose CTAs fit `waves` waves
+            if (count(hi) > places * waves) continue;    // (ends: count(8192) is finite)
+            while (lo < hi) {
+                const int64_t mid = (lo + hi) >> 1;
+                if (count(mid) <= places * waves) hi = mid; else lo = mid + 1;
+            }
+            seg = lo;
+            break;
+        }
+    }
+    if ((rc = L.seg_tables(s0, s1, seg, lag, st))) return rc;
+    const int64_t n_seg = (int64_t)L.h_seg_off.back();
     if (threads) {
         const ZwConst zc = make_zw_const(lag, threshold, seg);
-        const size_t smem = (size_t)(lag + 1) * 4 * (size_t)nt;
         const unsigned grid = (unsigned)((n_seg + nt - 1) / nt), grid3 = (unsigned)((s1 - s0 + ZSEQ_WARPS - 1) / ZSEQ_WARPS);
         CUDA_TRY(cudaMemsetAsync(L.d_nonfinite + s0, 0, sizeof(int) * (size_t)(s1 - s0), st));
         auto go = [&](auto walk, auto fix) -> int32_t {
