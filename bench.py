@@ -431,6 +431,35 @@ def main():
     ms_z = float(np.mean([e[1].elapsed_time(e[2]) for e in ev2]))
     z2_uncertain, _ = ctx.zscore_stats(reset=True)
     z2_uncertain /= (n2 + 1)
+    # `wave --influence 0.5` (stat.rs:40-48: the filtered series depends on earlier decisions): Kernel AB for GC and the influence-1
+    # decisions, then the walk (one thread per segment, zscore_tseg_walk_kernel / zscore_tseg_fix_kernel); timed outside the
+    # headline region, signals of three ctgs checked against the oracle
+    wave_infl = None
+    if args.influence == 1.0 and not args.skip_cpu:
+        d_sig_i = torch.empty(n_win, dtype=torch.int8, device=dev)
+        d_filt_i = torch.empty(n_win, dtype=torch.float32, device=dev)
+        plan.wave(stream, d_seq, THRESHOLD, 0.5, d_gc, d_sig_i, None, d_filt_i)
+        li0 = plan.launches
+        ei0, ei1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ei0.record()
+        for _ in range(5):
+            plan.wave(stream, d_seq, THRESHOLD, 0.5, d_gc, d_sig_i, None, d_filt_i)
+        ei1.record()
+        torch.cuda.synchronize()
+        ms_i = max_over_ranks(ei0.elapsed_time(ei1) / 5)
+        ok_i = None
+        if rank == 0:
+            from oracle import oracle as orc
+            woff_i = api.win_offsets(seq_off, SIZE, STEP)
+            ok_i = True
+            for c in sorted({0, n_ctg // 2, n_ctg - 1}):
+                sq = d_seq[int(seq_off[c]):int(seq_off[c + 1])].cpu().numpy()
+                _, _, _, rs = orc.wave_batch(sq, np.array([0, sq.size], dtype=np.uint64), SIZE, STEP, LAG, THRESHOLD, 0.5, threads=1)
+                ok_i &= bool(np.array_equal(d_sig_i[int(woff_i[c]):int(woff_i[c + 1])].cpu().numpy(), rs))
+        wave_infl = {"influence": 0.5, "ms_per_pass": ms_i, "value": total_bases / (ms_i * 1e-3) / 1e9, "unit": "Gbp/s",
+                     "gpu_launches_per_pass": int((plan.launches - li0) // 5), "bit_exact_sample": ok_i,
+                     "path": "gc_wave_fused_kernel + zscore_tseg_walk_kernel + zscore_tseg_fix_kernel (+ zscore_seq_ring_kernel for flagged series)"}
+        del d_sig_i, d_filt_i
     step()  # leave the headline path's outputs in d_gc / d_sig for the parity spot check
     torch.cuda.synchronize()
     ctx.zscore_stats(reset=True)
@@ -558,7 +587,7 @@ def main():
             e2e_gz = {"value": total_bases * n_e2e / dtg / 1e9, "unit": "Gbp/s", "ms_per_step": dtg / n_e2e * 1e3,
                       "h2d_bytes_per_step": n_gz, "d2h_bytes_per_step": int(n_win * 5 + n_ctg * 4), "steps": n_e2e,
                       "compressed_bytes": n_gz, "ratio": n_bases / n_gz, "matches_device_path": same,
-                      "api": "gams_cuda_wave_gz_batch (seq:{ctg} gzip blobs in pinned host memory -> device gunzip incl. CRC-32 -> fused GC-wave)",
+                      "api": "gams_cuda_wave_gz_batch (seq:{ctg} gzip blobs in pinned host memory -> device gunzip incl. CRC-32 -> fused GC-wave; decoded in two pieces, the windows of the first go down while the second is decoded)",
                       "host_compress_s": t_comp}
             gz_host = (p_gz, goff, n_gz)
         L.gams_cuda_host_free(h_gc_ptr)
@@ -659,7 +688,7 @@ def main():
             "timed_region_ms": ms_total, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "u8->u32 counts, f32 statistics", "data": "synthetic",
             "config": workload_config(args), "clocks": clocks, "e2e": e2e, "e2e_gz": e2e_gz, "gpu_launches": int(launches),
-            "roofline": roof_main, "kernels": kern, "path": "fused (gc_wave_fused_kernel)" if fused else ("gc_wave_fused_kernel + zscore_tseg_walk_kernel + zscore_tseg_fix_kernel (influence != 1; GAMS_CUDA_ZWALK_WARPS=1: the warp-per-segment kernels)" if args.influence != 1.0 and plan.fused(THRESHOLD, 1.0) else "gc_window_kernel + zscore kernel"), "cpu_baseline": cpu, "overlap": overlap, "sw": sw, "feed": feed, "frontend": frontend, "multi_gpu": multi, "parity_spot_check": parity,
+            "roofline": roof_main, "kernels": kern, "wave_influence": wave_infl, "path": "fused (gc_wave_fused_kernel)" if fused else ("gc_wave_fused_kernel + zscore_tseg_walk_kernel + zscore_tseg_fix_kernel (influence != 1; GAMS_CUDA_ZWALK_WARPS=1: the warp-per-segment kernels)" if args.influence != 1.0 and plan.fused(THRESHOLD, 1.0) else "gc_window_kernel + zscore kernel"), "cpu_baseline": cpu, "overlap": overlap, "sw": sw, "feed": feed, "frontend": frontend, "multi_gpu": multi, "parity_spot_check": parity,
             "windows_per_step": int(n_win), "bases_per_rank": int(n_bases),
         }
         print(json.dumps(line), flush=True)
