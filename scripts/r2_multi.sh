@@ -3,7 +3,7 @@
 N=$1; TAG=${2:-x}
 timeout 600 python -m pytest tests/test_parity_gpu.py -x -q --timeout 300 -k "multi_device" 2>&1 | tail -4
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
-timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/bench_n${N}_$TAG.log 2> gpurun_out/bench_n${N}_$TAG.err || tail -20 gpurun_out/bench_n${N}_$TAG.err
+timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 5 $BENCH_EXTRA > gpurun_out/bench_n${N}_$TAG.log 2> gpurun_out/bench_n${N}_$TAG.err || tail -20 gpurun_out/bench_n${N}_$TAG.err
 python - <<PY
 import json
 d=json.loads([l for l in open("gpurun_out/bench_n${N}_$TAG.log").read().strip().splitlines() if l.startswith("{")][-1])
