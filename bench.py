@@ -742,7 +742,28 @@ def bench_gunzip(args, ctx, L, dev, gz_host, seq_off, d_seq, n_bases):
         res[name] = {"ms_per_step": ms, "value": n_bases / (ms * 1e-3) / 1e9, "bit_exact": ok}
     ctx.set_gunzip_options(0, True)
     main = res["two_phase_crc"]
-    return {"what": "gunzip of the seq:{ctg} blobs on the device (gams_cuda_gunzip_dev), blobs and output in HBM; default decoder: block headers "
+    # the same through the host entry point (Conn::get_seq for a batch of ctgs: blobs in host memory, bases back in host memory;
+    # both pinned): the batch goes in two pieces, upload / decode / download of different pieces overlap
+    del d_out
+    torch.cuda.empty_cache()
+    p_out = pinned(n_bases, L)
+    st_h = np.zeros(n_ctg, dtype=np.int32)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+
+    def run_host():
+        api.check(L.gams_cuda_gunzip_batch(ctx.handle, n_ctg, p_gz, vp(goff), vp(seq_off), p_out, vp(st_h)))
+
+    run_host()
+    ok_h = bool(not st_h.any() and torch.equal(torch.from_numpy(as_np(p_out, n_bases, np.uint8)).to(dev), d_seq[:n_bases]))
+    t = time.perf_counter()
+    for _ in range(n):
+        run_host()
+    ms_h = (time.perf_counter() - t) / n * 1e3
+    L.gams_cuda_host_free(p_out)
+    e2e_feed = {"value": n_bases / (ms_h * 1e-3) / 1e9, "unit": "Gbp/s", "ms_per_step": ms_h, "h2d_bytes_per_step": int(n_gz),
+                "d2h_bytes_per_step": int(n_bases + 4 * n_ctg), "bit_exact": ok_h,
+                "api": "gams_cuda_gunzip_batch (host pointers, pinned; two pieces)"}
+    return {"e2e": e2e_feed, "what": "gunzip of the seq:{ctg} blobs on the device (gams_cuda_gunzip_dev), blobs and output in HBM; default decoder: block headers "
                     "found by a speculative search (one warp per group of 8 KB ranges) -> tokens (one thread per deflate block, verified "
                     "hand-over from block to block) -> bytes (one warp per blob) -> CRC-32",
             "value": main["value"], "unit": "Gbp/s", "ms_per_step": main["ms_per_step"], "blobs": int(n_ctg),

@@ -416,13 +416,64 @@ static int32_t gunzip_one(gams_cuda_ctx *ctx, int d, int64_t n_blob, const uint8
     uint8_t *d_gz = pd.scratch[0].as<uint8_t>(), *d_out = pd.scratch[1].as<uint8_t>();
     uint64_t *d_go = pd.scratch[2].as<uint64_t>(), *d_oo = d_go + (n_blob + 1);
     int32_t *d_status = reinterpret_cast<int32_t *>(d_oo + (n_blob + 1));
-    CUDA_TRY(cudaMemcpyAsync(d_gz, gz_concat + gz_off[0], n_in, cudaMemcpyHostToDevice, st));
+    // Large batches go in pieces (two by default, GAMS_CUDA_GZ_PIECES): every piece has its own upload, the decoder takes them one
+    // after the other, and the bytes of a piece go down while the next is decoded — the output is three times the input, so the
+    // download is the longest leg.  (More pieces do not pay: a piece costs the decoder its serial chains, whatever its size.)
+    const char *pe = getenv("GAMS_CUDA_GZ_PIECES");
+    int64_t n_piece = pe ? std::max<long>(1, std::min<long>(atol(pe), 16)) : std::min<int64_t>(2, (int64_t)(n_out >> 27));
+    n_piece = std::max<int64_t>(1, std::min<int64_t>(n_piece, n_blob));
+    if (n_piece == 1) {
+        CUDA_TRY(cudaMemcpyAsync(d_gz, gz_concat + gz_off[0], n_in, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d_go, go.data(), (size_t)(n_blob + 1) * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d_oo, oo.data(), (size_t)(n_blob + 1) * 8, cudaMemcpyHostToDevice, st));
+        if ((rc = launch_gunzip2(pd, st, d_gz, d_go, n_blob, d_out, d_oo, d_status, n_out, ctx->gunzip_mode, ctx->gunzip_crc != 0))) return rc;
+        if (n_out) CUDA_TRY(cudaMemcpyAsync(out_concat + out_off[0], d_out, n_out, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(status, d_status, (size_t)n_blob * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));   // go / oo are locals
+        return GAMS_CUDA_OK;
+    }
+    std::vector<int64_t> cut((size_t)n_piece + 1, 0);      // pieces of about equal output
+    for (int64_t q = 1, i = 0; q < n_piece; ++q) {
+        const uint64_t want = n_out / (uint64_t)n_piece * (uint64_t)q;
+        while (i < n_blob && oo[i] < want) ++i;
+        cut[q] = std::max(i, cut[q - 1]);
+    }
+    cut[n_piece] = n_blob;
+    struct Guard {      // an early return must not leave copies from / to the caller's buffers in flight
+        PerDevice &pd;
+        std::vector<cudaEvent_t> ev;
+        ~Guard() {
+            cudaStreamSynchronize(pd.copy_in);
+            cudaStreamSynchronize(pd.stream);
+            cudaStreamSynchronize(pd.copy_out);
+            for (auto e : ev) cudaEventDestroy(e);
+        }
+    } guard{pd, {}};
+    guard.ev.assign((size_t)n_piece * 2, nullptr);
+    for (auto &e : guard.ev) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    size_t by = 0;
+    if ((rc = gunzip2_scratch_bytes(pd, n_blob, n_out, ctx->gunzip_mode, ctx->gunzip_crc != 0, &by))) return rc;
+    if ((rc = pd.scratch[7].reserve(by))) return rc;       // no piece needs more: none re-allocates it under an earlier one
     CUDA_TRY(cudaMemcpyAsync(d_go, go.data(), (size_t)(n_blob + 1) * 8, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d_oo, oo.data(), (size_t)(n_blob + 1) * 8, cudaMemcpyHostToDevice, st));
-    if ((rc = launch_gunzip2(pd, st, d_gz, d_go, n_blob, d_out, d_oo, d_status, n_out, ctx->gunzip_mode, ctx->gunzip_crc != 0))) return rc;
-    if (n_out) CUDA_TRY(cudaMemcpyAsync(out_concat + out_off[0], d_out, n_out, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(status, d_status, (size_t)n_blob * 4, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));   // go / oo are locals
+    for (int64_t q = 0; q < n_piece; ++q) {
+        const int64_t a = cut[q], b = cut[q + 1];
+        if (go[b] > go[a]) CUDA_TRY(cudaMemcpyAsync(d_gz + go[a], gz_concat + gz_off[0] + go[a], go[b] - go[a], cudaMemcpyHostToDevice, pd.copy_in));
+        CUDA_TRY(cudaEventRecord(guard.ev[2 * q], pd.copy_in));
+    }
+    for (int64_t q = 0; q < n_piece; ++q) {
+        const int64_t a = cut[q], b = cut[q + 1], all = b - a;
+        if (all == 0) continue;
+        cudaEvent_t up = guard.ev[2 * q], done = guard.ev[2 * q + 1];
+        if ((rc = launch_gunzip2(pd, st, d_gz, d_go + a, all, d_out, d_oo + a, d_status + a, oo[b] - oo[a], ctx->gunzip_mode, ctx->gunzip_crc != 0,
+                                 1, &all, &up, done)))
+            return rc;
+        CUDA_TRY(cudaStreamWaitEvent(pd.copy_out, done, 0));
+        if (oo[b] > oo[a]) CUDA_TRY(cudaMemcpyAsync(out_concat + out_off[0] + oo[a], d_out + oo[a], oo[b] - oo[a], cudaMemcpyDeviceToHost, pd.copy_out));
+    }
+    CUDA_TRY(cudaMemcpyAsync(status, d_status, (size_t)n_blob * 4, cudaMemcpyDeviceToHost, st));   // behind the last CRC pass
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaStreamSynchronize(pd.copy_out));
     return GAMS_CUDA_OK;
 }
 

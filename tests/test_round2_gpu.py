@@ -350,6 +350,33 @@ def test_gunzip_two_decoders_agree(ctx, orc):
     assert np.array_equal(res[0], res[1])
 
 
+@pytest.mark.parametrize("pieces", [2, 5, 16])
+@pytest.mark.parametrize("decoder", [0, 1])
+def test_gunzip_batch_in_pieces(ctx, orc, pieces, decoder):
+    """gams_cuda_gunzip_batch cuts large batches into pieces (upload, decode and download of different pieces overlap): same bytes
+    and statuses as one piece — blobs of very different sizes, an empty one, a blob with a wrong CRC-32 in a later piece."""
+    import zlib
+    g = synth.genome(1_200_000, seed=77)
+    cuts = [0, 300_000, 300_000, 310_000, 700_001, 700_100, 1_000_000, 1_200_000]
+    plain = [g[a:b].tobytes() for a, b in zip(cuts[:-1], cuts[1:])]
+    blobs = [bytearray(_gzb(p, level=(1, 6)[i % 2])) for i, p in enumerate(plain)]
+    blobs[5][-8] ^= 0x01                                       # CRC-32 of the trailer
+    cat, goff = api.pack_blobs([bytes(b) for b in blobs])
+    ooff = np.array(cuts, dtype=np.uint64)
+    ctx.set_gunzip_options(decoder, True)
+    try:
+        with _Env(GAMS_CUDA_GZ_PIECES=1):
+            ref_out, _, ref_st = api.gunzip_batch(ctx, cat, goff, ooff, raise_on_error=False)
+        with _Env(GAMS_CUDA_GZ_PIECES=pieces):
+            out, off, st = api.gunzip_batch(ctx, cat, goff, ooff, raise_on_error=False)
+    finally:
+        ctx.set_gunzip_options(0, True)
+    assert st.tolist() == [0, 0, 0, 0, 0, 7, 0] and ref_st.tolist() == st.tolist()
+    assert np.array_equal(out, ref_out)
+    for i, p in enumerate(plain):
+        assert out[int(off[i]):int(off[i + 1])].tobytes() == p, f"blob {i}"
+
+
 # --------------------------------------------------------------- chained feed: seq:{ctg} gzip blobs -> gunzip -> GC-wave
 @pytest.mark.parametrize("infl", [1.0, 0.5])
 def test_wave_gz_batch_equals_wave_batch(ctx, orc, infl):
