@@ -728,7 +728,7 @@ struct ZwState {
 // Window i (>= lag + 1): decision, then the slide to the stats window of i + 1.  HAVE_D1: while the process is clean the decision is
 // d1 (the influence-1 decision), otherwise (and always without HAVE_D1) the certificate, and where that is inconclusive the
 // reference's own sums in its order over the ring (oldest value first).  ring: this thread's column (stride NT), RP = lag + 1
-// slots; `dold`: the value in slot st.h, which leaves (the caller may have loaded it long before: a slot is written only
+// slots; `old` / `dold`: the value in slot st.h, which leaves (the caller may have loaded it long before: a slot is written only
 // by the step that retires it).  One basic block but for the rare replay, and nothing of the next window's certificate waits
 // for this window's decision except through S1 / S2 two windows on: consecutive steps overlap.
 // f32 -> f64 by integer operations (the conversion unit takes 3 such conversions per window and is the slowest pipe of the walk):
@@ -743,7 +743,7 @@ __device__ __forceinline__ double zw_f2d(float f, bool &redo) {
 // FAST: an inconclusive certificate only raises `redo` (the caller rolls the block back and walks it again with FAST = false): the
 // step is one basic block, and eight of them in a row leave the compiler free to run the certificates side by side.
 template <int NT, bool HAVE_D1, bool FAST = false>
-__device__ __forceinline__ int zw_step(float *ring, int RP, ZwState &st, int i, int L, float xi, double dxi, double dold, int d1,
+__device__ __forceinline__ int zw_step(float *ring, int RP, ZwState &st, int i, int L, float xi, double dxi, float old, double dold, int d1,
                                        const ZwConst &zc, float flag, float flagm1, float threshold, float influence, float one_minus,
                                        bool *redo = nullptr) {
     const double D = fma(zc.dn, dxi, -st.S1);
@@ -778,6 +778,7 @@ __device__ __forceinline__ int zw_step(float *ring, int RP, ZwState &st, int i, 
     st.prev = fi;
     st.dprev = dec ? dblend : dxi;
     st.last_sig = dec ? i : st.last_sig;
+    (void)old;
     return dec;
 }
 // the same with the leaving value loaded here
@@ -785,7 +786,7 @@ template <int NT, bool HAVE_D1>
 __device__ __forceinline__ int zw_step1(float *ring, int RP, ZwState &st, int i, int L, float xi, int d1, const ZwConst &zc, float flag,
                                         float flagm1, float threshold, float influence, float one_minus) {
     const float old = ring[st.h * NT];
-    return zw_step<NT, HAVE_D1>(ring, RP, st, i, L, xi, (double)xi, (double)old, d1, zc, flag, flagm1, threshold, influence, one_minus);
+    return zw_step<NT, HAVE_D1>(ring, RP, st, i, L, xi, (double)xi, old, (double)old, d1, zc, flag, flagm1, threshold, influence, one_minus);
 }
 
 // series of segment g (seg_off: first segment of every series of the range)
@@ -892,7 +893,7 @@ zscore_tseg_walk_kernel(const float *__restrict__ x_all, const uint64_t *__restr
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int d1 = (int)(int8_t)(((j < 4) ? dcur.x : dcur.y) >> (8 * (j & 3)));
-            const uint32_t dec = (uint32_t)zw_step<NT, true, true>(ring, RP, st, i + j, L, xv[j], dxv[j], dov[j], d1, zc, flag, flagm1,
+            const uint32_t dec = (uint32_t)zw_step<NT, true, true>(ring, RP, st, i + j, L, xv[j], dxv[j], ov[j], dov[j], d1, zc, flag, flagm1,
                                                                    threshold, influence, one_minus, &redo) & 0xFFu;
             if (j < 4) o0 |= dec << (8 * j); else o1 |= dec << (8 * (j - 4));
         }
@@ -942,8 +943,8 @@ zscore_tseg_fix_kernel(const float *__restrict__ x_all, const uint64_t *__restri
     const int s = (int)(k * seg);
     ZwState st;
     const long long ls = seg_last[g - 1];
-    if (ls < (long long)s - 1 - L) return;  // the true process is clean at s: the segment is right as it stands
-    st.last_sig = (int)ls;
+    if (ls < (long long)s - 1 - L) return;
+    st.last_sig = (int)ls;    // the true process is clean at s: the segment is right as it stands
     const int64_t c = s_begin + lo;
     const uint64_t base = off[c];
     const int64_t n = (int64_t)(off[c + 1] - base);
